@@ -1,0 +1,179 @@
+/*
+ * rt_b200.h — C ABI of the B200-native render hot path (drop-in boundary).
+ *
+ * The reference (souhhcong/RaytracingGPU) has no FFI; its seams for this path
+ * are (i) the process CLI `./optimized <num_rays> <num_bounce>`
+ * (optimized.cu:774-785) and (ii) the kernel-launch signature
+ *   KernelLaunch(char* colors, int W, int H, int num_rays, int num_bounce,
+ *                TriangleIndices* indices, int indices_size,
+ *                Vector* vertices, int vertices_size, float* arr_bvh)
+ * (optimized.cu:670, 828-847) with the host steps around it
+ * (optimized.cu:791-826, 848-862). Every entry point below replaces one of
+ * those host steps; the citation on each says which.
+ *
+ * Conventions: plain pointers and sizes, no C++/torch types. Every function
+ * returns RT_OK (0) or a negative RT_ERR_* code and never calls exit()
+ * (the reference's gpuErrchk does, optimized.cu:24-30); rt_last_error()
+ * gives the message of the last failure on the calling thread. The caller
+ * owns host buffers, the library owns device buffers. Calls on one rt_scene
+ * are not thread-safe; different scenes may be driven from different threads.
+ * There is NO CPU fallback: without a CUDA device rt_scene_create fails with
+ * RT_ERR_CUDA.
+ */
+#ifndef RT_B200_H
+#define RT_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RT_ABI_VERSION 1
+
+enum {
+    RT_OK = 0,
+    RT_ERR_INVALID = -1,     /* bad argument */
+    RT_ERR_CUDA = -2,        /* CUDA runtime error or no device */
+    RT_ERR_NOMEM = -3,
+    RT_ERR_IO = -4,          /* file could not be opened / written */
+    RT_ERR_STATE = -5,       /* call order violated (e.g. render before scene upload) */
+    RT_ERR_UNSUPPORTED = -6  /* parameter combination not implemented */
+};
+
+/* ---- scene description (reference: Sphere optimized.cu:117-136, Geometry :103-115) ---- */
+
+/* One analytic sphere. `id` is the object's index in Scene::objects
+ * (optimized.cu:687-725 / cpu_launcher.cpp:540-543): intersect_all scans
+ * objects in ascending id and the lowest id wins exact-t ties (:549). */
+typedef struct rt_sphere {
+    float C[3];
+    float R;
+    float albedo[3];
+    int32_t mirror;          /* Geometry::mirror */
+    float n_in;              /* Geometry::in_refraction_index  */
+    float n_out;             /* Geometry::out_refraction_index */
+    int32_t id;
+} rt_sphere;
+
+/* Words per record of the reference interchange formats. */
+#define RT_TRI_RECORD_WORDS 10  /* TriangleIndices: vtxi,vtxj,vtxk,uvi,uvj,uvk,ni,nj,nk,group (optimized.cu:140-147) */
+#define RT_BVH_NODE_FLOATS 10   /* left,right,mn.xyz,mx.xyz,tri_start,tri_end (optimized.cu:512-534, array_bvh.cu:733-759) */
+
+/* Per-program knobs of the reference. */
+typedef struct rt_params {
+    int32_t W, H;            /* optimized.cu:786-787 (hard-coded 512 there) */
+    int32_t num_rays;        /* argv[1], samples per pixel (optimized.cu:785) */
+    int32_t num_bounce;      /* argv[2] */
+    float cam[3];            /* camera centre C, optimized.cu:747 */
+    float z;                 /* -W/(2 tan(alpha/2)), computed on the host once (optimized.cu:749): rt_camera_z */
+    float eps_surface;       /* P +- eps*N offset: 1e-4 optimized.cu:575, 1e-3 cpu_launcher.cpp:575 */
+    float eps_tri;           /* triangle accept t > eps_tri: 0 optimized.cu:275, 1e-4 cpu_launcher.cpp:301 */
+    int32_t push_order;      /* 0: push L then R (R popped first; cpu_launcher.cpp:291-292, array_bvh.cu:282-283)
+                                1: push R then L (L popped first; optimized.cu:265-266). Only decides exact-t ties. */
+    int32_t extra_segment;   /* 1: num_bounce+1 path segments (recursive getColor, cpu_launcher.cpp:567,710); 0: num_bounce (optimized.cu:566) */
+    float aa_sigma;          /* Box-Muller jitter sigma: 0 cpu_launcher.cpp:704, 0.2 optimized.cu:753. Only 0 is implemented (deterministic mode). */
+    int32_t indirect;        /* 1: cosine-weighted random bounce (optimized.cu:631-649). Only 0 is implemented. */
+    int32_t gamma_mode;      /* 0: trunc(min(pow((double)c, 1./2.2), 255.)) cpu_launcher.cpp:714-716
+                                1: trunc(min(powf(c, (float)(1./2.2)), 255.)) optimized.cu:765-767 */
+    int32_t row_begin;       /* sharding: this call renders image rows row_begin + k*row_step, k in [0,row_count) */
+    int32_t row_step;        /* 1 for a contiguous band, nranks for row-interleave */
+    int32_t row_count;       /* 0 means "all rows from row_begin with row_step" */
+    int32_t reserved;
+} rt_params;
+
+typedef struct rt_stats {
+    double kernel_ms;        /* CUDA-event time of the render kernels of this call */
+    uint64_t rays;           /* intersect_all calls (primary + bounce + shadow), counted on the device */
+    uint64_t node_visits;    /* inner BVH nodes popped (two box tests each); 0 unless RT_RENDER_COUNT_WORK */
+    uint64_t tri_tests;      /* Moller-Trumbore evaluations; 0 unless RT_RENDER_COUNT_WORK */
+    int32_t launches;        /* kernels launched by this call */
+    int32_t max_stack;       /* deepest traversal stack seen; 0 unless RT_RENDER_COUNT_WORK */
+} rt_stats;
+
+/* rt_render flags */
+#define RT_RENDER_COUNT_WORK 1u   /* fill node_visits / tri_tests / max_stack (slower instrumented kernel) */
+#define RT_RENDER_NO_SYNC    2u   /* enqueue only; kernel_ms and rays are not filled; call rt_scene_sync later */
+
+typedef struct rt_mesh rt_mesh;     /* host-side TriangleMeshHost replacement */
+typedef struct rt_scene rt_scene;   /* device-resident Scene replacement */
+
+/* ---- errors / device ---- */
+const char* rt_last_error(void);
+int rt_abi_version(void);
+int rt_device_count(int* count);                    /* RT_ERR_CUDA when no driver/device */
+
+/* ---- host mesh surface (TriangleMeshHost, optimized.cu:293-535) ---- */
+int rt_mesh_create(rt_mesh** out);
+void rt_mesh_destroy(rt_mesh* m);
+/* readOBJ (optimized.cu:303-454): sscanf cascade, v*0.8+(0,-10,0) for 3-field vertices.
+ * Unlike the reference (prints and continues, :310-313) a missing file is RT_ERR_IO. */
+int rt_mesh_read_obj(rt_mesh* m, const char* path);
+/* Replace the mesh by raw arrays: vertices nv*3 floats, triangles nt*3 vertex indices. */
+int rt_mesh_set_triangles(rt_mesh* m, const float* vertices, int32_t nv, const int32_t* vtx_indices, int32_t nt);
+/* rescale (optimized.cu:297-301): v = v*scale + offset, unfused float. */
+int rt_mesh_rescale(rt_mesh* m, float scale, const float offset[3]);
+/* Merge `copies` transformed instances of the current mesh into one mesh (config 5 of BASELINE.json:
+ * the reference has no instancing, so instances are baked). Instance c is v*scale[c] + offset[c]. */
+int rt_mesh_instance(rt_mesh* m, int32_t copies, const float* scales, const float* offsets /* copies*3 */);
+/* compute_bbox + buildBVH + bvhTreeToArray (optimized.cu:466-534, called at :809-813):
+ * reorders the triangle records in place and produces the 10-float array BVH. */
+int rt_mesh_build_bvh(rt_mesh* m);
+int rt_mesh_counts(const rt_mesh* m, int32_t* nv, int32_t* nt, int32_t* n_nodes);
+const float* rt_mesh_vertices(const rt_mesh* m);          /* nv*3 */
+const int32_t* rt_mesh_tri_records(const rt_mesh* m);     /* nt*RT_TRI_RECORD_WORDS, post-build order */
+const float* rt_mesh_arr_bvh(const rt_mesh* m);           /* n_nodes*RT_BVH_NODE_FLOATS, NULL before build */
+/* BVH shape facts used by tests: leaves, max depth, largest leaf. */
+int rt_mesh_bvh_info(const rt_mesh* m, int32_t* n_leaves, int32_t* max_depth, int32_t* max_leaf);
+
+/* ---- launcher helpers ---- */
+/* z = -W / (2 * tanf(alpha/2)) in float, as optimized.cu:748-749 / cpu_launcher.cpp:666,694 evaluate it on the host. */
+float rt_camera_z(int32_t W, float alpha);
+/* Fill `p` with the knobs of one reference program: "cpu" (cpu_launcher.cpp), "optimized" (optimized.cu),
+ * "array_bvh" (array_bvh.cu); deterministic mode (aa_sigma=0, indirect=0); camera (0,0,55), alpha=pi/3. */
+int rt_params_profile(rt_params* p, const char* profile, int32_t W, int32_t H, int32_t num_rays, int32_t num_bounce);
+/* The six wall spheres with the ids of the given profile and the id the mesh takes
+ * (cpu: walls 0-5, mesh 6, cpu_launcher.cpp:673-685; optimized: wall 0, mesh 1, walls 2-6, optimized.cu:684-726). */
+int rt_default_walls(const char* profile, rt_sphere walls[6], int32_t* mesh_id);
+/* PNG output, the role of stbi_write_png at optimized.cu:862. rgb is H*W*3, top row first. */
+int rt_write_png(const char* path, int32_t W, int32_t H, const uint8_t* rgb);
+/* One step of the reference's (never launched) MoveLightSource, realtime_render.cu:1072-1090, evaluated on the host in float. */
+void rt_move_light(float L[3], float angular_speed, float dt);
+
+/* ---- device scene (Scene + the cudaMalloc/cudaMemcpy block, optimized.cu:791-826) ---- */
+int rt_scene_create(rt_scene** out, int device);
+void rt_scene_destroy(rt_scene* s);
+/* Use an existing CUDA stream (a cudaStream_t cast to void*) instead of the scene's own. */
+int rt_scene_set_stream(rt_scene* s, void* cuda_stream);
+int rt_scene_set_spheres(rt_scene* s, const rt_sphere* spheres, int32_t n);
+/* Upload the mesh in the reference interchange formats (what optimized.cu:814-826 copies) and repack it on
+ * the device into the traversal layout. nt == 0 removes the mesh. */
+int rt_scene_set_mesh(rt_scene* s, const float* vertices, int32_t nv,
+                      const int32_t* tri_records, int32_t nt,
+                      const float* arr_bvh, int32_t n_nodes,
+                      const float albedo[3], int32_t mirror, float n_in, float n_out, int32_t id);
+/* Scene::L and Scene::intensity (optimized.cu:681-683). */
+int rt_scene_set_light(rt_scene* s, const float L[3], float intensity);
+/* Packed device scene as one contiguous blob, for a broadcast to other ranks (multi-GPU: the scene is built on
+ * rank 0 only). export gives a DEVICE pointer valid until the scene changes; import adopts bytes from a
+ * device buffer of that size (device-to-device copy). */
+int rt_scene_blob_size(rt_scene* s, size_t* bytes);
+int rt_scene_blob_export(rt_scene* s, void** device_ptr, size_t* bytes);
+int rt_scene_blob_import(rt_scene* s, const void* device_ptr, size_t bytes);
+
+/* The render call: replaces KernelLaunch<<<>>> + cudaDeviceSynchronize + cudaMemcpy D2H (optimized.cu:828-856).
+ * rgb_out: rows*W*3 bytes, interleaved RGB, top row first, rows = rows rendered by this call. Each output
+ * pointer may be a host pointer (copied back inside the call) or a device pointer on the scene's device
+ * (written in place), or NULL (hit buffers only) to skip it.
+ * hit_obj / hit_tri / hit_t: first-segment hit of sample 0 per pixel: object id (-1 = miss), triangle index in
+ * post-BVH-build order (-1 unless the mesh was hit), t. shadow: 1 shadowed, 0 lit, 2 no diffuse hit. */
+int rt_render(rt_scene* s, const rt_params* p, uint32_t flags,
+              uint8_t* rgb_out, int32_t* hit_obj, int32_t* hit_tri, float* hit_t, uint8_t* shadow,
+              rt_stats* stats);
+int rt_scene_sync(rt_scene* s, rt_stats* stats);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RT_B200_H */
