@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""bench.py — Mrays/s and ms/frame of the render hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU path on the host cores
+
+Workload (N = 1): BASELINE.json configs[1] — cadnav cat TriangleMesh with the array BVH + six wall spheres,
+1920x1080, 1 sample/pixel, primary + shadow rays (4,147,200 rays/frame), optimized.cu knobs. A "step" is one
+frame. For N > 1 the path shards by frame (BASELINE.json configs[3] style): every rank renders its own frames
+of a light-orbit animation of the same scene, no data-path collective ("scaling": "weak").
+
+`value` times the render kernels with the scene resident in HBM (CUDA events on the launching stream, L2
+flushed between steps). `e2e` goes through the C ABI with HOST buffers: every step re-uploads the mesh in the
+reference interchange formats (H2D), renders, and copies the 8-bit frame back to pinned host memory (D2H).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+CAT_REL = os.path.join("cadnav.com_model", "Models_F0202A090", "cat.obj")
+W, H = 1920, 1080
+METRIC = "Mrays/s"
+
+
+def find_cat():
+    for base in (os.environ.get("RT_REFERENCE_DIR", "/root/reference"), os.path.join(ROOT, "oracle", "_ref")):
+        p = os.path.join(base, CAT_REL)
+        if os.path.exists(p):
+            return p
+    return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def build_scene_host(rt):
+    """Host side of the launcher (optimized.cu:801-813): load, rescale, build the BVH — with the product's host code."""
+    cat = find_cat()
+    if cat:
+        mesh = rt.Mesh.read_obj(cat).rescale(0.6, (0.0, -4.0, 0.0)).build_bvh()
+        name = "cadnav cat (3954 tris, 2019 BVH nodes)"
+    else:  # the asset is not redistributable; without it a synthetic mesh of similar size keeps the bench runnable
+        sys.path.insert(0, ROOT)
+        from oracle import scenes
+        v, t = scenes.torus(64, 31)
+        mesh = rt.Mesh.from_arrays(v, t).build_bvh()
+        name = "synthetic torus (cat.obj unavailable)"
+    walls, mesh_id = rt.default_walls("optimized")
+    return mesh, walls, mesh_id, name
+
+
+def run_ours(args):
+    import torch
+    import raytracinggpu_b200 as rt
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if rt.device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device; raytracinggpu_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    mesh, walls, mesh_id, mesh_name = build_scene_host(rt)
+    verts, recs, bvh = mesh.vertices, mesh.tri_records, mesh.arr_bvh
+    sc = rt.Scene(local)
+    stream = torch.cuda.Stream()
+    sc.set_stream(stream.cuda_stream)
+    sc.set_spheres(walls)
+    sc.set_mesh(verts, recs, bvh, id=mesh_id)
+    p = rt.params_profile("optimized", W, H, 1, 1)
+
+    # frame-parallel for N > 1: rank r renders frames r, r+N, ... of a one-revolution light orbit
+    n_frames = (args.warmup + args.steps) * world
+    omega = 2 * np.pi / (240 * 0.02)
+    lights = rt.sharding.light_positions((-10.0, 20.0, 40.0), n_frames, omega, 0.02, rt.move_light) if world > 1 else [(-10.0, 20.0, 40.0)] * n_frames
+
+    rgb = torch.empty((H, W, 3), dtype=torch.uint8, device="cuda")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+
+    def one_step(i, timed_idx=None):
+        sc.set_light(lights[i * world + rank], 3e10)
+        with torch.cuda.stream(stream):
+            flush.zero_()  # L2 flush, outside the event pair
+            if timed_idx is not None:
+                ev[timed_idx][0].record(stream)
+            sc.render_into(p, rgb=rgb, flags=rt.RT_RENDER_NO_SYNC)
+            if timed_idx is not None:
+                ev[timed_idx][1].record(stream)
+
+    for i in range(args.warmup):
+        one_step(i)
+    stats0 = sc.sync()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        one_step(args.warmup + i, i)
+    st = sc.sync()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    wall_s = time.perf_counter() - t0
+    clocks = sampler.stop() if sampler else None
+    rays_per_frame = int(st.rays)
+    launches_per_step = int(st.launches)
+    ms_list = [a.elapsed_time(b) for a, b in ev]
+    ms_sum = float(sum(ms_list))
+    if world > 1:
+        t = torch.tensor([ms_sum], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_sum = float(t.item())
+        r = torch.tensor([rays_per_frame * args.steps], device="cuda", dtype=torch.int64)
+        dist.all_reduce(r)
+        total_rays = int(r.item())
+    else:
+        total_rays = rays_per_frame * args.steps
+    ms_per_step = ms_sum / args.steps
+    value = total_rays / (ms_sum * 1e-3) / 1e6
+
+    # ---- e2e through the C ABI with host buffers --------------------------------------------------------
+    host_rgb = torch.empty((H, W, 3), dtype=torch.uint8).pin_memory()
+    e2e_steps = max(3, min(args.steps, 20))
+    for _ in range(2):
+        sc.set_mesh(verts, recs, bvh, id=mesh_id)
+        sc.render_into(p, rgb=host_rgb.numpy())
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        sc.set_light(lights[(args.warmup + i % args.steps) * world + rank], 3e10)
+        sc.set_mesh(verts, recs, bvh, id=mesh_id)          # H2D of the interchange arrays + device repack
+        e2e_st = sc.render_into(p, rgb=host_rgb.numpy())    # render + D2H of the frame, synchronous
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = rays_per_frame * e2e_steps * world / e2e_s / 1e6
+    h2d = int(verts.nbytes + recs.nbytes + bvh.nbytes)
+    d2h = int(H * W * 3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (render) ---------------------------------------------------------
+    work = sc.render(p, want=("rgb",), count_work=True)["stats"]  # instrumented pass, not timed
+    n_mesh_queries = rays_per_frame  # every ray tests the mesh root box once
+    alg_bytes = 32 * (n_mesh_queries + 2 * work["node_visits"]) + 48 * work["tri_tests"] + H * W * 3
+    alg_flop = 150 * rays_per_frame + 19 * (n_mesh_queries + 2 * work["node_visits"]) + 50 * work["tri_tests"]
+    kernel_ms = float(np.mean(ms_list))
+    peak, peak_src = measured_peaks()
+    achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                "traffic": None, "peak_source": peak_src,
+                "note": "scene (0.3 MB) is L1/L2-resident: compulsory HBM traffic is the 6.2 MB frame; see fp32 for the binding roof",
+                "algorithmic_bytes_per_launch": int(alg_bytes), "node_visits": int(work["node_visits"]), "tri_tests": int(work["tri_tests"]),
+                "fp32": {"achieved_tflops": round(alg_flop / (kernel_ms * 1e-3) / 1e12, 3), "peak_tflops": round(148 * 128 * 2 * 1.965e9 / 1e12, 1),
+                         "frac": round(alg_flop / (kernel_ms * 1e-3) / (148 * 128 * 2 * 1.965e9), 4)}}
+
+    # ---- CPU baseline: the reference's own classes on this box's host cores (bounded sample) ---------------
+    cpu_baseline = cpu_reference_sample(budget_s=12.0)
+
+    out = {"metric": METRIC, "value": round(value, 2), "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": round(ms_per_step, 5), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+           "data": "synthetic",
+           "config": {"workload": "BASELINE.json configs[1]: %s + 6 wall spheres, 1920x1080, 1 spp, primary+shadow rays, optimized.cu knobs" % mesh_name,
+                      "rays_per_frame": rays_per_frame, "frames_per_step_per_gpu": 1, "sharding": "frame-parallel (light-orbit animation)" if world > 1 else "single GPU",
+                      "l2": "256 MB memset between steps, outside the event pair", "timed_wall_s": round(wall_s, 4)},
+           "e2e": {"value": round(e2e_value, 2), "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": round(e2e_s / e2e_steps * 1e3, 4),
+                   "steps": e2e_steps},
+           "gpu_launches": launches_per_step * args.steps, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
+           "ms_per_frame": round(kernel_ms, 5)}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_reference_sample(budget_s=12.0, threads=0):
+    """Time the reference's CPU render loop (oracle/_ref/libref_cpu.so = cpu_launcher.cpp's classes, OpenMP
+    schedule(dynamic,1) over rows) on a bounded sample of the same workload; falls back to the oracle port."""
+    from oracle import profiles, pyoracle, scenes
+    cores = os.cpu_count() or 1
+    cat = find_cat()
+    rays = 2 * W * H
+    if cat and pyoracle.ref_cpu_available():
+        # scene_kind 1 = optimized.cu object order + mesh transform; num_bounce 0 in the recursive CPU code = one
+        # segment + its shadow ray = the GPU program's num_bounce 1
+        pyoracle.ref_cpu_render(cat, 1, 480, 270, 1, 0, threads, hits=False)  # warm-up
+        n, spent = 0, 0.0
+        while spent < budget_s and n < 30:
+            r = pyoracle.ref_cpu_render(cat, 1, W, H, 1, 0, threads, hits=False)
+            spent += r["seconds"]
+            n += 1
+        return {"value": round(rays * n / spent / 1e6, 3), "unit": "Mrays/s", "cores": cores if threads <= 0 else threads, "kind": "reference",
+                "sample": "%d full 1920x1080 frames (%.2f s) by cpu_launcher.cpp's classes, render loop only" % (n, spent), "ms_per_frame": round(spent / n * 1e3, 2)}
+    desc = scenes.cat_scene("optimized") or scenes.torus_scene("optimized")
+    p = profiles.params("optimized", W, H, 1, 1)
+    n, spent = 0, 0.0
+    while spent < budget_s and n < 30:
+        o = scenes.run_oracle(desc, p, threads=threads, want=("rgb",))
+        spent += o["work"]["seconds"]
+        n += 1
+    return {"value": round(o["work"]["rays"] * n / spent / 1e6, 3), "unit": "Mrays/s", "cores": o["work"]["threads"], "kind": "port",
+            "sample": "%d full 1920x1080 frames (%.2f s) by the oracle port" % (n, spent), "ms_per_frame": round(spent / n * 1e3, 2)}
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path on the host cores, same config."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import pyoracle
+    cat = find_cat()
+    cores = os.cpu_count() or 1
+    rays = 2 * W * H
+    use_ref = bool(cat and pyoracle.ref_cpu_available())
+    if use_ref:
+        def frame():
+            return pyoracle.ref_cpu_render(cat, 1, W, H, 1, 0, 0, hits=False)["seconds"]
+        kind = "reference"
+    else:
+        from oracle import profiles, scenes
+        desc = scenes.cat_scene("optimized") or scenes.torus_scene("optimized")
+        p = profiles.params("optimized", W, H, 1, 1)
+
+        def frame():
+            return scenes.run_oracle(desc, p, want=("rgb",))["work"]["seconds"]
+        kind = "port"
+    for _ in range(min(args.warmup, 3)):
+        frame()
+    t0 = time.perf_counter()
+    times = [frame() for _ in range(args.steps)]
+    wall = time.perf_counter() - t0
+    total = float(sum(times))
+    value = rays * args.steps / total / 1e6
+    out = {"impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": round(total / args.steps * 1e3, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+           "data": "synthetic",
+           "config": {"workload": "BASELINE.json configs[1]: cat + 6 wall spheres, 1920x1080, 1 spp, primary+shadow rays; each step = one full frame on the host CPU",
+                      "rays_per_frame": rays, "wall_s": round(wall, 3)},
+           "cpu_baseline": {"value": round(value, 3), "unit": "Mrays/s", "cores": cores, "kind": kind,
+                            "sample": "%d full 1920x1080 frames, render loop only (cpu_launcher.cpp:695-718), OpenMP over rows" % args.steps},
+           "e2e": {"value": round(value, 3), "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        if args.steps > 40:
+            args.steps = 40
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

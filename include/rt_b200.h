@@ -173,6 +173,12 @@ int rt_render(rt_scene* s, const rt_params* p, uint32_t flags,
               rt_stats* stats);
 int rt_scene_sync(rt_scene* s, rt_stats* stats);
 
+/* ---- diagnostics ---- */
+/* Device self-test: the reciprocal-based exact division used by the fast slab test against div.rn.f32 on
+ * blocks*256*per_thread pseudo-random operand pairs. out[0] = mismatches with one correction step,
+ * out[1] = with two, out[2] = pairs tested. */
+int rt_selftest_division(int device, uint64_t seed, int blocks, int per_thread, uint64_t out[3]);
+
 #ifdef __cplusplus
 }
 #endif

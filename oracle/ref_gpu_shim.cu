@@ -1,0 +1,81 @@
+/*
+ * ref_gpu_shim.cu — TEST/BENCH INFRASTRUCTURE ONLY (oracle/_ref/ref_optimized).
+ *
+ * Times the reference's OWN GPU kernel: optimized.cu is included unmodified from where it lies
+ * (-DREF_GPU_SOURCE), compiled with the reference's flags retargeted to sm_100a (Makefile:4), and its
+ * KernelLaunch is launched exactly as optimized.cu:828-847 does, with W and H as arguments (the reference
+ * hard-codes 512, :786-787) and CUDA events around the launch. This is the "beat this" baseline of
+ * BASELINE.md §3; it is never part of the product path.
+ *
+ *   ref_optimized <obj> <W> <H> <num_rays> <num_bounce> <reps> [out.raw]
+ * prints one JSON line with per-launch kernel times.
+ */
+#define main ref_optimized_main
+#include REF_GPU_SOURCE
+#undef main
+
+#include <algorithm>
+#include <string>
+
+int main(int argc, char** argv) {
+	if (argc < 7) {
+		fprintf(stderr, "usage: %s <obj> <W> <H> <num_rays> <num_bounce> <reps> [out.raw]\n", argv[0]);
+		return 2;
+	}
+	const char* path = argv[1];
+	const int W = atoi(argv[2]), H = atoi(argv[3]), num_rays = atoi(argv[4]), num_bounce = atoi(argv[5]), reps = atoi(argv[6]);
+	const int BLOCK_DIM = 128;
+	if ((H * W) % BLOCK_DIM) { fprintf(stderr, "H*W must be a multiple of 128 (optimized.cu:789 has no tail guard)\n"); return 2; }
+	const int GRID_DIM = H * W / BLOCK_DIM;
+	int image_size = H * W * 3;
+	char* d_colors;
+	gpuErrchk(cudaMalloc((void**)&d_colors, image_size));
+	gpuErrchk(cudaDeviceSetLimit(cudaLimitStackSize, 1 << 14));
+
+	TriangleMeshHost* mesh_ptr = new TriangleMeshHost();
+	mesh_ptr->readOBJ(path);
+	mesh_ptr->rescale(0.6f, Vector(0.f, -4.f, 0.f));
+	mesh_ptr->bvh.bb = mesh_ptr->compute_bbox(0, mesh_ptr->indices.size());
+	mesh_ptr->buildBVH(&(mesh_ptr->bvh), 0, mesh_ptr->indices.size());
+	float* arr_bvh = (float*)malloc(sizeof(float) * mesh_ptr->n_bvhs * 10);
+	size_t arr_size = 1;
+	mesh_ptr->bvhTreeToArray(&(mesh_ptr->bvh), arr_bvh, arr_size);
+	float* d_arr_bvh;
+	gpuErrchk(cudaMalloc(&d_arr_bvh, sizeof(float) * mesh_ptr->n_bvhs * 10));
+	gpuErrchk(cudaMemcpy(d_arr_bvh, arr_bvh, sizeof(float) * mesh_ptr->n_bvhs * 10, cudaMemcpyHostToDevice));
+	TriangleIndices* d_indices;
+	Vector* d_vertices;
+	gpuErrchk(cudaMalloc((void**)&d_indices, mesh_ptr->indices.size() * sizeof(TriangleIndices)));
+	gpuErrchk(cudaMemcpy(d_indices, &(mesh_ptr->indices[0]), mesh_ptr->indices.size() * sizeof(TriangleIndices), cudaMemcpyHostToDevice));
+	gpuErrchk(cudaMalloc((void**)&d_vertices, mesh_ptr->vertices.size() * sizeof(Vector)));
+	gpuErrchk(cudaMemcpy(d_vertices, &(mesh_ptr->vertices[0]), mesh_ptr->vertices.size() * sizeof(Vector), cudaMemcpyHostToDevice));
+
+	const size_t smem = sizeof(char) * BLOCK_DIM * 3 + sizeof(Geometry) * 10 + sizeof(TriangleMesh) + sizeof(curandState) * BLOCK_DIM + sizeof(Scene);
+	cudaEvent_t e0, e1;
+	cudaEventCreate(&e0);
+	cudaEventCreate(&e1);
+	std::vector<float> ms;
+	for (int r = 0; r < reps + 3; r++) {
+		cudaEventRecord(e0);
+		KernelLaunch<<<GRID_DIM, BLOCK_DIM, smem>>>(d_colors, W, H, num_rays, num_bounce, d_indices, mesh_ptr->indices.size(), d_vertices,
+		                                           mesh_ptr->vertices.size(), d_arr_bvh);
+		cudaEventRecord(e1);
+		gpuErrchk(cudaPeekAtLastError());
+		gpuErrchk(cudaDeviceSynchronize());
+		float t;
+		cudaEventElapsedTime(&t, e0, e1);
+		if (r >= 3) ms.push_back(t);
+	}
+	std::sort(ms.begin(), ms.end());
+	const float med = ms[ms.size() / 2];
+	printf("{\"impl\": \"reference optimized.cu KernelLaunch (sm_100a, --use_fast_math)\", \"W\": %d, \"H\": %d, \"num_rays\": %d, \"num_bounce\": %d, "
+	       "\"reps\": %d, \"kernel_ms_median\": %.5f, \"kernel_ms_min\": %.5f, \"kernel_ms_max\": %.5f}\n",
+	       W, H, num_rays, num_bounce, reps, med, ms.front(), ms.back());
+	if (argc > 7) {
+		std::vector<char> image(image_size);
+		gpuErrchk(cudaMemcpy(image.data(), d_colors, image_size, cudaMemcpyDeviceToHost));
+		FILE* f = fopen(argv[7], "wb");
+		if (f) { fwrite(image.data(), 1, image_size, f); fclose(f); }
+	}
+	return 0;
+}

@@ -1,0 +1,79 @@
+/*
+ * launcher_main.cpp — the CLI of the reference launchers: `rt_render <num_rays> <num_bounce>`
+ * (optimized.cu:774-785, cpu_launcher.cpp:654-659; consumed by benchmark.py:20), writing a PNG in the CWD
+ * and printing `Rendering time: <s> s` (optimized.cu:879-881). Extras beyond the reference:
+ *   --profile optimized|cpu|array_bvh   knob set + scene layout of that reference program (default optimized)
+ *   --width W --height H                (the reference hard-codes 512x512, optimized.cu:786-787)
+ *   --obj PATH                          default cadnav.com_model/Models_F0202A090/cat.obj relative to the CWD (:802)
+ *   --out FILE                          default image_optimized.png (:862) / image.png (cpu_launcher.cpp:719)
+ *   --device D   --frames F             render F frames (kernel time is reported per frame)
+ */
+#include "scene.hpp"
+
+#include <chrono>
+#include <cstdlib>
+#include <cstring>
+#include <iostream>
+#include <memory>
+
+int main(int argc, char** argv) {
+    std::vector<std::string> pos;
+    std::string profile = "optimized", obj = "cadnav.com_model/Models_F0202A090/cat.obj", out;
+    int W = 512, H = 512, device = 0, frames = 1;
+    for (int i = 1; i < argc; i++) {
+        std::string a = argv[i];
+        auto next = [&]() -> const char* { return (i + 1 < argc) ? argv[++i] : ""; };
+        if (a == "--profile") profile = next();
+        else if (a == "--width") W = atoi(next());
+        else if (a == "--height") H = atoi(next());
+        else if (a == "--obj") obj = next();
+        else if (a == "--out") out = next();
+        else if (a == "--device") device = atoi(next());
+        else if (a == "--frames") frames = atoi(next());
+        else pos.push_back(a);
+    }
+    if (pos.size() != 2) {
+        std::cout << "Invalid number of arguments!\nThe first argument is number of rays and the second argument is number of bounces.\n";
+        return 0;
+    }
+    auto start_time = std::chrono::system_clock::now();
+    const int num_rays = atoi(pos[0].c_str()), num_bounce = atoi(pos[1].c_str());
+    if (out.empty()) out = (profile == "cpu") ? "image.png" : "image_optimized.png";
+    try {
+        rt_params p;
+        rtb200::check(rt_params_profile(&p, profile.c_str(), W, H, num_rays, num_bounce));
+        rt_sphere walls[6];
+        int32_t mesh_id = 0;
+        rtb200::check(rt_default_walls(profile.c_str(), walls, &mesh_id));
+
+        rtb200::TriangleMeshHost mesh; /* cat */
+        mesh.readOBJ(obj.c_str());
+        if (profile == "optimized") mesh.rescale(0.6f, rtb200::Vector(0.f, -4.f, 0.f));       /* optimized.cu:804 */
+        else if (profile == "array_bvh") mesh.rescale(0.6f, rtb200::Vector(0.f, -10.f, 0.f)); /* array_bvh.cu:1033 */
+        mesh.buildBVH();
+
+        rtb200::Scene scene(device);
+        for (int k = 0, id = 0; k < 6; k++, id++) {
+            if (id == mesh_id) {
+                scene.addObject(mesh);
+                id++;
+            }
+            const rt_sphere& w = walls[k];
+            scene.addObject(rtb200::Sphere(rtb200::Vector(w.C[0], w.C[1], w.C[2]), w.R, rtb200::Vector(w.albedo[0], w.albedo[1], w.albedo[2])));
+        }
+        if (mesh_id >= 6) scene.addObject(mesh);
+
+        std::vector<uint8_t> image((size_t)W * H * 3);
+        rt_stats st{};
+        for (int f = 0; f < frames; f++) st = scene.render(p, image.data());
+        rtb200::check(rt_write_png(out.c_str(), W, H, image.data()));
+        auto end_time = std::chrono::system_clock::now();
+        std::chrono::duration<float> run_time = end_time - start_time;
+        std::cout << "Rendering time: " << run_time.count() << " s\n";
+        std::cerr << "kernel " << st.kernel_ms << " ms/frame, " << st.rays << " rays, " << (st.rays / (st.kernel_ms * 1e3)) << " Mrays/s\n";
+    } catch (const rtb200::Error& e) {
+        std::cerr << "rt_render: " << e.what() << "\n";
+        return 1;
+    }
+    return 0;
+}

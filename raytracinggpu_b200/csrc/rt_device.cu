@@ -1,0 +1,579 @@
+/*
+ * rt_device.cu — the device half of the C ABI (include/rt_b200.h): rt_scene_* and rt_render.
+ *
+ * Replaces the host steps of the reference launcher around KernelLaunch:
+ *   cudaMalloc / cudaMemcpy H2D of arr_bvh, indices, vertices     optimized.cu:791-826
+ *   per-block scene construction in shared memory                  optimized.cu:679-743 (here: one header, built once)
+ *   KernelLaunch<<<>>> + cudaDeviceSynchronize + cudaMemcpy D2H    optimized.cu:828-856
+ * There is no CPU path in this file: every entry point needs a CUDA device and fails with RT_ERR_CUDA otherwise.
+ */
+#include "host_common.h"
+#include "rt_kernels.cuh"
+#include "rt_layout.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#define CUDA_TRY(expr)                                                                                         \
+    do {                                                                                                       \
+        cudaError_t e__ = (expr);                                                                              \
+        if (e__ != cudaSuccess) return rtb::fail(RT_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+struct rt_scene {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+    SceneHeader header;         /* host copy, passed to the kernels by value */
+    unsigned char* blob = nullptr;
+    size_t blob_bytes = 0;
+    bool header_dirty = true;
+
+    float* gamma_tab = nullptr;              /* device, 2 x 256 */
+    unsigned long long* counters = nullptr;  /* device, 4 */
+    unsigned long long* h_counters = nullptr; /* pinned */
+
+    /* scratch outputs for host-pointer callers */
+    unsigned char* scratch[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    size_t scratch_bytes[5] = {0, 0, 0, 0, 0};
+
+    /* pending copy-back of a RT_RENDER_NO_SYNC call */
+    bool pending = false;
+    int pending_launches = 0;
+};
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) == cudaSuccess && cudaSetDevice(dev) == cudaSuccess) ok = true;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+/* The 8-bit transfer function of the reference, evaluated on the host with its own libm expressions. */
+int transfer(float c, int mode) {
+    if (mode == 1) return (int)std::min((double)powf(c, (float)(1. / 2.2)), 255.); /* optimized.cu:765 */
+    return (int)std::min(std::pow((double)c, 1. / 2.2), 255.);                     /* cpu_launcher.cpp:714 */
+}
+
+/* T[k] = smallest non-negative float c with transfer(c) >= k, by bisection over the (ordered) bit patterns. */
+void build_gamma_table(float* T, int mode) {
+    T[0] = 0.f;
+    for (int k = 1; k < 256; k++) {
+        uint32_t lo = 0, hi = 0x7f800000u; /* transfer(+0) = 0 < k <= transfer(+inf) = 255 */
+        while (hi - lo > 1) {
+            const uint32_t mid = lo + (hi - lo) / 2;
+            float c;
+            memcpy(&c, &mid, 4);
+            if (transfer(c, mode) >= k) hi = mid;
+            else lo = mid;
+        }
+        memcpy(&T[k], &hi, 4);
+    }
+}
+
+bool is_device_pointer(const void* p, int device) {
+    if (!p) return false;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged) && (at.type == cudaMemoryTypeManaged || at.device == device);
+}
+
+int ensure_scratch(rt_scene* s, int slot, size_t bytes) {
+    if (s->scratch_bytes[slot] >= bytes) return RT_OK;
+    if (s->scratch[slot]) cudaFree(s->scratch[slot]);
+    s->scratch[slot] = nullptr;
+    s->scratch_bytes[slot] = 0;
+    CUDA_TRY(cudaMalloc(&s->scratch[slot], bytes));
+    s->scratch_bytes[slot] = bytes;
+    return RT_OK;
+}
+
+int upload_header(rt_scene* s) {
+    if (!s->blob) {
+        /* spheres-only scene: the blob is just the header */
+        CUDA_TRY(cudaMalloc(&s->blob, RT_HEADER_BYTES));
+        s->blob_bytes = RT_HEADER_BYTES;
+        s->header.off_nodes = s->header.off_tris = s->header.off_nhat = RT_HEADER_BYTES;
+        s->header.total_bytes = RT_HEADER_BYTES;
+    }
+    CUDA_TRY(cudaMemcpyAsync(s->blob, &s->header, sizeof(SceneHeader), cudaMemcpyHostToDevice, s->stream));
+    s->header_dirty = false;
+    return RT_OK;
+}
+
+void reset_mesh_fields(SceneHeader& h) {
+    h.has_mesh = 0;
+    h.n_inner = 0;
+    h.n_tris = 0;
+    h.max_depth = 0;
+    h.root_a = 0;
+    h.root_b = 0;
+    for (int k = 0; k < 3; k++) {
+        h.root_mn[k] = 0.f;
+        h.root_mx[k] = 0.f;
+    }
+}
+
+} // namespace
+
+extern "C" {
+
+int rt_device_count(int* count) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (count) *count = (e == cudaSuccess) ? n : 0;
+    if (e != cudaSuccess) return rtb::fail(RT_ERR_CUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    return RT_OK;
+}
+
+int rt_scene_create(rt_scene** out, int device) {
+    if (!out) return rtb::fail(RT_ERR_INVALID, "rt_scene_create: out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return rtb::fail(RT_ERR_CUDA, "rt_scene_create: no CUDA device (%s); this library has no CPU fallback", e != cudaSuccess ? cudaGetErrorString(e) : "0 devices");
+    if (device < 0 || device >= n) return rtb::fail(RT_ERR_INVALID, "rt_scene_create: device %d out of range (0..%d)", device, n - 1);
+    DeviceGuard g(device);
+    if (!g.ok) return rtb::fail(RT_ERR_CUDA, "rt_scene_create: cudaSetDevice(%d) failed", device);
+    rt_scene* s = new (std::nothrow) rt_scene();
+    if (!s) return rtb::fail(RT_ERR_NOMEM, "rt_scene_create: out of memory");
+    s->device = device;
+    memset(&s->header, 0, sizeof s->header);
+    s->header.magic = RT_BLOB_MAGIC;
+    s->header.layout_version = 1;
+    s->header.mesh_id = -1;
+    s->header.L[0] = -10.f; /* Scene::L / intensity defaults, optimized.cu:681-683 */
+    s->header.L[1] = 20.f;
+    s->header.L[2] = 40.f;
+    s->header.intensity = 3e10f;
+    reset_mesh_fields(s->header);
+    std::vector<float> tab(512);
+    build_gamma_table(tab.data(), 0);
+    build_gamma_table(tab.data() + 256, 1);
+    cudaError_t err = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
+    s->own_stream = (err == cudaSuccess);
+    if (err == cudaSuccess) err = cudaEventCreate(&s->ev0);
+    if (err == cudaSuccess) err = cudaEventCreate(&s->ev1);
+    if (err == cudaSuccess) err = cudaMalloc(&s->gamma_tab, 512 * sizeof(float));
+    if (err == cudaSuccess) err = cudaMalloc(&s->counters, 4 * sizeof(unsigned long long));
+    if (err == cudaSuccess) err = cudaMallocHost(&s->h_counters, 4 * sizeof(unsigned long long));
+    if (err == cudaSuccess) err = cudaMemcpy(s->gamma_tab, tab.data(), 512 * sizeof(float), cudaMemcpyHostToDevice);
+    if (err != cudaSuccess) {
+        rtb::fail(RT_ERR_CUDA, "rt_scene_create: %s", cudaGetErrorString(err));
+        rt_scene_destroy(s);
+        return RT_ERR_CUDA;
+    }
+    *out = s;
+    return RT_OK;
+}
+
+void rt_scene_destroy(rt_scene* s) {
+    if (!s) return;
+    DeviceGuard g(s->device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    if (s->blob) cudaFree(s->blob);
+    if (s->gamma_tab) cudaFree(s->gamma_tab);
+    if (s->counters) cudaFree(s->counters);
+    if (s->h_counters) cudaFreeHost(s->h_counters);
+    for (int k = 0; k < 5; k++)
+        if (s->scratch[k]) cudaFree(s->scratch[k]);
+    if (s->ev0) cudaEventDestroy(s->ev0);
+    if (s->ev1) cudaEventDestroy(s->ev1);
+    if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+}
+
+int rt_scene_set_stream(rt_scene* s, void* cuda_stream) {
+    if (!s) return rtb::fail(RT_ERR_INVALID, "rt_scene_set_stream: NULL scene");
+    DeviceGuard g(s->device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
+    s->stream = (cudaStream_t)cuda_stream;
+    s->own_stream = false;
+    return RT_OK;
+}
+
+int rt_scene_set_spheres(rt_scene* s, const rt_sphere* spheres, int32_t n) {
+    if (!s || n < 0 || (n > 0 && !spheres)) return rtb::fail(RT_ERR_INVALID, "rt_scene_set_spheres: bad argument");
+    if (n > RT_MAX_SPHERES) return rtb::fail(RT_ERR_UNSUPPORTED, "rt_scene_set_spheres: %d spheres, at most %d (the reference holds 10 objects, optimized.cu:663)", n, RT_MAX_SPHERES);
+    std::vector<rt_sphere> v(spheres, spheres + n);
+    std::stable_sort(v.begin(), v.end(), [](const rt_sphere& a, const rt_sphere& b) { return a.id < b.id; });
+    for (int k = 0; k < n; k++) {
+        if (v[k].id < 0 || (k > 0 && v[k].id == v[k - 1].id)) return rtb::fail(RT_ERR_INVALID, "rt_scene_set_spheres: ids must be distinct and >= 0");
+        DevSphere& d = s->header.spheres[k];
+        d.cx = v[k].C[0];
+        d.cy = v[k].C[1];
+        d.cz = v[k].C[2];
+        d.R = v[k].R;
+        d.RR = v[k].R * v[k].R;
+        d.ax = v[k].albedo[0];
+        d.ay = v[k].albedo[1];
+        d.az = v[k].albedo[2];
+        d.mirror = v[k].mirror ? 1 : 0;
+        d.n_in = v[k].n_in;
+        d.n_out = v[k].n_out;
+        d.id = v[k].id;
+    }
+    s->header.n_spheres = n;
+    s->header_dirty = true;
+    return RT_OK;
+}
+
+int rt_scene_set_light(rt_scene* s, const float L[3], float intensity) {
+    if (!s || !L) return rtb::fail(RT_ERR_INVALID, "rt_scene_set_light: bad argument");
+    s->header.L[0] = L[0];
+    s->header.L[1] = L[1];
+    s->header.L[2] = L[2];
+    s->header.intensity = intensity;
+    s->header_dirty = true;
+    return RT_OK;
+}
+
+int rt_scene_set_mesh(rt_scene* s, const float* vertices, int32_t nv, const int32_t* tri_records, int32_t nt, const float* arr_bvh,
+                      int32_t n_nodes, const float albedo[3], int32_t mirror, float n_in, float n_out, int32_t id) {
+    if (!s) return rtb::fail(RT_ERR_INVALID, "rt_scene_set_mesh: NULL scene");
+    DeviceGuard g(s->device);
+    if (!g.ok) return rtb::fail(RT_ERR_CUDA, "rt_scene_set_mesh: cudaSetDevice failed");
+    SceneHeader& h = s->header;
+    if (nt == 0) {
+        CUDA_TRY(cudaStreamSynchronize(s->stream));
+        if (s->blob) cudaFree(s->blob);
+        s->blob = nullptr;
+        s->blob_bytes = 0;
+        reset_mesh_fields(h);
+        h.mesh_id = -1;
+        s->header_dirty = true;
+        return RT_OK;
+    }
+    if (nt < 0 || nv <= 0 || n_nodes <= 0 || !vertices || !tri_records || !arr_bvh || !albedo)
+        return rtb::fail(RT_ERR_INVALID, "rt_scene_set_mesh: bad argument");
+    if (id < 0) return rtb::fail(RT_ERR_INVALID, "rt_scene_set_mesh: id must be >= 0");
+    for (int64_t i = 0; i < nt; i++)
+        for (int k = 0; k < 3; k++) {
+            const int32_t v = tri_records[i * RT_TRI_RECORD_WORDS + k];
+            if (v < 0 || v >= nv) return rtb::fail(RT_ERR_INVALID, "rt_scene_set_mesh: triangle %lld references vertex %d (nv=%d)", (long long)i, v, nv);
+        }
+
+    /* ---- node relayout on the host: 10-float pre-order nodes -> 64-B two-child records ----------------- */
+    std::vector<int32_t> inner_index((size_t)n_nodes, -1);
+    int32_t n_inner = 0;
+    for (int32_t k = 0; k < n_nodes; k++) {
+        const float* a = arr_bvh + (size_t)k * RT_BVH_NODE_FLOATS;
+        const int32_t l = (int32_t)a[0], r = (int32_t)a[1];
+        if ((l == -1) != (r == -1)) return rtb::fail(RT_ERR_INVALID, "rt_scene_set_mesh: node %d has exactly one child", k);
+        if (l != -1) {
+            if (l <= k || r <= k || l >= n_nodes || r >= n_nodes) return rtb::fail(RT_ERR_INVALID, "rt_scene_set_mesh: node %d child index out of order/range", k);
+            inner_index[k] = n_inner++;
+        } else {
+            const int32_t ts = (int32_t)a[8], te = (int32_t)a[9];
+            if (ts < 0 || te < ts || te > nt) return rtb::fail(RT_ERR_INVALID, "rt_scene_set_mesh: leaf %d triangle range [%d,%d) invalid", k, ts, te);
+        }
+    }
+    /* children have larger indices than their parent (pre-order), so one forward pass gives depths */
+    std::vector<int32_t> depth((size_t)n_nodes, 0);
+    depth[0] = 1;
+    int32_t max_depth = 1;
+    for (int32_t k = 0; k < n_nodes; k++) {
+        const float* a = arr_bvh + (size_t)k * RT_BVH_NODE_FLOATS;
+        const int32_t l = (int32_t)a[0], r = (int32_t)a[1];
+        if (depth[k] == 0) return rtb::fail(RT_ERR_INVALID, "rt_scene_set_mesh: node %d is unreachable", k);
+        if (l != -1) {
+            if (depth[l] != 0 || depth[r] != 0 || l == r) return rtb::fail(RT_ERR_INVALID, "rt_scene_set_mesh: node %d shares a child", k);
+            depth[l] = depth[r] = depth[k] + 1;
+            max_depth = std::max(max_depth, depth[k] + 1);
+        }
+    }
+    if (max_depth > RT_STACK_CAP - 2)
+        return rtb::fail(RT_ERR_UNSUPPORTED, "rt_scene_set_mesh: BVH depth %d exceeds the traversal stack (%d)", max_depth, RT_STACK_CAP - 2);
+
+    auto child_ref = [&](int32_t node, int32_t& a_out, int32_t& b_out) {
+        const float* a = arr_bvh + (size_t)node * RT_BVH_NODE_FLOATS;
+        if ((int32_t)a[0] != -1) {
+            a_out = inner_index[node];
+            b_out = -1;
+        } else {
+            a_out = (int32_t)a[8];
+            b_out = (int32_t)a[9];
+        }
+    };
+    std::vector<float> packed((size_t)std::max(n_inner, 1) * 16);
+    for (int32_t k = 0; k < n_nodes; k++) {
+        if (inner_index[k] < 0) continue;
+        const float* a = arr_bvh + (size_t)k * RT_BVH_NODE_FLOATS;
+        const float* L = arr_bvh + (size_t)(int32_t)a[0] * RT_BVH_NODE_FLOATS;
+        const float* R = arr_bvh + (size_t)(int32_t)a[1] * RT_BVH_NODE_FLOATS;
+        float* o = &packed[(size_t)inner_index[k] * 16];
+        for (int c = 0; c < 6; c++) {
+            o[c] = L[2 + c];
+            o[6 + c] = R[2 + c];
+        }
+        int32_t refs[4];
+        child_ref((int32_t)a[0], refs[0], refs[1]);
+        child_ref((int32_t)a[1], refs[2], refs[3]);
+        memcpy(o + 12, refs, sizeof refs);
+    }
+
+    /* ---- blob ------------------------------------------------------------------------------------------ */
+    const size_t off_nodes = RT_HEADER_BYTES;
+    const size_t off_tris = off_nodes + (size_t)n_inner * RT_NODE_BYTES;
+    const size_t off_nhat = off_tris + (size_t)nt * RT_TRI_BYTES;
+    const size_t total = off_nhat + (size_t)nt * RT_NHAT_BYTES;
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    if (s->blob_bytes < total || s->blob_bytes > 2 * total + (1u << 20)) {
+        if (s->blob) cudaFree(s->blob);
+        s->blob = nullptr;
+        s->blob_bytes = 0;
+        CUDA_TRY(cudaMalloc(&s->blob, total));
+        s->blob_bytes = total;
+    }
+    /* staging of the interchange arrays (freed after the repack) */
+    float* d_vertices = nullptr;
+    int32_t* d_recs = nullptr;
+    const size_t vbytes = (size_t)nv * 3 * sizeof(float), rbytes = (size_t)nt * RT_TRI_RECORD_WORDS * sizeof(int32_t);
+    CUDA_TRY(cudaMalloc(&d_vertices, vbytes));
+    cudaError_t err = cudaMalloc(&d_recs, rbytes);
+    if (err == cudaSuccess) err = cudaMemcpyAsync(d_vertices, vertices, vbytes, cudaMemcpyHostToDevice, s->stream);
+    if (err == cudaSuccess) err = cudaMemcpyAsync(d_recs, tri_records, rbytes, cudaMemcpyHostToDevice, s->stream);
+    if (err == cudaSuccess && n_inner > 0)
+        err = cudaMemcpyAsync(s->blob + off_nodes, packed.data(), (size_t)n_inner * RT_NODE_BYTES, cudaMemcpyHostToDevice, s->stream);
+    if (err == cudaSuccess) {
+        const int threads = 256, blocks = (nt + threads - 1) / threads;
+        rtk::repack_triangles<<<blocks, threads, 0, s->stream>>>(d_vertices, d_recs, nt, reinterpret_cast<float4*>(s->blob + off_tris),
+                                                               reinterpret_cast<float4*>(s->blob + off_nhat));
+        err = cudaGetLastError();
+    }
+    if (err == cudaSuccess) err = cudaStreamSynchronize(s->stream);
+    cudaFree(d_vertices);
+    if (d_recs) cudaFree(d_recs);
+    if (err != cudaSuccess) return rtb::fail(RT_ERR_CUDA, "rt_scene_set_mesh: %s", cudaGetErrorString(err));
+
+    h.has_mesh = 1;
+    h.n_inner = n_inner;
+    h.n_tris = nt;
+    h.max_depth = max_depth;
+    h.mesh_id = id;
+    h.mesh_mirror = mirror ? 1 : 0;
+    h.mesh_n_in = n_in;
+    h.mesh_n_out = n_out;
+    memcpy(h.mesh_albedo, albedo, sizeof h.mesh_albedo);
+    for (int c = 0; c < 3; c++) {
+        h.root_mn[c] = arr_bvh[2 + c];
+        h.root_mx[c] = arr_bvh[5 + c];
+    }
+    child_ref(0, h.root_a, h.root_b);
+    h.off_nodes = off_nodes;
+    h.off_tris = off_tris;
+    h.off_nhat = off_nhat;
+    h.total_bytes = total;
+    s->header_dirty = true;
+    return RT_OK;
+}
+
+int rt_scene_blob_size(rt_scene* s, size_t* bytes) {
+    if (!s || !bytes) return rtb::fail(RT_ERR_INVALID, "rt_scene_blob_size: bad argument");
+    *bytes = s->blob ? (size_t)s->header.total_bytes : (size_t)RT_HEADER_BYTES;
+    return RT_OK;
+}
+
+int rt_scene_blob_export(rt_scene* s, void** device_ptr, size_t* bytes) {
+    if (!s || !device_ptr || !bytes) return rtb::fail(RT_ERR_INVALID, "rt_scene_blob_export: bad argument");
+    DeviceGuard g(s->device);
+    if (s->header_dirty || !s->blob) {
+        int rc = upload_header(s);
+        if (rc != RT_OK) return rc;
+    }
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    *device_ptr = s->blob;
+    *bytes = (size_t)s->header.total_bytes;
+    return RT_OK;
+}
+
+int rt_scene_blob_import(rt_scene* s, const void* device_ptr, size_t bytes) {
+    if (!s || !device_ptr || bytes < RT_HEADER_BYTES) return rtb::fail(RT_ERR_INVALID, "rt_scene_blob_import: bad argument");
+    DeviceGuard g(s->device);
+    SceneHeader h;
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    CUDA_TRY(cudaMemcpy(&h, device_ptr, sizeof h, cudaMemcpyDeviceToHost));
+    if (h.magic != RT_BLOB_MAGIC || h.layout_version != 1 || h.total_bytes != bytes)
+        return rtb::fail(RT_ERR_INVALID, "rt_scene_blob_import: not a scene blob (magic %08x, %llu bytes declared, %llu given)", h.magic,
+                         (unsigned long long)h.total_bytes, (unsigned long long)bytes);
+    if (h.n_spheres < 0 || h.n_spheres > RT_MAX_SPHERES || h.off_nhat + (uint64_t)h.n_tris * RT_NHAT_BYTES > bytes)
+        return rtb::fail(RT_ERR_INVALID, "rt_scene_blob_import: inconsistent header");
+    if ((const unsigned char*)device_ptr != s->blob) {
+        if (s->blob_bytes < bytes) {
+            if (s->blob) cudaFree(s->blob);
+            s->blob = nullptr;
+            s->blob_bytes = 0;
+            CUDA_TRY(cudaMalloc(&s->blob, bytes));
+            s->blob_bytes = bytes;
+        }
+        CUDA_TRY(cudaMemcpyAsync(s->blob, device_ptr, bytes, cudaMemcpyDeviceToDevice, s->stream));
+        CUDA_TRY(cudaStreamSynchronize(s->stream));
+    }
+    s->header = h;
+    s->header_dirty = false;
+    return RT_OK;
+}
+
+int rt_scene_sync(rt_scene* s, rt_stats* stats) {
+    if (!s) return rtb::fail(RT_ERR_INVALID, "rt_scene_sync: NULL scene");
+    DeviceGuard g(s->device);
+    if (s->pending) CUDA_TRY(cudaMemcpyAsync(s->h_counters, s->counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    if (stats) {
+        memset(stats, 0, sizeof *stats);
+        if (s->pending) {
+            float ms = 0.f;
+            CUDA_TRY(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+            stats->kernel_ms = ms;
+            stats->rays = s->h_counters[0];
+            stats->node_visits = s->h_counters[1];
+            stats->tri_tests = s->h_counters[2];
+            stats->max_stack = (int32_t)s->h_counters[3];
+            stats->launches = s->pending_launches;
+        }
+    }
+    s->pending = false;
+    return RT_OK;
+}
+
+int rt_render(rt_scene* s, const rt_params* p, uint32_t flags, uint8_t* rgb_out, int32_t* hit_obj, int32_t* hit_tri, float* hit_t,
+              uint8_t* shadow, rt_stats* stats) {
+    if (!s || !p) return rtb::fail(RT_ERR_INVALID, "rt_render: NULL scene or params");
+    if (p->W <= 0 || p->H <= 0 || p->num_rays < 1 || p->num_bounce < 0) return rtb::fail(RT_ERR_INVALID, "rt_render: bad W/H/num_rays/num_bounce");
+    if (p->aa_sigma != 0.f || p->indirect != 0)
+        return rtb::fail(RT_ERR_UNSUPPORTED, "rt_render: only the deterministic mode (aa_sigma = 0, indirect = 0) is implemented");
+    if (p->gamma_mode != 0 && p->gamma_mode != 1) return rtb::fail(RT_ERR_INVALID, "rt_render: gamma_mode must be 0 or 1");
+    if (p->push_order != 0 && p->push_order != 1) return rtb::fail(RT_ERR_INVALID, "rt_render: push_order must be 0 or 1");
+    const int step = p->row_step > 0 ? p->row_step : 1;
+    if (p->row_begin < 0 || p->row_begin >= p->H) return rtb::fail(RT_ERR_INVALID, "rt_render: row_begin out of range");
+    const int max_rows = (p->H - p->row_begin + step - 1) / step;
+    const int rows = p->row_count > 0 ? p->row_count : max_rows;
+    if (rows > max_rows) return rtb::fail(RT_ERR_INVALID, "rt_render: row_count %d exceeds the %d rows available", rows, max_rows);
+    const SceneHeader& h = s->header;
+    if (h.n_spheres == 0 && !h.has_mesh) return rtb::fail(RT_ERR_STATE, "rt_render: empty scene (set spheres and/or a mesh first)");
+    /* object ids must be exactly 0..n-1, as Scene::objects indices are (optimized.cu:687-725) */
+    {
+        const int n_obj = h.n_spheres + (h.has_mesh ? 1 : 0);
+        unsigned seen = 0;
+        bool ok = true;
+        for (int k = 0; k < h.n_spheres; k++) {
+            const int id = h.spheres[k].id;
+            if (id >= n_obj || (seen >> id) & 1u) ok = false;
+            else seen |= 1u << id;
+        }
+        if (h.has_mesh && (h.mesh_id >= n_obj || ((seen >> h.mesh_id) & 1u))) ok = false;
+        if (!ok) return rtb::fail(RT_ERR_INVALID, "rt_render: object ids must be a permutation of 0..%d", n_obj - 1);
+    }
+    DeviceGuard g(s->device);
+    if (!g.ok) return rtb::fail(RT_ERR_CUDA, "rt_render: cudaSetDevice failed");
+    /* a still-pending RT_RENDER_NO_SYNC call needs no wait: counters, scratch buffers and events are reused in
+     * stream order, and the stats of the older call are simply superseded */
+    if (s->header_dirty || !s->blob) {
+        int rc = upload_header(s);
+        if (rc != RT_OK) return rc;
+    }
+
+    const size_t npx = (size_t)rows * p->W;
+    void* user[5] = {rgb_out, hit_obj, hit_tri, hit_t, shadow};
+    const size_t bytes[5] = {npx * 3, npx * 4, npx * 4, npx * 4, npx};
+    void* dev[5];
+    bool copy_back[5];
+    for (int k = 0; k < 5; k++) {
+        dev[k] = nullptr;
+        copy_back[k] = false;
+        if (!user[k]) continue;
+        if (is_device_pointer(user[k], s->device)) {
+            dev[k] = user[k];
+        } else {
+            int rc = ensure_scratch(s, k, bytes[k]);
+            if (rc != RT_OK) return rc;
+            dev[k] = s->scratch[k];
+            copy_back[k] = true;
+        }
+    }
+
+    rtk::RenderArgs a;
+    a.W = p->W;
+    a.H = p->H;
+    a.rows = rows;
+    a.row_begin = p->row_begin;
+    a.row_step = step;
+    a.segments = p->num_bounce + (p->extra_segment ? 1 : 0);
+    a.num_rays = p->num_rays;
+    a.camx = p->cam[0];
+    a.camy = p->cam[1];
+    a.camz = p->cam[2];
+    a.z = p->z;
+    a.eps_surface = p->eps_surface;
+    a.eps_tri = p->eps_tri;
+    a.push_order = p->push_order;
+    a.gamma_mode = p->gamma_mode;
+    a.rgb = (uint8_t*)dev[0];
+    a.hit_obj = (int32_t*)dev[1];
+    a.hit_tri = (int32_t*)dev[2];
+    a.hit_t = (float*)dev[3];
+    a.shadow = (uint8_t*)dev[4];
+    a.counters = s->counters;
+    a.gamma_tab = s->gamma_tab;
+
+    int launches = 0;
+    CUDA_TRY(cudaMemsetAsync(s->counters, 0, 4 * sizeof(unsigned long long), s->stream));
+    CUDA_TRY(cudaEventRecord(s->ev0, s->stream));
+    {
+        const int tiles_x = (p->W + 15) / 16, tiles_y = (rows + 7) / 8;
+        const unsigned grid = (unsigned)tiles_x * (unsigned)tiles_y;
+        if (flags & RT_RENDER_COUNT_WORK) rtk::render_mega<true><<<grid, 128, 0, s->stream>>>(s->header, s->blob, a);
+        else rtk::render_mega<false><<<grid, 128, 0, s->stream>>>(s->header, s->blob, a);
+        launches++;
+        CUDA_TRY(cudaGetLastError());
+    }
+    CUDA_TRY(cudaEventRecord(s->ev1, s->stream));
+    for (int k = 0; k < 5; k++)
+        if (copy_back[k]) CUDA_TRY(cudaMemcpyAsync(user[k], dev[k], bytes[k], cudaMemcpyDeviceToHost, s->stream));
+    s->pending = true; /* the counters are read back by rt_scene_sync, not per enqueued frame */
+    s->pending_launches = launches;
+    if (flags & RT_RENDER_NO_SYNC) {
+        if (stats) memset(stats, 0, sizeof *stats);
+        return RT_OK;
+    }
+    return rt_scene_sync(s, stats);
+}
+
+/* Device self-test used by tests/: agreement of the reciprocal-based division with div.rn.f32.
+ * out[0] mismatches (1 correction step), out[1] mismatches (2 steps), out[2] pairs tested. */
+int rt_selftest_division(int device, uint64_t seed, int blocks, int per_thread, uint64_t out[3]) {
+    if (!out || blocks <= 0 || per_thread <= 0) return rtb::fail(RT_ERR_INVALID, "rt_selftest_division: bad argument");
+    DeviceGuard g(device);
+    if (!g.ok) return rtb::fail(RT_ERR_CUDA, "rt_selftest_division: no device %d", device);
+    unsigned long long* d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, 3 * sizeof(unsigned long long)));
+    cudaMemset(d, 0, 3 * sizeof(unsigned long long));
+    rtk::selftest_division<<<blocks, 256>>>(seed, per_thread, d);
+    cudaError_t e = cudaDeviceSynchronize();
+    unsigned long long hst[3] = {0, 0, 0};
+    if (e == cudaSuccess) e = cudaMemcpy(hst, d, sizeof hst, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return rtb::fail(RT_ERR_CUDA, "rt_selftest_division: %s", cudaGetErrorString(e));
+    out[0] = hst[0];
+    out[1] = hst[1];
+    out[2] = hst[2];
+    return RT_OK;
+}
+
+} /* extern "C" */

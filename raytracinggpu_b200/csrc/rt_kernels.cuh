@@ -1,0 +1,368 @@
+/*
+ * rt_kernels.cuh — sm_100a render kernels.
+ *
+ * render_mega: one thread per pixel, every stage of the reference's per-pixel path fused in one launch:
+ *   ray generation            optimized.cu:746-760  (cpu_launcher.cpp:695-709)
+ *   Scene::intersect_all      optimized.cu:539-559
+ *   Sphere::intersect         optimized.cu:123-135
+ *   TriangleMesh::intersect   optimized.cu:220-285  (BVH traversal; cpu_launcher.cpp:277-311, array_bvh.cu:231-307)
+ *   BoundingBox::intersect    optimized.cu:173-184
+ *   moller_trumbore           optimized.cu:208-218
+ *   getColorIterative         optimized.cu:561-661  (deterministic subset: mirror / refraction chain, direct + shadow)
+ *   gamma + 8-bit store       optimized.cu:764-771
+ * A warp covers an 8x4 pixel tile (coherent rays: node and triangle loads of a warp mostly hit the same
+ * 64-B / 48-B record and are served as one L1 wavefront).
+ */
+#pragma once
+#include "rt_layout.h"
+#include "rt_math.cuh"
+
+namespace rtk {
+
+struct RenderArgs {
+    int32_t W, H, rows, row_begin, row_step;
+    int32_t segments, num_rays;
+    float camx, camy, camz, z;
+    float eps_surface, eps_tri;
+    int32_t push_order, gamma_mode;
+    uint8_t* rgb;
+    int32_t* hit_obj;
+    int32_t* hit_tri;
+    float* hit_t;
+    uint8_t* shadow;
+    unsigned long long* counters; /* [0] rays, [1] inner-node visits, [2] triangle tests, [3] max stack */
+    const float* gamma_tab;       /* 2 x 256 thresholds */
+};
+
+struct Work {
+    unsigned int rays, nodes, tris, max_stack;
+};
+
+/* One 8-bit channel: trunc(min(c^(1/2.2), 255)) (optimized.cu:765 / cpu_launcher.cpp:714) evaluated EXACTLY
+ * without pow: T[k] is the smallest float whose reference transfer value is >= k (built on the host with the
+ * reference's libm expression, rt_device.cu:build_gamma_table), so the result is the number of thresholds
+ * <= c. A two-MUFU estimate finds the neighbourhood, the table fixes it. */
+__device__ __forceinline__ int quantise(float c, const float* __restrict__ T) {
+    const float g = __powf(c, 0.45454545f);
+    int k = (int)fminf(fmaxf(g, 0.f), 255.f);
+    while (k > 0 && c < T[k]) --k;
+    while (k < 255 && c >= T[k + 1]) ++k;
+    return k;
+}
+
+/* Sphere::intersect, t only (the normal is a function of t and is formed for the winner only). */
+__device__ __forceinline__ bool sphere_t(const DevSphere& s, F3 O, F3 u, float& t) {
+    const F3 OC = f3(O.x - s.cx, O.y - s.cy, O.z - s.cz);
+    const float b = dot(u, OC);
+    const float delta = b * b - (norm2(OC) - s.RR);
+    if (delta < 0) return false;
+    const float sq = sqrtf(delta);
+    const float bc = -b; /* dot(u, C-O) == -dot(u, O-C) bit for bit (negation commutes with RN) */
+    const float t1 = bc - sq;
+    const float t2 = bc + sq;
+    if (t2 < 0) return false;
+    t = t1 < 0 ? t2 : t1;
+    return true;
+}
+
+/* moller_trumbore on the packed record (A, e1, e2, N precomputed exactly). Returns true with t when the
+ * reference's function returns 1. */
+__device__ __forceinline__ bool tri_exact(const float4* __restrict__ rec, F3 O, F3 u, float& t) {
+    const float4 q0 = __ldg(rec), q1 = __ldg(rec + 1), q2 = __ldg(rec + 2);
+    const F3 A = f3(q0.x, q0.y, q0.z), e1 = f3(q0.w, q1.x, q1.y), e2 = f3(q1.z, q1.w, q2.x), N = f3(q2.y, q2.z, q2.w);
+    const float d = dot(u, N);
+    if (d == 0) return false;
+    const F3 AO = A - O;
+    const F3 c = cross(AO, u);
+    const float beta = dot(e2, c) / d;
+    const float gamma = -dot(e1, c) / d;
+    if (!(0 <= beta && beta <= 1) || !(0 <= gamma && gamma <= 1)) return false;
+    t = dot(AO, N) / d;
+    return beta + gamma <= 1 && t > 0;
+}
+
+/* TriangleMesh::intersect. The reference visits nodes in a fixed LIFO order without pruning and accepts
+ * strictly closer hits, so the visiting order only decides exact-t ties: with
+ * push_order 1 (optimized.cu:265-266) leaves are seen in ascending triangle order -> the smallest leaf start
+ * wins a tie; with push_order 0 (cpu_launcher.cpp:291-292) in descending leaf order -> the largest leaf start
+ * wins; inside a leaf the first (smallest) index wins either way. Applying that rule makes the outcome
+ * independent of the order used here (left child first). */
+template <bool COUNT>
+__device__ __forceinline__ void mesh_closest(const SceneHeader& h, const float4* __restrict__ nodes, const float4* __restrict__ tris,
+                                             F3 O, F3 u, float eps_tri, int push_order, float& t_best, int& tri_best, Work& w) {
+    t_best = RTK_INF;
+    tri_best = -1;
+    int leaf_best = -1;
+    if (!slab_exact(h.root_mn[0], h.root_mn[1], h.root_mn[2], h.root_mx[0], h.root_mx[1], h.root_mx[2], O, u)) return;
+    int2 stack[RT_STACK_CAP];
+    int sp = 0;
+    int2 cur = make_int2(h.root_a, h.root_b);
+    for (;;) {
+        if (cur.y < 0) {
+            const float4* n = nodes + 4 * (size_t)cur.x;
+            const float4 q0 = __ldg(n), q1 = __ldg(n + 1), q2 = __ldg(n + 2);
+            const int4 q3 = __ldg(reinterpret_cast<const int4*>(n + 3));
+            if (COUNT) w.nodes++;
+            const bool okL = slab_exact(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, O, u);
+            const bool okR = slab_exact(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, O, u);
+            if (okL) {
+                cur = make_int2(q3.x, q3.y);
+                if (okR) {
+                    stack[sp++] = make_int2(q3.z, q3.w);
+                    if (COUNT) w.max_stack = max(w.max_stack, (unsigned)sp);
+                }
+                continue;
+            }
+            if (okR) {
+                cur = make_int2(q3.z, q3.w);
+                continue;
+            }
+        } else {
+            for (int i = cur.x; i < cur.y; i++) {
+                if (COUNT) w.tris++;
+                float t;
+                if (!tri_exact(tris + 3 * (size_t)i, O, u, t)) continue;
+                if (!(t > eps_tri)) continue; /* optimized.cu:275 / cpu_launcher.cpp:301 */
+                const bool tie = (tri_best >= 0) && (t == t_best) && (leaf_best != cur.x) && (push_order == 1 ? (cur.x < leaf_best) : (cur.x > leaf_best));
+                if (t < t_best || tie) {
+                    t_best = t;
+                    tri_best = i;
+                    leaf_best = cur.x;
+                }
+            }
+        }
+        if (sp == 0) break;
+        cur = stack[--sp];
+    }
+}
+
+struct SurfaceHit {
+    float t;
+    int obj;  /* object id, -1 = miss */
+    int tri;  /* triangle index or -1 */
+    int sidx; /* index into h.spheres or -1 */
+};
+
+/* Scene::intersect_all: ascending object id, strict t < t_min (lowest id wins exact ties). */
+template <bool COUNT>
+__device__ __forceinline__ SurfaceHit intersect_all(const SceneHeader& h, const float4* __restrict__ nodes, const float4* __restrict__ tris,
+                                                    F3 O, F3 u, float eps_tri, int push_order, Work& w) {
+    w.rays++;
+    SurfaceHit r;
+    r.t = RTK_INF;
+    r.obj = -1;
+    r.tri = -1;
+    r.sidx = -1;
+    for (int k = 0; k < h.n_spheres; k++) {
+        float t;
+        if (sphere_t(h.spheres[k], O, u, t) && t < r.t) {
+            r.t = t;
+            r.obj = h.spheres[k].id;
+            r.sidx = k;
+        }
+    }
+    if (h.has_mesh) {
+        float tm;
+        int tri;
+        mesh_closest<COUNT>(h, nodes, tris, O, u, eps_tri, push_order, tm, tri, w);
+        if (tri >= 0 && (tm < r.t || (tm == r.t && h.mesh_id < r.obj))) {
+            r.t = tm;
+            r.obj = h.mesh_id;
+            r.tri = tri;
+            r.sidx = -1;
+        }
+    }
+    return r;
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(128) render_mega(const __grid_constant__ SceneHeader h, const unsigned char* __restrict__ blob, const RenderArgs a) {
+    __shared__ float s_gamma[256];
+    for (int k = threadIdx.x; k < 256; k += blockDim.x) s_gamma[k] = a.gamma_tab[a.gamma_mode * 256 + k];
+    __syncthreads();
+
+    const float4* nodes = reinterpret_cast<const float4*>(blob + h.off_nodes);
+    const float4* tris = reinterpret_cast<const float4*>(blob + h.off_tris);
+    const float4* nhat = reinterpret_cast<const float4*>(blob + h.off_nhat);
+
+    /* 16x8 pixel tile per block, 8x4 per warp */
+    const int tiles_x = (a.W + 15) >> 4;
+    const int tile_x = blockIdx.x % tiles_x, tile_y = blockIdx.x / tiles_x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int j = tile_x * 16 + (warp & 1) * 8 + (lane & 7);
+    const int k = tile_y * 8 + (warp >> 1) * 4 + (lane >> 3);
+    const bool live = j < a.W && k < a.rows;
+
+    Work w;
+    w.rays = w.nodes = w.tris = w.max_stack = 0;
+    if (live) {
+        const int i = a.row_begin + k * a.row_step;
+        /* optimized.cu:751 — half-integers, exact in float */
+        const F3 uc = f3((float)j - (float)a.W / 2 + 0.5f, (float)a.H / 2 - (float)i - 0.5f, a.z);
+        const F3 cam = f3(a.camx, a.camy, a.camz);
+        const F3 Lp = f3(h.L[0], h.L[1], h.L[2]);
+        F3 O = cam;
+        F3 u = normalized(uc); /* sigma == 0: the jitter terms of :758 are exactly 0 */
+        float n_ray = 1.f;
+        F3 color = f3(0.f, 0.f, 0.f);
+        int first_obj = -1, first_tri = -1, shadow = 2;
+        float first_t = RTK_INF;
+        const float eps = a.eps_surface;
+
+        for (int depth = 0; depth < a.segments; depth++) {
+            const SurfaceHit hit = intersect_all<COUNT>(h, nodes, tris, O, u, a.eps_tri, a.push_order, w);
+            if (depth == 0) {
+                first_obj = hit.obj;
+                first_tri = hit.tri;
+                first_t = hit.t;
+            }
+            if (hit.obj < 0) break;
+            const F3 P = O + hit.t * u; /* :555 */
+            F3 N, albedo;
+            int mirror;
+            float n_in, n_out;
+            if (hit.sidx >= 0) {
+                const DevSphere& s = h.spheres[hit.sidx];
+                N = normalized(P - f3(s.cx, s.cy, s.cz)); /* :132-133 */
+                albedo = f3(s.ax, s.ay, s.az);
+                mirror = s.mirror;
+                n_in = s.n_in;
+                n_out = s.n_out;
+            } else {
+                const float4 nh = __ldg(nhat + hit.tri); /* N.normalize() :282, precomputed */
+                N = f3(nh.x, nh.y, nh.z);
+                albedo = f3(h.mesh_albedo[0], h.mesh_albedo[1], h.mesh_albedo[2]);
+                mirror = h.mesh_mirror;
+                n_in = h.mesh_n_in;
+                n_out = h.mesh_n_out;
+            }
+            if (mirror) { /* :572-579 */
+                const F3 Padj = P + eps * N;
+                const F3 dir = u - (2 * dot(u, N)) * N;
+                O = Padj;
+                u = dir;
+            } else if (n_in != n_out) { /* :580-609 */
+                float ratio;
+                const bool out2in = n_ray == n_out;
+                if (out2in) {
+                    ratio = n_out / n_in;
+                } else {
+                    ratio = n_in / n_out;
+                    N = -N;
+                }
+                const float un = dot(u, N);
+                if (((out2in && n_ray > n_in) || (!out2in && n_ray > n_out)) && (ratio * ratio) * (1 - un * un) > 1) {
+                    const F3 Padj = P + eps * N;
+                    const F3 dir = u - (2 * un) * N;
+                    O = Padj;
+                    u = dir;
+                    continue;
+                }
+                const F3 Padj = P - eps * N;
+                const F3 Ncomp = (-sqrtf(1 - (ratio * ratio) * (1 - un * un))) * N;
+                const F3 Tcomp = ratio * (u - un * N);
+                O = Padj;
+                u = Ncomp + Tcomp;
+                n_ray = out2in ? n_in : n_out;
+            } else { /* diffuse :610-650 */
+                const F3 Padj = P + eps * N;
+                const F3 toL = Lp - Padj;
+                const F3 su = toL / sqrtf(norm2(toL)); /* NORMED_VEC :618 */
+                const SurfaceHit sh = intersect_all<COUNT>(h, nodes, tris, Padj, su, a.eps_tri, a.push_order, w);
+                const F3 Ps = Padj + sh.t * su; /* on a miss t = 1e9f, as the reference leaves it */
+                if (norm2(Ps - Padj) <= norm2(toL)) { /* :620 */
+                    shadow = 1;
+                } else {
+                    shadow = 0;
+                    const F3 PL = Lp - P;
+                    const F3 wl = normalized(PL);
+                    const float ndl = dot(N, wl);
+                    const float lambert = (ndl < 0.f) ? 0.f : ndl; /* std::max(dot, 0.f) */
+                    /* :628 in double, as the source promotes it */
+                    const float l = (float)((double)h.intensity / (12.566370614359172 * (double)norm2(PL)) * (double)lambert);
+                    color = (l * albedo) / 3.14159274f; /* :629, Vector / float(PI) */
+                }
+                break; /* deterministic mode: the path ends at the first diffuse hit */
+            }
+        }
+
+        /* sample average :762-764 — the samples are identical in deterministic mode; keep the float sums */
+        F3 total = f3(0.f, 0.f, 0.f);
+        for (int s = 0; s < a.num_rays; s++) total = total + color;
+        const F3 avg = total / (float)a.num_rays;
+        const size_t px = (size_t)k * a.W + j;
+        if (a.rgb) {
+            a.rgb[px * 3 + 0] = (uint8_t)quantise(avg.x, s_gamma);
+            a.rgb[px * 3 + 1] = (uint8_t)quantise(avg.y, s_gamma);
+            a.rgb[px * 3 + 2] = (uint8_t)quantise(avg.z, s_gamma);
+        }
+        if (a.hit_obj) a.hit_obj[px] = first_obj;
+        if (a.hit_tri) a.hit_tri[px] = first_tri;
+        if (a.hit_t) a.hit_t[px] = first_t;
+        if (a.shadow) a.shadow[px] = (uint8_t)shadow;
+    }
+
+    /* ray / work counters: one atomic per warp */
+    unsigned int rays = __reduce_add_sync(0xffffffffu, w.rays);
+    if (lane == 0 && rays) atomicAdd(a.counters + 0, (unsigned long long)rays);
+    if (COUNT) {
+        unsigned int nn = __reduce_add_sync(0xffffffffu, w.nodes);
+        unsigned int tt = __reduce_add_sync(0xffffffffu, w.tris);
+        unsigned int ms = __reduce_max_sync(0xffffffffu, w.max_stack);
+        if (lane == 0) {
+            atomicAdd(a.counters + 1, (unsigned long long)nn);
+            atomicAdd(a.counters + 2, (unsigned long long)tt);
+            atomicMax(a.counters + 3, (unsigned long long)ms);
+        }
+    }
+}
+
+/* Mesh repack: reference interchange arrays -> packed triangle records + unit normals (rt_layout.h).
+ * e1, e2, N as moller_trumbore forms them (optimized.cu:209-211), N/|N| as :282 does. */
+__global__ void repack_triangles(const float* __restrict__ vertices, const int32_t* __restrict__ recs, int nt, float4* __restrict__ tris,
+                                 float4* __restrict__ nhat) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nt) return;
+    const int32_t* r = recs + (size_t)i * 10;
+    const int ia = r[0], ib = r[1], ic = r[2];
+    const F3 A = f3(vertices[3 * (size_t)ia], vertices[3 * (size_t)ia + 1], vertices[3 * (size_t)ia + 2]);
+    const F3 B = f3(vertices[3 * (size_t)ib], vertices[3 * (size_t)ib + 1], vertices[3 * (size_t)ib + 2]);
+    const F3 C = f3(vertices[3 * (size_t)ic], vertices[3 * (size_t)ic + 1], vertices[3 * (size_t)ic + 2]);
+    const F3 e1 = B - A, e2 = C - A;
+    const F3 N = cross(e1, e2);
+    const F3 nh = normalized(N);
+    tris[3 * (size_t)i + 0] = make_float4(A.x, A.y, A.z, e1.x);
+    tris[3 * (size_t)i + 1] = make_float4(e1.y, e1.z, e2.x, e2.y);
+    tris[3 * (size_t)i + 2] = make_float4(e2.z, N.x, N.y, N.z);
+    nhat[i] = make_float4(nh.x, nh.y, nh.z, 0.f);
+}
+
+/* Device self-test of div_by_rcp against div.rn.f32 on pseudo-random operands in the range RaySafe admits.
+ * out[0] += mismatches with 1 correction step, out[1] += mismatches with 2 steps, out[2] += pairs tested. */
+__global__ void selftest_division(unsigned long long seed, int per_thread, unsigned long long* out) {
+    unsigned long long s = seed + 0x9E3779B97F4A7C15ull * (blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x + 1);
+    unsigned int bad1 = 0, bad2 = 0, n = 0;
+    for (int it = 0; it < per_thread; it++) {
+        s ^= s << 13; s ^= s >> 7; s ^= s << 17;
+        const unsigned int ra = (unsigned int)s, rb = (unsigned int)(s >> 32);
+        /* exponents: a in 2^[-60,41), b in 2^[-40,2) ; random sign and mantissa; every 8th b has a
+         * near-all-ones / near-zero mantissa (the hard cases for reciprocal-based division) */
+        const unsigned int ea = 127 - 60 + (ra >> 24) % 101, eb = 127 - 40 + (rb >> 24) % 42;
+        unsigned int ma = ra & 0x7fffffu, mb = rb & 0x7fffffu;
+        if ((it & 7) == 0) mb = (it & 8) ? (0x7fffffu - (mb & 0xff)) : (mb & 0xff);
+        if ((it & 7) == 1) ma = (it & 8) ? (0x7fffffu - (ma & 0xff)) : (ma & 0xff);
+        const float x = __uint_as_float(((ra >> 23) & 1u) << 31 | ea << 23 | ma);
+        const float y = __uint_as_float(((rb >> 23) & 1u) << 31 | eb << 23 | mb);
+        const float ref = x / y;
+        const float r = __frcp_rn(y);
+        const float q1 = div_by_rcp<1>(x, y, r), q2 = div_by_rcp<2>(x, y, r);
+        bad1 += __float_as_uint(q1) != __float_as_uint(ref);
+        bad2 += __float_as_uint(q2) != __float_as_uint(ref);
+        n++;
+    }
+    atomicAdd(out + 0, (unsigned long long)bad1);
+    atomicAdd(out + 1, (unsigned long long)bad2);
+    atomicAdd(out + 2, (unsigned long long)n);
+}
+
+} // namespace rtk

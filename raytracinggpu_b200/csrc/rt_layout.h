@@ -1,0 +1,64 @@
+/*
+ * rt_layout.h — device-resident scene layout (HBM) shared by the host uploader and the kernels.
+ *
+ * One contiguous blob per scene, so that a scene built on rank 0 can be broadcast to the other GPUs in
+ * one collective:
+ *
+ *   [ SceneHeader, padded to RT_HEADER_BYTES ]
+ *   [ inner nodes : n_inner  x 64 B ]   both children's boxes + both child references in one record
+ *   [ triangles   : n_tris   x 48 B ]   A, e1 = B-A, e2 = C-A, N = e1 x e2 (12 floats = 3 x float4)
+ *   [ unit normals: n_tris   x 16 B ]   N / |N| (read once per ray, for the winning triangle only)
+ *
+ * versus the reference interchange format (what rt_scene_set_mesh receives and optimized.cu:814-826 uploads):
+ * 40-B nodes read as 10 scalar loads with every child node read twice (optimized.cu:223-238, 255-261), and
+ * a 40-B index record + 3 dependent 12-B vertex gathers per triangle test (:271). Here an inner-node visit is
+ * four 16-B loads of one 64-B line, a triangle test three 16-B loads of one 48-B record, no indirection.
+ *
+ * e1, e2, N and N/|N| depend only on the mesh, so they are precomputed once on the device with the same
+ * unfused IEEE operations moller_trumbore (optimized.cu:209-211) and N.normalize() (:282) apply per ray:
+ * bit-identical values, 15 fewer FLOP per triangle test.
+ */
+#pragma once
+#include <stdint.h>
+
+#define RT_MAX_SPHERES 16
+#define RT_HEADER_BYTES 1024
+#define RT_NODE_BYTES 64
+#define RT_TRI_BYTES 48
+#define RT_NHAT_BYTES 16
+#define RT_STACK_CAP 64 /* traversal stack entries; rt_scene_set_mesh rejects deeper trees */
+#define RT_BLOB_MAGIC 0x52544232u /* "RTB2" */
+
+struct DevSphere {
+    float cx, cy, cz, R;
+    float RR; /* RN(R*R), the product Sphere::intersect recomputes per ray (optimized.cu:124) */
+    float ax, ay, az;
+    int32_t mirror;
+    float n_in, n_out;
+    int32_t id;
+};
+
+/* Child reference (a, b): b < 0 -> inner node with index a in the inner-node array; b >= 0 -> leaf with
+ * triangles [a, b). */
+struct SceneHeader {
+    uint32_t magic;
+    uint32_t layout_version;
+    int32_t n_spheres;
+    int32_t has_mesh;
+    int32_t n_inner;
+    int32_t n_tris;
+    int32_t max_depth; /* levels of the BVH: bound on the traversal stack */
+    int32_t mesh_id;
+    int32_t mesh_mirror;
+    float mesh_n_in, mesh_n_out;
+    float mesh_albedo[3];
+    float root_mn[3], root_mx[3];
+    int32_t root_a, root_b;
+    float L[3];
+    float intensity;
+    uint64_t off_nodes, off_tris, off_nhat, total_bytes; /* byte offsets inside the blob */
+    DevSphere spheres[RT_MAX_SPHERES];                    /* ascending id */
+};
+
+static_assert(sizeof(DevSphere) == 48, "DevSphere layout");
+static_assert(sizeof(SceneHeader) <= RT_HEADER_BYTES, "SceneHeader must fit its slot");
