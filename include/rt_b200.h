@@ -85,11 +85,14 @@ typedef struct rt_params {
 
 typedef struct rt_stats {
     double kernel_ms;        /* CUDA-event time of the render kernels of this call */
-    uint64_t rays;           /* intersect_all calls (primary + bounce + shadow), counted on the device */
+    uint64_t rays;           /* intersect_all calls (primary + bounce + shadow) traced, counted on the device. The samples of a
+                                pixel are identical in deterministic mode and are traced once (summed num_rays times). */
     uint64_t node_visits;    /* inner BVH nodes popped (two box tests each); 0 unless RT_RENDER_COUNT_WORK */
     uint64_t tri_tests;      /* Moller-Trumbore evaluations; 0 unless RT_RENDER_COUNT_WORK */
     int32_t launches;        /* kernels launched by this call */
     int32_t max_stack;       /* deepest traversal stack seen; 0 unless RT_RENDER_COUNT_WORK */
+    uint64_t slab_fallbacks; /* box tests the certified fast path handed to the exact code; 0 unless RT_RENDER_COUNT_WORK */
+    uint64_t tri_exact;      /* triangle tests that evaluated the three exact divisions; 0 unless RT_RENDER_COUNT_WORK */
 } rt_stats;
 
 /* rt_render flags */

@@ -58,4 +58,6 @@ class rt_stats(C.Structure):
         ("tri_tests", C.c_uint64),
         ("launches", C.c_int32),
         ("max_stack", C.c_int32),
+        ("slab_fallbacks", C.c_uint64),
+        ("tri_exact", C.c_uint64),
     ]

@@ -13,10 +13,12 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
 
+#define RT_NCOUNTERS 8
 #define CUDA_TRY(expr)                                                                                         \
     do {                                                                                                       \
         cudaError_t e__ = (expr);                                                                              \
@@ -45,6 +47,9 @@ struct rt_scene {
     /* pending copy-back of a RT_RENDER_NO_SYNC call */
     bool pending = false;
     int pending_launches = 0;
+
+    /* kernel variant: 0 = plain exact arithmetic, 1 = certified fast paths (same results). RT_VARIANT overrides. */
+    int variant = 1;
 };
 
 namespace {
@@ -125,6 +130,7 @@ void reset_mesh_fields(SceneHeader& h) {
     for (int k = 0; k < 3; k++) {
         h.root_mn[k] = 0.f;
         h.root_mx[k] = 0.f;
+        h.box_abs[k] = 0.f;
     }
 }
 
@@ -153,6 +159,7 @@ int rt_scene_create(rt_scene** out, int device) {
     rt_scene* s = new (std::nothrow) rt_scene();
     if (!s) return rtb::fail(RT_ERR_NOMEM, "rt_scene_create: out of memory");
     s->device = device;
+    if (const char* v = getenv("RT_VARIANT")) s->variant = atoi(v);
     memset(&s->header, 0, sizeof s->header);
     s->header.magic = RT_BLOB_MAGIC;
     s->header.layout_version = 1;
@@ -170,8 +177,8 @@ int rt_scene_create(rt_scene** out, int device) {
     if (err == cudaSuccess) err = cudaEventCreate(&s->ev0);
     if (err == cudaSuccess) err = cudaEventCreate(&s->ev1);
     if (err == cudaSuccess) err = cudaMalloc(&s->gamma_tab, 512 * sizeof(float));
-    if (err == cudaSuccess) err = cudaMalloc(&s->counters, 4 * sizeof(unsigned long long));
-    if (err == cudaSuccess) err = cudaMallocHost(&s->h_counters, 4 * sizeof(unsigned long long));
+    if (err == cudaSuccess) err = cudaMalloc(&s->counters, RT_NCOUNTERS * sizeof(unsigned long long));
+    if (err == cudaSuccess) err = cudaMallocHost(&s->h_counters, RT_NCOUNTERS * sizeof(unsigned long long));
     if (err == cudaSuccess) err = cudaMemcpy(s->gamma_tab, tab.data(), 512 * sizeof(float), cudaMemcpyHostToDevice);
     if (err != cudaSuccess) {
         rtb::fail(RT_ERR_CUDA, "rt_scene_create: %s", cudaGetErrorString(err));
@@ -301,6 +308,11 @@ int rt_scene_set_mesh(rt_scene* s, const float* vertices, int32_t nv, const int3
     if (max_depth > RT_STACK_CAP - 2)
         return rtb::fail(RT_ERR_UNSUPPORTED, "rt_scene_set_mesh: BVH depth %d exceeds the traversal stack (%d)", max_depth, RT_STACK_CAP - 2);
 
+    float box_abs[3] = {0.f, 0.f, 0.f};
+    for (int32_t k = 0; k < n_nodes; k++) {
+        const float* a = arr_bvh + (size_t)k * RT_BVH_NODE_FLOATS;
+        for (int c = 0; c < 3; c++) box_abs[c] = std::max(box_abs[c], std::max(std::fabs(a[2 + c]), std::fabs(a[5 + c])));
+    }
     auto child_ref = [&](int32_t node, int32_t& a_out, int32_t& b_out) {
         const float* a = arr_bvh + (size_t)node * RT_BVH_NODE_FLOATS;
         if ((int32_t)a[0] != -1) {
@@ -376,6 +388,7 @@ int rt_scene_set_mesh(rt_scene* s, const float* vertices, int32_t nv, const int3
         h.root_mx[c] = arr_bvh[5 + c];
     }
     child_ref(0, h.root_a, h.root_b);
+    memcpy(h.box_abs, box_abs, sizeof box_abs);
     h.off_nodes = off_nodes;
     h.off_tris = off_tris;
     h.off_nhat = off_nhat;
@@ -433,7 +446,7 @@ int rt_scene_blob_import(rt_scene* s, const void* device_ptr, size_t bytes) {
 int rt_scene_sync(rt_scene* s, rt_stats* stats) {
     if (!s) return rtb::fail(RT_ERR_INVALID, "rt_scene_sync: NULL scene");
     DeviceGuard g(s->device);
-    if (s->pending) CUDA_TRY(cudaMemcpyAsync(s->h_counters, s->counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->stream));
+    if (s->pending) CUDA_TRY(cudaMemcpyAsync(s->h_counters, s->counters, RT_NCOUNTERS * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->stream));
     CUDA_TRY(cudaStreamSynchronize(s->stream));
     if (stats) {
         memset(stats, 0, sizeof *stats);
@@ -445,6 +458,8 @@ int rt_scene_sync(rt_scene* s, rt_stats* stats) {
             stats->node_visits = s->h_counters[1];
             stats->tri_tests = s->h_counters[2];
             stats->max_stack = (int32_t)s->h_counters[3];
+            stats->slab_fallbacks = s->h_counters[4];
+            stats->tri_exact = s->h_counters[5];
             stats->launches = s->pending_launches;
         }
     }
@@ -533,13 +548,19 @@ int rt_render(rt_scene* s, const rt_params* p, uint32_t flags, uint8_t* rgb_out,
     a.gamma_tab = s->gamma_tab;
 
     int launches = 0;
-    CUDA_TRY(cudaMemsetAsync(s->counters, 0, 4 * sizeof(unsigned long long), s->stream));
+    CUDA_TRY(cudaMemsetAsync(s->counters, 0, RT_NCOUNTERS * sizeof(unsigned long long), s->stream));
     CUDA_TRY(cudaEventRecord(s->ev0, s->stream));
     {
         const int tiles_x = (p->W + 15) / 16, tiles_y = (rows + 7) / 8;
         const unsigned grid = (unsigned)tiles_x * (unsigned)tiles_y;
-        if (flags & RT_RENDER_COUNT_WORK) rtk::render_mega<true><<<grid, 128, 0, s->stream>>>(s->header, s->blob, a);
-        else rtk::render_mega<false><<<grid, 128, 0, s->stream>>>(s->header, s->blob, a);
+        const bool count = (flags & RT_RENDER_COUNT_WORK) != 0;
+        if (s->variant == 0) {
+            if (count) rtk::render_mega<true, false><<<grid, 128, 0, s->stream>>>(s->header, s->blob, a);
+            else rtk::render_mega<false, false><<<grid, 128, 0, s->stream>>>(s->header, s->blob, a);
+        } else {
+            if (count) rtk::render_mega<true, true><<<grid, 128, 0, s->stream>>>(s->header, s->blob, a);
+            else rtk::render_mega<false, true><<<grid, 128, 0, s->stream>>>(s->header, s->blob, a);
+        }
         launches++;
         CUDA_TRY(cudaGetLastError());
     }

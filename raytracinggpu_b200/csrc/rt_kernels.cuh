@@ -30,12 +30,13 @@ struct RenderArgs {
     int32_t* hit_tri;
     float* hit_t;
     uint8_t* shadow;
-    unsigned long long* counters; /* [0] rays, [1] inner-node visits, [2] triangle tests, [3] max stack */
+    unsigned long long* counters; /* [0] rays, [1] inner-node visits, [2] triangle tests, [3] max stack, [4] slab exact fallbacks, [5] exact triangle evaluations */
     const float* gamma_tab;       /* 2 x 256 thresholds */
 };
 
 struct Work {
     unsigned int rays, nodes, tris, max_stack;
+    unsigned int slab_fallbacks, tri_exact; /* certified fast paths that had to evaluate the exact code */
 };
 
 /* One 8-bit channel: trunc(min(c^(1/2.2), 255)) (optimized.cu:765 / cpu_launcher.cpp:714) evaluated EXACTLY
@@ -81,19 +82,58 @@ __device__ __forceinline__ bool tri_exact(const float4* __restrict__ rec, F3 O, 
     return beta + gamma <= 1 && t > 0;
 }
 
+/* Certified triangle test: the numerators and the denominator are the reference's own (unfused) values; only
+ * the three divisions are first approximated by a multiplication with rcp.approx(d) (relative distance from
+ * the reference quotient < 2^-22). A triangle is rejected on the approximation only when the reference's
+ * comparison is certain to fail (margins 2^-20 .. 2^-18 around 0, 1 and t_limit); everything else — every
+ * accepted hit in particular — goes through the exact divisions, so accepted t values are the reference's bits.
+ * t_limit: hits with t certainly greater than t_limit are of no interest to the caller (current closest hit). */
+__device__ __forceinline__ bool tri_fast(const float4* __restrict__ rec, F3 O, F3 u, float t_limit, float& t, unsigned int& exact_evals) {
+    const float4 q0 = __ldg(rec), q1 = __ldg(rec + 1), q2 = __ldg(rec + 2);
+    const F3 A = f3(q0.x, q0.y, q0.z), e1 = f3(q0.w, q1.x, q1.y), e2 = f3(q1.z, q1.w, q2.x), N = f3(q2.y, q2.z, q2.w);
+    const float d = dot(u, N);
+    if (d == 0) return false;
+    const F3 AO = A - O;
+    const F3 c = cross(AO, u);
+    const float nb = dot(e2, c);
+    const float ng = -dot(e1, c);
+    const float nt = dot(AO, N);
+    if (fabsf(d) >= 1e-30f) {
+        const float rd = rcp_approx(d);
+        const float b = nb * rd, g = ng * rd;
+        if (b < -1e-30f || b > 1.000001f || g < -1e-30f || g > 1.000001f) return false;
+        if (b + g > 1.000004f) return false;
+        const float ta = nt * rd;
+        if (ta < -1e-30f || ta * 0.999999f > t_limit) return false;
+    }
+    exact_evals++;
+    const float beta = nb / d;
+    const float gamma = ng / d;
+    if (!(0 <= beta && beta <= 1) || !(0 <= gamma && gamma <= 1)) return false;
+    t = nt / d;
+    return beta + gamma <= 1 && t > 0;
+}
+
 /* TriangleMesh::intersect. The reference visits nodes in a fixed LIFO order without pruning and accepts
  * strictly closer hits, so the visiting order only decides exact-t ties: with
  * push_order 1 (optimized.cu:265-266) leaves are seen in ascending triangle order -> the smallest leaf start
  * wins a tie; with push_order 0 (cpu_launcher.cpp:291-292) in descending leaf order -> the largest leaf start
  * wins; inside a leaf the first (smallest) index wins either way. Applying that rule makes the outcome
  * independent of the order used here (left child first). */
-template <bool COUNT>
+template <bool COUNT, bool FAST>
 __device__ __forceinline__ void mesh_closest(const SceneHeader& h, const float4* __restrict__ nodes, const float4* __restrict__ tris,
                                              F3 O, F3 u, float eps_tri, int push_order, float& t_best, int& tri_best, Work& w) {
     t_best = RTK_INF;
     tri_best = -1;
     int leaf_best = -1;
-    if (!slab_exact(h.root_mn[0], h.root_mn[1], h.root_mn[2], h.root_mx[0], h.root_mx[1], h.root_mx[2], O, u)) return;
+    RayCtx ctx;
+    float tn;
+    if (FAST) {
+        ctx = make_ray_ctx(O, u, h.box_abs[0], h.box_abs[1], h.box_abs[2]);
+        if (!slab_fast(h.root_mn[0], h.root_mn[1], h.root_mn[2], h.root_mx[0], h.root_mx[1], h.root_mx[2], ctx, tn, w.slab_fallbacks)) return;
+    } else {
+        if (!slab_exact(h.root_mn[0], h.root_mn[1], h.root_mn[2], h.root_mx[0], h.root_mx[1], h.root_mx[2], O, u)) return;
+    }
     int2 stack[RT_STACK_CAP];
     int sp = 0;
     int2 cur = make_int2(h.root_a, h.root_b);
@@ -103,8 +143,14 @@ __device__ __forceinline__ void mesh_closest(const SceneHeader& h, const float4*
             const float4 q0 = __ldg(n), q1 = __ldg(n + 1), q2 = __ldg(n + 2);
             const int4 q3 = __ldg(reinterpret_cast<const int4*>(n + 3));
             if (COUNT) w.nodes++;
-            const bool okL = slab_exact(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, O, u);
-            const bool okR = slab_exact(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, O, u);
+            bool okL, okR;
+            if (FAST) {
+                okL = slab_fast(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, ctx, tn, w.slab_fallbacks);
+                okR = slab_fast(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, ctx, tn, w.slab_fallbacks);
+            } else {
+                okL = slab_exact(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, O, u);
+                okR = slab_exact(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, O, u);
+            }
             if (okL) {
                 cur = make_int2(q3.x, q3.y);
                 if (okR) {
@@ -121,7 +167,11 @@ __device__ __forceinline__ void mesh_closest(const SceneHeader& h, const float4*
             for (int i = cur.x; i < cur.y; i++) {
                 if (COUNT) w.tris++;
                 float t;
-                if (!tri_exact(tris + 3 * (size_t)i, O, u, t)) continue;
+                if (FAST) {
+                    if (!tri_fast(tris + 3 * (size_t)i, O, u, t_best, t, w.tri_exact)) continue;
+                } else {
+                    if (!tri_exact(tris + 3 * (size_t)i, O, u, t)) continue;
+                }
                 if (!(t > eps_tri)) continue; /* optimized.cu:275 / cpu_launcher.cpp:301 */
                 const bool tie = (tri_best >= 0) && (t == t_best) && (leaf_best != cur.x) && (push_order == 1 ? (cur.x < leaf_best) : (cur.x > leaf_best));
                 if (t < t_best || tie) {
@@ -144,7 +194,7 @@ struct SurfaceHit {
 };
 
 /* Scene::intersect_all: ascending object id, strict t < t_min (lowest id wins exact ties). */
-template <bool COUNT>
+template <bool COUNT, bool FAST>
 __device__ __forceinline__ SurfaceHit intersect_all(const SceneHeader& h, const float4* __restrict__ nodes, const float4* __restrict__ tris,
                                                     F3 O, F3 u, float eps_tri, int push_order, Work& w) {
     w.rays++;
@@ -164,7 +214,7 @@ __device__ __forceinline__ SurfaceHit intersect_all(const SceneHeader& h, const 
     if (h.has_mesh) {
         float tm;
         int tri;
-        mesh_closest<COUNT>(h, nodes, tris, O, u, eps_tri, push_order, tm, tri, w);
+        mesh_closest<COUNT, FAST>(h, nodes, tris, O, u, eps_tri, push_order, tm, tri, w);
         if (tri >= 0 && (tm < r.t || (tm == r.t && h.mesh_id < r.obj))) {
             r.t = tm;
             r.obj = h.mesh_id;
@@ -175,7 +225,7 @@ __device__ __forceinline__ SurfaceHit intersect_all(const SceneHeader& h, const 
     return r;
 }
 
-template <bool COUNT>
+template <bool COUNT, bool FAST>
 __global__ void __launch_bounds__(128) render_mega(const __grid_constant__ SceneHeader h, const unsigned char* __restrict__ blob, const RenderArgs a) {
     __shared__ float s_gamma[256];
     for (int k = threadIdx.x; k < 256; k += blockDim.x) s_gamma[k] = a.gamma_tab[a.gamma_mode * 256 + k];
@@ -194,7 +244,7 @@ __global__ void __launch_bounds__(128) render_mega(const __grid_constant__ Scene
     const bool live = j < a.W && k < a.rows;
 
     Work w;
-    w.rays = w.nodes = w.tris = w.max_stack = 0;
+    w.rays = w.nodes = w.tris = w.max_stack = w.slab_fallbacks = w.tri_exact = 0;
     if (live) {
         const int i = a.row_begin + k * a.row_step;
         /* optimized.cu:751 — half-integers, exact in float */
@@ -210,7 +260,7 @@ __global__ void __launch_bounds__(128) render_mega(const __grid_constant__ Scene
         const float eps = a.eps_surface;
 
         for (int depth = 0; depth < a.segments; depth++) {
-            const SurfaceHit hit = intersect_all<COUNT>(h, nodes, tris, O, u, a.eps_tri, a.push_order, w);
+            const SurfaceHit hit = intersect_all<COUNT, FAST>(h, nodes, tris, O, u, a.eps_tri, a.push_order, w);
             if (depth == 0) {
                 first_obj = hit.obj;
                 first_tri = hit.tri;
@@ -268,7 +318,7 @@ __global__ void __launch_bounds__(128) render_mega(const __grid_constant__ Scene
                 const F3 Padj = P + eps * N;
                 const F3 toL = Lp - Padj;
                 const F3 su = toL / sqrtf(norm2(toL)); /* NORMED_VEC :618 */
-                const SurfaceHit sh = intersect_all<COUNT>(h, nodes, tris, Padj, su, a.eps_tri, a.push_order, w);
+                const SurfaceHit sh = intersect_all<COUNT, FAST>(h, nodes, tris, Padj, su, a.eps_tri, a.push_order, w);
                 const F3 Ps = Padj + sh.t * su; /* on a miss t = 1e9f, as the reference leaves it */
                 if (norm2(Ps - Padj) <= norm2(toL)) { /* :620 */
                     shadow = 1;
@@ -313,6 +363,12 @@ __global__ void __launch_bounds__(128) render_mega(const __grid_constant__ Scene
             atomicAdd(a.counters + 1, (unsigned long long)nn);
             atomicAdd(a.counters + 2, (unsigned long long)tt);
             atomicMax(a.counters + 3, (unsigned long long)ms);
+        }
+        unsigned int sf = __reduce_add_sync(0xffffffffu, w.slab_fallbacks);
+        unsigned int te = __reduce_add_sync(0xffffffffu, w.tri_exact);
+        if (lane == 0) {
+            atomicAdd(a.counters + 4, (unsigned long long)sf);
+            atomicAdd(a.counters + 5, (unsigned long long)te);
         }
     }
 }

@@ -53,6 +53,7 @@ struct SceneHeader {
     float mesh_n_in, mesh_n_out;
     float mesh_albedo[3];
     float root_mn[3], root_mx[3];
+    float box_abs[3]; /* largest |coordinate| over all node boxes, per axis (bound used by the certified slab test) */
     int32_t root_a, root_b;
     float L[3];
     float intensity;
