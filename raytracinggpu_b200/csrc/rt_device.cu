@@ -10,6 +10,7 @@
 #include "host_common.h"
 #include "rt_kernels.cuh"
 #include "rt_layout.h"
+#include "rt_wave.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -48,8 +49,11 @@ struct rt_scene {
     bool pending = false;
     int pending_launches = 0;
 
-    /* kernel variant: 0 = plain exact arithmetic, 1 = certified fast paths (same results). RT_VARIANT overrides. */
-    int variant = 1;
+    /* kernel variant: 0 = render_mega, plain exact arithmetic; 1 = render_mega with the certified fast paths;
+     * 2 = render_wave (persistent blocks + ray queue + work stealing). Same results. RT_VARIANT overrides. */
+    int variant = 2;
+    int max_leaf = 0;        /* largest leaf of the uploaded BVH */
+    int wave_blocks_per_sm = 0, sm_count = 0;
 };
 
 namespace {
@@ -278,7 +282,7 @@ int rt_scene_set_mesh(rt_scene* s, const float* vertices, int32_t nv, const int3
 
     /* ---- node relayout on the host: 10-float pre-order nodes -> 64-B two-child records ----------------- */
     std::vector<int32_t> inner_index((size_t)n_nodes, -1);
-    int32_t n_inner = 0;
+    int32_t n_inner = 0, max_leaf = 0;
     for (int32_t k = 0; k < n_nodes; k++) {
         const float* a = arr_bvh + (size_t)k * RT_BVH_NODE_FLOATS;
         const int32_t l = (int32_t)a[0], r = (int32_t)a[1];
@@ -289,6 +293,7 @@ int rt_scene_set_mesh(rt_scene* s, const float* vertices, int32_t nv, const int3
         } else {
             const int32_t ts = (int32_t)a[8], te = (int32_t)a[9];
             if (ts < 0 || te < ts || te > nt) return rtb::fail(RT_ERR_INVALID, "rt_scene_set_mesh: leaf %d triangle range [%d,%d) invalid", k, ts, te);
+            max_leaf = std::max(max_leaf, te - ts);
         }
     }
     /* children have larger indices than their parent (pre-order), so one forward pass gives depths */
@@ -389,6 +394,7 @@ int rt_scene_set_mesh(rt_scene* s, const float* vertices, int32_t nv, const int3
     }
     child_ref(0, h.root_a, h.root_b);
     memcpy(h.box_abs, box_abs, sizeof box_abs);
+    s->max_leaf = max_leaf;
     h.off_nodes = off_nodes;
     h.off_tris = off_tris;
     h.off_nhat = off_nhat;
@@ -546,6 +552,7 @@ int rt_render(rt_scene* s, const rt_params* p, uint32_t flags, uint8_t* rgb_out,
     a.shadow = (uint8_t*)dev[4];
     a.counters = s->counters;
     a.gamma_tab = s->gamma_tab;
+    a.debug_cost = getenv("RT_DEBUG_COST") ? 1 : 0;
 
     int launches = 0;
     CUDA_TRY(cudaMemsetAsync(s->counters, 0, RT_NCOUNTERS * sizeof(unsigned long long), s->stream));
@@ -554,7 +561,26 @@ int rt_render(rt_scene* s, const rt_params* p, uint32_t flags, uint8_t* rgb_out,
         const int tiles_x = (p->W + 15) / 16, tiles_y = (rows + 7) / 8;
         const unsigned grid = (unsigned)tiles_x * (unsigned)tiles_y;
         const bool count = (flags & RT_RENDER_COUNT_WORK) != 0;
-        if (s->variant == 0) {
+        int variant = s->variant;
+        /* tie-break rank of render_wave: (n_tris - leaf_start) and the in-leaf offset share 32 bits */
+        int bits_n = 1;
+        while ((1ll << bits_n) <= (long long)h.n_tris) bits_n++;
+        a.rank_off_bits = std::min(32 - bits_n, 16);
+        if (variant == 2 && p->push_order == 0 && h.has_mesh && (long long)s->max_leaf > (1ll << a.rank_off_bits)) variant = 1;
+        if (variant == 2) {
+            if (s->wave_blocks_per_sm == 0) {
+                int nb = 0;
+                CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rtk::render_wave<false>, WV_THREADS, 0));
+                cudaDeviceProp prop;
+                CUDA_TRY(cudaGetDeviceProperties(&prop, s->device));
+                s->wave_blocks_per_sm = std::max(nb, 1);
+                s->sm_count = prop.multiProcessorCount;
+            }
+            const unsigned pgrid = std::min(grid, (unsigned)(s->sm_count * s->wave_blocks_per_sm));
+            int* tile_counter = reinterpret_cast<int*>(s->counters + 7);
+            if (count) rtk::render_wave<true><<<pgrid, WV_THREADS, 0, s->stream>>>(s->header, s->blob, a, tile_counter);
+            else rtk::render_wave<false><<<pgrid, WV_THREADS, 0, s->stream>>>(s->header, s->blob, a, tile_counter);
+        } else if (variant == 0) {
             if (count) rtk::render_mega<true, false><<<grid, 128, 0, s->stream>>>(s->header, s->blob, a);
             else rtk::render_mega<false, false><<<grid, 128, 0, s->stream>>>(s->header, s->blob, a);
         } else {

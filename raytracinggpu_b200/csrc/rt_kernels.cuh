@@ -32,6 +32,8 @@ struct RenderArgs {
     uint8_t* shadow;
     unsigned long long* counters; /* [0] rays, [1] inner-node visits, [2] triangle tests, [3] max stack, [4] slab exact fallbacks, [5] exact triangle evaluations */
     const float* gamma_tab;       /* 2 x 256 thresholds */
+    int32_t rank_off_bits;        /* render_wave: bits of the in-leaf offset in the tie-break rank (push_order 0) */
+    int32_t debug_cost;           /* investigation aid: with COUNT, hit_t <- thread clocks, hit_tri <- nodes+tris, hit_obj <- smid */
 };
 
 struct Work {
@@ -120,17 +122,29 @@ __device__ __forceinline__ bool tri_fast(const float4* __restrict__ rec, F3 O, F
  * wins a tie; with push_order 0 (cpu_launcher.cpp:291-292) in descending leaf order -> the largest leaf start
  * wins; inside a leaf the first (smallest) index wins either way. Applying that rule makes the outcome
  * independent of the order used here (left child first). */
-template <bool COUNT, bool FAST>
-__device__ __forceinline__ void mesh_closest(const SceneHeader& h, const float4* __restrict__ nodes, const float4* __restrict__ tris,
-                                             F3 O, F3 u, float eps_tri, int push_order, float& t_best, int& tri_best, Work& w) {
-    t_best = RTK_INF;
+/* The reference's shadow predicate (optimized.cu:618-620): the light is blocked iff the point the shadow ray's
+ * closest hit reconstructs, P' + t u, is not farther from P' than the light. */
+__device__ __forceinline__ bool blocks_light(F3 Padj, F3 su, float t, float D2) {
+    const F3 Ps = Padj + t * su;
+    return norm2(Ps - Padj) <= D2;
+}
+
+/* ANY = false: closest hit (t_best, tri_best). ANY = true: shadow query — returns as soon as one accepted
+ * triangle hit satisfies blocks_light; tri_best != -1 then means "blocked". This is the reference's outcome:
+ * f(t) = |fl(fl(P' + fl(t u)) - P')|^2 is non-decreasing in t (every rounding is monotone), so if any accepted
+ * hit has f(t) <= D2 the closest accepted hit, which the reference uses, has too; and if none has, neither has
+ * the closest. Children are visited nearest-first in ANY mode so blockers are found early. */
+template <bool COUNT, bool FAST, bool ANY>
+__device__ __forceinline__ void mesh_query(const SceneHeader& h, const float4* __restrict__ nodes, const float4* __restrict__ tris,
+                                           F3 O, F3 u, float eps_tri, int push_order, float D2, float t_limit, float& t_best, int& tri_best, Work& w) {
+    t_best = ANY ? t_limit : RTK_INF;
     tri_best = -1;
     int leaf_best = -1;
     RayCtx ctx;
-    float tn;
+    float tnL = 0.f, tnR = 0.f;
     if (FAST) {
         ctx = make_ray_ctx(O, u, h.box_abs[0], h.box_abs[1], h.box_abs[2]);
-        if (!slab_fast(h.root_mn[0], h.root_mn[1], h.root_mn[2], h.root_mx[0], h.root_mx[1], h.root_mx[2], ctx, tn, w.slab_fallbacks)) return;
+        if (!slab_fast(h.root_mn[0], h.root_mn[1], h.root_mn[2], h.root_mx[0], h.root_mx[1], h.root_mx[2], ctx, tnL, w.slab_fallbacks)) return;
     } else {
         if (!slab_exact(h.root_mn[0], h.root_mn[1], h.root_mn[2], h.root_mx[0], h.root_mx[1], h.root_mx[2], O, u)) return;
     }
@@ -145,22 +159,28 @@ __device__ __forceinline__ void mesh_closest(const SceneHeader& h, const float4*
             if (COUNT) w.nodes++;
             bool okL, okR;
             if (FAST) {
-                okL = slab_fast(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, ctx, tn, w.slab_fallbacks);
-                okR = slab_fast(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, ctx, tn, w.slab_fallbacks);
+                okL = slab_fast(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, ctx, tnL, w.slab_fallbacks);
+                okR = slab_fast(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, ctx, tnR, w.slab_fallbacks);
             } else {
                 okL = slab_exact(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, O, u);
                 okR = slab_exact(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, O, u);
             }
+            int2 cl = make_int2(q3.x, q3.y), cr = make_int2(q3.z, q3.w);
+            if (ANY && FAST && okL && okR && tnR < tnL) { /* nearest first; the order never changes the outcome */
+                const int2 s = cl;
+                cl = cr;
+                cr = s;
+            }
             if (okL) {
-                cur = make_int2(q3.x, q3.y);
+                cur = cl;
                 if (okR) {
-                    stack[sp++] = make_int2(q3.z, q3.w);
+                    stack[sp++] = cr;
                     if (COUNT) w.max_stack = max(w.max_stack, (unsigned)sp);
                 }
                 continue;
             }
             if (okR) {
-                cur = make_int2(q3.z, q3.w);
+                cur = cr;
                 continue;
             }
         } else {
@@ -173,6 +193,13 @@ __device__ __forceinline__ void mesh_closest(const SceneHeader& h, const float4*
                     if (!tri_exact(tris + 3 * (size_t)i, O, u, t)) continue;
                 }
                 if (!(t > eps_tri)) continue; /* optimized.cu:275 / cpu_launcher.cpp:301 */
+                if (ANY) {
+                    if (blocks_light(O, u, t, D2)) {
+                        tri_best = i;
+                        return;
+                    }
+                    continue;
+                }
                 const bool tie = (tri_best >= 0) && (t == t_best) && (leaf_best != cur.x) && (push_order == 1 ? (cur.x < leaf_best) : (cur.x > leaf_best));
                 if (t < t_best || tie) {
                     t_best = t;
@@ -214,7 +241,7 @@ __device__ __forceinline__ SurfaceHit intersect_all(const SceneHeader& h, const 
     if (h.has_mesh) {
         float tm;
         int tri;
-        mesh_closest<COUNT, FAST>(h, nodes, tris, O, u, eps_tri, push_order, tm, tri, w);
+        mesh_query<COUNT, FAST, false>(h, nodes, tris, O, u, eps_tri, push_order, 0.f, 0.f, tm, tri, w);
         if (tri >= 0 && (tm < r.t || (tm == r.t && h.mesh_id < r.obj))) {
             r.t = tm;
             r.obj = h.mesh_id;
@@ -223,6 +250,27 @@ __device__ __forceinline__ SurfaceHit intersect_all(const SceneHeader& h, const 
         }
     }
     return r;
+}
+
+/* Is the light blocked for the shadow ray (Padj, su)? The reference runs a full closest-hit intersect_all and
+ * applies blocks_light to its result (optimized.cu:618-620). By the monotonicity argument at mesh_query this
+ * equals "some object's reported hit satisfies blocks_light", which lets the spheres be checked first and the
+ * mesh be left as soon as one blocker is found. */
+template <bool COUNT, bool FAST>
+__device__ __forceinline__ bool light_blocked(const SceneHeader& h, const float4* __restrict__ nodes, const float4* __restrict__ tris,
+                                              F3 Padj, F3 su, float D2, float eps_tri, int push_order, Work& w) {
+    w.rays++;
+    for (int k = 0; k < h.n_spheres; k++) {
+        float t;
+        if (sphere_t(h.spheres[k], Padj, su, t) && t < RTK_INF && blocks_light(Padj, su, t, D2)) return true;
+    }
+    if (!h.has_mesh) return false;
+    /* |t su| ~ t: a hit with t > 1.001 sqrt(D2) cannot satisfy the predicate, the certified triangle test may drop it */
+    const float t_limit = sqrtf(D2) * 1.001f + 1e-3f;
+    float tm;
+    int tri;
+    mesh_query<COUNT, FAST, true>(h, nodes, tris, Padj, su, eps_tri, push_order, D2, t_limit, tm, tri, w);
+    return tri >= 0;
 }
 
 template <bool COUNT, bool FAST>
@@ -243,6 +291,7 @@ __global__ void __launch_bounds__(128) render_mega(const __grid_constant__ Scene
     const int k = tile_y * 8 + (warp >> 1) * 4 + (lane >> 3);
     const bool live = j < a.W && k < a.rows;
 
+    const long long clk0 = clock64();
     Work w;
     w.rays = w.nodes = w.tris = w.max_stack = w.slab_fallbacks = w.tri_exact = 0;
     if (live) {
@@ -318,9 +367,14 @@ __global__ void __launch_bounds__(128) render_mega(const __grid_constant__ Scene
                 const F3 Padj = P + eps * N;
                 const F3 toL = Lp - Padj;
                 const F3 su = toL / sqrtf(norm2(toL)); /* NORMED_VEC :618 */
-                const SurfaceHit sh = intersect_all<COUNT, FAST>(h, nodes, tris, Padj, su, a.eps_tri, a.push_order, w);
-                const F3 Ps = Padj + sh.t * su; /* on a miss t = 1e9f, as the reference leaves it */
-                if (norm2(Ps - Padj) <= norm2(toL)) { /* :620 */
+                bool blocked;
+                if (FAST) {
+                    blocked = light_blocked<COUNT, FAST>(h, nodes, tris, Padj, su, norm2(toL), a.eps_tri, a.push_order, w);
+                } else { /* literal reference: closest hit, then the predicate */
+                    const SurfaceHit sh = intersect_all<COUNT, FAST>(h, nodes, tris, Padj, su, a.eps_tri, a.push_order, w);
+                    blocked = blocks_light(Padj, su, sh.t, norm2(toL)); /* on a miss t = 1e9f, as the reference leaves it */
+                }
+                if (blocked) { /* :620 */
                     shadow = 1;
                 } else {
                     shadow = 0;
@@ -350,6 +404,13 @@ __global__ void __launch_bounds__(128) render_mega(const __grid_constant__ Scene
         if (a.hit_tri) a.hit_tri[px] = first_tri;
         if (a.hit_t) a.hit_t[px] = first_t;
         if (a.shadow) a.shadow[px] = (uint8_t)shadow;
+        if (COUNT && a.debug_cost) {
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            if (a.hit_t) a.hit_t[px] = (float)(clock64() - clk0);
+            if (a.hit_tri) a.hit_tri[px] = (int)(w.nodes + w.tris);
+            if (a.hit_obj) a.hit_obj[px] = (int)smid;
+        }
     }
 
     /* ray / work counters: one atomic per warp */

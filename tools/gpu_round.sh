@@ -7,7 +7,7 @@ OUT=gpurun_out/$TAG
 mkdir -p $OUT
 nvidia-smi --query-gpu=name,driver_version,clocks.max.sm,memory.total --format=csv > $OUT/gpu.txt 2>&1
 lscpu | grep -E "Model name|^CPU\(s\)|Thread|Socket" > $OUT/cpu.txt 2>&1
-echo "== pytest -m gpu"; timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -25 | tee $OUT/pytest_gpu.log
+echo "== pytest -m gpu"; timeout 600 python -m pytest tests -m gpu -q -x 2>&1 | tail -25 | tee $OUT/pytest_gpu.log
 echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -5 | tee $OUT/smoke.log
 for V in ${VARIANTS:-0 1}; do
   echo "== bench variant $V"; RT_VARIANT=$V timeout 900 python bench.py --steps 30 --warmup 5 > $OUT/bench_v$V.json 2> $OUT/bench_v$V.err; echo "bench exit $?"
