@@ -576,7 +576,8 @@ int rt_render(rt_scene* s, const rt_params* p, uint32_t flags, uint8_t* rgb_out,
                 s->wave_blocks_per_sm = std::max(nb, 1);
                 s->sm_count = prop.multiProcessorCount;
             }
-            const unsigned pgrid = std::min(grid, (unsigned)(s->sm_count * s->wave_blocks_per_sm));
+            const unsigned wtiles = (unsigned)((p->W + WV_TILE_W - 1) / WV_TILE_W) * (unsigned)((rows + WV_TILE_H - 1) / WV_TILE_H);
+            const unsigned pgrid = std::min(wtiles, (unsigned)(s->sm_count * s->wave_blocks_per_sm));
             int* tile_counter = reinterpret_cast<int*>(s->counters + 7);
             if (count) rtk::render_wave<true><<<pgrid, WV_THREADS, 0, s->stream>>>(s->header, s->blob, a, tile_counter);
             else rtk::render_wave<false><<<pgrid, WV_THREADS, 0, s->stream>>>(s->header, s->blob, a, tile_counter);

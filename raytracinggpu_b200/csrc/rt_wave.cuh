@@ -9,8 +9,9 @@
  * boxes and triangles a ray must test (no pruning: the winner is the strictly smallest computed t, and the
  * computed t of a grazing triangle is not bounded by its box), but not WHO tests them nor in which order. So:
  *
- *   - a block owns a 16x8 pixel tile at a time (tiles are handed out by an atomic counter: persistent
- *     blocks, natural load balance across the 148 SMs);
+ *   - a block owns an 8x4 pixel tile at a time (tiles are handed out by an atomic counter: persistent
+ *     blocks, natural load balance across the 148 SMs); warp 0 owns the 32 pixels, all four warps traverse, so
+ *     a heavy tile gets four lanes per pixel;
  *   - per round every pixel's owner thread does the cheap, uniform part of the path (ray generation,
  *     six sphere tests, root-box test, shading; optimized.cu:746-760, 539-559, 561-661) and, if its ray
  *     enters the mesh's root box, posts a query into the tile's shared-memory queue;
@@ -31,8 +32,10 @@
 namespace rtk {
 
 #define WV_THREADS 128
-#define WV_TILE_W 16
-#define WV_TILE_H 8
+#define WV_WARPS (WV_THREADS / 32)
+#define WV_TILE_W 8
+#define WV_TILE_H 4
+#define WV_TILE_PIX 32 /* one owner warp per tile; all WV_WARPS warps drain its queue (4 lanes per pixel) */
 #define WV_NOHIT 0xffffffffffffffffull
 
 enum { WV_DONE = 0, WV_TRACE = 1, WV_WAIT_HIT = 2, WV_WAIT_SHADOW = 3 };
@@ -41,14 +44,14 @@ enum { WV_Q_CLOSEST = 1, WV_Q_ANY = 2 };
 struct WaveSmem {
     float gamma[256];
     /* the pixel's current ray; it doubles as the query ray of slot == owner thread */
-    float ox[WV_THREADS], oy[WV_THREADS], oz[WV_THREADS];
-    float ux[WV_THREADS], uy[WV_THREADS], uz[WV_THREADS];
-    float ts[WV_THREADS];                 /* closest sphere t of the current segment */
-    float d2[WV_THREADS];                 /* shadow queries: |L - P'|^2 */
-    unsigned long long res[WV_THREADS];   /* closest: (t bits << 32) | rank, WV_NOHIT if none; any: 1 = blocked */
-    int sidx[WV_THREADS];
-    int queue[WV_THREADS];
-    unsigned char qmode[WV_THREADS];
+    float ox[WV_TILE_PIX], oy[WV_TILE_PIX], oz[WV_TILE_PIX];
+    float ux[WV_TILE_PIX], uy[WV_TILE_PIX], uz[WV_TILE_PIX];
+    float ts[WV_TILE_PIX];                 /* closest sphere t of the current segment */
+    float d2[WV_TILE_PIX];                 /* shadow queries: |L - P'|^2 */
+    unsigned long long res[WV_TILE_PIX];   /* closest: (t bits << 32) | rank, WV_NOHIT if none; any: 1 = blocked */
+    int sidx[WV_TILE_PIX];
+    int queue[WV_TILE_PIX];
+    unsigned char qmode[WV_TILE_PIX];
     int q_count, q_head, tile;
 };
 
@@ -121,6 +124,7 @@ __device__ __forceinline__ void drain_queue(const SceneHeader& h, const float4* 
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
     const int qn = sm.q_count;
+    const int share = max(1, (qn + WV_WARPS - 1) / WV_WARPS);
     const int2 root = make_int2(h.root_a, h.root_b);
     LaneTask k;
     k.busy = false;
@@ -135,12 +139,15 @@ __device__ __forceinline__ void drain_queue(const SceneHeader& h, const float4* 
         /* ---- work distribution ---------------------------------------------------------------------------- */
         const unsigned idle = __ballot_sync(FULL, !k.busy);
         if (idle) {
+            /* a warp takes its share of the queue, not all of it: the other warps of the block drain the same tile */
+            const int take = min(__popc(idle), share);
             int base = qn;
-            if (lane == 0 && *((volatile int*)&sm.q_head) < qn) base = atomicAdd(&sm.q_head, __popc(idle));
+            if (lane == 0 && *((volatile int*)&sm.q_head) < qn) base = atomicAdd(&sm.q_head, take);
             base = __shfl_sync(FULL, base, 0);
             if (!k.busy) {
-                const int my = base + __popc(idle & lt_mask);
-                if (my < qn) task_begin(k, sm, h, sm.queue[my], root);
+                const int r = __popc(idle & lt_mask);
+                const int my = base + r;
+                if (r < take && my < qn) task_begin(k, sm, h, sm.queue[my], root);
             }
             /* queue empty: idle lanes take a pending subtree from busy lanes of this warp */
             const unsigned thieves = __ballot_sync(FULL, !k.busy);
@@ -267,9 +274,9 @@ __global__ void __launch_bounds__(WV_THREADS) render_wave(const __grid_constant_
         const int tile = sm.tile;
         if (tile >= n_tiles) break;
         const int tile_x = tile % tiles_x, tile_y = tile / tiles_x;
-        const int j = tile_x * WV_TILE_W + (warp & 1) * 8 + (lane & 7);
-        const int kr = tile_y * WV_TILE_H + (warp >> 1) * 4 + (lane >> 3);
-        const bool live = j < a.W && kr < a.rows;
+        const int j = tile_x * WV_TILE_W + (lane & 7);
+        const int kr = tile_y * WV_TILE_H + (lane >> 3);
+        const bool live = warp == 0 && j < a.W && kr < a.rows; /* warp 0 owns the tile's 32 pixels */
         const size_t px = (size_t)kr * a.W + j;
 
         /* per-pixel path state (registers of the owner) */
@@ -475,7 +482,7 @@ __global__ void __launch_bounds__(WV_THREADS) render_wave(const __grid_constant_
         if (live) {
             F3 total = f3(0.f, 0.f, 0.f);
             for (int s = 0; s < a.num_rays; s++) total = total + color;
-            const F3 avg = total / (float)a.num_rays;
+            const F3 avg = a.num_rays == 1 ? total : total / (float)a.num_rays; /* x / 1.0f == x */
             if (a.rgb) {
                 a.rgb[px * 3 + 0] = (uint8_t)quantise(avg.x, sm.gamma);
                 a.rgb[px * 3 + 1] = (uint8_t)quantise(avg.y, sm.gamma);
