@@ -10,7 +10,7 @@
 #include "host_common.h"
 #include "rt_kernels.cuh"
 #include "rt_layout.h"
-#include "rt_wave.cuh"
+#include "rt_wavefront.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -50,10 +50,16 @@ struct rt_scene {
     int pending_launches = 0;
 
     /* kernel variant: 0 = render_mega, plain exact arithmetic; 1 = render_mega with the certified fast paths;
-     * 2 = render_wave (persistent blocks + ray queue + work stealing). Same results. RT_VARIANT overrides. */
+     * 2 = wavefront pipeline (rt_wavefront.cuh: streaming owner kernels + persistent queue traversal with work
+     * stealing). Same results. RT_VARIANT overrides. */
     int variant = 2;
     int max_leaf = 0;        /* largest leaf of the uploaded BVH */
-    int wave_blocks_per_sm = 0, sm_count = 0;
+    int trav_blocks_per_sm = 0, sm_count = 0;
+    rtk::QEntry* wf_queue = nullptr; /* 3 queues of wf_capacity entries: closest even / closest odd / shadow */
+    size_t wf_capacity = 0;
+    rtk::WfCounters* wf_counters = nullptr;
+    rtk::WfCounters* h_wf_counters = nullptr; /* pinned */
+    bool last_was_wavefront = false;
 };
 
 namespace {
@@ -201,6 +207,9 @@ void rt_scene_destroy(rt_scene* s) {
     if (s->gamma_tab) cudaFree(s->gamma_tab);
     if (s->counters) cudaFree(s->counters);
     if (s->h_counters) cudaFreeHost(s->h_counters);
+    if (s->wf_queue) cudaFree(s->wf_queue);
+    if (s->wf_counters) cudaFree(s->wf_counters);
+    if (s->h_wf_counters) cudaFreeHost(s->h_wf_counters);
     for (int k = 0; k < 5; k++)
         if (s->scratch[k]) cudaFree(s->scratch[k]);
     if (s->ev0) cudaEventDestroy(s->ev0);
@@ -452,7 +461,12 @@ int rt_scene_blob_import(rt_scene* s, const void* device_ptr, size_t bytes) {
 int rt_scene_sync(rt_scene* s, rt_stats* stats) {
     if (!s) return rtb::fail(RT_ERR_INVALID, "rt_scene_sync: NULL scene");
     DeviceGuard g(s->device);
-    if (s->pending) CUDA_TRY(cudaMemcpyAsync(s->h_counters, s->counters, RT_NCOUNTERS * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->stream));
+    if (s->pending) {
+        if (s->last_was_wavefront)
+            CUDA_TRY(cudaMemcpyAsync(s->h_counters, s->wf_counters->stats, RT_NCOUNTERS * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->stream));
+        else
+            CUDA_TRY(cudaMemcpyAsync(s->h_counters, s->counters, RT_NCOUNTERS * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->stream));
+    }
     CUDA_TRY(cudaStreamSynchronize(s->stream));
     if (stats) {
         memset(stats, 0, sizeof *stats);
@@ -555,8 +569,7 @@ int rt_render(rt_scene* s, const rt_params* p, uint32_t flags, uint8_t* rgb_out,
     a.debug_cost = getenv("RT_DEBUG_COST") ? 1 : 0;
 
     int launches = 0;
-    CUDA_TRY(cudaMemsetAsync(s->counters, 0, RT_NCOUNTERS * sizeof(unsigned long long), s->stream));
-    CUDA_TRY(cudaEventRecord(s->ev0, s->stream));
+    CUDA_TRY(cudaEventRecord(s->ev0, s->stream)); /* kernel_ms covers everything a frame enqueues, counter resets included */
     {
         const int tiles_x = (p->W + 15) / 16, tiles_y = (rows + 7) / 8;
         const unsigned grid = (unsigned)tiles_x * (unsigned)tiles_y;
@@ -567,24 +580,59 @@ int rt_render(rt_scene* s, const rt_params* p, uint32_t flags, uint8_t* rgb_out,
         while ((1ll << bits_n) <= (long long)h.n_tris) bits_n++;
         a.rank_off_bits = std::min(32 - bits_n, 16);
         if (variant == 2 && p->push_order == 0 && h.has_mesh && (long long)s->max_leaf > (1ll << a.rank_off_bits)) variant = 1;
+        const int segments = a.segments;
+        if (variant == 2 && segments > WF_MAX_ROUNDS - 1) variant = 1;
+        s->last_was_wavefront = (variant == 2);
         if (variant == 2) {
-            if (s->wave_blocks_per_sm == 0) {
+            if (s->trav_blocks_per_sm == 0) {
                 int nb = 0;
-                CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rtk::render_wave<false>, WV_THREADS, 0));
+                CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rtk::wf_traverse<false>, WF_THREADS, 0));
                 cudaDeviceProp prop;
                 CUDA_TRY(cudaGetDeviceProperties(&prop, s->device));
-                s->wave_blocks_per_sm = std::max(nb, 1);
+                s->trav_blocks_per_sm = std::max(nb, 1);
                 s->sm_count = prop.multiProcessorCount;
+                CUDA_TRY(cudaMalloc(&s->wf_counters, sizeof(rtk::WfCounters)));
+                CUDA_TRY(cudaMallocHost(&s->h_wf_counters, sizeof(rtk::WfCounters)));
             }
-            const unsigned wtiles = (unsigned)((p->W + WV_TILE_W - 1) / WV_TILE_W) * (unsigned)((rows + WV_TILE_H - 1) / WV_TILE_H);
-            const unsigned pgrid = std::min(wtiles, (unsigned)(s->sm_count * s->wave_blocks_per_sm));
-            int* tile_counter = reinterpret_cast<int*>(s->counters + 7);
-            if (count) rtk::render_wave<true><<<pgrid, WV_THREADS, 0, s->stream>>>(s->header, s->blob, a, tile_counter);
-            else rtk::render_wave<false><<<pgrid, WV_THREADS, 0, s->stream>>>(s->header, s->blob, a, tile_counter);
+            if (s->wf_capacity < npx) {
+                if (s->wf_queue) cudaFree(s->wf_queue);
+                s->wf_queue = nullptr;
+                s->wf_capacity = 0;
+                CUDA_TRY(cudaMalloc(&s->wf_queue, 3 * npx * sizeof(rtk::QEntry)));
+                s->wf_capacity = npx;
+            }
+            rtk::WfArgs g;
+            g.a = a;
+            g.qA[0] = s->wf_queue;
+            g.qA[1] = s->wf_queue + s->wf_capacity;
+            g.qS = s->wf_queue + 2 * s->wf_capacity;
+            g.c = s->wf_counters;
+            g.round = 0;
+            CUDA_TRY(cudaMemsetAsync(s->wf_counters, 0, sizeof(rtk::WfCounters), s->stream));
+            const unsigned wtiles = (unsigned)((p->W + 7) / 8) * (unsigned)((rows + 3) / 4);
+            const unsigned gen_grid = (wtiles + (WF_THREADS / 32) - 1) / (WF_THREADS / 32);
+            const unsigned pers_grid = (unsigned)(s->sm_count * s->trav_blocks_per_sm);
+            const unsigned shade_grid = (unsigned)std::min<size_t>((npx + WF_THREADS - 1) / WF_THREADS, (size_t)s->sm_count * 16);
+            if (count) rtk::wf_generate<true><<<gen_grid, WF_THREADS, 0, s->stream>>>(s->header, s->blob, g);
+            else rtk::wf_generate<false><<<gen_grid, WF_THREADS, 0, s->stream>>>(s->header, s->blob, g);
+            launches++;
+            for (int r = 0; r <= segments && segments > 0; r++) {
+                g.round = r;
+                if (count) rtk::wf_traverse<true><<<pers_grid, WF_THREADS, 0, s->stream>>>(s->header, s->blob, g);
+                else rtk::wf_traverse<false><<<pers_grid, WF_THREADS, 0, s->stream>>>(s->header, s->blob, g);
+                launches++;
+                if (r == segments) break;
+                if (count) rtk::wf_shade<true><<<shade_grid, WF_THREADS, 0, s->stream>>>(s->header, s->blob, g);
+                else rtk::wf_shade<false><<<shade_grid, WF_THREADS, 0, s->stream>>>(s->header, s->blob, g);
+                launches++;
+            }
+            launches--; /* the common launches++ below counts one */
         } else if (variant == 0) {
+            CUDA_TRY(cudaMemsetAsync(s->counters, 0, RT_NCOUNTERS * sizeof(unsigned long long), s->stream));
             if (count) rtk::render_mega<true, false><<<grid, 128, 0, s->stream>>>(s->header, s->blob, a);
             else rtk::render_mega<false, false><<<grid, 128, 0, s->stream>>>(s->header, s->blob, a);
         } else {
+            CUDA_TRY(cudaMemsetAsync(s->counters, 0, RT_NCOUNTERS * sizeof(unsigned long long), s->stream));
             if (count) rtk::render_mega<true, true><<<grid, 128, 0, s->stream>>>(s->header, s->blob, a);
             else rtk::render_mega<false, true><<<grid, 128, 0, s->stream>>>(s->header, s->blob, a);
         }
