@@ -16,6 +16,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <new>
 #include <vector>
 
@@ -55,6 +56,7 @@ struct rt_scene {
     int variant = 2;
     int max_leaf = 0;        /* largest leaf of the uploaded BVH */
     int trav_blocks_per_sm = 0, sm_count = 0;
+    size_t trav_smem = 0;
     rtk::QEntry* wf_queue = nullptr; /* 3 queues of wf_capacity entries: closest even / closest odd / shadow */
     size_t wf_capacity = 0;
     rtk::WfCounters* wf_counters = nullptr;
@@ -122,7 +124,7 @@ int upload_header(rt_scene* s) {
         /* spheres-only scene: the blob is just the header */
         CUDA_TRY(cudaMalloc(&s->blob, RT_HEADER_BYTES));
         s->blob_bytes = RT_HEADER_BYTES;
-        s->header.off_nodes = s->header.off_tris = s->header.off_nhat = RT_HEADER_BYTES;
+        s->header.off_nodes = s->header.off_leaves = s->header.off_tris = s->header.off_nhat = RT_HEADER_BYTES;
         s->header.total_bytes = RT_HEADER_BYTES;
     }
     CUDA_TRY(cudaMemcpyAsync(s->blob, &s->header, sizeof(SceneHeader), cudaMemcpyHostToDevice, s->stream));
@@ -135,8 +137,8 @@ void reset_mesh_fields(SceneHeader& h) {
     h.n_inner = 0;
     h.n_tris = 0;
     h.max_depth = 0;
-    h.root_a = 0;
-    h.root_b = 0;
+    h.root_ref = 0;
+    h.n_leaves = 0;
     for (int k = 0; k < 3; k++) {
         h.root_mn[k] = 0.f;
         h.root_mx[k] = 0.f;
@@ -327,36 +329,71 @@ int rt_scene_set_mesh(rt_scene* s, const float* vertices, int32_t nv, const int3
         const float* a = arr_bvh + (size_t)k * RT_BVH_NODE_FLOATS;
         for (int c = 0; c < 3; c++) box_abs[c] = std::max(box_abs[c], std::max(std::fabs(a[2 + c]), std::fabs(a[5 + c])));
     }
-    auto child_ref = [&](int32_t node, int32_t& a_out, int32_t& b_out) {
-        const float* a = arr_bvh + (size_t)node * RT_BVH_NODE_FLOATS;
-        if ((int32_t)a[0] != -1) {
-            a_out = inner_index[node];
-            b_out = -1;
-        } else {
-            a_out = (int32_t)a[8];
-            b_out = (int32_t)a[9];
-        }
-    };
+    /* packed tree: 64-B records (two child boxes + two int references), a leaf table with at most RT_LEAF_MAX
+     * triangles per entry; larger reference leaves hang under virtual nodes that repeat the leaf's own box */
     std::vector<float> packed((size_t)std::max(n_inner, 1) * 16);
+    std::vector<int32_t> leaves; /* pairs: first triangle, count | reference leaf start << 8 */
+    int32_t extra_levels = 0;
+    auto new_leaf = [&](int32_t start, int32_t count, int32_t orig_start) -> int32_t {
+        leaves.push_back(start);
+        leaves.push_back((int32_t)(((uint32_t)orig_start << 8) | (uint32_t)count));
+        return -1 - (int32_t)(leaves.size() / 2 - 1);
+    };
+    /* reference of the subtree holding chunks [lo, hi) of the reference leaf [ts, te) with box `bb` (6 floats) */
+    std::function<int32_t(int32_t, int32_t, int32_t, int32_t, const float*, int32_t)> chunk_tree =
+        [&](int32_t lo, int32_t hi, int32_t ts, int32_t te, const float* bb, int32_t level) -> int32_t {
+        if (hi - lo == 1) {
+            const int32_t st = ts + lo * RT_LEAF_MAX;
+            return new_leaf(st, std::min(RT_LEAF_MAX, te - st), ts);
+        }
+        extra_levels = std::max(extra_levels, level);
+        const int32_t idx = (int32_t)(packed.size() / 16);
+        packed.resize(packed.size() + 16);
+        const int32_t mid = lo + (hi - lo + 1) / 2;
+        const int32_t l = chunk_tree(lo, mid, ts, te, bb, level + 1);
+        const int32_t r = chunk_tree(mid, hi, ts, te, bb, level + 1);
+        float* o = &packed[(size_t)idx * 16];
+        for (int c = 0; c < 6; c++) {
+            o[c] = bb[c];
+            o[6 + c] = bb[c];
+        }
+        const int32_t refs[4] = {l, r, 1 /* virtual: not a node of the reference BVH */, 0};
+        memcpy(o + 12, refs, sizeof refs);
+        return idx;
+    };
+    auto child_ref = [&](int32_t node) -> int32_t {
+        const float* a = arr_bvh + (size_t)node * RT_BVH_NODE_FLOATS;
+        if ((int32_t)a[0] != -1) return inner_index[node];
+        const int32_t ts = (int32_t)a[8], te = (int32_t)a[9];
+        const int32_t chunks = std::max(1, (te - ts + RT_LEAF_MAX - 1) / RT_LEAF_MAX);
+        return chunk_tree(0, chunks, ts, te, a + 2, 1);
+    };
     for (int32_t k = 0; k < n_nodes; k++) {
         if (inner_index[k] < 0) continue;
         const float* a = arr_bvh + (size_t)k * RT_BVH_NODE_FLOATS;
         const float* L = arr_bvh + (size_t)(int32_t)a[0] * RT_BVH_NODE_FLOATS;
         const float* R = arr_bvh + (size_t)(int32_t)a[1] * RT_BVH_NODE_FLOATS;
+        const int32_t rl = child_ref((int32_t)a[0]), rr = child_ref((int32_t)a[1]); /* may grow `packed` */
         float* o = &packed[(size_t)inner_index[k] * 16];
         for (int c = 0; c < 6; c++) {
             o[c] = L[2 + c];
             o[6 + c] = R[2 + c];
         }
-        int32_t refs[4];
-        child_ref((int32_t)a[0], refs[0], refs[1]);
-        child_ref((int32_t)a[1], refs[2], refs[3]);
+        const int32_t refs[4] = {rl, rr, 0, 0};
         memcpy(o + 12, refs, sizeof refs);
     }
+    const int32_t root_ref = child_ref(0);
+    n_inner = (int32_t)(packed.size() / 16);
+    if (inner_index[0] < 0 && n_inner == 1 && root_ref < 0) n_inner = 0; /* the root is a small leaf: no node records */
+    const int32_t n_leaves = (int32_t)(leaves.size() / 2);
+    max_depth += extra_levels;
+    if (max_depth > RT_STACK_CAP - 2)
+        return rtb::fail(RT_ERR_UNSUPPORTED, "rt_scene_set_mesh: packed BVH depth %d exceeds the traversal stack (%d)", max_depth, RT_STACK_CAP - 2);
 
     /* ---- blob ------------------------------------------------------------------------------------------ */
     const size_t off_nodes = RT_HEADER_BYTES;
-    const size_t off_tris = off_nodes + (size_t)n_inner * RT_NODE_BYTES;
+    const size_t off_leaves = off_nodes + (size_t)n_inner * RT_NODE_BYTES;
+    const size_t off_tris = (off_leaves + (size_t)n_leaves * RT_LEAF_BYTES + 15) & ~(size_t)15;
     const size_t off_nhat = off_tris + (size_t)nt * RT_TRI_BYTES;
     const size_t total = off_nhat + (size_t)nt * RT_NHAT_BYTES;
     CUDA_TRY(cudaStreamSynchronize(s->stream));
@@ -377,6 +414,8 @@ int rt_scene_set_mesh(rt_scene* s, const float* vertices, int32_t nv, const int3
     if (err == cudaSuccess) err = cudaMemcpyAsync(d_recs, tri_records, rbytes, cudaMemcpyHostToDevice, s->stream);
     if (err == cudaSuccess && n_inner > 0)
         err = cudaMemcpyAsync(s->blob + off_nodes, packed.data(), (size_t)n_inner * RT_NODE_BYTES, cudaMemcpyHostToDevice, s->stream);
+    if (err == cudaSuccess && n_leaves > 0)
+        err = cudaMemcpyAsync(s->blob + off_leaves, leaves.data(), (size_t)n_leaves * RT_LEAF_BYTES, cudaMemcpyHostToDevice, s->stream);
     if (err == cudaSuccess) {
         const int threads = 256, blocks = (nt + threads - 1) / threads;
         rtk::repack_triangles<<<blocks, threads, 0, s->stream>>>(d_vertices, d_recs, nt, reinterpret_cast<float4*>(s->blob + off_tris),
@@ -390,6 +429,7 @@ int rt_scene_set_mesh(rt_scene* s, const float* vertices, int32_t nv, const int3
 
     h.has_mesh = 1;
     h.n_inner = n_inner;
+    h.n_leaves = n_leaves;
     h.n_tris = nt;
     h.max_depth = max_depth;
     h.mesh_id = id;
@@ -401,10 +441,11 @@ int rt_scene_set_mesh(rt_scene* s, const float* vertices, int32_t nv, const int3
         h.root_mn[c] = arr_bvh[2 + c];
         h.root_mx[c] = arr_bvh[5 + c];
     }
-    child_ref(0, h.root_a, h.root_b);
+    h.root_ref = root_ref;
     memcpy(h.box_abs, box_abs, sizeof box_abs);
     s->max_leaf = max_leaf;
     h.off_nodes = off_nodes;
+    h.off_leaves = off_leaves;
     h.off_tris = off_tris;
     h.off_nhat = off_nhat;
     h.total_bytes = total;
@@ -483,7 +524,15 @@ int rt_scene_sync(rt_scene* s, rt_stats* stats) {
             stats->launches = s->pending_launches;
         }
     }
+    const bool failed = s->pending && s->last_was_wavefront && s->h_counters[7] != 0;
+    if (s->pending && s->last_was_wavefront && getenv("RT_DEBUG_POOL")) {
+        unsigned long long d[8];
+        cudaMemcpy(d, s->wf_counters->dbg, sizeof d, cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[pool] N steps %llu tasks %llu (%.1f/step)  T steps %llu tasks %llu (%.1f/step)  admissions %llu\n", d[0], d[1],
+                d[0] ? (double)d[1] / d[0] : 0., d[2], d[3], d[2] ? (double)d[3] / d[2] : 0., d[4]);
+    }
     s->pending = false;
+    if (failed) return rtb::fail(RT_ERR_STATE, "rt_render: traversal task pool overflow (BVH deeper than the upload-time bound)");
     return RT_OK;
 }
 
@@ -519,9 +568,12 @@ int rt_render(rt_scene* s, const rt_params* p, uint32_t flags, uint8_t* rgb_out,
     if (!g.ok) return rtb::fail(RT_ERR_CUDA, "rt_render: cudaSetDevice failed");
     /* a still-pending RT_RENDER_NO_SYNC call needs no wait: counters, scratch buffers and events are reused in
      * stream order, and the stats of the older call are simply superseded */
-    if (s->header_dirty || !s->blob) {
+    /* the kernels take the header by value from the host copy: a changed light or sphere set needs no upload here
+     * (the device copy inside the blob is refreshed by rt_scene_blob_export, its only reader) */
+    if (!s->blob) {
         int rc = upload_header(s);
         if (rc != RT_OK) return rc;
+        s->header_dirty = true;
     }
 
     const size_t npx = (size_t)rows * p->W;
@@ -584,15 +636,25 @@ int rt_render(rt_scene* s, const rt_params* p, uint32_t flags, uint8_t* rgb_out,
         if (variant == 2 && segments > WF_MAX_ROUNDS - 1) variant = 1;
         s->last_was_wavefront = (variant == 2);
         if (variant == 2) {
-            if (s->trav_blocks_per_sm == 0) {
+            /* node pool of wf_traverse: 32 lanes x (levels of the packed tree + roots of two batches + slack) */
+            const int npool_cap = 32 * (h.max_depth + 4);
+            const size_t warp_bytes = (sizeof(rtk::WfWarpSmem) + (size_t)npool_cap * sizeof(int) + 15) & ~(size_t)15;
+            const size_t trav_smem = warp_bytes * (WF_THREADS / 32);
+            if (trav_smem > 200 * 1024) return rtb::fail(RT_ERR_UNSUPPORTED, "rt_render: BVH depth %d needs %zu B of shared memory per block", h.max_depth, trav_smem);
+            if (s->trav_blocks_per_sm == 0 || s->trav_smem != trav_smem) {
                 int nb = 0;
-                CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rtk::wf_traverse<false>, WF_THREADS, 0));
+                CUDA_TRY(cudaFuncSetAttribute(rtk::wf_traverse<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trav_smem));
+                CUDA_TRY(cudaFuncSetAttribute(rtk::wf_traverse<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trav_smem));
+                CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rtk::wf_traverse<false>, WF_THREADS, trav_smem));
                 cudaDeviceProp prop;
                 CUDA_TRY(cudaGetDeviceProperties(&prop, s->device));
                 s->trav_blocks_per_sm = std::max(nb, 1);
+                s->trav_smem = trav_smem;
                 s->sm_count = prop.multiProcessorCount;
-                CUDA_TRY(cudaMalloc(&s->wf_counters, sizeof(rtk::WfCounters)));
-                CUDA_TRY(cudaMallocHost(&s->h_wf_counters, sizeof(rtk::WfCounters)));
+                if (!s->wf_counters) {
+                    CUDA_TRY(cudaMalloc(&s->wf_counters, sizeof(rtk::WfCounters)));
+                    CUDA_TRY(cudaMallocHost(&s->h_wf_counters, sizeof(rtk::WfCounters)));
+                }
             }
             if (s->wf_capacity < npx) {
                 if (s->wf_queue) cudaFree(s->wf_queue);
@@ -613,18 +675,42 @@ int rt_render(rt_scene* s, const rt_params* p, uint32_t flags, uint8_t* rgb_out,
             const unsigned gen_grid = (wtiles + (WF_THREADS / 32) - 1) / (WF_THREADS / 32);
             const unsigned pers_grid = (unsigned)(s->sm_count * s->trav_blocks_per_sm);
             const unsigned shade_grid = (unsigned)std::min<size_t>((npx + WF_THREADS - 1) / WF_THREADS, (size_t)s->sm_count * 16);
+            static const bool dbg_times = getenv("RT_DEBUG_TIMES") != nullptr;
+            cudaEvent_t dev_ev[40];
+            int n_ev = 0;
+            auto mark = [&]() {
+                if (dbg_times && n_ev < 40) {
+                    cudaEventCreate(&dev_ev[n_ev]);
+                    cudaEventRecord(dev_ev[n_ev++], s->stream);
+                }
+            };
+            mark();
             if (count) rtk::wf_generate<true><<<gen_grid, WF_THREADS, 0, s->stream>>>(s->header, s->blob, g);
             else rtk::wf_generate<false><<<gen_grid, WF_THREADS, 0, s->stream>>>(s->header, s->blob, g);
             launches++;
+            mark();
             for (int r = 0; r <= segments && segments > 0; r++) {
                 g.round = r;
-                if (count) rtk::wf_traverse<true><<<pers_grid, WF_THREADS, 0, s->stream>>>(s->header, s->blob, g);
-                else rtk::wf_traverse<false><<<pers_grid, WF_THREADS, 0, s->stream>>>(s->header, s->blob, g);
+                if (count) rtk::wf_traverse<true><<<pers_grid, WF_THREADS, trav_smem, s->stream>>>(s->header, s->blob, g, npool_cap);
+                else rtk::wf_traverse<false><<<pers_grid, WF_THREADS, trav_smem, s->stream>>>(s->header, s->blob, g, npool_cap);
                 launches++;
+                mark();
                 if (r == segments) break;
                 if (count) rtk::wf_shade<true><<<shade_grid, WF_THREADS, 0, s->stream>>>(s->header, s->blob, g);
                 else rtk::wf_shade<false><<<shade_grid, WF_THREADS, 0, s->stream>>>(s->header, s->blob, g);
                 launches++;
+                mark();
+            }
+            if (dbg_times) {
+                cudaStreamSynchronize(s->stream);
+                fprintf(stderr, "[times us]");
+                for (int k = 1; k < n_ev; k++) {
+                    float ms = 0.f;
+                    cudaEventElapsedTime(&ms, dev_ev[k - 1], dev_ev[k]);
+                    fprintf(stderr, " %.1f", ms * 1e3f);
+                }
+                fprintf(stderr, "\n");
+                for (int k = 0; k < n_ev; k++) cudaEventDestroy(dev_ev[k]);
             }
             launches--; /* the common launches++ below counts one */
         } else if (variant == 0) {

@@ -135,8 +135,8 @@ __device__ __forceinline__ bool blocks_light(F3 Padj, F3 su, float t, float D2) 
  * hit has f(t) <= D2 the closest accepted hit, which the reference uses, has too; and if none has, neither has
  * the closest. Children are visited nearest-first in ANY mode so blockers are found early. */
 template <bool COUNT, bool FAST, bool ANY>
-__device__ __forceinline__ void mesh_query(const SceneHeader& h, const float4* __restrict__ nodes, const float4* __restrict__ tris,
-                                           F3 O, F3 u, float eps_tri, int push_order, float D2, float t_limit, float& t_best, int& tri_best, Work& w) {
+__device__ __forceinline__ void mesh_query(const SceneHeader& h, const float4* __restrict__ nodes, const int2* __restrict__ leaves,
+                                           const float4* __restrict__ tris, F3 O, F3 u, float eps_tri, int push_order, float D2, float t_limit, float& t_best, int& tri_best, Work& w) {
     t_best = ANY ? t_limit : RTK_INF;
     tri_best = -1;
     int leaf_best = -1;
@@ -148,15 +148,15 @@ __device__ __forceinline__ void mesh_query(const SceneHeader& h, const float4* _
     } else {
         if (!slab_exact(h.root_mn[0], h.root_mn[1], h.root_mn[2], h.root_mx[0], h.root_mx[1], h.root_mx[2], O, u)) return;
     }
-    int2 stack[RT_STACK_CAP];
+    int stack[RT_STACK_CAP];
     int sp = 0;
-    int2 cur = make_int2(h.root_a, h.root_b);
+    int cur = h.root_ref;
     for (;;) {
-        if (cur.y < 0) {
-            const float4* n = nodes + 4 * (size_t)cur.x;
+        if (cur >= 0) {
+            const float4* n = nodes + 4 * (size_t)cur;
             const float4 q0 = __ldg(n), q1 = __ldg(n + 1), q2 = __ldg(n + 2);
             const int4 q3 = __ldg(reinterpret_cast<const int4*>(n + 3));
-            if (COUNT) w.nodes++;
+            if (COUNT && q3.z == 0) w.nodes++; /* virtual nodes are not nodes of the reference BVH */
             bool okL, okR;
             if (FAST) {
                 okL = slab_fast(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, ctx, tnL, w.slab_fallbacks);
@@ -165,9 +165,9 @@ __device__ __forceinline__ void mesh_query(const SceneHeader& h, const float4* _
                 okL = slab_exact(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, O, u);
                 okR = slab_exact(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, O, u);
             }
-            int2 cl = make_int2(q3.x, q3.y), cr = make_int2(q3.z, q3.w);
+            int cl = q3.x, cr = q3.y;
             if (ANY && FAST && okL && okR && tnR < tnL) { /* nearest first; the order never changes the outcome */
-                const int2 s = cl;
+                const int s = cl;
                 cl = cr;
                 cr = s;
             }
@@ -184,7 +184,10 @@ __device__ __forceinline__ void mesh_query(const SceneHeader& h, const float4* _
                 continue;
             }
         } else {
-            for (int i = cur.x; i < cur.y; i++) {
+            const int2 lf = __ldg(leaves + (-1 - cur));
+            const int leaf_id = (int)((unsigned)lf.y >> 8); /* first triangle of the reference's leaf */
+            const int i_end = lf.x + (lf.y & 0xff);
+            for (int i = lf.x; i < i_end; i++) {
                 if (COUNT) w.tris++;
                 float t;
                 if (FAST) {
@@ -200,11 +203,12 @@ __device__ __forceinline__ void mesh_query(const SceneHeader& h, const float4* _
                     }
                     continue;
                 }
-                const bool tie = (tri_best >= 0) && (t == t_best) && (leaf_best != cur.x) && (push_order == 1 ? (cur.x < leaf_best) : (cur.x > leaf_best));
-                if (t < t_best || tie) {
+                /* exact tie: inside the reference's leaf the first (smallest) index wins, i.e. no update */
+                const bool tie = (tri_best >= 0) && (t == t_best) && (leaf_best != leaf_id) && (push_order == 1 ? (leaf_id < leaf_best) : (leaf_id > leaf_best));
+                if (t < t_best || tie || (tri_best >= 0 && t == t_best && leaf_best == leaf_id && i < tri_best)) {
                     t_best = t;
                     tri_best = i;
-                    leaf_best = cur.x;
+                    leaf_best = leaf_id;
                 }
             }
         }
@@ -222,8 +226,8 @@ struct SurfaceHit {
 
 /* Scene::intersect_all: ascending object id, strict t < t_min (lowest id wins exact ties). */
 template <bool COUNT, bool FAST>
-__device__ __forceinline__ SurfaceHit intersect_all(const SceneHeader& h, const float4* __restrict__ nodes, const float4* __restrict__ tris,
-                                                    F3 O, F3 u, float eps_tri, int push_order, Work& w) {
+__device__ __forceinline__ SurfaceHit intersect_all(const SceneHeader& h, const float4* __restrict__ nodes, const int2* __restrict__ leaves,
+                                                    const float4* __restrict__ tris, F3 O, F3 u, float eps_tri, int push_order, Work& w) {
     w.rays++;
     SurfaceHit r;
     r.t = RTK_INF;
@@ -241,7 +245,7 @@ __device__ __forceinline__ SurfaceHit intersect_all(const SceneHeader& h, const 
     if (h.has_mesh) {
         float tm;
         int tri;
-        mesh_query<COUNT, FAST, false>(h, nodes, tris, O, u, eps_tri, push_order, 0.f, 0.f, tm, tri, w);
+        mesh_query<COUNT, FAST, false>(h, nodes, leaves, tris, O, u, eps_tri, push_order, 0.f, 0.f, tm, tri, w);
         if (tri >= 0 && (tm < r.t || (tm == r.t && h.mesh_id < r.obj))) {
             r.t = tm;
             r.obj = h.mesh_id;
@@ -257,8 +261,8 @@ __device__ __forceinline__ SurfaceHit intersect_all(const SceneHeader& h, const 
  * equals "some object's reported hit satisfies blocks_light", which lets the spheres be checked first and the
  * mesh be left as soon as one blocker is found. */
 template <bool COUNT, bool FAST>
-__device__ __forceinline__ bool light_blocked(const SceneHeader& h, const float4* __restrict__ nodes, const float4* __restrict__ tris,
-                                              F3 Padj, F3 su, float D2, float eps_tri, int push_order, Work& w) {
+__device__ __forceinline__ bool light_blocked(const SceneHeader& h, const float4* __restrict__ nodes, const int2* __restrict__ leaves,
+                                              const float4* __restrict__ tris, F3 Padj, F3 su, float D2, float eps_tri, int push_order, Work& w) {
     w.rays++;
     for (int k = 0; k < h.n_spheres; k++) {
         float t;
@@ -269,7 +273,7 @@ __device__ __forceinline__ bool light_blocked(const SceneHeader& h, const float4
     const float t_limit = sqrtf(D2) * 1.001f + 1e-3f;
     float tm;
     int tri;
-    mesh_query<COUNT, FAST, true>(h, nodes, tris, Padj, su, eps_tri, push_order, D2, t_limit, tm, tri, w);
+    mesh_query<COUNT, FAST, true>(h, nodes, leaves, tris, Padj, su, eps_tri, push_order, D2, t_limit, tm, tri, w);
     return tri >= 0;
 }
 
@@ -280,6 +284,7 @@ __global__ void __launch_bounds__(128) render_mega(const __grid_constant__ Scene
     __syncthreads();
 
     const float4* nodes = reinterpret_cast<const float4*>(blob + h.off_nodes);
+    const int2* leaves = reinterpret_cast<const int2*>(blob + h.off_leaves);
     const float4* tris = reinterpret_cast<const float4*>(blob + h.off_tris);
     const float4* nhat = reinterpret_cast<const float4*>(blob + h.off_nhat);
 
@@ -309,7 +314,7 @@ __global__ void __launch_bounds__(128) render_mega(const __grid_constant__ Scene
         const float eps = a.eps_surface;
 
         for (int depth = 0; depth < a.segments; depth++) {
-            const SurfaceHit hit = intersect_all<COUNT, FAST>(h, nodes, tris, O, u, a.eps_tri, a.push_order, w);
+            const SurfaceHit hit = intersect_all<COUNT, FAST>(h, nodes, leaves, tris, O, u, a.eps_tri, a.push_order, w);
             if (depth == 0) {
                 first_obj = hit.obj;
                 first_tri = hit.tri;
@@ -369,9 +374,9 @@ __global__ void __launch_bounds__(128) render_mega(const __grid_constant__ Scene
                 const F3 su = toL / sqrtf(norm2(toL)); /* NORMED_VEC :618 */
                 bool blocked;
                 if (FAST) {
-                    blocked = light_blocked<COUNT, FAST>(h, nodes, tris, Padj, su, norm2(toL), a.eps_tri, a.push_order, w);
+                    blocked = light_blocked<COUNT, FAST>(h, nodes, leaves, tris, Padj, su, norm2(toL), a.eps_tri, a.push_order, w);
                 } else { /* literal reference: closest hit, then the predicate */
-                    const SurfaceHit sh = intersect_all<COUNT, FAST>(h, nodes, tris, Padj, su, a.eps_tri, a.push_order, w);
+                    const SurfaceHit sh = intersect_all<COUNT, FAST>(h, nodes, leaves, tris, Padj, su, a.eps_tri, a.push_order, w);
                     blocked = blocks_light(Padj, su, sh.t, norm2(toL)); /* on a miss t = 1e9f, as the reference leaves it */
                 }
                 if (blocked) { /* :620 */

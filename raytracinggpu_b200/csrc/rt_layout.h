@@ -6,8 +6,15 @@
  *
  *   [ SceneHeader, padded to RT_HEADER_BYTES ]
  *   [ inner nodes : n_inner  x 64 B ]   both children's boxes + both child references in one record
+ *   [ leaves      : n_leaves x  8 B ]   (first triangle, count <= RT_LEAF_MAX | start of the reference's leaf << 8)
  *   [ triangles   : n_tris   x 48 B ]   A, e1 = B-A, e2 = C-A, N = e1 x e2 (12 floats = 3 x float4)
  *   [ unit normals: n_tris   x 16 B ]   N / |N| (read once per ray, for the winning triangle only)
+ *
+ * A child reference is one int: >= 0 inner-node index, < 0 leaf (-1 - ref indexes the leaf table). Leaves hold at
+ * most RT_LEAF_MAX triangles: a larger leaf of the reference BVH (the cat has one of 73) is hung under a small
+ * tree of "virtual" inner nodes whose child boxes all equal the leaf's own box. The box test of a virtual node
+ * repeats the computation that already succeeded for its parent, so exactly the reference's triangles are still
+ * tested, while every traversal task stays small and uniform.
  *
  * versus the reference interchange format (what rt_scene_set_mesh receives and optimized.cu:814-826 uploads):
  * 40-B nodes read as 10 scalar loads with every child node read twice (optimized.cu:223-238, 255-261), and
@@ -24,6 +31,8 @@
 #define RT_MAX_SPHERES 16
 #define RT_HEADER_BYTES 1024
 #define RT_NODE_BYTES 64
+#define RT_LEAF_BYTES 8
+#define RT_LEAF_MAX 4
 #define RT_TRI_BYTES 48
 #define RT_NHAT_BYTES 16
 #define RT_STACK_CAP 64 /* traversal stack entries; rt_scene_set_mesh rejects deeper trees */
@@ -38,26 +47,26 @@ struct DevSphere {
     int32_t id;
 };
 
-/* Child reference (a, b): b < 0 -> inner node with index a in the inner-node array; b >= 0 -> leaf with
- * triangles [a, b). */
 struct SceneHeader {
     uint32_t magic;
     uint32_t layout_version;
     int32_t n_spheres;
     int32_t has_mesh;
-    int32_t n_inner;
+    int32_t n_inner;   /* inner-node records, virtual ones included */
+    int32_t n_leaves;  /* leaf-table entries */
     int32_t n_tris;
-    int32_t max_depth; /* levels of the BVH: bound on the traversal stack */
+    int32_t max_depth; /* levels of the packed tree (virtual levels included): bound on the traversal stacks */
     int32_t mesh_id;
     int32_t mesh_mirror;
     float mesh_n_in, mesh_n_out;
     float mesh_albedo[3];
     float root_mn[3], root_mx[3];
     float box_abs[3]; /* largest |coordinate| over all node boxes, per axis (bound used by the certified slab test) */
-    int32_t root_a, root_b;
+    int32_t root_ref;
+    int32_t pad0;
     float L[3];
     float intensity;
-    uint64_t off_nodes, off_tris, off_nhat, total_bytes; /* byte offsets inside the blob */
+    uint64_t off_nodes, off_leaves, off_tris, off_nhat, total_bytes; /* byte offsets inside the blob */
     DevSphere spheres[RT_MAX_SPHERES];                    /* ascending id */
 };
 

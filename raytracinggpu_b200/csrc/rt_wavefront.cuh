@@ -47,7 +47,8 @@ struct __align__(16) QEntry {
 static_assert(sizeof(QEntry) == 48, "QEntry is three float4");
 
 struct WfCounters {
-    unsigned long long stats[8]; /* rays, node visits, triangle tests, max stack, slab fallbacks, exact triangle evals */
+    unsigned long long stats[8]; /* rays, node visits, triangle tests, max stack, slab fallbacks, exact triangle evals, -, pool overflow */
+    unsigned long long dbg[8];   /* COUNT only: N steps, N tasks, T steps, T tasks, admissions, idle iterations */
     int nA[WF_MAX_ROUNDS + 2];   /* closest-hit queries posted for round r */
     int nS[WF_MAX_ROUNDS + 2];   /* shadow queries posted for round r */
     int head[WF_MAX_ROUNDS + 2]; /* traversal fetch cursor of round r */
@@ -320,201 +321,285 @@ __global__ void __launch_bounds__(WF_THREADS) wf_shade(const __grid_constant__ S
     flush_work(w, g.c, COUNT);
 }
 
-/* ---- wf_traverse: persistent warps drain the closest-hit and shadow queues of round g.round ------------------------ */
-struct LaneTask {
-    RayCtx ctx;
-    float t_best;       /* closest: best t of THIS lane's subtrees; any: t limit */
-    float d2;
-    unsigned rank_best;
-    int entry;          /* index into the round's queues (closest entries first, then shadow entries) */
-    int pixel;
-    int mode;
-    int2 cur;
-    int ti;             /* next triangle of the current leaf */
-    int sp;
-    bool busy;
-    bool shared;        /* other lanes of the warp work on subtrees of the same ray */
+/* ---- wf_traverse: persistent warps drain the closest-hit and shadow queues of round g.round ------------------------
+ *
+ * The reference's mesh query is an exhaustive search: every box on the way down whose slab test passes is
+ * opened, every triangle of every reached leaf is tested, the strictly smallest t wins (ties by visiting order,
+ * here by rank). Nothing orders or prunes it, so the search of one ray is a bag of independent (ray, node) and
+ * (ray, leaf) tasks. A warp keeps two task pools in shared memory for the 2 x 32 rays it has in flight:
+ *
+ *   N step  the 32 lanes pop 32 node tasks (any mix of rays), each tests the two child boxes of ITS node against
+ *           ITS ray (the ray's slab constants come from a shared-memory slot), and pushes the children that
+ *           were hit — inner children to the node pool, leaves to the leaf pool — at ballot-computed offsets.
+ *   T step  the lanes pop 32 leaf tasks and test their <= RT_LEAF_MAX triangles; an accepted hit updates the
+ *           ray's best (t bits, rank) with a shared-memory atomicMin.
+ *
+ * All lanes run the same code on different tasks: no per-lane stack, no per-lane loop, no idle lane while a pool
+ * holds 32 tasks — a 800-step ray is simply 800 tasks that spread over the lanes, where a thread-per-ray
+ * traversal holds one lane for 800 iterations (profiles/r01_notes.md). Rays are admitted in batches of 32; two
+ * batches overlap so the drain of one is covered by the other; a batch is complete when its count of
+ * outstanding tasks (kept warp-uniform with ballots) reaches zero, then its results go back to the queue
+ * entries. Shadow rays stop generating work once a blocker is found.
+ */
+/* position k of the strided visiting order of a queue of n entries (a permutation of 0..n-1): the queue is cut
+ * into 32 equal runs and read round-robin, one entry of each run per batch */
+__device__ __forceinline__ int qperm(int k, int n) {
+    const int run = (n + 31) >> 5;      /* entries per run */
+    const int full = n - 31 * run;      /* length of the last run (may be shorter, > 0 when n > 31 * run) */
+    /* row-major walk over a 32 x run grid whose last row has `full` valid cells */
+    if (full <= 0) return k;            /* tiny queues: identity */
+    const int rows_full = full * 32;    /* first `full` columns hold 32 entries each */
+    if (k < rows_full) return (k & 31) * run + (k >> 5);
+    const int k2 = k - rows_full;       /* remaining columns hold 31 entries each */
+    return (k2 % 31) * run + full + k2 / 31;
+}
+
+#define WF_SLOTS 64
+#define WF_TPOOL 160
+
+struct WfWarpSmem { /* per warp; followed by the node pool (npool_cap ints) */
+    float4 A[WF_SLOTS];  /* rx, ry, rz, M        (RN(1/u), certified-slab margin) */
+    float4 B[WF_SLOTS];  /* nox, noy, noz, d2    (-RN(O r); shadow rays: |L - P'|^2, set to -1 once a blocker is found) */
+    float4 C[WF_SLOTS];  /* ox, oy, oz, t_limit  (closest-hit rays: 1e9f, shadow rays: finite) */
+    float4 D[WF_SLOTS];  /* ux, uy, uz, (int) pixel */
+    unsigned long long best[WF_SLOTS]; /* closest: (t bits << 32) | rank, WF_NOHIT if none */
+    int entry[WF_SLOTS];               /* queue index of the ray */
+    int tpool[WF_TPOOL];
 };
 
 template <bool COUNT>
 __global__ void __launch_bounds__(WF_THREADS) wf_traverse(const __grid_constant__ SceneHeader h, const unsigned char* __restrict__ blob,
-                                                         const __grid_constant__ WfArgs g) {
+                                                         const __grid_constant__ WfArgs g, const int npool_cap) {
+    extern __shared__ __align__(16) unsigned char wf_smem[];
     const RenderArgs& a = g.a;
     const float4* nodes = reinterpret_cast<const float4*>(blob + h.off_nodes);
+    const int2* leaves = reinterpret_cast<const int2*>(blob + h.off_leaves);
     const float4* tris = reinterpret_cast<const float4*>(blob + h.off_tris);
     const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
+    const size_t warp_bytes = (sizeof(WfWarpSmem) + (size_t)npool_cap * sizeof(int) + 15) & ~(size_t)15;
+    WfWarpSmem& sm = *reinterpret_cast<WfWarpSmem*>(wf_smem + warp * warp_bytes);
+    int* npool = reinterpret_cast<int*>(wf_smem + warp * warp_bytes + sizeof(WfWarpSmem));
+
     const int nA = g.c->nA[g.round], nS = g.c->nS[g.round];
     const int total = nA + nS;
     QEntry* qA = g.qA[g.round & 1];
     QEntry* qS = g.qS;
     int* head = &g.c->head[g.round];
-    const int2 root = make_int2(h.root_a, h.root_b);
     Work w;
     w.rays = w.nodes = w.tris = w.max_stack = w.slab_fallbacks = w.tri_exact = 0;
 
-    LaneTask k;
-    k.busy = false;
-    k.shared = false;
-    k.sp = 0;
-    k.entry = 0;
-    k.pixel = 0;
-    k.mode = 0;
-    k.cur = root;
-    k.ti = 0;
-    int2 stack[RT_STACK_CAP];
-    int rs_next = 0, rs_end = 0; /* this warp's reserved range of queue indices (warp-uniform) */
+    int nN = 0, nT = 0;               /* pool fill (warp-uniform) */
+    int out0 = 0, out1 = 0;           /* outstanding tasks of batch 0 / 1 (warp-uniform) */
+    int cnt0 = 0, cnt1 = 0;           /* rays admitted in batch 0 / 1; 0 = batch free */
     bool exhausted = total == 0;
-
-    auto entry_ptr = [&](int e) -> QEntry* { return e < nA ? (qA + e) : (qS + (e - nA)); };
-    auto begin = [&](int e, int2 ref, bool shared) {
-        const float4* p = reinterpret_cast<const float4*>(entry_ptr(e));
-        const float4 p0 = __ldcg(p), p1 = __ldcg(p + 1);
-        k.entry = e;
-        k.mode = e < nA ? WF_MODE_CLOSEST : WF_MODE_ANY;
-        k.pixel = __float_as_int(p1.w);
-        k.ctx = make_ray_ctx(f3(p0.x, p0.y, p0.z), f3(p1.x, p1.y, p1.z), h.box_abs[0], h.box_abs[1], h.box_abs[2]);
-        k.d2 = p0.w;
-        /* any: a hit with t > 1.001 sqrt(D2) cannot satisfy the shadow predicate (|t u| ~ t) */
-        k.t_best = (k.mode == WF_MODE_ANY) ? (sqrtf(k.d2) * 1.001f + 1e-3f) : RTK_INF;
-        k.rank_best = 0xffffffffu;
-        k.cur = ref;
-        k.ti = ref.x;
-        k.sp = 0;
-        k.busy = true;
-        k.shared = shared;
-    };
-    auto finish = [&]() { /* publish this lane's result for its ray and become idle */
-        if (k.mode == WF_MODE_CLOSEST && k.rank_best != 0xffffffffu) {
-            const unsigned long long key = ((unsigned long long)__float_as_uint(k.t_best) << 32) | k.rank_best;
-            atomicMin(&entry_ptr(k.entry)->res, key);
-        }
-        k.busy = false;
-    };
-    auto pop = [&]() { /* next pending subtree of this lane, or the end of its task */
-        if (k.sp == 0 || (k.mode == WF_MODE_ANY && k.shared && *((volatile unsigned long long*)&entry_ptr(k.entry)->res) != 0ull)) {
-            finish();
-            return;
-        }
-        k.cur = stack[--k.sp];
-        k.ti = k.cur.x;
-    };
+    bool failed = false;
+    unsigned dbgNs = 0, dbgNt = 0, dbgTs = 0, dbgTt = 0, dbgAd = 0;
 
     for (;;) {
-        /* ---- work distribution -------------------------------------------------------------------------------- */
-        const unsigned idle = __ballot_sync(FULL, !k.busy);
-        if (idle) {
-            if (rs_next >= rs_end && !exhausted) { /* reserve the next 32 queue indices for this warp */
-                int base = 0;
-                if (lane == 0) base = atomicAdd(head, 32);
-                base = __shfl_sync(FULL, base, 0);
-                rs_next = base;
-                rs_end = min(base + 32, total);
-                if (base >= total) {
-                    exhausted = true;
-                    rs_next = rs_end = 0;
+        /* ---- retire complete batches: results go back to the queue entries ---------------------------------------- */
+#pragma unroll
+        for (int b = 0; b < 2; b++) {
+            const int cnt = b ? cnt1 : cnt0, out = b ? out1 : out0;
+            if (cnt > 0 && out == 0) {
+                if (lane < cnt) {
+                    const int slot = b * 32 + lane;
+                    const int e = sm.entry[slot];
+                    if (e < nA) {
+                        (qA + e)->res = sm.best[slot];
+                    } else if (sm.B[slot].w < 0.f) { /* the light is blocked: the pixel is black (optimized.cu:620-622) */
+                        const int px = __float_as_int(sm.D[slot].w);
+                        if (a.rgb) {
+                            a.rgb[(size_t)px * 3 + 0] = 0;
+                            a.rgb[(size_t)px * 3 + 1] = 0;
+                            a.rgb[(size_t)px * 3 + 2] = 0;
+                        }
+                        if (a.shadow) a.shadow[px] = 1;
+                    }
                 }
-            }
-            const int avail = rs_end - rs_next;
-            if (avail > 0) {
-                const int r = __popc(idle & lt_mask);
-                if (!k.busy && r < avail) begin(rs_next + r, root, false);
-                rs_next += min(avail, __popc(idle));
-            }
-            /* nothing left to fetch: idle lanes take a pending subtree from busy lanes of this warp */
-            const unsigned thieves = __ballot_sync(FULL, !k.busy);
-            const unsigned donors = __ballot_sync(FULL, k.busy && k.sp > 0);
-            if (thieves && donors) {
-                const int pairs = min(__popc(thieves), __popc(donors));
-                const int my_rank = __popc((k.busy ? donors : thieves) & lt_mask);
-                const bool donate = k.busy && k.sp > 0 && my_rank < pairs;
-                const bool steal = !k.busy && my_rank < pairs;
-                int2 give = make_int2(0, 0);
-                if (donate) {
-                    give = stack[--k.sp];
-                    k.shared = true;
-                }
-                const int src = steal ? (int)__fns(donors, 0, my_rank + 1) : lane;
-                const int g_entry = __shfl_sync(FULL, k.entry, src);
-                const int gx = __shfl_sync(FULL, give.x, src);
-                const int gy = __shfl_sync(FULL, give.y, src);
-                if (steal) begin(g_entry, make_int2(gx, gy), true);
+                __syncwarp();
+                if (b) cnt1 = 0;
+                else cnt0 = 0;
             }
         }
-        if (!__any_sync(FULL, k.busy)) {
-            if (exhausted) break;
+        /* ---- admit a batch of 32 rays when a batch is free and the pools run low ----------------------------------- */
+        if (!exhausted && (cnt0 == 0 || cnt1 == 0) && nN + nT < 48) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(head, 32);
+            base = __shfl_sync(FULL, base, 0);
+            const int take = min(32, total - base);
+            if (take <= 0) {
+                exhausted = true;
+            } else {
+                const int b = cnt0 == 0 ? 0 : 1;
+                if (COUNT) dbgAd++;
+                if (lane < take) {
+                    /* batch b of the queue is {b, b + stride, b + 2 stride, ...}: neighbouring queue entries are
+                     * neighbouring pixels, and the expensive rays cluster (the cat's head); striding gives every batch
+                     * the same mix, so no warp is left with 32 heavy rays at the end of the launch */
+                    const int e = qperm(base + lane, total);
+                    const float4* p = reinterpret_cast<const float4*>(e < nA ? (qA + e) : (qS + (e - nA)));
+                    const float4 p0 = __ldcg(p), p1 = __ldcg(p + 1);
+                    const RayCtx c = make_ray_ctx(f3(p0.x, p0.y, p0.z), f3(p1.x, p1.y, p1.z), h.box_abs[0], h.box_abs[1], h.box_abs[2]);
+                    const int slot = b * 32 + lane;
+                    const bool any = e >= nA;
+                    sm.A[slot] = make_float4(c.rx, c.ry, c.rz, c.M);
+                    sm.B[slot] = make_float4(c.nox, c.noy, c.noz, p0.w);
+                    /* shadow rays: a hit with t > 1.001 sqrt(D2) cannot satisfy the shadow predicate (|t u| ~ t) */
+                    sm.C[slot] = make_float4(p0.x, p0.y, p0.z, any ? (sqrtf(p0.w) * 1.001f + 1e-3f) : RTK_INF);
+                    sm.D[slot] = p1;
+                    sm.best[slot] = WF_NOHIT;
+                    sm.entry[slot] = e;
+                    const int task = (slot << 26) | (h.root_ref >= 0 ? h.root_ref : (-1 - h.root_ref));
+                    if (h.root_ref >= 0) npool[nN + lane] = task;
+                    else sm.tpool[nT + lane] = task;
+                }
+                if (h.root_ref >= 0) nN += take;
+                else nT += take;
+                if (b) {
+                    cnt1 = take;
+                    out1 = take;
+                } else {
+                    cnt0 = take;
+                    out0 = take;
+                }
+                __syncwarp();
+            }
+        }
+        if (nN == 0 && nT == 0) {
+            if (cnt0 == 0 && cnt1 == 0 && exhausted) break;
+            if (out0 != 0 || out1 != 0) { /* cannot happen: outstanding tasks with empty pools */
+                failed = true;
+                break;
+            }
             continue;
         }
 
-        /* ---- node phase: every lane whose current reference is an inner node steps it ----------------------------- */
-        while (__any_sync(FULL, k.busy && k.cur.y < 0)) {
-            if (k.busy && k.cur.y < 0) {
-                const float4* n = nodes + 4 * (size_t)k.cur.x;
-                const float4 q0 = __ldg(n), q1 = __ldg(n + 1), q2 = __ldg(n + 2);
-                const int4 q3 = __ldg(reinterpret_cast<const int4*>(n + 3));
-                if (COUNT) w.nodes++;
-                float tnL, tnR;
-                const bool okL = slab_fast(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, k.ctx, tnL, w.slab_fallbacks);
-                const bool okR = slab_fast(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, k.ctx, tnR, w.slab_fallbacks);
-                int2 cl = make_int2(q3.x, q3.y), cr = make_int2(q3.z, q3.w);
-                if (k.mode == WF_MODE_ANY && okL && okR && tnR < tnL) { /* nearest first: blockers are found sooner */
-                    const int2 s = cl;
-                    cl = cr;
-                    cr = s;
-                }
-                if (okL) {
-                    k.cur = cl;
-                    k.ti = cl.x;
-                    if (okR) {
-                        stack[k.sp++] = cr;
-                        if (COUNT) w.max_stack = max(w.max_stack, (unsigned)k.sp);
+        if (nT >= 32 || nN == 0) {
+            /* ---- T step: one leaf (<= RT_LEAF_MAX triangles) per lane ---------------------------------------------- */
+            const int cnt = min(nT, 32);
+            if (COUNT) { dbgTs++; dbgTt += cnt; }
+            const bool have = lane < cnt;
+            int slot = 0;
+            bool live = false;
+            if (have) {
+                const int task = sm.tpool[nT - 1 - lane];
+                slot = (unsigned)task >> 26;
+                const float d2 = sm.B[slot].w;
+                live = !(d2 < 0.f);
+                if (live) {
+                    const int2 lf = __ldg(leaves + (task & 0x3ffffff));
+                    const float4 c4 = sm.C[slot], d4 = sm.D[slot];
+                    const F3 O = f3(c4.x, c4.y, c4.z), u = f3(d4.x, d4.y, d4.z);
+                    const bool any = c4.w < RTK_INF;
+                    const int leaf_start = (int)((unsigned)lf.y >> 8);
+                    const int i_end = lf.x + (lf.y & 0xff);
+                    float t_limit = c4.w;
+                    if (!any) {
+                        const unsigned long long cur = sm.best[slot];
+                        if (cur != WF_NOHIT) t_limit = __uint_as_float((unsigned)(cur >> 32));
                     }
-                } else if (okR) {
-                    k.cur = cr;
-                    k.ti = cr.x;
-                } else {
-                    pop();
-                }
-            }
-        }
-        /* ---- triangle phase: one triangle per lane per step ---------------------------------------------------------- */
-        while (__any_sync(FULL, k.busy && k.cur.y >= 0)) {
-            if (k.busy && k.cur.y >= 0) {
-                if (k.ti < k.cur.y) {
-                    const int i = k.ti++;
-                    if (COUNT) w.tris++;
-                    float t;
-                    if (tri_fast(tris + 3 * (size_t)i, k.ctx.O, k.ctx.u, k.t_best, t, w.tri_exact) && t > a.eps_tri) {
-                        if (k.mode == WF_MODE_ANY) {
-                            if (blocks_light(k.ctx.O, k.ctx.u, t, k.d2)) { /* the light is blocked: the pixel is black (:620-622) */
-                                if (a.rgb) {
-                                    a.rgb[(size_t)k.pixel * 3 + 0] = 0;
-                                    a.rgb[(size_t)k.pixel * 3 + 1] = 0;
-                                    a.rgb[(size_t)k.pixel * 3 + 2] = 0;
-                                }
-                                if (a.shadow) a.shadow[k.pixel] = 1;
-                                if (k.shared) *((volatile unsigned long long*)&entry_ptr(k.entry)->res) = 1ull;
-                                k.sp = 0;
-                                k.ti = k.cur.y; /* leaves the leaf; pop() ends the task */
+                    for (int i = lf.x; i < i_end; i++) {
+                        if (COUNT) w.tris++;
+                        float t;
+                        if (!tri_fast(tris + 3 * (size_t)i, O, u, t_limit, t, w.tri_exact) || !(t > a.eps_tri)) continue;
+                        if (any) {
+                            if (blocks_light(O, u, t, d2)) {
+                                sm.B[slot].w = -1.f; /* no more work for this ray */
+                                break;
                             }
                         } else {
-                            const unsigned rank = tie_rank(i, k.cur.x, h.n_tris, a.push_order, a.rank_off_bits);
-                            if (t < k.t_best || (t == k.t_best && rank < k.rank_best)) {
-                                k.t_best = t;
-                                k.rank_best = rank;
-                            }
+                            const unsigned rank = tie_rank(i, leaf_start, h.n_tris, a.push_order, a.rank_off_bits);
+                            atomicMin(&sm.best[slot], ((unsigned long long)__float_as_uint(t) << 32) | rank);
+                            if (t < t_limit) t_limit = t;
                         }
                     }
-                } else {
-                    pop();
                 }
             }
-            /* leave the phase early when inner-node work is waiting and few lanes still have triangles */
-            const unsigned tri_lanes = __ballot_sync(FULL, k.busy && k.cur.y >= 0);
-            const unsigned node_lanes = __ballot_sync(FULL, k.busy && k.cur.y < 0);
-            if (node_lanes && __popc(tri_lanes) < 12) break;
+            const unsigned in1 = __ballot_sync(FULL, have && slot >= 32);
+            out1 -= __popc(in1);
+            out0 -= cnt - __popc(in1);
+            nT -= cnt;
+        } else {
+            /* ---- N step: one inner node (two child boxes) per lane ------------------------------------------------- */
+            if (nN + 64 > npool_cap) { /* the host sizes the pool from the tree depth; never expected */
+                failed = true;
+                break;
+            }
+            const int cnt = min(nN, 32);
+            if (COUNT) { dbgNs++; dbgNt += cnt; }
+            const bool have = lane < cnt;
+            int slot = 0;
+            bool pNL = false, pNR = false, pTL = false, pTR = false;
+            int refL = 0, refR = 0;
+            if (have) {
+                const int task = npool[nN - 1 - lane];
+                slot = (unsigned)task >> 26;
+                const float4 a4 = sm.A[slot], b4 = sm.B[slot];
+                if (!(b4.w < 0.f)) {
+                    const float4* n = nodes + 4 * (size_t)(task & 0x3ffffff);
+                    const float4 q0 = __ldg(n), q1 = __ldg(n + 1), q2 = __ldg(n + 2);
+                    const int2 q3 = __ldg(reinterpret_cast<const int2*>(n + 3));
+                    if (COUNT && __ldg(reinterpret_cast<const int*>(n + 3) + 2) == 0) w.nodes++;
+                    RayCtx c;
+                    c.rx = a4.x;
+                    c.ry = a4.y;
+                    c.rz = a4.z;
+                    c.M = a4.w;
+                    c.nox = b4.x;
+                    c.noy = b4.y;
+                    c.noz = b4.z;
+                    float tn;
+                    int rL = slab_certified(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, c, tn);
+                    int rR = slab_certified(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, c, tn);
+                    if (rL == 0 || rR == 0) { /* undecided by the margin: the reference's own slab test decides */
+                        const float4 c4 = sm.C[slot], d4 = sm.D[slot];
+                        const F3 O = f3(c4.x, c4.y, c4.z), u = f3(d4.x, d4.y, d4.z);
+                        if (rL == 0) {
+                            if (COUNT) w.slab_fallbacks++;
+                            rL = slab_exact(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, O, u) ? 1 : -1;
+                        }
+                        if (rR == 0) {
+                            if (COUNT) w.slab_fallbacks++;
+                            rR = slab_exact(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, O, u) ? 1 : -1;
+                        }
+                    }
+                    refL = q3.x;
+                    refR = q3.y;
+                    pNL = rL > 0 && refL >= 0;
+                    pTL = rL > 0 && refL < 0;
+                    pNR = rR > 0 && refR >= 0;
+                    pTR = rR > 0 && refR < 0;
+                }
+            }
+            nN -= cnt;
+            const unsigned bNL = __ballot_sync(FULL, pNL), bNR = __ballot_sync(FULL, pNR);
+            const unsigned bTL = __ballot_sync(FULL, pTL), bTR = __ballot_sync(FULL, pTR);
+            const unsigned in1 = __ballot_sync(FULL, have && slot >= 32);
+            const int tagged = slot << 26;
+            if (pNL) npool[nN + __popc(bNL & lt_mask)] = tagged | refL;
+            if (pNR) npool[nN + __popc(bNL) + __popc(bNR & lt_mask)] = tagged | refR;
+            if (pTL) sm.tpool[nT + __popc(bTL & lt_mask)] = tagged | (-1 - refL);
+            if (pTR) sm.tpool[nT + __popc(bTL) + __popc(bTR & lt_mask)] = tagged | (-1 - refR);
+            nN += __popc(bNL) + __popc(bNR);
+            nT += __popc(bTL) + __popc(bTR);
+            if (COUNT) w.max_stack = max(w.max_stack, (unsigned)nN);
+            const int mine = (int)pNL + (int)pNR + (int)pTL + (int)pTR;
+            const int pushed1 = __reduce_add_sync(FULL, (have && slot >= 32) ? mine : 0);
+            const int pushed = __popc(bNL) + __popc(bNR) + __popc(bTL) + __popc(bTR);
+            out1 += pushed1 - __popc(in1);
+            out0 += (pushed - pushed1) - (cnt - __popc(in1));
         }
+        __syncwarp(); /* pool and slot writes of this step are visible to the next pop */
+    }
+    if (failed && lane == 0) atomicExch(&g.c->stats[7], 1ull);
+    if (COUNT && lane == 0) {
+        atomicAdd(&g.c->dbg[0], (unsigned long long)dbgNs);
+        atomicAdd(&g.c->dbg[1], (unsigned long long)dbgNt);
+        atomicAdd(&g.c->dbg[2], (unsigned long long)dbgTs);
+        atomicAdd(&g.c->dbg[3], (unsigned long long)dbgTt);
+        atomicAdd(&g.c->dbg[4], (unsigned long long)dbgAd);
     }
     flush_work(w, g.c, COUNT);
 }
