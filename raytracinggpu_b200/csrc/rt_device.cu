@@ -124,7 +124,7 @@ int upload_header(rt_scene* s) {
         /* spheres-only scene: the blob is just the header */
         CUDA_TRY(cudaMalloc(&s->blob, RT_HEADER_BYTES));
         s->blob_bytes = RT_HEADER_BYTES;
-        s->header.off_nodes = s->header.off_leaves = s->header.off_tris = s->header.off_nhat = RT_HEADER_BYTES;
+        s->header.off_nodes = s->header.off_leaves = s->header.off_tris = RT_HEADER_BYTES;
         s->header.total_bytes = RT_HEADER_BYTES;
     }
     CUDA_TRY(cudaMemcpyAsync(s->blob, &s->header, sizeof(SceneHeader), cudaMemcpyHostToDevice, s->stream));
@@ -393,9 +393,8 @@ int rt_scene_set_mesh(rt_scene* s, const float* vertices, int32_t nv, const int3
     /* ---- blob ------------------------------------------------------------------------------------------ */
     const size_t off_nodes = RT_HEADER_BYTES;
     const size_t off_leaves = off_nodes + (size_t)n_inner * RT_NODE_BYTES;
-    const size_t off_tris = (off_leaves + (size_t)n_leaves * RT_LEAF_BYTES + 15) & ~(size_t)15;
-    const size_t off_nhat = off_tris + (size_t)nt * RT_TRI_BYTES;
-    const size_t total = off_nhat + (size_t)nt * RT_NHAT_BYTES;
+    const size_t off_tris = (off_leaves + (size_t)n_leaves * RT_LEAF_BYTES + 63) & ~(size_t)63;
+    const size_t total = off_tris + (size_t)nt * RT_TRI_BYTES;
     CUDA_TRY(cudaStreamSynchronize(s->stream));
     if (s->blob_bytes < total || s->blob_bytes > 2 * total + (1u << 20)) {
         if (s->blob) cudaFree(s->blob);
@@ -418,8 +417,7 @@ int rt_scene_set_mesh(rt_scene* s, const float* vertices, int32_t nv, const int3
         err = cudaMemcpyAsync(s->blob + off_leaves, leaves.data(), (size_t)n_leaves * RT_LEAF_BYTES, cudaMemcpyHostToDevice, s->stream);
     if (err == cudaSuccess) {
         const int threads = 256, blocks = (nt + threads - 1) / threads;
-        rtk::repack_triangles<<<blocks, threads, 0, s->stream>>>(d_vertices, d_recs, nt, reinterpret_cast<float4*>(s->blob + off_tris),
-                                                               reinterpret_cast<float4*>(s->blob + off_nhat));
+        rtk::repack_triangles<<<blocks, threads, 0, s->stream>>>(d_vertices, d_recs, nt, reinterpret_cast<float4*>(s->blob + off_tris));
         err = cudaGetLastError();
     }
     if (err == cudaSuccess) err = cudaStreamSynchronize(s->stream);
@@ -447,7 +445,6 @@ int rt_scene_set_mesh(rt_scene* s, const float* vertices, int32_t nv, const int3
     h.off_nodes = off_nodes;
     h.off_leaves = off_leaves;
     h.off_tris = off_tris;
-    h.off_nhat = off_nhat;
     h.total_bytes = total;
     s->header_dirty = true;
     return RT_OK;
@@ -481,7 +478,7 @@ int rt_scene_blob_import(rt_scene* s, const void* device_ptr, size_t bytes) {
     if (h.magic != RT_BLOB_MAGIC || h.layout_version != 1 || h.total_bytes != bytes)
         return rtb::fail(RT_ERR_INVALID, "rt_scene_blob_import: not a scene blob (magic %08x, %llu bytes declared, %llu given)", h.magic,
                          (unsigned long long)h.total_bytes, (unsigned long long)bytes);
-    if (h.n_spheres < 0 || h.n_spheres > RT_MAX_SPHERES || h.off_nhat + (uint64_t)h.n_tris * RT_NHAT_BYTES > bytes)
+    if (h.n_spheres < 0 || h.n_spheres > RT_MAX_SPHERES || h.off_tris + (uint64_t)h.n_tris * RT_TRI_BYTES > bytes)
         return rtb::fail(RT_ERR_INVALID, "rt_scene_blob_import: inconsistent header");
     if ((const unsigned char*)device_ptr != s->blob) {
         if (s->blob_bytes < bytes) {
@@ -637,7 +634,7 @@ int rt_render(rt_scene* s, const rt_params* p, uint32_t flags, uint8_t* rgb_out,
         s->last_was_wavefront = (variant == 2);
         if (variant == 2) {
             /* node pool of wf_traverse: 32 lanes x (levels of the packed tree + roots of two batches + slack) */
-            const int npool_cap = 32 * (h.max_depth + 4);
+            const int npool_cap = std::min(32 * (h.max_depth + 4), 512);
             const size_t warp_bytes = (sizeof(rtk::WfWarpSmem) + (size_t)npool_cap * sizeof(int) + 15) & ~(size_t)15;
             const size_t trav_smem = warp_bytes * (WF_THREADS / 32);
             if (trav_smem > 200 * 1024) return rtb::fail(RT_ERR_UNSUPPORTED, "rt_render: BVH depth %d needs %zu B of shared memory per block", h.max_depth, trav_smem);

@@ -71,7 +71,9 @@ __device__ __forceinline__ bool sphere_t(const DevSphere& s, F3 O, F3 u, float& 
 /* moller_trumbore on the packed record (A, e1, e2, N precomputed exactly). Returns true with t when the
  * reference's function returns 1. */
 __device__ __forceinline__ bool tri_exact(const float4* __restrict__ rec, F3 O, F3 u, float& t) {
-    const float4 q0 = __ldg(rec), q1 = __ldg(rec + 1), q2 = __ldg(rec + 2);
+    float4 q0, q1;
+    ldg256(rec, q0, q1);
+    const float4 q2 = __ldg(rec + 2);
     const F3 A = f3(q0.x, q0.y, q0.z), e1 = f3(q0.w, q1.x, q1.y), e2 = f3(q1.z, q1.w, q2.x), N = f3(q2.y, q2.z, q2.w);
     const float d = dot(u, N);
     if (d == 0) return false;
@@ -91,7 +93,9 @@ __device__ __forceinline__ bool tri_exact(const float4* __restrict__ rec, F3 O, 
  * accepted hit in particular — goes through the exact divisions, so accepted t values are the reference's bits.
  * t_limit: hits with t certainly greater than t_limit are of no interest to the caller (current closest hit). */
 __device__ __forceinline__ bool tri_fast(const float4* __restrict__ rec, F3 O, F3 u, float t_limit, float& t, unsigned int& exact_evals) {
-    const float4 q0 = __ldg(rec), q1 = __ldg(rec + 1), q2 = __ldg(rec + 2);
+    float4 q0, q1;
+    ldg256(rec, q0, q1);
+    const float4 q2 = __ldg(rec + 2);
     const F3 A = f3(q0.x, q0.y, q0.z), e1 = f3(q0.w, q1.x, q1.y), e2 = f3(q1.z, q1.w, q2.x), N = f3(q2.y, q2.z, q2.w);
     const float d = dot(u, N);
     if (d == 0) return false;
@@ -154,8 +158,10 @@ __device__ __forceinline__ void mesh_query(const SceneHeader& h, const float4* _
     for (;;) {
         if (cur >= 0) {
             const float4* n = nodes + 4 * (size_t)cur;
-            const float4 q0 = __ldg(n), q1 = __ldg(n + 1), q2 = __ldg(n + 2);
-            const int4 q3 = __ldg(reinterpret_cast<const int4*>(n + 3));
+            float4 q0, q1, q2, q3f;
+            ldg256(n, q0, q1);
+            ldg256(n + 2, q2, q3f);
+            const int4 q3 = make_int4(__float_as_int(q3f.x), __float_as_int(q3f.y), __float_as_int(q3f.z), __float_as_int(q3f.w));
             if (COUNT && q3.z == 0) w.nodes++; /* virtual nodes are not nodes of the reference BVH */
             bool okL, okR;
             if (FAST) {
@@ -191,9 +197,9 @@ __device__ __forceinline__ void mesh_query(const SceneHeader& h, const float4* _
                 if (COUNT) w.tris++;
                 float t;
                 if (FAST) {
-                    if (!tri_fast(tris + 3 * (size_t)i, O, u, t_best, t, w.tri_exact)) continue;
+                    if (!tri_fast(tris + 4 * (size_t)i, O, u, t_best, t, w.tri_exact)) continue;
                 } else {
-                    if (!tri_exact(tris + 3 * (size_t)i, O, u, t)) continue;
+                    if (!tri_exact(tris + 4 * (size_t)i, O, u, t)) continue;
                 }
                 if (!(t > eps_tri)) continue; /* optimized.cu:275 / cpu_launcher.cpp:301 */
                 if (ANY) {
@@ -286,7 +292,6 @@ __global__ void __launch_bounds__(128) render_mega(const __grid_constant__ Scene
     const float4* nodes = reinterpret_cast<const float4*>(blob + h.off_nodes);
     const int2* leaves = reinterpret_cast<const int2*>(blob + h.off_leaves);
     const float4* tris = reinterpret_cast<const float4*>(blob + h.off_tris);
-    const float4* nhat = reinterpret_cast<const float4*>(blob + h.off_nhat);
 
     /* 16x8 pixel tile per block, 8x4 per warp */
     const int tiles_x = (a.W + 15) >> 4;
@@ -333,7 +338,7 @@ __global__ void __launch_bounds__(128) render_mega(const __grid_constant__ Scene
                 n_in = s.n_in;
                 n_out = s.n_out;
             } else {
-                const float4 nh = __ldg(nhat + hit.tri); /* N.normalize() :282, precomputed */
+                const float4 nh = __ldg(tris + 4 * (size_t)hit.tri + 3); /* N.normalize() :282, precomputed */
                 N = f3(nh.x, nh.y, nh.z);
                 albedo = f3(h.mesh_albedo[0], h.mesh_albedo[1], h.mesh_albedo[2]);
                 mirror = h.mesh_mirror;
@@ -441,8 +446,7 @@ __global__ void __launch_bounds__(128) render_mega(const __grid_constant__ Scene
 
 /* Mesh repack: reference interchange arrays -> packed triangle records + unit normals (rt_layout.h).
  * e1, e2, N as moller_trumbore forms them (optimized.cu:209-211), N/|N| as :282 does. */
-__global__ void repack_triangles(const float* __restrict__ vertices, const int32_t* __restrict__ recs, int nt, float4* __restrict__ tris,
-                                 float4* __restrict__ nhat) {
+__global__ void repack_triangles(const float* __restrict__ vertices, const int32_t* __restrict__ recs, int nt, float4* __restrict__ tris) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nt) return;
     const int32_t* r = recs + (size_t)i * 10;
@@ -453,10 +457,10 @@ __global__ void repack_triangles(const float* __restrict__ vertices, const int32
     const F3 e1 = B - A, e2 = C - A;
     const F3 N = cross(e1, e2);
     const F3 nh = normalized(N);
-    tris[3 * (size_t)i + 0] = make_float4(A.x, A.y, A.z, e1.x);
-    tris[3 * (size_t)i + 1] = make_float4(e1.y, e1.z, e2.x, e2.y);
-    tris[3 * (size_t)i + 2] = make_float4(e2.z, N.x, N.y, N.z);
-    nhat[i] = make_float4(nh.x, nh.y, nh.z, 0.f);
+    tris[4 * (size_t)i + 0] = make_float4(A.x, A.y, A.z, e1.x);
+    tris[4 * (size_t)i + 1] = make_float4(e1.y, e1.z, e2.x, e2.y);
+    tris[4 * (size_t)i + 2] = make_float4(e2.z, N.x, N.y, N.z);
+    tris[4 * (size_t)i + 3] = make_float4(nh.x, nh.y, nh.z, 0.f);
 }
 
 /* Device self-test of div_by_rcp against div.rn.f32 on pseudo-random operands in the range RaySafe admits.

@@ -7,8 +7,8 @@
  *   [ SceneHeader, padded to RT_HEADER_BYTES ]
  *   [ inner nodes : n_inner  x 64 B ]   both children's boxes + both child references in one record
  *   [ leaves      : n_leaves x  8 B ]   (first triangle, count <= RT_LEAF_MAX | start of the reference's leaf << 8)
- *   [ triangles   : n_tris   x 48 B ]   A, e1 = B-A, e2 = C-A, N = e1 x e2 (12 floats = 3 x float4)
- *   [ unit normals: n_tris   x 16 B ]   N / |N| (read once per ray, for the winning triangle only)
+ *   [ triangles   : n_tris   x 64 B ]   A, e1 = B-A, e2 = C-A, N = e1 x e2 (12 floats) + N/|N| (3 floats) + pad:
+ *                                       one 64-B-aligned record = two 256-bit loads (LDG.E.256 on sm_100a)
  *
  * A child reference is one int: >= 0 inner-node index, < 0 leaf (-1 - ref indexes the leaf table). Leaves hold at
  * most RT_LEAF_MAX triangles: a larger leaf of the reference BVH (the cat has one of 73) is hung under a small
@@ -19,7 +19,7 @@
  * versus the reference interchange format (what rt_scene_set_mesh receives and optimized.cu:814-826 uploads):
  * 40-B nodes read as 10 scalar loads with every child node read twice (optimized.cu:223-238, 255-261), and
  * a 40-B index record + 3 dependent 12-B vertex gathers per triangle test (:271). Here an inner-node visit is
- * four 16-B loads of one 64-B line, a triangle test three 16-B loads of one 48-B record, no indirection.
+ * two 32-B loads of one 64-B record, a triangle test a 32-B and a 16-B load of one 64-B record, no indirection.
  *
  * e1, e2, N and N/|N| depend only on the mesh, so they are precomputed once on the device with the same
  * unfused IEEE operations moller_trumbore (optimized.cu:209-211) and N.normalize() (:282) apply per ray:
@@ -33,8 +33,7 @@
 #define RT_NODE_BYTES 64
 #define RT_LEAF_BYTES 8
 #define RT_LEAF_MAX 4
-#define RT_TRI_BYTES 48
-#define RT_NHAT_BYTES 16
+#define RT_TRI_BYTES 64
 #define RT_STACK_CAP 64 /* traversal stack entries; rt_scene_set_mesh rejects deeper trees */
 #define RT_BLOB_MAGIC 0x52544232u /* "RTB2" */
 
@@ -66,7 +65,7 @@ struct SceneHeader {
     int32_t pad0;
     float L[3];
     float intensity;
-    uint64_t off_nodes, off_leaves, off_tris, off_nhat, total_bytes; /* byte offsets inside the blob */
+    uint64_t off_nodes, off_leaves, off_tris, total_bytes; /* byte offsets inside the blob */
     DevSphere spheres[RT_MAX_SPHERES];                    /* ascending id */
 };
 

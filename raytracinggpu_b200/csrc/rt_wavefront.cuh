@@ -119,7 +119,7 @@ __device__ __forceinline__ void closest_sphere(const SceneHeader& h, F3 O, F3 u,
 /* Advance one pixel's path until it ends or needs the mesh. have_hit: (t_hit, sidx, tri) already hold the
  * answer of intersect_all for the current ray (wf_shade); otherwise the segment starts here. */
 template <bool COUNT>
-__device__ __forceinline__ void path_advance(const SceneHeader& h, const WfArgs& g, const float4* __restrict__ nhat, int post_round, int px, F3 O, F3 u,
+__device__ __forceinline__ void path_advance(const SceneHeader& h, const WfArgs& g, const float4* __restrict__ tris, int post_round, int px, F3 O, F3 u,
                                              float n_ray, int depth, bool have_hit, float t_hit, int sidx, int tri, Work& w) {
     const RenderArgs& a = g.a;
     const F3 Lp = f3(h.L[0], h.L[1], h.L[2]);
@@ -168,7 +168,7 @@ __device__ __forceinline__ void path_advance(const SceneHeader& h, const WfArgs&
             n_in = s.n_in;
             n_out = s.n_out;
         } else {
-            const float4 nh = __ldg(nhat + tri); /* N.normalize() :282, precomputed */
+            const float4 nh = __ldg(tris + 4 * (size_t)tri + 3); /* N.normalize() :282, precomputed */
             N = f3(nh.x, nh.y, nh.z);
             albedo = f3(h.mesh_albedo[0], h.mesh_albedo[1], h.mesh_albedo[2]);
             mirror = h.mesh_mirror;
@@ -261,7 +261,7 @@ template <bool COUNT>
 __global__ void __launch_bounds__(WF_THREADS) wf_generate(const __grid_constant__ SceneHeader h, const unsigned char* __restrict__ blob,
                                                          const __grid_constant__ WfArgs g) {
     const RenderArgs& a = g.a;
-    const float4* nhat = reinterpret_cast<const float4*>(blob + h.off_nhat);
+    const float4* tris = reinterpret_cast<const float4*>(blob + h.off_tris);
     const int lane = threadIdx.x & 31;
     const int wt = blockIdx.x * (WF_THREADS / 32) + (threadIdx.x >> 5);
     const int tiles_x = (a.W + 7) >> 3;
@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(WF_THREADS) wf_generate(const __grid_constant_
         if (a.hit_tri) a.hit_tri[px] = -1;
         if (a.hit_t) a.hit_t[px] = RTK_INF;
         if (a.shadow) a.shadow[px] = 2;
-        path_advance<COUNT>(h, g, nhat, 0, px, f3(a.camx, a.camy, a.camz), u0, 1.f, 0, false, 0.f, -1, -1, w);
+        path_advance<COUNT>(h, g, tris, 0, px, f3(a.camx, a.camy, a.camz), u0, 1.f, 0, false, 0.f, -1, -1, w);
     }
     flush_work(w, g.c, COUNT);
 }
@@ -288,7 +288,7 @@ template <bool COUNT>
 __global__ void __launch_bounds__(WF_THREADS) wf_shade(const __grid_constant__ SceneHeader h, const unsigned char* __restrict__ blob,
                                                       const __grid_constant__ WfArgs g) {
     const RenderArgs& a = g.a;
-    const float4* nhat = reinterpret_cast<const float4*>(blob + h.off_nhat);
+    const float4* tris = reinterpret_cast<const float4*>(blob + h.off_tris);
     const int n = g.c->nA[g.round];
     const QEntry* q = g.qA[g.round & 1];
     Work w;
@@ -316,7 +316,7 @@ __global__ void __launch_bounds__(WF_THREADS) wf_shade(const __grid_constant__ S
                 tri = rank_to_tri((unsigned)key, h.n_tris, a.push_order, a.rank_off_bits);
             }
         }
-        path_advance<COUNT>(h, g, nhat, g.round + 1, px, O, u, p2.x, depth, true, t_hit, sidx, tri, w);
+        path_advance<COUNT>(h, g, tris, g.round + 1, px, O, u, p2.x, depth, true, t_hit, sidx, tri, w);
     }
     flush_work(w, g.c, COUNT);
 }
@@ -476,7 +476,9 @@ __global__ void __launch_bounds__(WF_THREADS) wf_traverse(const __grid_constant_
             continue;
         }
 
-        if (nT >= 32 || nN == 0) {
+        /* an N step pops cnt tasks and may push 2 cnt: it needs cnt free entries */
+        const int room = npool_cap - nN;
+        if (nT >= 32 || nN == 0 || (room < 8 && nT > 0)) {
             /* ---- T step: one leaf (<= RT_LEAF_MAX triangles) per lane ---------------------------------------------- */
             const int cnt = min(nT, 32);
             if (COUNT) { dbgTs++; dbgTt += cnt; }
@@ -503,7 +505,7 @@ __global__ void __launch_bounds__(WF_THREADS) wf_traverse(const __grid_constant_
                     for (int i = lf.x; i < i_end; i++) {
                         if (COUNT) w.tris++;
                         float t;
-                        if (!tri_fast(tris + 3 * (size_t)i, O, u, t_limit, t, w.tri_exact) || !(t > a.eps_tri)) continue;
+                        if (!tri_fast(tris + 4 * (size_t)i, O, u, t_limit, t, w.tri_exact) || !(t > a.eps_tri)) continue;
                         if (any) {
                             if (blocks_light(O, u, t, d2)) {
                                 sm.B[slot].w = -1.f; /* no more work for this ray */
@@ -523,11 +525,11 @@ __global__ void __launch_bounds__(WF_THREADS) wf_traverse(const __grid_constant_
             nT -= cnt;
         } else {
             /* ---- N step: one inner node (two child boxes) per lane ------------------------------------------------- */
-            if (nN + 64 > npool_cap) { /* the host sizes the pool from the tree depth; never expected */
+            if (room < 1) { /* node pool full and no leaf work to drain: rt_scene_sync falls back to render_mega */
                 failed = true;
                 break;
             }
-            const int cnt = min(nN, 32);
+            const int cnt = min(min(nN, 32), room);
             if (COUNT) { dbgNs++; dbgNt += cnt; }
             const bool have = lane < cnt;
             int slot = 0;
@@ -539,9 +541,11 @@ __global__ void __launch_bounds__(WF_THREADS) wf_traverse(const __grid_constant_
                 const float4 a4 = sm.A[slot], b4 = sm.B[slot];
                 if (!(b4.w < 0.f)) {
                     const float4* n = nodes + 4 * (size_t)(task & 0x3ffffff);
-                    const float4 q0 = __ldg(n), q1 = __ldg(n + 1), q2 = __ldg(n + 2);
-                    const int2 q3 = __ldg(reinterpret_cast<const int2*>(n + 3));
-                    if (COUNT && __ldg(reinterpret_cast<const int*>(n + 3) + 2) == 0) w.nodes++;
+                    float4 q0, q1, q2, q3f;
+                    ldg256(n, q0, q1);
+                    ldg256(n + 2, q2, q3f);
+                    const int2 q3 = make_int2(__float_as_int(q3f.x), __float_as_int(q3f.y));
+                    if (COUNT && __float_as_int(q3f.z) == 0) w.nodes++;
                     RayCtx c;
                     c.rx = a4.x;
                     c.ry = a4.y;
