@@ -124,7 +124,7 @@ int upload_header(rt_scene* s) {
         /* spheres-only scene: the blob is just the header */
         CUDA_TRY(cudaMalloc(&s->blob, RT_HEADER_BYTES));
         s->blob_bytes = RT_HEADER_BYTES;
-        s->header.off_nodes = s->header.off_leaves = s->header.off_tris = RT_HEADER_BYTES;
+        s->header.off_nodes = s->header.off_tris = RT_HEADER_BYTES;
         s->header.total_bytes = RT_HEADER_BYTES;
     }
     CUDA_TRY(cudaMemcpyAsync(s->blob, &s->header, sizeof(SceneHeader), cudaMemcpyHostToDevice, s->stream));
@@ -332,12 +332,15 @@ int rt_scene_set_mesh(rt_scene* s, const float* vertices, int32_t nv, const int3
     /* packed tree: 64-B records (two child boxes + two int references), a leaf table with at most RT_LEAF_MAX
      * triangles per entry; larger reference leaves hang under virtual nodes that repeat the leaf's own box */
     std::vector<float> packed((size_t)std::max(n_inner, 1) * 16);
-    std::vector<int32_t> leaves; /* pairs: first triangle, count | reference leaf start << 8 */
-    int32_t extra_levels = 0;
+    std::vector<int32_t> leaf_start_of_tri((size_t)nt, 0); /* first triangle of the reference's leaf: the tie-break key */
+    int32_t n_leaves = 0, extra_levels = 0;
     auto new_leaf = [&](int32_t start, int32_t count, int32_t orig_start) -> int32_t {
-        leaves.push_back(start);
-        leaves.push_back((int32_t)(((uint32_t)orig_start << 8) | (uint32_t)count));
-        return -1 - (int32_t)(leaves.size() / 2 - 1);
+        n_leaves++;
+        for (int32_t i = start; i < start + count; i++) leaf_start_of_tri[i] = orig_start;
+        /* an empty leaf (only a hand-made arr_bvh can hold one) points past the last triangle: the kernels clamp
+         * the range to n_tris, so it tests nothing */
+        if (count <= 0) return -1 - ((nt << 2) | 0);
+        return -1 - ((start << 2) | (count - 1));
     };
     /* reference of the subtree holding chunks [lo, hi) of the reference leaf [ts, te) with box `bb` (6 floats) */
     std::function<int32_t(int32_t, int32_t, int32_t, int32_t, const float*, int32_t)> chunk_tree =
@@ -385,15 +388,13 @@ int rt_scene_set_mesh(rt_scene* s, const float* vertices, int32_t nv, const int3
     const int32_t root_ref = child_ref(0);
     n_inner = (int32_t)(packed.size() / 16);
     if (inner_index[0] < 0 && n_inner == 1 && root_ref < 0) n_inner = 0; /* the root is a small leaf: no node records */
-    const int32_t n_leaves = (int32_t)(leaves.size() / 2);
     max_depth += extra_levels;
     if (max_depth > RT_STACK_CAP - 2)
         return rtb::fail(RT_ERR_UNSUPPORTED, "rt_scene_set_mesh: packed BVH depth %d exceeds the traversal stack (%d)", max_depth, RT_STACK_CAP - 2);
 
     /* ---- blob ------------------------------------------------------------------------------------------ */
     const size_t off_nodes = RT_HEADER_BYTES;
-    const size_t off_leaves = off_nodes + (size_t)n_inner * RT_NODE_BYTES;
-    const size_t off_tris = (off_leaves + (size_t)n_leaves * RT_LEAF_BYTES + 63) & ~(size_t)63;
+    const size_t off_tris = (off_nodes + (size_t)n_inner * RT_NODE_BYTES + 63) & ~(size_t)63;
     const size_t total = off_tris + (size_t)nt * RT_TRI_BYTES;
     CUDA_TRY(cudaStreamSynchronize(s->stream));
     if (s->blob_bytes < total || s->blob_bytes > 2 * total + (1u << 20)) {
@@ -413,16 +414,18 @@ int rt_scene_set_mesh(rt_scene* s, const float* vertices, int32_t nv, const int3
     if (err == cudaSuccess) err = cudaMemcpyAsync(d_recs, tri_records, rbytes, cudaMemcpyHostToDevice, s->stream);
     if (err == cudaSuccess && n_inner > 0)
         err = cudaMemcpyAsync(s->blob + off_nodes, packed.data(), (size_t)n_inner * RT_NODE_BYTES, cudaMemcpyHostToDevice, s->stream);
-    if (err == cudaSuccess && n_leaves > 0)
-        err = cudaMemcpyAsync(s->blob + off_leaves, leaves.data(), (size_t)n_leaves * RT_LEAF_BYTES, cudaMemcpyHostToDevice, s->stream);
+    int32_t* d_leaf_start = nullptr;
+    if (err == cudaSuccess) err = cudaMalloc(&d_leaf_start, (size_t)nt * sizeof(int32_t));
+    if (err == cudaSuccess) err = cudaMemcpyAsync(d_leaf_start, leaf_start_of_tri.data(), (size_t)nt * sizeof(int32_t), cudaMemcpyHostToDevice, s->stream);
     if (err == cudaSuccess) {
         const int threads = 256, blocks = (nt + threads - 1) / threads;
-        rtk::repack_triangles<<<blocks, threads, 0, s->stream>>>(d_vertices, d_recs, nt, reinterpret_cast<float4*>(s->blob + off_tris));
+        rtk::repack_triangles<<<blocks, threads, 0, s->stream>>>(d_vertices, d_recs, nt, d_leaf_start, reinterpret_cast<float4*>(s->blob + off_tris));
         err = cudaGetLastError();
     }
     if (err == cudaSuccess) err = cudaStreamSynchronize(s->stream);
     cudaFree(d_vertices);
     if (d_recs) cudaFree(d_recs);
+    if (d_leaf_start) cudaFree(d_leaf_start);
     if (err != cudaSuccess) return rtb::fail(RT_ERR_CUDA, "rt_scene_set_mesh: %s", cudaGetErrorString(err));
 
     h.has_mesh = 1;
@@ -443,7 +446,6 @@ int rt_scene_set_mesh(rt_scene* s, const float* vertices, int32_t nv, const int3
     memcpy(h.box_abs, box_abs, sizeof box_abs);
     s->max_leaf = max_leaf;
     h.off_nodes = off_nodes;
-    h.off_leaves = off_leaves;
     h.off_tris = off_tris;
     h.total_bytes = total;
     s->header_dirty = true;
@@ -525,6 +527,10 @@ int rt_scene_sync(rt_scene* s, rt_stats* stats) {
     if (s->pending && s->last_was_wavefront && getenv("RT_DEBUG_POOL")) {
         unsigned long long d[8];
         cudaMemcpy(d, s->wf_counters->dbg, sizeof d, cudaMemcpyDeviceToHost);
+        rtk::WfCounters hc;
+        cudaMemcpy(&hc, s->wf_counters, sizeof hc, cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[queues] nA %d %d %d %d  nS %d %d %d %d  head %d %d %d %d\n", hc.nA[0], hc.nA[1], hc.nA[2], hc.nA[3], hc.nS[0], hc.nS[1], hc.nS[2],
+                hc.nS[3], hc.head[0], hc.head[1], hc.head[2], hc.head[3]);
         fprintf(stderr, "[pool] N steps %llu tasks %llu (%.1f/step)  T steps %llu tasks %llu (%.1f/step)  admissions %llu\n", d[0], d[1],
                 d[0] ? (double)d[1] / d[0] : 0., d[2], d[3], d[2] ? (double)d[3] / d[2] : 0., d[4]);
     }
@@ -634,7 +640,7 @@ int rt_render(rt_scene* s, const rt_params* p, uint32_t flags, uint8_t* rgb_out,
         s->last_was_wavefront = (variant == 2);
         if (variant == 2) {
             /* node pool of wf_traverse: 32 lanes x (levels of the packed tree + roots of two batches + slack) */
-            const int npool_cap = std::min(32 * (h.max_depth + 4), 512);
+            const int npool_cap = std::min(32 * (h.max_depth + 4), 256);
             const size_t warp_bytes = (sizeof(rtk::WfWarpSmem) + (size_t)npool_cap * sizeof(int) + 15) & ~(size_t)15;
             const size_t trav_smem = warp_bytes * (WF_THREADS / 32);
             if (trav_smem > 200 * 1024) return rtb::fail(RT_ERR_UNSUPPORTED, "rt_render: BVH depth %d needs %zu B of shared memory per block", h.max_depth, trav_smem);

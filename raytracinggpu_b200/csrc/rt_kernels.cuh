@@ -139,7 +139,7 @@ __device__ __forceinline__ bool blocks_light(F3 Padj, F3 su, float t, float D2) 
  * hit has f(t) <= D2 the closest accepted hit, which the reference uses, has too; and if none has, neither has
  * the closest. Children are visited nearest-first in ANY mode so blockers are found early. */
 template <bool COUNT, bool FAST, bool ANY>
-__device__ __forceinline__ void mesh_query(const SceneHeader& h, const float4* __restrict__ nodes, const int2* __restrict__ leaves,
+__device__ __forceinline__ void mesh_query(const SceneHeader& h, const float4* __restrict__ nodes,
                                            const float4* __restrict__ tris, F3 O, F3 u, float eps_tri, int push_order, float D2, float t_limit, float& t_best, int& tri_best, Work& w) {
     t_best = ANY ? t_limit : RTK_INF;
     tri_best = -1;
@@ -190,10 +190,9 @@ __device__ __forceinline__ void mesh_query(const SceneHeader& h, const float4* _
                 continue;
             }
         } else {
-            const int2 lf = __ldg(leaves + (-1 - cur));
-            const int leaf_id = (int)((unsigned)lf.y >> 8); /* first triangle of the reference's leaf */
-            const int i_end = lf.x + (lf.y & 0xff);
-            for (int i = lf.x; i < i_end; i++) {
+            const int code = -1 - cur;
+            const int i_begin = code >> 2, i_end = min(i_begin + (code & 3) + 1, h.n_tris);
+            for (int i = i_begin; i < i_end; i++) {
                 if (COUNT) w.tris++;
                 float t;
                 if (FAST) {
@@ -209,12 +208,13 @@ __device__ __forceinline__ void mesh_query(const SceneHeader& h, const float4* _
                     }
                     continue;
                 }
-                /* exact tie: inside the reference's leaf the first (smallest) index wins, i.e. no update */
+                /* exact tie: the first triangle of the reference's leaf is the key; inside one leaf the smallest index wins */
+                const int leaf_id = (t == t_best) ? __float_as_int(__ldg(tris + 4 * (size_t)i + 3).w) : -2;
                 const bool tie = (tri_best >= 0) && (t == t_best) && (leaf_best != leaf_id) && (push_order == 1 ? (leaf_id < leaf_best) : (leaf_id > leaf_best));
                 if (t < t_best || tie || (tri_best >= 0 && t == t_best && leaf_best == leaf_id && i < tri_best)) {
                     t_best = t;
                     tri_best = i;
-                    leaf_best = leaf_id;
+                    leaf_best = __float_as_int(__ldg(tris + 4 * (size_t)i + 3).w);
                 }
             }
         }
@@ -232,7 +232,7 @@ struct SurfaceHit {
 
 /* Scene::intersect_all: ascending object id, strict t < t_min (lowest id wins exact ties). */
 template <bool COUNT, bool FAST>
-__device__ __forceinline__ SurfaceHit intersect_all(const SceneHeader& h, const float4* __restrict__ nodes, const int2* __restrict__ leaves,
+__device__ __forceinline__ SurfaceHit intersect_all(const SceneHeader& h, const float4* __restrict__ nodes,
                                                     const float4* __restrict__ tris, F3 O, F3 u, float eps_tri, int push_order, Work& w) {
     w.rays++;
     SurfaceHit r;
@@ -251,7 +251,7 @@ __device__ __forceinline__ SurfaceHit intersect_all(const SceneHeader& h, const 
     if (h.has_mesh) {
         float tm;
         int tri;
-        mesh_query<COUNT, FAST, false>(h, nodes, leaves, tris, O, u, eps_tri, push_order, 0.f, 0.f, tm, tri, w);
+        mesh_query<COUNT, FAST, false>(h, nodes, tris, O, u, eps_tri, push_order, 0.f, 0.f, tm, tri, w);
         if (tri >= 0 && (tm < r.t || (tm == r.t && h.mesh_id < r.obj))) {
             r.t = tm;
             r.obj = h.mesh_id;
@@ -267,7 +267,7 @@ __device__ __forceinline__ SurfaceHit intersect_all(const SceneHeader& h, const 
  * equals "some object's reported hit satisfies blocks_light", which lets the spheres be checked first and the
  * mesh be left as soon as one blocker is found. */
 template <bool COUNT, bool FAST>
-__device__ __forceinline__ bool light_blocked(const SceneHeader& h, const float4* __restrict__ nodes, const int2* __restrict__ leaves,
+__device__ __forceinline__ bool light_blocked(const SceneHeader& h, const float4* __restrict__ nodes,
                                               const float4* __restrict__ tris, F3 Padj, F3 su, float D2, float eps_tri, int push_order, Work& w) {
     w.rays++;
     for (int k = 0; k < h.n_spheres; k++) {
@@ -279,7 +279,7 @@ __device__ __forceinline__ bool light_blocked(const SceneHeader& h, const float4
     const float t_limit = sqrtf(D2) * 1.001f + 1e-3f;
     float tm;
     int tri;
-    mesh_query<COUNT, FAST, true>(h, nodes, leaves, tris, Padj, su, eps_tri, push_order, D2, t_limit, tm, tri, w);
+    mesh_query<COUNT, FAST, true>(h, nodes, tris, Padj, su, eps_tri, push_order, D2, t_limit, tm, tri, w);
     return tri >= 0;
 }
 
@@ -290,7 +290,6 @@ __global__ void __launch_bounds__(128) render_mega(const __grid_constant__ Scene
     __syncthreads();
 
     const float4* nodes = reinterpret_cast<const float4*>(blob + h.off_nodes);
-    const int2* leaves = reinterpret_cast<const int2*>(blob + h.off_leaves);
     const float4* tris = reinterpret_cast<const float4*>(blob + h.off_tris);
 
     /* 16x8 pixel tile per block, 8x4 per warp */
@@ -319,7 +318,7 @@ __global__ void __launch_bounds__(128) render_mega(const __grid_constant__ Scene
         const float eps = a.eps_surface;
 
         for (int depth = 0; depth < a.segments; depth++) {
-            const SurfaceHit hit = intersect_all<COUNT, FAST>(h, nodes, leaves, tris, O, u, a.eps_tri, a.push_order, w);
+            const SurfaceHit hit = intersect_all<COUNT, FAST>(h, nodes, tris, O, u, a.eps_tri, a.push_order, w);
             if (depth == 0) {
                 first_obj = hit.obj;
                 first_tri = hit.tri;
@@ -379,9 +378,9 @@ __global__ void __launch_bounds__(128) render_mega(const __grid_constant__ Scene
                 const F3 su = toL / sqrtf(norm2(toL)); /* NORMED_VEC :618 */
                 bool blocked;
                 if (FAST) {
-                    blocked = light_blocked<COUNT, FAST>(h, nodes, leaves, tris, Padj, su, norm2(toL), a.eps_tri, a.push_order, w);
+                    blocked = light_blocked<COUNT, FAST>(h, nodes, tris, Padj, su, norm2(toL), a.eps_tri, a.push_order, w);
                 } else { /* literal reference: closest hit, then the predicate */
-                    const SurfaceHit sh = intersect_all<COUNT, FAST>(h, nodes, leaves, tris, Padj, su, a.eps_tri, a.push_order, w);
+                    const SurfaceHit sh = intersect_all<COUNT, FAST>(h, nodes, tris, Padj, su, a.eps_tri, a.push_order, w);
                     blocked = blocks_light(Padj, su, sh.t, norm2(toL)); /* on a miss t = 1e9f, as the reference leaves it */
                 }
                 if (blocked) { /* :620 */
@@ -446,7 +445,8 @@ __global__ void __launch_bounds__(128) render_mega(const __grid_constant__ Scene
 
 /* Mesh repack: reference interchange arrays -> packed triangle records + unit normals (rt_layout.h).
  * e1, e2, N as moller_trumbore forms them (optimized.cu:209-211), N/|N| as :282 does. */
-__global__ void repack_triangles(const float* __restrict__ vertices, const int32_t* __restrict__ recs, int nt, float4* __restrict__ tris) {
+__global__ void repack_triangles(const float* __restrict__ vertices, const int32_t* __restrict__ recs, int nt, const int32_t* __restrict__ leaf_start,
+                                 float4* __restrict__ tris) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nt) return;
     const int32_t* r = recs + (size_t)i * 10;
@@ -460,7 +460,7 @@ __global__ void repack_triangles(const float* __restrict__ vertices, const int32
     tris[4 * (size_t)i + 0] = make_float4(A.x, A.y, A.z, e1.x);
     tris[4 * (size_t)i + 1] = make_float4(e1.y, e1.z, e2.x, e2.y);
     tris[4 * (size_t)i + 2] = make_float4(e2.z, N.x, N.y, N.z);
-    tris[4 * (size_t)i + 3] = make_float4(nh.x, nh.y, nh.z, 0.f);
+    tris[4 * (size_t)i + 3] = make_float4(nh.x, nh.y, nh.z, __int_as_float(leaf_start[i]));
 }
 
 /* Device self-test of div_by_rcp against div.rn.f32 on pseudo-random operands in the range RaySafe admits.

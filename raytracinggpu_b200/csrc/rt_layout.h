@@ -6,12 +6,13 @@
  *
  *   [ SceneHeader, padded to RT_HEADER_BYTES ]
  *   [ inner nodes : n_inner  x 64 B ]   both children's boxes + both child references in one record
- *   [ leaves      : n_leaves x  8 B ]   (first triangle, count <= RT_LEAF_MAX | start of the reference's leaf << 8)
- *   [ triangles   : n_tris   x 64 B ]   A, e1 = B-A, e2 = C-A, N = e1 x e2 (12 floats) + N/|N| (3 floats) + pad:
- *                                       one 64-B-aligned record = two 256-bit loads (LDG.E.256 on sm_100a)
+ *   [ triangles   : n_tris   x 64 B ]   A, e1 = B-A, e2 = C-A, N = e1 x e2 (12 floats) + N/|N| (3 floats) + first
+ *                                       triangle of the reference's leaf (tie-break key): one 64-B-aligned record,
+ *                                       a 256-bit + a 128-bit load per test (LDG.E.256 on sm_100a)
  *
- * A child reference is one int: >= 0 inner-node index, < 0 leaf (-1 - ref indexes the leaf table). Leaves hold at
- * most RT_LEAF_MAX triangles: a larger leaf of the reference BVH (the cat has one of 73) is hung under a small
+ * A child reference is one int: >= 0 inner-node index; < 0 a leaf, -1 - ref = (first triangle << 2) | (count - 1)
+ * (triangle indices stay below 2^24 because the reference stores them in floats). Leaves hold at most RT_LEAF_MAX
+ * triangles: a larger leaf of the reference BVH (the cat has one of 73) is hung under a small
  * tree of "virtual" inner nodes whose child boxes all equal the leaf's own box. The box test of a virtual node
  * repeats the computation that already succeeded for its parent, so exactly the reference's triangles are still
  * tested, while every traversal task stays small and uniform.
@@ -31,7 +32,6 @@
 #define RT_MAX_SPHERES 16
 #define RT_HEADER_BYTES 1024
 #define RT_NODE_BYTES 64
-#define RT_LEAF_BYTES 8
 #define RT_LEAF_MAX 4
 #define RT_TRI_BYTES 64
 #define RT_STACK_CAP 64 /* traversal stack entries; rt_scene_set_mesh rejects deeper trees */
@@ -52,7 +52,7 @@ struct SceneHeader {
     int32_t n_spheres;
     int32_t has_mesh;
     int32_t n_inner;   /* inner-node records, virtual ones included */
-    int32_t n_leaves;  /* leaf-table entries */
+    int32_t n_leaves;  /* leaves of the packed tree (<= RT_LEAF_MAX triangles each) */
     int32_t n_tris;
     int32_t max_depth; /* levels of the packed tree (virtual levels included): bound on the traversal stacks */
     int32_t mesh_id;
@@ -65,7 +65,7 @@ struct SceneHeader {
     int32_t pad0;
     float L[3];
     float intensity;
-    uint64_t off_nodes, off_leaves, off_tris, total_bytes; /* byte offsets inside the blob */
+    uint64_t off_nodes, off_tris, total_bytes; /* byte offsets inside the blob */
     DevSphere spheres[RT_MAX_SPHERES];                    /* ascending id */
 };
 

@@ -74,16 +74,13 @@ __device__ __forceinline__ int rank_to_tri(unsigned rank, int n_tris, int push_o
     return leaf_start + (int)(rank & ((1u << off_bits) - 1u));
 }
 
-/* append one entry to a global queue; the lanes that reach this point together share one atomic */
-__device__ __forceinline__ int queue_slot(int* counter) {
-    const unsigned m = __activemask();
-    const int leader = __ffs(m) - 1;
-    const int lane = threadIdx.x & 31;
-    int base = 0;
-    if (lane == leader) base = atomicAdd(counter, __popc(m));
-    base = __shfl_sync(m, base, leader);
-    return base + __popc(m & ((1u << lane) - 1u));
-}
+/* what a pixel's path needs next from the mesh (at most one query per path_advance call) */
+struct Post {
+    int kind; /* 0 nothing, WF_MODE_CLOSEST, WF_MODE_ANY */
+    F3 O, u;
+    float aux, n_ray;
+    int packed;
+};
 
 __device__ __forceinline__ void store_entry(QEntry* q, int slot, F3 O, F3 u, float aux, int pixel, float n_ray, int packed, unsigned long long res) {
     float4* p = reinterpret_cast<float4*>(q + slot);
@@ -119,8 +116,8 @@ __device__ __forceinline__ void closest_sphere(const SceneHeader& h, F3 O, F3 u,
 /* Advance one pixel's path until it ends or needs the mesh. have_hit: (t_hit, sidx, tri) already hold the
  * answer of intersect_all for the current ray (wf_shade); otherwise the segment starts here. */
 template <bool COUNT>
-__device__ __forceinline__ void path_advance(const SceneHeader& h, const WfArgs& g, const float4* __restrict__ tris, int post_round, int px, F3 O, F3 u,
-                                             float n_ray, int depth, bool have_hit, float t_hit, int sidx, int tri, Work& w) {
+__device__ __forceinline__ void path_advance(const SceneHeader& h, const WfArgs& g, const float4* __restrict__ tris, int px, F3 O, F3 u, float n_ray,
+                                             int depth, bool have_hit, float t_hit, int sidx, int tri, Work& w, Post& post) {
     const RenderArgs& a = g.a;
     const F3 Lp = f3(h.L[0], h.L[1], h.L[2]);
     const float eps = a.eps_surface;
@@ -137,8 +134,12 @@ __device__ __forceinline__ void path_advance(const SceneHeader& h, const WfArgs&
                 const RayCtx ctx = make_ray_ctx(O, u, h.box_abs[0], h.box_abs[1], h.box_abs[2]);
                 float tn;
                 if (slab_fast(h.root_mn[0], h.root_mn[1], h.root_mn[2], h.root_mx[0], h.root_mx[1], h.root_mx[2], ctx, tn, w.slab_fallbacks)) {
-                    const int slot = queue_slot(&g.c->nA[post_round]);
-                    store_entry(g.qA[post_round & 1], slot, O, u, t_hit, px, n_ray, (sidx & 0xff) | (depth << 8) | (WF_MODE_CLOSEST << 24), WF_NOHIT);
+                    post.kind = WF_MODE_CLOSEST;
+                    post.O = O;
+                    post.u = u;
+                    post.aux = t_hit;
+                    post.n_ray = n_ray;
+                    post.packed = (sidx & 0xff) | (depth << 8) | (WF_MODE_CLOSEST << 24);
                     return;
                 }
             }
@@ -146,6 +147,9 @@ __device__ __forceinline__ void path_advance(const SceneHeader& h, const WfArgs&
         have_hit = false;
         /* ---- the hit of this segment is known: shade it (optimized.cu:571-650) ---------------------------------- */
         const int obj = tri >= 0 ? h.mesh_id : (sidx >= 0 ? h.spheres[sidx].id : -1);
+#ifdef RT_TRACE
+        if (depth == 0) printf("  first-hit write px %d obj %d tri %d t %f (have_hit path)\n", px, obj, tri, t_hit);
+#endif
         if (depth == 0) {
             if (a.hit_obj) a.hit_obj[px] = obj;
             if (a.hit_tri) a.hit_tri[px] = tri;
@@ -229,13 +233,38 @@ __device__ __forceinline__ void path_advance(const SceneHeader& h, const WfArgs&
                 float tn;
                 if (slab_fast(h.root_mn[0], h.root_mn[1], h.root_mn[2], h.root_mx[0], h.root_mx[1], h.root_mx[2], ctx, tn, w.slab_fallbacks)) {
                     /* the pixel keeps its lit colour unless the traversal finds a blocker, which paints it black */
-                    const int slot = queue_slot(&g.c->nS[post_round]);
-                    store_entry(g.qS, slot, Padj, su, D2, px, 1.f, 0xff | (depth << 8) | (WF_MODE_ANY << 24), 0ull);
+                    post.kind = WF_MODE_ANY;
+                    post.O = Padj;
+                    post.u = su;
+                    post.aux = D2;
+                    post.n_ray = 1.f;
+                    post.packed = 0xff | (depth << 8) | (WF_MODE_ANY << 24);
                 }
             }
             return;
         }
     }
+}
+
+/* Append the warp's queries to the global queues of round post_round: one atomic per warp and queue. Must be
+ * called by all 32 lanes together (the offsets come from full-mask ballots). */
+__device__ __forceinline__ void post_queries(const WfArgs& g, int post_round, const Post& post, int px) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    const unsigned mA = __ballot_sync(FULL, post.kind == WF_MODE_CLOSEST);
+    const unsigned mS = __ballot_sync(FULL, post.kind == WF_MODE_ANY);
+    int baseA = 0, baseS = 0;
+    if (lane == 0) {
+        if (mA) baseA = atomicAdd(&g.c->nA[post_round], __popc(mA));
+        if (mS) baseS = atomicAdd(&g.c->nS[post_round], __popc(mS));
+    }
+    baseA = __shfl_sync(FULL, baseA, 0);
+    baseS = __shfl_sync(FULL, baseS, 0);
+    if (post.kind == WF_MODE_CLOSEST)
+        store_entry(g.qA[post_round & 1], baseA + __popc(mA & lt), post.O, post.u, post.aux, px, post.n_ray, post.packed, WF_NOHIT);
+    else if (post.kind == WF_MODE_ANY)
+        store_entry(g.qS, baseS + __popc(mS & lt), post.O, post.u, post.aux, px, post.n_ray, post.packed, 0ull);
 }
 
 __device__ __forceinline__ void flush_work(const Work& w, WfCounters* c, bool count) {
@@ -269,8 +298,10 @@ __global__ void __launch_bounds__(WF_THREADS) wf_generate(const __grid_constant_
     const int kr = (wt / tiles_x) * 4 + (lane >> 3);
     Work w;
     w.rays = w.nodes = w.tris = w.max_stack = w.slab_fallbacks = w.tri_exact = 0;
+    Post post;
+    post.kind = 0;
+    const int px = kr * a.W + j;
     if (j < a.W && kr < a.rows) {
-        const int px = kr * a.W + j;
         const int i = a.row_begin + kr * a.row_step;
         const F3 uc = f3((float)j - (float)a.W / 2 + 0.5f, (float)a.H / 2 - (float)i - 0.5f, a.z); /* optimized.cu:751, exact in float */
         const F3 u0 = normalized(uc); /* sigma == 0: the jitter terms of :758 are exactly 0 */
@@ -278,8 +309,9 @@ __global__ void __launch_bounds__(WF_THREADS) wf_generate(const __grid_constant_
         if (a.hit_tri) a.hit_tri[px] = -1;
         if (a.hit_t) a.hit_t[px] = RTK_INF;
         if (a.shadow) a.shadow[px] = 2;
-        path_advance<COUNT>(h, g, tris, 0, px, f3(a.camx, a.camy, a.camz), u0, 1.f, 0, false, 0.f, -1, -1, w);
+        path_advance<COUNT>(h, g, tris, px, f3(a.camx, a.camy, a.camz), u0, 1.f, 0, false, 0.f, -1, -1, w, post);
     }
+    post_queries(g, 0, post, px);
     flush_work(w, g.c, COUNT);
 }
 
@@ -295,28 +327,36 @@ __global__ void __launch_bounds__(WF_THREADS) wf_shade(const __grid_constant__ S
     w.rays = w.nodes = w.tris = w.max_stack = w.slab_fallbacks = w.tri_exact = 0;
     const int n_round = (n + 31) & ~31; /* whole warps stay in the loop so that flush_work sees 32 lanes */
     for (int e = blockIdx.x * WF_THREADS + threadIdx.x; e < n_round; e += gridDim.x * WF_THREADS) {
-        if (e >= n) continue;
-        const float4* p = reinterpret_cast<const float4*>(q + e);
-        const float4 p0 = p[0], p1 = p[1], p2 = p[2];
-        const F3 O = f3(p0.x, p0.y, p0.z), u = f3(p1.x, p1.y, p1.z);
-        float t_hit = p0.w;
-        const int px = __float_as_int(p1.w);
-        const int packed = __float_as_int(p2.y);
-        int sidx = packed & 0xff;
-        if (sidx == 0xff) sidx = -1;
-        const int depth = (packed >> 8) & 0xffff;
-        const unsigned long long key = ((unsigned long long)__float_as_uint(p2.w) << 32) | __float_as_uint(p2.z);
-        int tri = -1;
-        if (key != WF_NOHIT) { /* mesh vs spheres: ascending id, strict < (optimized.cu:549) */
-            const float tm = __uint_as_float((unsigned)(key >> 32));
-            const int sid = sidx >= 0 ? h.spheres[sidx].id : -1;
-            if (tm < t_hit || (tm == t_hit && h.mesh_id < sid)) {
-                t_hit = tm;
-                sidx = -1;
-                tri = rank_to_tri((unsigned)key, h.n_tris, a.push_order, a.rank_off_bits);
+        Post post;
+        post.kind = 0;
+        int px = 0;
+        if (e < n) {
+            const float4* p = reinterpret_cast<const float4*>(q + e);
+            const float4 p0 = p[0], p1 = p[1], p2 = p[2];
+            const F3 O = f3(p0.x, p0.y, p0.z), u = f3(p1.x, p1.y, p1.z);
+            float t_hit = p0.w;
+            px = __float_as_int(p1.w);
+            const int packed = __float_as_int(p2.y);
+            int sidx = packed & 0xff;
+            if (sidx == 0xff) sidx = -1;
+            const int depth = (packed >> 8) & 0xffff;
+            const unsigned long long key = ((unsigned long long)__float_as_uint(p2.w) << 32) | __float_as_uint(p2.z);
+            int tri = -1;
+            if (key != WF_NOHIT) { /* mesh vs spheres: ascending id, strict < (optimized.cu:549) */
+                const float tm = __uint_as_float((unsigned)(key >> 32));
+                const int sid = sidx >= 0 ? h.spheres[sidx].id : -1;
+                if (tm < t_hit || (tm == t_hit && h.mesh_id < sid)) {
+                    t_hit = tm;
+                    sidx = -1;
+                    tri = rank_to_tri((unsigned)key, h.n_tris, a.push_order, a.rank_off_bits);
+                }
             }
+#ifdef RT_TRACE
+            printf("  shade e %d px %d key %llx t_hit %f sidx %d tri %d depth %d\n", e, px, key, t_hit, sidx, tri, depth);
+#endif
+            path_advance<COUNT>(h, g, tris, px, O, u, p2.x, depth, true, t_hit, sidx, tri, w, post);
         }
-        path_advance<COUNT>(h, g, tris, g.round + 1, px, O, u, p2.x, depth, true, t_hit, sidx, tri, w);
+        post_queries(g, g.round + 1, post, px);
     }
     flush_work(w, g.c, COUNT);
 }
@@ -341,19 +381,6 @@ __global__ void __launch_bounds__(WF_THREADS) wf_shade(const __grid_constant__ S
  * outstanding tasks (kept warp-uniform with ballots) reaches zero, then its results go back to the queue
  * entries. Shadow rays stop generating work once a blocker is found.
  */
-/* position k of the strided visiting order of a queue of n entries (a permutation of 0..n-1): the queue is cut
- * into 32 equal runs and read round-robin, one entry of each run per batch */
-__device__ __forceinline__ int qperm(int k, int n) {
-    const int run = (n + 31) >> 5;      /* entries per run */
-    const int full = n - 31 * run;      /* length of the last run (may be shorter, > 0 when n > 31 * run) */
-    /* row-major walk over a 32 x run grid whose last row has `full` valid cells */
-    if (full <= 0) return k;            /* tiny queues: identity */
-    const int rows_full = full * 32;    /* first `full` columns hold 32 entries each */
-    if (k < rows_full) return (k & 31) * run + (k >> 5);
-    const int k2 = k - rows_full;       /* remaining columns hold 31 entries each */
-    return (k2 % 31) * run + full + k2 / 31;
-}
-
 #define WF_SLOTS 64
 #define WF_TPOOL 160
 
@@ -373,7 +400,6 @@ __global__ void __launch_bounds__(WF_THREADS) wf_traverse(const __grid_constant_
     extern __shared__ __align__(16) unsigned char wf_smem[];
     const RenderArgs& a = g.a;
     const float4* nodes = reinterpret_cast<const float4*>(blob + h.off_nodes);
-    const int2* leaves = reinterpret_cast<const int2*>(blob + h.off_leaves);
     const float4* tris = reinterpret_cast<const float4*>(blob + h.off_tris);
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -393,6 +419,9 @@ __global__ void __launch_bounds__(WF_THREADS) wf_traverse(const __grid_constant_
     int nN = 0, nT = 0;               /* pool fill (warp-uniform) */
     int out0 = 0, out1 = 0;           /* outstanding tasks of batch 0 / 1 (warp-uniform) */
     int cnt0 = 0, cnt1 = 0;           /* rays admitted in batch 0 / 1; 0 = batch free */
+    unsigned vm0 = 0, vm1 = 0;        /* lanes (= slots) of batch 0 / 1 that hold a ray */
+    const int n_runs = (total + 7) >> 3;      /* runs of 8 consecutive queue entries */
+    const int n_batches = (n_runs + 3) >> 2;  /* four runs per batch */
     bool exhausted = total == 0;
     bool failed = false;
     unsigned dbgNs = 0, dbgNt = 0, dbgTs = 0, dbgTt = 0, dbgAd = 0;
@@ -403,7 +432,7 @@ __global__ void __launch_bounds__(WF_THREADS) wf_traverse(const __grid_constant_
         for (int b = 0; b < 2; b++) {
             const int cnt = b ? cnt1 : cnt0, out = b ? out1 : out0;
             if (cnt > 0 && out == 0) {
-                if (lane < cnt) {
+                if (((b ? vm1 : vm0) >> lane) & 1u) {
                     const int slot = b * 32 + lane;
                     const int e = sm.entry[slot];
                     if (e < nA) {
@@ -425,20 +454,24 @@ __global__ void __launch_bounds__(WF_THREADS) wf_traverse(const __grid_constant_
         }
         /* ---- admit a batch of 32 rays when a batch is free and the pools run low ----------------------------------- */
         if (!exhausted && (cnt0 == 0 || cnt1 == 0) && nN + nT < 48) {
-            int base = 0;
-            if (lane == 0) base = atomicAdd(head, 32);
-            base = __shfl_sync(FULL, base, 0);
-            const int take = min(32, total - base);
-            if (take <= 0) {
+            /* A batch is four runs of 8 consecutive queue entries taken a quarter of the queue apart: neighbouring
+             * entries are neighbouring pixels, whose tasks address the same nodes and triangles (few cache lines per
+             * step), while the expensive rays, which cluster in the image (the cat's head), are spread over four
+             * times as many warps, so no warp is left with 32 of them at the end of the launch. */
+            int j = 0;
+            if (lane == 0) j = atomicAdd(head, 1);
+            j = __shfl_sync(FULL, j, 0);
+            if (j >= n_batches) {
                 exhausted = true;
             } else {
                 const int b = cnt0 == 0 ? 0 : 1;
                 if (COUNT) dbgAd++;
-                if (lane < take) {
-                    /* batch b of the queue is {b, b + stride, b + 2 stride, ...}: neighbouring queue entries are
-                     * neighbouring pixels, and the expensive rays cluster (the cat's head); striding gives every batch
-                     * the same mix, so no warp is left with 32 heavy rays at the end of the launch */
-                    const int e = qperm(base + lane, total);
+                const int run = (lane >> 3) * n_batches + j;
+                const int e = run * 8 + (lane & 7);
+                const bool valid = run < n_runs && e < total;
+                const unsigned vmask = __ballot_sync(FULL, valid);
+                const int take = __popc(vmask);
+                if (valid) {
                     const float4* p = reinterpret_cast<const float4*>(e < nA ? (qA + e) : (qS + (e - nA)));
                     const float4 p0 = __ldcg(p), p1 = __ldcg(p + 1);
                     const RayCtx c = make_ray_ctx(f3(p0.x, p0.y, p0.z), f3(p1.x, p1.y, p1.z), h.box_abs[0], h.box_abs[1], h.box_abs[2]);
@@ -452,17 +485,20 @@ __global__ void __launch_bounds__(WF_THREADS) wf_traverse(const __grid_constant_
                     sm.best[slot] = WF_NOHIT;
                     sm.entry[slot] = e;
                     const int task = (slot << 26) | (h.root_ref >= 0 ? h.root_ref : (-1 - h.root_ref));
-                    if (h.root_ref >= 0) npool[nN + lane] = task;
-                    else sm.tpool[nT + lane] = task;
+                    const int pos = __popc(vmask & lt_mask);
+                    if (h.root_ref >= 0) npool[nN + pos] = task;
+                    else sm.tpool[nT + pos] = task;
                 }
                 if (h.root_ref >= 0) nN += take;
                 else nT += take;
                 if (b) {
                     cnt1 = take;
                     out1 = take;
+                    vm1 = vmask;
                 } else {
                     cnt0 = take;
                     out0 = take;
+                    vm0 = vmask;
                 }
                 __syncwarp();
             }
@@ -491,18 +527,17 @@ __global__ void __launch_bounds__(WF_THREADS) wf_traverse(const __grid_constant_
                 const float d2 = sm.B[slot].w;
                 live = !(d2 < 0.f);
                 if (live) {
-                    const int2 lf = __ldg(leaves + (task & 0x3ffffff));
+                    const int code = task & 0x3ffffff; /* first triangle << 2 | count - 1 */
                     const float4 c4 = sm.C[slot], d4 = sm.D[slot];
                     const F3 O = f3(c4.x, c4.y, c4.z), u = f3(d4.x, d4.y, d4.z);
                     const bool any = c4.w < RTK_INF;
-                    const int leaf_start = (int)((unsigned)lf.y >> 8);
-                    const int i_end = lf.x + (lf.y & 0xff);
+                    const int i_begin = code >> 2, i_end = min(i_begin + (code & 3) + 1, h.n_tris);
                     float t_limit = c4.w;
                     if (!any) {
                         const unsigned long long cur = sm.best[slot];
                         if (cur != WF_NOHIT) t_limit = __uint_as_float((unsigned)(cur >> 32));
                     }
-                    for (int i = lf.x; i < i_end; i++) {
+                    for (int i = i_begin; i < i_end; i++) {
                         if (COUNT) w.tris++;
                         float t;
                         if (!tri_fast(tris + 4 * (size_t)i, O, u, t_limit, t, w.tri_exact) || !(t > a.eps_tri)) continue;
@@ -512,6 +547,7 @@ __global__ void __launch_bounds__(WF_THREADS) wf_traverse(const __grid_constant_
                                 break;
                             }
                         } else {
+                            const int leaf_start = __float_as_int(__ldg(tris + 4 * (size_t)i + 3).w);
                             const unsigned rank = tie_rank(i, leaf_start, h.n_tris, a.push_order, a.rank_off_bits);
                             atomicMin(&sm.best[slot], ((unsigned long long)__float_as_uint(t) << 32) | rank);
                             if (t < t_limit) t_limit = t;
