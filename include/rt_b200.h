@@ -164,6 +164,9 @@ int rt_scene_set_light(rt_scene* s, const float L[3], float intensity);
 int rt_scene_blob_size(rt_scene* s, size_t* bytes);
 int rt_scene_blob_export(rt_scene* s, void** device_ptr, size_t* bytes);
 int rt_scene_blob_import(rt_scene* s, const void* device_ptr, size_t bytes);
+/* Copy the blob into a caller-owned DEVICE buffer of at least rt_scene_blob_size bytes (e.g. the tensor a
+ * broadcast collective sends from rank 0). */
+int rt_scene_blob_copy_out(rt_scene* s, void* device_dst, size_t bytes);
 
 /* The render call: replaces KernelLaunch<<<>>> + cudaDeviceSynchronize + cudaMemcpy D2H (optimized.cu:828-856).
  * rgb_out: rows*W*3 bytes, interleaved RGB, top row first, rows = rows rendered by this call. Each output

@@ -48,6 +48,7 @@ SIGNATURES = {
     "rt_scene_blob_size": (C.c_int, [_vp, C.POINTER(C.c_size_t)]),
     "rt_scene_blob_export": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(C.c_size_t)]),
     "rt_scene_blob_import": (C.c_int, [_vp, _vp, C.c_size_t]),
+    "rt_scene_blob_copy_out": (C.c_int, [_vp, _vp, C.c_size_t]),
     "rt_render": (C.c_int, [_vp, C.POINTER(rt_params), C.c_uint32, _vp, _vp, _vp, _vp, _vp, C.POINTER(rt_stats)]),
     "rt_scene_sync": (C.c_int, [_vp, C.POINTER(rt_stats)]),
     "rt_selftest_division": (C.c_int, [C.c_int, _u64, C.c_int, C.c_int, C.POINTER(_u64)]),
@@ -250,6 +251,14 @@ class Scene:
         p, n = C.c_void_p(), C.c_size_t()
         _check(lib().rt_scene_blob_export(self._h, C.byref(p), C.byref(n)))
         return p.value, n.value
+
+    def blob_size(self):
+        n = C.c_size_t()
+        _check(lib().rt_scene_blob_size(self._h, C.byref(n)))
+        return n.value
+
+    def blob_copy_out(self, device_ptr, nbytes):
+        _check(lib().rt_scene_blob_copy_out(self._h, C.c_void_p(int(device_ptr)), int(nbytes)))
 
     def blob_import(self, device_ptr, nbytes):
         _check(lib().rt_scene_blob_import(self._h, C.c_void_p(int(device_ptr)), int(nbytes)))

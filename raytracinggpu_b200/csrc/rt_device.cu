@@ -471,6 +471,18 @@ int rt_scene_blob_export(rt_scene* s, void** device_ptr, size_t* bytes) {
     return RT_OK;
 }
 
+int rt_scene_blob_copy_out(rt_scene* s, void* device_dst, size_t bytes) {
+    void* src = nullptr;
+    size_t n = 0;
+    int rc = rt_scene_blob_export(s, &src, &n);
+    if (rc != RT_OK) return rc;
+    if (!device_dst || bytes < n) return rtb::fail(RT_ERR_INVALID, "rt_scene_blob_copy_out: destination of %zu bytes is smaller than the blob (%zu)", bytes, n);
+    DeviceGuard g(s->device);
+    CUDA_TRY(cudaMemcpyAsync(device_dst, src, n, cudaMemcpyDeviceToDevice, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return RT_OK;
+}
+
 int rt_scene_blob_import(rt_scene* s, const void* device_ptr, size_t bytes) {
     if (!s || !device_ptr || bytes < RT_HEADER_BYTES) return rtb::fail(RT_ERR_INVALID, "rt_scene_blob_import: bad argument");
     DeviceGuard g(s->device);
