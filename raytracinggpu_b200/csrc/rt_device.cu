@@ -62,6 +62,10 @@ struct rt_scene {
     rtk::WfCounters* wf_counters = nullptr;
     rtk::WfCounters* h_wf_counters = nullptr; /* pinned */
     bool last_was_wavefront = false;
+    int* wf_spill = nullptr;  /* node-pool overflow area of wf_traverse */
+    size_t wf_spill_ints = 0;
+    int* dbg_warps = nullptr; /* RT_DEBUG_WARPS=<file>: per-warp timeline of wf_traverse (count_work renders) */
+    size_t dbg_warps_ints = 0;
 };
 
 namespace {
@@ -211,6 +215,8 @@ void rt_scene_destroy(rt_scene* s) {
     if (s->h_counters) cudaFreeHost(s->h_counters);
     if (s->wf_queue) cudaFree(s->wf_queue);
     if (s->wf_counters) cudaFree(s->wf_counters);
+    if (s->dbg_warps) cudaFree(s->dbg_warps);
+    if (s->wf_spill) cudaFree(s->wf_spill);
     if (s->h_wf_counters) cudaFreeHost(s->h_wf_counters);
     for (int k = 0; k < 5; k++)
         if (s->scratch[k]) cudaFree(s->scratch[k]);
@@ -546,6 +552,14 @@ int rt_scene_sync(rt_scene* s, rt_stats* stats) {
         fprintf(stderr, "[pool] N steps %llu tasks %llu (%.1f/step)  T steps %llu tasks %llu (%.1f/step)  admissions %llu\n", d[0], d[1],
                 d[0] ? (double)d[1] / d[0] : 0., d[2], d[3], d[2] ? (double)d[3] / d[2] : 0., d[4]);
     }
+    if (s->pending && s->last_was_wavefront && s->dbg_warps && getenv("RT_DEBUG_WARPS")) {
+        std::vector<int> hst(s->dbg_warps_ints);
+        cudaMemcpy(hst.data(), s->dbg_warps, hst.size() * sizeof(int), cudaMemcpyDeviceToHost);
+        if (FILE* f = fopen(getenv("RT_DEBUG_WARPS"), "wb")) {
+            fwrite(hst.data(), sizeof(int), hst.size(), f);
+            fclose(f);
+        }
+    }
     s->pending = false;
     if (failed) return rtb::fail(RT_ERR_STATE, "rt_render: traversal task pool overflow (BVH deeper than the upload-time bound)");
     return RT_OK;
@@ -652,7 +666,8 @@ int rt_render(rt_scene* s, const rt_params* p, uint32_t flags, uint8_t* rgb_out,
         s->last_was_wavefront = (variant == 2);
         if (variant == 2) {
             /* node pool of wf_traverse: 32 lanes x (levels of the packed tree + roots of two batches + slack) */
-            const int npool_cap = std::min(32 * (h.max_depth + 4), 256);
+            int npool_cap = std::min(32 * (h.max_depth + 4), 256);
+            if (const char* v = getenv("RT_NPOOL_CAP")) npool_cap = std::max(64, std::min(atoi(v), 256)) & ~31; /* test hook: a small pool forces the spill path */
             const size_t warp_bytes = (sizeof(rtk::WfWarpSmem) + (size_t)npool_cap * sizeof(int) + 15) & ~(size_t)15;
             const size_t trav_smem = warp_bytes * (WF_THREADS / 32);
             if (trav_smem > 200 * 1024) return rtb::fail(RT_ERR_UNSUPPORTED, "rt_render: BVH depth %d needs %zu B of shared memory per block", h.max_depth, trav_smem);
@@ -685,6 +700,31 @@ int rt_render(rt_scene* s, const rt_params* p, uint32_t flags, uint8_t* rgb_out,
             g.qS = s->wf_queue + 2 * s->wf_capacity;
             g.c = s->wf_counters;
             g.round = 0;
+            g.dbg_warps = nullptr;
+            {   /* per traversal warp: room for every ray slot holding a full root-to-leaf path of pending siblings */
+                const int spill_cap = WF_SLOTS * (h.max_depth + 2);
+                const size_t ints = (size_t)spill_cap * s->sm_count * s->trav_blocks_per_sm * (WF_THREADS / 32);
+                if (s->wf_spill_ints < ints) {
+                    if (s->wf_spill) cudaFree(s->wf_spill);
+                    s->wf_spill = nullptr;
+                    s->wf_spill_ints = 0;
+                    CUDA_TRY(cudaMalloc(&s->wf_spill, ints * sizeof(int)));
+                    s->wf_spill_ints = ints;
+                }
+                g.spill = s->wf_spill;
+                g.spill_cap = spill_cap;
+            }
+            if (count && getenv("RT_DEBUG_WARPS")) {
+                const size_t ints = (size_t)(segments + 1) * s->sm_count * s->trav_blocks_per_sm * (WF_THREADS / 32) * 16;
+                if (s->dbg_warps_ints < ints) {
+                    if (s->dbg_warps) cudaFree(s->dbg_warps);
+    if (s->wf_spill) cudaFree(s->wf_spill);
+                    CUDA_TRY(cudaMalloc(&s->dbg_warps, ints * sizeof(int)));
+                    s->dbg_warps_ints = ints;
+                }
+                CUDA_TRY(cudaMemsetAsync(s->dbg_warps, 0, ints * sizeof(int), s->stream));
+                g.dbg_warps = s->dbg_warps;
+            }
             CUDA_TRY(cudaMemsetAsync(s->wf_counters, 0, sizeof(rtk::WfCounters), s->stream));
             const unsigned wtiles = (unsigned)((p->W + 7) / 8) * (unsigned)((rows + 3) / 4);
             const unsigned gen_grid = (wtiles + (WF_THREADS / 32) - 1) / (WF_THREADS / 32);

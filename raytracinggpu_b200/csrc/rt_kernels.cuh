@@ -92,10 +92,8 @@ __device__ __forceinline__ bool tri_exact(const float4* __restrict__ rec, F3 O, 
  * comparison is certain to fail (margins 2^-20 .. 2^-18 around 0, 1 and t_limit); everything else — every
  * accepted hit in particular — goes through the exact divisions, so accepted t values are the reference's bits.
  * t_limit: hits with t certainly greater than t_limit are of no interest to the caller (current closest hit). */
-__device__ __forceinline__ bool tri_fast(const float4* __restrict__ rec, F3 O, F3 u, float t_limit, float& t, unsigned int& exact_evals) {
-    float4 q0, q1;
-    ldg256(rec, q0, q1);
-    const float4 q2 = __ldg(rec + 2);
+/* the test proper, on a record already in registers (q0, q1 = first 32 B, q2 = next 16 B) */
+__device__ __forceinline__ bool tri_fast_regs(const float4 q0, const float4 q1, const float4 q2, F3 O, F3 u, float t_limit, float& t, unsigned int& exact_evals) {
     const F3 A = f3(q0.x, q0.y, q0.z), e1 = f3(q0.w, q1.x, q1.y), e2 = f3(q1.z, q1.w, q2.x), N = f3(q2.y, q2.z, q2.w);
     const float d = dot(u, N);
     if (d == 0) return false;
@@ -118,6 +116,43 @@ __device__ __forceinline__ bool tri_fast(const float4* __restrict__ rec, F3 O, F
     if (!(0 <= beta && beta <= 1) || !(0 <= gamma && gamma <= 1)) return false;
     t = nt / d;
     return beta + gamma <= 1 && t > 0;
+}
+
+__device__ __forceinline__ bool tri_fast(const float4* __restrict__ rec, F3 O, F3 u, float t_limit, float& t, unsigned int& exact_evals) {
+    float4 q0, q1;
+    ldg256(rec, q0, q1);
+    const float4 q2 = __ldg(rec + 2);
+    return tri_fast_regs(q0, q1, q2, O, u, t_limit, t, exact_evals);
+}
+
+/* The certified test split in two for latency: tri_screen is straight-line code (no branch), so the screens of
+ * two triangles interleave in one instruction stream; tri_finish evaluates the reference's three divisions for
+ * the few tests the screen could not reject. tri_screen + tri_finish == tri_fast_regs, decision for decision
+ * (every comparison with a NaN is false in both, so an undecidable screen falls through to the exact code). */
+struct TriScreen {
+    float d, nb, ng, nt;
+    bool maybe;
+};
+__device__ __forceinline__ TriScreen tri_screen(const float4 q0, const float4 q1, const float4 q2, F3 O, F3 u, float t_limit) {
+    const F3 A = f3(q0.x, q0.y, q0.z), e1 = f3(q0.w, q1.x, q1.y), e2 = f3(q1.z, q1.w, q2.x), N = f3(q2.y, q2.z, q2.w);
+    TriScreen s;
+    s.d = dot(u, N);
+    const F3 AO = A - O;
+    const F3 c = cross(AO, u);
+    s.nb = dot(e2, c);
+    s.ng = -dot(e1, c);
+    s.nt = dot(AO, N);
+    const float rd = rcp_approx(s.d);
+    const float b = s.nb * rd, g = s.ng * rd, ta = s.nt * rd;
+    const bool rej = (b < -1e-30f) | (b > 1.000001f) | (g < -1e-30f) | (g > 1.000001f) | (b + g > 1.000004f) | (ta < -1e-30f) | (ta * 0.999999f > t_limit);
+    s.maybe = (s.d != 0) & !((fabsf(s.d) >= 1e-30f) & rej);
+    return s;
+}
+__device__ __forceinline__ bool tri_finish(const TriScreen& s, float& t) {
+    const float beta = s.nb / s.d;
+    const float gamma = s.ng / s.d;
+    t = s.nt / s.d;
+    return (0 <= beta) & (beta <= 1) & (0 <= gamma) & (gamma <= 1) & (beta + gamma <= 1) & (t > 0);
 }
 
 /* TriangleMesh::intersect. The reference visits nodes in a fixed LIFO order without pruning and accepts

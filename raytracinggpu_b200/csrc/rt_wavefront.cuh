@@ -60,6 +60,9 @@ struct WfArgs {
     QEntry* qS;    /* shadow queue of the current round */
     WfCounters* c;
     int round;     /* round whose queues this launch consumes (traverse, shade) */
+    int* spill;     /* node-pool overflow area: spill_cap ints per traversal warp (global memory) */
+    int spill_cap;
+    int* dbg_warps; /* investigation aid (RT_DEBUG_WARPS, COUNT kernels only): 16 ints per traversal warp and round */
 };
 
 __device__ __forceinline__ unsigned tie_rank(int i, int leaf_start, int n_tris, int push_order, int off_bits) {
@@ -417,17 +420,24 @@ __global__ void __launch_bounds__(WF_THREADS) wf_traverse(const __grid_constant_
     w.rays = w.nodes = w.tris = w.max_stack = w.slab_fallbacks = w.tri_exact = 0;
 
     int nN = 0, nT = 0;               /* pool fill (warp-uniform) */
+    int nSp = 0;                      /* node tasks parked in the warp's global overflow area (warp-uniform) */
+    int* spill = g.spill + (size_t)(blockIdx.x * (WF_THREADS / 32) + warp) * g.spill_cap;
+    const int half = (npool_cap >> 1) & ~31;
     int out0 = 0, out1 = 0;           /* outstanding tasks of batch 0 / 1 (warp-uniform) */
     int cnt0 = 0, cnt1 = 0;           /* rays admitted in batch 0 / 1; 0 = batch free */
     unsigned vm0 = 0, vm1 = 0;        /* lanes (= slots) of batch 0 / 1 that hold a ray */
     const int n_runs = (total + 7) >> 3;      /* runs of 8 consecutive queue entries */
-    const int n_batches = (n_runs + 3) >> 2;  /* four runs per batch */
+    const int n_quarter = (n_runs + 3) >> 2;  /* the queue is consumed as four interleaved quarters */
     bool exhausted = total == 0;
     bool failed = false;
     unsigned dbgNs = 0, dbgNt = 0, dbgTs = 0, dbgTt = 0, dbgAd = 0;
+    unsigned long long dbg_t0 = 0;
+    long long cycN = 0, cycT = 0, cycA = 0, cycR = 0, cyc_mark = 0;
+    if (COUNT) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t0));
 
     for (;;) {
         /* ---- retire complete batches: results go back to the queue entries ---------------------------------------- */
+        if (COUNT) cyc_mark = clock64();
 #pragma unroll
         for (int b = 0; b < 2; b++) {
             const int cnt = b ? cnt1 : cnt0, out = b ? out1 : out0;
@@ -452,23 +462,29 @@ __global__ void __launch_bounds__(WF_THREADS) wf_traverse(const __grid_constant_
                 else cnt0 = 0;
             }
         }
+        if (COUNT) { const long long c = clock64(); cycR += c - cyc_mark; cyc_mark = c; }
         /* ---- admit a batch of 32 rays when a batch is free and the pools run low ----------------------------------- */
-        if (!exhausted && (cnt0 == 0 || cnt1 == 0) && nN + nT < 48) {
-            /* A batch is four runs of 8 consecutive queue entries taken a quarter of the queue apart: neighbouring
+        if (!exhausted && (cnt0 == 0 || cnt1 == 0) && nN + nT < 48 && nSp == 0) {
+            /* A batch is up to four runs of 8 consecutive queue entries taken a quarter of the queue apart: neighbouring
              * entries are neighbouring pixels, whose tasks address the same nodes and triangles (few cache lines per
              * step), while the expensive rays, which cluster in the image (the cat's head), are spread over four
-             * times as many warps, so no warp is left with 32 of them at the end of the launch. */
-            int j = 0;
-            if (lane == 0) j = atomicAdd(head, 1);
-            j = __shfl_sync(FULL, j, 0);
-            if (j >= n_batches) {
+             * times as many warps. */
+            /* The fuller the pools, the fewer runs are admitted at once: a warp that sits on expensive rays (full pools)
+             * takes on at most 8 more, so the expensive rays of a region end up spread over many warps. */
+            const int fill = nN + nT;
+            const int k = fill < 12 ? 4 : (fill < 28 ? 2 : 1);
+            int r0 = 0;
+            if (lane == 0) r0 = atomicAdd(head, k);
+            r0 = __shfl_sync(FULL, r0, 0);
+            if (r0 >= 4 * n_quarter) {
                 exhausted = true;
             } else {
                 const int b = cnt0 == 0 ? 0 : 1;
                 if (COUNT) dbgAd++;
-                const int run = (lane >> 3) * n_batches + j;
+                const int r = r0 + (lane >> 3);
+                const int run = (r & 3) * n_quarter + (r >> 2); /* consecutive run ids alternate between the four quarters of the queue */
                 const int e = run * 8 + (lane & 7);
-                const bool valid = run < n_runs && e < total;
+                const bool valid = (lane >> 3) < k && r < 4 * n_quarter && run < n_runs && e < total;
                 const unsigned vmask = __ballot_sync(FULL, valid);
                 const int take = __popc(vmask);
                 if (valid) {
@@ -502,6 +518,35 @@ __global__ void __launch_bounds__(WF_THREADS) wf_traverse(const __grid_constant_
                 }
                 __syncwarp();
             }
+        }
+        if (COUNT) { const long long c = clock64(); cycA += c - cyc_mark; cyc_mark = c; }
+        /* The node pool is a LIFO over all rays of the warp; nothing bounds it by the tree depth (a step expands up to 32
+         * nodes of any mix of rays). When it runs full with no leaf work to drain, its older half is parked in global
+         * memory and brought back when the pool has emptied. Rare (the cat: a few warps per frame). */
+        if (nN == 0 && nSp > 0) {
+            const int m = min(nSp, half);
+            for (int i = lane; i < m; i += 32) npool[i] = spill[nSp - m + i];
+            nSp -= m;
+            nN = m;
+            __syncwarp();
+        } else if (npool_cap - nN < 32 && nT == 0 && nN > half) {
+            if (nSp + half > g.spill_cap) { /* overflow area exhausted: reported as an error by rt_scene_sync */
+                failed = true;
+                break;
+            }
+            for (int i = lane; i < half; i += 32) spill[nSp + i] = npool[i];
+            __syncwarp();
+            const int rest = nN - half;
+            for (int i0 = 0; i0 < rest; i0 += 32) { /* slide the younger tasks down, 32 at a time (read, sync, write) */
+                const bool mv = i0 + lane < rest;
+                const int v = mv ? npool[half + i0 + lane] : 0;
+                __syncwarp();
+                if (mv) npool[i0 + lane] = v;
+                __syncwarp();
+            }
+            nSp += half;
+            nN = rest;
+            __syncwarp();
         }
         if (nN == 0 && nT == 0) {
             if (cnt0 == 0 && cnt1 == 0 && exhausted) break;
@@ -537,21 +582,44 @@ __global__ void __launch_bounds__(WF_THREADS) wf_traverse(const __grid_constant_
                         const unsigned long long cur = sm.best[slot];
                         if (cur != WF_NOHIT) t_limit = __uint_as_float((unsigned)(cur >> 32));
                     }
-                    for (int i = i_begin; i < i_end; i++) {
-                        if (COUNT) w.tris++;
-                        float t;
-                        if (!tri_fast(tris + 4 * (size_t)i, O, u, t_limit, t, w.tri_exact) || !(t > a.eps_tri)) continue;
-                        if (any) {
-                            if (blocks_light(O, u, t, d2)) {
-                                sm.B[slot].w = -1.f; /* no more work for this ray */
-                                break;
+                    /* two triangles per iteration, both records requested before either is tested: one L2 round trip per
+                     * pair instead of one per triangle (a lone warp's T step was four dependent round trips long) */
+                    for (int i = i_begin; i < i_end; i += 2) {
+                        const int i2 = min(i + 1, i_end - 1);
+                        float4 p0, p1, r0, r1;
+                        ldg256(tris + 4 * (size_t)i, p0, p1);
+                        ldg256(tris + 4 * (size_t)i2, r0, r1);
+                        const float4 p2 = __ldg(tris + 4 * (size_t)i + 2);
+                        const float4 r2 = __ldg(tris + 4 * (size_t)i2 + 2);
+                        const TriScreen s0 = tri_screen(p0, p1, p2, O, u, t_limit);
+                        TriScreen s1 = tri_screen(r0, r1, r2, O, u, t_limit);
+                        s1.maybe &= i2 != i;
+                        if (COUNT) w.tris += 1 + (i2 != i);
+                        bool stop = false;
+                        if (s0.maybe | s1.maybe) { /* rare per lane (4 % of the tests) */
+#pragma unroll
+                            for (int k = 0; k < 2; k++) {
+                                const TriScreen& sk = k ? s1 : s0;
+                                if (!sk.maybe) continue;
+                                const int ik = k ? i2 : i;
+                                if (COUNT) w.tri_exact++;
+                                float t;
+                                if (!tri_finish(sk, t) || !(t > a.eps_tri)) continue;
+                                if (any) {
+                                    if (blocks_light(O, u, t, d2)) {
+                                        sm.B[slot].w = -1.f; /* no more work for this ray */
+                                        stop = true;
+                                        break;
+                                    }
+                                } else {
+                                    unsigned rank = (unsigned)ik; /* push_order 1: ascending triangle index */
+                                    if (a.push_order != 1) rank = tie_rank(ik, __float_as_int(__ldg(tris + 4 * (size_t)ik + 3).w), h.n_tris, 0, a.rank_off_bits);
+                                    atomicMin(&sm.best[slot], ((unsigned long long)__float_as_uint(t) << 32) | rank);
+                                    if (t < t_limit) t_limit = t;
+                                }
                             }
-                        } else {
-                            const int leaf_start = __float_as_int(__ldg(tris + 4 * (size_t)i + 3).w);
-                            const unsigned rank = tie_rank(i, leaf_start, h.n_tris, a.push_order, a.rank_off_bits);
-                            atomicMin(&sm.best[slot], ((unsigned long long)__float_as_uint(t) << 32) | rank);
-                            if (t < t_limit) t_limit = t;
                         }
+                        if (stop) break;
                     }
                 }
             }
@@ -559,6 +627,7 @@ __global__ void __launch_bounds__(WF_THREADS) wf_traverse(const __grid_constant_
             out1 -= __popc(in1);
             out0 -= cnt - __popc(in1);
             nT -= cnt;
+            if (COUNT) { __syncwarp(); cycT += clock64() - cyc_mark; }
         } else {
             /* ---- N step: one inner node (two child boxes) per lane ------------------------------------------------- */
             if (room < 1) { /* node pool full and no leaf work to drain: rt_scene_sync falls back to render_mega */
@@ -630,10 +699,30 @@ __global__ void __launch_bounds__(WF_THREADS) wf_traverse(const __grid_constant_
             const int pushed = __popc(bNL) + __popc(bNR) + __popc(bTL) + __popc(bTR);
             out1 += pushed1 - __popc(in1);
             out0 += (pushed - pushed1) - (cnt - __popc(in1));
+            if (COUNT) { __syncwarp(); cycN += clock64() - cyc_mark; }
         }
         __syncwarp(); /* pool and slot writes of this step are visible to the next pop */
     }
     if (failed && lane == 0) atomicExch(&g.c->stats[7], 1ull);
+    if (COUNT && g.dbg_warps && lane == 0) {
+        unsigned long long t1;
+        unsigned smid;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        int* d = g.dbg_warps + ((size_t)g.round * gridDim.x * (WF_THREADS / 32) + blockIdx.x * (WF_THREADS / 32) + warp) * 16;
+        d[0] = (int)(unsigned)dbg_t0;
+        d[1] = (int)(unsigned)t1;
+        d[2] = (int)dbgNs;
+        d[3] = (int)dbgNt;
+        d[4] = (int)dbgTs;
+        d[5] = (int)dbgTt;
+        d[6] = (int)dbgAd;
+        d[7] = (int)smid;
+        d[8] = (int)(cycN >> 4);
+        d[9] = (int)(cycT >> 4);
+        d[10] = (int)(cycA >> 4);
+        d[11] = (int)(cycR >> 4);
+    }
     if (COUNT && lane == 0) {
         atomicAdd(&g.c->dbg[0], (unsigned long long)dbgNs);
         atomicAdd(&g.c->dbg[1], (unsigned long long)dbgNt);
