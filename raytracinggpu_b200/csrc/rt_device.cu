@@ -21,6 +21,7 @@
 #include <vector>
 
 #define RT_NCOUNTERS 8
+#define RT_MAX_STRIPS 8
 #define CUDA_TRY(expr)                                                                                         \
     do {                                                                                                       \
         cudaError_t e__ = (expr);                                                                              \
@@ -62,6 +63,10 @@ struct rt_scene {
     rtk::WfCounters* wf_counters = nullptr;
     rtk::WfCounters* h_wf_counters = nullptr; /* pinned */
     bool last_was_wavefront = false;
+    int n_strips = 2;         /* row bands rendered concurrently on separate streams (RT_STRIPS overrides) */
+    cudaStream_t strip_stream[RT_MAX_STRIPS] = {};
+    cudaEvent_t strip_done[RT_MAX_STRIPS] = {};
+    cudaEvent_t fork_ev = nullptr;
     int* wf_spill = nullptr;  /* node-pool overflow area of wf_traverse */
     size_t wf_spill_ints = 0;
     int* dbg_warps = nullptr; /* RT_DEBUG_WARPS=<file>: per-warp timeline of wf_traverse (count_work renders) */
@@ -176,6 +181,7 @@ int rt_scene_create(rt_scene** out, int device) {
     if (!s) return rtb::fail(RT_ERR_NOMEM, "rt_scene_create: out of memory");
     s->device = device;
     if (const char* v = getenv("RT_VARIANT")) s->variant = atoi(v);
+    if (const char* v = getenv("RT_STRIPS")) s->n_strips = std::max(1, std::min(atoi(v), RT_MAX_STRIPS));
     memset(&s->header, 0, sizeof s->header);
     s->header.magic = RT_BLOB_MAGIC;
     s->header.layout_version = 1;
@@ -220,6 +226,11 @@ void rt_scene_destroy(rt_scene* s) {
     if (s->h_wf_counters) cudaFreeHost(s->h_wf_counters);
     for (int k = 0; k < 5; k++)
         if (s->scratch[k]) cudaFree(s->scratch[k]);
+    for (int k = 0; k < RT_MAX_STRIPS; k++) {
+        if (s->strip_stream[k]) cudaStreamDestroy(s->strip_stream[k]);
+        if (s->strip_done[k]) cudaEventDestroy(s->strip_done[k]);
+    }
+    if (s->fork_ev) cudaEventDestroy(s->fork_ev);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
     if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
@@ -521,11 +532,17 @@ int rt_scene_sync(rt_scene* s, rt_stats* stats) {
     DeviceGuard g(s->device);
     if (s->pending) {
         if (s->last_was_wavefront)
-            CUDA_TRY(cudaMemcpyAsync(s->h_counters, s->wf_counters->stats, RT_NCOUNTERS * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->stream));
+            CUDA_TRY(cudaMemcpyAsync(s->h_wf_counters, s->wf_counters, RT_MAX_STRIPS * sizeof(rtk::WfCounters), cudaMemcpyDeviceToHost, s->stream));
         else
             CUDA_TRY(cudaMemcpyAsync(s->h_counters, s->counters, RT_NCOUNTERS * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->stream));
     }
     CUDA_TRY(cudaStreamSynchronize(s->stream));
+    if (s->pending && s->last_was_wavefront) { /* fold the strips' counters */
+        for (int k = 0; k < RT_NCOUNTERS; k++) s->h_counters[k] = 0;
+        for (int st = 0; st < RT_MAX_STRIPS; st++)
+            for (int k = 0; k < RT_NCOUNTERS; k++)
+                s->h_counters[k] = (k == 3) ? std::max<unsigned long long>(s->h_counters[k], s->h_wf_counters[st].stats[k]) : s->h_counters[k] + s->h_wf_counters[st].stats[k];
+    }
     if (stats) {
         memset(stats, 0, sizeof *stats);
         if (s->pending) {
@@ -682,8 +699,13 @@ int rt_render(rt_scene* s, const rt_params* p, uint32_t flags, uint8_t* rgb_out,
                 s->trav_smem = trav_smem;
                 s->sm_count = prop.multiProcessorCount;
                 if (!s->wf_counters) {
-                    CUDA_TRY(cudaMalloc(&s->wf_counters, sizeof(rtk::WfCounters)));
-                    CUDA_TRY(cudaMallocHost(&s->h_wf_counters, sizeof(rtk::WfCounters)));
+                    CUDA_TRY(cudaMalloc(&s->wf_counters, RT_MAX_STRIPS * sizeof(rtk::WfCounters)));
+                    CUDA_TRY(cudaMallocHost(&s->h_wf_counters, RT_MAX_STRIPS * sizeof(rtk::WfCounters)));
+                    CUDA_TRY(cudaEventCreateWithFlags(&s->fork_ev, cudaEventDisableTiming));
+                    for (int k = 0; k < RT_MAX_STRIPS; k++) {
+                        CUDA_TRY(cudaStreamCreateWithFlags(&s->strip_stream[k], cudaStreamNonBlocking));
+                        CUDA_TRY(cudaEventCreateWithFlags(&s->strip_done[k], cudaEventDisableTiming));
+                    }
                 }
             }
             if (s->wf_capacity < npx) {
@@ -693,44 +715,41 @@ int rt_render(rt_scene* s, const rt_params* p, uint32_t flags, uint8_t* rgb_out,
                 CUDA_TRY(cudaMalloc(&s->wf_queue, 3 * npx * sizeof(rtk::QEntry)));
                 s->wf_capacity = npx;
             }
-            rtk::WfArgs g;
-            g.a = a;
-            g.qA[0] = s->wf_queue;
-            g.qA[1] = s->wf_queue + s->wf_capacity;
-            g.qS = s->wf_queue + 2 * s->wf_capacity;
-            g.c = s->wf_counters;
-            g.round = 0;
-            g.dbg_warps = nullptr;
-            {   /* per traversal warp: room for every ray slot holding a full root-to-leaf path of pending siblings */
-                const int spill_cap = WF_SLOTS * (h.max_depth + 2);
-                const size_t ints = (size_t)spill_cap * s->sm_count * s->trav_blocks_per_sm * (WF_THREADS / 32);
+            static const bool dbg_times = getenv("RT_DEBUG_TIMES") != nullptr;
+            const bool dbg_warps = count && getenv("RT_DEBUG_WARPS");
+            /* Strips: the frame is cut into bands of rows, each rendered by its own generate / traverse / shade chain
+             * on its own stream. The end of a persistent traversal launch is a latency-bound tail (a few warps
+             * finishing their expensive rays on an otherwise idle GPU, profiles/r01_notes.md); with strips the tail of
+             * one band is covered by the bulk of the next, and only the last launch's tail is exposed. */
+            int n_strips = s->n_strips;
+            if (rows < 64 * n_strips) n_strips = std::max(1, rows / 64);
+            if (dbg_times || dbg_warps) n_strips = 1;
+            const unsigned pers_grid = (unsigned)(s->sm_count * s->trav_blocks_per_sm);
+            const int spill_cap = WF_SLOTS * (h.max_depth + 2); /* per traversal warp: every ray slot holding a full path of pending siblings */
+            {
+                const size_t ints = (size_t)spill_cap * pers_grid * (WF_THREADS / 32) * n_strips;
                 if (s->wf_spill_ints < ints) {
+                    CUDA_TRY(cudaStreamSynchronize(s->stream));
                     if (s->wf_spill) cudaFree(s->wf_spill);
                     s->wf_spill = nullptr;
                     s->wf_spill_ints = 0;
                     CUDA_TRY(cudaMalloc(&s->wf_spill, ints * sizeof(int)));
                     s->wf_spill_ints = ints;
                 }
-                g.spill = s->wf_spill;
-                g.spill_cap = spill_cap;
             }
-            if (count && getenv("RT_DEBUG_WARPS")) {
-                const size_t ints = (size_t)(segments + 1) * s->sm_count * s->trav_blocks_per_sm * (WF_THREADS / 32) * 16;
+            int* dbg_ptr = nullptr;
+            if (dbg_warps) {
+                const size_t ints = (size_t)(segments + 1) * pers_grid * (WF_THREADS / 32) * 16;
                 if (s->dbg_warps_ints < ints) {
                     if (s->dbg_warps) cudaFree(s->dbg_warps);
-    if (s->wf_spill) cudaFree(s->wf_spill);
                     CUDA_TRY(cudaMalloc(&s->dbg_warps, ints * sizeof(int)));
                     s->dbg_warps_ints = ints;
                 }
                 CUDA_TRY(cudaMemsetAsync(s->dbg_warps, 0, ints * sizeof(int), s->stream));
-                g.dbg_warps = s->dbg_warps;
+                dbg_ptr = s->dbg_warps;
             }
-            CUDA_TRY(cudaMemsetAsync(s->wf_counters, 0, sizeof(rtk::WfCounters), s->stream));
-            const unsigned wtiles = (unsigned)((p->W + 7) / 8) * (unsigned)((rows + 3) / 4);
-            const unsigned gen_grid = (wtiles + (WF_THREADS / 32) - 1) / (WF_THREADS / 32);
-            const unsigned pers_grid = (unsigned)(s->sm_count * s->trav_blocks_per_sm);
-            const unsigned shade_grid = (unsigned)std::min<size_t>((npx + WF_THREADS - 1) / WF_THREADS, (size_t)s->sm_count * 16);
-            static const bool dbg_times = getenv("RT_DEBUG_TIMES") != nullptr;
+            CUDA_TRY(cudaMemsetAsync(s->wf_counters, 0, RT_MAX_STRIPS * sizeof(rtk::WfCounters), s->stream));
+            if (n_strips > 1) CUDA_TRY(cudaEventRecord(s->fork_ev, s->stream));
             cudaEvent_t dev_ev[40];
             int n_ev = 0;
             auto mark = [&]() {
@@ -740,21 +759,56 @@ int rt_render(rt_scene* s, const rt_params* p, uint32_t flags, uint8_t* rgb_out,
                 }
             };
             mark();
-            if (count) rtk::wf_generate<true><<<gen_grid, WF_THREADS, 0, s->stream>>>(s->header, s->blob, g);
-            else rtk::wf_generate<false><<<gen_grid, WF_THREADS, 0, s->stream>>>(s->header, s->blob, g);
-            launches++;
-            mark();
-            for (int r = 0; r <= segments && segments > 0; r++) {
-                g.round = r;
-                if (count) rtk::wf_traverse<true><<<pers_grid, WF_THREADS, trav_smem, s->stream>>>(s->header, s->blob, g, npool_cap);
-                else rtk::wf_traverse<false><<<pers_grid, WF_THREADS, trav_smem, s->stream>>>(s->header, s->blob, g, npool_cap);
+            int row0 = 0;
+            for (int st = 0; st < n_strips; st++) {
+                /* band boundaries on multiples of 8 rows (generate tiles are 8x4) */
+                int row1 = (st == n_strips - 1) ? rows : (int)(((long long)rows * (st + 1) / n_strips) & ~7ll);
+                if (row1 <= row0) continue;
+                const int srows = row1 - row0;
+                const size_t spx = (size_t)srows * p->W, px0 = (size_t)row0 * p->W;
+                cudaStream_t stream = n_strips > 1 ? s->strip_stream[st] : s->stream;
+                if (n_strips > 1) CUDA_TRY(cudaStreamWaitEvent(stream, s->fork_ev, 0));
+                rtk::WfArgs g;
+                g.a = a;
+                g.a.rows = srows;
+                g.a.row_begin = a.row_begin + row0 * a.row_step;
+                g.a.rgb = a.rgb ? a.rgb + px0 * 3 : nullptr;
+                g.a.hit_obj = a.hit_obj ? a.hit_obj + px0 : nullptr;
+                g.a.hit_tri = a.hit_tri ? a.hit_tri + px0 : nullptr;
+                g.a.hit_t = a.hit_t ? a.hit_t + px0 : nullptr;
+                g.a.shadow = a.shadow ? a.shadow + px0 : nullptr;
+                g.qA[0] = s->wf_queue + px0;
+                g.qA[1] = s->wf_queue + s->wf_capacity + px0;
+                g.qS = s->wf_queue + 2 * s->wf_capacity + px0;
+                g.c = s->wf_counters + st;
+                g.round = 0;
+                g.spill = s->wf_spill + (size_t)st * spill_cap * pers_grid * (WF_THREADS / 32);
+                g.spill_cap = spill_cap;
+                g.dbg_warps = dbg_ptr;
+                const unsigned wtiles = (unsigned)((p->W + 7) / 8) * (unsigned)((srows + 3) / 4);
+                const unsigned gen_grid = (wtiles + (WF_THREADS / 32) - 1) / (WF_THREADS / 32);
+                const unsigned shade_grid = (unsigned)std::min<size_t>((spx + WF_THREADS - 1) / WF_THREADS, (size_t)s->sm_count * 16);
+                if (count) rtk::wf_generate<true><<<gen_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
+                else rtk::wf_generate<false><<<gen_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
                 launches++;
                 mark();
-                if (r == segments) break;
-                if (count) rtk::wf_shade<true><<<shade_grid, WF_THREADS, 0, s->stream>>>(s->header, s->blob, g);
-                else rtk::wf_shade<false><<<shade_grid, WF_THREADS, 0, s->stream>>>(s->header, s->blob, g);
-                launches++;
-                mark();
+                for (int r = 0; r <= segments && segments > 0; r++) {
+                    g.round = r;
+                    if (count) rtk::wf_traverse<true><<<pers_grid, WF_THREADS, trav_smem, stream>>>(s->header, s->blob, g, npool_cap);
+                    else rtk::wf_traverse<false><<<pers_grid, WF_THREADS, trav_smem, stream>>>(s->header, s->blob, g, npool_cap);
+                    launches++;
+                    mark();
+                    if (r == segments) break;
+                    if (count) rtk::wf_shade<true><<<shade_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
+                    else rtk::wf_shade<false><<<shade_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
+                    launches++;
+                    mark();
+                }
+                if (n_strips > 1) {
+                    CUDA_TRY(cudaEventRecord(s->strip_done[st], stream));
+                    CUDA_TRY(cudaStreamWaitEvent(s->stream, s->strip_done[st], 0));
+                }
+                row0 = row1;
             }
             if (dbg_times) {
                 cudaStreamSynchronize(s->stream);
