@@ -88,6 +88,18 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(kernel_substr="wf_traverse"):
+    """DRAM bytes per launch of the dominant kernel from the newest committed `ncu --set full` summary
+    (profiles/*_ncu_summary.json, written by tools/ncu_summary.py); None when no capture is committed."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_ncu_summary.json")))
+    if not files:
+        return None, None
+    d = json.load(open(files[-1]))
+    vals = [l["dram_traffic_B"] for l in d["launches"] if kernel_substr in l["kernel"]]
+    return (int(sum(vals) / len(vals)) if vals else None), os.path.basename(files[-1])
+
+
 def build_scene_host(rt):
     """Host side of the launcher (optimized.cu:801-813): load, rescale, build the BVH — with the product's host code."""
     cat = find_cat()
@@ -117,13 +129,22 @@ def run_ours(args):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    mesh, walls, mesh_id, mesh_name = build_scene_host(rt)
-    verts, recs, bvh = mesh.vertices, mesh.tri_records, mesh.arr_bvh
     sc = rt.Scene(local)
     stream = torch.cuda.Stream()
     sc.set_stream(stream.cuda_stream)
-    sc.set_spheres(walls)
-    sc.set_mesh(verts, recs, bvh, id=mesh_id)
+    mesh, walls, mesh_id, mesh_name = build_scene_host(rt)  # every rank keeps the host arrays for its own e2e leg
+    verts, recs, bvh = mesh.vertices, mesh.tri_records, mesh.arr_bvh
+    blob_bytes = 0
+    if world > 1:
+        # the device scene is built and packed on rank 0 only and broadcast once
+        from raytracinggpu_b200 import distributed as rtd
+        if rank == 0:
+            sc.set_spheres(walls)
+            sc.set_mesh(verts, recs, bvh, id=mesh_id)
+        blob_bytes = rtd.broadcast_scene(sc, src=0)
+    else:
+        sc.set_spheres(walls)
+        sc.set_mesh(verts, recs, bvh, id=mesh_id)
     p = rt.params_profile("optimized", W, H, 1, 1)
 
     # frame-parallel for N > 1: rank r renders frames r, r+N, ... of a one-revolution light orbit
@@ -200,21 +221,24 @@ def run_ours(args):
     h2d = int(verts.nbytes + recs.nbytes + bvh.nbytes)
     d2h = int(H * W * 3)
 
+    work = sc.render(p, want=("rgb",), count_work=True)["stats"]  # instrumented pass for the roofline, not timed
+    sharded = sharded_single_frame(rt, torch, sc, stream, world, rank, verts, recs, bvh, mesh_id, walls)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
     # ---- roofline of the dominant kernel (render) ---------------------------------------------------------
-    work = sc.render(p, want=("rgb",), count_work=True)["stats"]  # instrumented pass, not timed
     n_mesh_queries = rays_per_frame  # every ray tests the mesh root box once
     alg_bytes = 32 * (n_mesh_queries + 2 * work["node_visits"]) + 48 * work["tri_tests"] + H * W * 3
     alg_flop = 150 * rays_per_frame + 19 * (n_mesh_queries + 2 * work["node_visits"]) + 50 * work["tri_tests"]
     kernel_ms = float(np.mean(ms_list))
     peak, peak_src = measured_peaks()
+    traffic, traffic_src = ncu_traffic()
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                "traffic": None, "peak_source": peak_src,
+                "traffic": traffic, "traffic_source": "dram__bytes_read+write per wf_traverse launch, profiles/%s" % traffic_src if traffic_src else None, "peak_source": peak_src,
                 "note": "scene (0.3 MB) is L1/L2-resident: compulsory HBM traffic is the 6.2 MB frame; see fp32 for the binding roof",
                 "algorithmic_bytes_per_launch": int(alg_bytes), "node_visits": int(work["node_visits"]), "tri_tests": int(work["tri_tests"]),
                 "fp32": {"achieved_tflops": round(alg_flop / (kernel_ms * 1e-3) / 1e12, 3), "peak_tflops": round(148 * 128 * 2 * 1.965e9 / 1e12, 1),
@@ -232,10 +256,54 @@ def run_ours(args):
            "e2e": {"value": round(e2e_value, 2), "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": round(e2e_s / e2e_steps * 1e3, 4),
                    "steps": e2e_steps},
            "gpu_launches": launches_per_step * args.steps, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
-           "ms_per_frame": round(kernel_ms, 5)}
+           "ms_per_frame": round(kernel_ms, 5), "scene_broadcast_bytes": blob_bytes, "single_frame_sharded": sharded}
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+def sharded_single_frame(rt, torch, sc, stream, world, rank, verts, recs, bvh, mesh_id, walls, frames=8):
+    """BASELINE.json configs[2]: ONE 3840x2160 frame, mirror cat (reflection depth 4), rows interleaved over the ranks,
+    bands all-gathered (NCCL) and de-interleaved on the device. Strong scaling of a single frame; timed with CUDA
+    events around render + gather, max over ranks. Reported beside the headline, not as `value`."""
+    import torch.distributed as dist
+    from raytracinggpu_b200 import distributed as rtd
+    W4, H4 = 3840, 2160
+    if world > 1:
+        if rank == 0:
+            sc.set_mesh(verts, recs, bvh, mirror=1, id=mesh_id)
+        rtd.broadcast_scene(sc, src=0)
+    else:
+        sc.set_mesh(verts, recs, bvh, mirror=1, id=mesh_id)
+    sc.set_light((-10.0, 20.0, 40.0), 3e10)
+    fg = rtd.FrameGather(H4, W4, world, rank, torch.device("cuda", torch.cuda.current_device()))
+    p = fg.apply(rt.params_profile("optimized", W4, H4, 1, 4))
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(frames)]
+    rays = 0
+    for i in range(3 + frames):
+        if world > 1:
+            dist.barrier()
+        with torch.cuda.stream(stream):
+            k = i - 3
+            if k >= 0:
+                ev[k][0].record(stream)
+            sc.render_into(p, rgb=fg.band, flags=rt.RT_RENDER_NO_SYNC)
+            if k >= 0:
+                ev[k][1].record(stream)
+            fg.gather()
+            if k >= 0:
+                ev[k][2].record(stream)
+        rays = int(sc.sync().rays)
+    torch.cuda.synchronize()
+    t = torch.tensor([sum(a.elapsed_time(c) for a, _, c in ev), sum(a.elapsed_time(b) for a, b, _ in ev)], device="cuda", dtype=torch.float64)
+    r = torch.tensor([rays], device="cuda", dtype=torch.int64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(r)
+    total_ms, render_ms = float(t[0].item()) / frames, float(t[1].item()) / frames
+    return {"workload": "BASELINE.json configs[2]: mirror cat 3840x2160, reflection depth 4, rows interleaved over %d GPU(s), all-gather to every rank" % world,
+            "rays_per_frame": int(r.item()), "ms_per_frame": round(total_ms, 4), "render_ms": round(render_ms, 4), "gather_ms": round(total_ms - render_ms, 4),
+            "mrays_per_s": round(int(r.item()) / (total_ms * 1e-3) / 1e6, 1), "gather_bytes_per_rank": int(fg.band.numel()), "frames": frames, "scaling": "strong"}
 
 
 def cpu_reference_sample(budget_s=12.0, threads=0):

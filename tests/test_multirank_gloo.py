@@ -32,16 +32,20 @@ def _worker(rank, world, port, mode, H, W, q):
     p = profiles.params("optimized", W, H, 1, 1)
     p.row_begin, p.row_step, p.row_count = sharding.rows_for_rank(H, rank, world, mode)
     o = scenes.run_oracle(desc, p, threads=1, want=("rgb",))
-    pad = sharding.padded_rows(H, world, mode)
-    band = np.zeros((pad, W, 3), np.uint8)
-    band[:o["rgb"].shape[0]] = o["rgb"]
-    mine = torch.from_numpy(band)
-    gathered = [torch.empty_like(mine) for _ in range(world)]
-    dist.all_gather(gathered, mine)
+    # the product's gather helper (raytracinggpu_b200/distributed.py), on CPU tensors over gloo
+    from raytracinggpu_b200 import distributed as rtd
+    fg = rtd.FrameGather(H, W, world, rank, torch.device("cpu"), mode)
+    assert (fg.row_begin, fg.row_step, fg.row_count) == (p.row_begin, p.row_step, p.row_count)
+    fg.band[:o["rgb"].shape[0]] = torch.from_numpy(o["rgb"])
+    frame_t = fg.gather()
+    # and the plain numpy assembly of an explicit all_gather
+    gathered = [torch.empty_like(fg.band) for _ in range(world)]
+    dist.all_gather(gathered, fg.band)
     rays = torch.tensor([o["work"]["rays"]], dtype=torch.int64)
     dist.all_reduce(rays)
+    frame = sharding.assemble(torch.stack(gathered).numpy(), H, world, mode)
+    assert np.array_equal(frame, frame_t.numpy())
     if rank == 0:
-        frame = sharding.assemble(torch.stack(gathered).numpy(), H, world, mode)
         q.put((frame, int(rays.item())))
     dist.barrier()
     dist.destroy_process_group()
