@@ -245,7 +245,8 @@ def run_ours(args):
                          "frac": round(alg_flop / (kernel_ms * 1e-3) / (148 * 128 * 2 * 1.965e9), 4)}}
 
     # ---- CPU baseline: the reference's own classes on this box's host cores (bounded sample) ---------------
-    cpu_baseline = cpu_reference_sample(budget_s=12.0)
+    # N = 1 only; torchrun exports OMP_NUM_THREADS=1, so the thread count is passed explicitly
+    cpu_baseline = cpu_reference_sample(budget_s=12.0, threads=os.cpu_count() or 1) if world == 1 else None
 
     out = {"metric": METRIC, "value": round(value, 2), "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": round(ms_per_step, 5), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -347,7 +348,7 @@ def run_reference(args):
     use_ref = bool(cat and pyoracle.ref_cpu_available())
     if use_ref:
         def frame():
-            return pyoracle.ref_cpu_render(cat, 1, W, H, 1, 0, 0, hits=False)["seconds"]
+            return pyoracle.ref_cpu_render(cat, 1, W, H, 1, 0, cores, hits=False)["seconds"]
         kind = "reference"
     else:
         from oracle import profiles, scenes
@@ -355,7 +356,7 @@ def run_reference(args):
         p = profiles.params("optimized", W, H, 1, 1)
 
         def frame():
-            return scenes.run_oracle(desc, p, want=("rgb",))["work"]["seconds"]
+            return scenes.run_oracle(desc, p, threads=cores, want=("rgb",))["work"]["seconds"]
         kind = "port"
     for _ in range(min(args.warmup, 3)):
         frame()
