@@ -81,6 +81,21 @@ def mesh_scene(profile, verts, idx, mirror=0, n_in=1.0, n_out=1.0):
     return _scene(profiles.walls(profile), m, mm)
 
 
+def instanced_cat_scene(profile, copies, seed=12345, obj_path=None):
+    """BASELINE.json configs[4]: `copies` baked instances of the loader-transformed cat on
+    the lattice of raytracinggpu_b200.synthetic.instance_lattice, merged into one mesh, reference BVH on top. Built
+    here with numpy + the oracle's own host builder (independent of the product's rt_mesh_instance / build)."""
+    from raytracinggpu_b200 import synthetic
+    path = obj_path or pyoracle.cat_obj_path()
+    if path is None:
+        return None
+    base = pyoracle.Mesh.from_obj(path)
+    scales, offs = synthetic.instance_lattice(copies, seed)
+    v, t = synthetic.instanced_arrays(base.vertices, base.tri_records[:, :3], scales, offs)
+    m = pyoracle.Mesh.from_arrays(v, t).build_bvh()
+    return _scene(profiles.walls(profile), m, profiles.mesh_material(profile, 0))
+
+
 def spheres_scene(light=profiles.LIGHT):
     """BASELINE.json config 1/4: the six walls + the demo spheres of the commented lines cpu_launcher.cpp:668-672
     (white diffuse, mirror, refractive shell = inner R 9 (n 1 -> 1.5) inside outer R 10 (n 1.5 -> 1)). No mesh."""

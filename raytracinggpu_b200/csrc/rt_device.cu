@@ -792,7 +792,8 @@ int rt_render(rt_scene* s, const rt_params* p, uint32_t flags, uint8_t* rgb_out,
                 else rtk::wf_generate<false><<<gen_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
                 launches++;
                 mark();
-                for (int r = 0; r <= segments && segments > 0; r++) {
+                /* without a mesh no query is ever posted: wf_generate runs every path to its end */
+                for (int r = 0; r <= segments && segments > 0 && h.has_mesh; r++) {
                     g.round = r;
                     if (count) rtk::wf_traverse<true><<<pers_grid, WF_THREADS, trav_smem, stream>>>(s->header, s->blob, g, npool_cap);
                     else rtk::wf_traverse<false><<<pers_grid, WF_THREADS, trav_smem, stream>>>(s->header, s->blob, g, npool_cap);

@@ -163,3 +163,28 @@ def test_no_cpu_fallback(built):
     with pytest.raises(rt.RtError) as e:
         rt.Scene(0)
     assert e.value.code == -2 and "no CPU fallback" in str(e.value)
+
+
+def test_instancing_and_bvh_build_match_the_oracle_at_scale(cat_path):
+    """rt_mesh_instance + rt_mesh_build_bvh (product host code) against numpy instancing + the oracle's builder:
+    64 baked cat instances (253,056 triangles), the reduced form of BASELINE.json configs[4]."""
+    import raytracinggpu_b200 as rt
+    from raytracinggpu_b200 import synthetic
+    from oracle import scenes
+    copies = 64
+    scales, offs = synthetic.instance_lattice(copies)
+    m = rt.Mesh.read_obj(cat_path).instance(scales, offs).build_bvh()
+    desc = scenes.instanced_cat_scene("optimized", copies, obj_path=cat_path)
+    v, recs, bvh = desc["mesh"]
+    assert m.counts()[1] == copies * 3954 == recs.shape[0]
+    assert np.array_equal(m.vertices.view(np.uint32), np.asarray(v).view(np.uint32))
+    assert np.array_equal(m.tri_records[:, :3], np.asarray(recs)[:, :3])
+    assert np.array_equal(m.arr_bvh.view(np.uint32), np.asarray(bvh).view(np.uint32))
+
+
+def test_instance_lattice_is_deterministic_and_inside_the_room():
+    from raytracinggpu_b200 import synthetic
+    s1, o1 = synthetic.instance_lattice()
+    s2, o2 = synthetic.instance_lattice()
+    assert np.array_equal(o1, o2) and len(s1) == 2529 and 2529 * 3954 == 9999666
+    assert o1[:, 0].min() > -52 and o1[:, 0].max() < 52 and o1[:, 1].min() > -8 and o1[:, 1].max() < 48 and o1[:, 2].min() > -54 and o1[:, 2].max() < 30
