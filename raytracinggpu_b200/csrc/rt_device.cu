@@ -784,6 +784,12 @@ int rt_render(rt_scene* s, const rt_params* p, uint32_t flags, uint8_t* rgb_out,
                 g.round = 0;
                 g.spill = s->wf_spill + (size_t)st * spill_cap * pers_grid * (WF_THREADS / 32);
                 g.spill_cap = spill_cap;
+                {
+                    static const int env_rs = getenv("RT_RUN_SHIFT") ? atoi(getenv("RT_RUN_SHIFT")) : -1;
+                    static const int env_gss = getenv("RT_GSS") ? atoi(getenv("RT_GSS")) : 2;
+                    g.run_shift = env_rs;
+                    g.gss_factor = env_gss;
+                }
                 g.dbg_warps = dbg_ptr;
                 const unsigned wtiles = (unsigned)((p->W + 7) / 8) * (unsigned)((srows + 3) / 4);
                 const unsigned gen_grid = (wtiles + (WF_THREADS / 32) - 1) / (WF_THREADS / 32);

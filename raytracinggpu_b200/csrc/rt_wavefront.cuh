@@ -60,6 +60,8 @@ struct WfArgs {
     QEntry* qS;    /* shadow queue of the current round */
     WfCounters* c;
     int round;     /* round whose queues this launch consumes (traverse, shade) */
+    int run_shift;  /* log2 of the admission run length, -1 = chosen per launch from the queue length */
+    int gss_factor; /* the last gss_factor * n_warps runs are admitted one at a time */
     int* spill;     /* node-pool overflow area: spill_cap ints per traversal warp (global memory) */
     int spill_cap;
     int* dbg_warps; /* investigation aid (RT_DEBUG_WARPS, COUNT kernels only): 16 ints per traversal warp and round */
@@ -398,7 +400,7 @@ struct WfWarpSmem { /* per warp; followed by the node pool (npool_cap ints) */
 };
 
 template <bool COUNT>
-__global__ void __launch_bounds__(WF_THREADS) wf_traverse(const __grid_constant__ SceneHeader h, const unsigned char* __restrict__ blob,
+__global__ void __launch_bounds__(WF_THREADS, 8) wf_traverse(const __grid_constant__ SceneHeader h, const unsigned char* __restrict__ blob,
                                                          const __grid_constant__ WfArgs g, const int npool_cap) {
     extern __shared__ __align__(16) unsigned char wf_smem[];
     const RenderArgs& a = g.a;
@@ -426,8 +428,18 @@ __global__ void __launch_bounds__(WF_THREADS) wf_traverse(const __grid_constant_
     int out0 = 0, out1 = 0;           /* outstanding tasks of batch 0 / 1 (warp-uniform) */
     int cnt0 = 0, cnt1 = 0;           /* rays admitted in batch 0 / 1; 0 = batch free */
     unsigned vm0 = 0, vm1 = 0;        /* lanes (= slots) of batch 0 / 1 that hold a ray */
-    const int n_runs = (total + 7) >> 3;      /* runs of 8 consecutive queue entries */
-    const int n_quarter = (n_runs + 3) >> 2;  /* the queue is consumed as four interleaved quarters */
+    /* Rays are admitted in runs of 2^rs consecutive queue entries. Long queues use runs of 8 (neighbouring pixels share
+     * nodes and triangles); when there are few rays per warp (late bounce rounds, a small row shard) the runs shrink,
+     * so that the expensive rays of a region are spread over many warps instead of piling up in one. */
+    const int n_warps = gridDim.x * (WF_THREADS / 32);
+    int rs = g.run_shift;
+    if (rs < 0) {
+        const int rpw = total / n_warps;
+        rs = rpw >= 64 ? 3 : (rpw >= 16 ? 2 : (rpw >= 4 ? 1 : 0));
+    }
+    const int n_runs = (total + (1 << rs) - 1) >> rs; /* runs of 2^rs consecutive queue entries */
+    const int n_quarter = (n_runs + 3) >> 2;           /* the queue is consumed as four interleaved quarters */
+    int last_r0 = 0;                                   /* the queue cursor as this warp last saw it */
     bool exhausted = total == 0;
     bool failed = false;
     unsigned dbgNs = 0, dbgNt = 0, dbgTs = 0, dbgTt = 0, dbgAd = 0;
@@ -472,19 +484,22 @@ __global__ void __launch_bounds__(WF_THREADS) wf_traverse(const __grid_constant_
             /* The fuller the pools, the fewer runs are admitted at once: a warp that sits on expensive rays (full pools)
              * takes on at most 8 more, so the expensive rays of a region end up spread over many warps. */
             const int fill = nN + nT;
-            const int k = fill < 12 ? 4 : (fill < 28 ? 2 : 1);
+            int k = max(1, (fill < 12 ? 32 : (fill < 28 ? 16 : 8)) >> rs);
+            /* guided self-scheduling: the last runs of the queue go out one at a time */
+            if (4 * n_quarter - last_r0 < g.gss_factor * n_warps) k = 1;
             int r0 = 0;
             if (lane == 0) r0 = atomicAdd(head, k);
             r0 = __shfl_sync(FULL, r0, 0);
+            last_r0 = r0;
             if (r0 >= 4 * n_quarter) {
                 exhausted = true;
             } else {
                 const int b = cnt0 == 0 ? 0 : 1;
                 if (COUNT) dbgAd++;
-                const int r = r0 + (lane >> 3);
+                const int r = r0 + (lane >> rs);
                 const int run = (r & 3) * n_quarter + (r >> 2); /* consecutive run ids alternate between the four quarters of the queue */
-                const int e = run * 8 + (lane & 7);
-                const bool valid = (lane >> 3) < k && r < 4 * n_quarter && run < n_runs && e < total;
+                const int e = (run << rs) + (lane & ((1 << rs) - 1));
+                const bool valid = (lane >> rs) < k && r < 4 * n_quarter && run < n_runs && e < total;
                 const unsigned vmask = __ballot_sync(FULL, valid);
                 const int take = __popc(vmask);
                 if (valid) {
