@@ -11,11 +11,18 @@ sc = rt.Scene(0)
 sc.set_spheres(walls)
 sc.set_mesh(mesh.vertices, mesh.tri_records, mesh.arr_bvh, id=mesh_id)
 p = rt.params_profile("optimized", 1920, 1080, 1, 1)
+NR = 2
+if os.environ.get("RT_TL_SHARD"):  # one rank's share of configs[2]: 4K mirror cat, depth 4, rows r, r+world, ...
+    world = int(os.environ["RT_TL_SHARD"])
+    sc.set_mesh(mesh.vertices, mesh.tri_records, mesh.arr_bvh, mirror=1, id=mesh_id)
+    p = rt.params_profile("optimized", 3840, 2160, 1, 4)
+    p.row_begin, p.row_step, p.row_count = rt.sharding.rows_for_rank(2160, 0, world)
+    NR = 5
 for _ in range(4):
     o = sc.render(p, want=("rgb",), count_work=True)
 print(o["stats"])
-d = np.fromfile("/tmp/warps.bin", dtype=np.int32).reshape(2, -1, 16)
-for r in range(2):
+d = np.fromfile("/tmp/warps.bin", dtype=np.int32).reshape(NR, -1, 16)
+for r in range(NR):
     w = d[r]
     t0 = w[:, 0].astype(np.uint32).astype(np.int64); t1 = w[:, 1].astype(np.uint32).astype(np.int64)
     base = t0.min()
@@ -39,6 +46,7 @@ for r in range(2):
     tail = e > np.percentile(e, 99)
     print("   tail warps (last 1%%): cycles per N step %.0f  per T step %.0f  per admission %.0f" % (
         cyc[tail, 0].sum() / max(w[tail, 2].sum(), 1), cyc[tail, 1].sum() / max(w[tail, 4].sum(), 1), cyc[tail, 2].sum() / max(w[tail, 6].sum(), 1)))
+    print("   donated batches taken: total %d by %d warps" % (w[:, 12].sum(), (w[:, 12] > 0).sum()))
     late = np.argsort(e)[-8:]
     print("   last finishers: end us", np.round(e[late], 1), "steps", steps[late], "batches", w[late, 6])
 np.save("gpurun_out/warps.npy", d)
