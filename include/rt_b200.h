@@ -73,14 +73,17 @@ typedef struct rt_params {
     int32_t push_order;      /* 0: push L then R (R popped first; cpu_launcher.cpp:291-292, array_bvh.cu:282-283)
                                 1: push R then L (L popped first; optimized.cu:265-266). Only decides exact-t ties. */
     int32_t extra_segment;   /* 1: num_bounce+1 path segments (recursive getColor, cpu_launcher.cpp:567,710); 0: num_bounce (optimized.cu:566) */
-    float aa_sigma;          /* Box-Muller jitter sigma: 0 cpu_launcher.cpp:704, 0.2 optimized.cu:753. Only 0 is implemented (deterministic mode). */
-    int32_t indirect;        /* 1: cosine-weighted random bounce (optimized.cu:631-649). Only 0 is implemented. */
+    float aa_sigma;          /* Box-Muller jitter sigma: 0 cpu_launcher.cpp:704, 0.2 optimized.cu:753 */
+    int32_t indirect;        /* 1: cosine-weighted random bounce at every diffuse hit (optimized.cu:631-649).
+                                aa_sigma != 0 or indirect != 0 selects the stochastic mode: the random stream is the
+                                reference's, cuRAND XORWOW curand_init(seed, global pixel index, 0) (optimized.cu:745);
+                                rt_params_profile leaves both 0 (deterministic mode). */
     int32_t gamma_mode;      /* 0: trunc(min(pow((double)c, 1./2.2), 255.)) cpu_launcher.cpp:714-716
                                 1: trunc(min(powf(c, (float)(1./2.2)), 255.)) optimized.cu:765-767 */
     int32_t row_begin;       /* sharding: this call renders image rows row_begin + k*row_step, k in [0,row_count) */
     int32_t row_step;        /* 1 for a contiguous band, nranks for row-interleave */
     int32_t row_count;       /* 0 means "all rows from row_begin with row_step" */
-    int32_t reserved;
+    int32_t reserved;        /* stochastic mode: RNG seed, 0 = the reference's 123456 (optimized.cu:745) */
 } rt_params;
 
 typedef struct rt_stats {
@@ -184,6 +187,9 @@ int rt_scene_sync(rt_scene* s, rt_stats* stats);
  * blocks*256*per_thread pseudo-random operand pairs. out[0] = mismatches with one correction step,
  * out[1] = with two, out[2] = pairs tested. */
 int rt_selftest_division(int device, uint64_t seed, int blocks, int per_thread, uint64_t out[3]);
+/* Device self-test: the cuRAND library's XORWOW start states (d, v0..v4: n*6 words) and first four curand_uniform values
+ * (n*4 floats) of the listed subsequences — the random stream of optimized.cu:745 that the stochastic mode reproduces. */
+int rt_selftest_xorwow(int device, uint64_t seed, const uint32_t* subsequences, int32_t n, uint32_t* states6, float* uniforms4);
 
 #ifdef __cplusplus
 }

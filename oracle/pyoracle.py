@@ -206,6 +206,17 @@ def render(spheres, mesh_arrays, mesh_mat, light, params, threads=0, want=("rgb"
 _ref = None
 
 
+def xorwow(seed, subsequence, n):
+    """n curand_uniform values of XORWOW subsequence `subsequence` + the state right after curand_init (d, v0..v4)."""
+    L = lib()
+    L.orc_xorwow.restype = C.c_int
+    L.orc_xorwow.argtypes = [C.c_uint64, C.c_uint64, C.c_int32, C.c_void_p, C.c_void_p]
+    u = np.zeros(n, np.float32)
+    st = np.zeros(6, np.uint32)
+    L.orc_xorwow(int(seed), int(subsequence), int(n), u.ctypes.data, st.ctypes.data)
+    return u, st
+
+
 def ref_cpu_available():
     return os.path.exists(REF_CPU_SO)
 

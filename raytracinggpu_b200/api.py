@@ -52,6 +52,7 @@ SIGNATURES = {
     "rt_render": (C.c_int, [_vp, C.POINTER(rt_params), C.c_uint32, _vp, _vp, _vp, _vp, _vp, C.POINTER(rt_stats)]),
     "rt_scene_sync": (C.c_int, [_vp, C.POINTER(rt_stats)]),
     "rt_selftest_division": (C.c_int, [C.c_int, _u64, C.c_int, C.c_int, C.POINTER(_u64)]),
+    "rt_selftest_xorwow": (C.c_int, [C.c_int, _u64, _vp, C.c_int32, _vp, _vp]),
 }
 # rt_default_walls(profile, walls, mesh_id): fix the argument order to the header's
 SIGNATURES["rt_default_walls"] = (C.c_int, [C.c_char_p, C.POINTER(rt_sphere), _pi32])
@@ -293,3 +294,12 @@ def selftest_division(device=0, seed=1, blocks=148 * 8, per_thread=4096):
     out = (C.c_uint64 * 3)()
     _check(lib().rt_selftest_division(device, seed, blocks, per_thread, out))
     return {"mismatch_1step": out[0], "mismatch_2step": out[1], "pairs": out[2]}
+
+
+def selftest_xorwow(subsequences, seed=123456, device=0):
+    """(states [n, 6] uint32, uniforms [n, 4] float32) from the cuRAND device library for the given subsequences."""
+    sub = np.ascontiguousarray(subsequences, dtype=np.uint32)
+    st = np.zeros((len(sub), 6), np.uint32)
+    u = np.zeros((len(sub), 4), np.float32)
+    _check(lib().rt_selftest_xorwow(device, seed, sub.ctypes.data, len(sub), st.ctypes.data, u.ctypes.data))
+    return st, u

@@ -7,6 +7,9 @@
  *   --obj PATH                          default cadnav.com_model/Models_F0202A090/cat.obj relative to the CWD (:802)
  *   --out FILE                          default image_optimized.png (:862) / image.png (cpu_launcher.cpp:719)
  *   --device D   --frames F             render F frames (kernel time is reported per frame)
+ *   --stochastic                        the reference's own default: sigma 0.2 Box-Muller jitter + cosine-weighted
+ *                                       indirect bounce on the cuRAND XORWOW stream of optimized.cu:745 (without the
+ *                                       flag: the deterministic mode the parity contract is stated on)
  */
 #include "scene.hpp"
 
@@ -20,6 +23,7 @@ int main(int argc, char** argv) {
     std::vector<std::string> pos;
     std::string profile = "optimized", obj = "cadnav.com_model/Models_F0202A090/cat.obj", out;
     int W = 512, H = 512, device = 0, frames = 1;
+    bool stochastic = false;
     for (int i = 1; i < argc; i++) {
         std::string a = argv[i];
         auto next = [&]() -> const char* { return (i + 1 < argc) ? argv[++i] : ""; };
@@ -30,6 +34,7 @@ int main(int argc, char** argv) {
         else if (a == "--out") out = next();
         else if (a == "--device") device = atoi(next());
         else if (a == "--frames") frames = atoi(next());
+        else if (a == "--stochastic") stochastic = true;
         else pos.push_back(a);
     }
     if (pos.size() != 2) {
@@ -42,6 +47,10 @@ int main(int argc, char** argv) {
     try {
         rt_params p;
         rtb200::check(rt_params_profile(&p, profile.c_str(), W, H, num_rays, num_bounce));
+        if (stochastic) {
+            p.aa_sigma = 0.2f; /* optimized.cu:753 */
+            p.indirect = 1;    /* optimized.cu:631-649 */
+        }
         rt_sphere walls[6];
         int32_t mesh_id = 0;
         rtb200::check(rt_default_walls(profile.c_str(), walls, &mesh_id));

@@ -11,6 +11,7 @@
 #include "rt_kernels.cuh"
 #include "rt_layout.h"
 #include "rt_wavefront.cuh"
+#include "rt_stochastic.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -67,6 +68,10 @@ struct rt_scene {
     cudaStream_t strip_stream[RT_MAX_STRIPS] = {};
     cudaEvent_t strip_done[RT_MAX_STRIPS] = {};
     cudaEvent_t fork_ev = nullptr;
+    rtk::XorwowState* rng_states = nullptr; /* stochastic mode: curand_init(seed, pixel, 0) of every pixel of a rng_W x rng_H frame */
+    size_t rng_capacity = 0;
+    int rng_W = 0, rng_H = 0;
+    unsigned long long rng_seed = 0;
     int* wf_spill = nullptr;  /* node-pool overflow area of wf_traverse */
     size_t wf_spill_ints = 0;
     int* dbg_warps = nullptr; /* RT_DEBUG_WARPS=<file>: per-warp timeline of wf_traverse (count_work renders) */
@@ -223,6 +228,7 @@ void rt_scene_destroy(rt_scene* s) {
     if (s->wf_counters) cudaFree(s->wf_counters);
     if (s->dbg_warps) cudaFree(s->dbg_warps);
     if (s->wf_spill) cudaFree(s->wf_spill);
+    if (s->rng_states) cudaFree(s->rng_states);
     if (s->h_wf_counters) cudaFreeHost(s->h_wf_counters);
     for (int k = 0; k < 5; k++)
         if (s->scratch[k]) cudaFree(s->scratch[k]);
@@ -586,8 +592,9 @@ int rt_render(rt_scene* s, const rt_params* p, uint32_t flags, uint8_t* rgb_out,
               uint8_t* shadow, rt_stats* stats) {
     if (!s || !p) return rtb::fail(RT_ERR_INVALID, "rt_render: NULL scene or params");
     if (p->W <= 0 || p->H <= 0 || p->num_rays < 1 || p->num_bounce < 0) return rtb::fail(RT_ERR_INVALID, "rt_render: bad W/H/num_rays/num_bounce");
-    if (p->aa_sigma != 0.f || p->indirect != 0)
-        return rtb::fail(RT_ERR_UNSUPPORTED, "rt_render: only the deterministic mode (aa_sigma = 0, indirect = 0) is implemented");
+    const bool stochastic = p->aa_sigma != 0.f || p->indirect != 0;
+    if (stochastic && p->num_bounce + (p->extra_segment ? 1 : 0) > RT_STOCH_MAX_SEGMENTS)
+        return rtb::fail(RT_ERR_UNSUPPORTED, "rt_render: the stochastic mode supports at most %d path segments (the reference: MAX_RAY_DEPTH 10, optimized.cu:22)", RT_STOCH_MAX_SEGMENTS);
     if (p->gamma_mode != 0 && p->gamma_mode != 1) return rtb::fail(RT_ERR_INVALID, "rt_render: gamma_mode must be 0 or 1");
     if (p->push_order != 0 && p->push_order != 1) return rtb::fail(RT_ERR_INVALID, "rt_render: push_order must be 0 or 1");
     const int step = p->row_step > 0 ? p->row_step : 1;
@@ -673,6 +680,7 @@ int rt_render(rt_scene* s, const rt_params* p, uint32_t flags, uint8_t* rgb_out,
         const unsigned grid = (unsigned)tiles_x * (unsigned)tiles_y;
         const bool count = (flags & RT_RENDER_COUNT_WORK) != 0;
         int variant = s->variant;
+        if (stochastic) variant = 3; /* one thread per pixel over the whole path: the samples of a pixel share one random stream */
         /* tie-break rank of render_wave: (n_tris - leaf_start) and the in-leaf offset share 32 bits */
         int bits_n = 1;
         while ((1ll << bits_n) <= (long long)h.n_tris) bits_n++;
@@ -829,6 +837,30 @@ int rt_render(rt_scene* s, const rt_params* p, uint32_t flags, uint8_t* rgb_out,
                 for (int k = 0; k < n_ev; k++) cudaEventDestroy(dev_ev[k]);
             }
             launches--; /* the common launches++ below counts one */
+        } else if (variant == 3) {
+            /* start states of the random streams: once per (seed, W, H), not per launch (rt_stochastic.cuh) */
+            const unsigned long long seed = p->reserved ? (unsigned long long)(unsigned int)p->reserved : 123456ull; /* optimized.cu:745 */
+            const size_t frame_px = (size_t)p->W * p->H;
+            if (!s->rng_states || s->rng_W != p->W || s->rng_H != p->H || s->rng_seed != seed) {
+                if (s->rng_capacity < frame_px) {
+                    CUDA_TRY(cudaStreamSynchronize(s->stream));
+                    if (s->rng_states) cudaFree(s->rng_states);
+                    s->rng_states = nullptr;
+                    s->rng_capacity = 0;
+                    CUDA_TRY(cudaMalloc(&s->rng_states, frame_px * sizeof(rtk::XorwowState)));
+                    s->rng_capacity = frame_px;
+                }
+                rtk::xorwow_init_states<<<(unsigned)((frame_px + 255) / 256), 256, 0, s->stream>>>(seed, (unsigned)frame_px, s->rng_states);
+                CUDA_TRY(cudaGetLastError());
+                s->rng_W = p->W;
+                s->rng_H = p->H;
+                s->rng_seed = seed;
+                launches++;
+                CUDA_TRY(cudaEventRecord(s->ev0, s->stream)); /* the one-off table build is not part of the frame time */
+            }
+            CUDA_TRY(cudaMemsetAsync(s->counters, 0, RT_NCOUNTERS * sizeof(unsigned long long), s->stream));
+            if (count) rtk::render_stoch<true><<<grid, 128, 0, s->stream>>>(s->header, s->blob, a, s->rng_states, p->aa_sigma, p->indirect);
+            else rtk::render_stoch<false><<<grid, 128, 0, s->stream>>>(s->header, s->blob, a, s->rng_states, p->aa_sigma, p->indirect);
         } else if (variant == 0) {
             CUDA_TRY(cudaMemsetAsync(s->counters, 0, RT_NCOUNTERS * sizeof(unsigned long long), s->stream));
             if (count) rtk::render_mega<true, false><<<grid, 128, 0, s->stream>>>(s->header, s->blob, a);
@@ -871,6 +903,31 @@ int rt_selftest_division(int device, uint64_t seed, int blocks, int per_thread, 
     out[0] = hst[0];
     out[1] = hst[1];
     out[2] = hst[2];
+    return RT_OK;
+}
+
+/* Device self-test used by tests/: the cuRAND library's own XORWOW start states and first uniforms, the stream the
+ * stochastic mode must reproduce (optimized.cu:745, 32-37). states6: n*6 words (d, v0..v4); uniforms4: n*4 floats. */
+int rt_selftest_xorwow(int device, uint64_t seed, const uint32_t* subsequences, int32_t n, uint32_t* states6, float* uniforms4) {
+    if (!subsequences || n <= 0 || !states6 || !uniforms4) return rtb::fail(RT_ERR_INVALID, "rt_selftest_xorwow: bad argument");
+    DeviceGuard g(device);
+    if (!g.ok) return rtb::fail(RT_ERR_CUDA, "rt_selftest_xorwow: no device %d", device);
+    unsigned int *d_sub = nullptr, *d_st = nullptr;
+    float* d_u = nullptr;
+    cudaError_t e = cudaMalloc(&d_sub, (size_t)n * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&d_st, (size_t)n * 24);
+    if (e == cudaSuccess) e = cudaMalloc(&d_u, (size_t)n * 16);
+    if (e == cudaSuccess) e = cudaMemcpy(d_sub, subsequences, (size_t)n * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        rtk::selftest_xorwow<<<(n + 127) / 128, 128>>>((unsigned long long)seed, d_sub, n, d_st, d_u);
+        e = cudaDeviceSynchronize();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(states6, d_st, (size_t)n * 24, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(uniforms4, d_u, (size_t)n * 16, cudaMemcpyDeviceToHost);
+    if (d_sub) cudaFree(d_sub);
+    if (d_st) cudaFree(d_st);
+    if (d_u) cudaFree(d_u);
+    if (e != cudaSuccess) return rtb::fail(RT_ERR_CUDA, "rt_selftest_xorwow: %s", cudaGetErrorString(e));
     return RT_OK;
 }
 

@@ -1,0 +1,29 @@
+"""Generate the fixtures that only a GPU box can produce (run once under gpurun; outputs land in gpurun_out/golden/
+and are then committed under tests/golden/):
+
+  xorwow_vectors.json            cuRAND device library: XORWOW start states + first four curand_uniform values of a
+                                 list of subsequences, seed 123456 (the stream of optimized.cu:745, 32-37)
+  ref_gpu_optimized_512_R_B.raw  the UNMODIFIED reference kernel (oracle/_ref/ref_optimized = optimized.cu included
+                                 from where it lies, retargeted to sm_100a, reference flags incl. --use_fast_math):
+                                 512x512 frames for `./optimized R B`
+"""
+import json, os, subprocess, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+import numpy as np
+import raytracinggpu_b200 as rt
+
+out = os.path.join(ROOT, "gpurun_out", "golden")
+os.makedirs(out, exist_ok=True)
+subs = [0, 1, 2, 3, 5, 255, 256, 511, 512, 12345, 262143, 262144, 2073599, 8294399, 16777215]
+st, u = rt.selftest_xorwow(subs, seed=123456)
+json.dump({"seed": 123456, "subsequences": subs, "states_d_v0_v4": st.tolist(), "uniforms_bits": u.view(np.uint32).tolist(),
+           "source": "curand_init(seed, subsequence, 0) + 4 x curand_uniform, CUDA 12.9 curand_kernel.h on an NVIDIA B200"},
+          open(os.path.join(out, "xorwow_vectors.json"), "w"), indent=1)
+cat = os.path.join(ROOT, "oracle", "_ref", "cadnav.com_model", "Models_F0202A090", "cat.obj")
+exe = os.path.join(ROOT, "oracle", "_ref", "ref_optimized")
+for rays, bounce in ((1, 1), (4, 3)):
+    raw = os.path.join(out, "ref_gpu_optimized_512_%d_%d.raw" % (rays, bounce))
+    r = subprocess.run([exe, cat, "512", "512", str(rays), str(bounce), "1", raw], capture_output=True, text=True)
+    print(r.stdout.strip(), r.stderr.strip()[-200:])
+print("written", os.listdir(out))
