@@ -162,8 +162,8 @@ def test_error_paths(scene):
         scene.render(p)
     assert e.value.code == -5
     scenes.upload(scene, scenes.spheres_scene())
-    p.aa_sigma = 0.2
-    with pytest.raises(rt.RtError) as e:  # stochastic mode is not implemented: say so, do not approximate
+    p.aa_sigma, p.indirect, p.num_bounce = 0.2, 1, 40
+    with pytest.raises(rt.RtError) as e:  # more path segments than the stochastic kernel's fold arrays hold: say so
         scene.render(p)
     assert e.value.code == -6
     bad = scenes.spheres_scene()
