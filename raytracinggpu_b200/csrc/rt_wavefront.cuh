@@ -476,7 +476,7 @@ __global__ void __launch_bounds__(WF_THREADS, 8) wf_traverse(const __grid_consta
         }
         if (COUNT) { const long long c = clock64(); cycR += c - cyc_mark; cyc_mark = c; }
         /* ---- admit a batch of 32 rays when a batch is free and the pools run low ----------------------------------- */
-        if (!exhausted && (cnt0 == 0 || cnt1 == 0) && nN + nT < 48 && nSp == 0) {
+        if (!exhausted && (cnt0 == 0 || cnt1 == 0) && nN + nT < 48 && nSp == 0 && npool_cap - nN >= 32) { /* room for 32 root tasks */
             /* A batch is up to four runs of 8 consecutive queue entries taken a quarter of the queue apart: neighbouring
              * entries are neighbouring pixels, whose tasks address the same nodes and triangles (few cache lines per
              * step), while the expensive rays, which cluster in the image (the cat's head), are spread over four

@@ -46,7 +46,6 @@ for r in range(NR):
     tail = e > np.percentile(e, 99)
     print("   tail warps (last 1%%): cycles per N step %.0f  per T step %.0f  per admission %.0f" % (
         cyc[tail, 0].sum() / max(w[tail, 2].sum(), 1), cyc[tail, 1].sum() / max(w[tail, 4].sum(), 1), cyc[tail, 2].sum() / max(w[tail, 6].sum(), 1)))
-    print("   donated batches taken: total %d by %d warps" % (w[:, 12].sum(), (w[:, 12] > 0).sum()))
     late = np.argsort(e)[-8:]
     print("   last finishers: end us", np.round(e[late], 1), "steps", steps[late], "batches", w[late, 6])
 np.save("gpurun_out/warps.npy", d)
