@@ -72,6 +72,8 @@ struct rt_scene {
     size_t rng_capacity = 0;
     int rng_W = 0, rng_H = 0;
     unsigned long long rng_seed = 0;
+    unsigned char* st_buf = nullptr; /* stochastic wavefront: per-pixel stream state, colour sum, diffuse records */
+    size_t st_buf_bytes = 0;
     int* wf_spill = nullptr;  /* node-pool overflow area of wf_traverse */
     size_t wf_spill_ints = 0;
     int* dbg_warps = nullptr; /* RT_DEBUG_WARPS=<file>: per-warp timeline of wf_traverse (count_work renders) */
@@ -229,6 +231,7 @@ void rt_scene_destroy(rt_scene* s) {
     if (s->dbg_warps) cudaFree(s->dbg_warps);
     if (s->wf_spill) cudaFree(s->wf_spill);
     if (s->rng_states) cudaFree(s->rng_states);
+    if (s->st_buf) cudaFree(s->st_buf);
     if (s->h_wf_counters) cudaFreeHost(s->h_wf_counters);
     for (int k = 0; k < 5; k++)
         if (s->scratch[k]) cudaFree(s->scratch[k]);
@@ -680,15 +683,41 @@ int rt_render(rt_scene* s, const rt_params* p, uint32_t flags, uint8_t* rgb_out,
         const unsigned grid = (unsigned)tiles_x * (unsigned)tiles_y;
         const bool count = (flags & RT_RENDER_COUNT_WORK) != 0;
         int variant = s->variant;
-        if (stochastic) variant = 3; /* one thread per pixel over the whole path: the samples of a pixel share one random stream */
+        /* stochastic mode: one wavefront pass per sample (the samples of a pixel share one random stream); the
+         * thread-per-pixel kernel render_stoch is the fallback and the in-library cross-check (RT_STOCH_MEGA=1) */
+        const bool stoch_mega = getenv("RT_STOCH_MEGA") && atoi(getenv("RT_STOCH_MEGA")) != 0;
+        if (stochastic && (variant != 2 || stoch_mega)) variant = 3;
         /* tie-break rank of render_wave: (n_tris - leaf_start) and the in-leaf offset share 32 bits */
         int bits_n = 1;
         while ((1ll << bits_n) <= (long long)h.n_tris) bits_n++;
         a.rank_off_bits = std::min(32 - bits_n, 16);
         if (variant == 2 && p->push_order == 0 && h.has_mesh && (long long)s->max_leaf > (1ll << a.rank_off_bits)) variant = 1;
         const int segments = a.segments;
-        if (variant == 2 && segments > WF_MAX_ROUNDS - 1) variant = 1;
+        if (variant == 2 && segments > WF_MAX_ROUNDS - 1) variant = stochastic ? 3 : 1;
+        if (stochastic && variant == 1) variant = 3;
         s->last_was_wavefront = (variant == 2);
+        if (stochastic) {
+            /* start states of the random streams: once per (seed, W, H), not per launch (rt_stochastic.cuh) */
+            const unsigned long long seed = p->reserved ? (unsigned long long)(unsigned int)p->reserved : 123456ull; /* optimized.cu:745 */
+            const size_t frame_px = (size_t)p->W * p->H;
+            if (!s->rng_states || s->rng_W != p->W || s->rng_H != p->H || s->rng_seed != seed) {
+                if (s->rng_capacity < frame_px) {
+                    CUDA_TRY(cudaStreamSynchronize(s->stream));
+                    if (s->rng_states) cudaFree(s->rng_states);
+                    s->rng_states = nullptr;
+                    s->rng_capacity = 0;
+                    CUDA_TRY(cudaMalloc(&s->rng_states, frame_px * sizeof(rtk::XorwowState)));
+                    s->rng_capacity = frame_px;
+                }
+                rtk::xorwow_init_states<<<(unsigned)((frame_px + 255) / 256), 256, 0, s->stream>>>(seed, (unsigned)frame_px, s->rng_states);
+                CUDA_TRY(cudaGetLastError());
+                s->rng_W = p->W;
+                s->rng_H = p->H;
+                s->rng_seed = seed;
+                launches++;
+                CUDA_TRY(cudaEventRecord(s->ev0, s->stream)); /* the one-off table build is not part of the frame time */
+            }
+        }
         if (variant == 2) {
             /* node pool of wf_traverse: 32 lanes x (levels of the packed tree + roots of two batches + slack) */
             int npool_cap = std::min(32 * (h.max_depth + 4), 256);
@@ -698,9 +727,11 @@ int rt_render(rt_scene* s, const rt_params* p, uint32_t flags, uint8_t* rgb_out,
             if (trav_smem > 200 * 1024) return rtb::fail(RT_ERR_UNSUPPORTED, "rt_render: BVH depth %d needs %zu B of shared memory per block", h.max_depth, trav_smem);
             if (s->trav_blocks_per_sm == 0 || s->trav_smem != trav_smem) {
                 int nb = 0;
-                CUDA_TRY(cudaFuncSetAttribute(rtk::wf_traverse<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trav_smem));
-                CUDA_TRY(cudaFuncSetAttribute(rtk::wf_traverse<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trav_smem));
-                CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rtk::wf_traverse<false>, WF_THREADS, trav_smem));
+                CUDA_TRY(cudaFuncSetAttribute(rtk::wf_traverse<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trav_smem));
+                CUDA_TRY(cudaFuncSetAttribute(rtk::wf_traverse<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trav_smem));
+                CUDA_TRY(cudaFuncSetAttribute(rtk::wf_traverse<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trav_smem));
+                CUDA_TRY(cudaFuncSetAttribute(rtk::wf_traverse<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trav_smem));
+                CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rtk::wf_traverse<false, false>, WF_THREADS, trav_smem));
                 cudaDeviceProp prop;
                 CUDA_TRY(cudaGetDeviceProperties(&prop, s->device));
                 s->trav_blocks_per_sm = std::max(nb, 1);
@@ -757,6 +788,19 @@ int rt_render(rt_scene* s, const rt_params* p, uint32_t flags, uint8_t* rgb_out,
                 dbg_ptr = s->dbg_warps;
             }
             CUDA_TRY(cudaMemsetAsync(s->wf_counters, 0, RT_MAX_STRIPS * sizeof(rtk::WfCounters), s->stream));
+            /* stochastic mode: per compact pixel 32 B of stream state, 16 B of colour sum, 32 B per path segment of records */
+            const size_t st_rng_off = 0, st_total_off = npx * 32, st_rec_off = st_total_off + npx * 16;
+            if (stochastic) {
+                const size_t need = st_rec_off + npx * 32 * (size_t)std::max(segments, 1);
+                if (s->st_buf_bytes < need) {
+                    CUDA_TRY(cudaStreamSynchronize(s->stream));
+                    if (s->st_buf) cudaFree(s->st_buf);
+                    s->st_buf = nullptr;
+                    s->st_buf_bytes = 0;
+                    CUDA_TRY(cudaMalloc(&s->st_buf, need));
+                    s->st_buf_bytes = need;
+                }
+            }
             if (n_strips > 1) CUDA_TRY(cudaEventRecord(s->fork_ev, s->stream));
             cudaEvent_t dev_ev[40];
             int n_ev = 0;
@@ -802,22 +846,63 @@ int rt_render(rt_scene* s, const rt_params* p, uint32_t flags, uint8_t* rgb_out,
                 const unsigned wtiles = (unsigned)((p->W + 7) / 8) * (unsigned)((srows + 3) / 4);
                 const unsigned gen_grid = (wtiles + (WF_THREADS / 32) - 1) / (WF_THREADS / 32);
                 const unsigned shade_grid = (unsigned)std::min<size_t>((spx + WF_THREADS - 1) / WF_THREADS, (size_t)s->sm_count * 16);
-                if (count) rtk::wf_generate<true><<<gen_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
-                else rtk::wf_generate<false><<<gen_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
-                launches++;
-                mark();
-                /* without a mesh no query is ever posted: wf_generate runs every path to its end */
-                for (int r = 0; r <= segments && segments > 0 && h.has_mesh; r++) {
-                    g.round = r;
-                    if (count) rtk::wf_traverse<true><<<pers_grid, WF_THREADS, trav_smem, stream>>>(s->header, s->blob, g, npool_cap);
-                    else rtk::wf_traverse<false><<<pers_grid, WF_THREADS, trav_smem, stream>>>(s->header, s->blob, g, npool_cap);
+                g.stoch = stochastic ? 1 : 0;
+                g.sample = 0;
+                g.last_sample = 1;
+                g.indirect = p->indirect;
+                g.aa_sigma = p->aa_sigma;
+                g.npx = (int)spx;
+                g.rng_table = reinterpret_cast<const uint4*>(s->rng_states);
+                g.rng = stochastic ? reinterpret_cast<uint4*>(s->st_buf + st_rng_off) + px0 * 2 : nullptr;
+                g.total = stochastic ? reinterpret_cast<float4*>(s->st_buf + st_total_off) + px0 : nullptr;
+                g.rec = stochastic ? reinterpret_cast<float4*>(s->st_buf + st_rec_off) + px0 * 2 * (size_t)std::max(segments, 1) : nullptr;
+                /* deterministic mode: one pass (identical samples are traced once). Stochastic mode: one pass per sample,
+                 * in order, because the samples of a pixel share one random stream. */
+                const int n_pass = stochastic ? p->num_rays : 1;
+                for (int pass = 0; pass < n_pass; pass++) {
+                    g.sample = pass;
+                    g.last_sample = pass == n_pass - 1;
+                    g.round = 0;
+                    if (pass > 0) /* the queue counters restart with every pass; the work statistics keep adding up */
+                        CUDA_TRY(cudaMemsetAsync(reinterpret_cast<unsigned char*>(s->wf_counters + st) + offsetof(rtk::WfCounters, nA), 0,
+                                                 sizeof(rtk::WfCounters) - offsetof(rtk::WfCounters, nA), stream));
+                    if (stochastic) {
+                        if (count) rtk::wf_generate<true, true><<<gen_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
+                        else rtk::wf_generate<false, true><<<gen_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
+                    } else {
+                        if (count) rtk::wf_generate<true, false><<<gen_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
+                        else rtk::wf_generate<false, false><<<gen_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
+                    }
                     launches++;
                     mark();
-                    if (r == segments) break;
-                    if (count) rtk::wf_shade<true><<<shade_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
-                    else rtk::wf_shade<false><<<shade_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
-                    launches++;
-                    mark();
+                    /* without a mesh no query is ever posted: wf_generate runs every path to its end */
+                    for (int r = 0; r <= segments && segments > 0 && h.has_mesh; r++) {
+                        g.round = r;
+                        if (stochastic) {
+                            if (count) rtk::wf_traverse<true, true><<<pers_grid, WF_THREADS, trav_smem, stream>>>(s->header, s->blob, g, npool_cap);
+                            else rtk::wf_traverse<false, true><<<pers_grid, WF_THREADS, trav_smem, stream>>>(s->header, s->blob, g, npool_cap);
+                        } else {
+                            if (count) rtk::wf_traverse<true, false><<<pers_grid, WF_THREADS, trav_smem, stream>>>(s->header, s->blob, g, npool_cap);
+                            else rtk::wf_traverse<false, false><<<pers_grid, WF_THREADS, trav_smem, stream>>>(s->header, s->blob, g, npool_cap);
+                        }
+                        launches++;
+                        mark();
+                        if (r == segments) break;
+                        if (stochastic) {
+                            if (count) rtk::wf_shade<true, true><<<shade_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
+                            else rtk::wf_shade<false, true><<<shade_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
+                        } else {
+                            if (count) rtk::wf_shade<true, false><<<shade_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
+                            else rtk::wf_shade<false, false><<<shade_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
+                        }
+                        launches++;
+                        mark();
+                    }
+                    if (stochastic) {
+                        rtk::wf_fold<<<(unsigned)((spx + 255) / 256), 256, 0, stream>>>(g);
+                        launches++;
+                        mark();
+                    }
                 }
                 if (n_strips > 1) {
                     CUDA_TRY(cudaEventRecord(s->strip_done[st], stream));
@@ -838,26 +923,6 @@ int rt_render(rt_scene* s, const rt_params* p, uint32_t flags, uint8_t* rgb_out,
             }
             launches--; /* the common launches++ below counts one */
         } else if (variant == 3) {
-            /* start states of the random streams: once per (seed, W, H), not per launch (rt_stochastic.cuh) */
-            const unsigned long long seed = p->reserved ? (unsigned long long)(unsigned int)p->reserved : 123456ull; /* optimized.cu:745 */
-            const size_t frame_px = (size_t)p->W * p->H;
-            if (!s->rng_states || s->rng_W != p->W || s->rng_H != p->H || s->rng_seed != seed) {
-                if (s->rng_capacity < frame_px) {
-                    CUDA_TRY(cudaStreamSynchronize(s->stream));
-                    if (s->rng_states) cudaFree(s->rng_states);
-                    s->rng_states = nullptr;
-                    s->rng_capacity = 0;
-                    CUDA_TRY(cudaMalloc(&s->rng_states, frame_px * sizeof(rtk::XorwowState)));
-                    s->rng_capacity = frame_px;
-                }
-                rtk::xorwow_init_states<<<(unsigned)((frame_px + 255) / 256), 256, 0, s->stream>>>(seed, (unsigned)frame_px, s->rng_states);
-                CUDA_TRY(cudaGetLastError());
-                s->rng_W = p->W;
-                s->rng_H = p->H;
-                s->rng_seed = seed;
-                launches++;
-                CUDA_TRY(cudaEventRecord(s->ev0, s->stream)); /* the one-off table build is not part of the frame time */
-            }
             CUDA_TRY(cudaMemsetAsync(s->counters, 0, RT_NCOUNTERS * sizeof(unsigned long long), s->stream));
             if (count) rtk::render_stoch<true><<<grid, 128, 0, s->stream>>>(s->header, s->blob, a, s->rng_states, p->aa_sigma, p->indirect);
             else rtk::render_stoch<false><<<grid, 128, 0, s->stream>>>(s->header, s->blob, a, s->rng_states, p->aa_sigma, p->indirect);

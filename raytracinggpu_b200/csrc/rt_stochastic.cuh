@@ -26,8 +26,8 @@ namespace rtk {
 
 #define RT_STOCH_MAX_SEGMENTS 16
 
-struct XorwowState {
-    unsigned int d, v[5];
+struct __align__(16) XorwowState { /* 32 B: two uint4 per pixel (the wavefront pipeline reads it that way) */
+    unsigned int d, v[5], pad[2];
 };
 
 /* start state of every pixel of a W x H frame: the library's curand_init(seed, pixel, 0) */
@@ -40,6 +40,7 @@ __global__ void xorwow_init_states(unsigned long long seed, unsigned int npx, Xo
     o.d = st.d;
 #pragma unroll
     for (int k = 0; k < 5; k++) o.v[k] = st.v[k];
+    o.pad[0] = o.pad[1] = 0;
     out[i] = o;
 }
 
@@ -65,10 +66,6 @@ __device__ __forceinline__ float xorwow_uniform(XorwowState& s) {
     s.d += 362437u;
     return (float)(s.v[4] + s.d) * 2.3283064e-10f + (2.3283064e-10f / 2.0f);
 }
-
-__device__ __forceinline__ float canon_log(float x) { return (float)log((double)x); }
-__device__ __forceinline__ float canon_cos(float x) { return (float)cos((double)x); }
-__device__ __forceinline__ float canon_sin(float x) { return (float)sin((double)x); }
 
 template <bool COUNT>
 __global__ void __launch_bounds__(128) render_stoch(const __grid_constant__ SceneHeader h, const unsigned char* __restrict__ blob, const RenderArgs a,

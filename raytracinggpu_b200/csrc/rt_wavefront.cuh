@@ -60,6 +60,17 @@ struct WfArgs {
     QEntry* qS;    /* shadow queue of the current round */
     WfCounters* c;
     int round;     /* round whose queues this launch consumes (traverse, shade) */
+    /* stochastic mode (rt_stochastic.cuh explains the stream): one wavefront pass per sample */
+    int stoch;             /* 0: deterministic mode */
+    int sample;            /* sample index of this pass; first-hit outputs come from sample 0 */
+    int last_sample;       /* wf_fold of this pass writes the 8-bit pixel */
+    int indirect;
+    float aa_sigma;
+    int npx;               /* compact pixels of this strip: stride of rec */
+    const uint4* rng_table; /* start state of every pixel of the W x H frame, 2 x uint4 per pixel (d, v0..v4, -, -) */
+    uint4* rng;            /* running state per compact pixel of the strip, 2 x uint4 */
+    float4* total;         /* per compact pixel: colour summed over the samples (xyz), bit mask of the diffuse segments of this sample (w) */
+    float4* rec;           /* [segment][compact pixel][2]: direct term, albedo of the diffuse hit that ended that segment */
     int run_shift;  /* log2 of the admission run length, -1 = chosen per launch from the queue length */
     int gss_factor; /* the last gss_factor * n_warps runs are admitted one at a time */
     int* spill;     /* node-pool overflow area: spill_cap ints per traversal warp (global memory) */
@@ -85,7 +96,38 @@ struct Post {
     F3 O, u;
     float aux, n_ray;
     int packed;
+    /* stochastic mode: a diffuse hit posts its shadow query AND the path goes on, so one call may need a second slot */
+    int kind2; /* 0 or WF_MODE_CLOSEST: the next segment, root box NOT tested yet (pixel sign bit set in the entry) */
+    F3 O2, u2;
+    float aux2;
+    int packed2;
 };
+#define WF_ROOT_UNTESTED 0x80000000u /* in QEntry::pixel */
+
+/* running XORWOW state of a pixel in global memory (rt_stochastic.cuh: XorwowState), 2 x uint4 */
+struct RngRef {
+    uint4* p;
+    bool loaded;
+    unsigned d, v0, v1, v2, v3, v4;
+};
+__device__ __forceinline__ float rng_uniform(RngRef& r) {
+    if (!r.loaded) {
+        const uint4 a = r.p[0], b = r.p[1];
+        r.d = a.x; r.v0 = a.y; r.v1 = a.z; r.v2 = a.w; r.v3 = b.x; r.v4 = b.y;
+        r.loaded = true;
+    }
+    const unsigned t = r.v0 ^ (r.v0 >> 2); /* curand(): xorwow + Weyl, curand_kernel.h:863-874 */
+    r.v0 = r.v1; r.v1 = r.v2; r.v2 = r.v3; r.v3 = r.v4;
+    r.v4 = (r.v4 ^ (r.v4 << 4)) ^ (t ^ (t << 1));
+    r.d += 362437u;
+    return (float)(r.v4 + r.d) * 2.3283064e-10f + (2.3283064e-10f / 2.0f); /* curand_uniform */
+}
+__device__ __forceinline__ void rng_store(const RngRef& r) {
+    if (r.loaded) {
+        r.p[0] = make_uint4(r.d, r.v0, r.v1, r.v2);
+        r.p[1] = make_uint4(r.v3, r.v4, 0u, 0u);
+    }
+}
 
 __device__ __forceinline__ void store_entry(QEntry* q, int slot, F3 O, F3 u, float aux, int pixel, float n_ray, int packed, unsigned long long res) {
     float4* p = reinterpret_cast<float4*>(q + slot);
@@ -119,17 +161,21 @@ __device__ __forceinline__ void closest_sphere(const SceneHeader& h, F3 O, F3 u,
 }
 
 /* Advance one pixel's path until it ends or needs the mesh. have_hit: (t_hit, sidx, tri) already hold the
- * answer of intersect_all for the current ray (wf_shade); otherwise the segment starts here. */
-template <bool COUNT>
+ * answer of intersect_all for the current ray (wf_shade); otherwise the segment starts here.
+ * STOCH (stochastic mode, one pass per sample): nothing is written to the framebuffer here; every diffuse hit leaves a
+ * (direct, albedo) record for wf_fold, draws the two uniforms of optimized.cu:633-634 from the pixel's stream and, with
+ * the indirect bounce enabled, goes on along the cosine-weighted direction. */
+template <bool COUNT, bool STOCH>
 __device__ __forceinline__ void path_advance(const SceneHeader& h, const WfArgs& g, const float4* __restrict__ tris, int px, F3 O, F3 u, float n_ray,
                                              int depth, bool have_hit, float t_hit, int sidx, int tri, Work& w, Post& post) {
     const RenderArgs& a = g.a;
     const F3 Lp = f3(h.L[0], h.L[1], h.L[2]);
     const float eps = a.eps_surface;
+    const bool first_sample = !STOCH || g.sample == 0;
     for (;;) {
         if (!have_hit) {
             if (depth >= a.segments) { /* path budget used up without a diffuse hit: colour 0 (fold of optimized.cu:653-660) */
-                write_pixel(a, px, f3(0.f, 0.f, 0.f));
+                if (!STOCH) write_pixel(a, px, f3(0.f, 0.f, 0.f));
                 return;
             }
             w.rays++;
@@ -152,17 +198,14 @@ __device__ __forceinline__ void path_advance(const SceneHeader& h, const WfArgs&
         have_hit = false;
         /* ---- the hit of this segment is known: shade it (optimized.cu:571-650) ---------------------------------- */
         const int obj = tri >= 0 ? h.mesh_id : (sidx >= 0 ? h.spheres[sidx].id : -1);
-#ifdef RT_TRACE
-        if (depth == 0) printf("  first-hit write px %d obj %d tri %d t %f (have_hit path)\n", px, obj, tri, t_hit);
-#endif
-        if (depth == 0) {
+        if (depth == 0 && first_sample) {
             if (a.hit_obj) a.hit_obj[px] = obj;
             if (a.hit_tri) a.hit_tri[px] = tri;
             if (a.hit_t) a.hit_t[px] = t_hit;
         }
         depth++;
         if (obj < 0) { /* the ray left the scene */
-            write_pixel(a, px, f3(0.f, 0.f, 0.f));
+            if (!STOCH) write_pixel(a, px, f3(0.f, 0.f, 0.f));
             return;
         }
         const F3 P = O + t_hit * u; /* :555 */
@@ -209,7 +252,7 @@ __device__ __forceinline__ void path_advance(const SceneHeader& h, const WfArgs&
                 u = Ncomp + Tcomp;
                 n_ray = out2in ? n_in : n_out;
             }
-        } else { /* diffuse :610-650 — the deterministic path ends here */
+        } else { /* diffuse :610-650 */
             const F3 Padj = P + eps * N;
             const F3 toL = Lp - Padj;
             const float D2 = norm2(toL);
@@ -221,23 +264,32 @@ __device__ __forceinline__ void path_advance(const SceneHeader& h, const WfArgs&
                 float t;
                 if (sphere_t(h.spheres[s], Padj, su, t) && t < RTK_INF && blocks_light(Padj, su, t, D2)) blocked = true;
             }
-            if (blocked) {
-                write_pixel(a, px, f3(0.f, 0.f, 0.f));
-                if (a.shadow) a.shadow[px] = 1;
-                return;
+            F3 dcol = f3(0.f, 0.f, 0.f);
+            if (!blocked) {
+                const F3 PL = Lp - P;
+                const F3 wl = normalized(PL);
+                const float ndl = dot(N, wl);
+                const float lambert = (ndl < 0.f) ? 0.f : ndl; /* std::max(dot, 0.f) */
+                const float l = (float)((double)h.intensity / (12.566370614359172 * (double)norm2(PL)) * (double)lambert); /* :628, in double */
+                dcol = (l * albedo) / 3.14159274f;                                                                        /* :629 */
             }
-            const F3 PL = Lp - P;
-            const F3 wl = normalized(PL);
-            const float ndl = dot(N, wl);
-            const float lambert = (ndl < 0.f) ? 0.f : ndl; /* std::max(dot, 0.f) */
-            const float l = (float)((double)h.intensity / (12.566370614359172 * (double)norm2(PL)) * (double)lambert); /* :628, in double */
-            write_pixel(a, px, (l * albedo) / 3.14159274f);                                                      /* :629 */
-            if (a.shadow) a.shadow[px] = 0;
-            if (h.has_mesh) {
+            const int seg = depth - 1;
+            if (!STOCH) {
+                write_pixel(a, px, dcol);
+                if (a.shadow) a.shadow[px] = blocked ? 1 : 0;
+            } else {
+                float4* r = g.rec + ((size_t)seg * g.npx + px) * 2;
+                r[0] = make_float4(dcol.x, dcol.y, dcol.z, 0.f);
+                r[1] = (g.indirect ? make_float4(albedo.x, albedo.y, albedo.z, 0.f) : make_float4(0.f, 0.f, 0.f, 0.f));
+                int* types = reinterpret_cast<int*>(&g.total[px].w);
+                *types |= 1 << seg;
+                if (seg == 0 && first_sample && a.shadow) a.shadow[px] = blocked ? 1 : 0;
+            }
+            if (!blocked && h.has_mesh) {
                 const RayCtx ctx = make_ray_ctx(Padj, su, h.box_abs[0], h.box_abs[1], h.box_abs[2]);
                 float tn;
                 if (slab_fast(h.root_mn[0], h.root_mn[1], h.root_mn[2], h.root_mx[0], h.root_mx[1], h.root_mx[2], ctx, tn, w.slab_fallbacks)) {
-                    /* the pixel keeps its lit colour unless the traversal finds a blocker, which paints it black */
+                    /* the pixel (STOCH: the record) keeps its lit colour unless the traversal finds a blocker, which zeroes it */
                     post.kind = WF_MODE_ANY;
                     post.O = Padj;
                     post.u = su;
@@ -246,7 +298,34 @@ __device__ __forceinline__ void path_advance(const SceneHeader& h, const WfArgs&
                     post.packed = 0xff | (depth << 8) | (WF_MODE_ANY << 24);
                 }
             }
-            return;
+            if (!STOCH || !g.indirect) return; /* the deterministic path ends at the first diffuse hit */
+            /* ---- :631-649 — two uniforms at every diffuse hit (the last segment included), cosine-weighted direction */
+            RngRef rng;
+            rng.p = g.rng + (size_t)px * 2;
+            rng.loaded = false;
+            const float q1 = rng_uniform(rng), q2 = rng_uniform(rng);
+            rng_store(rng);
+            if (depth >= a.segments) return;
+            const float an = (float)(2 * 3.14159265358979323846 * (double)q1);
+            const float sq = sqrtf(1 - q2);
+            const float x = canon_cos(an) * sq, y = canon_sin(an) * sq, z = sqrtf(q2);
+            const F3 T1 = normalized((fabsf(N.y) != 0 && fabsf(N.x) != 0) ? f3(-N.y, N.x, 0.f) : f3(-N.z, 0.f, N.x));
+            const F3 T2 = cross(N, T1);
+            u = (x * T1 + y * T2) + z * N;
+            O = Padj;
+            n_ray = 1.f;
+            if (post.kind == WF_MODE_ANY) {
+                /* this call already owes a shadow query: the next segment goes through the queue with its root-box test
+                 * left to wf_traverse, so that no call ever posts more than one query of each kind */
+                w.rays++;
+                closest_sphere(h, O, u, t_hit, sidx);
+                post.kind2 = WF_MODE_CLOSEST;
+                post.O2 = O;
+                post.u2 = u;
+                post.aux2 = t_hit;
+                post.packed2 = (sidx & 0xff) | (depth << 8) | (WF_MODE_CLOSEST << 24);
+                return;
+            }
         }
     }
 }
@@ -257,19 +336,23 @@ __device__ __forceinline__ void post_queries(const WfArgs& g, int post_round, co
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
-    const unsigned mA = __ballot_sync(FULL, post.kind == WF_MODE_CLOSEST);
-    const unsigned mS = __ballot_sync(FULL, post.kind == WF_MODE_ANY);
+    const bool wantA = post.kind == WF_MODE_CLOSEST, wantS = post.kind == WF_MODE_ANY, want2 = post.kind2 == WF_MODE_CLOSEST;
+    const unsigned mA = __ballot_sync(FULL, wantA);
+    const unsigned mS = __ballot_sync(FULL, wantS);
+    const unsigned m2 = __ballot_sync(FULL, want2);
     int baseA = 0, baseS = 0;
     if (lane == 0) {
-        if (mA) baseA = atomicAdd(&g.c->nA[post_round], __popc(mA));
+        if (mA | m2) baseA = atomicAdd(&g.c->nA[post_round], __popc(mA) + __popc(m2));
         if (mS) baseS = atomicAdd(&g.c->nS[post_round], __popc(mS));
     }
     baseA = __shfl_sync(FULL, baseA, 0);
     baseS = __shfl_sync(FULL, baseS, 0);
-    if (post.kind == WF_MODE_CLOSEST)
+    if (wantA)
         store_entry(g.qA[post_round & 1], baseA + __popc(mA & lt), post.O, post.u, post.aux, px, post.n_ray, post.packed, WF_NOHIT);
-    else if (post.kind == WF_MODE_ANY)
+    else if (wantS)
         store_entry(g.qS, baseS + __popc(mS & lt), post.O, post.u, post.aux, px, post.n_ray, post.packed, 0ull);
+    if (want2)
+        store_entry(g.qA[post_round & 1], baseA + __popc(mA) + __popc(m2 & lt), post.O2, post.u2, post.aux2, (int)((unsigned)px | WF_ROOT_UNTESTED), 1.f, post.packed2, WF_NOHIT);
 }
 
 __device__ __forceinline__ void flush_work(const Work& w, WfCounters* c, bool count) {
@@ -291,7 +374,7 @@ __device__ __forceinline__ void flush_work(const Work& w, WfCounters* c, bool co
 }
 
 /* ---- wf_generate: one thread per pixel (a warp covers an 8x4 tile) ------------------------------------------------ */
-template <bool COUNT>
+template <bool COUNT, bool STOCH>
 __global__ void __launch_bounds__(WF_THREADS) wf_generate(const __grid_constant__ SceneHeader h, const unsigned char* __restrict__ blob,
                                                          const __grid_constant__ WfArgs g) {
     const RenderArgs& a = g.a;
@@ -305,23 +388,49 @@ __global__ void __launch_bounds__(WF_THREADS) wf_generate(const __grid_constant_
     w.rays = w.nodes = w.tris = w.max_stack = w.slab_fallbacks = w.tri_exact = 0;
     Post post;
     post.kind = 0;
+    post.kind2 = 0;
     const int px = kr * a.W + j;
     if (j < a.W && kr < a.rows) {
         const int i = a.row_begin + kr * a.row_step;
         const F3 uc = f3((float)j - (float)a.W / 2 + 0.5f, (float)a.H / 2 - (float)i - 0.5f, a.z); /* optimized.cu:751, exact in float */
-        const F3 u0 = normalized(uc); /* sigma == 0: the jitter terms of :758 are exactly 0 */
-        if (a.hit_obj) a.hit_obj[px] = -1;
-        if (a.hit_tri) a.hit_tri[px] = -1;
-        if (a.hit_t) a.hit_t[px] = RTK_INF;
-        if (a.shadow) a.shadow[px] = 2;
-        path_advance<COUNT>(h, g, tris, px, f3(a.camx, a.camy, a.camz), u0, 1.f, 0, false, 0.f, -1, -1, w, post);
+        F3 u0;
+        if (!STOCH) {
+            u0 = normalized(uc); /* sigma == 0: the jitter terms of :758 are exactly 0 */
+        } else {
+            /* the pixel's stream: sample 0 starts from curand_init(seed, GLOBAL pixel index, 0) (optimized.cu:745), later
+             * samples from where the previous sample's path left it */
+            RngRef rng;
+            rng.p = g.rng + (size_t)px * 2;
+            rng.loaded = false;
+            if (g.sample == 0) {
+                const uint4* t = g.rng_table + ((size_t)i * a.W + j) * 2;
+                const uint4 s0 = t[0], s1 = t[1];
+                rng.d = s0.x; rng.v0 = s0.y; rng.v1 = s0.z; rng.v2 = s0.w; rng.v3 = s1.x; rng.v4 = s1.y;
+                rng.loaded = true;
+                g.total[px] = make_float4(0.f, 0.f, 0.f, 0.f);
+            } else {
+                g.total[px].w = 0.f; /* no diffuse segment recorded yet in this sample */
+            }
+            const float r1 = rng_uniform(rng), r2 = rng_uniform(rng); /* :756-757 */
+            rng_store(rng);
+            const float rad = g.aa_sigma * sqrtf(-2 * canon_log(r1));
+            const float ang = (float)(2 * 3.14159265358979323846 * (double)r2);
+            u0 = normalized(uc + f3(rad * canon_cos(ang), rad * canon_sin(ang), 0.f)); /* :758-759 */
+        }
+        if (!STOCH || g.sample == 0) {
+            if (a.hit_obj) a.hit_obj[px] = -1;
+            if (a.hit_tri) a.hit_tri[px] = -1;
+            if (a.hit_t) a.hit_t[px] = RTK_INF;
+            if (a.shadow) a.shadow[px] = 2;
+        }
+        path_advance<COUNT, STOCH>(h, g, tris, px, f3(a.camx, a.camy, a.camz), u0, 1.f, 0, false, 0.f, -1, -1, w, post);
     }
     post_queries(g, 0, post, px);
     flush_work(w, g.c, COUNT);
 }
 
 /* ---- wf_shade: one thread per answered closest-hit query of round g.round ------------------------------------------ */
-template <bool COUNT>
+template <bool COUNT, bool STOCH>
 __global__ void __launch_bounds__(WF_THREADS) wf_shade(const __grid_constant__ SceneHeader h, const unsigned char* __restrict__ blob,
                                                       const __grid_constant__ WfArgs g) {
     const RenderArgs& a = g.a;
@@ -334,13 +443,14 @@ __global__ void __launch_bounds__(WF_THREADS) wf_shade(const __grid_constant__ S
     for (int e = blockIdx.x * WF_THREADS + threadIdx.x; e < n_round; e += gridDim.x * WF_THREADS) {
         Post post;
         post.kind = 0;
+        post.kind2 = 0;
         int px = 0;
         if (e < n) {
             const float4* p = reinterpret_cast<const float4*>(q + e);
             const float4 p0 = p[0], p1 = p[1], p2 = p[2];
             const F3 O = f3(p0.x, p0.y, p0.z), u = f3(p1.x, p1.y, p1.z);
             float t_hit = p0.w;
-            px = __float_as_int(p1.w);
+            px = (int)(__float_as_uint(p1.w) & ~WF_ROOT_UNTESTED);
             const int packed = __float_as_int(p2.y);
             int sidx = packed & 0xff;
             if (sidx == 0xff) sidx = -1;
@@ -359,11 +469,43 @@ __global__ void __launch_bounds__(WF_THREADS) wf_shade(const __grid_constant__ S
 #ifdef RT_TRACE
             printf("  shade e %d px %d key %llx t_hit %f sidx %d tri %d depth %d\n", e, px, key, t_hit, sidx, tri, depth);
 #endif
-            path_advance<COUNT>(h, g, tris, px, O, u, p2.x, depth, true, t_hit, sidx, tri, w, post);
+            path_advance<COUNT, STOCH>(h, g, tris, px, O, u, p2.x, depth, true, t_hit, sidx, tri, w, post);
         }
         post_queries(g, g.round + 1, post, px);
     }
     flush_work(w, g.c, COUNT);
+}
+
+/* ---- wf_fold (stochastic mode): the end of one sample pass. Folds the pixel's diffuse records back to front,
+ * c = albedo_i * c + direct_i (optimized.cu:653-660), adds the sample to the pixel's sum and, after the last sample,
+ * writes the averaged 8-bit pixel (optimized.cu:764-771). Runs after the pass's last traversal, when every shadow query
+ * has had its say about the direct terms. */
+__global__ void __launch_bounds__(256) wf_fold(const __grid_constant__ WfArgs g) {
+    const RenderArgs& a = g.a;
+    const int px = blockIdx.x * blockDim.x + threadIdx.x;
+    if (px >= g.npx) return;
+    float4 tot = g.total[px];
+    const unsigned types = (unsigned)__float_as_int(tot.w);
+    F3 ans = f3(0.f, 0.f, 0.f);
+    for (int d = a.segments - 1; d >= 0; d--) {
+        if ((types >> d) & 1u) {
+            const float4* r = g.rec + ((size_t)d * g.npx + px) * 2;
+            const float4 dc = r[0], al = r[1];
+            ans = f3(al.x, al.y, al.z) * ans + f3(dc.x, dc.y, dc.z);
+        }
+    }
+    const F3 sum = f3(tot.x, tot.y, tot.z) + ans; /* color_out = color_out + color, :762 */
+    if (g.last_sample) {
+        if (a.rgb) {
+            const F3 avg = sum / (float)a.num_rays; /* :764 */
+            const float* T = a.gamma_tab + a.gamma_mode * 256;
+            a.rgb[(size_t)px * 3 + 0] = (uint8_t)quantise(avg.x, T);
+            a.rgb[(size_t)px * 3 + 1] = (uint8_t)quantise(avg.y, T);
+            a.rgb[(size_t)px * 3 + 2] = (uint8_t)quantise(avg.z, T);
+        }
+    } else {
+        g.total[px] = make_float4(sum.x, sum.y, sum.z, 0.f);
+    }
 }
 
 /* ---- wf_traverse: persistent warps drain the closest-hit and shadow queues of round g.round ------------------------
@@ -399,7 +541,7 @@ struct WfWarpSmem { /* per warp; followed by the node pool (npool_cap ints) */
     int tpool[WF_TPOOL];
 };
 
-template <bool COUNT>
+template <bool COUNT, bool STOCH>
 __global__ void __launch_bounds__(WF_THREADS, 8) wf_traverse(const __grid_constant__ SceneHeader h, const unsigned char* __restrict__ blob,
                                                          const __grid_constant__ WfArgs g, const int npool_cap) {
     extern __shared__ __align__(16) unsigned char wf_smem[];
@@ -461,12 +603,18 @@ __global__ void __launch_bounds__(WF_THREADS, 8) wf_traverse(const __grid_consta
                         (qA + e)->res = sm.best[slot];
                     } else if (sm.B[slot].w < 0.f) { /* the light is blocked: the pixel is black (optimized.cu:620-622) */
                         const int px = __float_as_int(sm.D[slot].w);
-                        if (a.rgb) {
-                            a.rgb[(size_t)px * 3 + 0] = 0;
-                            a.rgb[(size_t)px * 3 + 1] = 0;
-                            a.rgb[(size_t)px * 3 + 2] = 0;
+                        if (!STOCH) {
+                            if (a.rgb) {
+                                a.rgb[(size_t)px * 3 + 0] = 0;
+                                a.rgb[(size_t)px * 3 + 1] = 0;
+                                a.rgb[(size_t)px * 3 + 2] = 0;
+                            }
+                            if (a.shadow) a.shadow[px] = 1;
+                        } else { /* stochastic mode: the direct term of that segment's record becomes 0 (direct_colors[ray_depth], :622) */
+                            const int seg = (((qS + (e - nA))->packed >> 8) & 0xffff) - 1;
+                            g.rec[((size_t)seg * g.npx + px) * 2] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (seg == 0 && g.sample == 0 && a.shadow) a.shadow[px] = 1;
                         }
-                        if (a.shadow) a.shadow[px] = 1;
                     }
                 }
                 __syncwarp();
@@ -499,13 +647,32 @@ __global__ void __launch_bounds__(WF_THREADS, 8) wf_traverse(const __grid_consta
                 const int r = r0 + (lane >> rs);
                 const int run = (r & 3) * n_quarter + (r >> 2); /* consecutive run ids alternate between the four quarters of the queue */
                 const int e = (run << rs) + (lane & ((1 << rs) - 1));
-                const bool valid = (lane >> rs) < k && r < 4 * n_quarter && run < n_runs && e < total;
+                bool valid = (lane >> rs) < k && r < 4 * n_quarter && run < n_runs && e < total;
+                float4 p0, p1;
+                RayCtx c;
+                if (STOCH && valid) {
+                    const float4* p = reinterpret_cast<const float4*>(e < nA ? (qA + e) : (qS + (e - nA)));
+                    p0 = __ldcg(p);
+                    p1 = __ldcg(p + 1);
+                    c = make_ray_ctx(f3(p0.x, p0.y, p0.z), f3(p1.x, p1.y, p1.z), h.box_abs[0], h.box_abs[1], h.box_abs[2]);
+                    if (__float_as_uint(p1.w) & WF_ROOT_UNTESTED) {
+                        /* a bounce ray queued without its root-box test (path_advance); a ray that misses the root box needs
+                         * nothing from the mesh — its entry keeps WF_NOHIT — and takes no slot */
+                        float tn;
+                        unsigned fb = 0;
+                        valid = slab_fast(h.root_mn[0], h.root_mn[1], h.root_mn[2], h.root_mx[0], h.root_mx[1], h.root_mx[2], c, tn, fb);
+                        p1.w = __uint_as_float(__float_as_uint(p1.w) & ~WF_ROOT_UNTESTED);
+                    }
+                }
                 const unsigned vmask = __ballot_sync(FULL, valid);
                 const int take = __popc(vmask);
                 if (valid) {
-                    const float4* p = reinterpret_cast<const float4*>(e < nA ? (qA + e) : (qS + (e - nA)));
-                    const float4 p0 = __ldcg(p), p1 = __ldcg(p + 1);
-                    const RayCtx c = make_ray_ctx(f3(p0.x, p0.y, p0.z), f3(p1.x, p1.y, p1.z), h.box_abs[0], h.box_abs[1], h.box_abs[2]);
+                    if (!STOCH) {
+                        const float4* p = reinterpret_cast<const float4*>(e < nA ? (qA + e) : (qS + (e - nA)));
+                        p0 = __ldcg(p);
+                        p1 = __ldcg(p + 1);
+                        c = make_ray_ctx(f3(p0.x, p0.y, p0.z), f3(p1.x, p1.y, p1.z), h.box_abs[0], h.box_abs[1], h.box_abs[2]);
+                    }
                     const int slot = b * 32 + lane;
                     const bool any = e >= nA;
                     sm.A[slot] = make_float4(c.rx, c.ry, c.rz, c.M);

@@ -88,6 +88,26 @@ def test_stochastic_sharding_keeps_the_image(scene):
     assert not np.array_equal(scene.render(q, want=("rgb",))["rgb"], full["rgb"])
 
 
+def test_wavefront_and_thread_per_pixel_kernels_agree(scene, monkeypatch):
+    """The stochastic mode has two implementations: one wavefront pass per sample (default) and the thread-per-pixel
+    kernel render_stoch (RT_STOCH_MEGA=1, also the fallback for more than 11 segments). Same stream, same arithmetic:
+    identical frames."""
+    d = scenes.cat_scene("optimized", mirror=0) or scenes.torus_scene("optimized")
+    scenes.upload(scene, d)
+    p = stoch("optimized", 400, 225, 3, 4)
+    a = scene.render(p)
+    monkeypatch.setenv("RT_STOCH_MEGA", "1")
+    b = scene.render(p)
+    monkeypatch.delenv("RT_STOCH_MEGA")
+    for k in ("rgb", "hit_obj", "hit_tri", "shadow"):
+        assert np.array_equal(a[k], b[k]), k
+    assert a["stats"]["rays"] == b["stats"]["rays"]
+    assert a["stats"]["launches"] > b["stats"]["launches"]
+    # more segments than the wavefront pipeline has rounds: falls back to the thread-per-pixel kernel
+    q = stoch("optimized", 96, 54, 1, 14)
+    scenes.compare(scene.render(q), scenes.run_oracle(d, q))
+
+
 @pytest.mark.parametrize("rays,bounce,min_exact", [(1, 1, 0.975), (4, 3, 0.80)])
 def test_against_the_unmodified_reference_gpu_kernel(scene, rays, bounce, min_exact):
     """optimized.cu's own KernelLaunch (oracle/_ref/ref_optimized, --use_fast_math) at 512x512 vs this library with the
