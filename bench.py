@@ -46,7 +46,7 @@ class ClockSampler:
     def __init__(self, index):
         self.rows, self.proc = [], None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -222,6 +222,7 @@ def run_ours(args):
     d2h = int(H * W * 3)
 
     work = sc.render(p, want=("rgb",), count_work=True)["stats"]  # instrumented pass for the roofline, not timed
+    like_for_like = stochastic_vs_reference_kernel(rt, torch, sc) if (world == 1 and rank == 0) else None
     sharded = sharded_single_frame(rt, torch, sc, stream, world, rank, verts, recs, bvh, mesh_id, walls)
 
     if rank != 0:
@@ -257,10 +258,41 @@ def run_ours(args):
            "e2e": {"value": round(e2e_value, 2), "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": round(e2e_s / e2e_steps * 1e3, 4),
                    "steps": e2e_steps},
            "gpu_launches": launches_per_step * args.steps, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
-           "ms_per_frame": round(kernel_ms, 5), "scene_broadcast_bytes": blob_bytes, "single_frame_sharded": sharded}
+           "ms_per_frame": round(kernel_ms, 5), "scene_broadcast_bytes": blob_bytes, "single_frame_sharded": sharded,
+           "stochastic_vs_reference_gpu_kernel": like_for_like}
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+def stochastic_vs_reference_kernel(rt, torch, sc):
+    """Like for like with the reference's GPU program: `./optimized 1 1` at 1920x1080 is the STOCHASTIC mode (sigma 0.2
+    jitter + cuRAND stream). Times this library's stochastic mode (CUDA events inside rt_render) next to the unmodified
+    optimized.cu kernel (oracle/_ref/ref_optimized: reference flags retargeted to sm_100a, CUDA events around its
+    KernelLaunch) on this GPU. Extra information beside the headline; None when the compiled reference did not travel."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_optimized")
+    cat = find_cat()
+    if not (cat and os.path.exists(exe)):
+        return None
+    out = {}
+    for rays, bounce in ((1, 1), (4, 3)):
+        p = rt.params_profile("optimized", W, H, rays, bounce)
+        p.aa_sigma, p.indirect = 0.2, 1
+        rgb = torch.empty((H, W, 3), dtype=torch.uint8, device="cuda")
+        ms = []
+        for i in range(8):
+            st = sc.render_into(p, rgb=rgb)
+            if i >= 3:
+                ms.append(st.kernel_ms)
+        try:
+            r = subprocess.run([exe, cat, str(W), str(H), str(rays), str(bounce), "5"], capture_output=True, text=True, timeout=120)
+            ref_ms = json.loads(r.stdout.strip().splitlines()[-1])["kernel_ms_median"]
+        except Exception as e:  # noqa: BLE001
+            ref_ms = None
+        ours = float(np.median(ms))
+        out["optimized_%d_%d" % (rays, bounce)] = {"this_ms": round(ours, 4), "reference_kernel_ms": ref_ms, "rays_per_frame": int(st.rays),
+                                                   "speedup": round(ref_ms / ours, 2) if ref_ms else None}
+    return out
 
 
 def sharded_single_frame(rt, torch, sc, stream, world, rank, verts, recs, bvh, mesh_id, walls, frames=8):

@@ -677,6 +677,7 @@ int rt_render(rt_scene* s, const rt_params* p, uint32_t flags, uint8_t* rgb_out,
     a.debug_cost = getenv("RT_DEBUG_COST") ? 1 : 0;
 
     int launches = 0;
+    bool strip_copied = false; /* host outputs already copied back band by band */
     CUDA_TRY(cudaEventRecord(s->ev0, s->stream)); /* kernel_ms covers everything a frame enqueues, counter resets included */
     {
         const int tiles_x = (p->W + 15) / 16, tiles_y = (rows + 7) / 8;
@@ -905,6 +906,14 @@ int rt_render(rt_scene* s, const rt_params* p, uint32_t flags, uint8_t* rgb_out,
                     }
                 }
                 if (n_strips > 1) {
+                    /* host outputs: this band's copy-back rides on the band's stream and overlaps the other bands' kernels
+                     * (kernel_ms then spans the copies of all bands but the last as well) */
+                    const size_t elem[5] = {3, 4, 4, 4, 1};
+                    for (int k = 0; k < 5; k++)
+                        if (copy_back[k]) {
+                            CUDA_TRY(cudaMemcpyAsync((unsigned char*)user[k] + px0 * elem[k], (unsigned char*)dev[k] + px0 * elem[k], spx * elem[k], cudaMemcpyDeviceToHost, stream));
+                            strip_copied = true;
+                        }
                     CUDA_TRY(cudaEventRecord(s->strip_done[st], stream));
                     CUDA_TRY(cudaStreamWaitEvent(s->stream, s->strip_done[st], 0));
                 }
@@ -940,7 +949,7 @@ int rt_render(rt_scene* s, const rt_params* p, uint32_t flags, uint8_t* rgb_out,
     }
     CUDA_TRY(cudaEventRecord(s->ev1, s->stream));
     for (int k = 0; k < 5; k++)
-        if (copy_back[k]) CUDA_TRY(cudaMemcpyAsync(user[k], dev[k], bytes[k], cudaMemcpyDeviceToHost, s->stream));
+        if (copy_back[k] && !strip_copied) CUDA_TRY(cudaMemcpyAsync(user[k], dev[k], bytes[k], cudaMemcpyDeviceToHost, s->stream));
     s->pending = true; /* the counters are read back by rt_scene_sync, not per enqueued frame */
     s->pending_launches = launches;
     if (flags & RT_RENDER_NO_SYNC) {
