@@ -1,0 +1,16 @@
+"""Short program for ncu: BASELINE.json configs[4] (9,999,666-triangle instanced cat, 3840x2160 primary + shadow)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import raytracinggpu_b200 as rt
+from raytracinggpu_b200 import synthetic
+from oracle import profiles, scenes, pyoracle
+scales, offs = synthetic.instance_lattice()
+mesh = rt.Mesh.read_obj(pyoracle.cat_obj_path()).instance(scales, offs).build_bvh()
+desc = dict(spheres=profiles.walls("optimized"), mesh=(mesh.vertices, mesh.tri_records, mesh.arr_bvh), mesh_mat=profiles.mesh_material("optimized", 0), light=profiles.LIGHT)
+sc = scenes.upload(rt.Scene(0), desc)
+p = profiles.params("optimized", 3840, 2160, 1, 1)
+rgb = torch.empty((2160, 3840, 3), dtype=torch.uint8, device="cuda")
+for i in range(int(sys.argv[1]) if len(sys.argv) > 1 else 3):
+    st = sc.render_into(p, rgb=rgb)
+print("kernel_ms", st.kernel_ms, "rays", st.rays, "launches", st.launches)
