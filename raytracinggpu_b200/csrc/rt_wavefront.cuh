@@ -557,15 +557,11 @@ __global__ void __launch_bounds__(WF_THREADS, 8) wf_traverse(const __grid_consta
 
     const int nA = g.c->nA[g.round], nS = g.c->nS[g.round];
     const int total = nA + nS;
-    QEntry* qA = g.qA[g.round & 1];
-    QEntry* qS = g.qS;
-    int* head = &g.c->head[g.round];
     Work w;
     w.rays = w.nodes = w.tris = w.max_stack = w.slab_fallbacks = w.tri_exact = 0;
 
     int nN = 0, nT = 0;               /* pool fill (warp-uniform) */
     int nSp = 0;                      /* node tasks parked in the warp's global overflow area (warp-uniform) */
-    int* spill = g.spill + (size_t)(blockIdx.x * (WF_THREADS / 32) + warp) * g.spill_cap;
     const int half = (npool_cap >> 1) & ~31;
     int out0 = 0, out1 = 0;           /* outstanding tasks of batch 0 / 1 (warp-uniform) */
     int cnt0 = 0, cnt1 = 0;           /* rays admitted in batch 0 / 1; 0 = batch free */
@@ -590,8 +586,15 @@ __global__ void __launch_bounds__(WF_THREADS, 8) wf_traverse(const __grid_consta
     if (COUNT) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t0));
 
     for (;;) {
-        /* ---- retire complete batches: results go back to the queue entries ---------------------------------------- */
+        /* Housekeeping — retiring finished batches, admitting rays, parking / fetching overflow, the exit test — only
+         * matters when the pools run low (slots are wanted, or the work is over) or the node pool runs full; while a warp
+         * has a comfortable backlog the loop is just the step (all of this is warp-uniform register arithmetic, but it was
+         * 17 % of the instructions of a launch when evaluated at every step). */
         if (COUNT) cyc_mark = clock64();
+        if (nN + nT < 48 || npool_cap - nN < 32) {
+        /* ---- retire complete batches: results go back to the queue entries ---------------------------------------- */
+        QEntry* const qA = g.qA[g.round & 1];
+        QEntry* const qS = g.qS;
 #pragma unroll
         for (int b = 0; b < 2; b++) {
             const int cnt = b ? cnt1 : cnt0, out = b ? out1 : out0;
@@ -636,7 +639,7 @@ __global__ void __launch_bounds__(WF_THREADS, 8) wf_traverse(const __grid_consta
             /* guided self-scheduling: the last runs of the queue go out one at a time */
             if (4 * n_quarter - last_r0 < g.gss_factor * n_warps) k = 1;
             int r0 = 0;
-            if (lane == 0) r0 = atomicAdd(head, k);
+            if (lane == 0) r0 = atomicAdd(&g.c->head[g.round], k);
             r0 = __shfl_sync(FULL, r0, 0);
             last_r0 = r0;
             if (r0 >= 4 * n_quarter) {
@@ -706,6 +709,7 @@ __global__ void __launch_bounds__(WF_THREADS, 8) wf_traverse(const __grid_consta
          * nodes of any mix of rays). When it runs full with no leaf work to drain, its older half is parked in global
          * memory and brought back when the pool has emptied. Rare (the cat: a few warps per frame). */
         if (nN == 0 && nSp > 0) {
+            int* const spill = g.spill + (size_t)(blockIdx.x * (WF_THREADS / 32) + warp) * g.spill_cap;
             const int m = min(nSp, half);
             for (int i = lane; i < m; i += 32) npool[i] = spill[nSp - m + i];
             nSp -= m;
@@ -716,6 +720,7 @@ __global__ void __launch_bounds__(WF_THREADS, 8) wf_traverse(const __grid_consta
                 failed = true;
                 break;
             }
+            int* const spill = g.spill + (size_t)(blockIdx.x * (WF_THREADS / 32) + warp) * g.spill_cap;
             for (int i = lane; i < half; i += 32) spill[nSp + i] = npool[i];
             __syncwarp();
             const int rest = nN - half;
@@ -738,6 +743,7 @@ __global__ void __launch_bounds__(WF_THREADS, 8) wf_traverse(const __grid_consta
             }
             continue;
         }
+        } /* housekeeping */
 
         /* an N step pops cnt tasks and may push 2 cnt: it needs cnt free entries */
         const int room = npool_cap - nN;
