@@ -13,7 +13,7 @@ from ._abi import (RT_BVH_NODE_FLOATS, RT_OK, RT_RENDER_COUNT_WORK, RT_RENDER_NO
                    rt_sphere, rt_stats)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librtb200.so")
+LIB_PATH = os.environ.get("RT_LIB_PATH") or os.path.join(_HERE, "librtb200.so")  # RT_LIB_PATH: A/B runs of two builds in one session
 
 # every symbol include/rt_b200.h declares: (restype, argtypes)
 _vp, _i32, _f, _u64 = C.c_void_p, C.c_int32, C.c_float, C.c_uint64
