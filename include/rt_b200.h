@@ -39,7 +39,9 @@ enum {
     RT_ERR_NOMEM = -3,
     RT_ERR_IO = -4,          /* file could not be opened / written */
     RT_ERR_STATE = -5,       /* call order violated (e.g. render before scene upload) */
-    RT_ERR_UNSUPPORTED = -6  /* parameter combination not implemented */
+    RT_ERR_UNSUPPORTED = -6, /* parameter combination not implemented */
+    RT_ERR_AGAIN = -7        /* rt_scene_sync after RT_RENDER_NO_SYNC frames: an internal buffer was too small and has been
+                              * enlarged; the frame is incomplete, render it again (a synchronous rt_render repeats by itself) */
 };
 
 /* ---- scene description (reference: Sphere optimized.cu:117-136, Geometry :103-115) ---- */

@@ -8,6 +8,7 @@ RT_ERR_NOMEM = -3
 RT_ERR_IO = -4
 RT_ERR_STATE = -5
 RT_ERR_UNSUPPORTED = -6
+RT_ERR_AGAIN = -7
 
 RT_TRI_RECORD_WORDS = 10
 RT_BVH_NODE_FLOATS = 10

@@ -1,0 +1,125 @@
+/*
+ * rt_bins.cuh — candidate lists for rays whose line passes through a fixed point (an "anchor").
+ *
+ * Two families of rays of the reference's path are anchored: the camera rays (all start at Scene camera C,
+ * optimized.cu:747-759) and the shadow rays (all aim at the light L, optimized.cu:616-618) — every ray of the
+ * primary + shadow configuration, and (1 + B) of the 2 B rays of a B-segment path.
+ *
+ * What the reference's mesh query computes for a ray is fixed by the LEAVES whose own box passes
+ * BoundingBox::intersect (rt_layout.h, "Wide index": a child box that passes implies its parent passes, because the
+ * test is monotone under IEEE rounding): every triangle of those leaves is tested, the strict minimum of the accepted t
+ * wins. The inner boxes only serve to find those leaves. For anchored rays they can be found without a tree: the
+ * directions around the anchor are cut into 3 faces (dominant axis x, y or z; d and -d share a cell because the
+ * slab test knows no t >= 0) of R x R cells of the two ratios d_a / d_k, d_b / d_k in [-1, 1], and every cell lists the
+ * leaves whose box — inflated by eps — meets a line through the anchor with a direction of that cell (padded by one
+ * cell on every side). A ray looks up the cell of its direction, applies the reference's own slab test (certified
+ * fast path + exact fallback, rt_math.cuh) to the listed boxes, and emits one (ray, leaf) task per box that passes;
+ * wf_leaves then tests the triangles. Versus the tree search: 2.3 box tests per leaf found instead of 9, no task pools,
+ * no dependent chain of tree levels, and the triangle work arrives as uniform independent tasks.
+ *
+ * Superset property (why no leaf is lost). If the slab test of ray (O, u) passes for box [mn, mx], every pair of the
+ * six computed distances satisfies t1_j > t0_k; each is the correctly rounded quotient of a correctly rounded difference,
+ * relative error < 2^-23, so the true per-axis parameter intervals of the box inflated by 2^-21 (S + |O|) (S = largest
+ * box coordinate) intersect pairwise, hence (intervals on a line) have a common point: the true line meets the inflated
+ * box. A camera ray's line passes through the anchor exactly. A shadow ray starts at P' and has the direction
+ * fl((L - P') / |L - P'|), within 2^-21 of the true one: over the distances involved (D = |L - P'| plus the extent of
+ * the scene) its line stays within 2^-20 (D + S + |L|) of the line through P' and L. With eps = 2^-12 (S + |anchor|) and
+ * the guard D <= 2^7 (S + |anchor|) on the ray side, both are covered with a factor > 4 to spare; rays beyond the guard,
+ * and rays with a zero, subnormal or non-finite direction component (where a slab distance may be NaN and the
+ * implication child => parent fails), are answered by the exact two-child traversal instead (wf_exact_query).
+ * The cell of a ray is computed with one rounding-level error in the ratios; the one-cell padding absorbs it.
+ * tools/proto_bins.py checks the property on every ray of a frame on the CPU; the GPU parity tests check the results.
+ *
+ * Leaves whose inflated box contains the anchor have no bounded set of cells; a scene that has one keeps the tree
+ * search for that anchor's rays (the builder reports it).
+ */
+#pragma once
+#include "rt_layout.h"
+#include "rt_math.cuh"
+
+namespace rtk {
+
+struct BinsView {       /* by value in kernel arguments */
+    float ax, ay, az;   /* the anchor */
+    float eps;          /* inflation of the leaf boxes */
+    float max_D2;       /* guard for rays that do not start at the anchor: (distance origin -> anchor)^2 must not exceed it */
+    int R;              /* cells per face side; 0 = no bins (tree search) */
+    const int* cell_start; /* 3 R R + 1 */
+    const int* items;      /* leaf-table indices */
+};
+
+/* cell of a direction (from or towards the anchor: the sign cancels in the ratios) */
+__device__ __forceinline__ int bins_cell(const BinsView& b, F3 d) {
+    const float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
+    int k;
+    float dk, da, db;
+    if (ax >= ay && ax >= az) { k = 0; dk = d.x; da = d.y; db = d.z; }
+    else if (ay >= az)        { k = 1; dk = d.y; da = d.z; db = d.x; }
+    else                      { k = 2; dk = d.z; da = d.x; db = d.y; }
+    const float r = rcp_approx(dk);
+    const float h = 0.5f * (float)b.R;
+    const int ca = min(max((int)floorf(__fmaf_rn(da * r, h, h)), 0), b.R - 1);
+    const int cb = min(max((int)floorf(__fmaf_rn(db * r, h, h)), 0), b.R - 1);
+    return (k * b.R + cb) * b.R + ca;
+}
+
+/* The cells a leaf must be listed in: calls f(cell) for each (a cell may be visited twice; harmless).
+ * Returns false when the inflated box contains the anchor (no bounded set of cells). */
+template <typename F>
+__device__ __forceinline__ bool bins_leaf_cells(const float4 q0, const float4 q1, float ax, float ay, float az, float eps, int R, F f) {
+    const float v0[3] = {q0.x - eps - ax, q0.y - eps - ay, q0.z - eps - az};
+    const float v1[3] = {q0.w + eps - ax, q1.x + eps - ay, q1.y + eps - az};
+    if (v0[0] <= 0.f && v1[0] >= 0.f && v0[1] <= 0.f && v1[1] >= 0.f && v0[2] <= 0.f && v1[2] >= 0.f) return false;
+    const float h = 0.5f * (float)R;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const int a = (k + 1) % 3, b = (k + 2) % 3;
+        const float mina = (v0[a] <= 0.f && v1[a] >= 0.f) ? 0.f : fminf(fabsf(v0[a]), fabsf(v1[a]));
+        const float minb = (v0[b] <= 0.f && v1[b] >= 0.f) ? 0.f : fminf(fabsf(v0[b]), fabsf(v1[b]));
+        /* on face k the direction's k component dominates: |v_k| >= |v_a|, |v_b| >= m. (m == 0 with v_k straddling 0 would
+         * be a box around the anchor, excluded above up to the degenerate flat cases, which the tiny bound handles
+         * conservatively: the ratios then cover the whole face.) */
+        const float m = fmaxf(fmaxf(mina, minb), 1e-30f);
+#pragma unroll
+        for (int part = 0; part < 2; part++) {
+            float k0, k1;
+            if (part == 0) { k0 = fmaxf(v0[k], m); k1 = v1[k]; }   /* v_k > 0 side */
+            else           { k0 = v0[k]; k1 = fminf(v1[k], -m); }  /* v_k < 0 side */
+            if (!(k0 <= k1)) continue;
+            float ra0 = 1e30f, ra1 = -1e30f, rb0 = 1e30f, rb1 = -1e30f;
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const float kk = (c & 1) ? k1 : k0;
+                const float qa = ((c & 2) ? v1[a] : v0[a]) / kk, qb = ((c & 2) ? v1[b] : v0[b]) / kk;
+                ra0 = fminf(ra0, qa); ra1 = fmaxf(ra1, qa);
+                rb0 = fminf(rb0, qb); rb1 = fmaxf(rb1, qb);
+            }
+            ra0 = fmaxf(ra0, -1.f); ra1 = fminf(ra1, 1.f);
+            rb0 = fmaxf(rb0, -1.f); rb1 = fminf(rb1, 1.f);
+            if (!(ra0 <= ra1) || !(rb0 <= rb1)) continue;
+            const int ca0 = max((int)floorf(__fmaf_rn(ra0, h, h)) - 1, 0), ca1 = min((int)floorf(__fmaf_rn(ra1, h, h)) + 1, R - 1);
+            const int cb0 = max((int)floorf(__fmaf_rn(rb0, h, h)) - 1, 0), cb1 = min((int)floorf(__fmaf_rn(rb1, h, h)) + 1, R - 1);
+            for (int cb = cb0; cb <= cb1; cb++)
+                for (int ca = ca0; ca <= ca1; ca++) f((k * R + cb) * R + ca);
+        }
+    }
+    return true;
+}
+
+/* pass 1: how many leaves does every cell list? flags[0] |= 1 when a leaf contains the anchor */
+__global__ void bins_count(const float4* __restrict__ leaves, int n_leaves, float ax, float ay, float az, float eps, int R, int* __restrict__ counts, int* __restrict__ flags) {
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= n_leaves) return;
+    const float4 q0 = leaves[2 * (size_t)l], q1 = leaves[2 * (size_t)l + 1];
+    if (!bins_leaf_cells(q0, q1, ax, ay, az, eps, R, [&](int cell) { atomicAdd(counts + cell, 1); })) atomicOr(flags, 1);
+}
+
+/* pass 2 (after the exclusive scan of counts into cell_start): fill the lists; cursor starts as a copy of cell_start */
+__global__ void bins_fill(const float4* __restrict__ leaves, int n_leaves, float ax, float ay, float az, float eps, int R, int* __restrict__ cursor, int* __restrict__ items) {
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= n_leaves) return;
+    const float4 q0 = leaves[2 * (size_t)l], q1 = leaves[2 * (size_t)l + 1];
+    bins_leaf_cells(q0, q1, ax, ay, az, eps, R, [&](int cell) { items[atomicAdd(cursor + cell, 1)] = l; });
+}
+
+} // namespace rtk

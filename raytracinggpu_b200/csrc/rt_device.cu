@@ -10,6 +10,7 @@
 #include "host_common.h"
 #include "rt_kernels.cuh"
 #include "rt_layout.h"
+#include <cub/cub.cuh>
 #include "rt_wavefront.cuh"
 #include "rt_stochastic.cuh"
 
@@ -22,6 +23,7 @@
 #include <vector>
 
 #define RT_NCOUNTERS 8
+#define RT_RENDER_RETRY_ 0x40000000u /* internal: this call is itself a repeat */
 #define RT_MAX_STRIPS 8
 #define CUDA_TRY(expr)                                                                                         \
     do {                                                                                                       \
@@ -75,6 +77,29 @@ struct rt_scene {
     unsigned char* st_buf = nullptr; /* stochastic wavefront: per-pixel stream state, colour sum, diffuse records */
     size_t st_buf_bytes = 0;
     int* wf_spill = nullptr;  /* node-pool overflow area of wf_traverse */
+    bool trav_wide = false;
+    uint64_t mesh_generation = 0; /* bumped whenever the mesh part of the blob changes: invalidates the anchored-ray bins */
+    /* anchored-ray bins (rt_bins.cuh): [0] camera, [1] light */
+    struct AnchorBins {
+        float A[3] = {0.f, 0.f, 0.f};
+        int R = 0;
+        uint64_t mesh_generation = ~0ull;
+        bool built = false, usable = false;
+        float eps = 0.f, max_D2 = 0.f;
+        int* cell_start = nullptr; /* 3 R R + 1 */
+        int* cursor = nullptr;
+        size_t cells_cap = 0;
+        int* items = nullptr;
+        size_t items_cap = 0, n_items = 0;
+    } bins[2];
+    void* scan_tmp = nullptr;
+    size_t scan_tmp_bytes = 0;
+    int* bins_flags = nullptr;
+    int2* wf_tasks = nullptr;
+    size_t wf_tasks_cap = 0;
+    int task_factor = 4;     /* task buffer entries per pixel; doubled after an overflow */
+    bool last_was_anchored = false;
+    int bins_builds = 0;
     size_t wf_spill_ints = 0;
     int* dbg_warps = nullptr; /* RT_DEBUG_WARPS=<file>: per-warp timeline of wf_traverse (count_work renders) */
     size_t dbg_warps_ints = 0;
@@ -140,7 +165,7 @@ int upload_header(rt_scene* s) {
         /* spheres-only scene: the blob is just the header */
         CUDA_TRY(cudaMalloc(&s->blob, RT_HEADER_BYTES));
         s->blob_bytes = RT_HEADER_BYTES;
-        s->header.off_nodes = s->header.off_tris = RT_HEADER_BYTES;
+        s->header.off_nodes = s->header.off_tris = s->header.off_wide = s->header.off_leaves = RT_HEADER_BYTES;
         s->header.total_bytes = RT_HEADER_BYTES;
     }
     CUDA_TRY(cudaMemcpyAsync(s->blob, &s->header, sizeof(SceneHeader), cudaMemcpyHostToDevice, s->stream));
@@ -154,12 +179,100 @@ void reset_mesh_fields(SceneHeader& h) {
     h.n_tris = 0;
     h.max_depth = 0;
     h.root_ref = 0;
+    h.wroot_ref = 0;
+    h.n_wide = 0;
+    h.wide_depth = 0;
     h.n_leaves = 0;
     for (int k = 0; k < 3; k++) {
         h.root_mn[k] = 0.f;
         h.root_mx[k] = 0.f;
         h.box_abs[k] = 0.f;
     }
+}
+
+/* (Re)build the candidate lists of one anchor (rt_bins.cuh) when the anchor, the mesh or the resolution changed.
+ * Three small launches (count, scan, fill) and one 8-byte read-back; a scene with a fixed camera and light builds them
+ * once. usable = false when a leaf box contains the anchor (the caller then keeps the tree search). */
+int ensure_bins(rt_scene* s, int which, const float A[3]) {
+    rt_scene::AnchorBins& b = s->bins[which];
+    const SceneHeader& h = s->header;
+    static const int env_R = getenv("RT_BINS_R") ? atoi(getenv("RT_BINS_R")) : 0;
+    const int R = env_R > 0 ? std::min(std::max(env_R, 8), 4096) : (h.n_leaves > 200000 ? 2048 : 512);
+    if (b.built && b.mesh_generation == s->mesh_generation && b.R == R && b.A[0] == A[0] && b.A[1] == A[1] && b.A[2] == A[2]) return RT_OK;
+    b.built = false;
+    b.usable = false;
+    const size_t n_cells = (size_t)3 * R * R;
+    if (b.cells_cap < n_cells + 1) {
+        CUDA_TRY(cudaStreamSynchronize(s->stream));
+        if (b.cell_start) cudaFree(b.cell_start);
+        if (b.cursor) cudaFree(b.cursor);
+        b.cell_start = b.cursor = nullptr;
+        b.cells_cap = 0;
+        CUDA_TRY(cudaMalloc(&b.cell_start, (n_cells + 1) * sizeof(int)));
+        CUDA_TRY(cudaMalloc(&b.cursor, (n_cells + 1) * sizeof(int)));
+        b.cells_cap = n_cells + 1;
+    }
+    if (!s->bins_flags) CUDA_TRY(cudaMalloc(&s->bins_flags, 2 * sizeof(int)));
+    const float S = std::max(h.box_abs[0], std::max(h.box_abs[1], h.box_abs[2]));
+    const float scale = S + std::max(std::fabs(A[0]), std::max(std::fabs(A[1]), std::fabs(A[2])));
+    b.eps = scale * (1.f / 4096.f);
+    b.max_D2 = (scale * 128.f) * (scale * 128.f);
+    const float4* leaves = reinterpret_cast<const float4*>(s->blob + h.off_leaves);
+    const int threads = 128, blocks = (h.n_leaves + threads - 1) / threads;
+    CUDA_TRY(cudaMemsetAsync(b.cell_start, 0, (n_cells + 1) * sizeof(int), s->stream));
+    CUDA_TRY(cudaMemsetAsync(s->bins_flags, 0, 2 * sizeof(int), s->stream));
+    rtk::bins_count<<<blocks, threads, 0, s->stream>>>(leaves, h.n_leaves, A[0], A[1], A[2], b.eps, R, b.cell_start, s->bins_flags);
+    CUDA_TRY(cudaGetLastError());
+    size_t tmp_bytes = 0;
+    CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, b.cell_start, b.cell_start, (int)(n_cells + 1), s->stream));
+    if (s->scan_tmp_bytes < tmp_bytes) {
+        CUDA_TRY(cudaStreamSynchronize(s->stream));
+        if (s->scan_tmp) cudaFree(s->scan_tmp);
+        s->scan_tmp = nullptr;
+        s->scan_tmp_bytes = 0;
+        CUDA_TRY(cudaMalloc(&s->scan_tmp, tmp_bytes));
+        s->scan_tmp_bytes = tmp_bytes;
+    }
+    CUDA_TRY(cub::DeviceScan::ExclusiveSum(s->scan_tmp, tmp_bytes, b.cell_start, b.cell_start, (int)(n_cells + 1), s->stream));
+    int total = 0, flags = 0;
+    CUDA_TRY(cudaMemcpyAsync(&total, b.cell_start + n_cells, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaMemcpyAsync(&flags, s->bins_flags, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    b.R = R;
+    b.A[0] = A[0];
+    b.A[1] = A[1];
+    b.A[2] = A[2];
+    b.mesh_generation = s->mesh_generation;
+    b.built = true;
+    s->bins_builds++;
+    if (flags != 0 || total < 0) return RT_OK; /* a leaf box around the anchor: not usable */
+    if (b.items_cap < (size_t)total) {
+        if (b.items) cudaFree(b.items);
+        b.items = nullptr;
+        b.items_cap = 0;
+        const size_t cap = (size_t)total + (size_t)total / 4 + 1024;
+        CUDA_TRY(cudaMalloc(&b.items, cap * sizeof(int)));
+        b.items_cap = cap;
+    }
+    b.n_items = (size_t)total;
+    CUDA_TRY(cudaMemcpyAsync(b.cursor, b.cell_start, (n_cells + 1) * sizeof(int), cudaMemcpyDeviceToDevice, s->stream));
+    rtk::bins_fill<<<blocks, threads, 0, s->stream>>>(leaves, h.n_leaves, A[0], A[1], A[2], b.eps, R, b.cursor, b.items);
+    CUDA_TRY(cudaGetLastError());
+    b.usable = true;
+    return RT_OK;
+}
+
+rtk::BinsView bins_view(const rt_scene::AnchorBins& b) {
+    rtk::BinsView v;
+    v.ax = b.A[0];
+    v.ay = b.A[1];
+    v.az = b.A[2];
+    v.eps = b.eps;
+    v.max_D2 = b.max_D2;
+    v.R = b.R;
+    v.cell_start = b.cell_start;
+    v.items = b.items;
+    return v;
 }
 
 } // namespace
@@ -191,7 +304,7 @@ int rt_scene_create(rt_scene** out, int device) {
     if (const char* v = getenv("RT_STRIPS")) s->n_strips = std::max(1, std::min(atoi(v), RT_MAX_STRIPS));
     memset(&s->header, 0, sizeof s->header);
     s->header.magic = RT_BLOB_MAGIC;
-    s->header.layout_version = 1;
+    s->header.layout_version = RT_LAYOUT_VERSION;
     s->header.mesh_id = -1;
     s->header.L[0] = -10.f; /* Scene::L / intensity defaults, optimized.cu:681-683 */
     s->header.L[1] = 20.f;
@@ -230,6 +343,14 @@ void rt_scene_destroy(rt_scene* s) {
     if (s->wf_counters) cudaFree(s->wf_counters);
     if (s->dbg_warps) cudaFree(s->dbg_warps);
     if (s->wf_spill) cudaFree(s->wf_spill);
+    for (int k = 0; k < 2; k++) {
+        if (s->bins[k].cell_start) cudaFree(s->bins[k].cell_start);
+        if (s->bins[k].cursor) cudaFree(s->bins[k].cursor);
+        if (s->bins[k].items) cudaFree(s->bins[k].items);
+    }
+    if (s->scan_tmp) cudaFree(s->scan_tmp);
+    if (s->bins_flags) cudaFree(s->bins_flags);
+    if (s->wf_tasks) cudaFree(s->wf_tasks);
     if (s->rng_states) cudaFree(s->rng_states);
     if (s->st_buf) cudaFree(s->st_buf);
     if (s->h_wf_counters) cudaFreeHost(s->h_wf_counters);
@@ -360,9 +481,18 @@ int rt_scene_set_mesh(rt_scene* s, const float* vertices, int32_t nv, const int3
     std::vector<float> packed((size_t)std::max(n_inner, 1) * 16);
     std::vector<int32_t> leaf_start_of_tri((size_t)nt, 0); /* first triangle of the reference's leaf: the tie-break key */
     int32_t n_leaves = 0, extra_levels = 0;
-    auto new_leaf = [&](int32_t start, int32_t count, int32_t orig_start) -> int32_t {
+    std::vector<float> leaf_table; /* 8 words per packed leaf: box, leaf code, first triangle of the reference leaf */
+    auto new_leaf = [&](int32_t start, int32_t count, int32_t orig_start, const float* bb) -> int32_t {
         n_leaves++;
         for (int32_t i = start; i < start + count; i++) leaf_start_of_tri[i] = orig_start;
+        if (count > 0) {
+            const size_t at = leaf_table.size();
+            leaf_table.resize(at + 8);
+            memcpy(&leaf_table[at], bb, 6 * sizeof(float));
+            const int32_t code = (start << 2) | (count - 1);
+            memcpy(&leaf_table[at + 6], &code, sizeof code);
+            memcpy(&leaf_table[at + 7], &orig_start, sizeof orig_start);
+        }
         /* an empty leaf (only a hand-made arr_bvh can hold one) points past the last triangle: the kernels clamp
          * the range to n_tris, so it tests nothing */
         if (count <= 0) return -1 - ((nt << 2) | 0);
@@ -373,7 +503,7 @@ int rt_scene_set_mesh(rt_scene* s, const float* vertices, int32_t nv, const int3
         [&](int32_t lo, int32_t hi, int32_t ts, int32_t te, const float* bb, int32_t level) -> int32_t {
         if (hi - lo == 1) {
             const int32_t st = ts + lo * RT_LEAF_MAX;
-            return new_leaf(st, std::min(RT_LEAF_MAX, te - st), ts);
+            return new_leaf(st, std::min(RT_LEAF_MAX, te - st), ts, bb);
         }
         extra_levels = std::max(extra_levels, level);
         const int32_t idx = (int32_t)(packed.size() / 16);
@@ -418,10 +548,103 @@ int rt_scene_set_mesh(rt_scene* s, const float* vertices, int32_t nv, const int3
     if (max_depth > RT_STACK_CAP - 2)
         return rtb::fail(RT_ERR_UNSUPPORTED, "rt_scene_set_mesh: packed BVH depth %d exceeds the traversal stack (%d)", max_depth, RT_STACK_CAP - 2);
 
+    /* ---- wide index (rt_layout.h): the two-child records collapsed into nodes of up to RT_WIDE children. A node starts
+     * with the two children of a record and keeps opening the inner child with the largest box until it is full.
+     * Built iteratively, parents before children. */
+    std::vector<float> wide;
+    int32_t n_wide = 0, wide_depth = 0, wroot_ref = 0;
+    if (n_inner > 0 && root_ref >= 0) {
+        struct Pending { int32_t record, wide_index, level; };
+        std::vector<Pending> todo;
+        std::vector<int32_t> wide_cnt;
+        todo.push_back({root_ref, 0, 1});
+        n_wide = 1;
+        wide.resize(32);
+        wide_cnt.push_back(0);
+        auto half_area = [](const float* b) {
+            const float dx = b[3] - b[0], dy = b[4] - b[1], dz = b[5] - b[2];
+            return dx * dy + dy * dz + dz * dx;
+        };
+        while (!todo.empty()) {
+            const Pending cur = todo.back();
+            todo.pop_back();
+            wide_depth = std::max(wide_depth, cur.level);
+            float box[RT_WIDE][6];
+            int32_t ref[RT_WIDE];
+            int cnt = 0;
+            auto add_children = [&](int32_t record) {
+                const float* o = &packed[(size_t)record * 16];
+                int32_t refs[2];
+                memcpy(refs, o + 12, sizeof refs);
+                for (int c = 0; c < 2; c++) {
+                    memcpy(box[cnt], o + 6 * c, 6 * sizeof(float));
+                    ref[cnt++] = refs[c];
+                }
+            };
+            add_children(cur.record);
+            while (cnt < RT_WIDE) {
+                int best = -1;
+                float best_area = -1.f;
+                for (int c = 0; c < cnt; c++)
+                    if (ref[c] >= 0) {
+                        const float ar = half_area(box[c]);
+                        if (best < 0 || ar > best_area) {
+                            best = c;
+                            best_area = ar;
+                        }
+                    }
+                if (best < 0) break;
+                const int32_t open = ref[best];
+                for (int c = best; c + 1 < cnt; c++) { /* close the gap, keep the order */
+                    memcpy(box[c], box[c + 1], sizeof box[c]);
+                    ref[c] = ref[c + 1];
+                }
+                cnt--;
+                add_children(open);
+            }
+            /* inner children become wide nodes of their own */
+            int32_t child_wide[RT_WIDE];
+            for (int c = 0; c < cnt; c++) {
+                child_wide[c] = -1;
+                if (ref[c] >= 0) {
+                    child_wide[c] = n_wide++;
+                    wide.resize((size_t)n_wide * 32);
+                    wide_cnt.push_back(0);
+                    todo.push_back({ref[c], child_wide[c], cur.level + 1});
+                }
+            }
+            wide_cnt[cur.wide_index] = cnt;
+            float* o = &wide[(size_t)cur.wide_index * 32];
+            for (int c = 0; c < RT_WIDE; c++) {
+                const int src = c < cnt ? c : 0; /* unused slots repeat child 0; the child count travels with every reference */
+                memcpy(o + 8 * c, box[src], 6 * sizeof(float));
+                const int32_t r = c < cnt ? (ref[c] >= 0 ? child_wide[c] /* patched below */ : ref[c]) : 0;
+                memcpy(o + 8 * c + 6, &r, sizeof r);
+                const int32_t aux = c < cnt ? 1 : 0;
+                memcpy(o + 8 * c + 7, &aux, sizeof aux);
+            }
+        }
+        /* inner references carry the child's own child count: (wide index << 2) | (count - 1) */
+        for (int32_t k = 0; k < n_wide; k++)
+            for (int c = 0; c < wide_cnt[k]; c++) {
+                int32_t r;
+                memcpy(&r, &wide[(size_t)k * 32 + 8 * c + 6], sizeof r);
+                if (r >= 0) {
+                    r = (r << 2) | (wide_cnt[r] - 1);
+                    memcpy(&wide[(size_t)k * 32 + 8 * c + 6], &r, sizeof r);
+                }
+            }
+        wroot_ref = (0 << 2) | (wide_cnt[0] - 1);
+        if (n_wide >= (1 << 24)) return rtb::fail(RT_ERR_UNSUPPORTED, "rt_scene_set_mesh: %d wide nodes exceed the task word", n_wide);
+    }
+
     /* ---- blob ------------------------------------------------------------------------------------------ */
     const size_t off_nodes = RT_HEADER_BYTES;
     const size_t off_tris = (off_nodes + (size_t)n_inner * RT_NODE_BYTES + 63) & ~(size_t)63;
-    const size_t total = off_tris + (size_t)nt * RT_TRI_BYTES;
+    const size_t off_wide = (off_tris + (size_t)nt * RT_TRI_BYTES + 127) & ~(size_t)127;
+    const size_t off_leaves = off_wide + (size_t)n_wide * RT_WNODE_BYTES;
+    const int32_t n_leafrecs = (int32_t)(leaf_table.size() / 8);
+    const size_t total = off_leaves + (size_t)n_leafrecs * RT_LEAFREC_BYTES;
     CUDA_TRY(cudaStreamSynchronize(s->stream));
     if (s->blob_bytes < total || s->blob_bytes > 2 * total + (1u << 20)) {
         if (s->blob) cudaFree(s->blob);
@@ -440,6 +663,10 @@ int rt_scene_set_mesh(rt_scene* s, const float* vertices, int32_t nv, const int3
     if (err == cudaSuccess) err = cudaMemcpyAsync(d_recs, tri_records, rbytes, cudaMemcpyHostToDevice, s->stream);
     if (err == cudaSuccess && n_inner > 0)
         err = cudaMemcpyAsync(s->blob + off_nodes, packed.data(), (size_t)n_inner * RT_NODE_BYTES, cudaMemcpyHostToDevice, s->stream);
+    if (err == cudaSuccess && n_wide > 0)
+        err = cudaMemcpyAsync(s->blob + off_wide, wide.data(), (size_t)n_wide * RT_WNODE_BYTES, cudaMemcpyHostToDevice, s->stream);
+    if (err == cudaSuccess && n_leafrecs > 0)
+        err = cudaMemcpyAsync(s->blob + off_leaves, leaf_table.data(), (size_t)n_leafrecs * RT_LEAFREC_BYTES, cudaMemcpyHostToDevice, s->stream);
     int32_t* d_leaf_start = nullptr;
     if (err == cudaSuccess) err = cudaMalloc(&d_leaf_start, (size_t)nt * sizeof(int32_t));
     if (err == cudaSuccess) err = cudaMemcpyAsync(d_leaf_start, leaf_start_of_tri.data(), (size_t)nt * sizeof(int32_t), cudaMemcpyHostToDevice, s->stream);
@@ -456,7 +683,7 @@ int rt_scene_set_mesh(rt_scene* s, const float* vertices, int32_t nv, const int3
 
     h.has_mesh = 1;
     h.n_inner = n_inner;
-    h.n_leaves = n_leaves;
+    h.n_leaves = n_leafrecs; /* records of the leaf table (empty hand-made leaves have none) */
     h.n_tris = nt;
     h.max_depth = max_depth;
     h.mesh_id = id;
@@ -473,6 +700,12 @@ int rt_scene_set_mesh(rt_scene* s, const float* vertices, int32_t nv, const int3
     s->max_leaf = max_leaf;
     h.off_nodes = off_nodes;
     h.off_tris = off_tris;
+    h.off_wide = off_wide;
+    h.off_leaves = off_leaves;
+    s->mesh_generation++;
+    h.n_wide = n_wide;
+    h.wide_depth = wide_depth;
+    h.wroot_ref = wroot_ref;
     h.total_bytes = total;
     s->header_dirty = true;
     return RT_OK;
@@ -515,10 +748,12 @@ int rt_scene_blob_import(rt_scene* s, const void* device_ptr, size_t bytes) {
     SceneHeader h;
     CUDA_TRY(cudaStreamSynchronize(s->stream));
     CUDA_TRY(cudaMemcpy(&h, device_ptr, sizeof h, cudaMemcpyDeviceToHost));
-    if (h.magic != RT_BLOB_MAGIC || h.layout_version != 1 || h.total_bytes != bytes)
+    if (h.magic != RT_BLOB_MAGIC || h.layout_version != RT_LAYOUT_VERSION || h.total_bytes != bytes)
         return rtb::fail(RT_ERR_INVALID, "rt_scene_blob_import: not a scene blob (magic %08x, %llu bytes declared, %llu given)", h.magic,
                          (unsigned long long)h.total_bytes, (unsigned long long)bytes);
-    if (h.n_spheres < 0 || h.n_spheres > RT_MAX_SPHERES || h.off_tris + (uint64_t)h.n_tris * RT_TRI_BYTES > bytes)
+    if (h.n_spheres < 0 || h.n_spheres > RT_MAX_SPHERES || h.off_tris + (uint64_t)h.n_tris * RT_TRI_BYTES > bytes ||
+        h.n_wide < 0 || h.off_wide + (uint64_t)h.n_wide * RT_WNODE_BYTES > bytes || h.n_leaves < 0 ||
+        h.off_leaves + (uint64_t)h.n_leaves * RT_LEAFREC_BYTES > bytes)
         return rtb::fail(RT_ERR_INVALID, "rt_scene_blob_import: inconsistent header");
     if ((const unsigned char*)device_ptr != s->blob) {
         if (s->blob_bytes < bytes) {
@@ -586,8 +821,15 @@ int rt_scene_sync(rt_scene* s, rt_stats* stats) {
             fclose(f);
         }
     }
+    const bool task_overflow = s->pending && s->last_was_wavefront && s->last_was_anchored && s->h_counters[6] != 0;
     s->pending = false;
     if (failed) return rtb::fail(RT_ERR_STATE, "rt_render: traversal task pool overflow (BVH deeper than the upload-time bound)");
+    if (task_overflow) {
+        /* more (ray, leaf) tasks than the buffer holds: the frame is incomplete. The next render gets a buffer twice the
+         * size; a synchronous rt_render repeats the frame by itself. */
+        s->task_factor = std::min(s->task_factor * 2, 256);
+        return rtb::fail(RT_ERR_AGAIN, "rt_render: (ray, leaf) task buffer overflow; render the frame again (buffer doubled to %d tasks per pixel)", s->task_factor);
+    }
     return RT_OK;
 }
 
@@ -720,19 +962,45 @@ int rt_render(rt_scene* s, const rt_params* p, uint32_t flags, uint8_t* rgb_out,
             }
         }
         if (variant == 2) {
+            /* the wide index (rt_layout.h) is the production search structure; the instrumented build counts the reference's
+             * own node visits and therefore walks the two-child records, as does RT_WIDE=0 (A/B timing, cross-check) */
+            static const bool env_wide = getenv("RT_WIDE") && atoi(getenv("RT_WIDE")) != 0; /* measured: no faster than the two-child records at 8 blocks per SM (profiles/r01_notes.md); off unless asked for */
+            static const bool env_wide_count = getenv("RT_WIDE_COUNT") != nullptr; /* timeline of the wide kernel: node_visits then counts wide nodes */
+            const bool wide = env_wide && (!count || env_wide_count) && h.n_wide > 0;
+            /* anchored rays (rt_bins.cuh): camera rays and shadow rays find their leaves through per-anchor bins and wf_leaves
+             * tests the triangles; wf_traverse keeps the rays that start anywhere else (bounces). The instrumented build
+             * counts the reference's node visits and therefore searches the tree; RT_ANCHOR=0 does so too (A/B, cross-check). */
+            static const bool env_anchor = !(getenv("RT_ANCHOR") && atoi(getenv("RT_ANCHOR")) == 0);
+            bool anchored = env_anchor && !count && h.has_mesh && h.n_leaves > 0 && segments > 0;
+            if (anchored) {
+                int rc = ensure_bins(s, 0, p->cam);
+                if (rc == RT_OK) rc = ensure_bins(s, 1, h.L);
+                if (rc != RT_OK) return rc;
+                anchored = s->bins[0].usable && s->bins[1].usable;
+            }
+            s->last_was_anchored = anchored;
+            /* round 0 holds tree-searched queries only when a path can go on inside wf_generate: past a mirror or refractive
+             * sphere, or along the indirect bounce of a pixel shaded on the spot */
+            bool trav_round0 = stochastic && p->indirect;
+            for (int k = 0; k < h.n_spheres; k++) trav_round0 = trav_round0 || h.spheres[k].mirror || h.spheres[k].n_in != h.spheres[k].n_out;
+            trav_round0 = trav_round0 && segments >= 2;
             /* node pool of wf_traverse: 32 lanes x (levels of the packed tree + roots of two batches + slack) */
-            int npool_cap = std::min(32 * (h.max_depth + 4), 256);
-            if (const char* v = getenv("RT_NPOOL_CAP")) npool_cap = std::max(64, std::min(atoi(v), 256)) & ~31; /* test hook: a small pool forces the spill path */
+            int npool_cap = wide ? std::min(96 * (h.wide_depth + 2), 352) : std::min(32 * (h.max_depth + 4), 256);
+            if (const char* v = getenv("RT_NPOOL_CAP")) npool_cap = std::max(64, std::min(atoi(v), npool_cap)) & ~31; /* test hook: a small pool forces the spill path */
             const size_t warp_bytes = (sizeof(rtk::WfWarpSmem) + (size_t)npool_cap * sizeof(int) + 15) & ~(size_t)15;
             const size_t trav_smem = warp_bytes * (WF_THREADS / 32);
             if (trav_smem > 200 * 1024) return rtb::fail(RT_ERR_UNSUPPORTED, "rt_render: BVH depth %d needs %zu B of shared memory per block", h.max_depth, trav_smem);
-            if (s->trav_blocks_per_sm == 0 || s->trav_smem != trav_smem) {
+            if (s->trav_blocks_per_sm == 0 || s->trav_smem != trav_smem || s->trav_wide != wide) {
+                s->trav_wide = wide;
                 int nb = 0;
-                CUDA_TRY(cudaFuncSetAttribute(rtk::wf_traverse<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trav_smem));
-                CUDA_TRY(cudaFuncSetAttribute(rtk::wf_traverse<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trav_smem));
-                CUDA_TRY(cudaFuncSetAttribute(rtk::wf_traverse<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trav_smem));
-                CUDA_TRY(cudaFuncSetAttribute(rtk::wf_traverse<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trav_smem));
-                CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rtk::wf_traverse<false, false>, WF_THREADS, trav_smem));
+                CUDA_TRY(cudaFuncSetAttribute(rtk::wf_traverse<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trav_smem));
+                CUDA_TRY(cudaFuncSetAttribute(rtk::wf_traverse<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trav_smem));
+                CUDA_TRY(cudaFuncSetAttribute(rtk::wf_traverse<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trav_smem));
+                CUDA_TRY(cudaFuncSetAttribute(rtk::wf_traverse<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trav_smem));
+                CUDA_TRY(cudaFuncSetAttribute(rtk::wf_traverse<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trav_smem));
+                CUDA_TRY(cudaFuncSetAttribute(rtk::wf_traverse<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trav_smem));
+                CUDA_TRY(cudaFuncSetAttribute(rtk::wf_traverse<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trav_smem));
+                CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wide ? rtk::wf_traverse<false, false, true> : rtk::wf_traverse<false, false, false>, WF_THREADS, trav_smem));
                 cudaDeviceProp prop;
                 CUDA_TRY(cudaGetDeviceProperties(&prop, s->device));
                 s->trav_blocks_per_sm = std::max(nb, 1);
@@ -755,6 +1023,18 @@ int rt_render(rt_scene* s, const rt_params* p, uint32_t flags, uint8_t* rgb_out,
                 CUDA_TRY(cudaMalloc(&s->wf_queue, 3 * npx * sizeof(rtk::QEntry)));
                 s->wf_capacity = npx;
             }
+            const size_t task_slack = 4096;
+            if (anchored) {
+                const size_t need = (size_t)s->task_factor * npx + task_slack * RT_MAX_STRIPS;
+                if (s->wf_tasks_cap < need) {
+                    CUDA_TRY(cudaStreamSynchronize(s->stream));
+                    if (s->wf_tasks) cudaFree(s->wf_tasks);
+                    s->wf_tasks = nullptr;
+                    s->wf_tasks_cap = 0;
+                    CUDA_TRY(cudaMalloc(&s->wf_tasks, need * sizeof(int2)));
+                    s->wf_tasks_cap = need;
+                }
+            }
             static const bool dbg_times = getenv("RT_DEBUG_TIMES") != nullptr;
             const bool dbg_warps = count && getenv("RT_DEBUG_WARPS");
             /* Strips: the frame is cut into bands of rows, each rendered by its own generate / traverse / shade chain
@@ -765,7 +1045,7 @@ int rt_render(rt_scene* s, const rt_params* p, uint32_t flags, uint8_t* rgb_out,
             if (rows < 64 * n_strips) n_strips = std::max(1, rows / 64);
             if (dbg_times || dbg_warps) n_strips = 1;
             const unsigned pers_grid = (unsigned)(s->sm_count * s->trav_blocks_per_sm);
-            const int spill_cap = WF_SLOTS * (h.max_depth + 2); /* per traversal warp: every ray slot holding a full path of pending siblings */
+            const int spill_cap = WF_SLOTS * std::max(h.max_depth + 2, (RT_WIDE - 1) * h.wide_depth + 2); /* per traversal warp: every ray slot holding a full path of pending siblings */
             {
                 const size_t ints = (size_t)spill_cap * pers_grid * (WF_THREADS / 32) * n_strips;
                 if (s->wf_spill_ints < ints) {
@@ -844,6 +1124,13 @@ int rt_render(rt_scene* s, const rt_params* p, uint32_t flags, uint8_t* rgb_out,
                     g.gss_factor = env_gss;
                 }
                 g.dbg_warps = dbg_ptr;
+                g.anchored = anchored ? 1 : 0;
+                g.bins[0] = bins_view(s->bins[0]);
+                g.bins[1] = bins_view(s->bins[1]);
+                g.tasks = anchored ? s->wf_tasks + (size_t)s->task_factor * px0 + task_slack * st : nullptr;
+                g.qcap = (int)spx;
+                g.task_cap = anchored ? (int)std::min<size_t>((size_t)s->task_factor * spx + task_slack, (size_t)0x7fffffff) : 0;
+                const unsigned leaves_grid = (unsigned)(s->sm_count * 16);
                 const unsigned wtiles = (unsigned)((p->W + 7) / 8) * (unsigned)((srows + 3) / 4);
                 const unsigned gen_grid = (wtiles + (WF_THREADS / 32) - 1) / (WF_THREADS / 32);
                 const unsigned shade_grid = (unsigned)std::min<size_t>((spx + WF_THREADS - 1) / WF_THREADS, (size_t)s->sm_count * 16);
@@ -879,12 +1166,31 @@ int rt_render(rt_scene* s, const rt_params* p, uint32_t flags, uint8_t* rgb_out,
                     /* without a mesh no query is ever posted: wf_generate runs every path to its end */
                     for (int r = 0; r <= segments && segments > 0 && h.has_mesh; r++) {
                         g.round = r;
-                        if (stochastic) {
-                            if (count) rtk::wf_traverse<true, true><<<pers_grid, WF_THREADS, trav_smem, stream>>>(s->header, s->blob, g, npool_cap);
-                            else rtk::wf_traverse<false, true><<<pers_grid, WF_THREADS, trav_smem, stream>>>(s->header, s->blob, g, npool_cap);
+                        if (anchored) {
+                            /* closest-hit queries of a round >= 1 start somewhere in the scene: tree search; every shadow
+                             * query and the camera rays of round 0 are (ray, leaf) tasks */
+                            if (r < segments && (r >= 1 || trav_round0)) {
+                                if (stochastic) {
+                                    if (wide) rtk::wf_traverse<false, true, true><<<pers_grid, WF_THREADS, trav_smem, stream>>>(s->header, s->blob, g, npool_cap);
+                                    else rtk::wf_traverse<false, true, false><<<pers_grid, WF_THREADS, trav_smem, stream>>>(s->header, s->blob, g, npool_cap);
+                                } else {
+                                    if (wide) rtk::wf_traverse<false, false, true><<<pers_grid, WF_THREADS, trav_smem, stream>>>(s->header, s->blob, g, npool_cap);
+                                    else rtk::wf_traverse<false, false, false><<<pers_grid, WF_THREADS, trav_smem, stream>>>(s->header, s->blob, g, npool_cap);
+                                }
+                                launches++;
+                                mark();
+                            }
+                            if (stochastic) rtk::wf_leaves<true><<<leaves_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
+                            else rtk::wf_leaves<false><<<leaves_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
+                        } else if (stochastic) {
+                            if (count) rtk::wf_traverse<true, true, false><<<pers_grid, WF_THREADS, trav_smem, stream>>>(s->header, s->blob, g, npool_cap);
+                            else if (wide) rtk::wf_traverse<false, true, true><<<pers_grid, WF_THREADS, trav_smem, stream>>>(s->header, s->blob, g, npool_cap);
+                            else rtk::wf_traverse<false, true, false><<<pers_grid, WF_THREADS, trav_smem, stream>>>(s->header, s->blob, g, npool_cap);
                         } else {
-                            if (count) rtk::wf_traverse<true, false><<<pers_grid, WF_THREADS, trav_smem, stream>>>(s->header, s->blob, g, npool_cap);
-                            else rtk::wf_traverse<false, false><<<pers_grid, WF_THREADS, trav_smem, stream>>>(s->header, s->blob, g, npool_cap);
+                            if (count && wide) rtk::wf_traverse<true, false, true><<<pers_grid, WF_THREADS, trav_smem, stream>>>(s->header, s->blob, g, npool_cap);
+                            else if (count) rtk::wf_traverse<true, false, false><<<pers_grid, WF_THREADS, trav_smem, stream>>>(s->header, s->blob, g, npool_cap);
+                            else if (wide) rtk::wf_traverse<false, false, true><<<pers_grid, WF_THREADS, trav_smem, stream>>>(s->header, s->blob, g, npool_cap);
+                            else rtk::wf_traverse<false, false, false><<<pers_grid, WF_THREADS, trav_smem, stream>>>(s->header, s->blob, g, npool_cap);
                         }
                         launches++;
                         mark();
@@ -956,7 +1262,14 @@ int rt_render(rt_scene* s, const rt_params* p, uint32_t flags, uint8_t* rgb_out,
         if (stats) memset(stats, 0, sizeof *stats);
         return RT_OK;
     }
-    return rt_scene_sync(s, stats);
+    const int rc = rt_scene_sync(s, stats);
+    if (rc == RT_ERR_AGAIN && !(flags & RT_RENDER_RETRY_)) { /* task buffer overflow: repeat with the doubled buffer (a few times at most) */
+        for (int attempt = 0; attempt < 6; attempt++) {
+            const int rc2 = rt_render(s, p, flags | RT_RENDER_RETRY_, rgb_out, hit_obj, hit_tri, hit_t, shadow, stats);
+            if (rc2 != RT_ERR_AGAIN) return rc2;
+        }
+    }
+    return rc;
 }
 
 /* Device self-test used by tests/: agreement of the reciprocal-based division with div.rn.f32.

@@ -70,9 +70,10 @@ __device__ __forceinline__ bool sphere_t(const DevSphere& s, F3 O, F3 u, float& 
 
 /* moller_trumbore on the packed record (A, e1, e2, N precomputed exactly). Returns true with t when the
  * reference's function returns 1. */
+template <bool V8 = true>
 __device__ __forceinline__ bool tri_exact(const float4* __restrict__ rec, F3 O, F3 u, float& t) {
     float4 q0, q1;
-    ldg256(rec, q0, q1);
+    ld32B<V8>(rec, q0, q1);
     const float4 q2 = __ldg(rec + 2);
     const F3 A = f3(q0.x, q0.y, q0.z), e1 = f3(q0.w, q1.x, q1.y), e2 = f3(q1.z, q1.w, q2.x), N = f3(q2.y, q2.z, q2.w);
     const float d = dot(u, N);
@@ -173,8 +174,8 @@ __device__ __forceinline__ bool blocks_light(F3 Padj, F3 su, float t, float D2) 
  * f(t) = |fl(fl(P' + fl(t u)) - P')|^2 is non-decreasing in t (every rounding is monotone), so if any accepted
  * hit has f(t) <= D2 the closest accepted hit, which the reference uses, has too; and if none has, neither has
  * the closest. Children are visited nearest-first in ANY mode so blockers are found early. */
-template <bool COUNT, bool FAST, bool ANY>
-__device__ __forceinline__ void mesh_query(const SceneHeader& h, const float4* __restrict__ nodes,
+template <bool COUNT, bool FAST, bool ANY, typename Header, bool V8 = true>
+__device__ __forceinline__ void mesh_query(const Header& h, const float4* __restrict__ nodes,
                                            const float4* __restrict__ tris, F3 O, F3 u, float eps_tri, int push_order, float D2, float t_limit, float& t_best, int& tri_best, Work& w) {
     t_best = ANY ? t_limit : RTK_INF;
     tri_best = -1;
@@ -194,8 +195,8 @@ __device__ __forceinline__ void mesh_query(const SceneHeader& h, const float4* _
         if (cur >= 0) {
             const float4* n = nodes + 4 * (size_t)cur;
             float4 q0, q1, q2, q3f;
-            ldg256(n, q0, q1);
-            ldg256(n + 2, q2, q3f);
+            ld32B<V8>(n, q0, q1);
+            ld32B<V8>(n + 2, q2, q3f);
             const int4 q3 = make_int4(__float_as_int(q3f.x), __float_as_int(q3f.y), __float_as_int(q3f.z), __float_as_int(q3f.w));
             if (COUNT && q3.z == 0) w.nodes++; /* virtual nodes are not nodes of the reference BVH */
             bool okL, okR;
@@ -233,7 +234,7 @@ __device__ __forceinline__ void mesh_query(const SceneHeader& h, const float4* _
                 if (FAST) {
                     if (!tri_fast(tris + 4 * (size_t)i, O, u, t_best, t, w.tri_exact)) continue;
                 } else {
-                    if (!tri_exact(tris + 4 * (size_t)i, O, u, t)) continue;
+                    if (!tri_exact<V8>(tris + 4 * (size_t)i, O, u, t)) continue;
                 }
                 if (!(t > eps_tri)) continue; /* optimized.cu:275 / cpu_launcher.cpp:301 */
                 if (ANY) {

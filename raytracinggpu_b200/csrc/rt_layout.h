@@ -9,6 +9,11 @@
  *   [ triangles   : n_tris   x 64 B ]   A, e1 = B-A, e2 = C-A, N = e1 x e2 (12 floats) + N/|N| (3 floats) + first
  *                                       triangle of the reference's leaf (tie-break key): one 64-B-aligned record,
  *                                       a 256-bit + a 128-bit load per test (LDG.E.256 on sm_100a)
+ *   [ leaf table  : n_leaves x 32 B ]   box of the reference leaf (6 floats), leaf code (first triangle << 2 | count - 1),
+ *                                       first triangle of the reference leaf: what the anchored-ray bins list
+ *                                       (rt_bins.cuh); a reference leaf larger than RT_LEAF_MAX appears once per chunk
+ *   [ wide nodes  : n_wide   x 128 B ]  the search index of wf_traverse: up to four (box, reference) children of 32 B
+ *                                       each, one LDG.E.256 per child (see "Wide index" below)
  *
  * A child reference is one int: >= 0 inner-node index; < 0 a leaf, -1 - ref = (first triangle << 2) | (count - 1)
  * (triangle indices stay below 2^24 because the reference stores them in floats). Leaves hold at most RT_LEAF_MAX
@@ -16,6 +21,17 @@
  * tree of "virtual" inner nodes whose child boxes all equal the leaf's own box. The box test of a virtual node
  * repeats the computation that already succeeded for its parent, so exactly the reference's triangles are still
  * tested, while every traversal task stays small and uniform.
+ *
+ * Wide index. A child box of the reference BVH lies inside its parent's box (compute_bbox takes the min/max over a
+ * sub-range of the parent's triangles, optimized.cu:466-474), and every operation of BoundingBox::intersect
+ * (optimized.cu:173-184: subtract, divide, swap, min/max, compare) is monotone under IEEE rounding, so "the child's box
+ * passes the slab test" implies "the parent's box passes it". The reference's traversal therefore tests exactly the
+ * triangles of the leaves whose OWN box passes the slab test (and whose ray does not divide 0 by 0, which needs a zero
+ * direction component: those rays take the binary records). Which inner boxes are consulted on the way is free. The
+ * wide nodes are the two-child records collapsed two-to-three levels at a time (always opening the child with the
+ * largest box): a third of the node visits and less than half the levels, i.e. less than half the dependent steps
+ * of a single expensive ray. Inner children may be opened conservatively; leaf children are decided exactly.
+ * A wide reference is (wide node index << 2) | (children - 1).
  *
  * versus the reference interchange format (what rt_scene_set_mesh receives and optimized.cu:814-826 uploads):
  * 40-B nodes read as 10 scalar loads with every child node read twice (optimized.cu:223-238, 255-261), and
@@ -35,7 +51,11 @@
 #define RT_LEAF_MAX 4
 #define RT_TRI_BYTES 64
 #define RT_STACK_CAP 64 /* traversal stack entries; rt_scene_set_mesh rejects deeper trees */
-#define RT_BLOB_MAGIC 0x52544232u /* "RTB2" */
+#define RT_WIDE 4
+#define RT_WNODE_BYTES 128
+#define RT_BLOB_MAGIC 0x52544233u /* "RTB3" */
+#define RT_LEAFREC_BYTES 32
+#define RT_LAYOUT_VERSION 3
 
 struct DevSphere {
     float cx, cy, cz, R;
@@ -62,10 +82,14 @@ struct SceneHeader {
     float root_mn[3], root_mx[3];
     float box_abs[3]; /* largest |coordinate| over all node boxes, per axis (bound used by the certified slab test) */
     int32_t root_ref;
-    int32_t pad0;
+    int32_t wroot_ref; /* wide reference of the root's wide node (meaningful when root_ref >= 0) */
     float L[3];
     float intensity;
     uint64_t off_nodes, off_tris, total_bytes; /* byte offsets inside the blob */
+    uint64_t off_wide;
+    uint64_t off_leaves;
+    int32_t n_wide;
+    int32_t wide_depth; /* levels of the wide index */
     DevSphere spheres[RT_MAX_SPHERES];                    /* ascending id */
 };
 

@@ -27,6 +27,7 @@
  */
 #pragma once
 #include "rt_kernels.cuh"
+#include "rt_bins.cuh"
 
 namespace rtk {
 
@@ -47,11 +48,14 @@ struct __align__(16) QEntry {
 static_assert(sizeof(QEntry) == 48, "QEntry is three float4");
 
 struct WfCounters {
-    unsigned long long stats[8]; /* rays, node visits, triangle tests, max stack, slab fallbacks, exact triangle evals, -, pool overflow */
+    unsigned long long stats[8]; /* rays, node visits, triangle tests, max stack, slab fallbacks, exact triangle evals, task buffer overflow, pool overflow */
     unsigned long long dbg[8];   /* COUNT only: N steps, N tasks, T steps, T tasks, admissions, idle iterations */
     int nA[WF_MAX_ROUNDS + 2];   /* closest-hit queries posted for round r */
     int nS[WF_MAX_ROUNDS + 2];   /* shadow queries posted for round r */
     int head[WF_MAX_ROUNDS + 2]; /* traversal fetch cursor of round r */
+    int nTask[WF_MAX_ROUNDS + 2]; /* (ray, leaf) tasks posted for round r (anchored rays) */
+    int nB[WF_MAX_ROUNDS + 2];    /* anchored closest-hit queries of round r: they fill the closest-hit queue from its END downwards,
+                                   * so that wf_traverse (entries 0 .. nA) never sees them; wf_shade handles both ranges */
 };
 
 struct WfArgs {
@@ -76,6 +80,14 @@ struct WfArgs {
     int* spill;     /* node-pool overflow area: spill_cap ints per traversal warp (global memory) */
     int spill_cap;
     int* dbg_warps; /* investigation aid (RT_DEBUG_WARPS, COUNT kernels only): 16 ints per traversal warp and round */
+    /* anchored rays (rt_bins.cuh): camera rays look their candidate leaves up in bins[0], shadow rays in bins[1]; the
+     * boxes that pass the slab test become (ray, leaf) tasks for wf_leaves. anchored == 0: everything goes through
+     * wf_traverse. */
+    int anchored;
+    BinsView bins[2];
+    int2* tasks;  /* x: queue entry | 0x80000000 for a shadow query, y: leaf code */
+    int task_cap;
+    int qcap;     /* entries of each queue of this strip */
 };
 
 __device__ __forceinline__ unsigned tie_rank(int i, int leaf_start, int n_tris, int push_order, int off_bits) {
@@ -97,6 +109,7 @@ struct Post {
     float aux, n_ray;
     int packed;
     /* stochastic mode: a diffuse hit posts its shadow query AND the path goes on, so one call may need a second slot */
+    int cand_start, cand_count; /* anchored query: its candidate leaves are items[cand_start .. + cand_count) of the anchor's bins */
     int kind2; /* 0 or WF_MODE_CLOSEST: the next segment, root box NOT tested yet (pixel sign bit set in the entry) */
     F3 O2, u2;
     float aux2;
@@ -160,13 +173,66 @@ __device__ __forceinline__ void closest_sphere(const SceneHeader& h, F3 O, F3 u,
     }
 }
 
+/* The exact tree search of one ray by one lane (mesh_query: the reference's own slab and triangle arithmetic over the
+ * two-child records, in the reference's visiting order): the way out for the rare rays the faster structures do not
+ * cover. Returns the winning triangle (-1: none) and its t; ANY: a triangle that blocks the light. */
+struct MeshRoot { /* the header fields mesh_query reads, by value: a kernel parameter cannot be handed to a real call by reference */
+    float root_mn[3], root_mx[3], box_abs[3];
+    int root_ref, n_tris;
+};
+__device__ __forceinline__ MeshRoot mesh_root(const SceneHeader& h) {
+    MeshRoot r;
+    for (int k = 0; k < 3; k++) {
+        r.root_mn[k] = h.root_mn[k];
+        r.root_mx[k] = h.root_mx[k];
+        r.box_abs[k] = h.box_abs[k];
+    }
+    r.root_ref = h.root_ref;
+    r.n_tris = h.n_tris;
+    return r;
+}
+__device__ __noinline__ int2 exact_mesh_query_(const MeshRoot h, const float4* __restrict__ nodes, const float4* __restrict__ tris, float ox, float oy, float oz,
+                                               float ux, float uy, float uz, float eps_tri, int push_order, float D2, int any) {
+    const F3 O = f3(ox, oy, oz), u = f3(ux, uy, uz);
+    Work w;
+    w.rays = w.nodes = w.tris = w.max_stack = w.slab_fallbacks = w.tri_exact = 0;
+    int tri;
+    float tm;
+    if (any) mesh_query<false, false, true, MeshRoot, false>(h, nodes, tris, O, u, eps_tri, push_order, D2, sqrtf(D2) * 1.001f + 1e-3f, tm, tri, w);
+    else mesh_query<false, false, false, MeshRoot, false>(h, nodes, tris, O, u, eps_tri, push_order, 0.f, 0.f, tm, tri, w);
+    return make_int2(tri, __float_as_int(tm));
+}
+__device__ __forceinline__ int exact_mesh_query(const MeshRoot h, const float4* __restrict__ nodes, const float4* __restrict__ tris, F3 O, F3 u, float eps_tri,
+                                                int push_order, float D2, bool any, float& tm) {
+    const int2 r = exact_mesh_query_(h, nodes, tris, O.x, O.y, O.z, u.x, u.y, u.z, eps_tri, push_order, D2, any ? 1 : 0);
+    tm = __int_as_float(r.y);
+    return r.x;
+}
+
+/* a shadow query found a blocker: the pixel is black (optimized.cu:620-622) */
+template <bool STOCH>
+__device__ __forceinline__ void light_is_blocked(const RenderArgs& a, const WfArgs& g, int px, int packed) {
+    if (!STOCH) {
+        if (a.rgb) {
+            a.rgb[(size_t)px * 3 + 0] = 0;
+            a.rgb[(size_t)px * 3 + 1] = 0;
+            a.rgb[(size_t)px * 3 + 2] = 0;
+        }
+        if (a.shadow) a.shadow[px] = 1;
+    } else { /* stochastic mode: the direct term of that segment's record becomes 0 (direct_colors[ray_depth], :622) */
+        const int seg = ((packed >> 8) & 0xffff) - 1;
+        g.rec[((size_t)seg * g.npx + px) * 2] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (seg == 0 && g.sample == 0 && a.shadow) a.shadow[px] = 1;
+    }
+}
+
 /* Advance one pixel's path until it ends or needs the mesh. have_hit: (t_hit, sidx, tri) already hold the
  * answer of intersect_all for the current ray (wf_shade); otherwise the segment starts here.
  * STOCH (stochastic mode, one pass per sample): nothing is written to the framebuffer here; every diffuse hit leaves a
  * (direct, albedo) record for wf_fold, draws the two uniforms of optimized.cu:633-634 from the pixel's stream and, with
  * the indirect bounce enabled, goes on along the cosine-weighted direction. */
 template <bool COUNT, bool STOCH>
-__device__ __forceinline__ void path_advance(const SceneHeader& h, const WfArgs& g, const float4* __restrict__ tris, int px, F3 O, F3 u, float n_ray,
+__device__ __forceinline__ void path_advance(const SceneHeader& h, const WfArgs& g, const float4* __restrict__ nodes, const float4* __restrict__ tris, int px, F3 O, F3 u, float n_ray,
                                              int depth, bool have_hit, float t_hit, int sidx, int tri, Work& w, Post& post) {
     const RenderArgs& a = g.a;
     const F3 Lp = f3(h.L[0], h.L[1], h.L[2]);
@@ -181,7 +247,32 @@ __device__ __forceinline__ void path_advance(const SceneHeader& h, const WfArgs&
             w.rays++;
             closest_sphere(h, O, u, t_hit, sidx);
             tri = -1;
-            if (h.has_mesh) {
+            if (h.has_mesh && g.anchored && depth == 0) {
+                /* a camera ray: its candidate leaves come from the camera's bins (rt_bins.cuh) */
+                const float mchk = (__frcp_rn(u.x) - __frcp_rn(u.x)) + (__frcp_rn(u.y) - __frcp_rn(u.y)) + (__frcp_rn(u.z) - __frcp_rn(u.z));
+                /* a zero / subnormal / non-finite component is outside the bins' contract: the query is posted without
+                 * candidates (cand_count -1) and answered by the exact tree search at the end of the kernel (answer_exact) */
+                const bool exact = mchk != mchk;
+                int c0 = 0, c1 = -1;
+                if (!exact) {
+                    const int cell = bins_cell(g.bins[0], u);
+                    c0 = __ldg(g.bins[0].cell_start + cell);
+                    c1 = __ldg(g.bins[0].cell_start + cell + 1);
+                }
+                {
+                    if (c1 != c0) {
+                        post.kind = WF_MODE_CLOSEST;
+                        post.O = O;
+                        post.u = u;
+                        post.aux = t_hit;
+                        post.n_ray = n_ray;
+                        post.packed = (sidx & 0xff) | (depth << 8) | (WF_MODE_CLOSEST << 24);
+                        post.cand_start = c0;
+                        post.cand_count = c1 - c0;
+                        return;
+                    }
+                }
+            } else if (h.has_mesh) {
                 const RayCtx ctx = make_ray_ctx(O, u, h.box_abs[0], h.box_abs[1], h.box_abs[2]);
                 float tn;
                 if (slab_fast(h.root_mn[0], h.root_mn[1], h.root_mn[2], h.root_mx[0], h.root_mx[1], h.root_mx[2], ctx, tn, w.slab_fallbacks)) {
@@ -285,7 +376,29 @@ __device__ __forceinline__ void path_advance(const SceneHeader& h, const WfArgs&
                 *types |= 1 << seg;
                 if (seg == 0 && first_sample && a.shadow) a.shadow[px] = blocked ? 1 : 0;
             }
-            if (!blocked && h.has_mesh) {
+            if (!blocked && h.has_mesh && g.anchored) {
+                /* a shadow ray: its candidate leaves come from the light's bins */
+                const float mchk = (__frcp_rn(su.x) - __frcp_rn(su.x)) + (__frcp_rn(su.y) - __frcp_rn(su.y)) + (__frcp_rn(su.z) - __frcp_rn(su.z));
+                const bool exact = mchk != mchk || !(D2 <= g.bins[1].max_D2); /* outside the bins' contract: see the camera rays above */
+                int c0 = 0, c1 = -1;
+                if (!exact) {
+                    const int cell = bins_cell(g.bins[1], toL);
+                    c0 = __ldg(g.bins[1].cell_start + cell);
+                    c1 = __ldg(g.bins[1].cell_start + cell + 1);
+                }
+                {
+                    if (c1 != c0) {
+                        post.kind = WF_MODE_ANY;
+                        post.O = Padj;
+                        post.u = su;
+                        post.aux = D2;
+                        post.n_ray = 1.f;
+                        post.packed = 0xff | (depth << 8) | (WF_MODE_ANY << 24);
+                        post.cand_start = c0;
+                        post.cand_count = c1 - c0;
+                    }
+                }
+            } else if (!blocked && h.has_mesh) {
                 const RayCtx ctx = make_ray_ctx(Padj, su, h.box_abs[0], h.box_abs[1], h.box_abs[2]);
                 float tn;
                 if (slab_fast(h.root_mn[0], h.root_mn[1], h.root_mn[2], h.root_mx[0], h.root_mx[1], h.root_mx[2], ctx, tn, w.slab_fallbacks)) {
@@ -332,11 +445,23 @@ __device__ __forceinline__ void path_advance(const SceneHeader& h, const WfArgs&
 
 /* Append the warp's queries to the global queues of round post_round: one atomic per warp and queue. Must be
  * called by all 32 lanes together (the offsets come from full-mask ballots). */
-__device__ __forceinline__ void post_queries(const WfArgs& g, int post_round, const Post& post, int px) {
+__device__ __forceinline__ int post_queries(const WfArgs& g, int post_round, const Post& post, int px) {
+    int my_slot = -1; /* queue entry of this lane's first query (closest or shadow), for the anchored tasks */
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
-    const bool wantA = post.kind == WF_MODE_CLOSEST, wantS = post.kind == WF_MODE_ANY, want2 = post.kind2 == WF_MODE_CLOSEST;
+    const bool wantB = post.kind == WF_MODE_CLOSEST && post.cand_count != 0; /* anchored closest-hit query (camera ray); -1: to be answered exactly */
+    const bool wantA = post.kind == WF_MODE_CLOSEST && !wantB, wantS = post.kind == WF_MODE_ANY, want2 = post.kind2 == WF_MODE_CLOSEST;
+    const unsigned mB = __ballot_sync(FULL, wantB);
+    if (mB) {
+        int baseB = 0;
+        if (lane == 0) baseB = atomicAdd(&g.c->nB[post_round], __popc(mB));
+        baseB = __shfl_sync(FULL, baseB, 0);
+        if (wantB) {
+            my_slot = g.qcap - 1 - (baseB + __popc(mB & lt));
+            store_entry(g.qA[post_round & 1], my_slot, post.O, post.u, post.aux, px, post.n_ray, post.packed, WF_NOHIT);
+        }
+    }
     const unsigned mA = __ballot_sync(FULL, wantA);
     const unsigned mS = __ballot_sync(FULL, wantS);
     const unsigned m2 = __ballot_sync(FULL, want2);
@@ -347,12 +472,77 @@ __device__ __forceinline__ void post_queries(const WfArgs& g, int post_round, co
     }
     baseA = __shfl_sync(FULL, baseA, 0);
     baseS = __shfl_sync(FULL, baseS, 0);
-    if (wantA)
-        store_entry(g.qA[post_round & 1], baseA + __popc(mA & lt), post.O, post.u, post.aux, px, post.n_ray, post.packed, WF_NOHIT);
-    else if (wantS)
-        store_entry(g.qS, baseS + __popc(mS & lt), post.O, post.u, post.aux, px, post.n_ray, post.packed, 0ull);
+    if (wantA) {
+        my_slot = baseA + __popc(mA & lt);
+        store_entry(g.qA[post_round & 1], my_slot, post.O, post.u, post.aux, px, post.n_ray, post.packed, WF_NOHIT);
+    } else if (wantS) {
+        my_slot = baseS + __popc(mS & lt);
+        store_entry(g.qS, my_slot, post.O, post.u, post.aux, px, post.n_ray, post.packed, 0ull);
+    }
     if (want2)
         store_entry(g.qA[post_round & 1], baseA + __popc(mA) + __popc(m2 & lt), post.O2, post.u2, post.aux2, (int)((unsigned)px | WF_ROOT_UNTESTED), 1.f, post.packed2, WF_NOHIT);
+    return my_slot;
+}
+
+/* ---- anchored queries: candidate boxes -> (ray, leaf) tasks --------------------------------------------------------
+ * Called by all 32 lanes after post_queries. A lane whose query came from the bins walks its cell's list and applies the
+ * reference's slab test (certified fast path, exact fallback) to every listed leaf box; each box that passes becomes one
+ * task. Tasks are staged per warp in shared memory and appended to the global task array with one atomic per flush. */
+#define WF_STAGE 128
+struct TaskStage {
+    int2* buf;  /* WF_STAGE entries of this warp (shared memory) */
+    int fill;   /* warp-uniform */
+};
+__device__ __forceinline__ void stage_flush(const WfArgs& g, int post_round, TaskStage& st) {
+    if (st.fill == 0) return;
+    const int lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == 0) base = atomicAdd(&g.c->nTask[post_round], st.fill);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base + st.fill <= g.task_cap) {
+        for (int i = lane; i < st.fill; i += 32) g.tasks[base + i] = st.buf[i];
+    } else if (lane == 0) {
+        atomicExch(&g.c->stats[6], 1ull); /* reported by rt_scene_sync: the frame is rendered again through the tree search */
+    }
+    st.fill = 0;
+    __syncwarp();
+}
+__device__ __forceinline__ void emit_tasks(const SceneHeader& h, const unsigned char* __restrict__ blob, const WfArgs& g, int post_round, const Post& post, int slot,
+                                           TaskStage& st) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    const bool mine = slot >= 0 && (post.kind == WF_MODE_CLOSEST || post.kind == WF_MODE_ANY) && post.cand_count > 0;
+    if (!__any_sync(FULL, mine)) return;
+    const float4* leaves = reinterpret_cast<const float4*>(blob + h.off_leaves);
+    const BinsView& b = g.bins[post.kind == WF_MODE_ANY ? 1 : 0];
+    int n = mine ? post.cand_count : 0;
+    const int* items = b.items + (mine ? post.cand_start : 0);
+    RayCtx ctx;
+    if (mine) ctx = make_ray_ctx(post.O, post.u, h.box_abs[0], h.box_abs[1], h.box_abs[2]);
+    const int etag = slot | (post.kind == WF_MODE_ANY ? (int)0x80000000u : 0);
+    unsigned fb = 0;
+    int i = 0;
+    while (__any_sync(FULL, i < n)) {
+        bool hit = false;
+        int code = 0;
+        if (i < n) {
+            const int id = __ldg(items + i);
+            i++;
+            float4 q0, q1;
+            ldg256(leaves + 2 * (size_t)id, q0, q1);
+            float tn;
+            hit = slab_fast(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, ctx, tn, fb);
+            code = __float_as_int(q1.z);
+        }
+        const unsigned m = __ballot_sync(FULL, hit);
+        if (m) {
+            if (hit) st.buf[st.fill + __popc(m & lt)] = make_int2(etag, code);
+            st.fill += __popc(m);
+            __syncwarp();
+            if (st.fill > WF_STAGE - 32) stage_flush(g, post_round, st);
+        }
+    }
 }
 
 __device__ __forceinline__ void flush_work(const Work& w, WfCounters* c, bool count) {
@@ -373,11 +563,41 @@ __device__ __forceinline__ void flush_work(const Work& w, WfCounters* c, bool co
     }
 }
 
+/* The wide index and the bins rest on "a child box that passes the slab test implies its parent box passes" (rt_layout.h),
+ * which holds as long as no slab distance is NaN, i.e. as long as no direction component is zero (0/0). A ray with a
+ * zero, subnormal or non-finite component (RayCtx::M is NaN), or a shadow ray from beyond the bins' distance guard, is
+ * answered here, by one lane, with the reference's own arithmetic over the two-child records (exact_mesh_query). */
+template <bool STOCH>
+__device__ __forceinline__ void answer_exact(const SceneHeader& h, const unsigned char* __restrict__ blob, const WfArgs& g, QEntry* entry, bool any) {
+    const RenderArgs& a = g.a;
+    const float4* nodes = reinterpret_cast<const float4*>(blob + h.off_nodes);
+    const float4* tris = reinterpret_cast<const float4*>(blob + h.off_tris);
+    const float4* p = reinterpret_cast<const float4*>(entry);
+    const float4 p0 = p[0], p1 = p[1];
+    const int px = (int)(__float_as_uint(p1.w) & ~WF_ROOT_UNTESTED);
+    float tm;
+    const int tri = exact_mesh_query(mesh_root(h), nodes, tris, f3(p0.x, p0.y, p0.z), f3(p1.x, p1.y, p1.z), a.eps_tri, a.push_order, p0.w, any, tm);
+    if (any) {
+        if (tri >= 0) light_is_blocked<STOCH>(a, g, px, entry->packed);
+    } else if (tri >= 0) {
+        const unsigned rank = tie_rank(tri, __float_as_int(__ldg(tris + 4 * (size_t)tri + 3).w), h.n_tris, a.push_order, a.rank_off_bits);
+        entry->res = ((unsigned long long)__float_as_uint(tm) << 32) | rank;
+    }
+}
+/* end of wf_generate / wf_shade: the lanes whose anchored query was posted without candidates answer it now */
+template <bool STOCH>
+__device__ __forceinline__ void answer_deferred(const SceneHeader& h, const unsigned char* __restrict__ blob, const WfArgs& g, int post_round, const Post& post, int slot) {
+    const bool need = slot >= 0 && post.cand_count < 0 && (post.kind == WF_MODE_CLOSEST || post.kind == WF_MODE_ANY);
+    if (!__any_sync(0xffffffffu, need)) return;
+    if (need) answer_exact<STOCH>(h, blob, g, (post.kind == WF_MODE_ANY ? g.qS : g.qA[post_round & 1]) + slot, post.kind == WF_MODE_ANY);
+}
+
 /* ---- wf_generate: one thread per pixel (a warp covers an 8x4 tile) ------------------------------------------------ */
 template <bool COUNT, bool STOCH>
 __global__ void __launch_bounds__(WF_THREADS) wf_generate(const __grid_constant__ SceneHeader h, const unsigned char* __restrict__ blob,
                                                          const __grid_constant__ WfArgs g) {
     const RenderArgs& a = g.a;
+    const float4* nodes = reinterpret_cast<const float4*>(blob + h.off_nodes);
     const float4* tris = reinterpret_cast<const float4*>(blob + h.off_tris);
     const int lane = threadIdx.x & 31;
     const int wt = blockIdx.x * (WF_THREADS / 32) + (threadIdx.x >> 5);
@@ -389,6 +609,7 @@ __global__ void __launch_bounds__(WF_THREADS) wf_generate(const __grid_constant_
     Post post;
     post.kind = 0;
     post.kind2 = 0;
+    post.cand_count = 0;
     const int px = kr * a.W + j;
     if (j < a.W && kr < a.rows) {
         const int i = a.row_begin + kr * a.row_step;
@@ -423,9 +644,18 @@ __global__ void __launch_bounds__(WF_THREADS) wf_generate(const __grid_constant_
             if (a.hit_t) a.hit_t[px] = RTK_INF;
             if (a.shadow) a.shadow[px] = 2;
         }
-        path_advance<COUNT, STOCH>(h, g, tris, px, f3(a.camx, a.camy, a.camz), u0, 1.f, 0, false, 0.f, -1, -1, w, post);
+        path_advance<COUNT, STOCH>(h, g, nodes, tris, px, f3(a.camx, a.camy, a.camz), u0, 1.f, 0, false, 0.f, -1, -1, w, post);
     }
-    post_queries(g, 0, post, px);
+    const int slot = post_queries(g, 0, post, px);
+    if (g.anchored) {
+        __shared__ int2 stage_buf[WF_THREADS / 32][WF_STAGE];
+        TaskStage st;
+        st.buf = stage_buf[threadIdx.x >> 5];
+        st.fill = 0;
+        emit_tasks(h, blob, g, 0, post, slot, st);
+        stage_flush(g, 0, st);
+        answer_deferred<STOCH>(h, blob, g, 0, post, slot);
+    }
     flush_work(w, g.c, COUNT);
 }
 
@@ -434,19 +664,26 @@ template <bool COUNT, bool STOCH>
 __global__ void __launch_bounds__(WF_THREADS) wf_shade(const __grid_constant__ SceneHeader h, const unsigned char* __restrict__ blob,
                                                       const __grid_constant__ WfArgs g) {
     const RenderArgs& a = g.a;
+    const float4* nodes = reinterpret_cast<const float4*>(blob + h.off_nodes);
     const float4* tris = reinterpret_cast<const float4*>(blob + h.off_tris);
-    const int n = g.c->nA[g.round];
+    const int nA = g.c->nA[g.round];
+    const int n = nA + g.c->nB[g.round]; /* tree-searched queries from the front of the queue, anchored ones from its end */
     const QEntry* q = g.qA[g.round & 1];
     Work w;
     w.rays = w.nodes = w.tris = w.max_stack = w.slab_fallbacks = w.tri_exact = 0;
     const int n_round = (n + 31) & ~31; /* whole warps stay in the loop so that flush_work sees 32 lanes */
+    __shared__ int2 stage_buf[WF_THREADS / 32][WF_STAGE];
+    TaskStage st;
+    st.buf = stage_buf[threadIdx.x >> 5];
+    st.fill = 0;
     for (int e = blockIdx.x * WF_THREADS + threadIdx.x; e < n_round; e += gridDim.x * WF_THREADS) {
         Post post;
         post.kind = 0;
         post.kind2 = 0;
+        post.cand_count = 0;
         int px = 0;
         if (e < n) {
-            const float4* p = reinterpret_cast<const float4*>(q + e);
+            const float4* p = reinterpret_cast<const float4*>(q + (e < nA ? e : g.qcap - 1 - (e - nA)));
             const float4 p0 = p[0], p1 = p[1], p2 = p[2];
             const F3 O = f3(p0.x, p0.y, p0.z), u = f3(p1.x, p1.y, p1.z);
             float t_hit = p0.w;
@@ -469,11 +706,84 @@ __global__ void __launch_bounds__(WF_THREADS) wf_shade(const __grid_constant__ S
 #ifdef RT_TRACE
             printf("  shade e %d px %d key %llx t_hit %f sidx %d tri %d depth %d\n", e, px, key, t_hit, sidx, tri, depth);
 #endif
-            path_advance<COUNT, STOCH>(h, g, tris, px, O, u, p2.x, depth, true, t_hit, sidx, tri, w, post);
+            path_advance<COUNT, STOCH>(h, g, nodes, tris, px, O, u, p2.x, depth, true, t_hit, sidx, tri, w, post);
         }
-        post_queries(g, g.round + 1, post, px);
+        const int slot = post_queries(g, g.round + 1, post, px);
+        if (g.anchored) {
+            emit_tasks(h, blob, g, g.round + 1, post, slot, st);
+            answer_deferred<STOCH>(h, blob, g, g.round + 1, post, slot);
+        }
     }
+    if (g.anchored) stage_flush(g, g.round + 1, st);
     flush_work(w, g.c, COUNT);
+}
+
+/* ---- wf_leaves: one thread per (ray, leaf) task of round g.round -------------------------------------------------------
+ * The triangle half of the reference's mesh query for anchored rays: the <= RT_LEAF_MAX triangles of the leaf against the
+ * ray of the queue entry, two at a time (both records requested before either is tested). A closest-hit task merges
+ * its accepted hits into the entry with a 64-bit atomicMin on (t bits, tie-break rank) — the reference's strict minimum
+ * with its first-visited rule, order-free; a shadow task that finds a blocker marks the entry and paints
+ * the pixel black. Tasks are uniform and independent: no pools, no tail. */
+template <bool STOCH>
+__global__ void __launch_bounds__(WF_THREADS) wf_leaves(const __grid_constant__ SceneHeader h, const unsigned char* __restrict__ blob,
+                                                       const __grid_constant__ WfArgs g) {
+    const RenderArgs& a = g.a;
+    const float4* tris = reinterpret_cast<const float4*>(blob + h.off_tris);
+    const int n = min(g.c->nTask[g.round], g.task_cap);
+    QEntry* const qA = g.qA[g.round & 1];
+    for (int i = blockIdx.x * WF_THREADS + threadIdx.x; i < n; i += gridDim.x * WF_THREADS) {
+        const int2 task = g.tasks[i];
+        const bool any = task.x < 0;
+        QEntry* const q = (any ? g.qS : qA) + (task.x & 0x7fffffff);
+        const float4* p = reinterpret_cast<const float4*>(q);
+        const float4 p0 = __ldcg(p), p1 = __ldcg(p + 1);
+        const F3 O = f3(p0.x, p0.y, p0.z), u = f3(p1.x, p1.y, p1.z);
+        const unsigned long long cur = __ldcg(&q->res);
+        float t_limit;
+        if (any) {
+            if (cur != 0ull) continue; /* a blocker was already found */
+            t_limit = sqrtf(p0.w) * 1.001f + 1e-3f; /* a hit with t > 1.001 sqrt(D2) cannot satisfy the shadow predicate (|t u| ~ t) */
+        } else {
+            t_limit = cur != WF_NOHIT ? __uint_as_float((unsigned)(cur >> 32)) : RTK_INF;
+        }
+        const int i_begin = task.y >> 2, i_end = min(i_begin + (task.y & 3) + 1, h.n_tris);
+        for (int k = i_begin; k < i_end; k += 2) {
+            const int k2 = min(k + 1, i_end - 1);
+            float4 a0, a1, b0, b1;
+            ldg256(tris + 4 * (size_t)k, a0, a1);
+            ldg256(tris + 4 * (size_t)k2, b0, b1);
+            const float4 a2 = __ldg(tris + 4 * (size_t)k + 2);
+            const float4 b2 = __ldg(tris + 4 * (size_t)k2 + 2);
+            const TriScreen s0 = tri_screen(a0, a1, a2, O, u, t_limit);
+            TriScreen s1 = tri_screen(b0, b1, b2, O, u, t_limit);
+            s1.maybe &= k2 != k;
+            bool stop = false;
+            if (s0.maybe | s1.maybe) {
+#pragma unroll
+                for (int j = 0; j < 2; j++) {
+                    const TriScreen& sj = j ? s1 : s0;
+                    if (!sj.maybe) continue;
+                    const int ij = j ? k2 : k;
+                    float t;
+                    if (!tri_finish(sj, t) || !(t > a.eps_tri)) continue;
+                    if (any) {
+                        if (blocks_light(O, u, t, p0.w)) {
+                            q->res = 1ull;
+                            light_is_blocked<STOCH>(a, g, (int)(__float_as_uint(p1.w) & ~WF_ROOT_UNTESTED), q->packed);
+                            stop = true;
+                            break;
+                        }
+                    } else {
+                        unsigned rank = (unsigned)ij; /* push_order 1: ascending triangle index */
+                        if (a.push_order != 1) rank = tie_rank(ij, __float_as_int(__ldg(tris + 4 * (size_t)ij + 3).w), h.n_tris, 0, a.rank_off_bits);
+                        atomicMin(&q->res, ((unsigned long long)__float_as_uint(t) << 32) | rank);
+                        if (t < t_limit) t_limit = t;
+                    }
+                }
+            }
+            if (stop) break;
+        }
+    }
 }
 
 /* ---- wf_fold (stochastic mode): the end of one sample pass. Folds the pixel's diffuse records back to front,
@@ -541,13 +851,23 @@ struct WfWarpSmem { /* per warp; followed by the node pool (npool_cap ints) */
     int tpool[WF_TPOOL];
 };
 
-template <bool COUNT, bool STOCH>
-__global__ void __launch_bounds__(WF_THREADS, 8) wf_traverse(const __grid_constant__ SceneHeader h, const unsigned char* __restrict__ blob,
+#ifndef RT_WIDE_LOADS
+#define RT_WIDE_LOADS 4 /* child records requested together by a wide N step */
+#endif
+#ifndef RT_WIDE_BLOCKS
+#define RT_WIDE_BLOCKS 8 /* resident blocks per SM the wide instantiations are compiled for */
+#endif
+template <bool COUNT, bool STOCH, bool WIDE>
+__global__ void __launch_bounds__(WF_THREADS, WIDE ? RT_WIDE_BLOCKS : 8) wf_traverse(const __grid_constant__ SceneHeader h, const unsigned char* __restrict__ blob,
                                                          const __grid_constant__ WfArgs g, const int npool_cap) {
     extern __shared__ __align__(16) unsigned char wf_smem[];
     const RenderArgs& a = g.a;
     const float4* nodes = reinterpret_cast<const float4*>(blob + h.off_nodes);
     const float4* tris = reinterpret_cast<const float4*>(blob + h.off_tris);
+    const float4* wnodes = reinterpret_cast<const float4*>(blob + h.off_wide);
+    /* WIDE: an N step may push RT_WIDE children per popped task */
+    constexpr int FAN = WIDE ? RT_WIDE : 2;
+    constexpr int NROOM = 32 * (FAN - 1); /* free node-pool entries a full N step needs */
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -555,7 +875,7 @@ __global__ void __launch_bounds__(WF_THREADS, 8) wf_traverse(const __grid_consta
     WfWarpSmem& sm = *reinterpret_cast<WfWarpSmem*>(wf_smem + warp * warp_bytes);
     int* npool = reinterpret_cast<int*>(wf_smem + warp * warp_bytes + sizeof(WfWarpSmem));
 
-    const int nA = g.c->nA[g.round], nS = g.c->nS[g.round];
+    const int nA = g.c->nA[g.round], nS = g.anchored ? 0 : g.c->nS[g.round]; /* anchored mode: shadow queries are wf_leaves' */
     const int total = nA + nS;
     Work w;
     w.rays = w.nodes = w.tris = w.max_stack = w.slab_fallbacks = w.tri_exact = 0;
@@ -591,7 +911,7 @@ __global__ void __launch_bounds__(WF_THREADS, 8) wf_traverse(const __grid_consta
          * has a comfortable backlog the loop is just the step (all of this is warp-uniform register arithmetic, but it was
          * 17 % of the instructions of a launch when evaluated at every step). */
         if (COUNT) cyc_mark = clock64();
-        if (nN + nT < 48 || npool_cap - nN < 32) {
+        if (nN + nT < 48 || npool_cap - nN < NROOM) {
         /* ---- retire complete batches: results go back to the queue entries ---------------------------------------- */
         QEntry* const qA = g.qA[g.round & 1];
         QEntry* const qS = g.qS;
@@ -605,19 +925,7 @@ __global__ void __launch_bounds__(WF_THREADS, 8) wf_traverse(const __grid_consta
                     if (e < nA) {
                         (qA + e)->res = sm.best[slot];
                     } else if (sm.B[slot].w < 0.f) { /* the light is blocked: the pixel is black (optimized.cu:620-622) */
-                        const int px = __float_as_int(sm.D[slot].w);
-                        if (!STOCH) {
-                            if (a.rgb) {
-                                a.rgb[(size_t)px * 3 + 0] = 0;
-                                a.rgb[(size_t)px * 3 + 1] = 0;
-                                a.rgb[(size_t)px * 3 + 2] = 0;
-                            }
-                            if (a.shadow) a.shadow[px] = 1;
-                        } else { /* stochastic mode: the direct term of that segment's record becomes 0 (direct_colors[ray_depth], :622) */
-                            const int seg = (((qS + (e - nA))->packed >> 8) & 0xffff) - 1;
-                            g.rec[((size_t)seg * g.npx + px) * 2] = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (seg == 0 && g.sample == 0 && a.shadow) a.shadow[px] = 1;
-                        }
+                        light_is_blocked<STOCH>(a, g, __float_as_int(sm.D[slot].w), STOCH ? (qS + (e - nA))->packed : 0);
                     }
                 }
                 __syncwarp();
@@ -653,12 +961,16 @@ __global__ void __launch_bounds__(WF_THREADS, 8) wf_traverse(const __grid_consta
                 bool valid = (lane >> rs) < k && r < 4 * n_quarter && run < n_runs && e < total;
                 float4 p0, p1;
                 RayCtx c;
-                if (STOCH && valid) {
-                    const float4* p = reinterpret_cast<const float4*>(e < nA ? (qA + e) : (qS + (e - nA)));
+                if ((STOCH || WIDE) && valid) {
+                    QEntry* const qe = e < nA ? (qA + e) : (qS + (e - nA));
+                    const float4* p = reinterpret_cast<const float4*>(qe);
                     p0 = __ldcg(p);
                     p1 = __ldcg(p + 1);
                     c = make_ray_ctx(f3(p0.x, p0.y, p0.z), f3(p1.x, p1.y, p1.z), h.box_abs[0], h.box_abs[1], h.box_abs[2]);
-                    if (__float_as_uint(p1.w) & WF_ROOT_UNTESTED) {
+                    if (WIDE && c.M != c.M) { /* a zero direction component: outside the wide index's contract */
+                        answer_exact<STOCH>(h, blob, g, qe, e >= nA);
+                        valid = false;
+                    } else if (STOCH && (__float_as_uint(p1.w) & WF_ROOT_UNTESTED)) {
                         /* a bounce ray queued without its root-box test (path_advance); a ray that misses the root box needs
                          * nothing from the mesh — its entry keeps WF_NOHIT — and takes no slot */
                         float tn;
@@ -670,7 +982,7 @@ __global__ void __launch_bounds__(WF_THREADS, 8) wf_traverse(const __grid_consta
                 const unsigned vmask = __ballot_sync(FULL, valid);
                 const int take = __popc(vmask);
                 if (valid) {
-                    if (!STOCH) {
+                    if (!STOCH && !WIDE) {
                         const float4* p = reinterpret_cast<const float4*>(e < nA ? (qA + e) : (qS + (e - nA)));
                         p0 = __ldcg(p);
                         p1 = __ldcg(p + 1);
@@ -685,7 +997,7 @@ __global__ void __launch_bounds__(WF_THREADS, 8) wf_traverse(const __grid_consta
                     sm.D[slot] = p1;
                     sm.best[slot] = WF_NOHIT;
                     sm.entry[slot] = e;
-                    const int task = (slot << 26) | (h.root_ref >= 0 ? h.root_ref : (-1 - h.root_ref));
+                    const int task = (slot << 26) | (h.root_ref >= 0 ? (WIDE ? h.wroot_ref : h.root_ref) : (-1 - h.root_ref));
                     const int pos = __popc(vmask & lt_mask);
                     if (h.root_ref >= 0) npool[nN + pos] = task;
                     else sm.tpool[nT + pos] = task;
@@ -715,7 +1027,7 @@ __global__ void __launch_bounds__(WF_THREADS, 8) wf_traverse(const __grid_consta
             nSp -= m;
             nN = m;
             __syncwarp();
-        } else if (npool_cap - nN < 32 && nT == 0 && nN > half) {
+        } else if (npool_cap - nN < NROOM && nT == 0 && nN > half) {
             if (nSp + half > g.spill_cap) { /* overflow area exhausted: reported as an error by rt_scene_sync */
                 failed = true;
                 break;
@@ -747,7 +1059,7 @@ __global__ void __launch_bounds__(WF_THREADS, 8) wf_traverse(const __grid_consta
 
         /* an N step pops cnt tasks and may push 2 cnt: it needs cnt free entries */
         const int room = npool_cap - nN;
-        if (nT >= 32 || nN == 0 || (room < 8 && nT > 0)) {
+        if (nT >= 32 || nN == 0 || (room < 8 * (FAN - 1) && nT > 0)) {
             /* ---- T step: one leaf (<= RT_LEAF_MAX triangles) per lane ---------------------------------------------- */
             const int cnt = min(nT, 32);
             if (COUNT) { dbgTs++; dbgTt += cnt; }
@@ -818,14 +1130,102 @@ __global__ void __launch_bounds__(WF_THREADS, 8) wf_traverse(const __grid_consta
             if (COUNT) { __syncwarp(); cycT += clock64() - cyc_mark; }
         } else {
             /* ---- N step: one inner node (two child boxes) per lane ------------------------------------------------- */
-            if (room < 1) { /* node pool full and no leaf work to drain: rt_scene_sync falls back to render_mega */
+            if (room < FAN - 1) { /* node pool full and no leaf work to drain: rt_scene_sync falls back to render_mega */
                 failed = true;
                 break;
             }
-            const int cnt = min(min(nN, 32), room);
+            const int cnt = min(min(nN, 32), room / (FAN - 1));
             if (COUNT) { dbgNs++; dbgNt += cnt; }
             const bool have = lane < cnt;
             int slot = 0;
+            if (WIDE) {
+                /* ---- wide N step: one wide node (<= RT_WIDE child boxes, one LDG.E.256 each) per lane ------------------ */
+                unsigned mN = 0, mT = 0; /* bit k: child k is opened (inner) / queued (leaf) */
+                int ref[RT_WIDE];
+#pragma unroll
+                for (int k = 0; k < RT_WIDE; k++) ref[k] = 0;
+                if (have) {
+                    const int task = npool[nN - 1 - lane];
+                    slot = (unsigned)task >> 26;
+                    const float4 a4 = sm.A[slot], b4 = sm.B[slot];
+                    if (!(b4.w < 0.f)) {
+                        const int payload = task & 0x3ffffff;
+                        const unsigned child_mask = (2u << (payload & 3)) - 1u;
+                        if (COUNT) w.nodes++;
+                        const float4* n = wnodes + 8 * (size_t)(payload >> 2);
+                        RayCtx c;
+                        c.rx = a4.x;
+                        c.ry = a4.y;
+                        c.rz = a4.z;
+                        c.M = a4.w;
+                        c.nox = b4.x;
+                        c.noy = b4.y;
+                        c.noz = b4.z;
+                        unsigned undecided = 0;
+#pragma unroll
+                        for (int k0 = 0; k0 < RT_WIDE; k0 += RT_WIDE_LOADS) {
+                            float4 q[2 * RT_WIDE_LOADS];
+#pragma unroll
+                            for (int k = 0; k < RT_WIDE_LOADS; k++) ldg256(n + 2 * (k0 + k), q[2 * k], q[2 * k + 1]); /* one 128-B line; unused slots repeat child 0 */
+#pragma unroll
+                            for (int k = 0; k < RT_WIDE_LOADS; k++) {
+                                float tn;
+                                const int r = slab_certified(q[2 * k].x, q[2 * k].y, q[2 * k].z, q[2 * k].w, q[2 * k + 1].x, q[2 * k + 1].y, c, tn);
+                                const int rk = __float_as_int(q[2 * k + 1].z);
+                                ref[k0 + k] = rk;
+                                /* undecided by the margin: an inner child is opened (conservative, rt_layout.h); a leaf is
+                                 * decided by the reference's own slab test below */
+                                const unsigned bit = 1u << (k0 + k);
+                                if (rk >= 0) {
+                                    if (r >= 0) mN |= bit;
+                                } else {
+                                    if (r > 0) mT |= bit;
+                                    if (r == 0) undecided |= bit;
+                                }
+                            }
+                        }
+                        mN &= child_mask;
+                        mT &= child_mask;
+                        undecided &= child_mask;
+                        if (undecided) { /* rare */
+                            const float4 c4 = sm.C[slot], d4 = sm.D[slot];
+#pragma unroll 1
+                            for (int k = 0; k < RT_WIDE; k++)
+                                if ((undecided >> k) & 1u) {
+                                    float4 q0, q1;
+                                    ldg256(n + 2 * k, q0, q1);
+                                    if (COUNT) w.slab_fallbacks++;
+                                    if (slab_exact(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, f3(c4.x, c4.y, c4.z), f3(d4.x, d4.y, d4.z))) mT |= 1u << k;
+                                }
+                        }
+                    }
+                }
+                nN -= cnt;
+                const int cN = __popc(mN), cT = __popc(mT);
+                /* inclusive warp scan of the (node, leaf) push counts, packed 16 + 16 bits */
+                int incl = cN | (cT << 16);
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int v = __shfl_up_sync(FULL, incl, d);
+                    if (lane >= d) incl += v;
+                }
+                const int tot = __shfl_sync(FULL, incl, 31);
+                int pN = nN + (incl & 0xffff) - cN, pT = nT + (incl >> 16) - cT;
+                const int tagged = slot << 26;
+#pragma unroll
+                for (int k = 0; k < RT_WIDE; k++) {
+                    if ((mN >> k) & 1u) npool[pN++] = tagged | ref[k];
+                    if ((mT >> k) & 1u) sm.tpool[pT++] = tagged | (-1 - ref[k]);
+                }
+                const unsigned in1 = __ballot_sync(FULL, have && slot >= 32);
+                const int pushedN = tot & 0xffff, pushedT = tot >> 16;
+                nN += pushedN;
+                nT += pushedT;
+                if (COUNT) w.max_stack = max(w.max_stack, (unsigned)nN);
+                const int pushed1 = __reduce_add_sync(FULL, (have && slot >= 32) ? cN + cT : 0);
+                out1 += pushed1 - __popc(in1);
+                out0 += (pushedN + pushedT - pushed1) - (cnt - __popc(in1));
+            } else {
             bool pNL = false, pNR = false, pTL = false, pTR = false;
             int refL = 0, refR = 0;
             if (have) {
@@ -887,6 +1287,7 @@ __global__ void __launch_bounds__(WF_THREADS, 8) wf_traverse(const __grid_consta
             const int pushed = __popc(bNL) + __popc(bNR) + __popc(bTL) + __popc(bTR);
             out1 += pushed1 - __popc(in1);
             out0 += (pushed - pushed1) - (cnt - __popc(in1));
+            }
             if (COUNT) { __syncwarp(); cycN += clock64() - cyc_mark; }
         }
         __syncwarp(); /* pool and slot writes of this step are visible to the next pop */
