@@ -97,7 +97,7 @@ struct rt_scene {
     int* bins_flags = nullptr;
     int2* wf_tasks = nullptr;
     size_t wf_tasks_cap = 0;
-    int task_factor = 4;     /* task buffer entries per pixel; doubled after an overflow */
+    int task_factor = 8;     /* task buffer entries per pixel; doubled after an overflow */
     bool last_was_anchored = false;
     int bins_builds = 0;
     size_t wf_spill_ints = 0;
@@ -197,7 +197,7 @@ int ensure_bins(rt_scene* s, int which, const float A[3]) {
     rt_scene::AnchorBins& b = s->bins[which];
     const SceneHeader& h = s->header;
     static const int env_R = getenv("RT_BINS_R") ? atoi(getenv("RT_BINS_R")) : 0;
-    const int R = env_R > 0 ? std::min(std::max(env_R, 8), 4096) : (h.n_leaves > 200000 ? 2048 : 512);
+    const int R = env_R > 0 ? std::min(std::max(env_R, 8), 4096) : (h.n_leaves > 200000 ? 2048 : 1024);
     if (b.built && b.mesh_generation == s->mesh_generation && b.R == R && b.A[0] == A[0] && b.A[1] == A[1] && b.A[2] == A[2]) return RT_OK;
     b.built = false;
     b.usable = false;

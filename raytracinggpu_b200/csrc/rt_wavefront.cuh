@@ -85,7 +85,7 @@ struct WfArgs {
      * wf_traverse. */
     int anchored;
     BinsView bins[2];
-    int2* tasks;  /* x: queue entry | 0x80000000 for a shadow query, y: leaf code */
+    int2* tasks;  /* x: queue entry | 0x80000000 for a shadow query, y: leaf-table index of the candidate */
     int task_cap;
     int qcap;     /* entries of each queue of this strip */
 };
@@ -484,64 +484,36 @@ __device__ __forceinline__ int post_queries(const WfArgs& g, int post_round, con
     return my_slot;
 }
 
-/* ---- anchored queries: candidate boxes -> (ray, leaf) tasks --------------------------------------------------------
- * Called by all 32 lanes after post_queries. A lane whose query came from the bins walks its cell's list and applies the
- * reference's slab test (certified fast path, exact fallback) to every listed leaf box; each box that passes becomes one
- * task. Tasks are staged per warp in shared memory and appended to the global task array with one atomic per flush. */
-#define WF_STAGE 128
-struct TaskStage {
-    int2* buf;  /* WF_STAGE entries of this warp (shared memory) */
-    int fill;   /* warp-uniform */
-};
-__device__ __forceinline__ void stage_flush(const WfArgs& g, int post_round, TaskStage& st) {
-    if (st.fill == 0) return;
-    const int lane = threadIdx.x & 31;
-    int base = 0;
-    if (lane == 0) base = atomicAdd(&g.c->nTask[post_round], st.fill);
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (base + st.fill <= g.task_cap) {
-        for (int i = lane; i < st.fill; i += 32) g.tasks[base + i] = st.buf[i];
-    } else if (lane == 0) {
-        atomicExch(&g.c->stats[6], 1ull); /* reported by rt_scene_sync: the frame is rendered again through the tree search */
-    }
-    st.fill = 0;
-    __syncwarp();
-}
-__device__ __forceinline__ void emit_tasks(const SceneHeader& h, const unsigned char* __restrict__ blob, const WfArgs& g, int post_round, const Post& post, int slot,
-                                           TaskStage& st) {
+/* ---- anchored queries: one (ray, candidate leaf) task per entry of the ray's cell list ------------------------------------
+ * Called by all 32 lanes after post_queries. Nothing is tested here: the lanes copy their candidate lists into the task
+ * array (one warp scan, one atomic per call; the loads of the copy loop are independent, so a long list costs bandwidth,
+ * not a chain of round trips). wf_leaves applies the slab test and, where it passes, the triangle tests. */
+__device__ __forceinline__ void emit_tasks(const WfArgs& g, int post_round, const Post& post, int slot) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
-    const unsigned lt = (1u << lane) - 1u;
     const bool mine = slot >= 0 && (post.kind == WF_MODE_CLOSEST || post.kind == WF_MODE_ANY) && post.cand_count > 0;
-    if (!__any_sync(FULL, mine)) return;
-    const float4* leaves = reinterpret_cast<const float4*>(blob + h.off_leaves);
-    const BinsView& b = g.bins[post.kind == WF_MODE_ANY ? 1 : 0];
-    int n = mine ? post.cand_count : 0;
-    const int* items = b.items + (mine ? post.cand_start : 0);
-    RayCtx ctx;
-    if (mine) ctx = make_ray_ctx(post.O, post.u, h.box_abs[0], h.box_abs[1], h.box_abs[2]);
-    const int etag = slot | (post.kind == WF_MODE_ANY ? (int)0x80000000u : 0);
-    unsigned fb = 0;
-    int i = 0;
-    while (__any_sync(FULL, i < n)) {
-        bool hit = false;
-        int code = 0;
-        if (i < n) {
-            const int id = __ldg(items + i);
-            i++;
-            float4 q0, q1;
-            ldg256(leaves + 2 * (size_t)id, q0, q1);
-            float tn;
-            hit = slab_fast(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, ctx, tn, fb);
-            code = __float_as_int(q1.z);
-        }
-        const unsigned m = __ballot_sync(FULL, hit);
-        if (m) {
-            if (hit) st.buf[st.fill + __popc(m & lt)] = make_int2(etag, code);
-            st.fill += __popc(m);
-            __syncwarp();
-            if (st.fill > WF_STAGE - 32) stage_flush(g, post_round, st);
-        }
+    const int n = mine ? post.cand_count : 0;
+    int incl = n;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int v = __shfl_up_sync(FULL, incl, d);
+        if (lane >= d) incl += v;
+    }
+    const int total = __shfl_sync(FULL, incl, 31);
+    if (total == 0) return;
+    int base = 0;
+    if (lane == 0) base = atomicAdd(&g.c->nTask[post_round], total);
+    base = __shfl_sync(FULL, base, 0);
+    if (base + total > g.task_cap) { /* reported by rt_scene_sync: the frame is rendered again with a larger buffer */
+        if (lane == 0) atomicExch(&g.c->stats[6], 1ull);
+        return;
+    }
+    if (n > 0) {
+        const int* items = g.bins[post.kind == WF_MODE_ANY ? 1 : 0].items + post.cand_start;
+        int2* out = g.tasks + base + (incl - n);
+        const int etag = slot | (post.kind == WF_MODE_ANY ? (int)0x80000000u : 0);
+#pragma unroll 4
+        for (int i = 0; i < n; i++) out[i] = make_int2(etag, __ldg(items + i));
     }
 }
 
@@ -648,12 +620,7 @@ __global__ void __launch_bounds__(WF_THREADS) wf_generate(const __grid_constant_
     }
     const int slot = post_queries(g, 0, post, px);
     if (g.anchored) {
-        __shared__ int2 stage_buf[WF_THREADS / 32][WF_STAGE];
-        TaskStage st;
-        st.buf = stage_buf[threadIdx.x >> 5];
-        st.fill = 0;
-        emit_tasks(h, blob, g, 0, post, slot, st);
-        stage_flush(g, 0, st);
+        emit_tasks(g, 0, post, slot);
         answer_deferred<STOCH>(h, blob, g, 0, post, slot);
     }
     flush_work(w, g.c, COUNT);
@@ -672,10 +639,6 @@ __global__ void __launch_bounds__(WF_THREADS) wf_shade(const __grid_constant__ S
     Work w;
     w.rays = w.nodes = w.tris = w.max_stack = w.slab_fallbacks = w.tri_exact = 0;
     const int n_round = (n + 31) & ~31; /* whole warps stay in the loop so that flush_work sees 32 lanes */
-    __shared__ int2 stage_buf[WF_THREADS / 32][WF_STAGE];
-    TaskStage st;
-    st.buf = stage_buf[threadIdx.x >> 5];
-    st.fill = 0;
     for (int e = blockIdx.x * WF_THREADS + threadIdx.x; e < n_round; e += gridDim.x * WF_THREADS) {
         Post post;
         post.kind = 0;
@@ -710,79 +673,118 @@ __global__ void __launch_bounds__(WF_THREADS) wf_shade(const __grid_constant__ S
         }
         const int slot = post_queries(g, g.round + 1, post, px);
         if (g.anchored) {
-            emit_tasks(h, blob, g, g.round + 1, post, slot, st);
+            emit_tasks(g, g.round + 1, post, slot);
             answer_deferred<STOCH>(h, blob, g, g.round + 1, post, slot);
         }
     }
-    if (g.anchored) stage_flush(g, g.round + 1, st);
     flush_work(w, g.c, COUNT);
 }
 
-/* ---- wf_leaves: one thread per (ray, leaf) task of round g.round -------------------------------------------------------
- * The triangle half of the reference's mesh query for anchored rays: the <= RT_LEAF_MAX triangles of the leaf against the
- * ray of the queue entry, two at a time (both records requested before either is tested). A closest-hit task merges
+/* ---- wf_leaves: one thread per (ray, candidate leaf) task of round g.round ----------------------------------------------
+ * The reference's mesh query for anchored rays: the leaf's box against the ray with the reference's slab test (certified fast
+ * path, exact fallback) and, where it passes, the <= RT_LEAF_MAX triangles of the leaf, two at a time (both records
+ * requested before either is tested). A closest-hit task merges
  * its accepted hits into the entry with a 64-bit atomicMin on (t bits, tie-break rank) — the reference's strict minimum
  * with its first-visited rule, order-free; a shadow task that finds a blocker marks the entry and paints
  * the pixel black. Tasks are uniform and independent: no pools, no tail. */
+/* the triangles of one leaf against the ray of one queue entry (the T half of a task) */
+template <bool STOCH>
+__device__ __forceinline__ void leaf_triangles(const SceneHeader& h, const WfArgs& g, const float4* __restrict__ tris, QEntry* q, bool any, int code) {
+    const RenderArgs& a = g.a;
+    const float4* p = reinterpret_cast<const float4*>(q);
+    const float4 p0 = __ldcg(p), p1 = __ldcg(p + 1);
+    const F3 O = f3(p0.x, p0.y, p0.z), u = f3(p1.x, p1.y, p1.z);
+    const unsigned long long cur = __ldcg(&q->res);
+    float t_limit;
+    if (any) {
+        if (cur != 0ull) return; /* a blocker was already found */
+        t_limit = sqrtf(p0.w) * 1.001f + 1e-3f; /* a hit with t > 1.001 sqrt(D2) cannot satisfy the shadow predicate (|t u| ~ t) */
+    } else {
+        t_limit = cur != WF_NOHIT ? __uint_as_float((unsigned)(cur >> 32)) : RTK_INF;
+    }
+    const int i_begin = code >> 2, i_end = min(i_begin + (code & 3) + 1, h.n_tris);
+    for (int k = i_begin; k < i_end; k += 2) {
+        const int k2 = min(k + 1, i_end - 1);
+        float4 a0, a1, b0, b1;
+        ldg256(tris + 4 * (size_t)k, a0, a1);
+        ldg256(tris + 4 * (size_t)k2, b0, b1);
+        const float4 a2 = __ldg(tris + 4 * (size_t)k + 2);
+        const float4 b2 = __ldg(tris + 4 * (size_t)k2 + 2);
+        const TriScreen s0 = tri_screen(a0, a1, a2, O, u, t_limit);
+        TriScreen s1 = tri_screen(b0, b1, b2, O, u, t_limit);
+        s1.maybe &= k2 != k;
+        if (s0.maybe | s1.maybe) {
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                const TriScreen& sj = j ? s1 : s0;
+                if (!sj.maybe) continue;
+                const int ij = j ? k2 : k;
+                float t;
+                if (!tri_finish(sj, t) || !(t > a.eps_tri)) continue;
+                if (any) {
+                    if (blocks_light(O, u, t, p0.w)) {
+                        q->res = 1ull;
+                        light_is_blocked<STOCH>(a, g, (int)(__float_as_uint(p1.w) & ~WF_ROOT_UNTESTED), q->packed);
+                        return;
+                    }
+                } else {
+                    unsigned rank = (unsigned)ij; /* push_order 1: ascending triangle index */
+                    if (a.push_order != 1) rank = tie_rank(ij, __float_as_int(__ldg(tris + 4 * (size_t)ij + 3).w), h.n_tris, 0, a.rank_off_bits);
+                    atomicMin(&q->res, ((unsigned long long)__float_as_uint(t) << 32) | rank);
+                    if (t < t_limit) t_limit = t;
+                }
+            }
+        }
+    }
+}
+
 template <bool STOCH>
 __global__ void __launch_bounds__(WF_THREADS) wf_leaves(const __grid_constant__ SceneHeader h, const unsigned char* __restrict__ blob,
                                                        const __grid_constant__ WfArgs g) {
-    const RenderArgs& a = g.a;
+    /* Two phases per warp, both with full lanes: the box phase takes 32 tasks and keeps those whose box passes the slab
+     * test (about half) in a small per-warp buffer; whenever the buffer holds 32 of them the triangle phase runs on 32. */
+    __shared__ int2 hitbuf[WF_THREADS / 32][64];
+    const unsigned FULL = 0xffffffffu;
     const float4* tris = reinterpret_cast<const float4*>(blob + h.off_tris);
+    const float4* leaves = reinterpret_cast<const float4*>(blob + h.off_leaves);
     const int n = min(g.c->nTask[g.round], g.task_cap);
     QEntry* const qA = g.qA[g.round & 1];
-    for (int i = blockIdx.x * WF_THREADS + threadIdx.x; i < n; i += gridDim.x * WF_THREADS) {
-        const int2 task = g.tasks[i];
-        const bool any = task.x < 0;
-        QEntry* const q = (any ? g.qS : qA) + (task.x & 0x7fffffff);
-        const float4* p = reinterpret_cast<const float4*>(q);
-        const float4 p0 = __ldcg(p), p1 = __ldcg(p + 1);
-        const F3 O = f3(p0.x, p0.y, p0.z), u = f3(p1.x, p1.y, p1.z);
-        const unsigned long long cur = __ldcg(&q->res);
-        float t_limit;
-        if (any) {
-            if (cur != 0ull) continue; /* a blocker was already found */
-            t_limit = sqrtf(p0.w) * 1.001f + 1e-3f; /* a hit with t > 1.001 sqrt(D2) cannot satisfy the shadow predicate (|t u| ~ t) */
-        } else {
-            t_limit = cur != WF_NOHIT ? __uint_as_float((unsigned)(cur >> 32)) : RTK_INF;
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    int2* const buf = hitbuf[threadIdx.x >> 5];
+    int fill = 0; /* warp-uniform */
+    const int n_round = (n + 31) & ~31;
+    for (int i = blockIdx.x * WF_THREADS + threadIdx.x; i < n_round; i += gridDim.x * WF_THREADS) {
+        bool hit = false;
+        int2 task = make_int2(0, 0);
+        int code = 0;
+        if (i < n) {
+            task = g.tasks[i];
+            const QEntry* q = ((task.x < 0) ? g.qS : qA) + (task.x & 0x7fffffff);
+            const float4* p = reinterpret_cast<const float4*>(q);
+            const float4 p0 = __ldcg(p), p1 = __ldcg(p + 1);
+            float4 l0, l1;
+            ldg256(leaves + 2 * (size_t)task.y, l0, l1);
+            const RayCtx ctx = make_ray_ctx(f3(p0.x, p0.y, p0.z), f3(p1.x, p1.y, p1.z), h.box_abs[0], h.box_abs[1], h.box_abs[2]);
+            float tn;
+            unsigned fb = 0;
+            hit = slab_fast(l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, ctx, tn, fb);
+            code = __float_as_int(l1.z);
         }
-        const int i_begin = task.y >> 2, i_end = min(i_begin + (task.y & 3) + 1, h.n_tris);
-        for (int k = i_begin; k < i_end; k += 2) {
-            const int k2 = min(k + 1, i_end - 1);
-            float4 a0, a1, b0, b1;
-            ldg256(tris + 4 * (size_t)k, a0, a1);
-            ldg256(tris + 4 * (size_t)k2, b0, b1);
-            const float4 a2 = __ldg(tris + 4 * (size_t)k + 2);
-            const float4 b2 = __ldg(tris + 4 * (size_t)k2 + 2);
-            const TriScreen s0 = tri_screen(a0, a1, a2, O, u, t_limit);
-            TriScreen s1 = tri_screen(b0, b1, b2, O, u, t_limit);
-            s1.maybe &= k2 != k;
-            bool stop = false;
-            if (s0.maybe | s1.maybe) {
-#pragma unroll
-                for (int j = 0; j < 2; j++) {
-                    const TriScreen& sj = j ? s1 : s0;
-                    if (!sj.maybe) continue;
-                    const int ij = j ? k2 : k;
-                    float t;
-                    if (!tri_finish(sj, t) || !(t > a.eps_tri)) continue;
-                    if (any) {
-                        if (blocks_light(O, u, t, p0.w)) {
-                            q->res = 1ull;
-                            light_is_blocked<STOCH>(a, g, (int)(__float_as_uint(p1.w) & ~WF_ROOT_UNTESTED), q->packed);
-                            stop = true;
-                            break;
-                        }
-                    } else {
-                        unsigned rank = (unsigned)ij; /* push_order 1: ascending triangle index */
-                        if (a.push_order != 1) rank = tie_rank(ij, __float_as_int(__ldg(tris + 4 * (size_t)ij + 3).w), h.n_tris, 0, a.rank_off_bits);
-                        atomicMin(&q->res, ((unsigned long long)__float_as_uint(t) << 32) | rank);
-                        if (t < t_limit) t_limit = t;
-                    }
-                }
-            }
-            if (stop) break;
+        const unsigned m = __ballot_sync(FULL, hit);
+        if (hit) buf[fill + __popc(m & lt)] = make_int2(task.x, code);
+        fill += __popc(m);
+        __syncwarp();
+        if (fill >= 32) {
+            const int2 t = buf[fill - 32 + lane];
+            fill -= 32;
+            leaf_triangles<STOCH>(h, g, tris, ((t.x < 0) ? g.qS : qA) + (t.x & 0x7fffffff), t.x < 0, t.y);
+            __syncwarp();
         }
+    }
+    if (lane < fill) {
+        const int2 t = buf[lane];
+        leaf_triangles<STOCH>(h, g, tris, ((t.x < 0) ? g.qS : qA) + (t.x & 0x7fffffff), t.x < 0, t.y);
     }
 }
 
