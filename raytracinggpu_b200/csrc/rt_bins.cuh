@@ -11,8 +11,7 @@
  * wins. The inner boxes only serve to find those leaves. For anchored rays they can be found without a tree: the
  * directions around the anchor are cut into 3 faces (dominant axis x, y or z; d and -d share a cell because the
  * slab test knows no t >= 0) of R x R cells of the two ratios d_a / d_k, d_b / d_k in [-1, 1], and every cell lists the
- * leaves whose box — inflated by eps — meets a line through the anchor with a direction of that cell (padded by one
- * cell on every side). A ray looks up the cell of its direction, applies the reference's own slab test (certified
+ * leaves whose box — inflated by eps — meets a line through the anchor with a direction of that cell. A ray looks up the cell of its direction, applies the reference's own slab test (certified
  * fast path + exact fallback, rt_math.cuh) to the listed boxes, and emits one (ray, leaf) task per box that passes;
  * wf_leaves then tests the triangles. Versus the tree search: 2.3 box tests per leaf found instead of 9, no task pools,
  * no dependent chain of tree levels, and the triangle work arrives as uniform independent tasks.
@@ -24,10 +23,11 @@
  * box. A camera ray's line passes through the anchor exactly. A shadow ray starts at P' and has the direction
  * fl((L - P') / |L - P'|), within 2^-21 of the true one: over the distances involved (D = |L - P'| plus the extent of
  * the scene) its line stays within 2^-20 (D + S + |L|) of the line through P' and L. With eps = 2^-12 (S + |anchor|) and
- * the guard D <= 2^7 (S + |anchor|) on the ray side, both are covered with a factor > 4 to spare; rays beyond the guard,
+ * the guard D <= 2^7 (S + |anchor|) on the ray side, both are covered with a factor > 2 to spare; rays beyond the guard,
  * and rays with a zero, subnormal or non-finite direction component (where a slab distance may be NaN and the
  * implication child => parent fails), are answered by the exact two-child traversal instead (wf_exact_query).
- * The cell of a ray is computed with one rounding-level error in the ratios; the one-cell padding absorbs it.
+ * The cell of a ray is computed with a rounding-level error in the ratios (a few 2^-23): the ratio bounds of a leaf are widened
+ * by 2^-20, still inside what the inflation leaves unused (eps / distance >= 2^-13 in ratio units).
  * tools/proto_bins.py checks the property on every ray of a frame on the CPU; the GPU parity tests check the results.
  *
  * Leaves whose inflated box contains the anchor have no bounded set of cells; a scene that has one keeps the tree
@@ -97,8 +97,11 @@ __device__ __forceinline__ bool bins_leaf_cells(const float4 q0, const float4 q1
             ra0 = fmaxf(ra0, -1.f); ra1 = fminf(ra1, 1.f);
             rb0 = fmaxf(rb0, -1.f); rb1 = fminf(rb1, 1.f);
             if (!(ra0 <= ra1) || !(rb0 <= rb1)) continue;
-            const int ca0 = max((int)floorf(__fmaf_rn(ra0, h, h)) - 1, 0), ca1 = min((int)floorf(__fmaf_rn(ra1, h, h)) + 1, R - 1);
-            const int cb0 = max((int)floorf(__fmaf_rn(rb0, h, h)) - 1, 0), cb1 = min((int)floorf(__fmaf_rn(rb1, h, h)) + 1, R - 1);
+            /* RATIO_SLACK covers the roundings of these bounds and of the ray's own cell computation (a few 2^-23, relative, on
+             * values <= 1): far below what the inflation by eps leaves unused (>= 2^-15 in ratio units, see the header) */
+            const float RATIO_SLACK = 9.5367431640625e-07f; /* 2^-20 */
+            const int ca0 = max((int)floorf(__fmaf_rn(ra0 - RATIO_SLACK, h, h)), 0), ca1 = min((int)floorf(__fmaf_rn(ra1 + RATIO_SLACK, h, h)), R - 1);
+            const int cb0 = max((int)floorf(__fmaf_rn(rb0 - RATIO_SLACK, h, h)), 0), cb1 = min((int)floorf(__fmaf_rn(rb1 + RATIO_SLACK, h, h)), R - 1);
             for (int cb = cb0; cb <= cb1; cb++)
                 for (int ca = ca0; ca <= ca1; ca++) f((k * R + cb) * R + ca);
         }
