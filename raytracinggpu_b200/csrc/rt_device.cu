@@ -99,6 +99,8 @@ struct rt_scene {
     size_t wf_tasks_cap = 0;
     int task_factor = 8;     /* task buffer entries per pixel; doubled after an overflow */
     bool last_was_anchored = false;
+    int leaves_blocks_per_sm = 0;
+    bool task_factor_from_env = false;
     int bins_builds = 0;
     size_t wf_spill_ints = 0;
     int* dbg_warps = nullptr; /* RT_DEBUG_WARPS=<file>: per-warp timeline of wf_traverse (count_work renders) */
@@ -197,6 +199,11 @@ int ensure_bins(rt_scene* s, int which, const float A[3]) {
     rt_scene::AnchorBins& b = s->bins[which];
     const SceneHeader& h = s->header;
     static const int env_R = getenv("RT_BINS_R") ? atoi(getenv("RT_BINS_R")) : 0;
+    static const int env_tf = getenv("RT_TASK_FACTOR") ? atoi(getenv("RT_TASK_FACTOR")) : 0; /* test hook: a small task buffer forces the overflow + repeat path */
+    if (env_tf > 0 && !s->task_factor_from_env) {
+        s->task_factor = env_tf;
+        s->task_factor_from_env = true;
+    }
     const int R = env_R > 0 ? std::min(std::max(env_R, 8), 4096) : (h.n_leaves > 200000 ? 2048 : 1024);
     if (b.built && b.mesh_generation == s->mesh_generation && b.R == R && b.A[0] == A[0] && b.A[1] == A[1] && b.A[2] == A[2]) return RT_OK;
     b.built = false;
@@ -425,6 +432,7 @@ int rt_scene_set_mesh(rt_scene* s, const float* vertices, int32_t nv, const int3
         s->blob = nullptr;
         s->blob_bytes = 0;
         reset_mesh_fields(h);
+        s->mesh_generation++;
         h.mesh_id = -1;
         s->header_dirty = true;
         return RT_OK;
@@ -768,6 +776,7 @@ int rt_scene_blob_import(rt_scene* s, const void* device_ptr, size_t bytes) {
     }
     s->header = h;
     s->header_dirty = false;
+    s->mesh_generation++; /* the anchored-ray bins of the previous mesh are stale */
     return RT_OK;
 }
 
@@ -970,8 +979,10 @@ int rt_render(rt_scene* s, const rt_params* p, uint32_t flags, uint8_t* rgb_out,
             /* anchored rays (rt_bins.cuh): camera rays and shadow rays find their leaves through per-anchor bins and wf_leaves
              * tests the triangles; wf_traverse keeps the rays that start anywhere else (bounces). The instrumented build
              * counts the reference's node visits and therefore searches the tree; RT_ANCHOR=0 does so too (A/B, cross-check). */
-            static const bool env_anchor = !(getenv("RT_ANCHOR") && atoi(getenv("RT_ANCHOR")) == 0);
-            bool anchored = env_anchor && !count && h.has_mesh && h.n_leaves > 0 && segments > 0;
+            static const int env_anchor = getenv("RT_ANCHOR") ? atoi(getenv("RT_ANCHOR")) : -1; /* 0 off, 1 on, unset: by mesh size */
+            /* measured (profiles/r01_configs.md): with millions of leaves a cell lists hundreds of them and one task per candidate
+             * loses against the tree search; the bins serve meshes up to 200 k leaves unless asked for */
+            bool anchored = (env_anchor > 0 || (env_anchor < 0 && h.n_leaves <= 200000)) && !count && h.has_mesh && h.n_leaves > 0 && segments > 0;
             if (anchored) {
                 int rc = ensure_bins(s, 0, p->cam);
                 if (rc == RT_OK) rc = ensure_bins(s, 1, h.L);
@@ -1129,8 +1140,24 @@ int rt_render(rt_scene* s, const rt_params* p, uint32_t flags, uint8_t* rgb_out,
                 g.bins[1] = bins_view(s->bins[1]);
                 g.tasks = anchored ? s->wf_tasks + (size_t)s->task_factor * px0 + task_slack * st : nullptr;
                 g.qcap = (int)spx;
+                for (int k = 0; k < RT_MAX_SPHERES; k++) {
+                    const DevSphere& sp = h.spheres[k];
+                    /* the operations of Sphere::intersect / sphere_t, in their order, in float (no contraction on the host) */
+                    volatile float ocx = a.camx - sp.cx, ocy = a.camy - sp.cy, ocz = a.camz - sp.cz;
+                    volatile float xx = ocx * ocx, yy = ocy * ocy, zz = ocz * ocz;
+                    volatile float n2 = xx + yy;
+                    n2 = n2 + zz;
+                    volatile float cc = n2 - sp.RR;
+                    g.cam_sph[k] = k < h.n_spheres ? make_float4(ocx, ocy, ocz, cc) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
                 g.task_cap = anchored ? (int)std::min<size_t>((size_t)s->task_factor * spx + task_slack, (size_t)0x7fffffff) : 0;
-                const unsigned leaves_grid = (unsigned)(s->sm_count * 16);
+                if (anchored && s->leaves_blocks_per_sm == 0) { /* one resident wave of wf_leaves: every block gets the same share of the tasks */
+                    int nb = 0;
+                    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rtk::wf_leaves<false>, WF_THREADS, 0));
+                    s->leaves_blocks_per_sm = std::max(nb, 1);
+                }
+                static const int env_lb = getenv("RT_LEAVES_BLOCKS") ? atoi(getenv("RT_LEAVES_BLOCKS")) : 0;
+                const unsigned leaves_grid = (unsigned)(s->sm_count * (env_lb > 0 ? env_lb : std::max(s->leaves_blocks_per_sm, 1)));
                 const unsigned wtiles = (unsigned)((p->W + 7) / 8) * (unsigned)((srows + 3) / 4);
                 const unsigned gen_grid = (wtiles + (WF_THREADS / 32) - 1) / (WF_THREADS / 32);
                 const unsigned shade_grid = (unsigned)std::min<size_t>((spx + WF_THREADS - 1) / WF_THREADS, (size_t)s->sm_count * 16);

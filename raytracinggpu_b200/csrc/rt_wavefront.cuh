@@ -88,6 +88,7 @@ struct WfArgs {
     int2* tasks;  /* x: queue entry | 0x80000000 for a shadow query, y: leaf-table index of the candidate */
     int task_cap;
     int qcap;     /* entries of each queue of this strip */
+    float4 cam_sph[RT_MAX_SPHERES]; /* per sphere: O - C (xyz) and |O - C|^2 - R^2 (w) for O = the camera (closest_sphere_cam) */
 };
 
 __device__ __forceinline__ unsigned tie_rank(int i, int leaf_start, int n_tris, int push_order, int off_bits) {
@@ -159,6 +160,36 @@ __device__ __forceinline__ void write_pixel(const RenderArgs& a, int px, F3 colo
     a.rgb[(size_t)px * 3 + 0] = (uint8_t)quantise(avg.x, T);
     a.rgb[(size_t)px * 3 + 1] = (uint8_t)quantise(avg.y, T);
     a.rgb[(size_t)px * 3 + 2] = (uint8_t)quantise(avg.z, T);
+}
+
+/* Is the ray outside the contract of the bins / the wide index (rt_bins.cuh)? A slab distance can only be NaN (0/0) when a
+ * direction component is zero; flagged here is the superset "zero, subnormal, tiny, infinite or NaN component" — such rays
+ * are answered by the exact tree search, which is right for every ray. */
+__device__ __forceinline__ bool outside_contract(F3 u) {
+    const float ax = fabsf(u.x), ay = fabsf(u.y), az = fabsf(u.z);
+    return !(ax >= 1e-37f && ay >= 1e-37f && az >= 1e-37f && ax <= 3e38f && ay <= 3e38f && az <= 3e38f);
+}
+
+/* closest_sphere for a ray that starts at the camera: O - C and |O - C|^2 - R^2 of Sphere::intersect (optimized.cu:124-126)
+ * do not depend on the pixel; cam_sph holds them (same operations, same order, evaluated once on the host). */
+__device__ __forceinline__ void closest_sphere_cam(const SceneHeader& h, const float4* __restrict__ cam_sph, F3 u, float& ts, int& sidx) {
+    ts = RTK_INF;
+    sidx = -1;
+    for (int k = 0; k < h.n_spheres; k++) {
+        const float4 c = cam_sph[k];
+        const float b = dot(u, f3(c.x, c.y, c.z));
+        const float delta = b * b - c.w;
+        if (delta < 0) continue;
+        const float sq = sqrtf(delta);
+        const float bc = -b;
+        const float t1 = bc - sq, t2 = bc + sq;
+        if (t2 < 0) continue;
+        const float t = t1 < 0 ? t2 : t1;
+        if (t < ts) {
+            ts = t;
+            sidx = k;
+        }
+    }
 }
 
 __device__ __forceinline__ void closest_sphere(const SceneHeader& h, F3 O, F3 u, float& ts, int& sidx) {
@@ -245,14 +276,14 @@ __device__ __forceinline__ void path_advance(const SceneHeader& h, const WfArgs&
                 return;
             }
             w.rays++;
-            closest_sphere(h, O, u, t_hit, sidx);
+            if (depth == 0) closest_sphere_cam(h, g.cam_sph, u, t_hit, sidx); /* depth 0 without a hit: the camera ray (wf_generate) */
+            else closest_sphere(h, O, u, t_hit, sidx);
             tri = -1;
             if (h.has_mesh && g.anchored && depth == 0) {
                 /* a camera ray: its candidate leaves come from the camera's bins (rt_bins.cuh) */
-                const float mchk = (__frcp_rn(u.x) - __frcp_rn(u.x)) + (__frcp_rn(u.y) - __frcp_rn(u.y)) + (__frcp_rn(u.z) - __frcp_rn(u.z));
                 /* a zero / subnormal / non-finite component is outside the bins' contract: the query is posted without
                  * candidates (cand_count -1) and answered by the exact tree search at the end of the kernel (answer_exact) */
-                const bool exact = mchk != mchk;
+                const bool exact = outside_contract(u);
                 int c0 = 0, c1 = -1;
                 if (!exact) {
                     const int cell = bins_cell(g.bins[0], u);
@@ -378,8 +409,7 @@ __device__ __forceinline__ void path_advance(const SceneHeader& h, const WfArgs&
             }
             if (!blocked && h.has_mesh && g.anchored) {
                 /* a shadow ray: its candidate leaves come from the light's bins */
-                const float mchk = (__frcp_rn(su.x) - __frcp_rn(su.x)) + (__frcp_rn(su.y) - __frcp_rn(su.y)) + (__frcp_rn(su.z) - __frcp_rn(su.z));
-                const bool exact = mchk != mchk || !(D2 <= g.bins[1].max_D2); /* outside the bins' contract: see the camera rays above */
+                const bool exact = outside_contract(su) || !(D2 <= g.bins[1].max_D2); /* outside the bins' contract: see the camera rays above */
                 int c0 = 0, c1 = -1;
                 if (!exact) {
                     const int cell = bins_cell(g.bins[1], toL);
@@ -754,12 +784,14 @@ __global__ void __launch_bounds__(WF_THREADS) wf_leaves(const __grid_constant__ 
     int2* const buf = hitbuf[threadIdx.x >> 5];
     int fill = 0; /* warp-uniform */
     const int n_round = (n + 31) & ~31;
-    for (int i = blockIdx.x * WF_THREADS + threadIdx.x; i < n_round; i += gridDim.x * WF_THREADS) {
+    const int stride = gridDim.x * WF_THREADS;
+    int i = blockIdx.x * WF_THREADS + threadIdx.x;
+    int2 task = i < n ? g.tasks[i] : make_int2(0, 0);
+    for (; i < n_round; i += stride) {
+        const int2 next = (i + stride < n) ? g.tasks[i + stride] : make_int2(0, 0); /* requested one iteration ahead */
         bool hit = false;
-        int2 task = make_int2(0, 0);
         int code = 0;
         if (i < n) {
-            task = g.tasks[i];
             const QEntry* q = ((task.x < 0) ? g.qS : qA) + (task.x & 0x7fffffff);
             const float4* p = reinterpret_cast<const float4*>(q);
             const float4 p0 = __ldcg(p), p1 = __ldcg(p + 1);
@@ -781,6 +813,7 @@ __global__ void __launch_bounds__(WF_THREADS) wf_leaves(const __grid_constant__ 
             leaf_triangles<STOCH>(h, g, tris, ((t.x < 0) ? g.qS : qA) + (t.x & 0x7fffffff), t.x < 0, t.y);
             __syncwarp();
         }
+        task = next;
     }
     if (lane < fill) {
         const int2 t = buf[lane];
