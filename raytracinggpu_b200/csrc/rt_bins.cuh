@@ -46,6 +46,8 @@ struct BinsView {       /* by value in kernel arguments */
     int R;              /* cells per face side; 0 = no bins (tree search) */
     const int* cell_start; /* 3 R R + 1 */
     const int* items;      /* leaf-table indices */
+    int items_cap;         /* entries of `items`; a list that ends beyond it was cut short by the build (exact search instead) */
+    const int* status;     /* [0] != 0: a leaf box contains the anchor, the lists are not complete (exact search instead) */
 };
 
 /* cell of a direction (from or towards the anchor: the sign cancels in the ratios) */
@@ -114,15 +116,20 @@ __global__ void bins_count(const float4* __restrict__ leaves, int n_leaves, floa
     const int l = blockIdx.x * blockDim.x + threadIdx.x;
     if (l >= n_leaves) return;
     const float4 q0 = leaves[2 * (size_t)l], q1 = leaves[2 * (size_t)l + 1];
-    if (!bins_leaf_cells(q0, q1, ax, ay, az, eps, R, [&](int cell) { atomicAdd(counts + cell, 1); })) atomicOr(flags, 1);
+    if (!bins_leaf_cells(q0, q1, ax, ay, az, eps, R, [&](int cell) { atomicAdd(counts + cell, 1); })) flags[0] = 1;
 }
 
 /* pass 2 (after the exclusive scan of counts into cell_start): fill the lists; cursor starts as a copy of cell_start */
-__global__ void bins_fill(const float4* __restrict__ leaves, int n_leaves, float ax, float ay, float az, float eps, int R, int* __restrict__ cursor, int* __restrict__ items) {
+__global__ void bins_fill(const float4* __restrict__ leaves, int n_leaves, float ax, float ay, float az, float eps, int R, int* __restrict__ cursor, int* __restrict__ items,
+                          int items_cap, int* __restrict__ status) {
     const int l = blockIdx.x * blockDim.x + threadIdx.x;
     if (l >= n_leaves) return;
     const float4 q0 = leaves[2 * (size_t)l], q1 = leaves[2 * (size_t)l + 1];
-    bins_leaf_cells(q0, q1, ax, ay, az, eps, R, [&](int cell) { items[atomicAdd(cursor + cell, 1)] = l; });
+    bins_leaf_cells(q0, q1, ax, ay, az, eps, R, [&](int cell) {
+        const int at = atomicAdd(cursor + cell, 1);
+        if (at < items_cap) items[at] = l;
+        else status[1] = 1; /* the lists outgrew the buffer (the anchor moved): rays of the cut lists take the exact search, the host enlarges it */
+    });
 }
 
 } // namespace rtk

@@ -90,11 +90,13 @@ struct rt_scene {
         int* cursor = nullptr;
         size_t cells_cap = 0;
         int* items = nullptr;
-        size_t items_cap = 0, n_items = 0;
+        size_t items_cap = 0;
+        int* status = nullptr;   /* device: [0] a leaf box contains the anchor, [1] the lists outgrew `items` */
+        int* h_status = nullptr; /* pinned copy, refreshed by rt_scene_sync */
+        bool grow = false;       /* the next build enlarges `items` */
     } bins[2];
     void* scan_tmp = nullptr;
     size_t scan_tmp_bytes = 0;
-    int* bins_flags = nullptr;
     int2* wf_tasks = nullptr;
     size_t wf_tasks_cap = 0;
     int task_factor = 8;     /* task buffer entries per pixel; doubled after an overflow */
@@ -192,22 +194,25 @@ void reset_mesh_fields(SceneHeader& h) {
     }
 }
 
-/* (Re)build the candidate lists of one anchor (rt_bins.cuh) when the anchor, the mesh or the resolution changed.
- * Three small launches (count, scan, fill) and one 8-byte read-back; a scene with a fixed camera and light builds them
- * once. usable = false when a leaf box contains the anchor (the caller then keeps the tree search). */
+/* (Re)build the candidate lists of one anchor (rt_bins.cuh) when the anchor, the mesh or the resolution changed: three
+ * small launches (count, scan, fill). The first build for a mesh reads the list total back to size the item buffer
+ * (one synchronisation, next to the ones rt_scene_set_mesh already has); later builds — a moving light or camera — are
+ * enqueued without any read-back: the buffer keeps a quarter of headroom, lists that still outgrow it are cut short and
+ * their rays take the exact search (device-side check), and rt_scene_sync enlarges the buffer for the next build. A leaf
+ * box around the anchor is flagged in the status word the kernels consult. */
 int ensure_bins(rt_scene* s, int which, const float A[3]) {
     rt_scene::AnchorBins& b = s->bins[which];
     const SceneHeader& h = s->header;
-    static const int env_R = getenv("RT_BINS_R") ? atoi(getenv("RT_BINS_R")) : 0;
-    static const int env_tf = getenv("RT_TASK_FACTOR") ? atoi(getenv("RT_TASK_FACTOR")) : 0; /* test hook: a small task buffer forces the overflow + repeat path */
+    const int env_R = getenv("RT_BINS_R") ? atoi(getenv("RT_BINS_R")) : 0;
+    const int env_tf = getenv("RT_TASK_FACTOR") ? atoi(getenv("RT_TASK_FACTOR")) : 0; /* test hook: a small task buffer forces the overflow + repeat path */
     if (env_tf > 0 && !s->task_factor_from_env) {
         s->task_factor = env_tf;
         s->task_factor_from_env = true;
     }
     const int R = env_R > 0 ? std::min(std::max(env_R, 8), 4096) : (h.n_leaves > 200000 ? 2048 : 1024);
-    if (b.built && b.mesh_generation == s->mesh_generation && b.R == R && b.A[0] == A[0] && b.A[1] == A[1] && b.A[2] == A[2]) return RT_OK;
+    if (b.built && b.mesh_generation == s->mesh_generation && b.R == R && b.A[0] == A[0] && b.A[1] == A[1] && b.A[2] == A[2] && !b.grow) return RT_OK;
+    const bool first = !b.built || b.mesh_generation != s->mesh_generation || b.R != R || b.items_cap == 0;
     b.built = false;
-    b.usable = false;
     const size_t n_cells = (size_t)3 * R * R;
     if (b.cells_cap < n_cells + 1) {
         CUDA_TRY(cudaStreamSynchronize(s->stream));
@@ -219,7 +224,20 @@ int ensure_bins(rt_scene* s, int which, const float A[3]) {
         CUDA_TRY(cudaMalloc(&b.cursor, (n_cells + 1) * sizeof(int)));
         b.cells_cap = n_cells + 1;
     }
-    if (!s->bins_flags) CUDA_TRY(cudaMalloc(&s->bins_flags, 2 * sizeof(int)));
+    if (!b.status) {
+        CUDA_TRY(cudaMalloc(&b.status, 4 * sizeof(int)));
+        CUDA_TRY(cudaMallocHost(&b.h_status, 4 * sizeof(int)));
+    }
+    if (b.grow) { /* the previous build outgrew the buffer (noticed by rt_scene_sync) */
+        CUDA_TRY(cudaStreamSynchronize(s->stream));
+        if (b.items) cudaFree(b.items);
+        b.items = nullptr;
+        const size_t cap = b.items_cap * 2 + 1024;
+        b.items_cap = 0;
+        CUDA_TRY(cudaMalloc(&b.items, cap * sizeof(int)));
+        b.items_cap = cap;
+        b.grow = false;
+    }
     const float S = std::max(h.box_abs[0], std::max(h.box_abs[1], h.box_abs[2]));
     const float scale = S + std::max(std::fabs(A[0]), std::max(std::fabs(A[1]), std::fabs(A[2])));
     b.eps = scale * (1.f / 4096.f);
@@ -227,8 +245,8 @@ int ensure_bins(rt_scene* s, int which, const float A[3]) {
     const float4* leaves = reinterpret_cast<const float4*>(s->blob + h.off_leaves);
     const int threads = 128, blocks = (h.n_leaves + threads - 1) / threads;
     CUDA_TRY(cudaMemsetAsync(b.cell_start, 0, (n_cells + 1) * sizeof(int), s->stream));
-    CUDA_TRY(cudaMemsetAsync(s->bins_flags, 0, 2 * sizeof(int), s->stream));
-    rtk::bins_count<<<blocks, threads, 0, s->stream>>>(leaves, h.n_leaves, A[0], A[1], A[2], b.eps, R, b.cell_start, s->bins_flags);
+    CUDA_TRY(cudaMemsetAsync(b.status, 0, 4 * sizeof(int), s->stream));
+    rtk::bins_count<<<blocks, threads, 0, s->stream>>>(leaves, h.n_leaves, A[0], A[1], A[2], b.eps, R, b.cell_start, b.status);
     CUDA_TRY(cudaGetLastError());
     size_t tmp_bytes = 0;
     CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, b.cell_start, b.cell_start, (int)(n_cells + 1), s->stream));
@@ -241,31 +259,32 @@ int ensure_bins(rt_scene* s, int which, const float A[3]) {
         s->scan_tmp_bytes = tmp_bytes;
     }
     CUDA_TRY(cub::DeviceScan::ExclusiveSum(s->scan_tmp, tmp_bytes, b.cell_start, b.cell_start, (int)(n_cells + 1), s->stream));
-    int total = 0, flags = 0;
-    CUDA_TRY(cudaMemcpyAsync(&total, b.cell_start + n_cells, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
-    CUDA_TRY(cudaMemcpyAsync(&flags, s->bins_flags, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
-    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    if (first) {
+        int total = 0;
+        CUDA_TRY(cudaMemcpyAsync(&total, b.cell_start + n_cells, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+        CUDA_TRY(cudaStreamSynchronize(s->stream));
+        if (total < 0) return rtb::fail(RT_ERR_UNSUPPORTED, "rt_render: candidate lists of %d cells overflow 2^31 entries", (int)n_cells);
+        const size_t cap = (size_t)total + (size_t)total / 4 + 1024;
+        if (b.items_cap < cap) {
+            if (b.items) cudaFree(b.items);
+            b.items = nullptr;
+            b.items_cap = 0;
+            CUDA_TRY(cudaMalloc(&b.items, cap * sizeof(int)));
+            b.items_cap = cap;
+        }
+    }
+    CUDA_TRY(cudaMemcpyAsync(b.cursor, b.cell_start, (n_cells + 1) * sizeof(int), cudaMemcpyDeviceToDevice, s->stream));
+    rtk::bins_fill<<<blocks, threads, 0, s->stream>>>(leaves, h.n_leaves, A[0], A[1], A[2], b.eps, R, b.cursor, b.items,
+                                                      (int)std::min<size_t>(b.items_cap, 0x7fffffff), b.status);
+    CUDA_TRY(cudaGetLastError());
     b.R = R;
     b.A[0] = A[0];
     b.A[1] = A[1];
     b.A[2] = A[2];
     b.mesh_generation = s->mesh_generation;
     b.built = true;
-    s->bins_builds++;
-    if (flags != 0 || total < 0) return RT_OK; /* a leaf box around the anchor: not usable */
-    if (b.items_cap < (size_t)total) {
-        if (b.items) cudaFree(b.items);
-        b.items = nullptr;
-        b.items_cap = 0;
-        const size_t cap = (size_t)total + (size_t)total / 4 + 1024;
-        CUDA_TRY(cudaMalloc(&b.items, cap * sizeof(int)));
-        b.items_cap = cap;
-    }
-    b.n_items = (size_t)total;
-    CUDA_TRY(cudaMemcpyAsync(b.cursor, b.cell_start, (n_cells + 1) * sizeof(int), cudaMemcpyDeviceToDevice, s->stream));
-    rtk::bins_fill<<<blocks, threads, 0, s->stream>>>(leaves, h.n_leaves, A[0], A[1], A[2], b.eps, R, b.cursor, b.items);
-    CUDA_TRY(cudaGetLastError());
     b.usable = true;
+    s->bins_builds++;
     return RT_OK;
 }
 
@@ -279,6 +298,8 @@ rtk::BinsView bins_view(const rt_scene::AnchorBins& b) {
     v.R = b.R;
     v.cell_start = b.cell_start;
     v.items = b.items;
+    v.items_cap = (int)std::min<size_t>(b.items_cap, 0x7fffffff);
+    v.status = b.status;
     return v;
 }
 
@@ -355,8 +376,11 @@ void rt_scene_destroy(rt_scene* s) {
         if (s->bins[k].cursor) cudaFree(s->bins[k].cursor);
         if (s->bins[k].items) cudaFree(s->bins[k].items);
     }
+    for (int k = 0; k < 2; k++) {
+        if (s->bins[k].status) cudaFree(s->bins[k].status);
+        if (s->bins[k].h_status) cudaFreeHost(s->bins[k].h_status);
+    }
     if (s->scan_tmp) cudaFree(s->scan_tmp);
-    if (s->bins_flags) cudaFree(s->bins_flags);
     if (s->wf_tasks) cudaFree(s->wf_tasks);
     if (s->rng_states) cudaFree(s->rng_states);
     if (s->st_buf) cudaFree(s->st_buf);
@@ -784,6 +808,9 @@ int rt_scene_sync(rt_scene* s, rt_stats* stats) {
     if (!s) return rtb::fail(RT_ERR_INVALID, "rt_scene_sync: NULL scene");
     DeviceGuard g(s->device);
     if (s->pending) {
+        if (s->last_was_wavefront && s->last_was_anchored)
+            for (int k = 0; k < 2; k++)
+                if (s->bins[k].status) CUDA_TRY(cudaMemcpyAsync(s->bins[k].h_status, s->bins[k].status, 4 * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
         if (s->last_was_wavefront)
             CUDA_TRY(cudaMemcpyAsync(s->h_wf_counters, s->wf_counters, RT_MAX_STRIPS * sizeof(rtk::WfCounters), cudaMemcpyDeviceToHost, s->stream));
         else
@@ -830,6 +857,9 @@ int rt_scene_sync(rt_scene* s, rt_stats* stats) {
             fclose(f);
         }
     }
+    if (s->pending && s->last_was_wavefront && s->last_was_anchored)
+        for (int k = 0; k < 2; k++)
+            if (s->bins[k].h_status && s->bins[k].h_status[1]) s->bins[k].grow = true; /* results were right (exact search for the cut lists); the next build gets room */
     const bool task_overflow = s->pending && s->last_was_wavefront && s->last_was_anchored && s->h_counters[6] != 0;
     s->pending = false;
     if (failed) return rtb::fail(RT_ERR_STATE, "rt_render: traversal task pool overflow (BVH deeper than the upload-time bound)");
@@ -837,6 +867,7 @@ int rt_scene_sync(rt_scene* s, rt_stats* stats) {
         /* more (ray, leaf) tasks than the buffer holds: the frame is incomplete. The next render gets a buffer twice the
          * size; a synchronous rt_render repeats the frame by itself. */
         s->task_factor = std::min(s->task_factor * 2, 256);
+        if (getenv("RT_DEBUG_POOL")) fprintf(stderr, "[tasks] buffer overflow, next frames get %d tasks per pixel\n", s->task_factor);
         return rtb::fail(RT_ERR_AGAIN, "rt_render: (ray, leaf) task buffer overflow; render the frame again (buffer doubled to %d tasks per pixel)", s->task_factor);
     }
     return RT_OK;
@@ -973,13 +1004,13 @@ int rt_render(rt_scene* s, const rt_params* p, uint32_t flags, uint8_t* rgb_out,
         if (variant == 2) {
             /* the wide index (rt_layout.h) is the production search structure; the instrumented build counts the reference's
              * own node visits and therefore walks the two-child records, as does RT_WIDE=0 (A/B timing, cross-check) */
-            static const bool env_wide = getenv("RT_WIDE") && atoi(getenv("RT_WIDE")) != 0; /* measured: no faster than the two-child records at 8 blocks per SM (profiles/r01_notes.md); off unless asked for */
-            static const bool env_wide_count = getenv("RT_WIDE_COUNT") != nullptr; /* timeline of the wide kernel: node_visits then counts wide nodes */
+            const bool env_wide = getenv("RT_WIDE") && atoi(getenv("RT_WIDE")) != 0; /* measured: no faster than the two-child records at 8 blocks per SM (profiles/r01_notes.md); off unless asked for */
+            const bool env_wide_count = getenv("RT_WIDE_COUNT") != nullptr; /* timeline of the wide kernel: node_visits then counts wide nodes */
             const bool wide = env_wide && (!count || env_wide_count) && h.n_wide > 0;
             /* anchored rays (rt_bins.cuh): camera rays and shadow rays find their leaves through per-anchor bins and wf_leaves
              * tests the triangles; wf_traverse keeps the rays that start anywhere else (bounces). The instrumented build
              * counts the reference's node visits and therefore searches the tree; RT_ANCHOR=0 does so too (A/B, cross-check). */
-            static const int env_anchor = getenv("RT_ANCHOR") ? atoi(getenv("RT_ANCHOR")) : -1; /* 0 off, 1 on, unset: by mesh size */
+            const int env_anchor = getenv("RT_ANCHOR") ? atoi(getenv("RT_ANCHOR")) : -1; /* 0 off, 1 on, unset: by mesh size */
             /* measured (profiles/r01_configs.md): with millions of leaves a cell lists hundreds of them and one task per candidate
              * loses against the tree search; the bins serve meshes up to 200 k leaves unless asked for */
             bool anchored = (env_anchor > 0 || (env_anchor < 0 && h.n_leaves <= 200000)) && !count && h.has_mesh && h.n_leaves > 0 && segments > 0;

@@ -283,12 +283,16 @@ __device__ __forceinline__ void path_advance(const SceneHeader& h, const WfArgs&
                 /* a camera ray: its candidate leaves come from the camera's bins (rt_bins.cuh) */
                 /* a zero / subnormal / non-finite component is outside the bins' contract: the query is posted without
                  * candidates (cand_count -1) and answered by the exact tree search at the end of the kernel (answer_exact) */
-                const bool exact = outside_contract(u);
+                const bool exact = outside_contract(u) || __ldg(g.bins[0].status) != 0;
                 int c0 = 0, c1 = -1;
                 if (!exact) {
                     const int cell = bins_cell(g.bins[0], u);
                     c0 = __ldg(g.bins[0].cell_start + cell);
                     c1 = __ldg(g.bins[0].cell_start + cell + 1);
+                    if (c1 > g.bins[0].items_cap) { /* a list the build had to cut short */
+                        c0 = 0;
+                        c1 = -1;
+                    }
                 }
                 {
                     if (c1 != c0) {
@@ -409,12 +413,16 @@ __device__ __forceinline__ void path_advance(const SceneHeader& h, const WfArgs&
             }
             if (!blocked && h.has_mesh && g.anchored) {
                 /* a shadow ray: its candidate leaves come from the light's bins */
-                const bool exact = outside_contract(su) || !(D2 <= g.bins[1].max_D2); /* outside the bins' contract: see the camera rays above */
+                const bool exact = outside_contract(su) || !(D2 <= g.bins[1].max_D2) || __ldg(g.bins[1].status) != 0; /* outside the bins' contract: see the camera rays above */
                 int c0 = 0, c1 = -1;
                 if (!exact) {
                     const int cell = bins_cell(g.bins[1], toL);
                     c0 = __ldg(g.bins[1].cell_start + cell);
                     c1 = __ldg(g.bins[1].cell_start + cell + 1);
+                    if (c1 > g.bins[1].items_cap) {
+                        c0 = 0;
+                        c1 = -1;
+                    }
                 }
                 {
                     if (c1 != c0) {
