@@ -94,6 +94,7 @@ struct rt_scene {
         int* status = nullptr;   /* device: [0] a leaf box contains the anchor, [1] the lists outgrew `items` */
         int* h_status = nullptr; /* pinned copy, refreshed by rt_scene_sync */
         bool grow = false;       /* the next build enlarges `items` */
+        rtk::BinsView view;      /* anchor, eps, windows (the pointers are filled in by bins_view) */
     } bins[2];
     void* scan_tmp = nullptr;
     size_t scan_tmp_bytes = 0;
@@ -213,16 +214,65 @@ int ensure_bins(rt_scene* s, int which, const float A[3]) {
     if (b.built && b.mesh_generation == s->mesh_generation && b.R == R && b.A[0] == A[0] && b.A[1] == A[1] && b.A[2] == A[2] && !b.grow) return RT_OK;
     const bool first = !b.built || b.mesh_generation != s->mesh_generation || b.R != R || b.items_cap == 0;
     b.built = false;
-    const size_t n_cells = (size_t)3 * R * R;
+    const float S = std::max(h.box_abs[0], std::max(h.box_abs[1], h.box_abs[2]));
+    const float scale = S + std::max(std::fabs(A[0]), std::max(std::fabs(A[1]), std::fabs(A[2])));
+    b.eps = scale * (1.f / 4096.f);
+    b.max_D2 = (scale * 128.f) * (scale * 128.f);
+    /* the windows: what the root box projects to on every face (bins_face_rect is inclusion-monotone, every leaf box lies in
+     * the root box), one cell of margin, the whole face when the root box contains the anchor */
+    rtk::BinsView& bv = b.view;
+    bv.ax = A[0];
+    bv.ay = A[1];
+    bv.az = A[2];
+    bv.eps = b.eps;
+    bv.max_D2 = b.max_D2;
+    bv.R = R;
+    size_t n_cells = 0;
+    {
+        const float v0[3] = {h.root_mn[0] - b.eps - A[0], h.root_mn[1] - b.eps - A[1], h.root_mn[2] - b.eps - A[2]};
+        const float v1[3] = {h.root_mx[0] + b.eps - A[0], h.root_mx[1] + b.eps - A[1], h.root_mx[2] + b.eps - A[2]};
+        const bool inside = v0[0] <= 0.f && v1[0] >= 0.f && v0[1] <= 0.f && v1[1] >= 0.f && v0[2] <= 0.f && v1[2] >= 0.f;
+        for (int k = 0; k < 3; k++) {
+            int lo_a = R, hi_a = -1, lo_b = R, hi_b = -1;
+            for (int part = 0; part < 2; part++) {
+                int ca0, ca1, cb0, cb1;
+                if (!rtk::bins_face_rect(v0, v1, k, part, R, ca0, ca1, cb0, cb1)) continue;
+                lo_a = std::min(lo_a, ca0);
+                hi_a = std::max(hi_a, ca1);
+                lo_b = std::min(lo_b, cb0);
+                hi_b = std::max(hi_b, cb1);
+            }
+            if (inside) {
+                lo_a = lo_b = 0;
+                hi_a = hi_b = R - 1;
+            }
+            rtk::BinsWindow& w = bv.win[k];
+            if (hi_a < lo_a || hi_b < lo_b) {
+                w.ca0 = w.cb0 = w.wa = w.wb = 0;
+            } else {
+                lo_a = std::max(lo_a - 1, 0);
+                lo_b = std::max(lo_b - 1, 0);
+                hi_a = std::min(hi_a + 1, R - 1);
+                hi_b = std::min(hi_b + 1, R - 1);
+                w.ca0 = lo_a;
+                w.cb0 = lo_b;
+                w.wa = hi_a - lo_a + 1;
+                w.wb = hi_b - lo_b + 1;
+            }
+            w.base = (int)n_cells;
+            n_cells += (size_t)w.wa * w.wb;
+        }
+    }
     if (b.cells_cap < n_cells + 1) {
         CUDA_TRY(cudaStreamSynchronize(s->stream));
         if (b.cell_start) cudaFree(b.cell_start);
         if (b.cursor) cudaFree(b.cursor);
         b.cell_start = b.cursor = nullptr;
         b.cells_cap = 0;
-        CUDA_TRY(cudaMalloc(&b.cell_start, (n_cells + 1) * sizeof(int)));
-        CUDA_TRY(cudaMalloc(&b.cursor, (n_cells + 1) * sizeof(int)));
-        b.cells_cap = n_cells + 1;
+        const size_t cap = (n_cells + 1) + (n_cells + 1) / 2; /* headroom: the windows change with the anchor */
+        CUDA_TRY(cudaMalloc(&b.cell_start, cap * sizeof(int)));
+        CUDA_TRY(cudaMalloc(&b.cursor, cap * sizeof(int)));
+        b.cells_cap = cap;
     }
     if (!b.status) {
         CUDA_TRY(cudaMalloc(&b.status, 4 * sizeof(int)));
@@ -238,15 +288,11 @@ int ensure_bins(rt_scene* s, int which, const float A[3]) {
         b.items_cap = cap;
         b.grow = false;
     }
-    const float S = std::max(h.box_abs[0], std::max(h.box_abs[1], h.box_abs[2]));
-    const float scale = S + std::max(std::fabs(A[0]), std::max(std::fabs(A[1]), std::fabs(A[2])));
-    b.eps = scale * (1.f / 4096.f);
-    b.max_D2 = (scale * 128.f) * (scale * 128.f);
     const float4* leaves = reinterpret_cast<const float4*>(s->blob + h.off_leaves);
-    const int threads = 128, blocks = (h.n_leaves + threads - 1) / threads;
+    const int threads = BINS_GROUP, blocks = h.n_leaves; /* one block per leaf */
     CUDA_TRY(cudaMemsetAsync(b.cell_start, 0, (n_cells + 1) * sizeof(int), s->stream));
     CUDA_TRY(cudaMemsetAsync(b.status, 0, 4 * sizeof(int), s->stream));
-    rtk::bins_count<<<blocks, threads, 0, s->stream>>>(leaves, h.n_leaves, A[0], A[1], A[2], b.eps, R, b.cell_start, b.status);
+    rtk::bins_count<<<blocks, threads, 0, s->stream>>>(leaves, h.n_leaves, bv, b.cell_start, b.status);
     CUDA_TRY(cudaGetLastError());
     size_t tmp_bytes = 0;
     CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, b.cell_start, b.cell_start, (int)(n_cells + 1), s->stream));
@@ -274,8 +320,7 @@ int ensure_bins(rt_scene* s, int which, const float A[3]) {
         }
     }
     CUDA_TRY(cudaMemcpyAsync(b.cursor, b.cell_start, (n_cells + 1) * sizeof(int), cudaMemcpyDeviceToDevice, s->stream));
-    rtk::bins_fill<<<blocks, threads, 0, s->stream>>>(leaves, h.n_leaves, A[0], A[1], A[2], b.eps, R, b.cursor, b.items,
-                                                      (int)std::min<size_t>(b.items_cap, 0x7fffffff), b.status);
+    rtk::bins_fill<<<blocks, threads, 0, s->stream>>>(leaves, h.n_leaves, bv, b.cursor, b.items, (int)std::min<size_t>(b.items_cap, 0x7fffffff), b.status);
     CUDA_TRY(cudaGetLastError());
     b.R = R;
     b.A[0] = A[0];
@@ -289,13 +334,7 @@ int ensure_bins(rt_scene* s, int which, const float A[3]) {
 }
 
 rtk::BinsView bins_view(const rt_scene::AnchorBins& b) {
-    rtk::BinsView v;
-    v.ax = b.A[0];
-    v.ay = b.A[1];
-    v.az = b.A[2];
-    v.eps = b.eps;
-    v.max_D2 = b.max_D2;
-    v.R = b.R;
+    rtk::BinsView v = b.view;
     v.cell_start = b.cell_start;
     v.items = b.items;
     v.items_cap = (int)std::min<size_t>(b.items_cap, 0x7fffffff);

@@ -287,11 +287,14 @@ __device__ __forceinline__ void path_advance(const SceneHeader& h, const WfArgs&
                 int c0 = 0, c1 = -1;
                 if (!exact) {
                     const int cell = bins_cell(g.bins[0], u);
-                    c0 = __ldg(g.bins[0].cell_start + cell);
-                    c1 = __ldg(g.bins[0].cell_start + cell + 1);
-                    if (c1 > g.bins[0].items_cap) { /* a list the build had to cut short */
-                        c0 = 0;
-                        c1 = -1;
+                    c1 = 0; /* outside the windows: no candidate */
+                    if (cell >= 0) {
+                        c0 = __ldg(g.bins[0].cell_start + cell);
+                        c1 = __ldg(g.bins[0].cell_start + cell + 1);
+                        if (c1 > g.bins[0].items_cap) { /* a list the build had to cut short */
+                            c0 = 0;
+                            c1 = -1;
+                        }
                     }
                 }
                 {
@@ -417,11 +420,14 @@ __device__ __forceinline__ void path_advance(const SceneHeader& h, const WfArgs&
                 int c0 = 0, c1 = -1;
                 if (!exact) {
                     const int cell = bins_cell(g.bins[1], toL);
-                    c0 = __ldg(g.bins[1].cell_start + cell);
-                    c1 = __ldg(g.bins[1].cell_start + cell + 1);
-                    if (c1 > g.bins[1].items_cap) {
-                        c0 = 0;
-                        c1 = -1;
+                    c1 = 0;
+                    if (cell >= 0) {
+                        c0 = __ldg(g.bins[1].cell_start + cell);
+                        c1 = __ldg(g.bins[1].cell_start + cell + 1);
+                        if (c1 > g.bins[1].items_cap) {
+                            c0 = 0;
+                            c1 = -1;
+                        }
                     }
                 }
                 {
