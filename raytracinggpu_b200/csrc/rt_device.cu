@@ -78,6 +78,8 @@ struct rt_scene {
     size_t st_buf_bytes = 0;
     int* wf_spill = nullptr;  /* node-pool overflow area of wf_traverse */
     bool trav_wide = false;
+    unsigned char* stage = nullptr; /* rt_scene_set_mesh: device staging of the interchange arrays */
+    size_t stage_bytes = 0;
     uint64_t mesh_generation = 0; /* bumped whenever the mesh part of the blob changes: invalidates the anchored-ray bins */
     /* anchored-ray bins (rt_bins.cuh): [0] camera, [1] light */
     struct AnchorBins {
@@ -94,6 +96,7 @@ struct rt_scene {
         int* status = nullptr;   /* device: [0] a leaf box contains the anchor, [1] the lists outgrew `items` */
         int* h_status = nullptr; /* pinned copy, refreshed by rt_scene_sync */
         bool grow = false;       /* the next build enlarges `items` */
+        int n_leaves = -1;       /* leaves of the mesh the item buffer was sized for */
         rtk::BinsView view;      /* anchor, eps, windows (the pointers are filled in by bins_view) */
     } bins[2];
     void* scan_tmp = nullptr;
@@ -212,7 +215,9 @@ int ensure_bins(rt_scene* s, int which, const float A[3]) {
     }
     const int R = env_R > 0 ? std::min(std::max(env_R, 8), 4096) : (h.n_leaves > 200000 ? 2048 : 1024);
     if (b.built && b.mesh_generation == s->mesh_generation && b.R == R && b.A[0] == A[0] && b.A[1] == A[1] && b.A[2] == A[2] && !b.grow) return RT_OK;
-    const bool first = !b.built || b.mesh_generation != s->mesh_generation || b.R != R || b.items_cap == 0;
+    /* the item buffer is sized by a read-back only when nothing is known about the lists: first build, or a mesh with a
+     * different number of leaves; a mesh uploaded again (the per-frame upload of a caller that owns the geometry) keeps it */
+    const bool first = b.R != R || b.items_cap == 0 || b.n_leaves != h.n_leaves;
     b.built = false;
     const float S = std::max(h.box_abs[0], std::max(h.box_abs[1], h.box_abs[2]));
     const float scale = S + std::max(std::fabs(A[0]), std::max(std::fabs(A[1]), std::fabs(A[2])));
@@ -327,6 +332,7 @@ int ensure_bins(rt_scene* s, int which, const float A[3]) {
     b.A[1] = A[1];
     b.A[2] = A[2];
     b.mesh_generation = s->mesh_generation;
+    b.n_leaves = h.n_leaves;
     b.built = true;
     b.usable = true;
     s->bins_builds++;
@@ -410,6 +416,7 @@ void rt_scene_destroy(rt_scene* s) {
     if (s->wf_counters) cudaFree(s->wf_counters);
     if (s->dbg_warps) cudaFree(s->dbg_warps);
     if (s->wf_spill) cudaFree(s->wf_spill);
+    if (s->stage) cudaFree(s->stage);
     for (int k = 0; k < 2; k++) {
         if (s->bins[k].cell_start) cudaFree(s->bins[k].cell_start);
         if (s->bins[k].cursor) cudaFree(s->bins[k].cursor);
@@ -724,12 +731,21 @@ int rt_scene_set_mesh(rt_scene* s, const float* vertices, int32_t nv, const int3
         CUDA_TRY(cudaMalloc(&s->blob, total));
         s->blob_bytes = total;
     }
-    /* staging of the interchange arrays (freed after the repack) */
-    float* d_vertices = nullptr;
-    int32_t* d_recs = nullptr;
+    /* staging of the interchange arrays: one grow-only device buffer kept with the scene (a mesh that is uploaded again
+     * every frame pays no allocation) */
     const size_t vbytes = (size_t)nv * 3 * sizeof(float), rbytes = (size_t)nt * RT_TRI_RECORD_WORDS * sizeof(int32_t);
-    CUDA_TRY(cudaMalloc(&d_vertices, vbytes));
-    cudaError_t err = cudaMalloc(&d_recs, rbytes);
+    const size_t v_off = 0, r_off = (vbytes + 255) & ~(size_t)255, l_off = (r_off + rbytes + 255) & ~(size_t)255;
+    const size_t stage_need = l_off + (size_t)nt * sizeof(int32_t);
+    if (s->stage_bytes < stage_need) {
+        if (s->stage) cudaFree(s->stage);
+        s->stage = nullptr;
+        s->stage_bytes = 0;
+        CUDA_TRY(cudaMalloc(&s->stage, stage_need + stage_need / 4));
+        s->stage_bytes = stage_need + stage_need / 4;
+    }
+    float* d_vertices = reinterpret_cast<float*>(s->stage + v_off);
+    int32_t* d_recs = reinterpret_cast<int32_t*>(s->stage + r_off);
+    cudaError_t err = cudaSuccess;
     if (err == cudaSuccess) err = cudaMemcpyAsync(d_vertices, vertices, vbytes, cudaMemcpyHostToDevice, s->stream);
     if (err == cudaSuccess) err = cudaMemcpyAsync(d_recs, tri_records, rbytes, cudaMemcpyHostToDevice, s->stream);
     if (err == cudaSuccess && n_inner > 0)
@@ -738,18 +754,14 @@ int rt_scene_set_mesh(rt_scene* s, const float* vertices, int32_t nv, const int3
         err = cudaMemcpyAsync(s->blob + off_wide, wide.data(), (size_t)n_wide * RT_WNODE_BYTES, cudaMemcpyHostToDevice, s->stream);
     if (err == cudaSuccess && n_leafrecs > 0)
         err = cudaMemcpyAsync(s->blob + off_leaves, leaf_table.data(), (size_t)n_leafrecs * RT_LEAFREC_BYTES, cudaMemcpyHostToDevice, s->stream);
-    int32_t* d_leaf_start = nullptr;
-    if (err == cudaSuccess) err = cudaMalloc(&d_leaf_start, (size_t)nt * sizeof(int32_t));
+    int32_t* d_leaf_start = reinterpret_cast<int32_t*>(s->stage + l_off);
     if (err == cudaSuccess) err = cudaMemcpyAsync(d_leaf_start, leaf_start_of_tri.data(), (size_t)nt * sizeof(int32_t), cudaMemcpyHostToDevice, s->stream);
     if (err == cudaSuccess) {
         const int threads = 256, blocks = (nt + threads - 1) / threads;
         rtk::repack_triangles<<<blocks, threads, 0, s->stream>>>(d_vertices, d_recs, nt, d_leaf_start, reinterpret_cast<float4*>(s->blob + off_tris));
         err = cudaGetLastError();
     }
-    if (err == cudaSuccess) err = cudaStreamSynchronize(s->stream);
-    cudaFree(d_vertices);
-    if (d_recs) cudaFree(d_recs);
-    if (d_leaf_start) cudaFree(d_leaf_start);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(s->stream); /* the host vectors above go out of scope */
     if (err != cudaSuccess) return rtb::fail(RT_ERR_CUDA, "rt_scene_set_mesh: %s", cudaGetErrorString(err));
 
     h.has_mesh = 1;
@@ -1229,8 +1241,13 @@ int rt_render(rt_scene* s, const rt_params* p, uint32_t flags, uint8_t* rgb_out,
                 static const int env_lb = getenv("RT_LEAVES_BLOCKS") ? atoi(getenv("RT_LEAVES_BLOCKS")) : 0;
                 const unsigned leaves_grid = (unsigned)(s->sm_count * (env_lb > 0 ? env_lb : std::max(s->leaves_blocks_per_sm, 1)));
                 const unsigned wtiles = (unsigned)((p->W + 7) / 8) * (unsigned)((srows + 3) / 4);
-                const unsigned gen_grid = (wtiles + (WF_THREADS / 32) - 1) / (WF_THREADS / 32);
-                const unsigned shade_grid = (unsigned)std::min<size_t>((spx + WF_THREADS - 1) / WF_THREADS, (size_t)s->sm_count * 16);
+                unsigned gen_grid = (wtiles + (WF_THREADS / 32) - 1) / (WF_THREADS / 32);
+                unsigned shade_grid = (unsigned)std::min<size_t>((spx + WF_THREADS - 1) / WF_THREADS, (size_t)s->sm_count * 16);
+                {   /* blocks per SM of the streaming kernels (experiment knobs: co-residency of the bands' kernels) */
+                    const int gb = getenv("RT_GEN_BLOCKS") ? atoi(getenv("RT_GEN_BLOCKS")) : 0, sb = getenv("RT_SHADE_BLOCKS") ? atoi(getenv("RT_SHADE_BLOCKS")) : 0;
+                    if (gb > 0) gen_grid = std::min(gen_grid, (unsigned)(s->sm_count * gb));
+                    if (sb > 0) shade_grid = std::min(shade_grid, (unsigned)(s->sm_count * sb));
+                }
                 g.stoch = stochastic ? 1 : 0;
                 g.sample = 0;
                 g.last_sample = 1;

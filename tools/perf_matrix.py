@@ -18,6 +18,7 @@ def timeit(sc, p, n=20):
 sc = scenes.upload(rt.Scene(0), scenes.cat_scene("optimized"))
 print("configs[1] deterministic 1080p      median %.4f  min %.4f" % timeit(sc, profiles.params("optimized", 1920, 1080, 1, 1), 40))
 p = profiles.params("optimized", 1920, 1080, 4, 3); p.aa_sigma, p.indirect = 0.2, 1
+if len(sys.argv) > 1 and sys.argv[1] == "det": sys.exit(0)
 print("stochastic 4 3 1080p                median %.4f  min %.4f" % timeit(sc, p, 8))
 scenes.upload(sc, scenes.cat_scene("optimized", mirror=1))
 print("configs[2] mirror 4K depth 4        median %.4f  min %.4f" % timeit(sc, profiles.params("optimized", 3840, 2160, 1, 4), 10))
