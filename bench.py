@@ -6,8 +6,10 @@
 
 Workload (N = 1): BASELINE.json configs[1] — cadnav cat TriangleMesh with the array BVH + six wall spheres,
 1920x1080, 1 sample/pixel, primary + shadow rays (4,147,200 rays/frame), optimized.cu knobs. A "step" is one
-frame. For N > 1 the path shards by frame (BASELINE.json configs[3] style): every rank renders its own frames
-of a light-orbit animation of the same scene, no data-path collective ("scaling": "weak").
+frame. For N > 1 the path shards by frame: every rank renders its own frames of the SAME workload (frame-parallel,
+no data-path collective, "scaling": "weak"), so that the per-N values are comparable; the frames of a light-orbit
+animation (BASELINE.json configs[3] style: the light's candidate bins are rebuilt every frame) and whole 4K depth-4
+frames rendered frame-parallel are reported beside the headline (`animation_light_orbit`, `frames_4k_depth4`).
 
 `value` times the render kernels with the scene resident in HBM (CUDA events on the launching stream, L2
 flushed between steps). `e2e` goes through the C ABI with HOST buffers: every step re-uploads the mesh in the
@@ -149,10 +151,11 @@ def run_ours(args):
         sc.set_mesh(verts, recs, bvh, id=mesh_id)
     p = rt.params_profile("optimized", W, H, 1, 1)
 
-    # frame-parallel for N > 1: rank r renders frames r, r+N, ... of a one-revolution light orbit
+    # frame-parallel for N > 1: rank r renders frames r, r+N, ... of a sequence whose frames are all configs[1] (static scene):
+    # the same per-GPU work at every N. The light-orbit animation is timed separately below.
     n_frames = (args.warmup + args.steps) * world
     omega = 2 * np.pi / (240 * 0.02)
-    lights = rt.sharding.light_positions((-10.0, 20.0, 40.0), n_frames, omega, 0.02, rt.move_light) if world > 1 else [(-10.0, 20.0, 40.0)] * n_frames
+    lights = [(-10.0, 20.0, 40.0)] * n_frames
 
     rgb = torch.empty((H, W, 3), dtype=torch.uint8, device="cuda")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
@@ -223,9 +226,44 @@ def run_ours(args):
     h2d = int(verts.nbytes + recs.nbytes + bvh.nbytes)
     d2h = int(H * W * 3)
 
+    # ---- extra lines: frames of a one-revolution light orbit (the light's bins are rebuilt every frame) and
+    # whole 4K depth-4 frames, both frame-parallel over the ranks, device-timed, max over ranks
+    def frame_parallel(params, frames, light_of):
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(frames)]
+        buf = torch.empty((params.H, params.W, 3), dtype=torch.uint8, device="cuda")
+        rays_f = 0
+        for i in range(3 + frames):
+            sc.set_light(light_of(i), 3e10)
+            with torch.cuda.stream(stream):
+                flush.zero_()
+                if i >= 3:
+                    evs[i - 3][0].record(stream)
+                sc.render_into(params, rgb=buf, flags=rt.RT_RENDER_NO_SYNC)
+                if i >= 3:
+                    evs[i - 3][1].record(stream)
+            if i == 2:
+                sc.sync()  # end of the warm-up: lets the library enlarge buffers the first frames found too small
+        rays_f = int(sc.sync().rays)
+        torch.cuda.synchronize()
+        ms = float(sum(a.elapsed_time(b) for a, b in evs))
+        if world > 1:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return {"ms_per_frame_per_gpu": round(ms / frames, 4), "rays_per_frame": rays_f, "frames_per_gpu": frames,
+                "mrays_per_s": round(rays_f * frames * world / (ms * 1e-3) / 1e6, 1), "scaling": "weak"}
+
+    orbit = rt.sharding.light_positions((-10.0, 20.0, 40.0), (3 + 20) * world, omega, 0.02, rt.move_light)
+    animation = frame_parallel(p, 20, lambda i: orbit[i * world + rank])
+    animation["workload"] = "configs[1] scene, light on a one-revolution orbit, frame f on rank f mod N (light bins rebuilt every frame)"
+    sc.set_light((-10.0, 20.0, 40.0), 3e10)
+
     work = sc.render(p, want=("rgb",), count_work=True)["stats"]  # instrumented pass for the roofline, not timed
     like_for_like = stochastic_vs_reference_kernel(rt, torch, sc) if (world == 1 and rank == 0) else None
     sharded = sharded_single_frame(rt, torch, sc, stream, world, rank, verts, recs, bvh, mesh_id, walls)
+    # after sharded_single_frame every rank holds the mirror-cat scene: whole 4K depth-4 frames, one per rank at a time
+    frames_4k = frame_parallel(rt.params_profile("optimized", 3840, 2160, 1, 4), 6, lambda i: (-10.0, 20.0, 40.0))
+    frames_4k["workload"] = "BASELINE.json configs[2] frames (mirror cat 3840x2160, reflection depth 4), whole frames, frame-parallel over the ranks"
 
     if rank != 0:
         if world > 1:
@@ -258,13 +296,13 @@ def run_ours(args):
            "ms_per_step": round(ms_per_step, 5), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
            "data": "synthetic",
            "config": {"workload": "BASELINE.json configs[1]: %s + 6 wall spheres, 1920x1080, 1 spp, primary+shadow rays, optimized.cu knobs" % mesh_name,
-                      "rays_per_frame": rays_per_frame, "frames_per_step_per_gpu": 1, "sharding": "frame-parallel (light-orbit animation)" if world > 1 else "single GPU",
+                      "rays_per_frame": rays_per_frame, "frames_per_step_per_gpu": 1, "sharding": "frame-parallel (every rank renders its own frames of this workload)" if world > 1 else "single GPU",
                       "l2": "256 MB memset between steps, outside the event pair", "timed_wall_s": round(wall_s, 4)},
            "e2e": {"value": round(e2e_value, 2), "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": round(e2e_s / e2e_steps * 1e3, 4),
                    "steps": e2e_steps},
            "gpu_launches": launches_per_step * args.steps, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
            "ms_per_frame": round(kernel_ms, 5), "scene_broadcast_bytes": blob_bytes, "single_frame_sharded": sharded,
-           "stochastic_vs_reference_gpu_kernel": like_for_like}
+           "animation_light_orbit": animation, "frames_4k_depth4": frames_4k, "stochastic_vs_reference_gpu_kernel": like_for_like}
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

@@ -150,14 +150,16 @@ __global__ void bins_count(const float4* __restrict__ leaves, int n_leaves, cons
     if (!bins_leaf_cells(q0, q1, bv, threadIdx.x % BINS_GROUP, BINS_GROUP, [&](int cell) { atomicAdd(counts + cell, 1); })) status[0] = 1;
 }
 
-/* pass 2 (after the exclusive scan of counts into cell_start): fill the lists; cursor starts as a copy of cell_start */
-__global__ void bins_fill(const float4* __restrict__ leaves, int n_leaves, const BinsView bv, int* __restrict__ cursor, int* __restrict__ items, int items_cap,
-                          int* __restrict__ status) {
+/* pass 2 (after the exclusive scan of counts into cell_start): fill the lists. A leaf takes the slot
+ * cell_start[cell] + (what is left of the cell's count) - 1, counting the counts back down to zero: the count array needs
+ * no clearing before the next build. */
+__global__ void bins_fill(const float4* __restrict__ leaves, int n_leaves, const BinsView bv, const int* __restrict__ cell_start, int* __restrict__ counts,
+                          int* __restrict__ items, int items_cap, int* __restrict__ status) {
     const int l = (blockIdx.x * blockDim.x + threadIdx.x) / BINS_GROUP;
     if (l >= n_leaves) return;
     const float4 q0 = leaves[2 * (size_t)l], q1 = leaves[2 * (size_t)l + 1];
     bins_leaf_cells(q0, q1, bv, threadIdx.x % BINS_GROUP, BINS_GROUP, [&](int cell) {
-        const int at = atomicAdd(cursor + cell, 1);
+        const int at = cell_start[cell] + atomicSub(counts + cell, 1) - 1;
         if (at < items_cap) items[at] = l;
         else status[1] = 1; /* the lists outgrew the buffer (the anchor moved): rays of the cut lists take the exact search, the host enlarges it */
     });

@@ -277,6 +277,7 @@ int ensure_bins(rt_scene* s, int which, const float A[3]) {
         const size_t cap = (n_cells + 1) + (n_cells + 1) / 2; /* headroom: the windows change with the anchor */
         CUDA_TRY(cudaMalloc(&b.cell_start, cap * sizeof(int)));
         CUDA_TRY(cudaMalloc(&b.cursor, cap * sizeof(int)));
+        CUDA_TRY(cudaMemsetAsync(b.cursor, 0, cap * sizeof(int), s->stream)); /* the per-cell counts: every build leaves them at zero again */
         b.cells_cap = cap;
     }
     if (!b.status) {
@@ -295,27 +296,26 @@ int ensure_bins(rt_scene* s, int which, const float A[3]) {
     }
     const float4* leaves = reinterpret_cast<const float4*>(s->blob + h.off_leaves);
     const int threads = BINS_GROUP, blocks = h.n_leaves; /* one block per leaf */
-    CUDA_TRY(cudaMemsetAsync(b.cell_start, 0, (n_cells + 1) * sizeof(int), s->stream));
     CUDA_TRY(cudaMemsetAsync(b.status, 0, 4 * sizeof(int), s->stream));
-    rtk::bins_count<<<blocks, threads, 0, s->stream>>>(leaves, h.n_leaves, bv, b.cell_start, b.status);
+    rtk::bins_count<<<blocks, threads, 0, s->stream>>>(leaves, h.n_leaves, bv, b.cursor, b.status);
     CUDA_TRY(cudaGetLastError());
     size_t tmp_bytes = 0;
-    CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, b.cell_start, b.cell_start, (int)(n_cells + 1), s->stream));
+    CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, b.cursor, b.cell_start, (int)(n_cells + 1), s->stream));
     if (s->scan_tmp_bytes < tmp_bytes) {
         CUDA_TRY(cudaStreamSynchronize(s->stream));
         if (s->scan_tmp) cudaFree(s->scan_tmp);
         s->scan_tmp = nullptr;
         s->scan_tmp_bytes = 0;
-        CUDA_TRY(cudaMalloc(&s->scan_tmp, tmp_bytes));
-        s->scan_tmp_bytes = tmp_bytes;
+        CUDA_TRY(cudaMalloc(&s->scan_tmp, 2 * tmp_bytes + 4096)); /* the windows, and with them the scan's work space, change with the anchor */
+        s->scan_tmp_bytes = 2 * tmp_bytes + 4096;
     }
-    CUDA_TRY(cub::DeviceScan::ExclusiveSum(s->scan_tmp, tmp_bytes, b.cell_start, b.cell_start, (int)(n_cells + 1), s->stream));
+    CUDA_TRY(cub::DeviceScan::ExclusiveSum(s->scan_tmp, tmp_bytes, b.cursor, b.cell_start, (int)(n_cells + 1), s->stream));
     if (first) {
         int total = 0;
         CUDA_TRY(cudaMemcpyAsync(&total, b.cell_start + n_cells, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
         CUDA_TRY(cudaStreamSynchronize(s->stream));
         if (total < 0) return rtb::fail(RT_ERR_UNSUPPORTED, "rt_render: candidate lists of %d cells overflow 2^31 entries", (int)n_cells);
-        const size_t cap = (size_t)total + (size_t)total / 4 + 1024;
+        const size_t cap = 2 * (size_t)total + 1024; /* room for the lists of a moving anchor */
         if (b.items_cap < cap) {
             if (b.items) cudaFree(b.items);
             b.items = nullptr;
@@ -324,8 +324,7 @@ int ensure_bins(rt_scene* s, int which, const float A[3]) {
             b.items_cap = cap;
         }
     }
-    CUDA_TRY(cudaMemcpyAsync(b.cursor, b.cell_start, (n_cells + 1) * sizeof(int), cudaMemcpyDeviceToDevice, s->stream));
-    rtk::bins_fill<<<blocks, threads, 0, s->stream>>>(leaves, h.n_leaves, bv, b.cursor, b.items, (int)std::min<size_t>(b.items_cap, 0x7fffffff), b.status);
+    rtk::bins_fill<<<blocks, threads, 0, s->stream>>>(leaves, h.n_leaves, bv, b.cell_start, b.cursor, b.items, (int)std::min<size_t>(b.items_cap, 0x7fffffff), b.status);
     CUDA_TRY(cudaGetLastError());
     b.R = R;
     b.A[0] = A[0];

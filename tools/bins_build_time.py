@@ -18,3 +18,24 @@ def run(move, n=40):
     return float(np.median(ms))
 print("fixed light  %.4f ms/frame" % run(False))
 print("moving light %.4f ms/frame (light bins rebuilt every frame)" % run(True))
+
+# the bench's way: frames enqueued without synchronising, L2 flushed between frames, one event pair per frame
+flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+stream = torch.cuda.Stream(); sc.set_stream(stream.cuda_stream)
+def run_async(move, do_flush, n=30):
+    L = (-10.0, 20.0, 40.0)
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
+    for i in range(n + 5):
+        if move: L = rt.move_light(L, 1.309, 0.02)
+        sc.set_light(L, 3e10)
+        with torch.cuda.stream(stream):
+            if do_flush: flush.zero_()
+            if i >= 5: evs[i - 5][0].record(stream)
+            sc.render_into(p, rgb=dev, flags=rt.RT_RENDER_NO_SYNC)
+            if i >= 5: evs[i - 5][1].record(stream)
+    sc.sync(); torch.cuda.synchronize()
+    ms = sorted(a.elapsed_time(b) for a, b in evs)
+    return ms[len(ms) // 2], ms[-1], sum(ms) / len(ms)
+for move in (False, True):
+    for fl in (False, True):
+        print("enqueued, move %d flush %d: median %.4f max %.4f mean %.4f ms" % ((move, fl) + run_async(move, fl)))
