@@ -214,10 +214,17 @@ int ensure_bins(rt_scene* s, int which, const float A[3]) {
         s->task_factor_from_env = true;
     }
     const int R = env_R > 0 ? std::min(std::max(env_R, 8), 4096) : (h.n_leaves > 200000 ? 2048 : 1024);
+    /* the status word of the previous build is copied to pinned memory right behind the build (no synchronisation): by the
+     * time the anchor moves again it tells whether the lists outgrew the item buffer */
+    if (b.h_status && b.h_status[1]) {
+        b.grow = true;
+        b.h_status[1] = 0;
+    }
     if (b.built && b.mesh_generation == s->mesh_generation && b.R == R && b.A[0] == A[0] && b.A[1] == A[1] && b.A[2] == A[2] && !b.grow) return RT_OK;
     /* the item buffer is sized by a read-back only when nothing is known about the lists: first build, or a mesh with a
      * different number of leaves; a mesh uploaded again (the per-frame upload of a caller that owns the geometry) keeps it */
     const bool first = b.R != R || b.items_cap == 0 || b.n_leaves != h.n_leaves;
+    static const bool dbg_bins = getenv("RT_DEBUG_BINS") != nullptr;
     b.built = false;
     const float S = std::max(h.box_abs[0], std::max(h.box_abs[1], h.box_abs[2]));
     const float scale = S + std::max(std::fabs(A[0]), std::max(std::fabs(A[1]), std::fabs(A[2])));
@@ -274,7 +281,7 @@ int ensure_bins(rt_scene* s, int which, const float A[3]) {
         if (b.cursor) cudaFree(b.cursor);
         b.cell_start = b.cursor = nullptr;
         b.cells_cap = 0;
-        const size_t cap = (n_cells + 1) + (n_cells + 1) / 2; /* headroom: the windows change with the anchor */
+        const size_t cap = 2 * (n_cells + 1); /* headroom: the windows change with the anchor */
         CUDA_TRY(cudaMalloc(&b.cell_start, cap * sizeof(int)));
         CUDA_TRY(cudaMalloc(&b.cursor, cap * sizeof(int)));
         CUDA_TRY(cudaMemsetAsync(b.cursor, 0, cap * sizeof(int), s->stream)); /* the per-cell counts: every build leaves them at zero again */
@@ -283,7 +290,9 @@ int ensure_bins(rt_scene* s, int which, const float A[3]) {
     if (!b.status) {
         CUDA_TRY(cudaMalloc(&b.status, 4 * sizeof(int)));
         CUDA_TRY(cudaMallocHost(&b.h_status, 4 * sizeof(int)));
+        memset(b.h_status, 0, 4 * sizeof(int));
     }
+    if (dbg_bins) fprintf(stderr, "[bins %d] build #%d first %d grow %d cells %zu (cap %zu) items cap %zu\n", which, s->bins_builds, (int)first, (int)b.grow, n_cells, b.cells_cap, b.items_cap);
     if (b.grow) { /* the previous build outgrew the buffer (noticed by rt_scene_sync) */
         CUDA_TRY(cudaStreamSynchronize(s->stream));
         if (b.items) cudaFree(b.items);
@@ -315,7 +324,7 @@ int ensure_bins(rt_scene* s, int which, const float A[3]) {
         CUDA_TRY(cudaMemcpyAsync(&total, b.cell_start + n_cells, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
         CUDA_TRY(cudaStreamSynchronize(s->stream));
         if (total < 0) return rtb::fail(RT_ERR_UNSUPPORTED, "rt_render: candidate lists of %d cells overflow 2^31 entries", (int)n_cells);
-        const size_t cap = 2 * (size_t)total + 1024; /* room for the lists of a moving anchor */
+        const size_t cap = 3 * (size_t)total + 1024; /* room for the lists of a moving anchor */
         if (b.items_cap < cap) {
             if (b.items) cudaFree(b.items);
             b.items = nullptr;
@@ -326,6 +335,7 @@ int ensure_bins(rt_scene* s, int which, const float A[3]) {
     }
     rtk::bins_fill<<<blocks, threads, 0, s->stream>>>(leaves, h.n_leaves, bv, b.cell_start, b.cursor, b.items, (int)std::min<size_t>(b.items_cap, 0x7fffffff), b.status);
     CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(b.h_status, b.status, 4 * sizeof(int), cudaMemcpyDeviceToHost, s->stream)); /* read at the next build, never waited for */
     b.R = R;
     b.A[0] = A[0];
     b.A[1] = A[1];
