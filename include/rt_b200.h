@@ -128,6 +128,10 @@ int rt_mesh_instance(rt_mesh* m, int32_t copies, const float* scales, const floa
 /* compute_bbox + buildBVH + bvhTreeToArray (optimized.cu:466-534, called at :809-813):
  * reorders the triangle records in place and produces the 10-float array BVH. */
 int rt_mesh_build_bvh(rt_mesh* m);
+/* The same builder on CUDA device `device`, a whole tree level at a time (csrc/rt_bvh_build.cuh): the identical arr_bvh
+ * and triangle order (the reference builds on the host, optimized.cu:806-813, or in one device thread,
+ * global_launcher.cu:298-331). build_ms (may be NULL): device time of the build without the transfers. */
+int rt_mesh_build_bvh_gpu(rt_mesh* m, int device, double* build_ms);
 int rt_mesh_counts(const rt_mesh* m, int32_t* nv, int32_t* nt, int32_t* n_nodes);
 const float* rt_mesh_vertices(const rt_mesh* m);          /* nv*3 */
 const int32_t* rt_mesh_tri_records(const rt_mesh* m);     /* nt*RT_TRI_RECORD_WORDS, post-build order */

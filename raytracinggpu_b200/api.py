@@ -29,6 +29,7 @@ SIGNATURES = {
     "rt_mesh_rescale": (C.c_int, [_vp, _f, _pf]),
     "rt_mesh_instance": (C.c_int, [_vp, _i32, _vp, _vp]),
     "rt_mesh_build_bvh": (C.c_int, [_vp]),
+    "rt_mesh_build_bvh_gpu": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_double)]),
     "rt_mesh_counts": (C.c_int, [_vp, _pi32, _pi32, _pi32]),
     "rt_mesh_vertices": (_vp, [_vp]),
     "rt_mesh_tri_records": (_vp, [_vp]),
@@ -173,6 +174,13 @@ class Mesh:
 
     def build_bvh(self):
         _check(lib().rt_mesh_build_bvh(self._h))
+        return self
+
+    def build_bvh_gpu(self, device=0):
+        """The reference's builder on the device (identical tree); self.build_ms = device time of the build."""
+        ms = C.c_double()
+        _check(lib().rt_mesh_build_bvh_gpu(self._h, int(device), C.byref(ms)))
+        self.build_ms = ms.value
         return self
 
     def counts(self):

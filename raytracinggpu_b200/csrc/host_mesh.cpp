@@ -294,6 +294,30 @@ int rt_mesh_build_bvh(rt_mesh* m) {
     return build_bvh(m);
 }
 
+int rt_mesh_build_bvh_gpu(rt_mesh* m, int device, double* build_ms) {
+    if (!m) return rtb::fail(RT_ERR_INVALID, "rt_mesh_build_bvh_gpu: NULL mesh");
+    const int32_t nt = (int32_t)m->tris.size(), nv = (int32_t)m->vertices.size();
+    if (build_ms) *build_ms = 0.;
+    if (nt < 2) return build_bvh(m); /* nothing to do in parallel */
+    if (nt >= (1 << 24)) return rtb::fail(RT_ERR_UNSUPPORTED, "rt_mesh_build_bvh_gpu: %d triangles do not fit the float-encoded array BVH (2^24)", nt);
+    std::vector<int32_t> idx((size_t)nt * 3), perm;
+    for (int32_t i = 0; i < nt; i++)
+        for (int k = 0; k < 3; k++) idx[(size_t)3 * i + k] = m->tris[i].w[k];
+    std::vector<float> arr;
+    int32_t info[4] = {0, 0, 0, 0};
+    const int rc = rtb::bvh_build_device(device, &m->vertices[0].x, nv, idx.data(), nt, &perm, &arr, info, build_ms);
+    if (rc != 0) return rtb::fail(RT_ERR_CUDA, "rt_mesh_build_bvh_gpu: CUDA error %d (this library has no CPU fallback for the device builder; rt_mesh_build_bvh is the host builder)", rc);
+    std::vector<TriRecord> sorted((size_t)nt);
+    for (int32_t i = 0; i < nt; i++) sorted[i] = m->tris[perm[i]];
+    m->tris.swap(sorted);
+    m->arr_bvh.swap(arr);
+    m->n_nodes = info[0];
+    m->n_leaves = info[1];
+    m->max_depth = info[2];
+    m->max_leaf = info[3];
+    return RT_OK;
+}
+
 int rt_mesh_counts(const rt_mesh* m, int32_t* nv, int32_t* nt, int32_t* n_nodes) {
     if (!m) return rtb::fail(RT_ERR_INVALID, "rt_mesh_counts: NULL mesh");
     if (nv) *nv = (int32_t)m->vertices.size();

@@ -13,6 +13,7 @@
 #include <cub/cub.cuh>
 #include "rt_wavefront.cuh"
 #include "rt_stochastic.cuh"
+#include "rt_bvh_build.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -358,6 +359,13 @@ rtk::BinsView bins_view(const rt_scene::AnchorBins& b) {
 }
 
 } // namespace
+
+namespace rtb {
+int bvh_build_device(int device, const float* vertices, int nv, const int32_t* idx3, int nt, std::vector<int32_t>* perm, std::vector<float>* arr, int32_t info[4],
+                     double* build_ms) {
+    return rtbuild::build(device, vertices, nv, idx3, nt, *perm, *arr, info, build_ms);
+}
+} // namespace rtb
 
 extern "C" {
 
