@@ -258,6 +258,20 @@ def run_ours(args):
     animation["workload"] = "configs[1] scene, light on a one-revolution orbit, frame f on rank f mod N (light bins rebuilt every frame)"
     sc.set_light((-10.0, 20.0, 40.0), 3e10)
 
+    # ---- extra line: the reference's BVH builder, host vs device, on the bench mesh
+    bvh_build = None
+    if rank == 0:
+        cat = find_cat()
+        if cat:
+            def fresh():
+                return rt.Mesh.read_obj(cat).rescale(0.6, (0.0, -4.0, 0.0))
+            fresh().build_bvh_gpu(local)  # warm-up
+            t0 = time.perf_counter(); fresh_h = fresh(); t1 = time.perf_counter(); fresh_h.build_bvh(); t2 = time.perf_counter()
+            g = fresh(); t3 = time.perf_counter(); g.build_bvh_gpu(local); t4 = time.perf_counter()
+            bvh_build = {"mesh": mesh_name, "host_builder_ms": round((t2 - t1) * 1e3, 3), "device_builder_wall_ms": round((t4 - t3) * 1e3, 3), "device_build_ms": round(g.build_ms, 3),
+                         "identical": bool(np.array_equal(fresh_h.arr_bvh, g.arr_bvh) and np.array_equal(fresh_h.tri_records, g.tri_records)),
+                         "note": "10 M triangles (configs[4] mesh): 2234 ms host, 36.9 ms on the device, see profiles/r01_notes.md"}
+
     work = sc.render(p, want=("rgb",), count_work=True)["stats"]  # instrumented pass for the roofline, not timed
     like_for_like = stochastic_vs_reference_kernel(rt, torch, sc) if (world == 1 and rank == 0) else None
     sharded = sharded_single_frame(rt, torch, sc, stream, world, rank, verts, recs, bvh, mesh_id, walls)
@@ -302,7 +316,7 @@ def run_ours(args):
                    "steps": e2e_steps},
            "gpu_launches": launches_per_step * args.steps, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
            "ms_per_frame": round(kernel_ms, 5), "scene_broadcast_bytes": blob_bytes, "single_frame_sharded": sharded,
-           "animation_light_orbit": animation, "frames_4k_depth4": frames_4k, "stochastic_vs_reference_gpu_kernel": like_for_like}
+           "animation_light_orbit": animation, "frames_4k_depth4": frames_4k, "bvh_build": bvh_build, "stochastic_vs_reference_gpu_kernel": like_for_like}
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

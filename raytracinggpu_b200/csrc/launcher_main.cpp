@@ -7,6 +7,7 @@
  *   --obj PATH                          default cadnav.com_model/Models_F0202A090/cat.obj relative to the CWD (:802)
  *   --out FILE                          default image_optimized.png (:862) / image.png (cpu_launcher.cpp:719)
  *   --device D   --frames F             render F frames (kernel time is reported per frame)
+ *   --gpu-build                         build the BVH on the device (same tree; the reference builds on the host, :809-813)
  *   --stochastic                        the reference's own default: sigma 0.2 Box-Muller jitter + cosine-weighted
  *                                       indirect bounce on the cuRAND XORWOW stream of optimized.cu:745 (without the
  *                                       flag: the deterministic mode the parity contract is stated on)
@@ -23,7 +24,7 @@ int main(int argc, char** argv) {
     std::vector<std::string> pos;
     std::string profile = "optimized", obj = "cadnav.com_model/Models_F0202A090/cat.obj", out;
     int W = 512, H = 512, device = 0, frames = 1;
-    bool stochastic = false;
+    bool stochastic = false, gpu_build = false;
     for (int i = 1; i < argc; i++) {
         std::string a = argv[i];
         auto next = [&]() -> const char* { return (i + 1 < argc) ? argv[++i] : ""; };
@@ -35,6 +36,7 @@ int main(int argc, char** argv) {
         else if (a == "--device") device = atoi(next());
         else if (a == "--frames") frames = atoi(next());
         else if (a == "--stochastic") stochastic = true;
+        else if (a == "--gpu-build") gpu_build = true;
         else pos.push_back(a);
     }
     if (pos.size() != 2) {
@@ -59,7 +61,8 @@ int main(int argc, char** argv) {
         mesh.readOBJ(obj.c_str());
         if (profile == "optimized") mesh.rescale(0.6f, rtb200::Vector(0.f, -4.f, 0.f));       /* optimized.cu:804 */
         else if (profile == "array_bvh") mesh.rescale(0.6f, rtb200::Vector(0.f, -10.f, 0.f)); /* array_bvh.cu:1033 */
-        mesh.buildBVH();
+        if (gpu_build) mesh.buildBVHDevice(device);
+        else mesh.buildBVH();
 
         rtb200::Scene scene(device);
         for (int k = 0, id = 0; k < 6; k++, id++) {

@@ -51,6 +51,12 @@ public:
     }
     /* compute_bbox + buildBVH + bvhTreeToArray in one step (optimized.cu:809-813) */
     void buildBVH() { check(rt_mesh_build_bvh(m_)); }
+    /* the same tree built on the device, a level at a time (global_launcher.cu:298-331 builds it in one device thread) */
+    double buildBVHDevice(int device = 0) {
+        double ms = 0.;
+        check(rt_mesh_build_bvh_gpu(m_, device, &ms));
+        return ms;
+    }
     int n_vertices() const { int32_t a; rt_mesh_counts(m_, &a, nullptr, nullptr); return a; }
     int n_triangles() const { int32_t a; rt_mesh_counts(m_, nullptr, &a, nullptr); return a; }
     int n_bvhs() const { int32_t a; rt_mesh_counts(m_, nullptr, nullptr, &a); return a; }
