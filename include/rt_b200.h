@@ -150,6 +150,16 @@ int rt_params_profile(rt_params* p, const char* profile, int32_t W, int32_t H, i
 int rt_default_walls(const char* profile, rt_sphere walls[6], int32_t* mesh_id);
 /* PNG output, the role of stbi_write_png at optimized.cu:862. rgb is H*W*3, top row first. */
 int rt_write_png(const char* path, int32_t W, int32_t H, const uint8_t* rgb);
+/* Asynchronous PNG output for frame sequences: rt_png_writer_submit copies the frame and returns; a background thread
+ * encodes (the scanlines in parallel bands) and writes it while the caller renders on. stbi_write_png at optimized.cu:862
+ * is synchronous and single-threaded: at 4K it costs a thousand times the render. threads <= 0: all hardware threads;
+ * max_pending <= 0: 4 queued frames before submit blocks. rt_png_writer_wait returns the first error of the frames written
+ * so far; rt_png_writer_destroy writes what is still queued. */
+typedef struct rt_png_writer rt_png_writer;
+int rt_png_writer_create(rt_png_writer** out, int32_t threads, int32_t max_pending);
+int rt_png_writer_submit(rt_png_writer* w, const char* path, int32_t W, int32_t H, const uint8_t* rgb);
+int rt_png_writer_wait(rt_png_writer* w);
+void rt_png_writer_destroy(rt_png_writer* w);
 /* One step of the reference's (never launched) MoveLightSource, realtime_render.cu:1072-1090, evaluated on the host in float. */
 void rt_move_light(float L[3], float angular_speed, float dt);
 

@@ -39,6 +39,10 @@ SIGNATURES = {
     "rt_params_profile": (C.c_int, [C.POINTER(rt_params), C.c_char_p, _i32, _i32, _i32, _i32]),
     "rt_default_walls": (C.c_int, [C.POINTER(rt_sphere), C.c_char_p, _pi32]),
     "rt_write_png": (C.c_int, [C.c_char_p, _i32, _i32, _vp]),
+    "rt_png_writer_create": (C.c_int, [C.POINTER(_vp), _i32, _i32]),
+    "rt_png_writer_submit": (C.c_int, [_vp, C.c_char_p, _i32, _i32, _vp]),
+    "rt_png_writer_wait": (C.c_int, [_vp]),
+    "rt_png_writer_destroy": (None, [_vp]),
     "rt_move_light": (None, [_pf, _f, _f]),
     "rt_scene_create": (C.c_int, [C.POINTER(_vp), C.c_int]),
     "rt_scene_destroy": (None, [_vp]),
@@ -127,6 +131,30 @@ def write_png(path, rgb):
     rgb = np.ascontiguousarray(rgb, dtype=np.uint8)
     H, W, _ = rgb.shape
     _check(lib().rt_write_png(path.encode(), W, H, rgb.ctypes.data))
+
+
+class PngWriter:
+    """Asynchronous PNG output (rt_png_writer_*): submit() copies the frame and returns, a background thread encodes and writes."""
+
+    def __init__(self, threads=0, max_pending=0):
+        self._h = C.c_void_p()
+        _check(lib().rt_png_writer_create(C.byref(self._h), int(threads), int(max_pending)))
+
+    def submit(self, path, rgb):
+        rgb = np.ascontiguousarray(rgb, dtype=np.uint8)
+        H, W, _ = rgb.shape
+        _check(lib().rt_png_writer_submit(self._h, path.encode(), W, H, rgb.ctypes.data))
+
+    def wait(self):
+        _check(lib().rt_png_writer_wait(self._h))
+
+    def close(self):
+        if self._h:
+            lib().rt_png_writer_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
 
 
 def move_light(L, angular_speed, dt=0.02):

@@ -7,6 +7,9 @@
  *   --obj PATH                          default cadnav.com_model/Models_F0202A090/cat.obj relative to the CWD (:802)
  *   --out FILE                          default image_optimized.png (:862) / image.png (cpu_launcher.cpp:719)
  *   --device D   --frames F             render F frames (kernel time is reported per frame)
+ *   --out-pattern P   --orbit W         with --frames: write EVERY frame to P (a printf pattern with one %d), encoded and
+ *                                       written in the background while the next frames render (rt_png_writer_*); between
+ *                                       frames the light moves by W rad/s x 0.02 s (MoveLightSource, realtime_render.cu:1072-1090)
  *   --gpu-build                         build the BVH on the device (same tree; the reference builds on the host, :809-813)
  *   --stochastic                        the reference's own default: sigma 0.2 Box-Muller jitter + cosine-weighted
  *                                       indirect bounce on the cuRAND XORWOW stream of optimized.cu:745 (without the
@@ -25,6 +28,8 @@ int main(int argc, char** argv) {
     std::string profile = "optimized", obj = "cadnav.com_model/Models_F0202A090/cat.obj", out;
     int W = 512, H = 512, device = 0, frames = 1;
     bool stochastic = false, gpu_build = false;
+    std::string pattern;
+    float orbit = 0.f;
     for (int i = 1; i < argc; i++) {
         std::string a = argv[i];
         auto next = [&]() -> const char* { return (i + 1 < argc) ? argv[++i] : ""; };
@@ -37,6 +42,8 @@ int main(int argc, char** argv) {
         else if (a == "--frames") frames = atoi(next());
         else if (a == "--stochastic") stochastic = true;
         else if (a == "--gpu-build") gpu_build = true;
+        else if (a == "--out-pattern") pattern = next();
+        else if (a == "--orbit") orbit = (float)atof(next());
         else pos.push_back(a);
     }
     if (pos.size() != 2) {
@@ -77,8 +84,31 @@ int main(int argc, char** argv) {
 
         std::vector<uint8_t> image((size_t)W * H * 3);
         rt_stats st{};
-        for (int f = 0; f < frames; f++) st = scene.render(p, image.data());
-        rtb200::check(rt_write_png(out.c_str(), W, H, image.data()));
+        rt_png_writer* writer = nullptr;
+        if (!pattern.empty()) rtb200::check(rt_png_writer_create(&writer, 0, 0));
+        float L[3] = {scene.L.x, scene.L.y, scene.L.z};
+        double kernel_ms_sum = 0.;
+        for (int f = 0; f < frames; f++) {
+            if (f > 0 && orbit != 0.f) {
+                rt_move_light(L, orbit, 0.02f);
+                scene.setLight(rtb200::Vector(L[0], L[1], L[2]), scene.intensity);
+            }
+            st = scene.render(p, image.data());
+            kernel_ms_sum += st.kernel_ms;
+            if (writer) {
+                char name[1024];
+                snprintf(name, sizeof name, pattern.c_str(), f);
+                rtb200::check(rt_png_writer_submit(writer, name, W, H, image.data())); /* copies; encode + write overlap the next frame */
+            }
+        }
+        if (writer) {
+            const int rc = rt_png_writer_wait(writer);
+            rt_png_writer_destroy(writer);
+            rtb200::check(rc);
+        } else {
+            rtb200::check(rt_write_png(out.c_str(), W, H, image.data()));
+        }
+        if (frames > 1) std::cerr << frames << " frames, mean kernel " << (kernel_ms_sum / frames) << " ms/frame\n";
         auto end_time = std::chrono::system_clock::now();
         std::chrono::duration<float> run_time = end_time - start_time;
         std::cout << "Rendering time: " << run_time.count() << " s\n";
