@@ -81,6 +81,8 @@ struct rt_scene {
     bool trav_wide = false;
     unsigned char* stage = nullptr; /* rt_scene_set_mesh: device staging of the interchange arrays */
     size_t stage_bytes = 0;
+    unsigned char* pin = nullptr;   /* rt_scene_set_mesh: pinned host staging (meshes up to 64 MB) */
+    size_t pin_bytes = 0;
     uint64_t mesh_generation = 0; /* bumped whenever the mesh part of the blob changes: invalidates the anchored-ray bins */
     /* anchored-ray bins (rt_bins.cuh): [0] camera, [1] light */
     struct AnchorBins {
@@ -107,6 +109,7 @@ struct rt_scene {
     int task_factor = 8;     /* task buffer entries per pixel; doubled after an overflow */
     bool last_was_anchored = false;
     int leaves_blocks_per_sm = 0;
+    bool n_strips_from_env = false;
     bool task_factor_from_env = false;
     int bins_builds = 0;
     size_t wf_spill_ints = 0;
@@ -391,7 +394,10 @@ int rt_scene_create(rt_scene** out, int device) {
     if (!s) return rtb::fail(RT_ERR_NOMEM, "rt_scene_create: out of memory");
     s->device = device;
     if (const char* v = getenv("RT_VARIANT")) s->variant = atoi(v);
-    if (const char* v = getenv("RT_STRIPS")) s->n_strips = std::max(1, std::min(atoi(v), RT_MAX_STRIPS));
+    if (const char* v = getenv("RT_STRIPS")) {
+        s->n_strips = std::max(1, std::min(atoi(v), RT_MAX_STRIPS));
+        s->n_strips_from_env = true;
+    }
     memset(&s->header, 0, sizeof s->header);
     s->header.magic = RT_BLOB_MAGIC;
     s->header.layout_version = RT_LAYOUT_VERSION;
@@ -434,6 +440,7 @@ void rt_scene_destroy(rt_scene* s) {
     if (s->dbg_warps) cudaFree(s->dbg_warps);
     if (s->wf_spill) cudaFree(s->wf_spill);
     if (s->stage) cudaFree(s->stage);
+    if (s->pin) cudaFreeHost(s->pin);
     for (int k = 0; k < 2; k++) {
         if (s->bins[k].cell_start) cudaFree(s->bins[k].cell_start);
         if (s->bins[k].cursor) cudaFree(s->bins[k].cursor);
@@ -762,23 +769,48 @@ int rt_scene_set_mesh(rt_scene* s, const float* vertices, int32_t nv, const int3
     }
     float* d_vertices = reinterpret_cast<float*>(s->stage + v_off);
     int32_t* d_recs = reinterpret_cast<int32_t*>(s->stage + r_off);
-    cudaError_t err = cudaSuccess;
-    if (err == cudaSuccess) err = cudaMemcpyAsync(d_vertices, vertices, vbytes, cudaMemcpyHostToDevice, s->stream);
-    if (err == cudaSuccess) err = cudaMemcpyAsync(d_recs, tri_records, rbytes, cudaMemcpyHostToDevice, s->stream);
-    if (err == cudaSuccess && n_inner > 0)
-        err = cudaMemcpyAsync(s->blob + off_nodes, packed.data(), (size_t)n_inner * RT_NODE_BYTES, cudaMemcpyHostToDevice, s->stream);
-    if (err == cudaSuccess && n_wide > 0)
-        err = cudaMemcpyAsync(s->blob + off_wide, wide.data(), (size_t)n_wide * RT_WNODE_BYTES, cudaMemcpyHostToDevice, s->stream);
-    if (err == cudaSuccess && n_leafrecs > 0)
-        err = cudaMemcpyAsync(s->blob + off_leaves, leaf_table.data(), (size_t)n_leafrecs * RT_LEAFREC_BYTES, cudaMemcpyHostToDevice, s->stream);
     int32_t* d_leaf_start = reinterpret_cast<int32_t*>(s->stage + l_off);
-    if (err == cudaSuccess) err = cudaMemcpyAsync(d_leaf_start, leaf_start_of_tri.data(), (size_t)nt * sizeof(int32_t), cudaMemcpyHostToDevice, s->stream);
+    cudaError_t err = cudaSuccess;
+    const size_t nodes_bytes = (size_t)n_inner * RT_NODE_BYTES, tail_bytes = (size_t)n_wide * RT_WNODE_BYTES + (size_t)n_leafrecs * RT_LEAFREC_BYTES;
+    const size_t pin_nodes = (stage_need + 255) & ~(size_t)255, pin_tail = (pin_nodes + nodes_bytes + 255) & ~(size_t)255, pin_need = pin_tail + tail_bytes;
+    bool need_sync = true;
+    if (pin_need <= ((size_t)64 << 20)) {
+        /* small and medium meshes (a mesh that is uploaded again every frame): everything is gathered in one pinned buffer kept
+         * with the scene and goes over in three truly asynchronous copies; nothing on the host has to outlive this call */
+        if (s->pin_bytes < pin_need) {
+            if (s->pin) cudaFreeHost(s->pin);
+            s->pin = nullptr;
+            s->pin_bytes = 0;
+            CUDA_TRY(cudaMallocHost(&s->pin, pin_need + pin_need / 4));
+            s->pin_bytes = pin_need + pin_need / 4;
+        }
+        memcpy(s->pin + v_off, vertices, vbytes);
+        memcpy(s->pin + r_off, tri_records, rbytes);
+        memcpy(s->pin + l_off, leaf_start_of_tri.data(), (size_t)nt * sizeof(int32_t));
+        if (nodes_bytes) memcpy(s->pin + pin_nodes, packed.data(), nodes_bytes);
+        if (n_wide > 0) memcpy(s->pin + pin_tail, wide.data(), (size_t)n_wide * RT_WNODE_BYTES);
+        if (n_leafrecs > 0) memcpy(s->pin + pin_tail + (size_t)n_wide * RT_WNODE_BYTES, leaf_table.data(), (size_t)n_leafrecs * RT_LEAFREC_BYTES);
+        err = cudaMemcpyAsync(s->stage, s->pin, stage_need, cudaMemcpyHostToDevice, s->stream);
+        if (err == cudaSuccess && nodes_bytes) err = cudaMemcpyAsync(s->blob + off_nodes, s->pin + pin_nodes, nodes_bytes, cudaMemcpyHostToDevice, s->stream);
+        if (err == cudaSuccess && tail_bytes) err = cudaMemcpyAsync(s->blob + off_wide, s->pin + pin_tail, tail_bytes, cudaMemcpyHostToDevice, s->stream);
+        need_sync = false; /* the next rt_scene_set_mesh waits for the stream before it touches the pinned buffer again */
+    } else {
+        if (err == cudaSuccess) err = cudaMemcpyAsync(d_vertices, vertices, vbytes, cudaMemcpyHostToDevice, s->stream);
+        if (err == cudaSuccess) err = cudaMemcpyAsync(d_recs, tri_records, rbytes, cudaMemcpyHostToDevice, s->stream);
+        if (err == cudaSuccess && n_inner > 0)
+            err = cudaMemcpyAsync(s->blob + off_nodes, packed.data(), nodes_bytes, cudaMemcpyHostToDevice, s->stream);
+        if (err == cudaSuccess && n_wide > 0)
+            err = cudaMemcpyAsync(s->blob + off_wide, wide.data(), (size_t)n_wide * RT_WNODE_BYTES, cudaMemcpyHostToDevice, s->stream);
+        if (err == cudaSuccess && n_leafrecs > 0)
+            err = cudaMemcpyAsync(s->blob + off_leaves, leaf_table.data(), (size_t)n_leafrecs * RT_LEAFREC_BYTES, cudaMemcpyHostToDevice, s->stream);
+        if (err == cudaSuccess) err = cudaMemcpyAsync(d_leaf_start, leaf_start_of_tri.data(), (size_t)nt * sizeof(int32_t), cudaMemcpyHostToDevice, s->stream);
+    }
     if (err == cudaSuccess) {
         const int threads = 256, blocks = (nt + threads - 1) / threads;
         rtk::repack_triangles<<<blocks, threads, 0, s->stream>>>(d_vertices, d_recs, nt, d_leaf_start, reinterpret_cast<float4*>(s->blob + off_tris));
         err = cudaGetLastError();
     }
-    if (err == cudaSuccess) err = cudaStreamSynchronize(s->stream); /* the host vectors above go out of scope */
+    if (err == cudaSuccess && need_sync) err = cudaStreamSynchronize(s->stream); /* the host vectors above go out of scope */
     if (err != cudaSuccess) return rtb::fail(RT_ERR_CUDA, "rt_scene_set_mesh: %s", cudaGetErrorString(err));
 
     h.has_mesh = 1;
@@ -1152,6 +1184,11 @@ int rt_render(rt_scene* s, const rt_params* p, uint32_t flags, uint8_t* rgb_out,
              * finishing their expensive rays on an otherwise idle GPU, profiles/r01_notes.md); with strips the tail of
              * one band is covered by the bulk of the next, and only the last launch's tail is exposed. */
             int n_strips = s->n_strips;
+            {   /* host outputs: more bands, so that only the last band's copy-back is not covered by rendering */
+                bool any_copy = false;
+                for (int k = 0; k < 5; k++) any_copy = any_copy || copy_back[k];
+                if (any_copy && !s->n_strips_from_env) n_strips = std::min(RT_MAX_STRIPS, 4);
+            }
             if (rows < 64 * n_strips) n_strips = std::max(1, rows / 64);
             if (dbg_times || dbg_warps) n_strips = 1;
             const unsigned pers_grid = (unsigned)(s->sm_count * s->trav_blocks_per_sm);

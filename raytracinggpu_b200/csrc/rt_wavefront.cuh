@@ -740,7 +740,7 @@ template <bool STOCH>
 __device__ __forceinline__ void leaf_triangles(const SceneHeader& h, const WfArgs& g, const float4* __restrict__ tris, QEntry* q, bool any, int code) {
     const RenderArgs& a = g.a;
     const float4* p = reinterpret_cast<const float4*>(q);
-    const float4 p0 = __ldcg(p), p1 = __ldcg(p + 1);
+    const float4 p0 = __ldg(p), p1 = __ldg(p + 1); /* origin, direction: read-only in this kernel (L1-cached); res below is not */
     const F3 O = f3(p0.x, p0.y, p0.z), u = f3(p1.x, p1.y, p1.z);
     const unsigned long long cur = __ldcg(&q->res);
     float t_limit;
@@ -812,7 +812,7 @@ __global__ void __launch_bounds__(WF_THREADS) wf_leaves(const __grid_constant__ 
         if (i < n) {
             const QEntry* q = ((task.x < 0) ? g.qS : qA) + (task.x & 0x7fffffff);
             const float4* p = reinterpret_cast<const float4*>(q);
-            const float4 p0 = __ldcg(p), p1 = __ldcg(p + 1);
+            const float4 p0 = __ldg(p), p1 = __ldg(p + 1);
             float4 l0, l1;
             ldg256(leaves + 2 * (size_t)task.y, l0, l1);
             const RayCtx ctx = make_ray_ctx(f3(p0.x, p0.y, p0.z), f3(p1.x, p1.y, p1.z), h.box_abs[0], h.box_abs[1], h.box_abs[2]);
