@@ -1190,6 +1190,13 @@ int rt_render(rt_scene* s, const rt_params* p, uint32_t flags, uint8_t* rgb_out,
                 if (any_copy && !s->n_strips_from_env) n_strips = std::min(RT_MAX_STRIPS, 4);
             }
             if (rows < 64 * n_strips) n_strips = std::max(1, rows / 64);
+            /* a small shard (one rank's rows of a frame split over 8 GPUs) is bound by launch latencies: one band
+             * (measured: 4K depth-4 frame, 1/8 of the rows: 0.33 ms against 0.37 ms with two) */
+            if (!s->n_strips_from_env && npx < 1500000 && !(flags & RT_RENDER_COUNT_WORK)) {
+                bool any_copy = false;
+                for (int k = 0; k < 5; k++) any_copy = any_copy || copy_back[k];
+                if (!any_copy) n_strips = 1;
+            }
             if (dbg_times || dbg_warps) n_strips = 1;
             const unsigned pers_grid = (unsigned)(s->sm_count * s->trav_blocks_per_sm);
             const int spill_cap = WF_SLOTS * std::max(h.max_depth + 2, (RT_WIDE - 1) * h.wide_depth + 2); /* per traversal warp: every ray slot holding a full path of pending siblings */
