@@ -71,6 +71,9 @@ struct rt_scene {
     cudaStream_t strip_stream[RT_MAX_STRIPS] = {};
     cudaEvent_t strip_done[RT_MAX_STRIPS] = {};
     cudaEvent_t fork_ev = nullptr;
+    /* a band's tree search (bounce rays) and its (ray, leaf) tasks of the same round are independent: side stream + events */
+    cudaStream_t side_stream[RT_MAX_STRIPS] = {};
+    cudaEvent_t side_fork[RT_MAX_STRIPS] = {}, side_join[RT_MAX_STRIPS] = {};
     rtk::XorwowState* rng_states = nullptr; /* stochastic mode: curand_init(seed, pixel, 0) of every pixel of a rng_W x rng_H frame */
     size_t rng_capacity = 0;
     int rng_W = 0, rng_H = 0;
@@ -460,6 +463,9 @@ void rt_scene_destroy(rt_scene* s) {
     for (int k = 0; k < RT_MAX_STRIPS; k++) {
         if (s->strip_stream[k]) cudaStreamDestroy(s->strip_stream[k]);
         if (s->strip_done[k]) cudaEventDestroy(s->strip_done[k]);
+        if (s->side_stream[k]) cudaStreamDestroy(s->side_stream[k]);
+        if (s->side_fork[k]) cudaEventDestroy(s->side_fork[k]);
+        if (s->side_join[k]) cudaEventDestroy(s->side_join[k]);
     }
     if (s->fork_ev) cudaEventDestroy(s->fork_ev);
     if (s->ev0) cudaEventDestroy(s->ev0);
@@ -1155,6 +1161,9 @@ int rt_render(rt_scene* s, const rt_params* p, uint32_t flags, uint8_t* rgb_out,
                     for (int k = 0; k < RT_MAX_STRIPS; k++) {
                         CUDA_TRY(cudaStreamCreateWithFlags(&s->strip_stream[k], cudaStreamNonBlocking));
                         CUDA_TRY(cudaEventCreateWithFlags(&s->strip_done[k], cudaEventDisableTiming));
+                        CUDA_TRY(cudaStreamCreateWithFlags(&s->side_stream[k], cudaStreamNonBlocking));
+                        CUDA_TRY(cudaEventCreateWithFlags(&s->side_fork[k], cudaEventDisableTiming));
+                        CUDA_TRY(cudaEventCreateWithFlags(&s->side_join[k], cudaEventDisableTiming));
                     }
                 }
             }
@@ -1344,19 +1353,33 @@ int rt_render(rt_scene* s, const rt_params* p, uint32_t flags, uint8_t* rgb_out,
                         if (anchored) {
                             /* closest-hit queries of a round >= 1 start somewhere in the scene: tree search; every shadow
                              * query and the camera rays of round 0 are (ray, leaf) tasks */
-                            if (r < segments && (r >= 1 || trav_round0)) {
+                            const bool trav_now = r < segments && (r >= 1 || trav_round0);
+                            /* the two kernels of the round touch disjoint entries: the tree search goes to the band's side stream
+                             * and runs beside wf_leaves (its latency-bound tail is covered by the LSU-bound task kernel) */
+                            static const bool env_side = !(getenv("RT_SIDE_STREAM") && atoi(getenv("RT_SIDE_STREAM")) == 0);
+                            const bool side = trav_now && env_side && !dbg_times;
+                            cudaStream_t tstream = side ? s->side_stream[st] : stream;
+                            if (side) {
+                                CUDA_TRY(cudaEventRecord(s->side_fork[st], stream));
+                                CUDA_TRY(cudaStreamWaitEvent(tstream, s->side_fork[st], 0));
+                            }
+                            if (trav_now) {
                                 if (stochastic) {
-                                    if (wide) rtk::wf_traverse<false, true, true><<<pers_grid, WF_THREADS, trav_smem, stream>>>(s->header, s->blob, g, npool_cap);
-                                    else rtk::wf_traverse<false, true, false><<<pers_grid, WF_THREADS, trav_smem, stream>>>(s->header, s->blob, g, npool_cap);
+                                    if (wide) rtk::wf_traverse<false, true, true><<<pers_grid, WF_THREADS, trav_smem, tstream>>>(s->header, s->blob, g, npool_cap);
+                                    else rtk::wf_traverse<false, true, false><<<pers_grid, WF_THREADS, trav_smem, tstream>>>(s->header, s->blob, g, npool_cap);
                                 } else {
-                                    if (wide) rtk::wf_traverse<false, false, true><<<pers_grid, WF_THREADS, trav_smem, stream>>>(s->header, s->blob, g, npool_cap);
-                                    else rtk::wf_traverse<false, false, false><<<pers_grid, WF_THREADS, trav_smem, stream>>>(s->header, s->blob, g, npool_cap);
+                                    if (wide) rtk::wf_traverse<false, false, true><<<pers_grid, WF_THREADS, trav_smem, tstream>>>(s->header, s->blob, g, npool_cap);
+                                    else rtk::wf_traverse<false, false, false><<<pers_grid, WF_THREADS, trav_smem, tstream>>>(s->header, s->blob, g, npool_cap);
                                 }
                                 launches++;
                                 mark();
                             }
                             if (stochastic) rtk::wf_leaves<true><<<leaves_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
                             else rtk::wf_leaves<false><<<leaves_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
+                            if (side) { /* join: wf_shade needs both */
+                                CUDA_TRY(cudaEventRecord(s->side_join[st], tstream));
+                                CUDA_TRY(cudaStreamWaitEvent(stream, s->side_join[st], 0));
+                            }
                         } else if (stochastic) {
                             if (count) rtk::wf_traverse<true, true, false><<<pers_grid, WF_THREADS, trav_smem, stream>>>(s->header, s->blob, g, npool_cap);
                             else if (wide) rtk::wf_traverse<false, true, true><<<pers_grid, WF_THREADS, trav_smem, stream>>>(s->header, s->blob, g, npool_cap);
