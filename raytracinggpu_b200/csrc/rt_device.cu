@@ -1110,7 +1110,11 @@ int rt_render(rt_scene* s, const rt_params* p, uint32_t flags, uint8_t* rgb_out,
         if (variant == 2) {
             /* the wide index (rt_layout.h) is the production search structure; the instrumented build counts the reference's
              * own node visits and therefore walks the two-child records, as does RT_WIDE=0 (A/B timing, cross-check) */
-            const bool env_wide = getenv("RT_WIDE") && atoi(getenv("RT_WIDE")) != 0; /* measured: no faster than the two-child records at 8 blocks per SM (profiles/r01_notes.md); off unless asked for */
+            /* RT_WIDE: 1 on, 0 off; unset: on for the incoherent bounce rays of the stochastic mode (measured, 6 blocks per SM:
+             * stochastic 4 3 4.91 -> 4.67 ms, but the mirror 4K frame 1.23 -> 1.28 ms and no gain for the tree search of
+             * coherent rays, profiles/r01_notes.md) */
+            const int env_wide_v = getenv("RT_WIDE") ? atoi(getenv("RT_WIDE")) : -1;
+            const bool env_wide = env_wide_v > 0 || (env_wide_v < 0 && stochastic && p->indirect != 0);
             const bool env_wide_count = getenv("RT_WIDE_COUNT") != nullptr; /* timeline of the wide kernel: node_visits then counts wide nodes */
             const bool wide = env_wide && (!count || env_wide_count) && h.n_wide > 0;
             /* anchored rays (rt_bins.cuh): camera rays and shadow rays find their leaves through per-anchor bins and wf_leaves

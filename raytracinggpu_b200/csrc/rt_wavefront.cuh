@@ -908,7 +908,7 @@ struct WfWarpSmem { /* per warp; followed by the node pool (npool_cap ints) */
 #define RT_WIDE_LOADS 4 /* child records requested together by a wide N step */
 #endif
 #ifndef RT_WIDE_BLOCKS
-#define RT_WIDE_BLOCKS 8 /* resident blocks per SM the wide instantiations are compiled for */
+#define RT_WIDE_BLOCKS 6 /* resident blocks per SM the wide instantiations are compiled for: 80 registers, no spills (8: 64 registers, 86 B of spills, slower) */
 #endif
 template <bool COUNT, bool STOCH, bool WIDE>
 __global__ void __launch_bounds__(WF_THREADS, WIDE ? RT_WIDE_BLOCKS : 8) wf_traverse(const __grid_constant__ SceneHeader h, const unsigned char* __restrict__ blob,
