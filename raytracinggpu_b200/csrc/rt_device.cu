@@ -1315,13 +1315,8 @@ int rt_render(rt_scene* s, const rt_params* p, uint32_t flags, uint8_t* rgb_out,
                 static const int env_lb = getenv("RT_LEAVES_BLOCKS") ? atoi(getenv("RT_LEAVES_BLOCKS")) : 0;
                 const unsigned leaves_grid = (unsigned)(s->sm_count * (env_lb > 0 ? env_lb : std::max(s->leaves_blocks_per_sm, 1)));
                 const unsigned wtiles = (unsigned)((p->W + 7) / 8) * (unsigned)((srows + 3) / 4);
-                unsigned gen_grid = (wtiles + (WF_THREADS / 32) - 1) / (WF_THREADS / 32);
-                unsigned shade_grid = (unsigned)std::min<size_t>((spx + WF_THREADS - 1) / WF_THREADS, (size_t)s->sm_count * 16);
-                {   /* blocks per SM of the streaming kernels (experiment knobs: co-residency of the bands' kernels) */
-                    const int gb = getenv("RT_GEN_BLOCKS") ? atoi(getenv("RT_GEN_BLOCKS")) : 0, sb = getenv("RT_SHADE_BLOCKS") ? atoi(getenv("RT_SHADE_BLOCKS")) : 0;
-                    if (gb > 0) gen_grid = std::min(gen_grid, (unsigned)(s->sm_count * gb));
-                    if (sb > 0) shade_grid = std::min(shade_grid, (unsigned)(s->sm_count * sb));
-                }
+                const unsigned gen_grid = (wtiles + (WF_THREADS / 32) - 1) / (WF_THREADS / 32);
+                const unsigned shade_grid = (unsigned)std::min<size_t>((spx + WF_THREADS - 1) / WF_THREADS, (size_t)s->sm_count * 16);
                 g.stoch = stochastic ? 1 : 0;
                 g.sample = 0;
                 g.last_sample = 1;

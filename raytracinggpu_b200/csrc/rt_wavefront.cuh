@@ -617,12 +617,11 @@ __global__ void __launch_bounds__(WF_THREADS) wf_generate(const __grid_constant_
     const float4* tris = reinterpret_cast<const float4*>(blob + h.off_tris);
     const int lane = threadIdx.x & 31;
     const int tiles_x = (a.W + 7) >> 3;
-    const int n_tiles = tiles_x * ((a.rows + 3) >> 2);
     Work w;
     w.rays = w.nodes = w.tris = w.max_stack = w.slab_fallbacks = w.tri_exact = 0;
-    /* a warp takes 8x4 tiles at the grid's stride: the launcher may give the kernel fewer blocks than tiles, so that it
-     * shares the SMs with the (LSU-bound) wf_leaves of the other row band instead of running before or after it */
-    for (int wt = blockIdx.x * (WF_THREADS / 32) + (threadIdx.x >> 5); wt < n_tiles; wt += gridDim.x * (WF_THREADS / 32)) {
+    /* one 8x4 tile per warp (a grid-stride loop over tiles, tried to make the kernel share the SMs with the LSU-bound
+     * wf_leaves of the other row band, cost 16 registers and was slower in every launch shape: profiles/r01_notes.md) */
+    const int wt = blockIdx.x * (WF_THREADS / 32) + (threadIdx.x >> 5);
     const int j = (wt % tiles_x) * 8 + (lane & 7);
     const int kr = (wt / tiles_x) * 4 + (lane >> 3);
     Post post;
@@ -669,7 +668,6 @@ __global__ void __launch_bounds__(WF_THREADS) wf_generate(const __grid_constant_
     if (g.anchored) {
         emit_tasks(g, 0, post, slot);
         answer_deferred<STOCH>(h, blob, g, 0, post, slot);
-    }
     }
     flush_work(w, g.c, COUNT);
 }

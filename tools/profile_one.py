@@ -14,7 +14,9 @@ sc = rt.Scene(0)
 sc.set_spheres(walls)
 sc.set_mesh(mesh.vertices, mesh.tri_records, mesh.arr_bvh, id=mesh_id)
 p = rt.params_profile("optimized", Wd, Hd, 1, 1)
-out = None
+import torch  # noqa: E402
+rgb = torch.empty((Hd, Wd, 3), dtype=torch.uint8, device="cuda")  # a device buffer, as in bench.py's timed loop (two row bands)
+st = None
 for i in range(3 + n):
-    out = sc.render(p, want=("rgb",))
-print(name, out["stats"])
+    st = sc.render_into(p, rgb=rgb)
+print(name, st.kernel_ms, st.rays, st.launches)
