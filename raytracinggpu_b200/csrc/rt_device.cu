@@ -1121,9 +1121,10 @@ int rt_render(rt_scene* s, const rt_params* p, uint32_t flags, uint8_t* rgb_out,
              * tests the triangles; wf_traverse keeps the rays that start anywhere else (bounces). The instrumented build
              * counts the reference's node visits and therefore searches the tree; RT_ANCHOR=0 does so too (A/B, cross-check). */
             const int env_anchor = getenv("RT_ANCHOR") ? atoi(getenv("RT_ANCHOR")) : -1; /* 0 off, 1 on, unset: by mesh size */
-            /* measured (profiles/r01_configs.md): with millions of leaves a cell lists hundreds of them and one task per candidate
-             * loses against the tree search; the bins serve meshes up to 200 k leaves unless asked for */
-            bool anchored = (env_anchor > 0 || (env_anchor < 0 && h.n_leaves <= 200000)) && !count && h.has_mesh && h.n_leaves > 0 && segments > 0;
+            /* measured (tools/size_sweep.py, profiles/r01_notes.md): the bins win from 1 k to 1 M leaves (1080p: 0.25 vs 0.41 ms at
+             * 1 k, 0.77 vs 1.20 ms at 241 k, 5.97 vs 6.46 ms at 1 M); at 2.5 M leaves and 4K a cell lists hundreds of leaves and
+             * one task per candidate loses against the tree search (13.9 vs 12.9 ms) */
+            bool anchored = (env_anchor > 0 || (env_anchor < 0 && h.n_leaves <= 1200000)) && !count && h.has_mesh && h.n_leaves > 0 && segments > 0;
             if (anchored) {
                 int rc = ensure_bins(s, 0, p->cam);
                 if (rc == RT_OK) rc = ensure_bins(s, 1, h.L);

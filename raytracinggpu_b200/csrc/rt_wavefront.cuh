@@ -674,7 +674,7 @@ __global__ void __launch_bounds__(WF_THREADS) wf_generate(const __grid_constant_
 
 /* ---- wf_shade: one thread per answered closest-hit query of round g.round ------------------------------------------ */
 template <bool COUNT, bool STOCH>
-__global__ void __launch_bounds__(WF_THREADS) wf_shade(const __grid_constant__ SceneHeader h, const unsigned char* __restrict__ blob,
+__global__ void __launch_bounds__(WF_THREADS, 8) wf_shade(const __grid_constant__ SceneHeader h, const unsigned char* __restrict__ blob,
                                                       const __grid_constant__ WfArgs g) {
     const RenderArgs& a = g.a;
     const float4* nodes = reinterpret_cast<const float4*>(blob + h.off_nodes);
