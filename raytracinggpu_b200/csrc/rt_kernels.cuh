@@ -46,6 +46,7 @@ struct Work {
  * reference's libm expression, rt_device.cu:build_gamma_table), so the result is the number of thresholds
  * <= c. A two-MUFU estimate finds the neighbourhood, the table fixes it. */
 __device__ __forceinline__ int quantise(float c, const float* __restrict__ T) {
+    if (c < T[1]) return 0; /* below the first threshold: most channels of the scene (wall albedos have zero channels, shadows are black) */
     const float g = __powf(c, 0.45454545f);
     int k = (int)fminf(fmaxf(g, 0.f), 255.f);
     while (k > 0 && c < T[k]) --k;
