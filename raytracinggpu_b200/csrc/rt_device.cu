@@ -1315,8 +1315,7 @@ int rt_render(rt_scene* s, const rt_params* p, uint32_t flags, uint8_t* rgb_out,
                 }
                 static const int env_lb = getenv("RT_LEAVES_BLOCKS") ? atoi(getenv("RT_LEAVES_BLOCKS")) : 0;
                 const unsigned leaves_grid = (unsigned)(s->sm_count * (env_lb > 0 ? env_lb : std::max(s->leaves_blocks_per_sm, 1)));
-                const unsigned wtiles = (unsigned)((p->W + 7) / 8) * (unsigned)((srows + 3) / 4);
-                const unsigned gen_grid = (wtiles + (WF_THREADS / 32) - 1) / (WF_THREADS / 32);
+                const dim3 gen_grid((unsigned)(((p->W + 7) / 8 + (WF_THREADS / 32) - 1) / (WF_THREADS / 32)), (unsigned)((srows + 3) / 4));
                 const unsigned shade_grid = (unsigned)std::min<size_t>((spx + WF_THREADS - 1) / WF_THREADS, (size_t)s->sm_count * 16);
                 g.stoch = stochastic ? 1 : 0;
                 g.sample = 0;

@@ -153,8 +153,8 @@ __device__ __forceinline__ void store_entry(QEntry* q, int slot, F3 O, F3 u, flo
 /* sample average + transfer function + store (optimized.cu:762-771) */
 __device__ __forceinline__ void write_pixel(const RenderArgs& a, int px, F3 color) {
     if (!a.rgb) return;
-    F3 total = f3(0.f, 0.f, 0.f);
-    for (int s = 0; s < a.num_rays; s++) total = total + color;
+    F3 total = f3(0.f, 0.f, 0.f) + color; /* the first of num_rays additions (0 + x, as the reference's accumulation starts) */
+    for (int s = 1; s < a.num_rays; s++) total = total + color;
     const F3 avg = a.num_rays == 1 ? total : total / (float)a.num_rays; /* x / 1.0f == x */
     const float* T = a.gamma_tab + a.gamma_mode * 256;
     a.rgb[(size_t)px * 3 + 0] = (uint8_t)quantise(avg.x, T);
@@ -616,14 +616,14 @@ __global__ void __launch_bounds__(WF_THREADS) wf_generate(const __grid_constant_
     const float4* nodes = reinterpret_cast<const float4*>(blob + h.off_nodes);
     const float4* tris = reinterpret_cast<const float4*>(blob + h.off_tris);
     const int lane = threadIdx.x & 31;
-    const int tiles_x = (a.W + 7) >> 3;
     Work w;
     w.rays = w.nodes = w.tris = w.max_stack = w.slab_fallbacks = w.tri_exact = 0;
     /* one 8x4 tile per warp (a grid-stride loop over tiles, tried to make the kernel share the SMs with the LSU-bound
      * wf_leaves of the other row band, cost 16 registers and was slower in every launch shape: profiles/r01_notes.md) */
-    const int wt = blockIdx.x * (WF_THREADS / 32) + (threadIdx.x >> 5);
-    const int j = (wt % tiles_x) * 8 + (lane & 7);
-    const int kr = (wt / tiles_x) * 4 + (lane >> 3);
+    /* grid: x = groups of four tiles along a row of tiles, y = the row of tiles (no division in the kernel) */
+    const int tx = blockIdx.x * (WF_THREADS / 32) + (threadIdx.x >> 5);
+    const int j = tx * 8 + (lane & 7);
+    const int kr = blockIdx.y * 4 + (lane >> 3);
     Post post;
     post.kind = 0;
     post.kind2 = 0;
