@@ -391,7 +391,41 @@ def sharded_single_frame(rt, torch, sc, stream, world, rank, verts, recs, bvh, m
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(r)
     total_ms, render_ms = float(t[0].item()) / frames, float(t[1].item()) / frames
+    # the same frame with the bands pushed into rank 0's frame buffer over NVLink (CUDA IPC peer copies + one barrier)
+    push = None
+    if world > 1:
+        fp = rtd.FramePush(sc, H4, W4, world, rank, torch.device("cuda", torch.cuda.current_device()))
+        pp = fp.apply(rt.params_profile("optimized", W4, H4, 1, 4))
+        ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(frames)]
+        for i in range(3 + frames):
+            dist.barrier()
+            with torch.cuda.stream(stream):
+                k = i - 3
+                if k >= 0:
+                    ev2[k][0].record(stream)
+                sc.render_into(pp, rgb=fp.band, flags=rt.RT_RENDER_NO_SYNC)
+                if k >= 0:
+                    ev2[k][1].record(stream)
+                fp.push()
+                if k >= 0:
+                    ev2[k][2].record(stream)
+            sc.sync()
+        torch.cuda.synchronize()
+        t2 = torch.tensor([sum(a.elapsed_time(c) for a, _, c in ev2), sum(a.elapsed_time(b) for a, b, _ in ev2)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+        same = None
+        if rank == 0:
+            with torch.cuda.stream(stream):
+                pushed = fp.frame_tensor()
+            sc.sync()
+            torch.cuda.synchronize()
+            same = bool(torch.equal(pushed, fg.frame))
+        fp.close()
+        push = {"ms_per_frame": round(float(t2[0].item()) / frames, 4), "render_ms": round(float(t2[1].item()) / frames, 4),
+                "push_and_barrier_ms": round(float(t2[0].item() - t2[1].item()) / frames, 4), "frame_equals_all_gather": same,
+                "how": "rank 0 owns the frame (CUDA IPC handle broadcast once); every rank copies its band into it over NVLink, one barrier per frame"}
     return {"workload": "BASELINE.json configs[2]: mirror cat 3840x2160, reflection depth 4, rows interleaved over %d GPU(s), all-gather to every rank" % world,
+            "p2p_push": push,
             "rays_per_frame": int(r.item()), "ms_per_frame": round(total_ms, 4), "render_ms": round(render_ms, 4), "gather_ms": round(total_ms - render_ms, 4),
             "mrays_per_s": round(int(r.item()) / (total_ms * 1e-3) / 1e6, 1), "gather_bytes_per_rank": int(fg.band.numel()), "frames": frames, "scaling": "strong"}
 

@@ -199,6 +199,17 @@ int rt_render(rt_scene* s, const rt_params* p, uint32_t flags,
 int rt_scene_sync(rt_scene* s, rt_stats* stats);
 
 /* ---- diagnostics ---- */
+/* ---- peer frame buffer (multi-GPU, one process per GPU): the gather of a row-sharded frame as direct NVLink copies.
+ * The destination rank allocates the frame (rt_peer_alloc) and hands the 64-byte CUDA IPC handle to the other ranks
+ * (any transport); they open it (rt_peer_open) and push their row bands into it on their scene's stream
+ * (rt_scene_push_rows: rows row_begin, row_begin + row_step, ... of a frame of W pixels per row). A barrier after the pushes is
+ * the caller's. The reference is single-GPU; this replaces an NCCL all-gather of the bands. */
+int rt_peer_alloc(int device, size_t bytes, void** ptr, uint8_t handle[64]);
+int rt_peer_open(int device, const uint8_t handle[64], void** ptr);
+int rt_peer_close(int device, void* ptr);
+int rt_peer_free(int device, void* ptr);
+int rt_scene_push_rows(rt_scene* s, const void* band, void* frame, int32_t W, int32_t bytes_per_pixel, int32_t row_begin, int32_t row_step, int32_t rows);
+
 /* Device self-test: the reciprocal-based exact division used by the fast slab test against div.rn.f32 on
  * blocks*256*per_thread pseudo-random operand pairs. out[0] = mismatches with one correction step,
  * out[1] = with two, out[2] = pairs tested. */

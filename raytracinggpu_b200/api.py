@@ -39,6 +39,11 @@ SIGNATURES = {
     "rt_params_profile": (C.c_int, [C.POINTER(rt_params), C.c_char_p, _i32, _i32, _i32, _i32]),
     "rt_default_walls": (C.c_int, [C.POINTER(rt_sphere), C.c_char_p, _pi32]),
     "rt_write_png": (C.c_int, [C.c_char_p, _i32, _i32, _vp]),
+    "rt_peer_alloc": (C.c_int, [C.c_int, C.c_size_t, C.POINTER(_vp), _vp]),
+    "rt_peer_open": (C.c_int, [C.c_int, _vp, C.POINTER(_vp)]),
+    "rt_peer_close": (C.c_int, [C.c_int, _vp]),
+    "rt_peer_free": (C.c_int, [C.c_int, _vp]),
+    "rt_scene_push_rows": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32]),
     "rt_png_writer_create": (C.c_int, [C.POINTER(_vp), _i32, _i32]),
     "rt_png_writer_submit": (C.c_int, [_vp, C.c_char_p, _i32, _i32, _vp]),
     "rt_png_writer_wait": (C.c_int, [_vp]),
@@ -131,6 +136,28 @@ def write_png(path, rgb):
     rgb = np.ascontiguousarray(rgb, dtype=np.uint8)
     H, W, _ = rgb.shape
     _check(lib().rt_write_png(path.encode(), W, H, rgb.ctypes.data))
+
+
+def peer_alloc(device, nbytes):
+    """(device pointer, 64-byte CUDA IPC handle) of a buffer other processes can open with peer_open."""
+    p, h = C.c_void_p(), (C.c_uint8 * 64)()
+    _check(lib().rt_peer_alloc(int(device), int(nbytes), C.byref(p), h))
+    return p.value, bytes(h)
+
+
+def peer_open(device, handle):
+    p = C.c_void_p()
+    buf = (C.c_uint8 * 64).from_buffer_copy(handle)
+    _check(lib().rt_peer_open(int(device), buf, C.byref(p)))
+    return p.value
+
+
+def peer_close(device, ptr):
+    _check(lib().rt_peer_close(int(device), C.c_void_p(int(ptr))))
+
+
+def peer_free(device, ptr):
+    _check(lib().rt_peer_free(int(device), C.c_void_p(int(ptr))))
 
 
 class PngWriter:
@@ -299,6 +326,11 @@ class Scene:
 
     def blob_import(self, device_ptr, nbytes):
         _check(lib().rt_scene_blob_import(self._h, C.c_void_p(int(device_ptr)), int(nbytes)))
+
+    def push_rows(self, band_ptr, frame_ptr, W, bytes_per_pixel, row_begin, row_step, rows):
+        """Strided device-to-device copy of this rank's row band into a (peer) frame buffer, on the scene's stream."""
+        _check(lib().rt_scene_push_rows(self._h, C.c_void_p(int(band_ptr)), C.c_void_p(int(frame_ptr)), int(W), int(bytes_per_pixel), int(row_begin),
+                                        int(row_step), int(rows)))
 
     def render_into(self, params, rgb=None, hit_obj=None, hit_tri=None, hit_t=None, shadow=None, flags=0):
         """rt_render with caller-provided buffers (numpy = host, torch cuda tensor / int = device)."""

@@ -1469,6 +1469,60 @@ int rt_render(rt_scene* s, const rt_params* p, uint32_t flags, uint8_t* rgb_out,
     return rc;
 }
 
+/* ---- peer frame buffer: the gather of a row-sharded frame as direct NVLink copies -----------------------------------
+ * One process per GPU: the destination rank allocates the frame and exports a CUDA IPC handle; the other ranks open it and
+ * push their row bands straight into it (strided device-to-device copy over NVLink / NVSwitch on the scene's stream). The
+ * only synchronisation left is one barrier that tells the destination all bands have landed. */
+int rt_peer_alloc(int device, size_t bytes, void** ptr, uint8_t handle[64]) {
+    if (!ptr || !handle || bytes == 0) return rtb::fail(RT_ERR_INVALID, "rt_peer_alloc: bad argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+    DeviceGuard g(device);
+    if (!g.ok) return rtb::fail(RT_ERR_CUDA, "rt_peer_alloc: no device %d", device);
+    CUDA_TRY(cudaMalloc(ptr, bytes));
+    cudaIpcMemHandle_t hd;
+    const cudaError_t e = cudaIpcGetMemHandle(&hd, *ptr);
+    if (e != cudaSuccess) {
+        cudaFree(*ptr);
+        *ptr = nullptr;
+        return rtb::fail(RT_ERR_CUDA, "rt_peer_alloc: cudaIpcGetMemHandle: %s", cudaGetErrorString(e));
+    }
+    memcpy(handle, &hd, 64);
+    return RT_OK;
+}
+
+int rt_peer_open(int device, const uint8_t handle[64], void** ptr) {
+    if (!ptr || !handle) return rtb::fail(RT_ERR_INVALID, "rt_peer_open: bad argument");
+    DeviceGuard g(device);
+    if (!g.ok) return rtb::fail(RT_ERR_CUDA, "rt_peer_open: no device %d", device);
+    cudaIpcMemHandle_t hd;
+    memcpy(&hd, handle, 64);
+    const cudaError_t e = cudaIpcOpenMemHandle(ptr, hd, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) return rtb::fail(RT_ERR_CUDA, "rt_peer_open: cudaIpcOpenMemHandle: %s", cudaGetErrorString(e));
+    return RT_OK;
+}
+
+int rt_peer_close(int device, void* ptr) {
+    DeviceGuard g(device);
+    if (ptr && cudaIpcCloseMemHandle(ptr) != cudaSuccess) return rtb::fail(RT_ERR_CUDA, "rt_peer_close failed");
+    return RT_OK;
+}
+
+int rt_peer_free(int device, void* ptr) {
+    DeviceGuard g(device);
+    if (ptr) cudaFree(ptr);
+    return RT_OK;
+}
+
+int rt_scene_push_rows(rt_scene* s, const void* band, void* frame, int32_t W, int32_t bytes_per_pixel, int32_t row_begin, int32_t row_step, int32_t rows) {
+    if (!s || !band || !frame || W <= 0 || bytes_per_pixel <= 0 || row_begin < 0 || row_step < 1 || rows < 0)
+        return rtb::fail(RT_ERR_INVALID, "rt_scene_push_rows: bad argument");
+    if (rows == 0) return RT_OK;
+    DeviceGuard g(s->device);
+    const size_t line = (size_t)W * bytes_per_pixel;
+    CUDA_TRY(cudaMemcpy2DAsync((unsigned char*)frame + (size_t)row_begin * line, (size_t)row_step * line, band, line, line, (size_t)rows, cudaMemcpyDefault, s->stream));
+    return RT_OK;
+}
+
 /* Device self-test used by tests/: agreement of the reciprocal-based division with div.rn.f32.
  * out[0] mismatches (1 correction step), out[1] mismatches (2 steps), out[2] pairs tested. */
 int rt_selftest_division(int device, uint64_t seed, int blocks, int per_thread, uint64_t out[3]) {
