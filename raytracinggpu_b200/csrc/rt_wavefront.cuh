@@ -740,13 +740,14 @@ __device__ __forceinline__ void leaf_triangles(const SceneHeader& h, const WfArg
     const float4* p = reinterpret_cast<const float4*>(q);
     const float4 p0 = __ldg(p), p1 = __ldg(p + 1); /* origin, direction: read-only in this kernel (L1-cached); res below is not */
     const F3 O = f3(p0.x, p0.y, p0.z), u = f3(p1.x, p1.y, p1.z);
-    const unsigned long long cur = __ldcg(&q->res);
     float t_limit;
     if (any) {
-        if (cur != 0ull) return; /* a blocker was already found */
+        if (__ldcg(&q->res) != 0ull) return; /* a blocker was already found */
         t_limit = sqrtf(p0.w) * 1.001f + 1e-3f; /* a hit with t > 1.001 sqrt(D2) cannot satisfy the shadow predicate (|t u| ~ t) */
     } else {
-        t_limit = cur != WF_NOHIT ? __uint_as_float((unsigned)(cur >> 32)) : RTK_INF;
+        /* the closest sphere of this segment (aux): a mesh hit certainly behind it loses the merge in wf_shade whatever its
+         * rank, so the screen may drop it (it keeps equal t: the mesh wins a tie against a sphere of higher id) */
+        t_limit = p0.w;
     }
     const int i_begin = code >> 2, i_end = min(i_begin + (code & 3) + 1, h.n_tris);
     for (int k = i_begin; k < i_end; k += 2) {
