@@ -790,7 +790,7 @@ __global__ void __launch_bounds__(WF_THREADS) wf_leaves(const __grid_constant__ 
                                                        const __grid_constant__ WfArgs g) {
     /* Two phases per warp, both with full lanes: the box phase takes 32 tasks and keeps those whose box passes the slab
      * test (about half) in a small per-warp buffer; whenever the buffer holds 32 of them the triangle phase runs on 32. */
-    __shared__ int2 hitbuf[WF_THREADS / 32][64];
+    __shared__ int2 hitbuf[WF_THREADS / 32][96]; /* < 32 left over + up to 64 new */
     const unsigned FULL = 0xffffffffu;
     const float4* tris = reinterpret_cast<const float4*>(blob + h.off_tris);
     const float4* leaves = reinterpret_cast<const float4*>(blob + h.off_leaves);
@@ -800,31 +800,46 @@ __global__ void __launch_bounds__(WF_THREADS) wf_leaves(const __grid_constant__ 
     const unsigned lt = (1u << lane) - 1u;
     int2* const buf = hitbuf[threadIdx.x >> 5];
     int fill = 0; /* warp-uniform */
-    const int n_round = (n + 31) & ~31;
-    const int stride = gridDim.x * WF_THREADS;
-    int i = blockIdx.x * WF_THREADS + threadIdx.x;
-    int2 task = i < n ? g.tasks[i] : make_int2(0, 0);
+    /* a lane takes TWO consecutive tasks per step (one 16-byte load): they usually belong to the same ray, whose slab
+     * constants are then formed once, and the two leaf records are in flight together */
+    const int n_round = (n + 63) & ~63;
+    const int stride = gridDim.x * WF_THREADS * 2;
+    int i = (blockIdx.x * WF_THREADS + threadIdx.x) * 2;
+    const int4* const tasks2 = reinterpret_cast<const int4*>(g.tasks);
+    int4 task = i < n ? __ldg(tasks2 + (i >> 1)) : make_int4(0, 0, 0, 0);
     for (; i < n_round; i += stride) {
-        const int2 next = (i + stride < n) ? g.tasks[i + stride] : make_int2(0, 0); /* requested one iteration ahead */
-        bool hit = false;
-        int code = 0;
+        const int4 next = (i + stride < n) ? __ldg(tasks2 + ((i + stride) >> 1)) : make_int4(0, 0, 0, 0); /* requested one iteration ahead */
+        bool hit0 = false, hit1 = false;
+        int code0 = 0, code1 = 0;
         if (i < n) {
+            const bool two = i + 1 < n;
             const QEntry* q = ((task.x < 0) ? g.qS : qA) + (task.x & 0x7fffffff);
             const float4* p = reinterpret_cast<const float4*>(q);
             const float4 p0 = __ldg(p), p1 = __ldg(p + 1);
-            float4 l0, l1;
+            float4 l0, l1, m0, m1;
             ldg256(leaves + 2 * (size_t)task.y, l0, l1);
-            const RayCtx ctx = make_ray_ctx(f3(p0.x, p0.y, p0.z), f3(p1.x, p1.y, p1.z), h.box_abs[0], h.box_abs[1], h.box_abs[2]);
+            ldg256(leaves + 2 * (size_t)(two ? task.w : task.y), m0, m1);
+            RayCtx ctx = make_ray_ctx(f3(p0.x, p0.y, p0.z), f3(p1.x, p1.y, p1.z), h.box_abs[0], h.box_abs[1], h.box_abs[2]);
             float tn;
             unsigned fb = 0;
-            hit = slab_fast(l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, ctx, tn, fb);
-            code = __float_as_int(l1.z);
+            hit0 = slab_fast(l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, ctx, tn, fb);
+            code0 = __float_as_int(l1.z);
+            if (two) {
+                if (task.z != task.x) { /* the second task starts the next ray */
+                    const float4* r = reinterpret_cast<const float4*>(((task.z < 0) ? g.qS : qA) + (task.z & 0x7fffffff));
+                    const float4 r0 = __ldg(r), r1 = __ldg(r + 1);
+                    ctx = make_ray_ctx(f3(r0.x, r0.y, r0.z), f3(r1.x, r1.y, r1.z), h.box_abs[0], h.box_abs[1], h.box_abs[2]);
+                }
+                hit1 = slab_fast(m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, ctx, tn, fb);
+                code1 = __float_as_int(m1.z);
+            }
         }
-        const unsigned m = __ballot_sync(FULL, hit);
-        if (hit) buf[fill + __popc(m & lt)] = make_int2(task.x, code);
-        fill += __popc(m);
+        const unsigned b0 = __ballot_sync(FULL, hit0), b1 = __ballot_sync(FULL, hit1);
+        if (hit0) buf[fill + __popc(b0 & lt)] = make_int2(task.x, code0);
+        if (hit1) buf[fill + __popc(b0) + __popc(b1 & lt)] = make_int2(task.z, code1);
+        fill += __popc(b0) + __popc(b1);
         __syncwarp();
-        if (fill >= 32) {
+        while (fill >= 32) {
             const int2 t = buf[fill - 32 + lane];
             fill -= 32;
             leaf_triangles<STOCH>(h, g, tris, ((t.x < 0) ? g.qS : qA) + (t.x & 0x7fffffff), t.x < 0, t.y);
