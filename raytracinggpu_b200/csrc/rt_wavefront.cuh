@@ -610,7 +610,7 @@ __device__ __forceinline__ void answer_deferred(const SceneHeader& h, const unsi
 
 /* ---- wf_generate: one thread per pixel (a warp covers an 8x4 tile) ------------------------------------------------ */
 template <bool COUNT, bool STOCH>
-__global__ void __launch_bounds__(WF_THREADS) wf_generate(const __grid_constant__ SceneHeader h, const unsigned char* __restrict__ blob,
+__global__ void __launch_bounds__(WF_THREADS, 10) wf_generate(const __grid_constant__ SceneHeader h, const unsigned char* __restrict__ blob,
                                                          const __grid_constant__ WfArgs g) {
     const RenderArgs& a = g.a;
     const float4* nodes = reinterpret_cast<const float4*>(blob + h.off_nodes);
