@@ -175,6 +175,7 @@ __device__ __forceinline__ bool outside_contract(F3 u) {
 __device__ __forceinline__ void closest_sphere_cam(const SceneHeader& h, const float4* __restrict__ cam_sph, F3 u, float& ts, int& sidx) {
     ts = RTK_INF;
     sidx = -1;
+#pragma unroll 2
     for (int k = 0; k < h.n_spheres; k++) {
         const float4 c = cam_sph[k];
         const float b = dot(u, f3(c.x, c.y, c.z));
@@ -195,6 +196,7 @@ __device__ __forceinline__ void closest_sphere_cam(const SceneHeader& h, const f
 __device__ __forceinline__ void closest_sphere(const SceneHeader& h, F3 O, F3 u, float& ts, int& sidx) {
     ts = RTK_INF;
     sidx = -1;
+#pragma unroll 2
     for (int k = 0; k < h.n_spheres; k++) { /* ascending id, strict < (optimized.cu:543-554) */
         float t;
         if (sphere_t(h.spheres[k], O, u, t) && t < ts) {
@@ -389,9 +391,12 @@ __device__ __forceinline__ void path_advance(const SceneHeader& h, const WfArgs&
             /* shadow ray: the spheres here, the mesh through the queue (see mesh_query for the equivalence) */
             w.rays++;
             bool blocked = false;
-            for (int s = 0; s < h.n_spheres && !blocked; s++) {
+            /* no early exit: a sphere that blocks is rare, and without the exit the tests are independent of one another */
+#pragma unroll 2
+            for (int s = 0; s < h.n_spheres; s++) {
                 float t;
-                if (sphere_t(h.spheres[s], Padj, su, t) && t < RTK_INF && blocks_light(Padj, su, t, D2)) blocked = true;
+                const bool hit = sphere_t(h.spheres[s], Padj, su, t) && t < RTK_INF && blocks_light(Padj, su, t, D2);
+                blocked = blocked || hit;
             }
             F3 dcol = f3(0.f, 0.f, 0.f);
             if (!blocked) {
