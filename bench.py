@@ -296,7 +296,7 @@ def run_ours(args):
                 "traffic": traffic, "traffic_source": "dram__bytes_read+write summed over the render launches of one frame, profiles/%s" % traffic_src if traffic_src else None, "peak_source": peak_src,
                 "note": "per FRAME (generate + leaves + shade launches; no single dominant kernel). Algorithmic bytes = SURVEY.md 8d: 32 B per box test and 48 B per triangle test of "
                         "the reference's own traversal (node visits / triangle tests counted by the instrumented tree search). The anchored-ray bins find the same leaves with a "
-                        "quarter of the box tests, so the achieved figure is work the reference algorithm defines divided by the time this path needs; the scene (0.4 MB) is "
+                        "quarter of the box tests, so the achieved figure is work the reference algorithm defines divided by the time this path needs (it can exceed the HBM peak: most of those bytes are never moved; measured DRAM traffic is `traffic`); the scene (0.4 MB) is "
                         "L1/L2-resident and the binding limits are instruction issue (generate) and LSU wavefronts (leaves), see profiles/ and fp32",
                 "algorithmic_bytes_per_launch": int(alg_bytes), "node_visits": int(work["node_visits"]), "tri_tests": int(work["tri_tests"]),
                 "fp32": {"achieved_tflops": round(alg_flop / (kernel_ms * 1e-3) / 1e12, 3), "peak_tflops": round(148 * 128 * 2 * 1.965e9 / 1e12, 1),
