@@ -1132,6 +1132,9 @@ int rt_render(rt_scene* s, const rt_params* p, uint32_t flags, uint8_t* rgb_out,
                 anchored = s->bins[0].usable && s->bins[1].usable;
             }
             s->last_was_anchored = anchored;
+            /* no mirror, no refractive object: the kernels without the reflection / refraction code (smaller, less instruction fetch) */
+            bool diffuse_only = !(h.has_mesh && (h.mesh_mirror || h.mesh_n_in != h.mesh_n_out)) && !(getenv("RT_DIFFUSE_KERNELS") && atoi(getenv("RT_DIFFUSE_KERNELS")) == 0);
+            for (int k = 0; k < h.n_spheres; k++) diffuse_only = diffuse_only && !h.spheres[k].mirror && h.spheres[k].n_in == h.spheres[k].n_out;
             /* round 0 holds tree-searched queries only when a path can go on inside wf_generate: past a mirror or refractive
              * sphere, or along the indirect bounce of a pixel shaded on the spot */
             bool trav_round0 = stochastic && p->indirect;
@@ -1342,6 +1345,7 @@ int rt_render(rt_scene* s, const rt_params* p, uint32_t flags, uint8_t* rgb_out,
                         else rtk::wf_generate<false, true><<<gen_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
                     } else {
                         if (count) rtk::wf_generate<true, false><<<gen_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
+                        else if (diffuse_only) rtk::wf_generate<false, false, true><<<gen_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
                         else rtk::wf_generate<false, false><<<gen_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
                     }
                     launches++;
@@ -1397,6 +1401,7 @@ int rt_render(rt_scene* s, const rt_params* p, uint32_t flags, uint8_t* rgb_out,
                             else rtk::wf_shade<false, true><<<shade_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
                         } else {
                             if (count) rtk::wf_shade<true, false><<<shade_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
+                            else if (diffuse_only) rtk::wf_shade<false, false, true><<<shade_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
                             else rtk::wf_shade<false, false><<<shade_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
                         }
                         launches++;

@@ -264,7 +264,9 @@ __device__ __forceinline__ void light_is_blocked(const RenderArgs& a, const WfAr
  * STOCH (stochastic mode, one pass per sample): nothing is written to the framebuffer here; every diffuse hit leaves a
  * (direct, albedo) record for wf_fold, draws the two uniforms of optimized.cu:633-634 from the pixel's stream and, with
  * the indirect bounce enabled, goes on along the cosine-weighted direction. */
-template <bool COUNT, bool STOCH>
+/* DIFFUSE: the host knows that no object of the scene is a mirror or refractive (every path ends at its first hit): the
+ * reflection / refraction code is left out of the kernel (67 KB of SASS otherwise; instruction fetch is wf_generate's top stall) */
+template <bool COUNT, bool STOCH, bool DIFFUSE = false>
 __device__ __forceinline__ void path_advance(const SceneHeader& h, const WfArgs& g, const float4* __restrict__ nodes, const float4* __restrict__ tris, int px, F3 O, F3 u, float n_ray,
                                              int depth, bool have_hit, float t_hit, int sidx, int tri, Work& w, Post& post) {
     const RenderArgs& a = g.a;
@@ -358,11 +360,11 @@ __device__ __forceinline__ void path_advance(const SceneHeader& h, const WfArgs&
             n_in = h.mesh_n_in;
             n_out = h.mesh_n_out;
         }
-        if (mirror) { /* :572-579 */
+        if (!DIFFUSE && mirror) { /* :572-579 */
             const F3 nu = u - (2 * dot(u, N)) * N;
             O = P + eps * N;
             u = nu;
-        } else if (n_in != n_out) { /* :580-609 */
+        } else if (!DIFFUSE && n_in != n_out) { /* :580-609 */
             float ratio;
             const bool out2in = n_ray == n_out;
             if (out2in) {
@@ -614,7 +616,7 @@ __device__ __forceinline__ void answer_deferred(const SceneHeader& h, const unsi
 }
 
 /* ---- wf_generate: one thread per pixel (a warp covers an 8x4 tile) ------------------------------------------------ */
-template <bool COUNT, bool STOCH>
+template <bool COUNT, bool STOCH, bool DIFFUSE = false>
 __global__ void __launch_bounds__(WF_THREADS, 10) wf_generate(const __grid_constant__ SceneHeader h, const unsigned char* __restrict__ blob,
                                                          const __grid_constant__ WfArgs g) {
     const RenderArgs& a = g.a;
@@ -667,7 +669,7 @@ __global__ void __launch_bounds__(WF_THREADS, 10) wf_generate(const __grid_const
             if (a.hit_t) a.hit_t[px] = RTK_INF;
             if (a.shadow) a.shadow[px] = 2;
         }
-        path_advance<COUNT, STOCH>(h, g, nodes, tris, px, f3(a.camx, a.camy, a.camz), u0, 1.f, 0, false, 0.f, -1, -1, w, post);
+        path_advance<COUNT, STOCH, DIFFUSE>(h, g, nodes, tris, px, f3(a.camx, a.camy, a.camz), u0, 1.f, 0, false, 0.f, -1, -1, w, post);
     }
     const int slot = post_queries(g, 0, post, px);
     if (g.anchored) {
@@ -678,7 +680,7 @@ __global__ void __launch_bounds__(WF_THREADS, 10) wf_generate(const __grid_const
 }
 
 /* ---- wf_shade: one thread per answered closest-hit query of round g.round ------------------------------------------ */
-template <bool COUNT, bool STOCH>
+template <bool COUNT, bool STOCH, bool DIFFUSE = false>
 __global__ void __launch_bounds__(WF_THREADS, 8) wf_shade(const __grid_constant__ SceneHeader h, const unsigned char* __restrict__ blob,
                                                       const __grid_constant__ WfArgs g) {
     const RenderArgs& a = g.a;
@@ -720,7 +722,7 @@ __global__ void __launch_bounds__(WF_THREADS, 8) wf_shade(const __grid_constant_
 #ifdef RT_TRACE
             printf("  shade e %d px %d key %llx t_hit %f sidx %d tri %d depth %d\n", e, px, key, t_hit, sidx, tri, depth);
 #endif
-            path_advance<COUNT, STOCH>(h, g, nodes, tris, px, O, u, p2.x, depth, true, t_hit, sidx, tri, w, post);
+            path_advance<COUNT, STOCH, DIFFUSE>(h, g, nodes, tris, px, O, u, p2.x, depth, true, t_hit, sidx, tri, w, post);
         }
         const int slot = post_queries(g, g.round + 1, post, px);
         if (g.anchored) {
