@@ -1342,6 +1342,7 @@ int rt_render(rt_scene* s, const rt_params* p, uint32_t flags, uint8_t* rgb_out,
                                                  sizeof(rtk::WfCounters) - offsetof(rtk::WfCounters, nA), stream));
                     if (stochastic) {
                         if (count) rtk::wf_generate<true, true><<<gen_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
+                        else if (diffuse_only) rtk::wf_generate<false, true, true><<<gen_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
                         else rtk::wf_generate<false, true><<<gen_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
                     } else {
                         if (count) rtk::wf_generate<true, false><<<gen_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
@@ -1398,6 +1399,7 @@ int rt_render(rt_scene* s, const rt_params* p, uint32_t flags, uint8_t* rgb_out,
                         if (r == segments) break;
                         if (stochastic) {
                             if (count) rtk::wf_shade<true, true><<<shade_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
+                            else if (diffuse_only) rtk::wf_shade<false, true, true><<<shade_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
                             else rtk::wf_shade<false, true><<<shade_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
                         } else {
                             if (count) rtk::wf_shade<true, false><<<shade_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
