@@ -1346,6 +1346,7 @@ int rt_render(rt_scene* s, const rt_params* p, uint32_t flags, uint8_t* rgb_out,
                         else rtk::wf_generate<false, true><<<gen_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
                     } else {
                         if (count) rtk::wf_generate<true, false><<<gen_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
+                        else if (diffuse_only && anchored) rtk::wf_generate<false, false, true, true><<<gen_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
                         else if (diffuse_only) rtk::wf_generate<false, false, true><<<gen_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
                         else rtk::wf_generate<false, false><<<gen_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
                     }
@@ -1403,6 +1404,7 @@ int rt_render(rt_scene* s, const rt_params* p, uint32_t flags, uint8_t* rgb_out,
                             else rtk::wf_shade<false, true><<<shade_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
                         } else {
                             if (count) rtk::wf_shade<true, false><<<shade_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
+                            else if (diffuse_only && anchored) rtk::wf_shade<false, false, true, true><<<shade_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
                             else if (diffuse_only) rtk::wf_shade<false, false, true><<<shade_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
                             else rtk::wf_shade<false, false><<<shade_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
                         }

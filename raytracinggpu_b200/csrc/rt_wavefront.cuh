@@ -266,7 +266,10 @@ __device__ __forceinline__ void light_is_blocked(const RenderArgs& a, const WfAr
  * the indirect bounce enabled, goes on along the cosine-weighted direction. */
 /* DIFFUSE: the host knows that no object of the scene is a mirror or refractive (every path ends at its first hit): the
  * reflection / refraction code is left out of the kernel (67 KB of SASS otherwise; instruction fetch is wf_generate's top stall) */
-template <bool COUNT, bool STOCH, bool DIFFUSE = false>
+/* LEAN (with DIFFUSE, deterministic mode, anchored-ray bins in use — the primary + shadow pipeline): every query is an
+ * anchored one and every path ends at its first hit, so the tree-search branches (root-box tests with their exact
+ * fallbacks, the general sphere search, the posting of tree-searched queries) are left out as well. */
+template <bool COUNT, bool STOCH, bool DIFFUSE = false, bool LEAN = false>
 __device__ __forceinline__ void path_advance(const SceneHeader& h, const WfArgs& g, const float4* __restrict__ nodes, const float4* __restrict__ tris, int px, F3 O, F3 u, float n_ray,
                                              int depth, bool have_hit, float t_hit, int sidx, int tri, Work& w, Post& post) {
     const RenderArgs& a = g.a;
@@ -280,10 +283,10 @@ __device__ __forceinline__ void path_advance(const SceneHeader& h, const WfArgs&
                 return;
             }
             w.rays++;
-            if (depth == 0) closest_sphere_cam(h, g.cam_sph, u, t_hit, sidx); /* depth 0 without a hit: the camera ray (wf_generate) */
+            if (LEAN || depth == 0) closest_sphere_cam(h, g.cam_sph, u, t_hit, sidx); /* depth 0 without a hit: the camera ray (wf_generate) */
             else closest_sphere(h, O, u, t_hit, sidx);
             tri = -1;
-            if (h.has_mesh && g.anchored && depth == 0) {
+            if (h.has_mesh && (LEAN || (g.anchored && depth == 0))) {
                 /* a camera ray: its candidate leaves come from the camera's bins (rt_bins.cuh) */
                 /* a zero / subnormal / non-finite component is outside the bins' contract: the query is posted without
                  * candidates (cand_count -1) and answered by the exact tree search at the end of the kernel (answer_exact) */
@@ -314,7 +317,7 @@ __device__ __forceinline__ void path_advance(const SceneHeader& h, const WfArgs&
                         return;
                     }
                 }
-            } else if (h.has_mesh) {
+            } else if (!LEAN && h.has_mesh) {
                 const RayCtx ctx = make_ray_ctx(O, u, h.box_abs[0], h.box_abs[1], h.box_abs[2]);
                 float tn;
                 if (slab_fast(h.root_mn[0], h.root_mn[1], h.root_mn[2], h.root_mx[0], h.root_mx[1], h.root_mx[2], ctx, tn, w.slab_fallbacks)) {
@@ -421,7 +424,7 @@ __device__ __forceinline__ void path_advance(const SceneHeader& h, const WfArgs&
                 *types |= 1 << seg;
                 if (seg == 0 && first_sample && a.shadow) a.shadow[px] = blocked ? 1 : 0;
             }
-            if (!blocked && h.has_mesh && g.anchored) {
+            if (!blocked && h.has_mesh && (LEAN || g.anchored)) {
                 /* a shadow ray: its candidate leaves come from the light's bins */
                 const bool exact = outside_contract(su) || !(D2 <= g.bins[1].max_D2) || __ldg(g.bins[1].status) != 0; /* outside the bins' contract: see the camera rays above */
                 int c0 = 0, c1 = -1;
@@ -449,7 +452,7 @@ __device__ __forceinline__ void path_advance(const SceneHeader& h, const WfArgs&
                         post.cand_count = c1 - c0;
                     }
                 }
-            } else if (!blocked && h.has_mesh) {
+            } else if (!LEAN && !blocked && h.has_mesh) {
                 const RayCtx ctx = make_ray_ctx(Padj, su, h.box_abs[0], h.box_abs[1], h.box_abs[2]);
                 float tn;
                 if (slab_fast(h.root_mn[0], h.root_mn[1], h.root_mn[2], h.root_mx[0], h.root_mx[1], h.root_mx[2], ctx, tn, w.slab_fallbacks)) {
@@ -496,13 +499,15 @@ __device__ __forceinline__ void path_advance(const SceneHeader& h, const WfArgs&
 
 /* Append the warp's queries to the global queues of round post_round: one atomic per warp and queue. Must be
  * called by all 32 lanes together (the offsets come from full-mask ballots). */
+template <bool LEAN = false>
 __device__ __forceinline__ int post_queries(const WfArgs& g, int post_round, const Post& post, int px) {
     int my_slot = -1; /* queue entry of this lane's first query (closest or shadow), for the anchored tasks */
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
     const bool wantB = post.kind == WF_MODE_CLOSEST && post.cand_count != 0; /* anchored closest-hit query (camera ray); -1: to be answered exactly */
-    const bool wantA = post.kind == WF_MODE_CLOSEST && !wantB, wantS = post.kind == WF_MODE_ANY, want2 = post.kind2 == WF_MODE_CLOSEST;
+    /* LEAN: no tree-searched query can be posted (every closest-hit query is a camera ray with candidates, no second query) */
+    const bool wantA = !LEAN && post.kind == WF_MODE_CLOSEST && !wantB, wantS = post.kind == WF_MODE_ANY, want2 = !LEAN && post.kind2 == WF_MODE_CLOSEST;
     const unsigned mB = __ballot_sync(FULL, wantB);
     if (mB) {
         int baseB = 0;
@@ -513,9 +518,9 @@ __device__ __forceinline__ int post_queries(const WfArgs& g, int post_round, con
             store_entry(g.qA[post_round & 1], my_slot, post.O, post.u, post.aux, px, post.n_ray, post.packed, WF_NOHIT);
         }
     }
-    const unsigned mA = __ballot_sync(FULL, wantA);
+    const unsigned mA = LEAN ? 0u : __ballot_sync(FULL, wantA);
     const unsigned mS = __ballot_sync(FULL, wantS);
-    const unsigned m2 = __ballot_sync(FULL, want2);
+    const unsigned m2 = LEAN ? 0u : __ballot_sync(FULL, want2);
     int baseA = 0, baseS = 0;
     if (lane == 0) {
         if (mA | m2) baseA = atomicAdd(&g.c->nA[post_round], __popc(mA) + __popc(m2));
@@ -616,7 +621,7 @@ __device__ __forceinline__ void answer_deferred(const SceneHeader& h, const unsi
 }
 
 /* ---- wf_generate: one thread per pixel (a warp covers an 8x4 tile) ------------------------------------------------ */
-template <bool COUNT, bool STOCH, bool DIFFUSE = false>
+template <bool COUNT, bool STOCH, bool DIFFUSE = false, bool LEAN = false>
 __global__ void __launch_bounds__(WF_THREADS, 10) wf_generate(const __grid_constant__ SceneHeader h, const unsigned char* __restrict__ blob,
                                                          const __grid_constant__ WfArgs g) {
     const RenderArgs& a = g.a;
@@ -669,10 +674,10 @@ __global__ void __launch_bounds__(WF_THREADS, 10) wf_generate(const __grid_const
             if (a.hit_t) a.hit_t[px] = RTK_INF;
             if (a.shadow) a.shadow[px] = 2;
         }
-        path_advance<COUNT, STOCH, DIFFUSE>(h, g, nodes, tris, px, f3(a.camx, a.camy, a.camz), u0, 1.f, 0, false, 0.f, -1, -1, w, post);
+        path_advance<COUNT, STOCH, DIFFUSE, LEAN>(h, g, nodes, tris, px, f3(a.camx, a.camy, a.camz), u0, 1.f, 0, false, 0.f, -1, -1, w, post);
     }
-    const int slot = post_queries(g, 0, post, px);
-    if (g.anchored) {
+    const int slot = post_queries<LEAN>(g, 0, post, px);
+    if (LEAN || g.anchored) {
         emit_tasks(g, 0, post, slot);
         answer_deferred<STOCH>(h, blob, g, 0, post, slot);
     }
@@ -680,7 +685,7 @@ __global__ void __launch_bounds__(WF_THREADS, 10) wf_generate(const __grid_const
 }
 
 /* ---- wf_shade: one thread per answered closest-hit query of round g.round ------------------------------------------ */
-template <bool COUNT, bool STOCH, bool DIFFUSE = false>
+template <bool COUNT, bool STOCH, bool DIFFUSE = false, bool LEAN = false>
 __global__ void __launch_bounds__(WF_THREADS, 8) wf_shade(const __grid_constant__ SceneHeader h, const unsigned char* __restrict__ blob,
                                                       const __grid_constant__ WfArgs g) {
     const RenderArgs& a = g.a;
@@ -722,10 +727,10 @@ __global__ void __launch_bounds__(WF_THREADS, 8) wf_shade(const __grid_constant_
 #ifdef RT_TRACE
             printf("  shade e %d px %d key %llx t_hit %f sidx %d tri %d depth %d\n", e, px, key, t_hit, sidx, tri, depth);
 #endif
-            path_advance<COUNT, STOCH, DIFFUSE>(h, g, nodes, tris, px, O, u, p2.x, depth, true, t_hit, sidx, tri, w, post);
+            path_advance<COUNT, STOCH, DIFFUSE, LEAN>(h, g, nodes, tris, px, O, u, p2.x, depth, true, t_hit, sidx, tri, w, post);
         }
-        const int slot = post_queries(g, g.round + 1, post, px);
-        if (g.anchored) {
+        const int slot = post_queries<LEAN>(g, g.round + 1, post, px);
+        if (LEAN || g.anchored) {
             emit_tasks(g, g.round + 1, post, slot);
             answer_deferred<STOCH>(h, blob, g, g.round + 1, post, slot);
         }
