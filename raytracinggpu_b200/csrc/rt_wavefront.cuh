@@ -548,6 +548,7 @@ __device__ __forceinline__ void emit_tasks(const WfArgs& g, int post_round, cons
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const bool mine = slot >= 0 && (post.kind == WF_MODE_CLOSEST || post.kind == WF_MODE_ANY) && post.cand_count > 0;
+    if (!__any_sync(FULL, mine)) return; /* most warps of a frame never meet the mesh */
     const int n = mine ? post.cand_count : 0;
     int incl = n;
 #pragma unroll
