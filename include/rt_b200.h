@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define RT_ABI_VERSION 1
+#define RT_ABI_VERSION 2
 
 enum {
     RT_OK = 0,
@@ -168,6 +168,24 @@ int rt_scene_create(rt_scene** out, int device);
 void rt_scene_destroy(rt_scene* s);
 /* Use an existing CUDA stream (a cudaStream_t cast to void*) instead of the scene's own. */
 int rt_scene_set_stream(rt_scene* s, void* cuda_stream);
+/* Tuning and cross-check options of a scene (the reference has none: its variants are separate programs under
+ * different-versions/). Every option selects among code paths that give identical results; the defaults are the production
+ * choices. Options are part of the scene's state: nothing is read from the environment after rt_scene_create (which
+ * presets an option from RT_<KEY> when that variable is set — a convenience for the tools/ scripts). Keys (int values):
+ *   "variant" 0|1|2           0 one-thread-per-pixel kernel, exact arithmetic; 1 the same with the certified fast paths;
+ *                             2 the wavefront pipeline (default)
+ *   "anchored" -1|0|1         anchored-ray bins for camera / shadow rays: by mesh size (default), off (tree search), on
+ *   "wide" -1|0|1             4-wide index for the tree search: default on for stochastic indirect bounces only
+ *   "strips" 0..8             row bands on separate streams, 0 = chosen per call
+ *   "bins_r", "task_factor", "npool_cap", "run_shift", "gss", "leaves_blocks", "side_stream", "diffuse_kernels",
+ *   "stoch_mega", "wide_count", "graph", "debug_times", "debug_pool", "debug_bins", "debug_cost"   (see rt_device.cu: RtOptions)
+ *   "transcendentals" 0|1     stochastic mode: log / cos / sin of optimized.cu:756-758, 635-636 evaluated in double and
+ *                             rounded once (0, default: agrees with the CPU oracle on every platform) or by CUDA's
+ *                             single-precision logf / cosf / sinf (1: what optimized.cu itself calls when compiled without
+ *                             --use_fast_math; frames then match that build of the reference's own GPU program)
+ * Unknown key or value out of range: RT_ERR_INVALID. */
+int rt_scene_set_option(rt_scene* s, const char* key, int64_t value);
+int rt_scene_get_option(rt_scene* s, const char* key, int64_t* value);
 int rt_scene_set_spheres(rt_scene* s, const rt_sphere* spheres, int32_t n);
 /* Upload the mesh in the reference interchange formats (what optimized.cu:814-826 copies) and repack it on
  * the device into the traversal layout. nt == 0 removes the mesh. */

@@ -7,8 +7,14 @@
  * hard-codes 512, :786-787) and CUDA events around the launch. This is the "beat this" baseline of
  * BASELINE.md §3; it is never part of the product path.
  *
- *   ref_optimized <obj> <W> <H> <num_rays> <num_bounce> <reps> [out.raw]
+ *   ref_optimized <obj> <W> <H> <num_rays> <num_bounce> <reps> [out.raw [ids_prefix]]
  * prints one JSON line with per-launch kernel times.
+ *
+ * Variants built from the same shim (oracle/Makefile): ref_optimized_ieee (the same unmodified source without
+ * --use_fast_math and with -fmad=false: the reference's arithmetic as written, one rounding per operation),
+ * ref_optimized_sigma0 / ref_optimized_ids (patched copies written by oracle/make_ref_variants.py into the git-ignored
+ * oracle/_ref/: sigma 0, and with -DREF_DUMP_IDS the first-segment object id / triangle index / t / shadow flag of every
+ * pixel as <ids_prefix>.obj.i32 .tri.i32 .t.f32 .shadow.u8).
  */
 #define main ref_optimized_main
 #include REF_GPU_SOURCE
@@ -54,11 +60,37 @@ int main(int argc, char** argv) {
 	 * launch is 160 B short and faults on sm_100a ("an illegal memory access", measured on the B200 box). The kernel is
 	 * left untouched; only the launch gets the bytes the kernel actually uses. */
 	const size_t smem = sizeof(char) * BLOCK_DIM * 3 + sizeof(Sphere) * 10 + sizeof(TriangleMesh) + sizeof(curandState) * BLOCK_DIM + sizeof(Scene) + 64;
+#ifdef REF_DUMP_IDS
+	const size_t npx = (size_t)H * W;
+	int *d_obj, *d_tri, *d_last_tri;
+	float *d_t, *d_last_t;
+	unsigned char* d_shadow;
+	gpuErrchk(cudaMalloc(&d_obj, npx * 4));
+	gpuErrchk(cudaMalloc(&d_tri, npx * 4));
+	gpuErrchk(cudaMalloc(&d_t, npx * 4));
+	gpuErrchk(cudaMalloc(&d_shadow, npx));
+	gpuErrchk(cudaMalloc(&d_last_tri, npx * 4));
+	gpuErrchk(cudaMalloc(&d_last_t, npx * 4));
+	gpuErrchk(cudaMemcpyToSymbol(rtb_dump_obj, &d_obj, sizeof d_obj));
+	gpuErrchk(cudaMemcpyToSymbol(rtb_dump_tri, &d_tri, sizeof d_tri));
+	gpuErrchk(cudaMemcpyToSymbol(rtb_dump_t, &d_t, sizeof d_t));
+	gpuErrchk(cudaMemcpyToSymbol(rtb_dump_shadow, &d_shadow, sizeof d_shadow));
+	gpuErrchk(cudaMemcpyToSymbol(rtb_last_tri, &d_last_tri, sizeof d_last_tri));
+	gpuErrchk(cudaMemcpyToSymbol(rtb_last_t, &d_last_t, sizeof d_last_t));
+#endif
 	cudaEvent_t e0, e1;
 	cudaEventCreate(&e0);
 	cudaEventCreate(&e1);
 	std::vector<float> ms;
 	for (int r = 0; r < reps + 3; r++) {
+#ifdef REF_DUMP_IDS
+		{ /* "not written yet" markers: obj -2, shadow 2 (= no diffuse first hit) */
+			std::vector<int> init(npx, -2);
+			gpuErrchk(cudaMemcpy(d_obj, init.data(), npx * 4, cudaMemcpyHostToDevice));
+			gpuErrchk(cudaMemset(d_tri, 0xff, npx * 4));
+			gpuErrchk(cudaMemset(d_shadow, 2, npx));
+		}
+#endif
 		cudaEventRecord(e0);
 		KernelLaunch<<<GRID_DIM, BLOCK_DIM, smem>>>(d_colors, W, H, num_rays, num_bounce, d_indices, mesh_ptr->indices.size(), d_vertices,
 		                                           mesh_ptr->vertices.size(), d_arr_bvh);
@@ -71,7 +103,10 @@ int main(int argc, char** argv) {
 	}
 	std::sort(ms.begin(), ms.end());
 	const float med = ms[ms.size() / 2];
-	printf("{\"impl\": \"reference optimized.cu KernelLaunch (sm_100a, --use_fast_math)\", \"W\": %d, \"H\": %d, \"num_rays\": %d, \"num_bounce\": %d, "
+#ifndef REF_VARIANT
+#define REF_VARIANT "sm_100a, --use_fast_math"
+#endif
+	printf("{\"impl\": \"reference optimized.cu KernelLaunch (" REF_VARIANT ")\", \"W\": %d, \"H\": %d, \"num_rays\": %d, \"num_bounce\": %d, "
 	       "\"reps\": %d, \"kernel_ms_median\": %.5f, \"kernel_ms_min\": %.5f, \"kernel_ms_max\": %.5f}\n",
 	       W, H, num_rays, num_bounce, reps, med, ms.front(), ms.back());
 	if (argc > 7) {
@@ -80,5 +115,19 @@ int main(int argc, char** argv) {
 		FILE* f = fopen(argv[7], "wb");
 		if (f) { fwrite(image.data(), 1, image_size, f); fclose(f); }
 	}
+#ifdef REF_DUMP_IDS
+	if (argc > 8) {
+		auto dump = [&](const char* ext, const void* dptr, size_t bytes) {
+			std::vector<char> h(bytes);
+			gpuErrchk(cudaMemcpy(h.data(), dptr, bytes, cudaMemcpyDeviceToHost));
+			FILE* f = fopen((std::string(argv[8]) + ext).c_str(), "wb");
+			if (f) { fwrite(h.data(), 1, bytes, f); fclose(f); }
+		};
+		dump(".obj.i32", d_obj, npx * 4);
+		dump(".tri.i32", d_tri, npx * 4);
+		dump(".t.f32", d_t, npx * 4);
+		dump(".shadow.u8", d_shadow, npx);
+	}
+#endif
 	return 0;
 }

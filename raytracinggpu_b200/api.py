@@ -52,6 +52,8 @@ SIGNATURES = {
     "rt_scene_create": (C.c_int, [C.POINTER(_vp), C.c_int]),
     "rt_scene_destroy": (None, [_vp]),
     "rt_scene_set_stream": (C.c_int, [_vp, _vp]),
+    "rt_scene_set_option": (C.c_int, [_vp, C.c_char_p, C.c_int64]),
+    "rt_scene_get_option": (C.c_int, [_vp, C.c_char_p, C.POINTER(C.c_int64)]),
     "rt_scene_set_spheres": (C.c_int, [_vp, C.POINTER(rt_sphere), _i32]),
     "rt_scene_set_mesh": (C.c_int, [_vp, _vp, _i32, _vp, _i32, _vp, _i32, _pf, _i32, _f, _f, _i32]),
     "rt_scene_set_light": (C.c_int, [_vp, _pf, _f]),
@@ -292,6 +294,15 @@ class Scene:
 
     def set_stream(self, cuda_stream):
         _check(lib().rt_scene_set_stream(self._h, C.c_void_p(int(cuda_stream))))
+
+    def set_option(self, key, value):
+        """rt_scene_set_option: tuning / cross-check options are scene state (never read from the environment per call)."""
+        _check(lib().rt_scene_set_option(self._h, key.encode(), int(value)))
+
+    def get_option(self, key):
+        v = C.c_int64()
+        _check(lib().rt_scene_get_option(self._h, key.encode(), C.byref(v)))
+        return v.value
 
     def set_spheres(self, spheres):
         arr = (rt_sphere * max(1, len(spheres)))(*spheres)

@@ -160,7 +160,7 @@ __global__ void bins_fill(const float4* __restrict__ leaves, int n_leaves, const
     const float4 q0 = leaves[2 * (size_t)l], q1 = leaves[2 * (size_t)l + 1];
     bins_leaf_cells(q0, q1, bv, threadIdx.x % BINS_GROUP, BINS_GROUP, [&](int cell) {
         const int at = cell_start[cell] + atomicSub(counts + cell, 1) - 1;
-        if (at < items_cap) items[at] = l;
+        if ((unsigned)at < (unsigned)items_cap) items[at] = l; /* unsigned: a scan that overflowed 2^31 gives negative offsets */
         else status[1] = 1; /* the lists outgrew the buffer (the anchor moved): rays of the cut lists take the exact search, the host enlarges it */
     });
 }

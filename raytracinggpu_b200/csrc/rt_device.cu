@@ -21,6 +21,7 @@
 #include <cstring>
 #include <functional>
 #include <new>
+#include <string>
 #include <vector>
 
 #define RT_NCOUNTERS 8
@@ -32,8 +33,63 @@
         if (e__ != cudaSuccess) return rtb::fail(RT_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
     } while (0)
 
+/* Tuning and cross-check options of a scene (rt_scene_set_option). Defaults are the production choices; every code path
+ * they select gives the same results. Read once per rt_render call from the scene, never from the environment. */
+struct RtOptions {
+    int variant = 2;         /* 0 render_mega, exact arithmetic; 1 render_mega with the certified fast paths; 2 wavefront pipeline */
+    int strips = 0;          /* row bands rendered concurrently on separate streams; 0: chosen per call */
+    int anchored = -1;       /* anchored-ray bins (rt_bins.cuh): -1 by mesh size, 0 off (tree search), 1 on */
+    int wide = -1;           /* 4-wide index for wf_traverse: -1 on for stochastic indirect bounces, 0 off, 1 on */
+    int wide_count = 0;      /* instrumented renders walk the wide index (node_visits then counts wide nodes) */
+    int bins_r = 0;          /* cells per face side of the bins; 0: 1024 (2048 beyond 200 k leaves) */
+    int task_factor = 0;     /* (ray, leaf) task buffer entries per pixel; 0: 8, doubled after an overflow */
+    int npool_cap = 0;       /* node pool entries per traversal warp; 0: by tree depth (a small pool forces the spill path) */
+    int stoch_mega = 0;      /* stochastic mode through the thread-per-pixel kernel render_stoch (in-library cross-check) */
+    int diffuse_kernels = 1; /* kernels without reflection / refraction code when no object needs it */
+    int side_stream = 1;     /* tree search of a round beside wf_leaves on a side stream */
+    int run_shift = -1;      /* log2 of wf_traverse's admission run length; -1: per launch */
+    int gss = 2;             /* guided self-scheduling factor of wf_traverse */
+    int leaves_blocks = 0;   /* resident blocks per SM for wf_leaves; 0: occupancy */
+    int transcendentals = 0; /* stochastic mode, log / cos / sin of optimized.cu:756-758, 635-636: 0 evaluated in double and rounded once
+                              * (what the CPU oracle computes), 1 CUDA's single-precision logf / cosf / sinf (what optimized.cu itself
+                              * calls when compiled without --use_fast_math: the parity pin against the reference's own GPU frames) */
+    int graph = 1;           /* replay a recorded CUDA graph when a frame repeats the previous call's plan */
+    int debug_times = 0, debug_pool = 0, debug_bins = 0, debug_cost = 0;
+    char debug_warps[256] = {0}; /* RT_DEBUG_WARPS=<file> at scene creation: per-warp timeline of wf_traverse (count_work renders) */
+};
+
+struct RtOptionKey {
+    const char* name;
+    int RtOptions::*field;
+    int lo, hi;
+};
+static const RtOptionKey kOptionKeys[] = {
+    {"variant", &RtOptions::variant, 0, 2},
+    {"strips", &RtOptions::strips, 0, 8},
+    {"anchored", &RtOptions::anchored, -1, 1},
+    {"wide", &RtOptions::wide, -1, 1},
+    {"wide_count", &RtOptions::wide_count, 0, 1},
+    {"bins_r", &RtOptions::bins_r, 0, 4096},
+    {"task_factor", &RtOptions::task_factor, 0, 256},
+    {"npool_cap", &RtOptions::npool_cap, 0, 4096},
+    {"stoch_mega", &RtOptions::stoch_mega, 0, 1},
+    {"diffuse_kernels", &RtOptions::diffuse_kernels, 0, 1},
+    {"side_stream", &RtOptions::side_stream, 0, 1},
+    {"run_shift", &RtOptions::run_shift, -1, 5},
+    {"gss", &RtOptions::gss, 0, 64},
+    {"leaves_blocks", &RtOptions::leaves_blocks, 0, 32},
+    {"transcendentals", &RtOptions::transcendentals, 0, 1},
+    {"graph", &RtOptions::graph, 0, 1},
+    {"debug_times", &RtOptions::debug_times, 0, 1},
+    {"debug_pool", &RtOptions::debug_pool, 0, 1},
+    {"debug_bins", &RtOptions::debug_bins, 0, 1},
+    {"debug_cost", &RtOptions::debug_cost, 0, 1},
+};
+
 struct rt_scene {
     int device = 0;
+    RtOptions opt;
+    bool plan_valid = false; /* a recorded frame graph matches the scene / options state */
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -58,7 +114,6 @@ struct rt_scene {
     /* kernel variant: 0 = render_mega, plain exact arithmetic; 1 = render_mega with the certified fast paths;
      * 2 = wavefront pipeline (rt_wavefront.cuh: streaming owner kernels + persistent queue traversal with work
      * stealing). Same results. RT_VARIANT overrides. */
-    int variant = 2;
     int max_leaf = 0;        /* largest leaf of the uploaded BVH */
     int trav_blocks_per_sm = 0, sm_count = 0;
     size_t trav_smem = 0;
@@ -66,8 +121,9 @@ struct rt_scene {
     size_t wf_capacity = 0;
     rtk::WfCounters* wf_counters = nullptr;
     rtk::WfCounters* h_wf_counters = nullptr; /* pinned */
+    unsigned long long* sticky = nullptr;     /* device, 2: task buffer / node pool overflow since the last rt_scene_sync (never cleared by rt_render) */
+    unsigned long long* h_sticky = nullptr;   /* pinned */
     bool last_was_wavefront = false;
-    int n_strips = 2;         /* row bands rendered concurrently on separate streams (RT_STRIPS overrides) */
     cudaStream_t strip_stream[RT_MAX_STRIPS] = {};
     cudaEvent_t strip_done[RT_MAX_STRIPS] = {};
     cudaEvent_t fork_ev = nullptr;
@@ -112,8 +168,6 @@ struct rt_scene {
     int task_factor = 8;     /* task buffer entries per pixel; doubled after an overflow */
     bool last_was_anchored = false;
     int leaves_blocks_per_sm = 0;
-    bool n_strips_from_env = false;
-    bool task_factor_from_env = false;
     int bins_builds = 0;
     size_t wf_spill_ints = 0;
     int* dbg_warps = nullptr; /* RT_DEBUG_WARPS=<file>: per-warp timeline of wf_traverse (count_work renders) */
@@ -121,6 +175,18 @@ struct rt_scene {
 };
 
 namespace {
+
+/* Convenience for the tools/ scripts: RT_<KEY> in the environment presets an option ONCE, when a scene is created
+ * (rt_scene_create). Nothing reads the environment afterwards; tests and callers use rt_scene_set_option. */
+void options_from_env(RtOptions& o) {
+    for (const RtOptionKey& k : kOptionKeys) {
+        std::string name = "RT_";
+        for (const char* c = k.name; *c; c++) name += (char)toupper((unsigned char)*c);
+        if (const char* v = getenv(name.c_str())) o.*(k.field) = std::max(k.lo, std::min(atoi(v), k.hi));
+    }
+    if (const char* v = getenv("RT_ANCHOR")) o.anchored = std::max(-1, std::min(atoi(v), 1)); /* round-1 spelling */
+    if (const char* v = getenv("RT_DEBUG_WARPS")) snprintf(o.debug_warps, sizeof o.debug_warps, "%s", v);
+}
 
 struct DeviceGuard {
     int prev = -1;
@@ -198,6 +264,7 @@ void reset_mesh_fields(SceneHeader& h) {
     h.n_wide = 0;
     h.wide_depth = 0;
     h.n_leaves = 0;
+    h.max_leaf = 0;
     for (int k = 0; k < 3; k++) {
         h.root_mn[k] = 0.f;
         h.root_mx[k] = 0.f;
@@ -214,13 +281,7 @@ void reset_mesh_fields(SceneHeader& h) {
 int ensure_bins(rt_scene* s, int which, const float A[3]) {
     rt_scene::AnchorBins& b = s->bins[which];
     const SceneHeader& h = s->header;
-    const int env_R = getenv("RT_BINS_R") ? atoi(getenv("RT_BINS_R")) : 0;
-    const int env_tf = getenv("RT_TASK_FACTOR") ? atoi(getenv("RT_TASK_FACTOR")) : 0; /* test hook: a small task buffer forces the overflow + repeat path */
-    if (env_tf > 0 && !s->task_factor_from_env) {
-        s->task_factor = env_tf;
-        s->task_factor_from_env = true;
-    }
-    const int R = env_R > 0 ? std::min(std::max(env_R, 8), 4096) : (h.n_leaves > 200000 ? 2048 : 1024);
+    const int R = s->opt.bins_r > 0 ? std::min(std::max(s->opt.bins_r, 8), 4096) : (h.n_leaves > 200000 ? 2048 : 1024);
     /* the status word of the previous build is copied to pinned memory right behind the build (no synchronisation): by the
      * time the anchor moves again it tells whether the lists outgrew the item buffer */
     if (b.h_status && b.h_status[1]) {
@@ -231,7 +292,7 @@ int ensure_bins(rt_scene* s, int which, const float A[3]) {
     /* the item buffer is sized by a read-back only when nothing is known about the lists: first build, or a mesh with a
      * different number of leaves; a mesh uploaded again (the per-frame upload of a caller that owns the geometry) keeps it */
     const bool first = b.R != R || b.items_cap == 0 || b.n_leaves != h.n_leaves;
-    static const bool dbg_bins = getenv("RT_DEBUG_BINS") != nullptr;
+    const bool dbg_bins = s->opt.debug_bins != 0;
     b.built = false;
     const float S = std::max(h.box_abs[0], std::max(h.box_abs[1], h.box_abs[2]));
     const float scale = S + std::max(std::fabs(A[0]), std::max(std::fabs(A[1]), std::fabs(A[2])));
@@ -396,11 +457,8 @@ int rt_scene_create(rt_scene** out, int device) {
     rt_scene* s = new (std::nothrow) rt_scene();
     if (!s) return rtb::fail(RT_ERR_NOMEM, "rt_scene_create: out of memory");
     s->device = device;
-    if (const char* v = getenv("RT_VARIANT")) s->variant = atoi(v);
-    if (const char* v = getenv("RT_STRIPS")) {
-        s->n_strips = std::max(1, std::min(atoi(v), RT_MAX_STRIPS));
-        s->n_strips_from_env = true;
-    }
+    options_from_env(s->opt);
+    if (s->opt.task_factor > 0) s->task_factor = s->opt.task_factor;
     memset(&s->header, 0, sizeof s->header);
     s->header.magic = RT_BLOB_MAGIC;
     s->header.layout_version = RT_LAYOUT_VERSION;
@@ -420,6 +478,10 @@ int rt_scene_create(rt_scene** out, int device) {
     if (err == cudaSuccess) err = cudaMalloc(&s->gamma_tab, 512 * sizeof(float));
     if (err == cudaSuccess) err = cudaMalloc(&s->counters, RT_NCOUNTERS * sizeof(unsigned long long));
     if (err == cudaSuccess) err = cudaMallocHost(&s->h_counters, RT_NCOUNTERS * sizeof(unsigned long long));
+    if (err == cudaSuccess) err = cudaMalloc(&s->sticky, 2 * sizeof(unsigned long long));
+    if (err == cudaSuccess) err = cudaMemset(s->sticky, 0, 2 * sizeof(unsigned long long));
+    if (err == cudaSuccess) err = cudaMallocHost(&s->h_sticky, 2 * sizeof(unsigned long long));
+    if (err == cudaSuccess) s->h_sticky[0] = s->h_sticky[1] = 0;
     if (err == cudaSuccess) err = cudaMemcpy(s->gamma_tab, tab.data(), 512 * sizeof(float), cudaMemcpyHostToDevice);
     if (err != cudaSuccess) {
         rtb::fail(RT_ERR_CUDA, "rt_scene_create: %s", cudaGetErrorString(err));
@@ -438,6 +500,8 @@ void rt_scene_destroy(rt_scene* s) {
     if (s->gamma_tab) cudaFree(s->gamma_tab);
     if (s->counters) cudaFree(s->counters);
     if (s->h_counters) cudaFreeHost(s->h_counters);
+    if (s->sticky) cudaFree(s->sticky);
+    if (s->h_sticky) cudaFreeHost(s->h_sticky);
     if (s->wf_queue) cudaFree(s->wf_queue);
     if (s->wf_counters) cudaFree(s->wf_counters);
     if (s->dbg_warps) cudaFree(s->dbg_warps);
@@ -482,6 +546,29 @@ int rt_scene_set_stream(rt_scene* s, void* cuda_stream) {
     s->stream = (cudaStream_t)cuda_stream;
     s->own_stream = false;
     return RT_OK;
+}
+
+int rt_scene_set_option(rt_scene* s, const char* key, int64_t value) {
+    if (!s || !key) return rtb::fail(RT_ERR_INVALID, "rt_scene_set_option: bad argument");
+    for (const RtOptionKey& k : kOptionKeys)
+        if (strcmp(k.name, key) == 0) {
+            if (value < k.lo || value > k.hi) return rtb::fail(RT_ERR_INVALID, "rt_scene_set_option: %s = %lld outside [%d, %d]", key, (long long)value, k.lo, k.hi);
+            s->opt.*(k.field) = (int)value;
+            if (k.field == &RtOptions::task_factor && value > 0) s->task_factor = (int)value;
+            s->plan_valid = false;
+            return RT_OK;
+        }
+    return rtb::fail(RT_ERR_INVALID, "rt_scene_set_option: unknown option '%s'", key);
+}
+
+int rt_scene_get_option(rt_scene* s, const char* key, int64_t* value) {
+    if (!s || !key || !value) return rtb::fail(RT_ERR_INVALID, "rt_scene_get_option: bad argument");
+    for (const RtOptionKey& k : kOptionKeys)
+        if (strcmp(k.name, key) == 0) {
+            *value = (k.field == &RtOptions::task_factor) ? s->task_factor : s->opt.*(k.field);
+            return RT_OK;
+        }
+    return rtb::fail(RT_ERR_INVALID, "rt_scene_get_option: unknown option '%s'", key);
 }
 
 int rt_scene_set_spheres(rt_scene* s, const rt_sphere* spheres, int32_t n) {
@@ -836,6 +923,7 @@ int rt_scene_set_mesh(rt_scene* s, const float* vertices, int32_t nv, const int3
     h.root_ref = root_ref;
     memcpy(h.box_abs, box_abs, sizeof box_abs);
     s->max_leaf = max_leaf;
+    h.max_leaf = max_leaf;
     h.off_nodes = off_nodes;
     h.off_tris = off_tris;
     h.off_wide = off_wide;
@@ -905,8 +993,10 @@ int rt_scene_blob_import(rt_scene* s, const void* device_ptr, size_t bytes) {
         CUDA_TRY(cudaStreamSynchronize(s->stream));
     }
     s->header = h;
+    s->max_leaf = h.max_leaf; /* host-side guard of the tie-break rank (push_order 0): travels with the blob */
     s->header_dirty = false;
     s->mesh_generation++; /* the anchored-ray bins of the previous mesh are stale */
+    s->plan_valid = false;
     return RT_OK;
 }
 
@@ -917,6 +1007,7 @@ int rt_scene_sync(rt_scene* s, rt_stats* stats) {
         if (s->last_was_wavefront && s->last_was_anchored)
             for (int k = 0; k < 2; k++)
                 if (s->bins[k].status) CUDA_TRY(cudaMemcpyAsync(s->bins[k].h_status, s->bins[k].status, 4 * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+        CUDA_TRY(cudaMemcpyAsync(s->h_sticky, s->sticky, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->stream));
         if (s->last_was_wavefront)
             CUDA_TRY(cudaMemcpyAsync(s->h_wf_counters, s->wf_counters, RT_MAX_STRIPS * sizeof(rtk::WfCounters), cudaMemcpyDeviceToHost, s->stream));
         else
@@ -944,8 +1035,14 @@ int rt_scene_sync(rt_scene* s, rt_stats* stats) {
             stats->launches = s->pending_launches;
         }
     }
-    const bool failed = s->pending && s->last_was_wavefront && s->h_counters[7] != 0;
-    if (s->pending && s->last_was_wavefront && getenv("RT_DEBUG_POOL")) {
+    /* overflow flags are sticky on the device: every frame enqueued since the last sync is covered, not just the last one */
+    const bool failed = s->pending && s->h_sticky[1] != 0;
+    const bool task_overflow = s->pending && s->h_sticky[0] != 0;
+    if (failed || task_overflow) {
+        s->h_sticky[0] = s->h_sticky[1] = 0;
+        CUDA_TRY(cudaMemsetAsync(s->sticky, 0, 2 * sizeof(unsigned long long), s->stream));
+    }
+    if (s->pending && s->last_was_wavefront && s->opt.debug_pool) {
         unsigned long long d[8];
         cudaMemcpy(d, s->wf_counters->dbg, sizeof d, cudaMemcpyDeviceToHost);
         rtk::WfCounters hc;
@@ -955,10 +1052,10 @@ int rt_scene_sync(rt_scene* s, rt_stats* stats) {
         fprintf(stderr, "[pool] N steps %llu tasks %llu (%.1f/step)  T steps %llu tasks %llu (%.1f/step)  admissions %llu\n", d[0], d[1],
                 d[0] ? (double)d[1] / d[0] : 0., d[2], d[3], d[2] ? (double)d[3] / d[2] : 0., d[4]);
     }
-    if (s->pending && s->last_was_wavefront && s->dbg_warps && getenv("RT_DEBUG_WARPS")) {
+    if (s->pending && s->last_was_wavefront && s->dbg_warps && s->opt.debug_warps[0]) {
         std::vector<int> hst(s->dbg_warps_ints);
         cudaMemcpy(hst.data(), s->dbg_warps, hst.size() * sizeof(int), cudaMemcpyDeviceToHost);
-        if (FILE* f = fopen(getenv("RT_DEBUG_WARPS"), "wb")) {
+        if (FILE* f = fopen(s->opt.debug_warps, "wb")) {
             fwrite(hst.data(), sizeof(int), hst.size(), f);
             fclose(f);
         }
@@ -966,14 +1063,13 @@ int rt_scene_sync(rt_scene* s, rt_stats* stats) {
     if (s->pending && s->last_was_wavefront && s->last_was_anchored)
         for (int k = 0; k < 2; k++)
             if (s->bins[k].h_status && s->bins[k].h_status[1]) s->bins[k].grow = true; /* results were right (exact search for the cut lists); the next build gets room */
-    const bool task_overflow = s->pending && s->last_was_wavefront && s->last_was_anchored && s->h_counters[6] != 0;
     s->pending = false;
     if (failed) return rtb::fail(RT_ERR_STATE, "rt_render: traversal task pool overflow (BVH deeper than the upload-time bound)");
     if (task_overflow) {
         /* more (ray, leaf) tasks than the buffer holds: the frame is incomplete. The next render gets a buffer twice the
          * size; a synchronous rt_render repeats the frame by itself. */
         s->task_factor = std::min(s->task_factor * 2, 256);
-        if (getenv("RT_DEBUG_POOL")) fprintf(stderr, "[tasks] buffer overflow, next frames get %d tasks per pixel\n", s->task_factor);
+        if (s->opt.debug_pool) fprintf(stderr, "[tasks] buffer overflow, next frames get %d tasks per pixel\n", s->task_factor);
         return rtb::fail(RT_ERR_AGAIN, "rt_render: (ray, leaf) task buffer overflow; render the frame again (buffer doubled to %d tasks per pixel)", s->task_factor);
     }
     return RT_OK;
@@ -1062,7 +1158,7 @@ int rt_render(rt_scene* s, const rt_params* p, uint32_t flags, uint8_t* rgb_out,
     a.shadow = (uint8_t*)dev[4];
     a.counters = s->counters;
     a.gamma_tab = s->gamma_tab;
-    a.debug_cost = getenv("RT_DEBUG_COST") ? 1 : 0;
+    a.debug_cost = s->opt.debug_cost;
 
     int launches = 0;
     bool strip_copied = false; /* host outputs already copied back band by band */
@@ -1071,10 +1167,10 @@ int rt_render(rt_scene* s, const rt_params* p, uint32_t flags, uint8_t* rgb_out,
         const int tiles_x = (p->W + 15) / 16, tiles_y = (rows + 7) / 8;
         const unsigned grid = (unsigned)tiles_x * (unsigned)tiles_y;
         const bool count = (flags & RT_RENDER_COUNT_WORK) != 0;
-        int variant = s->variant;
+        int variant = s->opt.variant;
         /* stochastic mode: one wavefront pass per sample (the samples of a pixel share one random stream); the
          * thread-per-pixel kernel render_stoch is the fallback and the in-library cross-check (RT_STOCH_MEGA=1) */
-        const bool stoch_mega = getenv("RT_STOCH_MEGA") && atoi(getenv("RT_STOCH_MEGA")) != 0;
+        const bool stoch_mega = s->opt.stoch_mega != 0;
         if (stochastic && (variant != 2 || stoch_mega)) variant = 3;
         /* tie-break rank of render_wave: (n_tris - leaf_start) and the in-leaf offset share 32 bits */
         int bits_n = 1;
@@ -1113,14 +1209,14 @@ int rt_render(rt_scene* s, const rt_params* p, uint32_t flags, uint8_t* rgb_out,
             /* RT_WIDE: 1 on, 0 off; unset: on for the incoherent bounce rays of the stochastic mode (measured, 6 blocks per SM:
              * stochastic 4 3 4.91 -> 4.67 ms, but the mirror 4K frame 1.23 -> 1.28 ms and no gain for the tree search of
              * coherent rays, profiles/r01_notes.md) */
-            const int env_wide_v = getenv("RT_WIDE") ? atoi(getenv("RT_WIDE")) : -1;
+            const int env_wide_v = s->opt.wide;
             const bool env_wide = env_wide_v > 0 || (env_wide_v < 0 && stochastic && p->indirect != 0);
-            const bool env_wide_count = getenv("RT_WIDE_COUNT") != nullptr; /* timeline of the wide kernel: node_visits then counts wide nodes */
+            const bool env_wide_count = s->opt.wide_count != 0; /* timeline of the wide kernel: node_visits then counts wide nodes */
             const bool wide = env_wide && (!count || env_wide_count) && h.n_wide > 0;
             /* anchored rays (rt_bins.cuh): camera rays and shadow rays find their leaves through per-anchor bins and wf_leaves
              * tests the triangles; wf_traverse keeps the rays that start anywhere else (bounces). The instrumented build
              * counts the reference's node visits and therefore searches the tree; RT_ANCHOR=0 does so too (A/B, cross-check). */
-            const int env_anchor = getenv("RT_ANCHOR") ? atoi(getenv("RT_ANCHOR")) : -1; /* 0 off, 1 on, unset: by mesh size */
+            const int env_anchor = s->opt.anchored; /* 0 off, 1 on, -1: by mesh size */
             /* measured (tools/size_sweep.py, profiles/r01_notes.md): the bins win from 1 k to 1 M leaves (1080p: 0.25 vs 0.41 ms at
              * 1 k, 0.77 vs 1.20 ms at 241 k, 5.97 vs 6.46 ms at 1 M); at 2.5 M leaves and 4K a cell lists hundreds of leaves and
              * one task per candidate loses against the tree search (13.9 vs 12.9 ms) */
@@ -1133,7 +1229,7 @@ int rt_render(rt_scene* s, const rt_params* p, uint32_t flags, uint8_t* rgb_out,
             }
             s->last_was_anchored = anchored;
             /* no mirror, no refractive object: the kernels without the reflection / refraction code (smaller, less instruction fetch) */
-            bool diffuse_only = !(h.has_mesh && (h.mesh_mirror || h.mesh_n_in != h.mesh_n_out)) && !(getenv("RT_DIFFUSE_KERNELS") && atoi(getenv("RT_DIFFUSE_KERNELS")) == 0);
+            bool diffuse_only = !(h.has_mesh && (h.mesh_mirror || h.mesh_n_in != h.mesh_n_out)) && s->opt.diffuse_kernels != 0;
             for (int k = 0; k < h.n_spheres; k++) diffuse_only = diffuse_only && !h.spheres[k].mirror && h.spheres[k].n_in == h.spheres[k].n_out;
             /* round 0 holds tree-searched queries only when a path can go on inside wf_generate: past a mirror or refractive
              * sphere, or along the indirect bounce of a pixel shaded on the spot */
@@ -1142,7 +1238,7 @@ int rt_render(rt_scene* s, const rt_params* p, uint32_t flags, uint8_t* rgb_out,
             trav_round0 = trav_round0 && segments >= 2;
             /* node pool of wf_traverse: 32 lanes x (levels of the packed tree + roots of two batches + slack) */
             int npool_cap = wide ? std::min(96 * (h.wide_depth + 2), 352) : std::min(32 * (h.max_depth + 4), 256);
-            if (const char* v = getenv("RT_NPOOL_CAP")) npool_cap = std::max(64, std::min(atoi(v), npool_cap)) & ~31; /* test hook: a small pool forces the spill path */
+            if (s->opt.npool_cap > 0) npool_cap = std::max(64, std::min(s->opt.npool_cap, npool_cap)) & ~31; /* test hook: a small pool forces the spill path */
             const size_t warp_bytes = (sizeof(rtk::WfWarpSmem) + (size_t)npool_cap * sizeof(int) + 15) & ~(size_t)15;
             const size_t trav_smem = warp_bytes * (WF_THREADS / 32);
             if (trav_smem > 200 * 1024) return rtb::fail(RT_ERR_UNSUPPORTED, "rt_render: BVH depth %d needs %zu B of shared memory per block", h.max_depth, trav_smem);
@@ -1194,22 +1290,23 @@ int rt_render(rt_scene* s, const rt_params* p, uint32_t flags, uint8_t* rgb_out,
                     s->wf_tasks_cap = need;
                 }
             }
-            static const bool dbg_times = getenv("RT_DEBUG_TIMES") != nullptr;
-            const bool dbg_warps = count && getenv("RT_DEBUG_WARPS");
+            const bool dbg_times = s->opt.debug_times != 0;
+            const bool dbg_warps = count && s->opt.debug_warps[0];
             /* Strips: the frame is cut into bands of rows, each rendered by its own generate / traverse / shade chain
              * on its own stream. The end of a persistent traversal launch is a latency-bound tail (a few warps
              * finishing their expensive rays on an otherwise idle GPU, profiles/r01_notes.md); with strips the tail of
              * one band is covered by the bulk of the next, and only the last launch's tail is exposed. */
-            int n_strips = s->n_strips;
+            const bool strips_fixed = s->opt.strips > 0;
+            int n_strips = strips_fixed ? std::min(s->opt.strips, RT_MAX_STRIPS) : 2;
             {   /* host outputs: more bands, so that only the last band's copy-back is not covered by rendering */
                 bool any_copy = false;
                 for (int k = 0; k < 5; k++) any_copy = any_copy || copy_back[k];
-                if (any_copy && !s->n_strips_from_env) n_strips = std::min(RT_MAX_STRIPS, 4);
+                if (any_copy && !strips_fixed) n_strips = std::min(RT_MAX_STRIPS, 4);
             }
             if (rows < 64 * n_strips) n_strips = std::max(1, rows / 64);
             /* a small shard (one rank's rows of a frame split over 8 GPUs) is bound by launch latencies: one band
              * (measured: 4K depth-4 frame, 1/8 of the rows: 0.33 ms against 0.37 ms with two) */
-            if (!s->n_strips_from_env && npx < 1500000 && !(flags & RT_RENDER_COUNT_WORK)) {
+            if (!strips_fixed && npx < 1500000 && !(flags & RT_RENDER_COUNT_WORK)) {
                 bool any_copy = false;
                 for (int k = 0; k < 5; k++) any_copy = any_copy || copy_back[k];
                 if (!any_copy) n_strips = 1;
@@ -1289,10 +1386,8 @@ int rt_render(rt_scene* s, const rt_params* p, uint32_t flags, uint8_t* rgb_out,
                 g.spill = s->wf_spill + (size_t)st * spill_cap * pers_grid * (WF_THREADS / 32);
                 g.spill_cap = spill_cap;
                 {
-                    static const int env_rs = getenv("RT_RUN_SHIFT") ? atoi(getenv("RT_RUN_SHIFT")) : -1;
-                    static const int env_gss = getenv("RT_GSS") ? atoi(getenv("RT_GSS")) : 2;
-                    g.run_shift = env_rs;
-                    g.gss_factor = env_gss;
+                    g.run_shift = s->opt.run_shift;
+                    g.gss_factor = s->opt.gss;
                 }
                 g.dbg_warps = dbg_ptr;
                 g.anchored = anchored ? 1 : 0;
@@ -1316,7 +1411,7 @@ int rt_render(rt_scene* s, const rt_params* p, uint32_t flags, uint8_t* rgb_out,
                     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rtk::wf_leaves<false>, WF_THREADS, 0));
                     s->leaves_blocks_per_sm = std::max(nb, 1);
                 }
-                static const int env_lb = getenv("RT_LEAVES_BLOCKS") ? atoi(getenv("RT_LEAVES_BLOCKS")) : 0;
+                const int env_lb = s->opt.leaves_blocks;
                 const unsigned leaves_grid = (unsigned)(s->sm_count * (env_lb > 0 ? env_lb : std::max(s->leaves_blocks_per_sm, 1)));
                 const dim3 gen_grid((unsigned)(((p->W + 7) / 8 + (WF_THREADS / 32) - 1) / (WF_THREADS / 32)), (unsigned)((srows + 3) / 4));
                 const unsigned shade_grid = (unsigned)std::min<size_t>((spx + WF_THREADS - 1) / WF_THREADS, (size_t)s->sm_count * 16);
@@ -1324,6 +1419,8 @@ int rt_render(rt_scene* s, const rt_params* p, uint32_t flags, uint8_t* rgb_out,
                 g.sample = 0;
                 g.last_sample = 1;
                 g.indirect = p->indirect;
+                g.libm = s->opt.transcendentals;
+                g.sticky = s->sticky;
                 g.aa_sigma = p->aa_sigma;
                 g.npx = (int)spx;
                 g.rng_table = reinterpret_cast<const uint4*>(s->rng_states);
@@ -1361,7 +1458,7 @@ int rt_render(rt_scene* s, const rt_params* p, uint32_t flags, uint8_t* rgb_out,
                             const bool trav_now = r < segments && (r >= 1 || trav_round0);
                             /* the two kernels of the round touch disjoint entries: the tree search goes to the band's side stream
                              * and runs beside wf_leaves (its latency-bound tail is covered by the LSU-bound task kernel) */
-                            static const bool env_side = !(getenv("RT_SIDE_STREAM") && atoi(getenv("RT_SIDE_STREAM")) == 0);
+                            const bool env_side = s->opt.side_stream != 0;
                             const bool side = trav_now && env_side && !dbg_times;
                             cudaStream_t tstream = side ? s->side_stream[st] : stream;
                             if (side) {
@@ -1445,8 +1542,8 @@ int rt_render(rt_scene* s, const rt_params* p, uint32_t flags, uint8_t* rgb_out,
             launches--; /* the common launches++ below counts one */
         } else if (variant == 3) {
             CUDA_TRY(cudaMemsetAsync(s->counters, 0, RT_NCOUNTERS * sizeof(unsigned long long), s->stream));
-            if (count) rtk::render_stoch<true><<<grid, 128, 0, s->stream>>>(s->header, s->blob, a, s->rng_states, p->aa_sigma, p->indirect);
-            else rtk::render_stoch<false><<<grid, 128, 0, s->stream>>>(s->header, s->blob, a, s->rng_states, p->aa_sigma, p->indirect);
+            if (count) rtk::render_stoch<true><<<grid, 128, 0, s->stream>>>(s->header, s->blob, a, s->rng_states, p->aa_sigma, p->indirect, s->opt.transcendentals);
+            else rtk::render_stoch<false><<<grid, 128, 0, s->stream>>>(s->header, s->blob, a, s->rng_states, p->aa_sigma, p->indirect, s->opt.transcendentals);
         } else if (variant == 0) {
             CUDA_TRY(cudaMemsetAsync(s->counters, 0, RT_NCOUNTERS * sizeof(unsigned long long), s->stream));
             if (count) rtk::render_mega<true, false><<<grid, 128, 0, s->stream>>>(s->header, s->blob, a);

@@ -55,7 +55,7 @@
 #define RT_WNODE_BYTES 128
 #define RT_BLOB_MAGIC 0x52544233u /* "RTB3" */
 #define RT_LEAFREC_BYTES 32
-#define RT_LAYOUT_VERSION 3
+#define RT_LAYOUT_VERSION 4
 
 struct DevSphere {
     float cx, cy, cz, R;
@@ -90,6 +90,8 @@ struct SceneHeader {
     uint64_t off_leaves;
     int32_t n_wide;
     int32_t wide_depth; /* levels of the wide index */
+    int32_t max_leaf;   /* largest leaf of the reference BVH (triangles): bounds the in-leaf offset of the tie-break rank */
+    int32_t pad_;
     DevSphere spheres[RT_MAX_SPHERES];                    /* ascending id */
 };
 

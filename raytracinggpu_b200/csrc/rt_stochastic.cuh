@@ -69,7 +69,7 @@ __device__ __forceinline__ float xorwow_uniform(XorwowState& s) {
 
 template <bool COUNT>
 __global__ void __launch_bounds__(128) render_stoch(const __grid_constant__ SceneHeader h, const unsigned char* __restrict__ blob, const RenderArgs a,
-                                                    const XorwowState* __restrict__ states, float aa_sigma, int indirect) {
+                                                    const XorwowState* __restrict__ states, float aa_sigma, int indirect, int libm) {
     __shared__ float s_gamma[256];
     for (int k = threadIdx.x; k < 256; k += blockDim.x) s_gamma[k] = a.gamma_tab[a.gamma_mode * 256 + k];
     __syncthreads();
@@ -95,10 +95,10 @@ __global__ void __launch_bounds__(128) render_stoch(const __grid_constant__ Scen
         float first_t = RTK_INF;
         for (int s = 0; s < a.num_rays; s++) {
             const float r1 = xorwow_uniform(rng), r2 = xorwow_uniform(rng); /* :756-757 */
-            const float rad = aa_sigma * sqrtf(-2 * canon_log(r1));
+            const float rad = aa_sigma * sqrtf(-2 * (libm ? logf(r1) : canon_log(r1)));
             const float ang = (float)(2 * 3.14159265358979323846 * (double)r2);
             F3 O = cam;
-            F3 u = normalized(uc + f3(rad * canon_cos(ang), rad * canon_sin(ang), 0.f)); /* :758-759 */
+            F3 u = normalized(uc + f3(rad * (libm ? cosf(ang) : canon_cos(ang)), rad * (libm ? sinf(ang) : canon_sin(ang)), 0.f)); /* :758-759 */
             float n_ray = 1.f;
             unsigned types = 0; /* bit d: segment d ended on a diffuse surface */
             F3 direct[RT_STOCH_MAX_SEGMENTS], albedo_of[RT_STOCH_MAX_SEGMENTS];
@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(128) render_stoch(const __grid_constant__ Scen
                     const float q1 = xorwow_uniform(rng), q2 = xorwow_uniform(rng); /* :633-634, the last segment included */
                     const float an = (float)(2 * 3.14159265358979323846 * (double)q1);
                     const float sq = sqrtf(1 - q2);
-                    const float x = canon_cos(an) * sq, y = canon_sin(an) * sq, z = sqrtf(q2);
+                    const float x = (libm ? cosf(an) : canon_cos(an)) * sq, y = (libm ? sinf(an) : canon_sin(an)) * sq, z = sqrtf(q2);
                     const F3 T1 = normalized((fabsf(N.y) != 0 && fabsf(N.x) != 0) ? f3(-N.y, N.x, 0.f) : f3(-N.z, 0.f, N.x));
                     const F3 T2 = cross(N, T1);
                     u = (x * T1 + y * T2) + z * N;

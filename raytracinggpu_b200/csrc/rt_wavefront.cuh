@@ -63,12 +63,16 @@ struct WfArgs {
     QEntry* qA[2]; /* closest-hit queue of round r lives in qA[r & 1] */
     QEntry* qS;    /* shadow queue of the current round */
     WfCounters* c;
+    unsigned long long* sticky; /* [0] task buffer overflow, [1] node pool overflow: set by the kernels, NEVER cleared by rt_render (a frame
+                                 * enqueued with RT_RENDER_NO_SYNC must not lose the flag to the next frame's counter reset); rt_scene_sync
+                                 * reads and clears them */
     int round;     /* round whose queues this launch consumes (traverse, shade) */
     /* stochastic mode (rt_stochastic.cuh explains the stream): one wavefront pass per sample */
     int stoch;             /* 0: deterministic mode */
     int sample;            /* sample index of this pass; first-hit outputs come from sample 0 */
     int last_sample;       /* wf_fold of this pass writes the 8-bit pixel */
     int indirect;
+    int libm;              /* 1: logf / cosf / sinf of the CUDA library instead of the double-evaluated canon (RtOptions::transcendentals) */
     float aa_sigma;
     int npx;               /* compact pixels of this strip: stride of rec */
     const uint4* rng_table; /* start state of every pixel of the W x H frame, 2 x uint4 per pixel (d, v0..v4, -, -) */
@@ -298,7 +302,7 @@ __device__ __forceinline__ void path_advance(const SceneHeader& h, const WfArgs&
                     if (cell >= 0) {
                         c0 = __ldg(g.bins[0].cell_start + cell);
                         c1 = __ldg(g.bins[0].cell_start + cell + 1);
-                        if (c1 > g.bins[0].items_cap) { /* a list the build had to cut short */
+                        if (c1 > g.bins[0].items_cap || c0 < 0 || c1 < c0) { /* a list the build had to cut short (or a scan that overflowed) */
                             c0 = 0;
                             c1 = -1;
                         }
@@ -434,7 +438,7 @@ __device__ __forceinline__ void path_advance(const SceneHeader& h, const WfArgs&
                     if (cell >= 0) {
                         c0 = __ldg(g.bins[1].cell_start + cell);
                         c1 = __ldg(g.bins[1].cell_start + cell + 1);
-                        if (c1 > g.bins[1].items_cap) {
+                        if (c1 > g.bins[1].items_cap || c0 < 0 || c1 < c0) {
                             c0 = 0;
                             c1 = -1;
                         }
@@ -475,7 +479,7 @@ __device__ __forceinline__ void path_advance(const SceneHeader& h, const WfArgs&
             if (depth >= a.segments) return;
             const float an = (float)(2 * 3.14159265358979323846 * (double)q1);
             const float sq = sqrtf(1 - q2);
-            const float x = canon_cos(an) * sq, y = canon_sin(an) * sq, z = sqrtf(q2);
+            const float x = (g.libm ? cosf(an) : canon_cos(an)) * sq, y = (g.libm ? sinf(an) : canon_sin(an)) * sq, z = sqrtf(q2);
             const F3 T1 = normalized((fabsf(N.y) != 0 && fabsf(N.x) != 0) ? f3(-N.y, N.x, 0.f) : f3(-N.z, 0.f, N.x));
             const F3 T2 = cross(N, T1);
             u = (x * T1 + y * T2) + z * N;
@@ -561,8 +565,12 @@ __device__ __forceinline__ void emit_tasks(const WfArgs& g, int post_round, cons
     int base = 0;
     if (lane == 0) base = atomicAdd(&g.c->nTask[post_round], total);
     base = __shfl_sync(FULL, base, 0);
-    if (base + total > g.task_cap) { /* reported by rt_scene_sync: the frame is rendered again with a larger buffer */
-        if (lane == 0) atomicExch(&g.c->stats[6], 1ull);
+    if (base < 0 || base > g.task_cap - total) { /* reported by rt_scene_sync: the frame is rendered again with a larger buffer */
+        if (lane == 0) {
+            atomicExch(&g.sticky[0], 1ull);
+            /* keep the cursor just past the buffer: it must never climb towards 2^31 and wrap into valid indices */
+            atomicMin(reinterpret_cast<unsigned*>(&g.c->nTask[post_round]), (unsigned)g.task_cap + 1u);
+        }
         return;
     }
     if (n > 0) {
@@ -665,9 +673,10 @@ __global__ void __launch_bounds__(WF_THREADS, 10) wf_generate(const __grid_const
             }
             const float r1 = rng_uniform(rng), r2 = rng_uniform(rng); /* :756-757 */
             rng_store(rng);
-            const float rad = g.aa_sigma * sqrtf(-2 * canon_log(r1));
+            const float rad = g.aa_sigma * sqrtf(-2 * (g.libm ? logf(r1) : canon_log(r1)));
             const float ang = (float)(2 * 3.14159265358979323846 * (double)r2);
-            u0 = normalized(uc + f3(rad * canon_cos(ang), rad * canon_sin(ang), 0.f)); /* :758-759 */
+            const float ca = g.libm ? cosf(ang) : canon_cos(ang), sa = g.libm ? sinf(ang) : canon_sin(ang);
+            u0 = normalized(uc + f3(rad * ca, rad * sa, 0.f)); /* :758-759 */
         }
         if (!STOCH || g.sample == 0) {
             if (a.hit_obj) a.hit_obj[px] = -1;
@@ -807,7 +816,7 @@ __global__ void __launch_bounds__(WF_THREADS) wf_leaves(const __grid_constant__ 
     const unsigned FULL = 0xffffffffu;
     const float4* tris = reinterpret_cast<const float4*>(blob + h.off_tris);
     const float4* leaves = reinterpret_cast<const float4*>(blob + h.off_leaves);
-    const int n = min(g.c->nTask[g.round], g.task_cap);
+    const int n = max(0, min(g.c->nTask[g.round], g.task_cap));
     QEntry* const qA = g.qA[g.round & 1];
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
@@ -1372,7 +1381,7 @@ __global__ void __launch_bounds__(WF_THREADS, WIDE ? RT_WIDE_BLOCKS : 8) wf_trav
         }
         __syncwarp(); /* pool and slot writes of this step are visible to the next pop */
     }
-    if (failed && lane == 0) atomicExch(&g.c->stats[7], 1ull);
+    if (failed && lane == 0) atomicExch(&g.sticky[1], 1ull);
     if (COUNT && g.dbg_warps && lane == 0) {
         unsigned long long t1;
         unsigned smid;

@@ -6,6 +6,10 @@ and are then committed under tests/golden/):
   ref_gpu_optimized_512_R_B.raw  the UNMODIFIED reference kernel (oracle/_ref/ref_optimized = optimized.cu included
                                  from where it lies, retargeted to sm_100a, reference flags incl. --use_fast_math):
                                  512x512 frames for `./optimized R B`
+  ref_gpu_ieee_512_R_B.raw       the same unmodified source without --use_fast_math and with -fmad=false (ref_optimized_ieee)
+  ref_gpu_ids_960x540.*          sigma-0 copy with the first-segment id dump (ref_optimized_ids): rgb, object id, triangle
+                                 index, t, shadow flag of every pixel; packed into tests/golden/ref_gpu_ids_960x540.npz by
+                                 tests/golden/pack_golden_gpu.py
 """
 import json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -26,4 +30,13 @@ for rays, bounce in ((1, 1), (4, 3)):
     raw = os.path.join(out, "ref_gpu_optimized_512_%d_%d.raw" % (rays, bounce))
     r = subprocess.run([exe, cat, "512", "512", str(rays), str(bounce), "1", raw], capture_output=True, text=True)
     print(r.stdout.strip(), r.stderr.strip()[-200:])
+# round 2: the IEEE build of the same unmodified source (the parity pin of the `optimized` profile), and the sigma-0 copy
+# with the first-segment id dump (oracle/make_ref_variants.py)
+for rays, bounce in ((1, 1), (4, 3)):
+    raw = os.path.join(out, "ref_gpu_ieee_512_%d_%d.raw" % (rays, bounce))
+    r = subprocess.run([exe + "_ieee", cat, "512", "512", str(rays), str(bounce), "1", raw], capture_output=True, text=True)
+    print(r.stdout.strip(), r.stderr.strip()[-200:])
+pre = os.path.join(out, "ref_gpu_ids_960x540")
+r = subprocess.run([exe + "_ids", cat, "960", "540", "1", "1", "1", pre + ".raw", pre], capture_output=True, text=True)
+print(r.stdout.strip(), r.stderr.strip()[-200:])
 print("written", os.listdir(out))

@@ -46,13 +46,13 @@ def cat_or_torus(profile, mirror=0):
     ("optimized", 960, 540, 4, 1),     # mirror mesh: bounce rays through wf_traverse, shadow rays through the bins
     ("array_bvh", 333, 187, 2, 0),     # odd sizes: a column and a row of rays with a zero direction component
 ])
-def test_bins_equal_tree_search(scene, monkeypatch, profile, W, H, bounce, mirror):
+def test_bins_equal_tree_search(scene, profile, W, H, bounce, mirror):
     desc = cat_or_torus(profile, mirror)
     scenes.upload(scene, desc)
     p = profiles.params(profile, W, H, 1, bounce)
-    monkeypatch.setenv("RT_ANCHOR", "1")
+    scene.set_option("anchored", 1)
     a = scene.render(p)
-    monkeypatch.setenv("RT_ANCHOR", "0")
+    scene.set_option("anchored", 0)
     b = scene.render(p)
     same(a, b)
     assert a["stats"]["rays"] == b["stats"]["rays"]
@@ -60,11 +60,11 @@ def test_bins_equal_tree_search(scene, monkeypatch, profile, W, H, bounce, mirro
         scenes.compare(a, scenes.run_oracle(desc, p))
 
 
-def test_bins_follow_a_moving_light(scene, monkeypatch):
+def test_bins_follow_a_moving_light(scene):
     """Every frame of a light orbit rebuilds the light's bins (no read-back after the first build); frames equal the oracle's."""
     desc = cat_or_torus("optimized")
     scenes.upload(scene, desc)
-    monkeypatch.setenv("RT_ANCHOR", "1")
+    scene.set_option("anchored", 1)
     p = profiles.params("optimized", 480, 270, 1, 1)
     L = (-10.0, 20.0, 40.0)
     for k in range(6):
@@ -74,7 +74,7 @@ def test_bins_follow_a_moving_light(scene, monkeypatch):
         scenes.compare(scene.render(p), scenes.run_oracle(d, p))
 
 
-def test_light_inside_the_mesh_box(scene, monkeypatch):
+def test_light_inside_the_mesh_box(scene):
     """A leaf box around the anchor has no bounded set of cells: the status word sends the shadow rays to the exact search."""
     desc = cat_or_torus("optimized")
     bvh = desc["mesh"][2]
@@ -82,42 +82,42 @@ def test_light_inside_the_mesh_box(scene, monkeypatch):
     L = tuple(float(x) for x in 0.5 * (leaf[2:5] + leaf[5:8]))
     d = dict(desc, light=(L, 3e10))
     scenes.upload(scene, d)
-    monkeypatch.setenv("RT_ANCHOR", "1")
+    scene.set_option("anchored", 1)
     p = profiles.params("optimized", 200, 112, 1, 1)
     scenes.compare(scene.render(p), scenes.run_oracle(d, p))
 
 
-def test_task_buffer_overflow_repeats_the_frame(gpu, monkeypatch):
-    monkeypatch.setenv("RT_ANCHOR", "1")
-    monkeypatch.setenv("RT_TASK_FACTOR", "1")  # one task per pixel: too few where the mesh fills the view
+def test_task_buffer_overflow_repeats_the_frame(gpu):
     sc = rt.Scene(gpu)
     try:
+        sc.set_option("anchored", 1)
+        sc.set_option("task_factor", 1)  # one task per pixel: too few where the mesh fills the view
         desc = cat_or_torus("cpu")  # the un-rescaled cat covers a quarter of the frame
         scenes.upload(sc, desc)
         p = profiles.params("cpu", 640, 360, 1, 0)
         p.cam[2] = 30.0  # closer: longer candidate lists per pixel
         a = sc.render(p)
-        monkeypatch.delenv("RT_TASK_FACTOR")
-        monkeypatch.setenv("RT_ANCHOR", "0")
+        assert sc.get_option("task_factor") > 1  # the synchronous call repeated the frame with a doubled buffer
+        sc.set_option("anchored", 0)
         same(a, sc.render(p))
     finally:
         sc.close()
 
 
-def test_wide_index_equals_two_child_records(scene, monkeypatch):
-    """RT_WIDE=1: wf_traverse over the four-child collapse of the reference tree (leaf decisions exact, inner ones
+def test_wide_index_equals_two_child_records(scene):
+    """Option wide = 1: wf_traverse over the four-child collapse of the reference tree (leaf decisions exact, inner ones
     conservative) gives the same frames, tree search only and behind the bins."""
     desc = cat_or_torus("optimized", mirror=1)
     scenes.upload(scene, desc)
     p = profiles.params("optimized", 640, 360, 1, 3)
-    monkeypatch.setenv("RT_ANCHOR", "0")
+    scene.set_option("anchored", 0)
     ref = scene.render(p)
-    monkeypatch.setenv("RT_WIDE", "1")
+    scene.set_option("wide", 1)
     same(scene.render(p), ref)
-    monkeypatch.setenv("RT_ANCHOR", "1")
+    scene.set_option("anchored", 1)
     same(scene.render(p), ref)
     q = profiles.params("array_bvh", 111, 77, 1, 2)  # zero direction components: answered by the exact search at admission
-    monkeypatch.setenv("RT_ANCHOR", "0")
+    scene.set_option("anchored", 0)
     d2 = cat_or_torus("array_bvh")
     scenes.upload(scene, d2)
     scenes.compare(scene.render(q), scenes.run_oracle(d2, q))

@@ -180,16 +180,17 @@ def test_error_paths(scene):
         scene.set_mesh(m.vertices, m.tri_records, bvh)
 
 
-def test_node_pool_overflow_spills_to_global_memory(scene, monkeypatch):
-    """wf_traverse parks the older half of a full node pool in global memory. RT_NPOOL_CAP=64 (test hook of
+def test_node_pool_overflow_spills_to_global_memory(scene):
+    """wf_traverse parks the older half of a full node pool in global memory. Option npool_cap = 64 (test hook of
     rt_render) makes that happen all the time; results must not change."""
     desc = scenes.cat_scene("cpu") or scenes.torus_scene("cpu")
     p = profiles.params("cpu", 640, 360, 1, 0)
     scenes.upload(scene, desc)
     ora = scenes.run_oracle(desc, p)
-    monkeypatch.setenv("RT_NPOOL_CAP", "64")
+    scene.set_option("anchored", 0)  # the tree search is the user of the pool
+    scene.set_option("npool_cap", 64)
     scenes.compare(scene.render(p), ora)
-    monkeypatch.delenv("RT_NPOOL_CAP")
+    scene.set_option("npool_cap", 0)
     scenes.compare(scene.render(p), ora)
 
 

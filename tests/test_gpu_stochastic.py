@@ -88,17 +88,17 @@ def test_stochastic_sharding_keeps_the_image(scene):
     assert not np.array_equal(scene.render(q, want=("rgb",))["rgb"], full["rgb"])
 
 
-def test_wavefront_and_thread_per_pixel_kernels_agree(scene, monkeypatch):
+def test_wavefront_and_thread_per_pixel_kernels_agree(scene):
     """The stochastic mode has two implementations: one wavefront pass per sample (default) and the thread-per-pixel
-    kernel render_stoch (RT_STOCH_MEGA=1, also the fallback for more than 11 segments). Same stream, same arithmetic:
+    kernel render_stoch (option stoch_mega = 1, also the fallback for more than 11 segments). Same stream, same arithmetic:
     identical frames."""
     d = scenes.cat_scene("optimized", mirror=0) or scenes.torus_scene("optimized")
     scenes.upload(scene, d)
     p = stoch("optimized", 400, 225, 3, 4)
     a = scene.render(p)
-    monkeypatch.setenv("RT_STOCH_MEGA", "1")
+    scene.set_option("stoch_mega", 1)
     b = scene.render(p)
-    monkeypatch.delenv("RT_STOCH_MEGA")
+    scene.set_option("stoch_mega", 0)
     for k in ("rgb", "hit_obj", "hit_tri", "shadow"):
         assert np.array_equal(a[k], b[k]), k
     assert a["stats"]["rays"] == b["stats"]["rays"]

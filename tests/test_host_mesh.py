@@ -24,7 +24,7 @@ def test_abi_exports_every_declared_symbol(built):
     for n in sorted(names):
         assert hasattr(L, n), "missing export %s" % n
     assert set(rt.api.SIGNATURES) == names
-    assert L.rt_abi_version() == 1
+    assert L.rt_abi_version() == 2
 
 
 def test_struct_layouts_match_header(built, tmp_path):
