@@ -142,6 +142,11 @@ int rt_mesh_bvh_info(const rt_mesh* m, int32_t* n_leaves, int32_t* max_depth, in
 /* ---- launcher helpers ---- */
 /* z = -W / (2 * tanf(alpha/2)) in float, as optimized.cu:748-749 / cpu_launcher.cpp:666,694 evaluate it on the host. */
 float rt_camera_z(int32_t W, float alpha);
+/* The same expression evaluated ON THE DEVICE, as optimized.cu:748-749 does inside KernelLaunch (tan(float) there is CUDA's
+ * tanf, one ulp off glibc's for alpha = pi/3): the z with which frames, t bits and shadow flags equal those of the
+ * reference's own GPU program (IEEE build). rt_params_profile fills the host value; a caller reproducing optimized.cu's
+ * output overrides rt_params::z with this one (the CLI does, for --profile optimized). */
+int rt_camera_z_device(int device, int32_t W, float alpha, float* z);
 /* Fill `p` with the knobs of one reference program: "cpu" (cpu_launcher.cpp), "optimized" (optimized.cu),
  * "array_bvh" (array_bvh.cu); deterministic mode (aa_sigma=0, indirect=0); camera (0,0,55), alpha=pi/3. */
 int rt_params_profile(rt_params* p, const char* profile, int32_t W, int32_t H, int32_t num_rays, int32_t num_bounce);
@@ -168,6 +173,9 @@ int rt_scene_create(rt_scene** out, int device);
 void rt_scene_destroy(rt_scene* s);
 /* Use an existing CUDA stream (a cudaStream_t cast to void*) instead of the scene's own. */
 int rt_scene_set_stream(rt_scene* s, void* cuda_stream);
+/* The stream every call on this scene enqueues on (a cudaStream_t): work of the caller that consumes a frame rendered with
+ * RT_RENDER_NO_SYNC, or a band pushed with rt_scene_push_rows, must be ordered after it (event or same stream). */
+int rt_scene_get_stream(rt_scene* s, void** cuda_stream);
 /* Tuning and cross-check options of a scene (the reference has none: its variants are separate programs under
  * different-versions/). Every option selects among code paths that give identical results; the defaults are the production
  * choices. Options are part of the scene's state: nothing is read from the environment after rt_scene_create (which
@@ -227,6 +235,27 @@ int rt_peer_open(int device, const uint8_t handle[64], void** ptr);
 int rt_peer_close(int device, void* ptr);
 int rt_peer_free(int device, void* ptr);
 int rt_scene_push_rows(rt_scene* s, const void* band, void* frame, int32_t W, int32_t bytes_per_pixel, int32_t row_begin, int32_t row_step, int32_t rows);
+
+/* ---- multi-GPU (the reference is single-GPU, optimized.cu:774-884): pixels are independent, so a frame shards by
+ * rows (row % nranks == rank through rt_params::row_begin / row_step) and an animation by frames; the only exchanges are the
+ * scene broadcast before and the framebuffer gather after. NCCL is bound at run time (dlopen of libnccl.so.2).
+ *   one process (or thread) per GPU:  rank 0 calls rt_comm_unique_id, the application transports the 128 bytes (MPI, a file,
+ *                                     torch.distributed, ...), every rank calls rt_comm_init
+ *   one process, N devices:           rt_comm_init_all (what `rt_render --gpus N` uses; peer access is enabled between the devices)
+ * rt_scene_broadcast: the root's packed scene (built once: OBJ, BVH, repack) goes to every rank with ncclBroadcast on the scenes'
+ *   streams and is adopted in place. Collective: every rank calls it with its own scene and communicator.
+ * rt_gather_framebuffer: the row-interleaved bands (DEVICE pointers; rank r holds rows r, r + n, ... of an H-row frame, W *
+ *   bytes_per_pixel bytes per row) are assembled in `frame` (device, H rows) on the root: grouped ncclSend / ncclRecv + one
+ *   strided copy per source rank, on the scenes' streams. frame may be NULL on the other ranks. Collective. */
+typedef struct rt_comm rt_comm;
+int rt_comm_available(int* nccl_version);                       /* RT_ERR_UNSUPPORTED when libnccl.so.2 cannot be loaded */
+int rt_comm_unique_id(uint8_t id[128]);
+int rt_comm_init(rt_comm** out, int nranks, int rank, const uint8_t id[128], int device);
+int rt_comm_init_all(rt_comm** comms /* ndev */, int ndev, const int* devices /* NULL: 0..ndev-1 */);
+void rt_comm_destroy(rt_comm* c);
+int rt_comm_rank(const rt_comm* c, int* rank, int* nranks);
+int rt_scene_broadcast(rt_scene* s, rt_comm* c, int root, size_t* bytes /* may be NULL: size of the blob */);
+int rt_gather_framebuffer(rt_scene* s, rt_comm* c, const void* band, int32_t W, int32_t H, int32_t bytes_per_pixel, void* frame, int root);
 
 /* Device self-test: the reciprocal-based exact division used by the fast slab test against div.rn.f32 on
  * blocks*256*per_thread pseudo-random operand pairs. out[0] = mismatches with one correction step,

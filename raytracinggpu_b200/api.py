@@ -36,6 +36,7 @@ SIGNATURES = {
     "rt_mesh_arr_bvh": (_vp, [_vp]),
     "rt_mesh_bvh_info": (C.c_int, [_vp, _pi32, _pi32, _pi32]),
     "rt_camera_z": (_f, [_i32, _f]),
+    "rt_camera_z_device": (C.c_int, [C.c_int, _i32, _f, _pf]),
     "rt_params_profile": (C.c_int, [C.POINTER(rt_params), C.c_char_p, _i32, _i32, _i32, _i32]),
     "rt_default_walls": (C.c_int, [C.POINTER(rt_sphere), C.c_char_p, _pi32]),
     "rt_write_png": (C.c_int, [C.c_char_p, _i32, _i32, _vp]),
@@ -52,6 +53,7 @@ SIGNATURES = {
     "rt_scene_create": (C.c_int, [C.POINTER(_vp), C.c_int]),
     "rt_scene_destroy": (None, [_vp]),
     "rt_scene_set_stream": (C.c_int, [_vp, _vp]),
+    "rt_scene_get_stream": (C.c_int, [_vp, C.POINTER(_vp)]),
     "rt_scene_set_option": (C.c_int, [_vp, C.c_char_p, C.c_int64]),
     "rt_scene_get_option": (C.c_int, [_vp, C.c_char_p, C.POINTER(C.c_int64)]),
     "rt_scene_set_spheres": (C.c_int, [_vp, C.POINTER(rt_sphere), _i32]),
@@ -63,6 +65,14 @@ SIGNATURES = {
     "rt_scene_blob_copy_out": (C.c_int, [_vp, _vp, C.c_size_t]),
     "rt_render": (C.c_int, [_vp, C.POINTER(rt_params), C.c_uint32, _vp, _vp, _vp, _vp, _vp, C.POINTER(rt_stats)]),
     "rt_scene_sync": (C.c_int, [_vp, C.POINTER(rt_stats)]),
+    "rt_comm_available": (C.c_int, [C.POINTER(C.c_int)]),
+    "rt_comm_unique_id": (C.c_int, [_vp]),
+    "rt_comm_init": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, _vp, C.c_int]),
+    "rt_comm_init_all": (C.c_int, [C.POINTER(_vp), C.c_int, C.POINTER(C.c_int)]),
+    "rt_comm_destroy": (None, [_vp]),
+    "rt_comm_rank": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "rt_scene_broadcast": (C.c_int, [_vp, _vp, C.c_int, C.POINTER(C.c_size_t)]),
+    "rt_gather_framebuffer": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, C.c_int]),
     "rt_selftest_division": (C.c_int, [C.c_int, _u64, C.c_int, C.c_int, C.POINTER(_u64)]),
     "rt_selftest_xorwow": (C.c_int, [C.c_int, _u64, _vp, C.c_int32, _vp, _vp]),
 }
@@ -119,6 +129,13 @@ def device_count():
 
 def camera_z(W, alpha=np.float32(np.pi / 3)):
     return lib().rt_camera_z(int(W), float(alpha))
+
+
+def camera_z_device(W, alpha=np.float32(np.pi / 3), device=0):
+    """z as optimized.cu's kernel evaluates it (CUDA tanf on the device), see rt_camera_z_device."""
+    z = C.c_float()
+    _check(lib().rt_camera_z_device(int(device), int(W), float(alpha), C.byref(z)))
+    return z.value
 
 
 def params_profile(profile, W, H, num_rays=1, num_bounce=1):
@@ -295,6 +312,12 @@ class Scene:
     def set_stream(self, cuda_stream):
         _check(lib().rt_scene_set_stream(self._h, C.c_void_p(int(cuda_stream))))
 
+    def get_stream(self):
+        """The cudaStream_t (as an int) every call on this scene enqueues on."""
+        p = C.c_void_p()
+        _check(lib().rt_scene_get_stream(self._h, C.byref(p)))
+        return p.value or 0
+
     def set_option(self, key, value):
         """rt_scene_set_option: tuning / cross-check options are scene state (never read from the environment per call)."""
         _check(lib().rt_scene_set_option(self._h, key.encode(), int(value)))
@@ -367,6 +390,58 @@ class Scene:
                               RT_RENDER_COUNT_WORK if count_work else 0)
         out["stats"] = {f[0]: getattr(st, f[0]) for f in rt_stats._fields_}
         return out
+
+
+class Comm:
+    """rt_comm: NCCL communicator behind the C ABI (one process or thread per GPU, or one process driving N devices)."""
+
+    def __init__(self, handle):
+        self._h = handle
+
+    @staticmethod
+    def unique_id():
+        buf = (C.c_uint8 * 128)()
+        _check(lib().rt_comm_unique_id(buf))
+        return bytes(buf)
+
+    @classmethod
+    def init(cls, nranks, rank, uid, device):
+        h = C.c_void_p()
+        buf = (C.c_uint8 * 128).from_buffer_copy(uid)
+        _check(lib().rt_comm_init(C.byref(h), int(nranks), int(rank), buf, int(device)))
+        return cls(h)
+
+    @classmethod
+    def init_all(cls, ndev, devices=None):
+        hs = (C.c_void_p * ndev)()
+        devs = (C.c_int * ndev)(*devices) if devices is not None else None
+        _check(lib().rt_comm_init_all(hs, int(ndev), devs))
+        return [cls(C.c_void_p(h)) for h in hs]
+
+    def close(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.rt_comm_destroy(self._h)
+            self._h = None
+
+    def rank(self):
+        r, n = C.c_int(), C.c_int()
+        _check(lib().rt_comm_rank(self._h, C.byref(r), C.byref(n)))
+        return r.value, n.value
+
+    def broadcast_scene(self, scene, root=0):
+        n = C.c_size_t()
+        _check(lib().rt_scene_broadcast(scene._h, self._h, int(root), C.byref(n)))
+        return n.value
+
+    def gather_framebuffer(self, scene, band_ptr, W, H, bytes_per_pixel, frame_ptr, root=0):
+        _check(lib().rt_gather_framebuffer(scene._h, self._h, C.c_void_p(int(band_ptr)), int(W), int(H), int(bytes_per_pixel),
+                                           C.c_void_p(int(frame_ptr)) if frame_ptr else None, int(root)))
+
+
+def comm_available():
+    v = C.c_int()
+    rc = lib().rt_comm_available(C.byref(v))
+    return v.value if rc == RT_OK else 0
 
 
 def selftest_division(device=0, seed=1, blocks=148 * 8, per_thread=4096):

@@ -60,6 +60,8 @@ int main(int argc, char** argv) {
             p.aa_sigma = 0.2f; /* optimized.cu:753 */
             p.indirect = 1;    /* optimized.cu:631-649 */
         }
+        /* optimized.cu evaluates z inside the kernel (:748-749, CUDA's tanf); cpu_launcher.cpp and array_bvh.cu on the host */
+        if (profile == "optimized") rtb200::check(rt_camera_z_device(device, W, (float)(3.14159265358979323846 / 3), &p.z));
         rt_sphere walls[6];
         int32_t mesh_id = 0;
         rtb200::check(rt_default_walls(profile.c_str(), walls, &mesh_id));

@@ -428,6 +428,26 @@ rtk::BinsView bins_view(const rt_scene::AnchorBins& b) {
 } // namespace
 
 namespace rtb {
+/* rt_comm.cu (multi-GPU entry points) reaches the scene through these three */
+cudaStream_t scene_stream(rt_scene* s) { return s->stream; }
+int scene_device(rt_scene* s) { return s->device; }
+/* make the scene's blob at least `bytes` large and hand out its address: a broadcast is received in place and then adopted
+ * by rt_scene_blob_import(s, that pointer, bytes) without a copy */
+int scene_blob_reserve(rt_scene* s, size_t bytes, void** device_ptr) {
+    DeviceGuard g(s->device);
+    if (bytes < RT_HEADER_BYTES) return fail(RT_ERR_INVALID, "scene_blob_reserve: %zu bytes is smaller than a scene header", bytes);
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    if (s->blob_bytes < bytes) {
+        if (s->blob) cudaFree(s->blob);
+        s->blob = nullptr;
+        s->blob_bytes = 0;
+        CUDA_TRY(cudaMalloc(&s->blob, bytes));
+        s->blob_bytes = bytes;
+    }
+    s->plan_valid = false;
+    *device_ptr = s->blob;
+    return RT_OK;
+}
 int bvh_build_device(int device, const float* vertices, int nv, const int32_t* idx3, int nt, std::vector<int32_t>* perm, std::vector<float>* arr, int32_t info[4],
                      double* build_ms) {
     return rtbuild::build(device, vertices, nv, idx3, nt, *perm, *arr, info, build_ms);
@@ -545,6 +565,12 @@ int rt_scene_set_stream(rt_scene* s, void* cuda_stream) {
     if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
     s->stream = (cudaStream_t)cuda_stream;
     s->own_stream = false;
+    return RT_OK;
+}
+
+int rt_scene_get_stream(rt_scene* s, void** cuda_stream) {
+    if (!s || !cuda_stream) return rtb::fail(RT_ERR_INVALID, "rt_scene_get_stream: bad argument");
+    *cuda_stream = (void*)s->stream;
     return RT_OK;
 }
 
@@ -1626,6 +1652,26 @@ int rt_scene_push_rows(rt_scene* s, const void* band, void* frame, int32_t W, in
     DeviceGuard g(s->device);
     const size_t line = (size_t)W * bytes_per_pixel;
     CUDA_TRY(cudaMemcpy2DAsync((unsigned char*)frame + (size_t)row_begin * line, (size_t)row_step * line, band, line, line, (size_t)rows, cudaMemcpyDefault, s->stream));
+    return RT_OK;
+}
+
+/* optimized.cu:748-749 evaluates `float z = -W / (2 * tan(alpha/2))` INSIDE KernelLaunch: in device code tan(float) is CUDA's
+ * tanf, whose result for alpha = pi/3 is one ulp above glibc's (measured on the B200: tan 0.57735032 vs 0.57735026; with that
+ * z the reference kernel's t bits, shadow flags and colours are reproduced exactly, with the host value 15 % of the t bits
+ * and 0.6 % of the pixels differ). This evaluates the same expression on the device, compiled like an IEEE build of the
+ * reference (no fast math, no contraction). cpu_launcher.cpp evaluates it on the host: rt_camera_z. */
+__global__ void camera_z_kernel(int W, float alpha, float* out) { *out = -W / (2 * tanf(alpha / 2)); }
+
+int rt_camera_z_device(int device, int32_t W, float alpha, float* z) {
+    if (!z || W <= 0) return rtb::fail(RT_ERR_INVALID, "rt_camera_z_device: bad argument");
+    DeviceGuard g(device);
+    if (!g.ok) return rtb::fail(RT_ERR_CUDA, "rt_camera_z_device: no device %d", device);
+    float* d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, sizeof(float)));
+    camera_z_kernel<<<1, 1>>>(W, alpha, d);
+    cudaError_t e = cudaMemcpy(z, d, sizeof(float), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return rtb::fail(RT_ERR_CUDA, "rt_camera_z_device: %s", cudaGetErrorString(e));
     return RT_OK;
 }
 

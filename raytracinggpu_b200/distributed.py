@@ -18,6 +18,33 @@ import torch.distributed as dist
 from . import sharding
 
 
+def _order_after_scene(scene):
+    """Make torch's current stream wait for everything enqueued so far on the scene's stream (the render, a pushed band):
+    the scene's stream is a private non-blocking stream unless the caller handed it torch's with set_stream."""
+    if not torch.cuda.is_available():
+        return
+    sp = scene.get_stream()
+    cur = torch.cuda.current_stream()
+    if sp == cur.cuda_stream:
+        return
+    ev = torch.cuda.Event()
+    ev.record(torch.cuda.ExternalStream(sp))
+    cur.wait_event(ev)
+
+
+def _order_scene_after_current(scene):
+    """The reverse edge: later work on the scene's stream waits for what torch's current stream holds (a collective)."""
+    if not torch.cuda.is_available():
+        return
+    sp = scene.get_stream()
+    cur = torch.cuda.current_stream()
+    if sp == cur.cuda_stream:
+        return
+    ev = torch.cuda.Event()
+    ev.record(cur)
+    torch.cuda.ExternalStream(sp).wait_event(ev)
+
+
 def broadcast_scene(scene, src=0, device=None):
     """Make `scene` on every rank hold rank `src`'s packed scene. Returns the blob size in bytes."""
     rank = dist.get_rank()
@@ -52,8 +79,11 @@ class FrameGather:
         params.row_begin, params.row_step, params.row_count = self.row_begin, self.row_step, self.row_count
         return params
 
-    def gather(self):
-        """All-gather the bands; returns the assembled [H, W, C] frame (valid on every rank)."""
+    def gather(self, scene=None):
+        """All-gather the bands; returns the assembled [H, W, C] frame (valid on every rank). `scene`: the scene that rendered
+        the band — the collective (torch's current stream) is ordered after its stream."""
+        if scene is not None:
+            _order_after_scene(scene)
         if self.world > 1:
             try:
                 dist.all_gather_into_tensor(self.gathered.view(-1), self.band.view(-1))
@@ -81,16 +111,21 @@ class FramePush:
         self.band = torch.zeros((max(self.row_count, 1), W, channels), dtype=torch.uint8, device=device)
         handle = torch.zeros(64, dtype=torch.uint8, device=device)
         self._own = self._peer = None
+        # two frames alternate: the destination may still be reading frame k while the peers push frame k + 1; the all-reduce
+        # after push k + 1 (enqueued on the destination behind its read of frame k) is what lets buffer k % 2 be written again
+        self.frame_bytes = H * W * channels
+        self.k = 0
         if rank == dst:
-            self._own, hb = api.peer_alloc(self.device_index, H * W * channels)
+            self._own, hb = api.peer_alloc(self.device_index, 2 * self.frame_bytes)
             handle.copy_(torch.frombuffer(bytearray(hb), dtype=torch.uint8))
         if world > 1:
             dist.broadcast(handle, dst)
         if rank == dst:
-            self.frame_ptr = self._own
+            self._base = self._own
         else:
             self._peer = api.peer_open(self.device_index, bytes(handle.cpu().numpy().tobytes()))
-            self.frame_ptr = self._peer
+            self._base = self._peer
+        self.frame_ptr = self._base
         self._token = torch.zeros(1, dtype=torch.int32, device=device)
 
     def apply(self, params):
@@ -99,15 +134,19 @@ class FramePush:
 
     def push(self):
         """Enqueue this rank's copy (on the scene's stream) and the barrier that tells `dst` every band has landed."""
+        self.frame_ptr = self._base + (self.k & 1) * self.frame_bytes
+        self.k += 1
         self.scene.push_rows(self.band.data_ptr(), self.frame_ptr, self.W, self.channels, self.row_begin, self.row_step, self.row_count)
         if self.world > 1:
-            dist.all_reduce(self._token)  # ordered after the copy on the current stream; complete when every rank's copy is
+            _order_after_scene(self.scene)   # the collective runs on torch's current stream: behind the copy on the scene's
+            dist.all_reduce(self._token)     # complete when every rank's copy is
+            _order_scene_after_current(self.scene)  # what the destination enqueues next on the scene's stream sees every band
 
     def frame_tensor(self):
         """rank `dst` only: a copy of the assembled frame as a torch tensor (enqueued on the scene's stream)."""
         assert self.rank == self.dst
         out = torch.empty((self.H, self.W, self.channels), dtype=torch.uint8, device=self.band.device)
-        self.scene.push_rows(self._own, out.data_ptr(), self.W, self.channels, 0, 1, self.H)
+        self.scene.push_rows(self.frame_ptr, out.data_ptr(), self.W, self.channels, 0, 1, self.H)
         return out
 
     def close(self):

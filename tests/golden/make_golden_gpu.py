@@ -39,4 +39,8 @@ for rays, bounce in ((1, 1), (4, 3)):
 pre = os.path.join(out, "ref_gpu_ids_960x540")
 r = subprocess.run([exe + "_ids", cat, "960", "540", "1", "1", "1", pre + ".raw", pre], capture_output=True, text=True)
 print(r.stdout.strip(), r.stderr.strip()[-200:])
+json.dump({"z_device_960": rt.camera_z_device(960), "z_device_512": rt.camera_z_device(512), "z_device_1920": rt.camera_z_device(1920),
+           "z_host_960": rt.camera_z(960), "z_host_512": rt.camera_z(512), "z_host_1920": rt.camera_z(1920),
+           "source": "-W / (2 * tanf(alpha / 2)), alpha = (float)(pi/3), evaluated on an NVIDIA B200 (rt_camera_z_device) and by the host libm (rt_camera_z)"},
+          open(os.path.join(out, "camera_z.json"), "w"), indent=1)
 print("written", os.listdir(out))
