@@ -265,6 +265,10 @@ int rt_selftest_division(int device, uint64_t seed, int blocks, int per_thread, 
  * (n*4 floats) of the listed subsequences — the random stream of optimized.cu:745 that the stochastic mode reproduces. */
 int rt_selftest_xorwow(int device, uint64_t seed, const uint32_t* subsequences, int32_t n, uint32_t* states6, float* uniforms4);
 
+/* Device self-test: CUDA's single-precision logf (which = 0) / sinf (1) / cosf (2) / tanf (3) on n host arguments — the functions
+ * option "transcendentals" = 1 and rt_camera_z_device evaluate (optimized.cu:749, 756-758, 635-636 call them in the kernel). */
+int rt_selftest_libm(int device, int which, const float* x, int32_t n, float* y);
+
 #ifdef __cplusplus
 }
 #endif

@@ -82,6 +82,12 @@ def lib():
         L.orc_quantise.argtypes = [C.c_float, C.c_int32]
         L.orc_camera_z.argtypes = [C.c_int32, C.c_float]
         L.orc_camera_z.restype = C.c_float
+        L.orc_camera_z_device.argtypes = [C.c_int32, C.c_float]
+        L.orc_camera_z_device.restype = C.c_float
+        L.orc_set_transcendentals.argtypes = [C.c_int32]
+        L.orc_set_transcendentals.restype = None
+        L.orc_cuda_libm.argtypes = [C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]
+        L.orc_cuda_libm.restype = None
         _lib = L
     return _lib
 
@@ -204,6 +210,29 @@ def render(spheres, mesh_arrays, mesh_mat, light, params, threads=0, want=("rgb"
 
 # ---- the compiled reference (oracle/_ref) ---------------------------------------------------------------
 _ref = None
+
+
+def camera_z(W, alpha=np.float32(np.pi / 3)):
+    """z as the host evaluates it (cpu_launcher.cpp:666,694)."""
+    return lib().orc_camera_z(int(W), float(alpha))
+
+
+def camera_z_device(W, alpha=np.float32(np.pi / 3)):
+    """z as optimized.cu's KERNEL evaluates it (CUDA's tanf, restated in the oracle): rt_camera_z_device's counterpart."""
+    return lib().orc_camera_z_device(int(W), float(alpha))
+
+
+def set_transcendentals(mode):
+    """0: double-evaluated log / cos / sin (default); 1: CUDA's logf / cosf / sinf restated (what optimized.cu calls)."""
+    lib().orc_set_transcendentals(int(mode))
+
+
+def cuda_libm(which, x):
+    """The oracle's restatement of CUDA's logf / sinf / cosf / tanf (which = 'log' | 'sin' | 'cos' | 'tan')."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    y = np.empty_like(x)
+    lib().orc_cuda_libm({"log": 0, "sin": 1, "cos": 2, "tan": 3}[which], x.ctypes.data, x.size, y.ctypes.data)
+    return y
 
 
 def xorwow(seed, subsequence, n):

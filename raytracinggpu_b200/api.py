@@ -73,6 +73,7 @@ SIGNATURES = {
     "rt_comm_rank": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "rt_scene_broadcast": (C.c_int, [_vp, _vp, C.c_int, C.POINTER(C.c_size_t)]),
     "rt_gather_framebuffer": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, C.c_int]),
+    "rt_selftest_libm": (C.c_int, [C.c_int, C.c_int, _vp, _i32, _vp]),
     "rt_selftest_division": (C.c_int, [C.c_int, _u64, C.c_int, C.c_int, C.POINTER(_u64)]),
     "rt_selftest_xorwow": (C.c_int, [C.c_int, _u64, _vp, C.c_int32, _vp, _vp]),
 }
@@ -442,6 +443,14 @@ def comm_available():
     v = C.c_int()
     rc = lib().rt_comm_available(C.byref(v))
     return v.value if rc == RT_OK else 0
+
+
+def selftest_libm(which, x, device=0):
+    """CUDA's logf / sinf / cosf / tanf ('log' | 'sin' | 'cos' | 'tan') evaluated on the device for the float32 array x."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    y = np.empty_like(x)
+    _check(lib().rt_selftest_libm(int(device), {"log": 0, "sin": 1, "cos": 2, "tan": 3}[which], x.ctypes.data, x.size, y.ctypes.data))
+    return y
 
 
 def selftest_division(device=0, seed=1, blocks=148 * 8, per_thread=4096):

@@ -1675,6 +1675,34 @@ int rt_camera_z_device(int device, int32_t W, float alpha, float* z) {
     return RT_OK;
 }
 
+/* Device self-test used by tests/: CUDA's single-precision logf (0) / sinf (1) / cosf (2) / tanf (3) on n arguments, compiled
+ * like the rest of this translation unit (no fast math, no contraction): the functions option transcendentals = 1 and
+ * rt_camera_z_device evaluate, and that the oracle restates for the CPU (oracle/rt_oracle.cpp: cuda_logf ...). */
+__global__ void selftest_libm_kernel(int which, const float* __restrict__ x, int n, float* __restrict__ y) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float a = x[i];
+    y[i] = which == 0 ? logf(a) : which == 1 ? sinf(a) : which == 2 ? cosf(a) : tanf(a);
+}
+
+int rt_selftest_libm(int device, int which, const float* x, int32_t n, float* y) {
+    if (!x || !y || n <= 0 || which < 0 || which > 3) return rtb::fail(RT_ERR_INVALID, "rt_selftest_libm: bad argument");
+    DeviceGuard g(device);
+    if (!g.ok) return rtb::fail(RT_ERR_CUDA, "rt_selftest_libm: no device %d", device);
+    float *dx = nullptr, *dy = nullptr;
+    cudaError_t e = cudaMalloc(&dx, (size_t)n * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&dy, (size_t)n * 4);
+    if (e == cudaSuccess) e = cudaMemcpy(dx, x, (size_t)n * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        selftest_libm_kernel<<<(n + 255) / 256, 256>>>(which, dx, n, dy);
+        e = cudaMemcpy(y, dy, (size_t)n * 4, cudaMemcpyDeviceToHost);
+    }
+    if (dx) cudaFree(dx);
+    if (dy) cudaFree(dy);
+    if (e != cudaSuccess) return rtb::fail(RT_ERR_CUDA, "rt_selftest_libm: %s", cudaGetErrorString(e));
+    return RT_OK;
+}
+
 /* Device self-test used by tests/: agreement of the reciprocal-based division with div.rn.f32.
  * out[0] mismatches (1 correction step), out[1] mismatches (2 steps), out[2] pairs tested. */
 int rt_selftest_division(int device, uint64_t seed, int blocks, int per_thread, uint64_t out[3]) {

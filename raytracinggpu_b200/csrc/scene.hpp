@@ -103,15 +103,19 @@ public:
         intensity = intensity_;
         dirty_ = true;
     }
-    /* One frame into a host buffer (H*W*3). */
-    rt_stats render(const rt_params& p, uint8_t* rgb, int32_t* hit_obj = nullptr, int32_t* hit_tri = nullptr, float* hit_t = nullptr,
-                    uint8_t* shadow = nullptr, uint32_t flags = 0) {
+    /* push pending addObject / setLight state to the device scene */
+    void flush() {
         if (dirty_) {
             check(rt_scene_set_spheres(s_, spheres_.data(), (int32_t)spheres_.size()));
             const float l[3] = {L.x, L.y, L.z};
             check(rt_scene_set_light(s_, l, intensity));
             dirty_ = false;
         }
+    }
+    /* One frame into a host buffer (H*W*3). */
+    rt_stats render(const rt_params& p, uint8_t* rgb, int32_t* hit_obj = nullptr, int32_t* hit_tri = nullptr, float* hit_t = nullptr,
+                    uint8_t* shadow = nullptr, uint32_t flags = 0) {
+        flush();
         rt_stats st;
         check(rt_render(s_, &p, flags, rgb, hit_obj, hit_tri, hit_t, shadow, &st));
         return st;

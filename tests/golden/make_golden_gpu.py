@@ -39,6 +39,15 @@ for rays, bounce in ((1, 1), (4, 3)):
 pre = os.path.join(out, "ref_gpu_ids_960x540")
 r = subprocess.run([exe + "_ids", cat, "960", "540", "1", "1", "1", pre + ".raw", pre], capture_output=True, text=True)
 print(r.stdout.strip(), r.stderr.strip()[-200:])
+rng = np.random.default_rng(20261018)
+u = (rng.integers(1, 2**32, 4096, dtype=np.uint64).astype(np.float64) * 2.0**-32 + 2.0**-33).astype(np.float32)  # curand_uniform values
+ang = (2 * np.pi * u.astype(np.float64)).astype(np.float32)                                                      # (float)(2 pi u)
+libm = {"x_log_bits": u.view(np.uint32).tolist(), "x_trig_bits": ang.view(np.uint32).tolist(),
+        "log_bits": rt.selftest_libm("log", u).view(np.uint32).tolist(), "sin_bits": rt.selftest_libm("sin", ang).view(np.uint32).tolist(),
+        "cos_bits": rt.selftest_libm("cos", ang).view(np.uint32).tolist(),
+        "tan_pi_6_bits": int(rt.selftest_libm("tan", np.float32([np.float32(np.float32(np.pi / 3) / np.float32(2))])).view(np.uint32)[0]),
+        "source": "logf / sinf / cosf / tanf of CUDA 12.9 (nvcc -fmad=false, no fast math) evaluated on an NVIDIA B200 through rt_selftest_libm"}
+json.dump(libm, open(os.path.join(out, "cuda_libm_vectors.json"), "w"))
 json.dump({"z_device_960": rt.camera_z_device(960), "z_device_512": rt.camera_z_device(512), "z_device_1920": rt.camera_z_device(1920),
            "z_host_960": rt.camera_z(960), "z_host_512": rt.camera_z(512), "z_host_1920": rt.camera_z(1920),
            "source": "-W / (2 * tanf(alpha / 2)), alpha = (float)(pi/3), evaluated on an NVIDIA B200 (rt_camera_z_device) and by the host libm (rt_camera_z)"},

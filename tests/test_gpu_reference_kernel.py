@@ -92,12 +92,21 @@ def test_library_matches_the_ieee_build_of_optimized_cu(scene, W, H, rays, bounc
 
 @pytest.mark.parametrize("rays,bounce", [(1, 1), (4, 3)])
 def test_oracle_matches_the_ieee_build_of_optimized_cu(rays, bounce):
-    """The CPU oracle (transcendentals evaluated in double: a few 1-ulp differences from CUDA's logf / cosf / sinf)."""
+    """The CPU oracle with its second canon (CUDA's logf / cosf / sinf restated, oracle/rt_oracle.cpp) against the live
+    reference kernel; the default canon (double evaluation, a few 1-ulp differences in the bounce directions that the
+    chaotic self-shadow speckle of the R = 940 walls amplifies) is printed beside it."""
     ref = run_ref("ieee", 512, 512, rays, bounce)["rgb"]
-    o = scenes.run_oracle(scenes.cat_scene("optimized"), stoch(512, 512, rays, bounce), want=("rgb",))["rgb"]
+    p = stoch(512, 512, rays, bounce)
+    try:
+        pyoracle.set_transcendentals(1)
+        o = scenes.run_oracle(scenes.cat_scene("optimized"), p, want=("rgb",))["rgb"]
+    finally:
+        pyoracle.set_transcendentals(0)
     r = lsb(o, ref)
-    print("oracle vs IEEE optimized.cu 512x512 `%d %d`:" % (rays, bounce), r)
-    assert r["within1"] >= 0.999, r
+    r0 = lsb(scenes.run_oracle(scenes.cat_scene("optimized"), p, want=("rgb",))["rgb"], ref)
+    print("oracle (CUDA canon) vs IEEE optimized.cu 512x512 `%d %d`:" % (rays, bounce), r, " double canon:", r0)
+    assert r["within1"] >= 0.999 and r["exact"] >= 0.9999, r
+    assert r0["within1"] >= 0.99, r0
 
 
 def test_deterministic_frame_and_hit_ids_equal_the_reference_kernels(scene):
