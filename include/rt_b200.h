@@ -187,10 +187,9 @@ int rt_scene_get_stream(rt_scene* s, void** cuda_stream);
  *   "strips" 0..8             row bands on separate streams, 0 = chosen per call
  *   "bins_r", "task_factor", "npool_cap", "run_shift", "gss", "leaves_blocks", "side_stream", "diffuse_kernels",
  *   "stoch_mega", "wide_count", "graph", "debug_times", "debug_pool", "debug_bins", "debug_cost"   (see rt_device.cu: RtOptions)
- *   "transcendentals" 0|1     stochastic mode: log / cos / sin of optimized.cu:756-758, 635-636 evaluated in double and
- *                             rounded once (0, default: agrees with the CPU oracle on every platform) or by CUDA's
- *                             single-precision logf / cosf / sinf (1: what optimized.cu itself calls when compiled without
- *                             --use_fast_math; frames then match that build of the reference's own GPU program)
+ *   "transcendentals" 1|0     stochastic mode: log / cos / sin of optimized.cu:756-758, 635-636 by CUDA's single-precision
+ *                             logf / cosf / sinf (1, default: what optimized.cu itself calls; frames equal those of the reference
+ *                             kernel compiled without --use_fast_math bit for bit) or evaluated in double and rounded once (0)
  * Unknown key or value out of range: RT_ERR_INVALID. */
 int rt_scene_set_option(rt_scene* s, const char* key, int64_t value);
 int rt_scene_get_option(rt_scene* s, const char* key, int64_t* value);

@@ -223,7 +223,7 @@ def camera_z_device(W, alpha=np.float32(np.pi / 3)):
 
 
 def set_transcendentals(mode):
-    """0: double-evaluated log / cos / sin (default); 1: CUDA's logf / cosf / sinf restated (what optimized.cu calls)."""
+    """1: CUDA's logf / cosf / sinf restated (default: what optimized.cu calls, and the library's default); 0: double-evaluated."""
     lib().orc_set_transcendentals(int(mode))
 
 

@@ -50,9 +50,10 @@ struct RtOptions {
     int run_shift = -1;      /* log2 of wf_traverse's admission run length; -1: per launch */
     int gss = 2;             /* guided self-scheduling factor of wf_traverse */
     int leaves_blocks = 0;   /* resident blocks per SM for wf_leaves; 0: occupancy */
-    int transcendentals = 0; /* stochastic mode, log / cos / sin of optimized.cu:756-758, 635-636: 0 evaluated in double and rounded once
-                              * (what the CPU oracle computes), 1 CUDA's single-precision logf / cosf / sinf (what optimized.cu itself
-                              * calls when compiled without --use_fast_math: the parity pin against the reference's own GPU frames) */
+    int transcendentals = 1; /* stochastic mode, log / cos / sin of optimized.cu:756-758, 635-636: 1 CUDA's single-precision logf / cosf /
+                              * sinf — what optimized.cu itself calls; frames equal those of its IEEE build bit for bit, and the oracle
+                              * restates the functions for the CPU (rt_oracle.cpp: cuda_logf ...); 0 evaluated in double and rounded once
+                              * (the oracle's other canon: what a correctly rounded libm would give; 3-4x the instructions) */
     int graph = 1;           /* replay a recorded CUDA graph when a frame repeats the previous call's plan */
     int debug_times = 0, debug_pool = 0, debug_bins = 0, debug_cost = 0;
     char debug_warps[256] = {0}; /* RT_DEBUG_WARPS=<file> at scene creation: per-warp timeline of wf_traverse (count_work renders) */
@@ -89,7 +90,11 @@ static const RtOptionKey kOptionKeys[] = {
 struct rt_scene {
     int device = 0;
     RtOptions opt;
-    bool plan_valid = false; /* a recorded frame graph matches the scene / options state */
+    bool plan_valid = false; /* unused marker kept for setters that invalidate recorded frames (the key comparison decides) */
+    cudaGraphExec_t graph_exec = nullptr;      /* the recorded frame (rt_render) */
+    std::vector<unsigned char> graph_key;      /* what it was recorded for */
+    std::vector<unsigned char> last_key;       /* the previous call's key: a frame is recorded when it repeats */
+    int graph_launches = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -142,7 +147,10 @@ struct rt_scene {
     size_t stage_bytes = 0;
     unsigned char* pin = nullptr;   /* rt_scene_set_mesh: pinned host staging (meshes up to 64 MB) */
     size_t pin_bytes = 0;
-    uint64_t mesh_generation = 0; /* bumped whenever the mesh part of the blob changes: invalidates the anchored-ray bins */
+    uint64_t mesh_generation = 0; /* bumped whenever the TREE part of the blob changes: invalidates the anchored-ray bins */
+    std::vector<float> last_bvh;  /* host copy of the arr_bvh the packed tree was built from: a mesh uploaded again with the same tree
+                                   * (the per-frame upload of a caller that owns the geometry) skips the node relayout, keeps the bins */
+    int32_t last_nv = 0, last_nt = 0;
     /* anchored-ray bins (rt_bins.cuh): [0] camera, [1] light */
     struct AnchorBins {
         float A[3] = {0.f, 0.f, 0.f};
@@ -516,6 +524,7 @@ void rt_scene_destroy(rt_scene* s) {
     if (!s) return;
     DeviceGuard g(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
+    if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
     if (s->blob) cudaFree(s->blob);
     if (s->gamma_tab) cudaFree(s->gamma_tab);
     if (s->counters) cudaFree(s->counters);
@@ -565,6 +574,7 @@ int rt_scene_set_stream(rt_scene* s, void* cuda_stream) {
     if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
     s->stream = (cudaStream_t)cuda_stream;
     s->own_stream = false;
+    s->last_key.clear();
     return RT_OK;
 }
 
@@ -646,6 +656,9 @@ int rt_scene_set_mesh(rt_scene* s, const float* vertices, int32_t nv, const int3
         s->blob_bytes = 0;
         reset_mesh_fields(h);
         s->mesh_generation++;
+        s->plan_valid = false;
+        s->last_bvh.clear();
+        s->last_nv = s->last_nt = 0;
         h.mesh_id = -1;
         s->header_dirty = true;
         return RT_OK;
@@ -658,6 +671,35 @@ int rt_scene_set_mesh(rt_scene* s, const float* vertices, int32_t nv, const int3
             const int32_t v = tri_records[i * RT_TRI_RECORD_WORDS + k];
             if (v < 0 || v >= nv) return rtb::fail(RT_ERR_INVALID, "rt_scene_set_mesh: triangle %lld references vertex %d (nv=%d)", (long long)i, v, nv);
         }
+
+    /* ---- same tree as the last upload? Then only the triangles are new: the packed nodes, the wide index, the leaf table and the
+     * per-triangle leaf keys (all functions of arr_bvh alone) stay on the device, the bins stay valid (they list leaf BOXES), and the
+     * upload is vertices + records + the repack kernel. The interchange arrays still cross the bus: they are this call's input. */
+    if (s->blob && h.has_mesh && s->last_nv == nv && s->last_nt == nt && (int32_t)(s->last_bvh.size() / RT_BVH_NODE_FLOATS) == n_nodes && s->pin &&
+        memcmp(s->last_bvh.data(), arr_bvh, s->last_bvh.size() * sizeof(float)) == 0) {
+        const size_t vbytes = (size_t)nv * 3 * sizeof(float), rbytes = (size_t)nt * RT_TRI_RECORD_WORDS * sizeof(int32_t);
+        const size_t r_off = (vbytes + 255) & ~(size_t)255, l_off = (r_off + rbytes + 255) & ~(size_t)255;
+        CUDA_TRY(cudaStreamSynchronize(s->stream)); /* the pinned buffer may still feed the previous upload */
+        memcpy(s->pin, vertices, vbytes);
+        memcpy(s->pin + r_off, tri_records, rbytes);
+        CUDA_TRY(cudaMemcpyAsync(s->stage, s->pin, r_off + rbytes, cudaMemcpyHostToDevice, s->stream));
+        const int threads = 256, blocks = (nt + threads - 1) / threads;
+        rtk::repack_triangles<<<blocks, threads, 0, s->stream>>>(reinterpret_cast<float*>(s->stage), reinterpret_cast<int32_t*>(s->stage + r_off), nt,
+                                                                reinterpret_cast<int32_t*>(s->stage + l_off), reinterpret_cast<float4*>(s->blob + h.off_tris));
+        CUDA_TRY(cudaGetLastError());
+        const bool same_material = h.mesh_id == id && h.mesh_mirror == (mirror ? 1 : 0) && h.mesh_n_in == n_in && h.mesh_n_out == n_out &&
+                                   memcmp(h.mesh_albedo, albedo, sizeof h.mesh_albedo) == 0;
+        if (!same_material) {
+            h.mesh_id = id;
+            h.mesh_mirror = mirror ? 1 : 0;
+            h.mesh_n_in = n_in;
+            h.mesh_n_out = n_out;
+            memcpy(h.mesh_albedo, albedo, sizeof h.mesh_albedo);
+            s->header_dirty = true;
+            s->plan_valid = false;
+        }
+        return RT_OK;
+    }
 
     /* ---- node relayout on the host: 10-float pre-order nodes -> 64-B two-child records ----------------- */
     std::vector<int32_t> inner_index((size_t)n_nodes, -1);
@@ -955,6 +997,10 @@ int rt_scene_set_mesh(rt_scene* s, const float* vertices, int32_t nv, const int3
     h.off_wide = off_wide;
     h.off_leaves = off_leaves;
     s->mesh_generation++;
+    s->plan_valid = false;
+    s->last_bvh.assign(arr_bvh, arr_bvh + (size_t)n_nodes * RT_BVH_NODE_FLOATS);
+    s->last_nv = pin_need <= ((size_t)64 << 20) ? nv : 0; /* the fast path needs the pinned staging layout */
+    s->last_nt = nt;
     h.n_wide = n_wide;
     h.wide_depth = wide_depth;
     h.wroot_ref = wroot_ref;
@@ -1020,6 +1066,8 @@ int rt_scene_blob_import(rt_scene* s, const void* device_ptr, size_t bytes) {
     }
     s->header = h;
     s->max_leaf = h.max_leaf; /* host-side guard of the tie-break rank (push_order 0): travels with the blob */
+    s->last_bvh.clear();
+    s->last_nv = s->last_nt = 0;
     s->header_dirty = false;
     s->mesh_generation++; /* the anchored-ray bins of the previous mesh are stale */
     s->plan_valid = false;
@@ -1101,9 +1149,40 @@ int rt_scene_sync(rt_scene* s, rt_stats* stats) {
     return RT_OK;
 }
 
-int rt_render(rt_scene* s, const rt_params* p, uint32_t flags, uint8_t* rgb_out, int32_t* hit_obj, int32_t* hit_tri, float* hit_t,
-              uint8_t* shadow, rt_stats* stats) {
-    if (!s || !p) return rtb::fail(RT_ERR_INVALID, "rt_render: NULL scene or params");
+} /* extern "C" */
+
+namespace {
+
+/* What rt_render decides before it launches (plan_frame) and what the launches need (enqueue_frame). Plain data: two frames with
+ * byte-equal plans (and scene state, see frame_key) are the same sequence of launches. */
+struct FramePlan {
+    rt_params p;
+    uint32_t flags;
+    int rows;
+    size_t npx;
+    void* user[5];
+    void* dev[5];
+    bool copy_back[5];
+    size_t bytes[5];
+    rtk::RenderArgs a;
+    int variant;       /* 0 / 1 render_mega, 2 wavefront, 3 render_stoch */
+    unsigned grid;     /* render_mega / render_stoch */
+    bool stochastic, count;
+    /* wavefront pipeline */
+    bool wide, anchored, diffuse_only, trav_round0, dbg_times;
+    int segments, npool_cap, n_strips, spill_cap;
+    size_t trav_smem;
+    unsigned pers_grid;
+    int* dbg_ptr;
+    size_t dbg_ints;
+    size_t st_rng_off, st_total_off, st_rec_off, task_slack;
+    int prelaunches;   /* one-off launches plan_frame enqueued itself (random-stream table) */
+};
+
+/* ---- rt_render, first half: everything that is decided, sized or (re)built before a frame is launched -------------------------
+ * Validation, output buffers, kernel variant, queue / task / overflow buffers, the anchored-ray bins. May allocate and
+ * synchronise; enqueues nothing of the frame itself (only one-off set-up work: the random-stream table, a bins build). */
+int plan_frame(rt_scene* s, const rt_params* p, uint32_t flags, void* const user_in[5], FramePlan& P) {
     if (p->W <= 0 || p->H <= 0 || p->num_rays < 1 || p->num_bounce < 0) return rtb::fail(RT_ERR_INVALID, "rt_render: bad W/H/num_rays/num_bounce");
     const bool stochastic = p->aa_sigma != 0.f || p->indirect != 0;
     if (stochastic && p->num_bounce + (p->extra_segment ? 1 : 0) > RT_STOCH_MAX_SEGMENTS)
@@ -1130,8 +1209,6 @@ int rt_render(rt_scene* s, const rt_params* p, uint32_t flags, uint8_t* rgb_out,
         if (h.has_mesh && (h.mesh_id >= n_obj || ((seen >> h.mesh_id) & 1u))) ok = false;
         if (!ok) return rtb::fail(RT_ERR_INVALID, "rt_render: object ids must be a permutation of 0..%d", n_obj - 1);
     }
-    DeviceGuard g(s->device);
-    if (!g.ok) return rtb::fail(RT_ERR_CUDA, "rt_render: cudaSetDevice failed");
     /* a still-pending RT_RENDER_NO_SYNC call needs no wait: counters, scratch buffers and events are reused in
      * stream order, and the stats of the older call are simply superseded */
     /* the kernels take the header by value from the host copy: a changed light or sphere set needs no upload here
@@ -1143,7 +1220,7 @@ int rt_render(rt_scene* s, const rt_params* p, uint32_t flags, uint8_t* rgb_out,
     }
 
     const size_t npx = (size_t)rows * p->W;
-    void* user[5] = {rgb_out, hit_obj, hit_tri, hit_t, shadow};
+    void* user[5] = {user_in[0], user_in[1], user_in[2], user_in[3], user_in[4]};
     const size_t bytes[5] = {npx * 3, npx * 4, npx * 4, npx * 4, npx};
     void* dev[5];
     bool copy_back[5];
@@ -1162,6 +1239,7 @@ int rt_render(rt_scene* s, const rt_params* p, uint32_t flags, uint8_t* rgb_out,
     }
 
     rtk::RenderArgs a;
+    memset(&a, 0, sizeof a); /* padding too: the plan is compared byte-wise with the previous frame's */
     a.W = p->W;
     a.H = p->H;
     a.rows = rows;
@@ -1186,412 +1264,561 @@ int rt_render(rt_scene* s, const rt_params* p, uint32_t flags, uint8_t* rgb_out,
     a.gamma_tab = s->gamma_tab;
     a.debug_cost = s->opt.debug_cost;
 
-    int launches = 0;
-    bool strip_copied = false; /* host outputs already copied back band by band */
-    CUDA_TRY(cudaEventRecord(s->ev0, s->stream)); /* kernel_ms covers everything a frame enqueues, counter resets included */
-    {
-        const int tiles_x = (p->W + 15) / 16, tiles_y = (rows + 7) / 8;
-        const unsigned grid = (unsigned)tiles_x * (unsigned)tiles_y;
-        const bool count = (flags & RT_RENDER_COUNT_WORK) != 0;
-        int variant = s->opt.variant;
-        /* stochastic mode: one wavefront pass per sample (the samples of a pixel share one random stream); the
-         * thread-per-pixel kernel render_stoch is the fallback and the in-library cross-check (RT_STOCH_MEGA=1) */
-        const bool stoch_mega = s->opt.stoch_mega != 0;
-        if (stochastic && (variant != 2 || stoch_mega)) variant = 3;
-        /* tie-break rank of render_wave: (n_tris - leaf_start) and the in-leaf offset share 32 bits */
-        int bits_n = 1;
-        while ((1ll << bits_n) <= (long long)h.n_tris) bits_n++;
-        a.rank_off_bits = std::min(32 - bits_n, 16);
-        if (variant == 2 && p->push_order == 0 && h.has_mesh && (long long)s->max_leaf > (1ll << a.rank_off_bits)) variant = 1;
-        const int segments = a.segments;
-        if (variant == 2 && segments > WF_MAX_ROUNDS - 1) variant = stochastic ? 3 : 1;
-        if (stochastic && variant == 1) variant = 3;
-        s->last_was_wavefront = (variant == 2);
-        if (stochastic) {
-            /* start states of the random streams: once per (seed, W, H), not per launch (rt_stochastic.cuh) */
-            const unsigned long long seed = p->reserved ? (unsigned long long)(unsigned int)p->reserved : 123456ull; /* optimized.cu:745 */
-            const size_t frame_px = (size_t)p->W * p->H;
-            if (!s->rng_states || s->rng_W != p->W || s->rng_H != p->H || s->rng_seed != seed) {
-                if (s->rng_capacity < frame_px) {
-                    CUDA_TRY(cudaStreamSynchronize(s->stream));
-                    if (s->rng_states) cudaFree(s->rng_states);
-                    s->rng_states = nullptr;
-                    s->rng_capacity = 0;
-                    CUDA_TRY(cudaMalloc(&s->rng_states, frame_px * sizeof(rtk::XorwowState)));
-                    s->rng_capacity = frame_px;
-                }
-                rtk::xorwow_init_states<<<(unsigned)((frame_px + 255) / 256), 256, 0, s->stream>>>(seed, (unsigned)frame_px, s->rng_states);
-                CUDA_TRY(cudaGetLastError());
-                s->rng_W = p->W;
-                s->rng_H = p->H;
-                s->rng_seed = seed;
-                launches++;
-                CUDA_TRY(cudaEventRecord(s->ev0, s->stream)); /* the one-off table build is not part of the frame time */
+    P.prelaunches = 0;
+    const int tiles_x = (p->W + 15) / 16, tiles_y = (rows + 7) / 8;
+    const unsigned grid = (unsigned)tiles_x * (unsigned)tiles_y;
+    const bool count = (flags & RT_RENDER_COUNT_WORK) != 0;
+    int variant = s->opt.variant;
+    /* stochastic mode: one wavefront pass per sample (the samples of a pixel share one random stream); the
+     * thread-per-pixel kernel render_stoch is the fallback and the in-library cross-check (RT_STOCH_MEGA=1) */
+    const bool stoch_mega = s->opt.stoch_mega != 0;
+    if (stochastic && (variant != 2 || stoch_mega)) variant = 3;
+    /* tie-break rank of render_wave: (n_tris - leaf_start) and the in-leaf offset share 32 bits */
+    int bits_n = 1;
+    while ((1ll << bits_n) <= (long long)h.n_tris) bits_n++;
+    a.rank_off_bits = std::min(32 - bits_n, 16);
+    if (variant == 2 && p->push_order == 0 && h.has_mesh && (long long)s->max_leaf > (1ll << a.rank_off_bits)) variant = 1;
+    const int segments = a.segments;
+    if (variant == 2 && segments > WF_MAX_ROUNDS - 1) variant = stochastic ? 3 : 1;
+    if (stochastic && variant == 1) variant = 3;
+    s->last_was_wavefront = (variant == 2);
+    if (stochastic) {
+        /* start states of the random streams: once per (seed, W, H), not per launch (rt_stochastic.cuh) */
+        const unsigned long long seed = p->reserved ? (unsigned long long)(unsigned int)p->reserved : 123456ull; /* optimized.cu:745 */
+        const size_t frame_px = (size_t)p->W * p->H;
+        if (!s->rng_states || s->rng_W != p->W || s->rng_H != p->H || s->rng_seed != seed) {
+            if (s->rng_capacity < frame_px) {
+                CUDA_TRY(cudaStreamSynchronize(s->stream));
+                if (s->rng_states) cudaFree(s->rng_states);
+                s->rng_states = nullptr;
+                s->rng_capacity = 0;
+                CUDA_TRY(cudaMalloc(&s->rng_states, frame_px * sizeof(rtk::XorwowState)));
+                s->rng_capacity = frame_px;
             }
+            rtk::xorwow_init_states<<<(unsigned)((frame_px + 255) / 256), 256, 0, s->stream>>>(seed, (unsigned)frame_px, s->rng_states);
+            CUDA_TRY(cudaGetLastError());
+            s->rng_W = p->W;
+            s->rng_H = p->H;
+            s->rng_seed = seed;
+            P.prelaunches++; /* the one-off table build is not part of the frame time */
         }
-        if (variant == 2) {
-            /* the wide index (rt_layout.h) is the production search structure; the instrumented build counts the reference's
-             * own node visits and therefore walks the two-child records, as does RT_WIDE=0 (A/B timing, cross-check) */
-            /* RT_WIDE: 1 on, 0 off; unset: on for the incoherent bounce rays of the stochastic mode (measured, 6 blocks per SM:
-             * stochastic 4 3 4.91 -> 4.67 ms, but the mirror 4K frame 1.23 -> 1.28 ms and no gain for the tree search of
-             * coherent rays, profiles/r01_notes.md) */
-            const int env_wide_v = s->opt.wide;
-            const bool env_wide = env_wide_v > 0 || (env_wide_v < 0 && stochastic && p->indirect != 0);
-            const bool env_wide_count = s->opt.wide_count != 0; /* timeline of the wide kernel: node_visits then counts wide nodes */
-            const bool wide = env_wide && (!count || env_wide_count) && h.n_wide > 0;
-            /* anchored rays (rt_bins.cuh): camera rays and shadow rays find their leaves through per-anchor bins and wf_leaves
-             * tests the triangles; wf_traverse keeps the rays that start anywhere else (bounces). The instrumented build
-             * counts the reference's node visits and therefore searches the tree; RT_ANCHOR=0 does so too (A/B, cross-check). */
-            const int env_anchor = s->opt.anchored; /* 0 off, 1 on, -1: by mesh size */
-            /* measured (tools/size_sweep.py, profiles/r01_notes.md): the bins win from 1 k to 1 M leaves (1080p: 0.25 vs 0.41 ms at
-             * 1 k, 0.77 vs 1.20 ms at 241 k, 5.97 vs 6.46 ms at 1 M); at 2.5 M leaves and 4K a cell lists hundreds of leaves and
-             * one task per candidate loses against the tree search (13.9 vs 12.9 ms) */
-            bool anchored = (env_anchor > 0 || (env_anchor < 0 && h.n_leaves <= 1200000)) && !count && h.has_mesh && h.n_leaves > 0 && segments > 0;
-            if (anchored) {
-                int rc = ensure_bins(s, 0, p->cam);
-                if (rc == RT_OK) rc = ensure_bins(s, 1, h.L);
-                if (rc != RT_OK) return rc;
-                anchored = s->bins[0].usable && s->bins[1].usable;
-            }
-            s->last_was_anchored = anchored;
-            /* no mirror, no refractive object: the kernels without the reflection / refraction code (smaller, less instruction fetch) */
-            bool diffuse_only = !(h.has_mesh && (h.mesh_mirror || h.mesh_n_in != h.mesh_n_out)) && s->opt.diffuse_kernels != 0;
-            for (int k = 0; k < h.n_spheres; k++) diffuse_only = diffuse_only && !h.spheres[k].mirror && h.spheres[k].n_in == h.spheres[k].n_out;
-            /* round 0 holds tree-searched queries only when a path can go on inside wf_generate: past a mirror or refractive
-             * sphere, or along the indirect bounce of a pixel shaded on the spot */
-            bool trav_round0 = stochastic && p->indirect;
-            for (int k = 0; k < h.n_spheres; k++) trav_round0 = trav_round0 || h.spheres[k].mirror || h.spheres[k].n_in != h.spheres[k].n_out;
-            trav_round0 = trav_round0 && segments >= 2;
-            /* node pool of wf_traverse: 32 lanes x (levels of the packed tree + roots of two batches + slack) */
-            int npool_cap = wide ? std::min(96 * (h.wide_depth + 2), 352) : std::min(32 * (h.max_depth + 4), 256);
-            if (s->opt.npool_cap > 0) npool_cap = std::max(64, std::min(s->opt.npool_cap, npool_cap)) & ~31; /* test hook: a small pool forces the spill path */
-            const size_t warp_bytes = (sizeof(rtk::WfWarpSmem) + (size_t)npool_cap * sizeof(int) + 15) & ~(size_t)15;
-            const size_t trav_smem = warp_bytes * (WF_THREADS / 32);
-            if (trav_smem > 200 * 1024) return rtb::fail(RT_ERR_UNSUPPORTED, "rt_render: BVH depth %d needs %zu B of shared memory per block", h.max_depth, trav_smem);
-            if (s->trav_blocks_per_sm == 0 || s->trav_smem != trav_smem || s->trav_wide != wide) {
-                s->trav_wide = wide;
-                int nb = 0;
-                CUDA_TRY(cudaFuncSetAttribute(rtk::wf_traverse<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trav_smem));
-                CUDA_TRY(cudaFuncSetAttribute(rtk::wf_traverse<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trav_smem));
-                CUDA_TRY(cudaFuncSetAttribute(rtk::wf_traverse<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trav_smem));
-                CUDA_TRY(cudaFuncSetAttribute(rtk::wf_traverse<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trav_smem));
-                CUDA_TRY(cudaFuncSetAttribute(rtk::wf_traverse<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trav_smem));
-                CUDA_TRY(cudaFuncSetAttribute(rtk::wf_traverse<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trav_smem));
-                CUDA_TRY(cudaFuncSetAttribute(rtk::wf_traverse<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trav_smem));
-                CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wide ? rtk::wf_traverse<false, false, true> : rtk::wf_traverse<false, false, false>, WF_THREADS, trav_smem));
-                cudaDeviceProp prop;
-                CUDA_TRY(cudaGetDeviceProperties(&prop, s->device));
-                s->trav_blocks_per_sm = std::max(nb, 1);
-                s->trav_smem = trav_smem;
-                s->sm_count = prop.multiProcessorCount;
-                if (!s->wf_counters) {
-                    CUDA_TRY(cudaMalloc(&s->wf_counters, RT_MAX_STRIPS * sizeof(rtk::WfCounters)));
-                    CUDA_TRY(cudaMallocHost(&s->h_wf_counters, RT_MAX_STRIPS * sizeof(rtk::WfCounters)));
-                    CUDA_TRY(cudaEventCreateWithFlags(&s->fork_ev, cudaEventDisableTiming));
-                    for (int k = 0; k < RT_MAX_STRIPS; k++) {
-                        CUDA_TRY(cudaStreamCreateWithFlags(&s->strip_stream[k], cudaStreamNonBlocking));
-                        CUDA_TRY(cudaEventCreateWithFlags(&s->strip_done[k], cudaEventDisableTiming));
-                        CUDA_TRY(cudaStreamCreateWithFlags(&s->side_stream[k], cudaStreamNonBlocking));
-                        CUDA_TRY(cudaEventCreateWithFlags(&s->side_fork[k], cudaEventDisableTiming));
-                        CUDA_TRY(cudaEventCreateWithFlags(&s->side_join[k], cudaEventDisableTiming));
-                    }
-                }
-            }
-            if (s->wf_capacity < npx) {
-                if (s->wf_queue) cudaFree(s->wf_queue);
-                s->wf_queue = nullptr;
-                s->wf_capacity = 0;
-                CUDA_TRY(cudaMalloc(&s->wf_queue, 3 * npx * sizeof(rtk::QEntry)));
-                s->wf_capacity = npx;
-            }
-            const size_t task_slack = 4096;
-            if (anchored) {
-                const size_t need = (size_t)s->task_factor * npx + task_slack * RT_MAX_STRIPS;
-                if (s->wf_tasks_cap < need) {
-                    CUDA_TRY(cudaStreamSynchronize(s->stream));
-                    if (s->wf_tasks) cudaFree(s->wf_tasks);
-                    s->wf_tasks = nullptr;
-                    s->wf_tasks_cap = 0;
-                    CUDA_TRY(cudaMalloc(&s->wf_tasks, need * sizeof(int2)));
-                    s->wf_tasks_cap = need;
-                }
-            }
-            const bool dbg_times = s->opt.debug_times != 0;
-            const bool dbg_warps = count && s->opt.debug_warps[0];
-            /* Strips: the frame is cut into bands of rows, each rendered by its own generate / traverse / shade chain
-             * on its own stream. The end of a persistent traversal launch is a latency-bound tail (a few warps
-             * finishing their expensive rays on an otherwise idle GPU, profiles/r01_notes.md); with strips the tail of
-             * one band is covered by the bulk of the next, and only the last launch's tail is exposed. */
-            const bool strips_fixed = s->opt.strips > 0;
-            int n_strips = strips_fixed ? std::min(s->opt.strips, RT_MAX_STRIPS) : 2;
-            {   /* host outputs: more bands, so that only the last band's copy-back is not covered by rendering */
-                bool any_copy = false;
-                for (int k = 0; k < 5; k++) any_copy = any_copy || copy_back[k];
-                if (any_copy && !strips_fixed) n_strips = std::min(RT_MAX_STRIPS, 4);
-            }
-            if (rows < 64 * n_strips) n_strips = std::max(1, rows / 64);
-            /* a small shard (one rank's rows of a frame split over 8 GPUs) is bound by launch latencies: one band
-             * (measured: 4K depth-4 frame, 1/8 of the rows: 0.33 ms against 0.37 ms with two) */
-            if (!strips_fixed && npx < 1500000 && !(flags & RT_RENDER_COUNT_WORK)) {
-                bool any_copy = false;
-                for (int k = 0; k < 5; k++) any_copy = any_copy || copy_back[k];
-                if (!any_copy) n_strips = 1;
-            }
-            if (dbg_times || dbg_warps) n_strips = 1;
-            const unsigned pers_grid = (unsigned)(s->sm_count * s->trav_blocks_per_sm);
-            const int spill_cap = WF_SLOTS * std::max(h.max_depth + 2, (RT_WIDE - 1) * h.wide_depth + 2); /* per traversal warp: every ray slot holding a full path of pending siblings */
-            {
-                const size_t ints = (size_t)spill_cap * pers_grid * (WF_THREADS / 32) * n_strips;
-                if (s->wf_spill_ints < ints) {
-                    CUDA_TRY(cudaStreamSynchronize(s->stream));
-                    if (s->wf_spill) cudaFree(s->wf_spill);
-                    s->wf_spill = nullptr;
-                    s->wf_spill_ints = 0;
-                    CUDA_TRY(cudaMalloc(&s->wf_spill, ints * sizeof(int)));
-                    s->wf_spill_ints = ints;
-                }
-            }
-            int* dbg_ptr = nullptr;
-            if (dbg_warps) {
-                const size_t ints = (size_t)(segments + 1) * pers_grid * (WF_THREADS / 32) * 16;
-                if (s->dbg_warps_ints < ints) {
-                    if (s->dbg_warps) cudaFree(s->dbg_warps);
-                    CUDA_TRY(cudaMalloc(&s->dbg_warps, ints * sizeof(int)));
-                    s->dbg_warps_ints = ints;
-                }
-                CUDA_TRY(cudaMemsetAsync(s->dbg_warps, 0, ints * sizeof(int), s->stream));
-                dbg_ptr = s->dbg_warps;
-            }
-            CUDA_TRY(cudaMemsetAsync(s->wf_counters, 0, RT_MAX_STRIPS * sizeof(rtk::WfCounters), s->stream));
-            /* stochastic mode: per compact pixel 32 B of stream state, 16 B of colour sum, 32 B per path segment of records */
-            const size_t st_rng_off = 0, st_total_off = npx * 32, st_rec_off = st_total_off + npx * 16;
-            if (stochastic) {
-                const size_t need = st_rec_off + npx * 32 * (size_t)std::max(segments, 1);
-                if (s->st_buf_bytes < need) {
-                    CUDA_TRY(cudaStreamSynchronize(s->stream));
-                    if (s->st_buf) cudaFree(s->st_buf);
-                    s->st_buf = nullptr;
-                    s->st_buf_bytes = 0;
-                    CUDA_TRY(cudaMalloc(&s->st_buf, need));
-                    s->st_buf_bytes = need;
-                }
-            }
-            if (n_strips > 1) CUDA_TRY(cudaEventRecord(s->fork_ev, s->stream));
-            cudaEvent_t dev_ev[40];
-            int n_ev = 0;
-            auto mark = [&]() {
-                if (dbg_times && n_ev < 40) {
-                    cudaEventCreate(&dev_ev[n_ev]);
-                    cudaEventRecord(dev_ev[n_ev++], s->stream);
-                }
-            };
-            mark();
-            int row0 = 0;
-            for (int st = 0; st < n_strips; st++) {
-                /* band boundaries on multiples of 8 rows (generate tiles are 8x4) */
-                int row1 = (st == n_strips - 1) ? rows : (int)(((long long)rows * (st + 1) / n_strips) & ~7ll);
-                if (row1 <= row0) continue;
-                const int srows = row1 - row0;
-                const size_t spx = (size_t)srows * p->W, px0 = (size_t)row0 * p->W;
-                cudaStream_t stream = n_strips > 1 ? s->strip_stream[st] : s->stream;
-                if (n_strips > 1) CUDA_TRY(cudaStreamWaitEvent(stream, s->fork_ev, 0));
-                rtk::WfArgs g;
-                g.a = a;
-                g.a.rows = srows;
-                g.a.row_begin = a.row_begin + row0 * a.row_step;
-                g.a.rgb = a.rgb ? a.rgb + px0 * 3 : nullptr;
-                g.a.hit_obj = a.hit_obj ? a.hit_obj + px0 : nullptr;
-                g.a.hit_tri = a.hit_tri ? a.hit_tri + px0 : nullptr;
-                g.a.hit_t = a.hit_t ? a.hit_t + px0 : nullptr;
-                g.a.shadow = a.shadow ? a.shadow + px0 : nullptr;
-                g.qA[0] = s->wf_queue + px0;
-                g.qA[1] = s->wf_queue + s->wf_capacity + px0;
-                g.qS = s->wf_queue + 2 * s->wf_capacity + px0;
-                g.c = s->wf_counters + st;
-                g.round = 0;
-                g.spill = s->wf_spill + (size_t)st * spill_cap * pers_grid * (WF_THREADS / 32);
-                g.spill_cap = spill_cap;
-                {
-                    g.run_shift = s->opt.run_shift;
-                    g.gss_factor = s->opt.gss;
-                }
-                g.dbg_warps = dbg_ptr;
-                g.anchored = anchored ? 1 : 0;
-                g.bins[0] = bins_view(s->bins[0]);
-                g.bins[1] = bins_view(s->bins[1]);
-                g.tasks = anchored ? s->wf_tasks + (size_t)s->task_factor * px0 + task_slack * st : nullptr;
-                g.qcap = (int)spx;
-                for (int k = 0; k < RT_MAX_SPHERES; k++) {
-                    const DevSphere& sp = h.spheres[k];
-                    /* the operations of Sphere::intersect / sphere_t, in their order, in float (no contraction on the host) */
-                    volatile float ocx = a.camx - sp.cx, ocy = a.camy - sp.cy, ocz = a.camz - sp.cz;
-                    volatile float xx = ocx * ocx, yy = ocy * ocy, zz = ocz * ocz;
-                    volatile float n2 = xx + yy;
-                    n2 = n2 + zz;
-                    volatile float cc = n2 - sp.RR;
-                    g.cam_sph[k] = k < h.n_spheres ? make_float4(ocx, ocy, ocz, cc) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-                g.task_cap = anchored ? (int)std::min<size_t>((size_t)s->task_factor * spx + task_slack, (size_t)0x7fffffff) : 0;
-                if (anchored && s->leaves_blocks_per_sm == 0) { /* one resident wave of wf_leaves: every block gets the same share of the tasks */
-                    int nb = 0;
-                    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rtk::wf_leaves<false>, WF_THREADS, 0));
-                    s->leaves_blocks_per_sm = std::max(nb, 1);
-                }
-                const int env_lb = s->opt.leaves_blocks;
-                const unsigned leaves_grid = (unsigned)(s->sm_count * (env_lb > 0 ? env_lb : std::max(s->leaves_blocks_per_sm, 1)));
-                const dim3 gen_grid((unsigned)(((p->W + 7) / 8 + (WF_THREADS / 32) - 1) / (WF_THREADS / 32)), (unsigned)((srows + 3) / 4));
-                const unsigned shade_grid = (unsigned)std::min<size_t>((spx + WF_THREADS - 1) / WF_THREADS, (size_t)s->sm_count * 16);
-                g.stoch = stochastic ? 1 : 0;
-                g.sample = 0;
-                g.last_sample = 1;
-                g.indirect = p->indirect;
-                g.libm = s->opt.transcendentals;
-                g.sticky = s->sticky;
-                g.aa_sigma = p->aa_sigma;
-                g.npx = (int)spx;
-                g.rng_table = reinterpret_cast<const uint4*>(s->rng_states);
-                g.rng = stochastic ? reinterpret_cast<uint4*>(s->st_buf + st_rng_off) + px0 * 2 : nullptr;
-                g.total = stochastic ? reinterpret_cast<float4*>(s->st_buf + st_total_off) + px0 : nullptr;
-                g.rec = stochastic ? reinterpret_cast<float4*>(s->st_buf + st_rec_off) + px0 * 2 * (size_t)std::max(segments, 1) : nullptr;
-                /* deterministic mode: one pass (identical samples are traced once). Stochastic mode: one pass per sample,
-                 * in order, because the samples of a pixel share one random stream. */
-                const int n_pass = stochastic ? p->num_rays : 1;
-                for (int pass = 0; pass < n_pass; pass++) {
-                    g.sample = pass;
-                    g.last_sample = pass == n_pass - 1;
-                    g.round = 0;
-                    if (pass > 0) /* the queue counters restart with every pass; the work statistics keep adding up */
-                        CUDA_TRY(cudaMemsetAsync(reinterpret_cast<unsigned char*>(s->wf_counters + st) + offsetof(rtk::WfCounters, nA), 0,
-                                                 sizeof(rtk::WfCounters) - offsetof(rtk::WfCounters, nA), stream));
-                    if (stochastic) {
-                        if (count) rtk::wf_generate<true, true><<<gen_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
-                        else if (diffuse_only) rtk::wf_generate<false, true, true><<<gen_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
-                        else rtk::wf_generate<false, true><<<gen_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
-                    } else {
-                        if (count) rtk::wf_generate<true, false><<<gen_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
-                        else if (diffuse_only && anchored) rtk::wf_generate<false, false, true, true><<<gen_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
-                        else if (diffuse_only) rtk::wf_generate<false, false, true><<<gen_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
-                        else rtk::wf_generate<false, false><<<gen_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
-                    }
-                    launches++;
-                    mark();
-                    /* without a mesh no query is ever posted: wf_generate runs every path to its end */
-                    for (int r = 0; r <= segments && segments > 0 && h.has_mesh; r++) {
-                        g.round = r;
-                        if (anchored) {
-                            /* closest-hit queries of a round >= 1 start somewhere in the scene: tree search; every shadow
-                             * query and the camera rays of round 0 are (ray, leaf) tasks */
-                            const bool trav_now = r < segments && (r >= 1 || trav_round0);
-                            /* the two kernels of the round touch disjoint entries: the tree search goes to the band's side stream
-                             * and runs beside wf_leaves (its latency-bound tail is covered by the LSU-bound task kernel) */
-                            const bool env_side = s->opt.side_stream != 0;
-                            const bool side = trav_now && env_side && !dbg_times;
-                            cudaStream_t tstream = side ? s->side_stream[st] : stream;
-                            if (side) {
-                                CUDA_TRY(cudaEventRecord(s->side_fork[st], stream));
-                                CUDA_TRY(cudaStreamWaitEvent(tstream, s->side_fork[st], 0));
-                            }
-                            if (trav_now) {
-                                if (stochastic) {
-                                    if (wide) rtk::wf_traverse<false, true, true><<<pers_grid, WF_THREADS, trav_smem, tstream>>>(s->header, s->blob, g, npool_cap);
-                                    else rtk::wf_traverse<false, true, false><<<pers_grid, WF_THREADS, trav_smem, tstream>>>(s->header, s->blob, g, npool_cap);
-                                } else {
-                                    if (wide) rtk::wf_traverse<false, false, true><<<pers_grid, WF_THREADS, trav_smem, tstream>>>(s->header, s->blob, g, npool_cap);
-                                    else rtk::wf_traverse<false, false, false><<<pers_grid, WF_THREADS, trav_smem, tstream>>>(s->header, s->blob, g, npool_cap);
-                                }
-                                launches++;
-                                mark();
-                            }
-                            if (stochastic) rtk::wf_leaves<true><<<leaves_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
-                            else rtk::wf_leaves<false><<<leaves_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
-                            if (side) { /* join: wf_shade needs both */
-                                CUDA_TRY(cudaEventRecord(s->side_join[st], tstream));
-                                CUDA_TRY(cudaStreamWaitEvent(stream, s->side_join[st], 0));
-                            }
-                        } else if (stochastic) {
-                            if (count) rtk::wf_traverse<true, true, false><<<pers_grid, WF_THREADS, trav_smem, stream>>>(s->header, s->blob, g, npool_cap);
-                            else if (wide) rtk::wf_traverse<false, true, true><<<pers_grid, WF_THREADS, trav_smem, stream>>>(s->header, s->blob, g, npool_cap);
-                            else rtk::wf_traverse<false, true, false><<<pers_grid, WF_THREADS, trav_smem, stream>>>(s->header, s->blob, g, npool_cap);
-                        } else {
-                            if (count && wide) rtk::wf_traverse<true, false, true><<<pers_grid, WF_THREADS, trav_smem, stream>>>(s->header, s->blob, g, npool_cap);
-                            else if (count) rtk::wf_traverse<true, false, false><<<pers_grid, WF_THREADS, trav_smem, stream>>>(s->header, s->blob, g, npool_cap);
-                            else if (wide) rtk::wf_traverse<false, false, true><<<pers_grid, WF_THREADS, trav_smem, stream>>>(s->header, s->blob, g, npool_cap);
-                            else rtk::wf_traverse<false, false, false><<<pers_grid, WF_THREADS, trav_smem, stream>>>(s->header, s->blob, g, npool_cap);
-                        }
-                        launches++;
-                        mark();
-                        if (r == segments) break;
-                        if (stochastic) {
-                            if (count) rtk::wf_shade<true, true><<<shade_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
-                            else if (diffuse_only) rtk::wf_shade<false, true, true><<<shade_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
-                            else rtk::wf_shade<false, true><<<shade_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
-                        } else {
-                            if (count) rtk::wf_shade<true, false><<<shade_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
-                            else if (diffuse_only && anchored) rtk::wf_shade<false, false, true, true><<<shade_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
-                            else if (diffuse_only) rtk::wf_shade<false, false, true><<<shade_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
-                            else rtk::wf_shade<false, false><<<shade_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
-                        }
-                        launches++;
-                        mark();
-                    }
-                    if (stochastic) {
-                        rtk::wf_fold<<<(unsigned)((spx + 255) / 256), 256, 0, stream>>>(g);
-                        launches++;
-                        mark();
-                    }
-                }
-                if (n_strips > 1) {
-                    /* host outputs: this band's copy-back rides on the band's stream and overlaps the other bands' kernels
-                     * (kernel_ms then spans the copies of all bands but the last as well) */
-                    const size_t elem[5] = {3, 4, 4, 4, 1};
-                    for (int k = 0; k < 5; k++)
-                        if (copy_back[k]) {
-                            CUDA_TRY(cudaMemcpyAsync((unsigned char*)user[k] + px0 * elem[k], (unsigned char*)dev[k] + px0 * elem[k], spx * elem[k], cudaMemcpyDeviceToHost, stream));
-                            strip_copied = true;
-                        }
-                    CUDA_TRY(cudaEventRecord(s->strip_done[st], stream));
-                    CUDA_TRY(cudaStreamWaitEvent(s->stream, s->strip_done[st], 0));
-                }
-                row0 = row1;
-            }
-            if (dbg_times) {
-                cudaStreamSynchronize(s->stream);
-                fprintf(stderr, "[times us]");
-                for (int k = 1; k < n_ev; k++) {
-                    float ms = 0.f;
-                    cudaEventElapsedTime(&ms, dev_ev[k - 1], dev_ev[k]);
-                    fprintf(stderr, " %.1f", ms * 1e3f);
-                }
-                fprintf(stderr, "\n");
-                for (int k = 0; k < n_ev; k++) cudaEventDestroy(dev_ev[k]);
-            }
-            launches--; /* the common launches++ below counts one */
-        } else if (variant == 3) {
-            CUDA_TRY(cudaMemsetAsync(s->counters, 0, RT_NCOUNTERS * sizeof(unsigned long long), s->stream));
-            if (count) rtk::render_stoch<true><<<grid, 128, 0, s->stream>>>(s->header, s->blob, a, s->rng_states, p->aa_sigma, p->indirect, s->opt.transcendentals);
-            else rtk::render_stoch<false><<<grid, 128, 0, s->stream>>>(s->header, s->blob, a, s->rng_states, p->aa_sigma, p->indirect, s->opt.transcendentals);
-        } else if (variant == 0) {
-            CUDA_TRY(cudaMemsetAsync(s->counters, 0, RT_NCOUNTERS * sizeof(unsigned long long), s->stream));
-            if (count) rtk::render_mega<true, false><<<grid, 128, 0, s->stream>>>(s->header, s->blob, a);
-            else rtk::render_mega<false, false><<<grid, 128, 0, s->stream>>>(s->header, s->blob, a);
-        } else {
-            CUDA_TRY(cudaMemsetAsync(s->counters, 0, RT_NCOUNTERS * sizeof(unsigned long long), s->stream));
-            if (count) rtk::render_mega<true, true><<<grid, 128, 0, s->stream>>>(s->header, s->blob, a);
-            else rtk::render_mega<false, true><<<grid, 128, 0, s->stream>>>(s->header, s->blob, a);
-        }
-        launches++;
-        CUDA_TRY(cudaGetLastError());
     }
+    bool wide = false, anchored = false, diffuse_only = false, trav_round0 = false, dbg_times = false;
+    int npool_cap = 0, n_strips = 1, spill_cap = 0;
+    size_t trav_smem = 0, st_rng_off = 0, st_total_off = 0, st_rec_off = 0;
+    const size_t task_slack = 4096;
+    unsigned pers_grid = 0;
+    int* dbg_ptr = nullptr;
+    if (variant == 2) {
+    /* the wide index (rt_layout.h) is the production search structure; the instrumented build counts the reference's
+     * own node visits and therefore walks the two-child records, as does RT_WIDE=0 (A/B timing, cross-check) */
+    /* RT_WIDE: 1 on, 0 off; unset: on for the incoherent bounce rays of the stochastic mode (measured, 6 blocks per SM:
+     * stochastic 4 3 4.91 -> 4.67 ms, but the mirror 4K frame 1.23 -> 1.28 ms and no gain for the tree search of
+     * coherent rays, profiles/r01_notes.md) */
+    const int env_wide_v = s->opt.wide;
+    const bool env_wide = env_wide_v > 0 || (env_wide_v < 0 && stochastic && p->indirect != 0);
+    const bool env_wide_count = s->opt.wide_count != 0; /* timeline of the wide kernel: node_visits then counts wide nodes */
+    const bool wide = env_wide && (!count || env_wide_count) && h.n_wide > 0;
+    /* anchored rays (rt_bins.cuh): camera rays and shadow rays find their leaves through per-anchor bins and wf_leaves
+     * tests the triangles; wf_traverse keeps the rays that start anywhere else (bounces). The instrumented build
+     * counts the reference's node visits and therefore searches the tree; RT_ANCHOR=0 does so too (A/B, cross-check). */
+    const int env_anchor = s->opt.anchored; /* 0 off, 1 on, -1: by mesh size */
+    /* measured (tools/size_sweep.py, profiles/r01_notes.md): the bins win from 1 k to 1 M leaves (1080p: 0.25 vs 0.41 ms at
+     * 1 k, 0.77 vs 1.20 ms at 241 k, 5.97 vs 6.46 ms at 1 M); at 2.5 M leaves and 4K a cell lists hundreds of leaves and
+     * one task per candidate loses against the tree search (13.9 vs 12.9 ms) */
+    bool anchored = (env_anchor > 0 || (env_anchor < 0 && h.n_leaves <= 1200000)) && !count && h.has_mesh && h.n_leaves > 0 && segments > 0;
+    if (anchored) {
+        int rc = ensure_bins(s, 0, p->cam);
+        if (rc == RT_OK) rc = ensure_bins(s, 1, h.L);
+        if (rc != RT_OK) return rc;
+        anchored = s->bins[0].usable && s->bins[1].usable;
+    }
+    s->last_was_anchored = anchored;
+    /* no mirror, no refractive object: the kernels without the reflection / refraction code (smaller, less instruction fetch) */
+    bool diffuse_only = !(h.has_mesh && (h.mesh_mirror || h.mesh_n_in != h.mesh_n_out)) && s->opt.diffuse_kernels != 0;
+    for (int k = 0; k < h.n_spheres; k++) diffuse_only = diffuse_only && !h.spheres[k].mirror && h.spheres[k].n_in == h.spheres[k].n_out;
+    /* round 0 holds tree-searched queries only when a path can go on inside wf_generate: past a mirror or refractive
+     * sphere, or along the indirect bounce of a pixel shaded on the spot */
+    bool trav_round0 = stochastic && p->indirect;
+    for (int k = 0; k < h.n_spheres; k++) trav_round0 = trav_round0 || h.spheres[k].mirror || h.spheres[k].n_in != h.spheres[k].n_out;
+    trav_round0 = trav_round0 && segments >= 2;
+    /* node pool of wf_traverse: 32 lanes x (levels of the packed tree + roots of two batches + slack) */
+    int npool_cap = wide ? std::min(96 * (h.wide_depth + 2), 352) : std::min(32 * (h.max_depth + 4), 256);
+    if (s->opt.npool_cap > 0) npool_cap = std::max(64, std::min(s->opt.npool_cap, npool_cap)) & ~31; /* test hook: a small pool forces the spill path */
+    const size_t warp_bytes = (sizeof(rtk::WfWarpSmem) + (size_t)npool_cap * sizeof(int) + 15) & ~(size_t)15;
+    const size_t trav_smem = warp_bytes * (WF_THREADS / 32);
+    if (trav_smem > 200 * 1024) return rtb::fail(RT_ERR_UNSUPPORTED, "rt_render: BVH depth %d needs %zu B of shared memory per block", h.max_depth, trav_smem);
+    if (s->trav_blocks_per_sm == 0 || s->trav_smem != trav_smem || s->trav_wide != wide) {
+        s->trav_wide = wide;
+        int nb = 0;
+        CUDA_TRY(cudaFuncSetAttribute(rtk::wf_traverse<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trav_smem));
+        CUDA_TRY(cudaFuncSetAttribute(rtk::wf_traverse<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trav_smem));
+        CUDA_TRY(cudaFuncSetAttribute(rtk::wf_traverse<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trav_smem));
+        CUDA_TRY(cudaFuncSetAttribute(rtk::wf_traverse<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trav_smem));
+        CUDA_TRY(cudaFuncSetAttribute(rtk::wf_traverse<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trav_smem));
+        CUDA_TRY(cudaFuncSetAttribute(rtk::wf_traverse<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trav_smem));
+        CUDA_TRY(cudaFuncSetAttribute(rtk::wf_traverse<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trav_smem));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wide ? rtk::wf_traverse<false, false, true> : rtk::wf_traverse<false, false, false>, WF_THREADS, trav_smem));
+        cudaDeviceProp prop;
+        CUDA_TRY(cudaGetDeviceProperties(&prop, s->device));
+        s->trav_blocks_per_sm = std::max(nb, 1);
+        s->trav_smem = trav_smem;
+        s->sm_count = prop.multiProcessorCount;
+        if (!s->wf_counters) {
+            CUDA_TRY(cudaMalloc(&s->wf_counters, RT_MAX_STRIPS * sizeof(rtk::WfCounters)));
+            CUDA_TRY(cudaMallocHost(&s->h_wf_counters, RT_MAX_STRIPS * sizeof(rtk::WfCounters)));
+            CUDA_TRY(cudaEventCreateWithFlags(&s->fork_ev, cudaEventDisableTiming));
+            for (int k = 0; k < RT_MAX_STRIPS; k++) {
+                CUDA_TRY(cudaStreamCreateWithFlags(&s->strip_stream[k], cudaStreamNonBlocking));
+                CUDA_TRY(cudaEventCreateWithFlags(&s->strip_done[k], cudaEventDisableTiming));
+                CUDA_TRY(cudaStreamCreateWithFlags(&s->side_stream[k], cudaStreamNonBlocking));
+                CUDA_TRY(cudaEventCreateWithFlags(&s->side_fork[k], cudaEventDisableTiming));
+                CUDA_TRY(cudaEventCreateWithFlags(&s->side_join[k], cudaEventDisableTiming));
+            }
+        }
+    }
+    if (s->wf_capacity < npx) {
+        if (s->wf_queue) cudaFree(s->wf_queue);
+        s->wf_queue = nullptr;
+        s->wf_capacity = 0;
+        CUDA_TRY(cudaMalloc(&s->wf_queue, 3 * npx * sizeof(rtk::QEntry)));
+        s->wf_capacity = npx;
+    }
+    if (anchored) {
+        const size_t need = (size_t)s->task_factor * npx + task_slack * RT_MAX_STRIPS;
+        if (s->wf_tasks_cap < need) {
+            CUDA_TRY(cudaStreamSynchronize(s->stream));
+            if (s->wf_tasks) cudaFree(s->wf_tasks);
+            s->wf_tasks = nullptr;
+            s->wf_tasks_cap = 0;
+            CUDA_TRY(cudaMalloc(&s->wf_tasks, need * sizeof(int2)));
+            s->wf_tasks_cap = need;
+        }
+    }
+    const bool dbg_times = s->opt.debug_times != 0;
+    const bool dbg_warps = count && s->opt.debug_warps[0];
+    /* Strips: the frame is cut into bands of rows, each rendered by its own generate / traverse / shade chain
+     * on its own stream. The end of a persistent traversal launch is a latency-bound tail (a few warps
+     * finishing their expensive rays on an otherwise idle GPU, profiles/r01_notes.md); with strips the tail of
+     * one band is covered by the bulk of the next, and only the last launch's tail is exposed. */
+    const bool strips_fixed = s->opt.strips > 0;
+    int n_strips = strips_fixed ? std::min(s->opt.strips, RT_MAX_STRIPS) : 2;
+    {   /* host outputs: more bands, so that only the last band's copy-back is not covered by rendering */
+        bool any_copy = false;
+        for (int k = 0; k < 5; k++) any_copy = any_copy || copy_back[k];
+        if (any_copy && !strips_fixed) n_strips = std::min(RT_MAX_STRIPS, 4);
+    }
+    if (rows < 64 * n_strips) n_strips = std::max(1, rows / 64);
+    /* a small shard (one rank's rows of a frame split over 8 GPUs) is bound by launch latencies: one band
+     * (measured: 4K depth-4 frame, 1/8 of the rows: 0.33 ms against 0.37 ms with two) */
+    if (!strips_fixed && npx < 1500000 && !(flags & RT_RENDER_COUNT_WORK)) {
+        bool any_copy = false;
+        for (int k = 0; k < 5; k++) any_copy = any_copy || copy_back[k];
+        if (!any_copy) n_strips = 1;
+    }
+    if (dbg_times || dbg_warps) n_strips = 1;
+    const unsigned pers_grid = (unsigned)(s->sm_count * s->trav_blocks_per_sm);
+    const int spill_cap = WF_SLOTS * std::max(h.max_depth + 2, (RT_WIDE - 1) * h.wide_depth + 2); /* per traversal warp: every ray slot holding a full path of pending siblings */
+    {
+        const size_t ints = (size_t)spill_cap * pers_grid * (WF_THREADS / 32) * n_strips;
+        if (s->wf_spill_ints < ints) {
+            CUDA_TRY(cudaStreamSynchronize(s->stream));
+            if (s->wf_spill) cudaFree(s->wf_spill);
+            s->wf_spill = nullptr;
+            s->wf_spill_ints = 0;
+            CUDA_TRY(cudaMalloc(&s->wf_spill, ints * sizeof(int)));
+            s->wf_spill_ints = ints;
+        }
+    }
+    int* dbg_ptr = nullptr;
+    if (dbg_warps) {
+        const size_t ints = (size_t)(segments + 1) * pers_grid * (WF_THREADS / 32) * 16;
+        if (s->dbg_warps_ints < ints) {
+            if (s->dbg_warps) cudaFree(s->dbg_warps);
+            CUDA_TRY(cudaMalloc(&s->dbg_warps, ints * sizeof(int)));
+            s->dbg_warps_ints = ints;
+        }
+        CUDA_TRY(cudaMemsetAsync(s->dbg_warps, 0, ints * sizeof(int), s->stream));
+        dbg_ptr = s->dbg_warps;
+    }
+    CUDA_TRY(cudaMemsetAsync(s->wf_counters, 0, RT_MAX_STRIPS * sizeof(rtk::WfCounters), s->stream));
+    /* stochastic mode: per compact pixel 32 B of stream state, 16 B of colour sum, 32 B per path segment of records */
+    const size_t st_rng_off = 0, st_total_off = npx * 32, st_rec_off = st_total_off + npx * 16;
+    if (stochastic) {
+        const size_t need = st_rec_off + npx * 32 * (size_t)std::max(segments, 1);
+        if (s->st_buf_bytes < need) {
+            CUDA_TRY(cudaStreamSynchronize(s->stream));
+            if (s->st_buf) cudaFree(s->st_buf);
+            s->st_buf = nullptr;
+            s->st_buf_bytes = 0;
+            CUDA_TRY(cudaMalloc(&s->st_buf, need));
+            s->st_buf_bytes = need;
+        }
+    }
+    }
+    P.p = *p;
+    P.flags = flags;
+    P.rows = rows;
+    P.npx = npx;
+    for (int k = 0; k < 5; k++) {
+        P.user[k] = user[k];
+        P.dev[k] = dev[k];
+        P.copy_back[k] = copy_back[k];
+        P.bytes[k] = bytes[k];
+    }
+    P.a = a;
+    P.variant = variant;
+    P.grid = grid;
+    P.stochastic = stochastic;
+    P.count = count;
+    P.wide = wide;
+    P.anchored = anchored;
+    P.diffuse_only = diffuse_only;
+    P.trav_round0 = trav_round0;
+    P.dbg_times = dbg_times;
+    P.segments = segments;
+    P.npool_cap = npool_cap;
+    P.n_strips = n_strips;
+    P.spill_cap = spill_cap;
+    P.trav_smem = trav_smem;
+    P.pers_grid = pers_grid;
+    P.dbg_ptr = dbg_ptr;
+    P.st_rng_off = st_rng_off;
+    P.st_total_off = st_total_off;
+    P.st_rec_off = st_rec_off;
+    P.task_slack = task_slack;
+    return RT_OK;
+}
+
+/* ---- rt_render, second half: the launches of one frame, nothing else (no allocation, no synchronisation, no host read-back):
+ * the sequence is the same for every frame with the same plan, so it can be recorded once into a CUDA graph and replayed. */
+int enqueue_frame(rt_scene* s, const FramePlan& P, int& launches, bool& strip_copied) {
+    const rt_params* p = &P.p;
+    const SceneHeader& h = s->header;
+    const rtk::RenderArgs& a = P.a;
+    const bool stochastic = P.stochastic, count = P.count, wide = P.wide, anchored = P.anchored, diffuse_only = P.diffuse_only, trav_round0 = P.trav_round0,
+               dbg_times = P.dbg_times;
+    const int segments = P.segments, npool_cap = P.npool_cap, n_strips = P.n_strips, spill_cap = P.spill_cap, rows = P.rows, variant = P.variant;
+    const size_t trav_smem = P.trav_smem, st_rng_off = P.st_rng_off, st_total_off = P.st_total_off, st_rec_off = P.st_rec_off, task_slack = P.task_slack;
+    const unsigned pers_grid = P.pers_grid, grid = P.grid;
+    int* const dbg_ptr = P.dbg_ptr;
+    void* const* user = P.user;
+    void* const* dev = P.dev;
+    const bool* copy_back = P.copy_back;
+    if (variant == 2) {
+        if (P.dbg_ints) CUDA_TRY(cudaMemsetAsync(s->dbg_warps, 0, P.dbg_ints * sizeof(int), s->stream));
+        /* queue cursors and work statistics restart with every frame; the overflow flags live elsewhere (rt_scene::sticky) */
+        CUDA_TRY(cudaMemsetAsync(s->wf_counters, 0, RT_MAX_STRIPS * sizeof(rtk::WfCounters), s->stream));
+    if (n_strips > 1) CUDA_TRY(cudaEventRecord(s->fork_ev, s->stream));
+    cudaEvent_t dev_ev[40];
+    int n_ev = 0;
+    auto mark = [&]() {
+        if (dbg_times && n_ev < 40) {
+            cudaEventCreate(&dev_ev[n_ev]);
+            cudaEventRecord(dev_ev[n_ev++], s->stream);
+        }
+    };
+    mark();
+    int row0 = 0;
+    for (int st = 0; st < n_strips; st++) {
+        /* band boundaries on multiples of 8 rows (generate tiles are 8x4) */
+        int row1 = (st == n_strips - 1) ? rows : (int)(((long long)rows * (st + 1) / n_strips) & ~7ll);
+        if (row1 <= row0) continue;
+        const int srows = row1 - row0;
+        const size_t spx = (size_t)srows * p->W, px0 = (size_t)row0 * p->W;
+        cudaStream_t stream = n_strips > 1 ? s->strip_stream[st] : s->stream;
+        if (n_strips > 1) CUDA_TRY(cudaStreamWaitEvent(stream, s->fork_ev, 0));
+        rtk::WfArgs g;
+        g.a = a;
+        g.a.rows = srows;
+        g.a.row_begin = a.row_begin + row0 * a.row_step;
+        g.a.rgb = a.rgb ? a.rgb + px0 * 3 : nullptr;
+        g.a.hit_obj = a.hit_obj ? a.hit_obj + px0 : nullptr;
+        g.a.hit_tri = a.hit_tri ? a.hit_tri + px0 : nullptr;
+        g.a.hit_t = a.hit_t ? a.hit_t + px0 : nullptr;
+        g.a.shadow = a.shadow ? a.shadow + px0 : nullptr;
+        g.qA[0] = s->wf_queue + px0;
+        g.qA[1] = s->wf_queue + s->wf_capacity + px0;
+        g.qS = s->wf_queue + 2 * s->wf_capacity + px0;
+        g.c = s->wf_counters + st;
+        g.round = 0;
+        g.spill = s->wf_spill + (size_t)st * spill_cap * pers_grid * (WF_THREADS / 32);
+        g.spill_cap = spill_cap;
+        {
+            g.run_shift = s->opt.run_shift;
+            g.gss_factor = s->opt.gss;
+        }
+        g.dbg_warps = dbg_ptr;
+        g.anchored = anchored ? 1 : 0;
+        g.bins[0] = bins_view(s->bins[0]);
+        g.bins[1] = bins_view(s->bins[1]);
+        g.tasks = anchored ? s->wf_tasks + (size_t)s->task_factor * px0 + task_slack * st : nullptr;
+        g.qcap = (int)spx;
+        for (int k = 0; k < RT_MAX_SPHERES; k++) {
+            const DevSphere& sp = h.spheres[k];
+            /* the operations of Sphere::intersect / sphere_t, in their order, in float (no contraction on the host) */
+            volatile float ocx = a.camx - sp.cx, ocy = a.camy - sp.cy, ocz = a.camz - sp.cz;
+            volatile float xx = ocx * ocx, yy = ocy * ocy, zz = ocz * ocz;
+            volatile float n2 = xx + yy;
+            n2 = n2 + zz;
+            volatile float cc = n2 - sp.RR;
+            g.cam_sph[k] = k < h.n_spheres ? make_float4(ocx, ocy, ocz, cc) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        g.task_cap = anchored ? (int)std::min<size_t>((size_t)s->task_factor * spx + task_slack, (size_t)0x7fffffff) : 0;
+        if (anchored && s->leaves_blocks_per_sm == 0) { /* one resident wave of wf_leaves: every block gets the same share of the tasks */
+            int nb = 0;
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rtk::wf_leaves<false>, WF_THREADS, 0));
+            s->leaves_blocks_per_sm = std::max(nb, 1);
+        }
+        const int env_lb = s->opt.leaves_blocks;
+        const unsigned leaves_grid = (unsigned)(s->sm_count * (env_lb > 0 ? env_lb : std::max(s->leaves_blocks_per_sm, 1)));
+        const dim3 gen_grid((unsigned)(((p->W + 7) / 8 + (WF_THREADS / 32) - 1) / (WF_THREADS / 32)), (unsigned)((srows + 3) / 4));
+        const unsigned shade_grid = (unsigned)std::min<size_t>((spx + WF_THREADS - 1) / WF_THREADS, (size_t)s->sm_count * 16);
+        g.stoch = stochastic ? 1 : 0;
+        g.sample = 0;
+        g.last_sample = 1;
+        g.indirect = p->indirect;
+        g.libm = s->opt.transcendentals;
+        g.sticky = s->sticky;
+        g.aa_sigma = p->aa_sigma;
+        g.npx = (int)spx;
+        g.rng_table = reinterpret_cast<const uint4*>(s->rng_states);
+        g.rng = stochastic ? reinterpret_cast<uint4*>(s->st_buf + st_rng_off) + px0 * 2 : nullptr;
+        g.total = stochastic ? reinterpret_cast<float4*>(s->st_buf + st_total_off) + px0 : nullptr;
+        g.rec = stochastic ? reinterpret_cast<float4*>(s->st_buf + st_rec_off) + px0 * 2 * (size_t)std::max(segments, 1) : nullptr;
+        /* deterministic mode: one pass (identical samples are traced once). Stochastic mode: one pass per sample,
+         * in order, because the samples of a pixel share one random stream. */
+        const int n_pass = stochastic ? p->num_rays : 1;
+        for (int pass = 0; pass < n_pass; pass++) {
+            g.sample = pass;
+            g.last_sample = pass == n_pass - 1;
+            g.round = 0;
+            if (pass > 0) /* the queue counters restart with every pass; the work statistics keep adding up */
+                CUDA_TRY(cudaMemsetAsync(reinterpret_cast<unsigned char*>(s->wf_counters + st) + offsetof(rtk::WfCounters, nA), 0,
+                                         sizeof(rtk::WfCounters) - offsetof(rtk::WfCounters, nA), stream));
+            if (stochastic) {
+                if (count) rtk::wf_generate<true, true><<<gen_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
+                else if (diffuse_only) rtk::wf_generate<false, true, true><<<gen_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
+                else rtk::wf_generate<false, true><<<gen_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
+            } else {
+                if (count) rtk::wf_generate<true, false><<<gen_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
+                else if (diffuse_only && anchored) rtk::wf_generate<false, false, true, true><<<gen_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
+                else if (diffuse_only) rtk::wf_generate<false, false, true><<<gen_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
+                else rtk::wf_generate<false, false><<<gen_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
+            }
+            launches++;
+            mark();
+            /* without a mesh no query is ever posted: wf_generate runs every path to its end */
+            for (int r = 0; r <= segments && segments > 0 && h.has_mesh; r++) {
+                g.round = r;
+                if (anchored) {
+                    /* closest-hit queries of a round >= 1 start somewhere in the scene: tree search; every shadow
+                     * query and the camera rays of round 0 are (ray, leaf) tasks */
+                    const bool trav_now = r < segments && (r >= 1 || trav_round0);
+                    /* the two kernels of the round touch disjoint entries: the tree search goes to the band's side stream
+                     * and runs beside wf_leaves (its latency-bound tail is covered by the LSU-bound task kernel) */
+                    const bool env_side = s->opt.side_stream != 0;
+                    const bool side = trav_now && env_side && !dbg_times;
+                    cudaStream_t tstream = side ? s->side_stream[st] : stream;
+                    if (side) {
+                        CUDA_TRY(cudaEventRecord(s->side_fork[st], stream));
+                        CUDA_TRY(cudaStreamWaitEvent(tstream, s->side_fork[st], 0));
+                    }
+                    if (trav_now) {
+                        if (stochastic) {
+                            if (wide) rtk::wf_traverse<false, true, true><<<pers_grid, WF_THREADS, trav_smem, tstream>>>(s->header, s->blob, g, npool_cap);
+                            else rtk::wf_traverse<false, true, false><<<pers_grid, WF_THREADS, trav_smem, tstream>>>(s->header, s->blob, g, npool_cap);
+                        } else {
+                            if (wide) rtk::wf_traverse<false, false, true><<<pers_grid, WF_THREADS, trav_smem, tstream>>>(s->header, s->blob, g, npool_cap);
+                            else rtk::wf_traverse<false, false, false><<<pers_grid, WF_THREADS, trav_smem, tstream>>>(s->header, s->blob, g, npool_cap);
+                        }
+                        launches++;
+                        mark();
+                    }
+                    if (stochastic) rtk::wf_leaves<true><<<leaves_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
+                    else rtk::wf_leaves<false><<<leaves_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
+                    if (side) { /* join: wf_shade needs both */
+                        CUDA_TRY(cudaEventRecord(s->side_join[st], tstream));
+                        CUDA_TRY(cudaStreamWaitEvent(stream, s->side_join[st], 0));
+                    }
+                } else if (stochastic) {
+                    if (count) rtk::wf_traverse<true, true, false><<<pers_grid, WF_THREADS, trav_smem, stream>>>(s->header, s->blob, g, npool_cap);
+                    else if (wide) rtk::wf_traverse<false, true, true><<<pers_grid, WF_THREADS, trav_smem, stream>>>(s->header, s->blob, g, npool_cap);
+                    else rtk::wf_traverse<false, true, false><<<pers_grid, WF_THREADS, trav_smem, stream>>>(s->header, s->blob, g, npool_cap);
+                } else {
+                    if (count && wide) rtk::wf_traverse<true, false, true><<<pers_grid, WF_THREADS, trav_smem, stream>>>(s->header, s->blob, g, npool_cap);
+                    else if (count) rtk::wf_traverse<true, false, false><<<pers_grid, WF_THREADS, trav_smem, stream>>>(s->header, s->blob, g, npool_cap);
+                    else if (wide) rtk::wf_traverse<false, false, true><<<pers_grid, WF_THREADS, trav_smem, stream>>>(s->header, s->blob, g, npool_cap);
+                    else rtk::wf_traverse<false, false, false><<<pers_grid, WF_THREADS, trav_smem, stream>>>(s->header, s->blob, g, npool_cap);
+                }
+                launches++;
+                mark();
+                if (r == segments) break;
+                if (stochastic) {
+                    if (count) rtk::wf_shade<true, true><<<shade_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
+                    else if (diffuse_only) rtk::wf_shade<false, true, true><<<shade_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
+                    else rtk::wf_shade<false, true><<<shade_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
+                } else {
+                    if (count) rtk::wf_shade<true, false><<<shade_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
+                    else if (diffuse_only && anchored) rtk::wf_shade<false, false, true, true><<<shade_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
+                    else if (diffuse_only) rtk::wf_shade<false, false, true><<<shade_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
+                    else rtk::wf_shade<false, false><<<shade_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
+                }
+                launches++;
+                mark();
+            }
+            if (stochastic) {
+                rtk::wf_fold<<<(unsigned)((spx + 255) / 256), 256, 0, stream>>>(g);
+                launches++;
+                mark();
+            }
+        }
+        if (n_strips > 1) {
+            /* host outputs: this band's copy-back rides on the band's stream and overlaps the other bands' kernels
+             * (kernel_ms then spans the copies of all bands but the last as well) */
+            const size_t elem[5] = {3, 4, 4, 4, 1};
+            for (int k = 0; k < 5; k++)
+                if (copy_back[k]) {
+                    CUDA_TRY(cudaMemcpyAsync((unsigned char*)user[k] + px0 * elem[k], (unsigned char*)dev[k] + px0 * elem[k], spx * elem[k], cudaMemcpyDeviceToHost, stream));
+                    strip_copied = true;
+                }
+            CUDA_TRY(cudaEventRecord(s->strip_done[st], stream));
+            CUDA_TRY(cudaStreamWaitEvent(s->stream, s->strip_done[st], 0));
+        }
+        row0 = row1;
+    }
+    if (dbg_times) {
+        cudaStreamSynchronize(s->stream);
+        fprintf(stderr, "[times us]");
+        for (int k = 1; k < n_ev; k++) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, dev_ev[k - 1], dev_ev[k]);
+            fprintf(stderr, " %.1f", ms * 1e3f);
+        }
+        fprintf(stderr, "\n");
+        for (int k = 0; k < n_ev; k++) cudaEventDestroy(dev_ev[k]);
+    }
+        launches--; /* the common launches++ below counts one */
+    } else if (variant == 3) {
+        CUDA_TRY(cudaMemsetAsync(s->counters, 0, RT_NCOUNTERS * sizeof(unsigned long long), s->stream));
+        if (count) rtk::render_stoch<true><<<grid, 128, 0, s->stream>>>(s->header, s->blob, a, s->rng_states, p->aa_sigma, p->indirect, s->opt.transcendentals);
+        else rtk::render_stoch<false><<<grid, 128, 0, s->stream>>>(s->header, s->blob, a, s->rng_states, p->aa_sigma, p->indirect, s->opt.transcendentals);
+    } else if (variant == 0) {
+        CUDA_TRY(cudaMemsetAsync(s->counters, 0, RT_NCOUNTERS * sizeof(unsigned long long), s->stream));
+        if (count) rtk::render_mega<true, false><<<grid, 128, 0, s->stream>>>(s->header, s->blob, a);
+        else rtk::render_mega<false, false><<<grid, 128, 0, s->stream>>>(s->header, s->blob, a);
+    } else {
+        CUDA_TRY(cudaMemsetAsync(s->counters, 0, RT_NCOUNTERS * sizeof(unsigned long long), s->stream));
+        if (count) rtk::render_mega<true, true><<<grid, 128, 0, s->stream>>>(s->header, s->blob, a);
+        else rtk::render_mega<false, true><<<grid, 128, 0, s->stream>>>(s->header, s->blob, a);
+    }
+    launches++;
+    CUDA_TRY(cudaGetLastError());
+    for (int k = 0; k < 5; k++) /* host outputs of a frame rendered as one band (or by the one-kernel variants) */
+        if (copy_back[k] && !strip_copied) CUDA_TRY(cudaMemcpyAsync(user[k], dev[k], P.bytes[k], cudaMemcpyDeviceToHost, s->stream));
+    return RT_OK;
+}
+
+bool is_pinned_host(const void* p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeHost;
+}
+
+/* Everything a recorded frame depends on, as bytes: the plan (parameters, output pointers, kernel choices), the scene header the
+ * kernels take by value, the bins, the buffers and the options. Equal keys <=> the same launches with the same arguments. */
+void frame_key(rt_scene* s, const FramePlan& P, std::vector<unsigned char>& key) {
+    key.clear();
+    auto put = [&](const void* p, size_t n) { key.insert(key.end(), (const unsigned char*)p, (const unsigned char*)p + n); };
+    put(&P, sizeof P);
+    put(&s->header, sizeof s->header);
+    for (int k = 0; k < 2; k++) {
+        rtk::BinsView v;
+        memset(&v, 0, sizeof v);
+        if (P.anchored) v = bins_view(s->bins[k]);
+        put(&v, sizeof v);
+    }
+    const void* ptrs[] = {s->blob, s->wf_queue, s->wf_tasks, s->wf_counters, s->wf_spill, s->st_buf, s->rng_states, s->gamma_tab, s->sticky, s->stream};
+    put(ptrs, sizeof ptrs);
+    const size_t nums[] = {s->wf_capacity, s->wf_tasks_cap, (size_t)s->task_factor, (size_t)s->leaves_blocks_per_sm, (size_t)s->sm_count, (size_t)s->trav_blocks_per_sm};
+    put(nums, sizeof nums);
+    put(&s->opt, sizeof s->opt);
+}
+
+} // namespace
+
+extern "C" {
+
+/* The render call. plan_frame decides and sizes, enqueue_frame launches. A frame whose plan equals the previous call's is
+ * recorded into a CUDA graph the second time it is seen and replayed from then on (one graph launch instead of 8-30 kernel
+ * launches + stream events: what a caller that renders the same view again and again pays per frame); any change — parameters,
+ * output pointers, light, mesh, options — goes back to direct launches. Option "graph" = 0 turns the replay off. */
+int rt_render(rt_scene* s, const rt_params* p, uint32_t flags, uint8_t* rgb_out, int32_t* hit_obj, int32_t* hit_tri, float* hit_t,
+              uint8_t* shadow, rt_stats* stats) {
+    if (!s || !p) return rtb::fail(RT_ERR_INVALID, "rt_render: NULL scene or params");
+    DeviceGuard g(s->device);
+    if (!g.ok) return rtb::fail(RT_ERR_CUDA, "rt_render: cudaSetDevice failed");
+    void* user[5] = {rgb_out, hit_obj, hit_tri, hit_t, shadow};
+    FramePlan P;
+    memset(&P, 0, sizeof P);
+    int rc = plan_frame(s, p, flags, user, P);
+    if (rc != RT_OK) return rc;
+    int launches = P.prelaunches;
+    bool strip_copied = false;
+
+    bool graph_ok = s->opt.graph != 0 && P.variant == 2 && !P.count && !P.dbg_times;
+    for (int k = 0; k < 5 && graph_ok; k++)
+        if (P.copy_back[k] && !is_pinned_host(P.user[k])) graph_ok = false; /* pageable host memory: the copy is not a pure stream operation */
+    std::vector<unsigned char> key;
+    if (graph_ok) frame_key(s, P, key);
+
+    CUDA_TRY(cudaEventRecord(s->ev0, s->stream)); /* kernel_ms covers everything the frame enqueues, counter resets and copies to host outputs included */
+    if (graph_ok && s->graph_exec && key == s->graph_key) {
+        CUDA_TRY(cudaGraphLaunch(s->graph_exec, s->stream));
+        launches += s->graph_launches;
+    } else if (graph_ok && key == s->last_key) {
+        /* second identical frame in a row: record it */
+        CUDA_TRY(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
+        int n = 0;
+        rc = enqueue_frame(s, P, n, strip_copied);
+        cudaGraph_t graph = nullptr;
+        const cudaError_t e = cudaStreamEndCapture(s->stream, &graph);
+        if (rc != RT_OK || e != cudaSuccess) {
+            if (graph) cudaGraphDestroy(graph);
+            cudaGetLastError();
+            s->last_key.clear();
+            return rc != RT_OK ? rc : rtb::fail(RT_ERR_CUDA, "rt_render: cudaStreamEndCapture: %s", cudaGetErrorString(e));
+        }
+        if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
+        s->graph_exec = nullptr;
+        const cudaError_t e2 = cudaGraphInstantiate(&s->graph_exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e2 != cudaSuccess) {
+            s->graph_exec = nullptr;
+            s->last_key.clear();
+            return rtb::fail(RT_ERR_CUDA, "rt_render: cudaGraphInstantiate: %s", cudaGetErrorString(e2));
+        }
+        s->graph_key = key;
+        s->graph_launches = n;
+        CUDA_TRY(cudaEventRecord(s->ev0, s->stream)); /* recording and instantiating are one-off costs, not frame time */
+        CUDA_TRY(cudaGraphLaunch(s->graph_exec, s->stream));
+        launches += n;
+    } else {
+        rc = enqueue_frame(s, P, launches, strip_copied);
+        if (rc != RT_OK) return rc;
+    }
+    s->last_key.swap(key);
     CUDA_TRY(cudaEventRecord(s->ev1, s->stream));
-    for (int k = 0; k < 5; k++)
-        if (copy_back[k] && !strip_copied) CUDA_TRY(cudaMemcpyAsync(user[k], dev[k], bytes[k], cudaMemcpyDeviceToHost, s->stream));
     s->pending = true; /* the counters are read back by rt_scene_sync, not per enqueued frame */
     s->pending_launches = launches;
     if (flags & RT_RENDER_NO_SYNC) {
         if (stats) memset(stats, 0, sizeof *stats);
         return RT_OK;
     }
-    const int rc = rt_scene_sync(s, stats);
+    rc = rt_scene_sync(s, stats);
     if (rc == RT_ERR_AGAIN && !(flags & RT_RENDER_RETRY_)) { /* task buffer overflow: repeat with the doubled buffer (a few times at most) */
         for (int attempt = 0; attempt < 6; attempt++) {
             const int rc2 = rt_render(s, p, flags | RT_RENDER_RETRY_, rgb_out, hit_obj, hit_tri, hit_t, shadow, stats);

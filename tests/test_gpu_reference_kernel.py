@@ -9,9 +9,9 @@ GPU box; /root/reference does not):
   ref_optimized_ids     sigma 0 + a dump of the first-segment object id / triangle index / t / shadow flag per pixel,
                         the quantities the kernel computes but never emits
 
-north_star's bar: hit ids bit-exact, 8-bit colour within 1 LSB on >= 99.9 % of the pixels. The library runs with option
-transcendentals = 1 (CUDA's logf / cosf / sinf, what optimized.cu itself calls) so that the jitter and the bounce
-directions are the reference build's bit for bit; the oracle (canonical double evaluation) is compared as well.
+north_star's bar: hit ids bit-exact, 8-bit colour within 1 LSB on >= 99.9 % of the pixels. The library's default
+(option transcendentals = 1: CUDA's logf / cosf / sinf, what optimized.cu itself calls) makes the jitter and the bounce
+directions the reference build's bit for bit; the oracle restates those functions for the CPU (its default canon too).
 """
 import os
 import subprocess
@@ -83,7 +83,6 @@ def test_library_matches_the_ieee_build_of_optimized_cu(scene, W, H, rays, bounc
     """`./optimized R B` as the reference's source says it (IEEE), frame against frame."""
     ref = run_ref("ieee", W, H, rays, bounce)["rgb"]
     scenes.upload(scene, scenes.cat_scene("optimized"))
-    scene.set_option("transcendentals", 1)
     got = scene.render(stoch(W, H, rays, bounce), want=("rgb",))["rgb"]
     r = lsb(got, ref)
     print("library vs IEEE optimized.cu %dx%d `%d %d`:" % (W, H, rays, bounce), r)
@@ -97,13 +96,13 @@ def test_oracle_matches_the_ieee_build_of_optimized_cu(rays, bounce):
     chaotic self-shadow speckle of the R = 940 walls amplifies) is printed beside it."""
     ref = run_ref("ieee", 512, 512, rays, bounce)["rgb"]
     p = stoch(512, 512, rays, bounce)
-    try:
-        pyoracle.set_transcendentals(1)
-        o = scenes.run_oracle(scenes.cat_scene("optimized"), p, want=("rgb",))["rgb"]
-    finally:
-        pyoracle.set_transcendentals(0)
+    o = scenes.run_oracle(scenes.cat_scene("optimized"), p, want=("rgb",))["rgb"]
     r = lsb(o, ref)
-    r0 = lsb(scenes.run_oracle(scenes.cat_scene("optimized"), p, want=("rgb",))["rgb"], ref)
+    try:
+        pyoracle.set_transcendentals(0)
+        r0 = lsb(scenes.run_oracle(scenes.cat_scene("optimized"), p, want=("rgb",))["rgb"], ref)
+    finally:
+        pyoracle.set_transcendentals(1)
     print("oracle (CUDA canon) vs IEEE optimized.cu 512x512 `%d %d`:" % (rays, bounce), r, " double canon:", r0)
     assert r["within1"] >= 0.999 and r["exact"] >= 0.9999, r
     assert r0["within1"] >= 0.99, r0
@@ -134,7 +133,6 @@ def test_sigma0_with_indirect_bounces_matches(scene):
     W, H = 640, 360
     ref = run_ref("sigma0", W, H, 2, 3)["rgb"]
     scenes.upload(scene, scenes.cat_scene("optimized"))
-    scene.set_option("transcendentals", 1)
     got = scene.render(stoch(W, H, 2, 3, sigma=0.0), want=("rgb",))["rgb"]
     r = lsb(got, ref)
     print("sigma 0, `2 3` vs optimized.cu:", r)
