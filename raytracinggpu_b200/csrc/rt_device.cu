@@ -1303,13 +1303,16 @@ int plan_frame(rt_scene* s, const rt_params* p, uint32_t flags, void* const user
             P.prelaunches++; /* the one-off table build is not part of the frame time */
         }
     }
-    bool wide = false, anchored = false, diffuse_only = false, trav_round0 = false, dbg_times = false;
-    int npool_cap = 0, n_strips = 1, spill_cap = 0;
-    size_t trav_smem = 0, st_rng_off = 0, st_total_off = 0, st_rec_off = 0;
-    const size_t task_slack = 4096;
-    unsigned pers_grid = 0;
-    int* dbg_ptr = nullptr;
+    P.wide = P.anchored = P.diffuse_only = P.trav_round0 = P.dbg_times = false;
+    P.npool_cap = P.spill_cap = 0;
+    P.n_strips = 1;
+    P.trav_smem = P.st_rng_off = P.st_total_off = P.st_rec_off = 0;
+    P.task_slack = 4096;
+    P.pers_grid = 0;
+    P.dbg_ptr = nullptr;
+    P.dbg_ints = 0;
     if (variant == 2) {
+        const size_t task_slack = P.task_slack;
     /* the wide index (rt_layout.h) is the production search structure; the instrumented build counts the reference's
      * own node visits and therefore walks the two-child records, as does RT_WIDE=0 (A/B timing, cross-check) */
     /* RT_WIDE: 1 on, 0 off; unset: on for the incoherent bounce rays of the stochastic mode (measured, 6 blocks per SM:
@@ -1438,10 +1441,9 @@ int plan_frame(rt_scene* s, const rt_params* p, uint32_t flags, void* const user
             CUDA_TRY(cudaMalloc(&s->dbg_warps, ints * sizeof(int)));
             s->dbg_warps_ints = ints;
         }
-        CUDA_TRY(cudaMemsetAsync(s->dbg_warps, 0, ints * sizeof(int), s->stream));
+        P.dbg_ints = ints; /* cleared at the head of the frame (enqueue_frame) */
         dbg_ptr = s->dbg_warps;
     }
-    CUDA_TRY(cudaMemsetAsync(s->wf_counters, 0, RT_MAX_STRIPS * sizeof(rtk::WfCounters), s->stream));
     /* stochastic mode: per compact pixel 32 B of stream state, 16 B of colour sum, 32 B per path segment of records */
     const size_t st_rng_off = 0, st_total_off = npx * 32, st_rec_off = st_total_off + npx * 16;
     if (stochastic) {
@@ -1455,6 +1457,20 @@ int plan_frame(rt_scene* s, const rt_params* p, uint32_t flags, void* const user
             s->st_buf_bytes = need;
         }
     }
+        P.wide = wide;
+        P.anchored = anchored;
+        P.diffuse_only = diffuse_only;
+        P.trav_round0 = trav_round0;
+        P.dbg_times = dbg_times;
+        P.npool_cap = npool_cap;
+        P.n_strips = n_strips;
+        P.spill_cap = spill_cap;
+        P.trav_smem = trav_smem;
+        P.pers_grid = pers_grid;
+        P.dbg_ptr = dbg_ptr;
+        P.st_rng_off = st_rng_off;
+        P.st_total_off = st_total_off;
+        P.st_rec_off = st_rec_off;
     }
     P.p = *p;
     P.flags = flags;
@@ -1471,22 +1487,7 @@ int plan_frame(rt_scene* s, const rt_params* p, uint32_t flags, void* const user
     P.grid = grid;
     P.stochastic = stochastic;
     P.count = count;
-    P.wide = wide;
-    P.anchored = anchored;
-    P.diffuse_only = diffuse_only;
-    P.trav_round0 = trav_round0;
-    P.dbg_times = dbg_times;
     P.segments = segments;
-    P.npool_cap = npool_cap;
-    P.n_strips = n_strips;
-    P.spill_cap = spill_cap;
-    P.trav_smem = trav_smem;
-    P.pers_grid = pers_grid;
-    P.dbg_ptr = dbg_ptr;
-    P.st_rng_off = st_rng_off;
-    P.st_total_off = st_total_off;
-    P.st_rec_off = st_rec_off;
-    P.task_slack = task_slack;
     return RT_OK;
 }
 
