@@ -86,6 +86,16 @@ typedef struct rt_params {
     int32_t row_step;        /* 1 for a contiguous band, nranks for row-interleave */
     int32_t row_count;       /* 0 means "all rows from row_begin with row_step" */
     int32_t reserved;        /* stochastic mode: RNG seed, 0 = the reference's 123456 (optimized.cu:745) */
+    /* ---- viewer-derived features (realtime_render.cu; the GLUT program itself is out of scope). All 0 = the launchers' behaviour. */
+    int32_t camera_mode;     /* 0: fixed camera of the launchers, u_center = (j - W/2 + 0.5, H/2 - i - 0.5, z) (optimized.cu:751)
+                                1: the viewer's camera basis, u_center = C + bz*z + bx*(j - W/2 + 0.5) + by*(H/2 - i - 0.5)
+                                   (realtime_render.cu:1113 — the camera position IS added to the direction there; replicated) */
+    float cam_bx[3], cam_by[3], cam_bz[3]; /* rt_camera_basis(yaw, pitch): Camera::rotate, realtime_render.cu:828-849 */
+    int32_t smooth_normals;  /* 1: a mesh hit is shaded with the interpolated vertex normals, N = normalize(alpha Na + beta Nb + gamma Nc)
+                                (get_smooth_normal, realtime_render.cu:221-245, called at :311); needs rt_scene_set_mesh_normals */
+    int32_t accumulate;      /* progressive accumulation (realtime_render.cu:1136-1140): k >= 1 is the frame number — the frame's linear
+                                colour is added to the scene's accumulation buffer (cleared first when k == 1) and the 8-bit frame
+                                is quantise(buffer / k); 0: off. Wavefront pipeline only. */
 } rt_params;
 
 typedef struct rt_stats {
@@ -122,6 +132,13 @@ int rt_mesh_read_obj(rt_mesh* m, const char* path);
 int rt_mesh_set_triangles(rt_mesh* m, const float* vertices, int32_t nv, const int32_t* vtx_indices, int32_t nt);
 /* rescale (optimized.cu:297-301): v = v*scale + offset, unfused float. */
 int rt_mesh_rescale(rt_mesh* m, float scale, const float offset[3]);
+/* Vertex normals (the viewer's loader keeps them, realtime_render.cu:489-493, 538-545; optimized.cu's drops them). keep != 0 before
+ * rt_mesh_read_obj: the `vn` lines become the normals array and the faces' normal indices words 6-8 (ni, nj, nk) of the triangle
+ * records. rt_mesh_set_normals attaches normals + nt*3 indices to a mesh given by arrays. Both before the BVH build. */
+int rt_mesh_keep_normals(rt_mesh* m, int keep);
+int rt_mesh_set_normals(rt_mesh* m, const float* normals, int32_t n_normals, const int32_t* normal_indices /* nt*3 */);
+int rt_mesh_normal_count(const rt_mesh* m, int32_t* n_normals);
+const float* rt_mesh_normals(const rt_mesh* m);            /* n_normals*3, NULL when none */
 /* Merge `copies` transformed instances of the current mesh into one mesh (config 5 of BASELINE.json:
  * the reference has no instancing, so instances are baked). Instance c is v*scale[c] + offset[c]. */
 int rt_mesh_instance(rt_mesh* m, int32_t copies, const float* scales, const float* offsets /* copies*3 */);
@@ -147,8 +164,12 @@ float rt_camera_z(int32_t W, float alpha);
  * reference's own GPU program (IEEE build). rt_params_profile fills the host value; a caller reproducing optimized.cu's
  * output overrides rt_params::z with this one (the CLI does, for --profile optimized). */
 int rt_camera_z_device(int device, int32_t W, float alpha, float* z);
+/* Camera::rotate (realtime_render.cu:828-849): the viewer's camera basis for a yaw and a pitch, evaluated on the host in float. */
+void rt_camera_basis(float yaw, float pitch, float bx[3], float by[3], float bz[3]);
 /* Fill `p` with the knobs of one reference program: "cpu" (cpu_launcher.cpp), "optimized" (optimized.cu),
- * "array_bvh" (array_bvh.cu); deterministic mode (aa_sigma=0, indirect=0); camera (0,0,55), alpha=pi/3. */
+ * "array_bvh" (array_bvh.cu), "realtime" (realtime_render.cu: viewer camera with pitch 0.3 and a 90 degree field of view,
+ * smooth normals, eps 1e-3, walls 0-5 + mesh 6 with the R = 940 floor; its light (0, 15, 40) is the caller's to set);
+ * deterministic mode (aa_sigma=0, indirect=0); camera (0,0,55), alpha=pi/3. */
 int rt_params_profile(rt_params* p, const char* profile, int32_t W, int32_t H, int32_t num_rays, int32_t num_bounce);
 /* The six wall spheres with the ids of the given profile and the id the mesh takes
  * (cpu: walls 0-5, mesh 6, cpu_launcher.cpp:673-685; optimized: wall 0, mesh 1, walls 2-6, optimized.cu:684-726). */
@@ -200,6 +221,10 @@ int rt_scene_set_mesh(rt_scene* s, const float* vertices, int32_t nv,
                       const int32_t* tri_records, int32_t nt,
                       const float* arr_bvh, int32_t n_nodes,
                       const float albedo[3], int32_t mirror, float n_in, float n_out, int32_t id);
+/* Per-vertex normals for rt_params::smooth_normals (TriangleMesh::normals + TriangleIndices::ni,nj,nk, realtime_render.cu:239-241):
+ * call after rt_scene_set_mesh with the mesh's normals array (rt_mesh_normals); the normal indices are words 6-8 of the triangle
+ * records that call uploaded. Held beside the scene blob (not part of a broadcast: the viewer is single-GPU). n_normals == 0 removes them. */
+int rt_scene_set_mesh_normals(rt_scene* s, const float* normals, int32_t n_normals);
 /* Scene::L and Scene::intensity (optimized.cu:681-683). */
 int rt_scene_set_light(rt_scene* s, const float L[3], float intensity);
 /* Packed device scene as one contiguous blob, for a broadcast to other ranks (multi-GPU: the scene is built on

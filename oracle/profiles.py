@@ -25,6 +25,8 @@ PROFILES = {
     "cpu": dict(eps_surface=1e-3, eps_tri=1e-4, push_order=0, extra_segment=1, gamma_mode=0, mesh_id=6, rescale=None),
     "optimized": dict(eps_surface=1e-4, eps_tri=0.0, push_order=1, extra_segment=0, gamma_mode=1, mesh_id=1, rescale=(0.6, (0., -4., 0.))),
     "array_bvh": dict(eps_surface=1e-4, eps_tri=1e-4, push_order=0, extra_segment=0, gamma_mode=0, mesh_id=6, rescale=(0.6, (0., -10., 0.))),
+    # the GLUT viewer (realtime_render.cu:908,298,288-289,1021,809,311): viewer camera (pitch 0.3, 90 degree field of view), smooth normals
+    "realtime": dict(eps_surface=1e-3, eps_tri=1e-3, push_order=0, extra_segment=0, gamma_mode=1, mesh_id=6, rescale=(0.6, (0., -10., 0.))),
 }
 
 
@@ -66,6 +68,12 @@ def params(profile, W, H, num_rays=1, num_bounce=1):
     p.indirect = 0
     p.gamma_mode = k["gamma_mode"]
     p.row_begin, p.row_step, p.row_count = 0, 1, 0
+    if profile == "realtime":
+        p.z = pyoracle.lib().orc_camera_z(W, float(np.float32(math.pi / 2)))
+        p.camera_mode = 1
+        bx, by, bz = pyoracle.camera_basis(0.0, 0.3)
+        p.cam_bx[:], p.cam_by[:], p.cam_bz[:] = [float(x) for x in bx], [float(x) for x in by], [float(x) for x in bz]
+        p.smooth_normals = 1
     return p
 
 

@@ -84,6 +84,13 @@ def lib():
         L.orc_camera_z.restype = C.c_float
         L.orc_camera_z_device.argtypes = [C.c_int32, C.c_float]
         L.orc_camera_z_device.restype = C.c_float
+        L.orc_set_mesh_normals.argtypes = [C.c_void_p]
+        L.orc_set_mesh_normals.restype = None
+        L.orc_mesh_set_normals.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+        L.orc_camera_basis.argtypes = [C.c_float, C.c_float, C.c_void_p]
+        L.orc_camera_basis.restype = None
+        L.orc_accumulate.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]
+        L.orc_accumulate.restype = None
         L.orc_set_transcendentals.argtypes = [C.c_int32]
         L.orc_set_transcendentals.restype = None
         L.orc_cuda_libm.argtypes = [C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]
@@ -139,6 +146,13 @@ class Mesh:
         lib().orc_mesh_rescale(self._h, float(scale), _f3(offset))
         return self
 
+    def set_normals(self, normals, normal_indices):
+        """Per-vertex normals + (nt, 3) normal indices (words 6-8 of the records); before build_bvh."""
+        self.normals = np.ascontiguousarray(normals, dtype=np.float32).reshape(-1, 3)
+        idx = np.ascontiguousarray(normal_indices, dtype=np.int32).reshape(-1, 3)
+        lib().orc_mesh_set_normals(self._h, self.normals.ctypes.data, self.normals.shape[0], idx.ctypes.data)
+        return self
+
     def build_bvh(self):
         lib().orc_mesh_build_bvh(self._h)
         return self
@@ -169,10 +183,28 @@ class Mesh:
         return _np_from(lib().orc_mesh_arr_bvh(self._h), (nn, 10), np.float32)
 
 
-def render(spheres, mesh_arrays, mesh_mat, light, params, threads=0, want=("rgb", "hit_obj", "hit_tri", "hit_t", "shadow")):
+def camera_basis(yaw, pitch):
+    """Camera::rotate (realtime_render.cu:828-849): (bx, by, bz) as three float32 triples."""
+    out = np.zeros(9, np.float32)
+    lib().orc_camera_basis(float(yaw), float(pitch), out.ctypes.data)
+    return out[0:3].copy(), out[3:6].copy(), out[6:9].copy()
+
+
+def accumulate(acc, linear, k, gamma_mode):
+    """Progressive accumulation step (realtime_render.cu:1136-1140): acc (float32, in place) += linear; returns the 8-bit frame."""
+    rgb = np.zeros(linear.shape, np.uint8)
+    lin = np.ascontiguousarray(linear, dtype=np.float32)
+    lib().orc_accumulate(acc.ctypes.data, lin.ctypes.data, lin.size, int(k), int(gamma_mode), rgb.ctypes.data)
+    return rgb
+
+
+def render(spheres, mesh_arrays, mesh_mat, light, params, threads=0, want=("rgb", "hit_obj", "hit_tri", "hit_t", "shadow"), normals=None):
     """Run the oracle. spheres: list of rt_sphere. mesh_arrays: None or (vertices, tri_records, arr_bvh).
-    mesh_mat: dict(albedo, mirror, n_in, n_out, id). light: (L, intensity). Returns dict of numpy arrays + 'work'."""
+    mesh_mat: dict(albedo, mirror, n_in, n_out, id). light: (L, intensity). normals: (nn, 3) per-vertex normals for
+    params.smooth_normals. Returns dict of numpy arrays + 'work'."""
     L = lib()
+    nrm = np.ascontiguousarray(normals, dtype=np.float32) if normals is not None else None
+    L.orc_set_mesh_normals(nrm.ctypes.data if nrm is not None else None)
     p = params
     step = p.row_step if p.row_step > 0 else 1
     rows = p.row_count if p.row_count > 0 else (p.H - p.row_begin + step - 1) // step

@@ -109,7 +109,46 @@ def spheres_scene(light=profiles.LIGHT):
 
 
 def run_oracle(scene, params, threads=0, want=("rgb", "hit_obj", "hit_tri", "hit_t", "shadow")):
-    return pyoracle.render(scene["spheres"], scene["mesh"], scene["mesh_mat"], scene["light"], params, threads=threads, want=want)
+    return pyoracle.render(scene["spheres"], scene["mesh"], scene["mesh_mat"], scene["light"], params, threads=threads, want=want,
+                           normals=scene.get("normals"))
+
+
+def obj_normals(path):
+    """The viewer loader's extra (realtime_render.cu:489-493, 538-545), restated independently in Python: the `vn` lines of an OBJ
+    file as (nn, 3) float32 and the normal indices of its faces, fan-triangulated in file order, as (nt, 3) int32 (-1: none)."""
+    normals, idx = [], []
+    for line in open(path, "r", errors="replace"):
+        if line.startswith("vn "):
+            normals.append([np.float32(x) for x in line.split()[1:4]])
+        elif line.startswith("f"):
+            toks = line[1:].split()
+            ni = []
+            for t in toks:
+                parts = t.split("/")
+                if not parts[0].lstrip("-").isdigit():
+                    break
+                k = int(parts[2]) if len(parts) >= 3 and parts[2] else 0
+                ni.append(k - 1 if k > 0 else (len(normals) + k if k < 0 else -1))
+            for k in range(2, len(ni)):
+                tri = [ni[0], ni[k - 1], ni[k]]
+                idx.append(tri if min(tri) >= 0 else [-1, -1, -1])
+    return np.asarray(normals, np.float32).reshape(-1, 3), np.asarray(idx, np.int32).reshape(-1, 3)
+
+
+def viewer_cat_scene(obj_path=None):
+    """The viewer's scene (realtime_render.cu:1018-1050): walls 0-5 with the R = 940 floor, cat = object 6 with vertex normals, mesh
+    transform 0.6 / (0, -10, 0) after the loader's (:1309), light (0, 15, 40). None without the cat asset."""
+    path = obj_path or pyoracle.cat_obj_path()
+    if path is None:
+        return None
+    m = pyoracle.Mesh.from_obj(path, rescale=(0.6, (0., -10., 0.)))
+    m.set_normals(*obj_normals(path))
+    m.build_bvh()
+    sp = profiles.walls("cpu")
+    sp[1].R = 940.0
+    d = _scene(sp, m, profiles.mesh_material("cpu", 0), ((0., 15., 40.), 3e10))
+    d["normals"] = m.normals
+    return d
 
 
 def upload(rt_scene, scene):
@@ -119,6 +158,8 @@ def upload(rt_scene, scene):
     if scene["mesh"] is not None:
         mm = scene["mesh_mat"]
         rt_scene.set_mesh(*scene["mesh"], albedo=mm["albedo"], mirror=mm["mirror"], n_in=mm["n_in"], n_out=mm["n_out"], id=mm["id"])
+        if scene.get("normals") is not None:
+            rt_scene.set_mesh_normals(scene["normals"])
     else:
         rt_scene.clear_mesh()
     return rt_scene

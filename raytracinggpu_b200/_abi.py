@@ -48,6 +48,12 @@ class rt_params(C.Structure):
         ("row_step", C.c_int32),
         ("row_count", C.c_int32),
         ("reserved", C.c_int32),
+        ("camera_mode", C.c_int32),
+        ("cam_bx", C.c_float * 3),
+        ("cam_by", C.c_float * 3),
+        ("cam_bz", C.c_float * 3),
+        ("smooth_normals", C.c_int32),
+        ("accumulate", C.c_int32),
     ]
 
 

@@ -27,6 +27,12 @@ SIGNATURES = {
     "rt_mesh_read_obj": (C.c_int, [_vp, C.c_char_p]),
     "rt_mesh_set_triangles": (C.c_int, [_vp, _vp, _i32, _vp, _i32]),
     "rt_mesh_rescale": (C.c_int, [_vp, _f, _pf]),
+    "rt_mesh_keep_normals": (C.c_int, [_vp, C.c_int]),
+    "rt_mesh_set_normals": (C.c_int, [_vp, _vp, _i32, _vp]),
+    "rt_mesh_normal_count": (C.c_int, [_vp, _pi32]),
+    "rt_mesh_normals": (_vp, [_vp]),
+    "rt_camera_basis": (None, [_f, _f, _pf, _pf, _pf]),
+    "rt_scene_set_mesh_normals": (C.c_int, [_vp, _vp, _i32]),
     "rt_mesh_instance": (C.c_int, [_vp, _i32, _vp, _vp]),
     "rt_mesh_build_bvh": (C.c_int, [_vp]),
     "rt_mesh_build_bvh_gpu": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_double)]),
@@ -132,6 +138,13 @@ def camera_z(W, alpha=np.float32(np.pi / 3)):
     return lib().rt_camera_z(int(W), float(alpha))
 
 
+def camera_basis(yaw, pitch):
+    """Camera::rotate of the viewer (realtime_render.cu:828-849): (bx, by, bz) as float32 triples."""
+    b = [(C.c_float * 3)() for _ in range(3)]
+    lib().rt_camera_basis(float(yaw), float(pitch), b[0], b[1], b[2])
+    return tuple(np.array(list(x), np.float32) for x in b)
+
+
 def camera_z_device(W, alpha=np.float32(np.pi / 3), device=0):
     """z as optimized.cu's kernel evaluates it (CUDA tanf on the device), see rt_camera_z_device."""
     z = C.c_float()
@@ -223,10 +236,25 @@ class Mesh:
             self._h = None
 
     @classmethod
-    def read_obj(cls, path):
+    def read_obj(cls, path, keep_normals=False):
+        """readOBJ. keep_normals: the viewer's loader (realtime_render.cu:489-493, 538-545) — `vn` lines + normal indices kept."""
         m = cls()
+        if keep_normals:
+            _check(lib().rt_mesh_keep_normals(m._h, 1))
         _check(lib().rt_mesh_read_obj(m._h, path.encode()))
         return m
+
+    def set_normals(self, normals, normal_indices):
+        n = np.ascontiguousarray(normals, dtype=np.float32).reshape(-1, 3)
+        i = np.ascontiguousarray(normal_indices, dtype=np.int32).reshape(-1, 3)
+        _check(lib().rt_mesh_set_normals(self._h, n.ctypes.data, n.shape[0], i.ctypes.data))
+        return self
+
+    @property
+    def normals(self):
+        n = C.c_int32()
+        _check(lib().rt_mesh_normal_count(self._h, C.byref(n)))
+        return _view(lib().rt_mesh_normals(self._h), (n.value, 3), np.float32)
 
     @classmethod
     def from_arrays(cls, vertices, vtx_indices):
@@ -342,6 +370,11 @@ class Scene:
         _check(lib().rt_scene_set_mesh(self._h, v.ctypes.data, v.shape[0], t.ctypes.data, t.shape[0], b.ctypes.data, b.shape[0],
                                        _f3(albedo), int(mirror), float(n_in), float(n_out), int(id)))
         self.mesh_h2d_bytes = v.nbytes + t.nbytes + b.nbytes
+
+    def set_mesh_normals(self, normals):
+        """Per-vertex normals for rt_params.smooth_normals (after set_mesh; indices are words 6-8 of its triangle records)."""
+        n = np.ascontiguousarray(normals, dtype=np.float32).reshape(-1, 3) if normals is not None else np.zeros((0, 3), np.float32)
+        _check(lib().rt_scene_set_mesh_normals(self._h, n.ctypes.data if n.shape[0] else None, n.shape[0]))
 
     def clear_mesh(self):
         _check(lib().rt_scene_set_mesh(self._h, None, 0, None, 0, None, 0, _f3((0, 0, 0)), 0, 1.0, 1.0, 0))

@@ -35,6 +35,8 @@ const float kInf = (float)(1e9 + 9); /* INF as stored into BoundingBox floats, o
 
 struct rt_mesh {
     std::vector<rtb::Vec3> vertices;
+    std::vector<rtb::Vec3> normals; /* `vn` lines, kept only on request (rt_mesh_keep_normals): realtime_render.cu:489-493 */
+    bool keep_normals = false;
     std::vector<TriRecord> tris;
     std::vector<float> arr_bvh; /* n_nodes * 10 */
     int32_t n_nodes = 0, n_leaves = 0, max_depth = 0, max_leaf = 0;
@@ -61,9 +63,10 @@ int parse_floats(const char* p, const char* end, float* out, int max) {
     return n;
 }
 
-/* One face-vertex token `a`, `a/b`, `a/b/c` or `a//c`; only the vertex index is kept (optimized.cu drops
- * uv / normal indices). Returns false when no integer starts at p. */
-bool parse_face_vertex(const char*& p, const char* end, long& vi) {
+/* One face-vertex token `a`, `a/b`, `a/b/c` or `a//c`: the vertex index, and the normal index c (0 = absent) for the
+ * loaders that keep it (realtime_render.cu:538-545; optimized.cu drops uv / normal indices). Returns false when no integer
+ * starts at p. */
+bool parse_face_vertex(const char*& p, const char* end, long& vi, long& ni) {
     while (p < end && is_blank(*p)) p++;
     if (p >= end) return false;
     char* q = nullptr;
@@ -71,11 +74,13 @@ bool parse_face_vertex(const char*& p, const char* end, long& vi) {
     long v = strtol(p, &q, 10);
     if (q == p) return false;
     vi = v;
+    ni = 0;
     p = q;
     for (int k = 0; k < 2 && p < end && *p == '/'; k++) {
         p++;
         if (p < end && (*p == '-' || (*p >= '0' && *p <= '9'))) {
-            strtol(p, &q, 10);
+            const long w = strtol(p, &q, 10);
+            if (k == 1) ni = w;
             p = q;
         }
     }
@@ -97,13 +102,14 @@ int read_obj(rt_mesh* m, const char* path) {
     fclose(f);
     buf.push_back('\n');
     m->vertices.clear();
+    m->normals.clear();
     m->tris.clear();
     m->arr_bvh.clear();
     m->n_nodes = 0;
 
     const char* p = buf.data();
     const char* const eof = p + buf.size();
-    std::vector<long> poly;
+    std::vector<long> poly, poly_n;
     while (p < eof) {
         const char* eol = (const char*)memchr(p, '\n', (size_t)(eof - p));
         if (!eol) eol = eof;
@@ -118,12 +124,21 @@ int read_obj(rt_mesh* m, const char* path) {
                 q.z = q.z * 0.8f + 0.f;
             }
             m->vertices.push_back(q);
+        } else if (m->keep_normals && eol - p >= 3 && p[0] == 'v' && p[1] == 'n' && p[2] == ' ') {
+            float v[3] = {0, 0, 0};
+            parse_floats(p + 3, eol, v, 3);
+            m->normals.push_back(rtb::Vec3{v[0], v[1], v[2]}); /* realtime_render.cu:489-493: as read */
         } else if (eol - p >= 1 && p[0] == 'f') {
             poly.clear();
+            poly_n.clear();
             const char* q = p + 1;
-            long vi;
-            while (parse_face_vertex(q, eol, vi)) poly.push_back(vi);
+            long vi, ni;
+            while (parse_face_vertex(q, eol, vi, ni)) {
+                poly.push_back(vi);
+                poly_n.push_back(ni);
+            }
             const size_t nv = m->vertices.size();
+            const size_t nnrm = m->normals.size();
             /* fan triangulation (i0, i_{k-1}, i_k): optimized.cu:398-447 */
             for (size_t k = 2; k < poly.size(); k++) {
                 TriRecord t;
@@ -131,15 +146,22 @@ int read_obj(rt_mesh* m, const char* path) {
                 t.w[0] = resolve(poly[0], nv);
                 t.w[1] = resolve(poly[k - 1], nv);
                 t.w[2] = resolve(poly[k], nv);
+                if (m->keep_normals && poly_n[0] && poly_n[k - 1] && poly_n[k]) { /* ni, nj, nk: realtime_render.cu:538-545 */
+                    t.w[6] = resolve(poly_n[0], nnrm);
+                    t.w[7] = resolve(poly_n[k - 1], nnrm);
+                    t.w[8] = resolve(poly_n[k], nnrm);
+                }
                 m->tris.push_back(t);
             }
         }
         p = eol + 1;
     }
-    const int32_t nv = (int32_t)m->vertices.size();
+    const int32_t nv = (int32_t)m->vertices.size(), nn = (int32_t)m->normals.size();
     for (const TriRecord& t : m->tris)
-        for (int k = 0; k < 3; k++)
+        for (int k = 0; k < 3; k++) {
             if (t.w[k] < 0 || t.w[k] >= nv) return rtb::fail(RT_ERR_INVALID, "rt_mesh_read_obj: face index out of range in '%s'", path);
+            if (t.w[6 + k] >= nn) return rtb::fail(RT_ERR_INVALID, "rt_mesh_read_obj: normal index out of range in '%s'", path);
+        }
     return RT_OK;
 }
 
@@ -248,9 +270,37 @@ int rt_mesh_set_triangles(rt_mesh* m, const float* vertices, int32_t nv, const i
         for (int k = 0; k < 3; k++) m->tris[i].w[k] = idx[3 * i + k];
     }
     m->arr_bvh.clear();
+    m->normals.clear();
     m->n_nodes = 0;
     return RT_OK;
 }
+
+int rt_mesh_keep_normals(rt_mesh* m, int keep) {
+    if (!m) return rtb::fail(RT_ERR_INVALID, "rt_mesh_keep_normals: NULL mesh");
+    m->keep_normals = keep != 0;
+    return RT_OK;
+}
+
+int rt_mesh_set_normals(rt_mesh* m, const float* normals, int32_t nn, const int32_t* normal_indices) {
+    if (!m || nn < 0 || (nn > 0 && (!normals || !normal_indices))) return rtb::fail(RT_ERR_INVALID, "rt_mesh_set_normals: bad argument");
+    if (m->n_nodes > 0) return rtb::fail(RT_ERR_STATE, "rt_mesh_set_normals: attach the normals before the BVH is built (the build reorders the records)");
+    const size_t nt = m->tris.size();
+    for (size_t i = 0; i < 3 * nt && nn > 0; i++)
+        if (normal_indices[i] < 0 || normal_indices[i] >= nn) return rtb::fail(RT_ERR_INVALID, "rt_mesh_set_normals: normal index %d out of range", normal_indices[i]);
+    m->normals.resize((size_t)nn);
+    for (int32_t i = 0; i < nn; i++) m->normals[i] = rtb::Vec3{normals[3 * i], normals[3 * i + 1], normals[3 * i + 2]};
+    for (size_t i = 0; i < nt; i++)
+        for (int k = 0; k < 3; k++) m->tris[i].w[6 + k] = nn > 0 ? normal_indices[3 * i + k] : -1;
+    return RT_OK;
+}
+
+int rt_mesh_normal_count(const rt_mesh* m, int32_t* nn) {
+    if (!m || !nn) return rtb::fail(RT_ERR_INVALID, "rt_mesh_normal_count: bad argument");
+    *nn = (int32_t)m->normals.size();
+    return RT_OK;
+}
+
+const float* rt_mesh_normals(const rt_mesh* m) { return (m && !m->normals.empty()) ? &m->normals[0].x : nullptr; }
 
 int rt_mesh_rescale(rt_mesh* m, float scale, const float offset[3]) {
     if (!m || !offset) return rtb::fail(RT_ERR_INVALID, "rt_mesh_rescale: NULL argument");

@@ -39,12 +39,13 @@ const WallDef kWalls[6] = {
     {{0, 0, 1000}, 940, {1, 0, 1}},  /* magenta back wall */
 };
 
-enum Profile { kCpu, kOptimized, kArrayBvh, kUnknown };
+enum Profile { kCpu, kOptimized, kArrayBvh, kRealtime, kUnknown };
 Profile parse_profile(const char* s) {
     if (!s) return kUnknown;
     if (!strcmp(s, "cpu")) return kCpu;
     if (!strcmp(s, "optimized")) return kOptimized;
     if (!strcmp(s, "array_bvh")) return kArrayBvh;
+    if (!strcmp(s, "realtime")) return kRealtime;
     return kUnknown;
 }
 
@@ -80,10 +81,37 @@ float rt_camera_z(int32_t W, float alpha) {
     return -W / (2 * t);
 }
 
+void rt_camera_basis(float yaw, float pitch, float bx_[3], float by_[3], float bz_[3]) {
+    /* Camera::rotate, realtime_render.cu:828-849, operation for operation in float (Vector * float, Vector + Vector, cross,
+     * normalize = three divisions by sqrtf(norm2)); cos / sin of a float argument are the float functions in CUDA host code */
+    struct V { float x, y, z; };
+    auto mul = [](V a, float b) { return V{a.x * b, a.y * b, a.z * b}; };
+    auto add = [](V a, V b) { return V{a.x + b.x, a.y + b.y, a.z + b.z}; };
+    auto sub = [](V a, V b) { return V{a.x - b.x, a.y - b.y, a.z - b.z}; };
+    auto cross = [](V a, V b) { return V{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; };
+    auto normalize = [](V a) {
+        const float n = sqrtf(a.x * a.x + a.y * a.y + a.z * a.z);
+        return V{a.x / n, a.y / n, a.z / n};
+    };
+    V bx{1, 0, 0}, by{0, 1, 0}, bz{0, 0, -1};
+    const float cy = cosf(yaw), sy = sinf(yaw);
+    bx = add(mul(bx, cy), mul(bz, sy));
+    bz = cross(by, bx);
+    const float cp = cosf(pitch), sp = sinf(pitch);
+    by = sub(mul(by, cp), mul(bz, sp));
+    bz = cross(bx, by);
+    bx = normalize(bx);
+    by = normalize(by);
+    bz = normalize(bz);
+    bx_[0] = bx.x; bx_[1] = bx.y; bx_[2] = bx.z;
+    by_[0] = by.x; by_[1] = by.y; by_[2] = by.z;
+    bz_[0] = bz.x; bz_[1] = bz.y; bz_[2] = bz.z;
+}
+
 int rt_params_profile(rt_params* p, const char* profile, int32_t W, int32_t H, int32_t num_rays, int32_t num_bounce) {
     if (!p) return rtb::fail(RT_ERR_INVALID, "rt_params_profile: NULL params");
     const Profile pr = parse_profile(profile);
-    if (pr == kUnknown) return rtb::fail(RT_ERR_INVALID, "rt_params_profile: unknown profile '%s' (cpu | optimized | array_bvh)", profile ? profile : "(null)");
+    if (pr == kUnknown) return rtb::fail(RT_ERR_INVALID, "rt_params_profile: unknown profile '%s' (cpu | optimized | array_bvh | realtime)", profile ? profile : "(null)");
     if (W <= 0 || H <= 0 || num_rays < 0 || num_bounce < 0) return rtb::fail(RT_ERR_INVALID, "rt_params_profile: bad size");
     memset(p, 0, sizeof *p);
     p->W = W;
@@ -114,6 +142,17 @@ int rt_params_profile(rt_params* p, const char* profile, int32_t W, int32_t H, i
         p->extra_segment = 0;
         p->gamma_mode = 1;
         break;
+    case kRealtime: /* realtime_render.cu:908,298,288-289; pov = PI/2 :1021; Camera() pitch 0.3 :809; smooth normals :311 */
+        p->eps_surface = 1e-3f;
+        p->eps_tri = 1e-3f;
+        p->push_order = 0;
+        p->extra_segment = 0;
+        p->gamma_mode = 1;
+        p->z = rt_camera_z(W, (float)(3.14159265358979323846 / 2));
+        p->camera_mode = 1;
+        rt_camera_basis(0.f, 0.3f, p->cam_bx, p->cam_by, p->cam_bz);
+        p->smooth_normals = 1;
+        break;
     default: /* array_bvh.cu:805,292,282-283; host gamma :1112-1118 */
         p->eps_surface = 1e-4f;
         p->eps_tri = 1e-4f;
@@ -128,13 +167,13 @@ int rt_params_profile(rt_params* p, const char* profile, int32_t W, int32_t H, i
 int rt_default_walls(const char* profile, rt_sphere walls[6], int32_t* mesh_id) {
     const Profile pr = parse_profile(profile);
     if (pr == kUnknown || !walls) return rtb::fail(RT_ERR_INVALID, "rt_default_walls: bad argument");
-    const int32_t mid = (pr == kOptimized) ? 1 : 6; /* optimized.cu:690-700 vs cpu_launcher.cpp:685 */
+    const int32_t mid = (pr == kOptimized) ? 1 : 6; /* optimized.cu:690-700 vs cpu_launcher.cpp:685, realtime_render.cu:1026-1050 */
     int32_t next = 0;
     for (int k = 0; k < 6; k++) {
         if (next == mid) next++;
         rt_sphere& s = walls[k];
         memcpy(s.C, kWalls[k].C, sizeof s.C);
-        s.R = kWalls[k].R;
+        s.R = (pr == kRealtime && k == 1) ? 940.f : kWalls[k].R; /* the viewer's floor: realtime_render.cu:1027 */
         memcpy(s.albedo, kWalls[k].albedo, sizeof s.albedo);
         s.mirror = 0;
         s.n_in = 1.f;

@@ -151,6 +151,15 @@ struct rt_scene {
     std::vector<float> last_bvh;  /* host copy of the arr_bvh the packed tree was built from: a mesh uploaded again with the same tree
                                    * (the per-frame upload of a caller that owns the geometry) skips the node relayout, keeps the bins */
     int32_t last_nv = 0, last_nt = 0;
+    size_t stage_r_off = 0;          /* where the uploaded triangle records sit in `stage` (rt_scene_set_mesh_normals reads words 6-8) */
+    int32_t stage_nt = 0;
+    float4* tri_normals = nullptr;   /* viewer feature: 3 x float4 per triangle (vertex normals), beside the blob */
+    float* d_normals = nullptr;
+    size_t tri_normals_cap = 0, d_normals_cap = 0;
+    bool has_normals = false;
+    float4* accum = nullptr;         /* viewer feature: progressive accumulation buffer + the frame's linear colour */
+    float4* linear = nullptr;
+    size_t accum_px = 0;
     /* anchored-ray bins (rt_bins.cuh): [0] camera, [1] light */
     struct AnchorBins {
         float A[3] = {0.f, 0.f, 0.f};
@@ -525,6 +534,10 @@ void rt_scene_destroy(rt_scene* s) {
     DeviceGuard g(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
     if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
+    if (s->tri_normals) cudaFree(s->tri_normals);
+    if (s->d_normals) cudaFree(s->d_normals);
+    if (s->accum) cudaFree(s->accum);
+    if (s->linear) cudaFree(s->linear);
     if (s->blob) cudaFree(s->blob);
     if (s->gamma_tab) cudaFree(s->gamma_tab);
     if (s->counters) cudaFree(s->counters);
@@ -659,6 +672,8 @@ int rt_scene_set_mesh(rt_scene* s, const float* vertices, int32_t nv, const int3
         s->plan_valid = false;
         s->last_bvh.clear();
         s->last_nv = s->last_nt = 0;
+        s->has_normals = false;
+        s->stage_nt = 0;
         h.mesh_id = -1;
         s->header_dirty = true;
         return RT_OK;
@@ -687,6 +702,7 @@ int rt_scene_set_mesh(rt_scene* s, const float* vertices, int32_t nv, const int3
         rtk::repack_triangles<<<blocks, threads, 0, s->stream>>>(reinterpret_cast<float*>(s->stage), reinterpret_cast<int32_t*>(s->stage + r_off), nt,
                                                                 reinterpret_cast<int32_t*>(s->stage + l_off), reinterpret_cast<float4*>(s->blob + h.off_tris));
         CUDA_TRY(cudaGetLastError());
+        s->has_normals = false; /* the records were uploaded again: rt_scene_set_mesh_normals must follow */
         const bool same_material = h.mesh_id == id && h.mesh_mirror == (mirror ? 1 : 0) && h.mesh_n_in == n_in && h.mesh_n_out == n_out &&
                                    memcmp(h.mesh_albedo, albedo, sizeof h.mesh_albedo) == 0;
         if (!same_material) {
@@ -1001,11 +1017,48 @@ int rt_scene_set_mesh(rt_scene* s, const float* vertices, int32_t nv, const int3
     s->last_bvh.assign(arr_bvh, arr_bvh + (size_t)n_nodes * RT_BVH_NODE_FLOATS);
     s->last_nv = pin_need <= ((size_t)64 << 20) ? nv : 0; /* the fast path needs the pinned staging layout */
     s->last_nt = nt;
+    s->stage_r_off = r_off;
+    s->stage_nt = nt;
+    s->has_normals = false;
     h.n_wide = n_wide;
     h.wide_depth = wide_depth;
     h.wroot_ref = wroot_ref;
     h.total_bytes = total;
     s->header_dirty = true;
+    return RT_OK;
+}
+
+int rt_scene_set_mesh_normals(rt_scene* s, const float* normals, int32_t n_normals) {
+    if (!s || n_normals < 0 || (n_normals > 0 && !normals)) return rtb::fail(RT_ERR_INVALID, "rt_scene_set_mesh_normals: bad argument");
+    DeviceGuard g(s->device);
+    if (n_normals == 0) {
+        s->has_normals = false;
+        return RT_OK;
+    }
+    if (!s->header.has_mesh || s->stage_nt != s->header.n_tris || !s->stage)
+        return rtb::fail(RT_ERR_STATE, "rt_scene_set_mesh_normals: call rt_scene_set_mesh first (the normal indices are words 6-8 of its triangle records)");
+    const int nt = s->stage_nt;
+    if (s->d_normals_cap < (size_t)n_normals * 3) {
+        CUDA_TRY(cudaStreamSynchronize(s->stream));
+        if (s->d_normals) cudaFree(s->d_normals);
+        s->d_normals = nullptr;
+        s->d_normals_cap = 0;
+        CUDA_TRY(cudaMalloc(&s->d_normals, (size_t)n_normals * 3 * sizeof(float)));
+        s->d_normals_cap = (size_t)n_normals * 3;
+    }
+    if (s->tri_normals_cap < (size_t)nt * 3) {
+        CUDA_TRY(cudaStreamSynchronize(s->stream));
+        if (s->tri_normals) cudaFree(s->tri_normals);
+        s->tri_normals = nullptr;
+        s->tri_normals_cap = 0;
+        CUDA_TRY(cudaMalloc(&s->tri_normals, (size_t)nt * 3 * sizeof(float4)));
+        s->tri_normals_cap = (size_t)nt * 3;
+    }
+    CUDA_TRY(cudaMemcpyAsync(s->d_normals, normals, (size_t)n_normals * 3 * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+    rtk::repack_normals<<<(nt + 255) / 256, 256, 0, s->stream>>>(s->d_normals, n_normals, reinterpret_cast<const int32_t*>(s->stage + s->stage_r_off), nt, s->tri_normals);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(s->stream)); /* the caller's array may go away */
+    s->has_normals = true;
     return RT_OK;
 }
 
@@ -1068,6 +1121,8 @@ int rt_scene_blob_import(rt_scene* s, const void* device_ptr, size_t bytes) {
     s->max_leaf = h.max_leaf; /* host-side guard of the tie-break rank (push_order 0): travels with the blob */
     s->last_bvh.clear();
     s->last_nv = s->last_nt = 0;
+    s->has_normals = false; /* vertex normals are not part of the blob */
+    s->stage_nt = 0;
     s->header_dirty = false;
     s->mesh_generation++; /* the anchored-ray bins of the previous mesh are stale */
     s->plan_valid = false;
@@ -1263,6 +1318,32 @@ int plan_frame(rt_scene* s, const rt_params* p, uint32_t flags, void* const user
     a.counters = s->counters;
     a.gamma_tab = s->gamma_tab;
     a.debug_cost = s->opt.debug_cost;
+    if (p->camera_mode != 0 && p->camera_mode != 1) return rtb::fail(RT_ERR_INVALID, "rt_render: camera_mode must be 0 or 1");
+    a.camera_mode = p->camera_mode;
+    for (int k = 0; k < 3; k++) {
+        a.bx[k] = p->cam_bx[k];
+        a.by[k] = p->cam_by[k];
+        a.bz[k] = p->cam_bz[k];
+    }
+    if (p->smooth_normals && h.has_mesh) {
+        if (!s->has_normals) return rtb::fail(RT_ERR_STATE, "rt_render: smooth_normals needs rt_scene_set_mesh_normals after rt_scene_set_mesh");
+        a.tri_normals = s->tri_normals;
+    }
+    if (p->accumulate < 0) return rtb::fail(RT_ERR_INVALID, "rt_render: accumulate must be >= 0");
+    if (p->accumulate > 0) {
+        if (p->accumulate > 1 && s->accum_px != npx) return rtb::fail(RT_ERR_STATE, "rt_render: accumulation frame %d without a frame 1 of the same size", p->accumulate);
+        if (s->accum_px != npx) {
+            CUDA_TRY(cudaStreamSynchronize(s->stream));
+            if (s->accum) cudaFree(s->accum);
+            if (s->linear) cudaFree(s->linear);
+            s->accum = s->linear = nullptr;
+            s->accum_px = 0;
+            CUDA_TRY(cudaMalloc(&s->accum, npx * sizeof(float4)));
+            CUDA_TRY(cudaMalloc(&s->linear, npx * sizeof(float4)));
+            s->accum_px = npx;
+        }
+        a.linear = s->linear;
+    }
 
     P.prelaunches = 0;
     const int tiles_x = (p->W + 15) / 16, tiles_y = (rows + 7) / 8;
@@ -1282,6 +1363,8 @@ int plan_frame(rt_scene* s, const rt_params* p, uint32_t flags, void* const user
     if (variant == 2 && segments > WF_MAX_ROUNDS - 1) variant = stochastic ? 3 : 1;
     if (stochastic && variant == 1) variant = 3;
     s->last_was_wavefront = (variant == 2);
+    if (variant != 2 && (p->camera_mode || a.tri_normals || a.linear))
+        return rtb::fail(RT_ERR_UNSUPPORTED, "rt_render: the viewer-derived features (camera basis, smooth normals, accumulation) need the wavefront pipeline (variant 2, <= %d segments)", WF_MAX_ROUNDS - 1);
     if (stochastic) {
         /* start states of the random streams: once per (seed, W, H), not per launch (rt_stochastic.cuh) */
         const unsigned long long seed = p->reserved ? (unsigned long long)(unsigned int)p->reserved : 123456ull; /* optimized.cu:745 */
@@ -1679,7 +1762,7 @@ int enqueue_frame(rt_scene* s, const FramePlan& P, int& launches, bool& strip_co
              * (kernel_ms then spans the copies of all bands but the last as well) */
             const size_t elem[5] = {3, 4, 4, 4, 1};
             for (int k = 0; k < 5; k++)
-                if (copy_back[k]) {
+                if (copy_back[k] && !(a.linear && k == 0)) { /* accumulation: the 8-bit frame exists only after accumulate_frame */
                     CUDA_TRY(cudaMemcpyAsync((unsigned char*)user[k] + px0 * elem[k], (unsigned char*)dev[k] + px0 * elem[k], spx * elem[k], cudaMemcpyDeviceToHost, stream));
                     strip_copied = true;
                 }
@@ -1699,6 +1782,11 @@ int enqueue_frame(rt_scene* s, const FramePlan& P, int& launches, bool& strip_co
         fprintf(stderr, "\n");
         for (int k = 0; k < n_ev; k++) cudaEventDestroy(dev_ev[k]);
     }
+        if (a.linear) { /* progressive accumulation (realtime_render.cu:1136-1140) once every band has joined */
+            rtk::accumulate_frame<<<(unsigned)((P.npx + 255) / 256), 256, 0, s->stream>>>(s->accum, s->linear, (int)P.npx, p->accumulate, a.rgb, a.gamma_tab, a.gamma_mode);
+            launches++;
+            if (copy_back[0] && strip_copied) CUDA_TRY(cudaMemcpyAsync(user[0], dev[0], P.bytes[0], cudaMemcpyDeviceToHost, s->stream));
+        }
         launches--; /* the common launches++ below counts one */
     } else if (variant == 3) {
         CUDA_TRY(cudaMemsetAsync(s->counters, 0, RT_NCOUNTERS * sizeof(unsigned long long), s->stream));

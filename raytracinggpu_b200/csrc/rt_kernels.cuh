@@ -33,6 +33,11 @@ struct RenderArgs {
     unsigned long long* counters; /* [0] rays, [1] inner-node visits, [2] triangle tests, [3] max stack, [4] slab exact fallbacks, [5] exact triangle evaluations */
     const float* gamma_tab;       /* 2 x 256 thresholds */
     int32_t rank_off_bits;        /* render_wave: bits of the in-leaf offset in the tie-break rank (push_order 0) */
+    /* viewer-derived features (realtime_render.cu), wavefront pipeline only; all zero = the launchers' behaviour */
+    int32_t camera_mode;          /* 1: u_center = C + bz z + bx (j - W/2 + 0.5) + by (H/2 - i - 0.5), realtime_render.cu:1113 */
+    float bx[3], by[3], bz[3];
+    const float4* tri_normals;    /* 3 x float4 per triangle: the vertex normals Na, Nb, Nc (w of the first: 1 = present); NULL = geometric normals */
+    float4* linear;               /* progressive accumulation: the frame's linear colour per compact pixel instead of the 8-bit store */
     int32_t debug_cost;           /* investigation aid: with COUNT, hit_t <- thread clocks, hit_tri <- nodes+tris, hit_obj <- smid */
 };
 
@@ -498,6 +503,53 @@ __global__ void repack_triangles(const float* __restrict__ vertices, const int32
     tris[4 * (size_t)i + 1] = make_float4(e1.y, e1.z, e2.x, e2.y);
     tris[4 * (size_t)i + 2] = make_float4(e2.z, N.x, N.y, N.z);
     tris[4 * (size_t)i + 3] = make_float4(nh.x, nh.y, nh.z, __int_as_float(leaf_start[i]));
+}
+
+/* Per-triangle vertex normals for smooth shading (get_smooth_normal reads normals[tid.ni / nj / nk], realtime_render.cu:239-241):
+ * gathered once into 3 x float4 per triangle, in the order of the uploaded triangle records. */
+__global__ void repack_normals(const float* __restrict__ normals, int n_normals, const int32_t* __restrict__ recs, int nt, float4* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nt) return;
+    const int32_t* r = recs + (size_t)i * 10;
+    const int na = r[6], nb = r[7], nc = r[8];
+    const bool ok = na >= 0 && nb >= 0 && nc >= 0 && na < n_normals && nb < n_normals && nc < n_normals;
+    for (int k = 0; k < 3; k++) {
+        const int j = ok ? r[6 + k] : 0;
+        out[3 * (size_t)i + k] = ok ? make_float4(normals[3 * (size_t)j], normals[3 * (size_t)j + 1], normals[3 * (size_t)j + 2], 1.f) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
+/* get_smooth_normal, realtime_render.cu:221-245: beta and gamma with moller_trumbore's own expressions on the packed record
+ * (A, e1, e2, N = e1 x e2 are the reference's values bit for bit), N = normalize(alpha Na + beta Nb + gamma Nc). */
+__device__ __forceinline__ F3 smooth_normal(const float4* __restrict__ tris, const float4* __restrict__ tri_normals, int tri, F3 O, F3 u, F3 flat) {
+    const float4 na = __ldg(tri_normals + 3 * (size_t)tri);
+    if (na.w == 0.f) return flat; /* the record carries no normal indices */
+    const float4 nb = __ldg(tri_normals + 3 * (size_t)tri + 1), nc = __ldg(tri_normals + 3 * (size_t)tri + 2);
+    const float4 q0 = __ldg(tris + 4 * (size_t)tri), q1 = __ldg(tris + 4 * (size_t)tri + 1), q2 = __ldg(tris + 4 * (size_t)tri + 2);
+    const F3 A = f3(q0.x, q0.y, q0.z), e1 = f3(q0.w, q1.x, q1.y), e2 = f3(q1.z, q1.w, q2.x), Ng = f3(q2.y, q2.z, q2.w);
+    const float beta = dot(e2, cross(A - O, u)) / dot(u, Ng);
+    const float gamma = -dot(e1, cross(A - O, u)) / dot(u, Ng);
+    const float alpha = 1 - beta - gamma;
+    return normalized((alpha * f3(na.x, na.y, na.z) + beta * f3(nb.x, nb.y, nb.z)) + gamma * f3(nc.x, nc.y, nc.z));
+}
+
+/* Progressive accumulation, realtime_render.cu:1136-1140: accumbuffer += the frame's colour, the displayed 8-bit frame is
+ * accumbuffer / framenumber through the transfer function. k == 1 starts a new accumulation. */
+__global__ void accumulate_frame(float4* __restrict__ acc, const float4* __restrict__ linear, int npx, int k, uint8_t* __restrict__ rgb,
+                                 const float* __restrict__ gamma_tab, int gamma_mode) {
+    const int px = blockIdx.x * blockDim.x + threadIdx.x;
+    if (px >= npx) return;
+    const float4 c = linear[px];
+    float4 a = k == 1 ? make_float4(0.f, 0.f, 0.f, 0.f) : acc[px];
+    a = make_float4(a.x + c.x, a.y + c.y, a.z + c.z, 0.f);
+    acc[px] = a;
+    if (rgb) {
+        const float* T = gamma_tab + gamma_mode * 256;
+        const float kf = (float)k;
+        rgb[(size_t)px * 3 + 0] = (uint8_t)quantise(a.x / kf, T);
+        rgb[(size_t)px * 3 + 1] = (uint8_t)quantise(a.y / kf, T);
+        rgb[(size_t)px * 3 + 2] = (uint8_t)quantise(a.z / kf, T);
+    }
 }
 
 /* Device self-test of div_by_rcp against div.rn.f32 on pseudo-random operands in the range RaySafe admits.

@@ -156,10 +156,14 @@ __device__ __forceinline__ void store_entry(QEntry* q, int slot, F3 O, F3 u, flo
 
 /* sample average + transfer function + store (optimized.cu:762-771) */
 __device__ __forceinline__ void write_pixel(const RenderArgs& a, int px, F3 color) {
-    if (!a.rgb) return;
+    if (!a.rgb && !a.linear) return;
     F3 total = f3(0.f, 0.f, 0.f) + color; /* the first of num_rays additions (0 + x, as the reference's accumulation starts) */
     for (int s = 1; s < a.num_rays; s++) total = total + color;
     const F3 avg = a.num_rays == 1 ? total : total / (float)a.num_rays; /* x / 1.0f == x */
+    if (a.linear) { /* progressive accumulation: accumulate_frame quantises after the frame */
+        a.linear[px] = make_float4(avg.x, avg.y, avg.z, 0.f);
+        return;
+    }
     const float* T = a.gamma_tab + a.gamma_mode * 256;
     a.rgb[(size_t)px * 3 + 0] = (uint8_t)quantise(avg.x, T);
     a.rgb[(size_t)px * 3 + 1] = (uint8_t)quantise(avg.y, T);
@@ -250,7 +254,9 @@ __device__ __forceinline__ int exact_mesh_query(const MeshRoot h, const float4* 
 template <bool STOCH>
 __device__ __forceinline__ void light_is_blocked(const RenderArgs& a, const WfArgs& g, int px, int packed) {
     if (!STOCH) {
-        if (a.rgb) {
+        if (a.linear) {
+            a.linear[px] = make_float4(0.f, 0.f, 0.f, 0.f);
+        } else if (a.rgb) {
             a.rgb[(size_t)px * 3 + 0] = 0;
             a.rgb[(size_t)px * 3 + 1] = 0;
             a.rgb[(size_t)px * 3 + 2] = 0;
@@ -362,6 +368,7 @@ __device__ __forceinline__ void path_advance(const SceneHeader& h, const WfArgs&
         } else {
             const float4 nh = __ldg(tris + 4 * (size_t)tri + 3); /* N.normalize() :282, precomputed */
             N = f3(nh.x, nh.y, nh.z);
+            if (a.tri_normals) N = smooth_normal(tris, a.tri_normals, tri, O, u, N); /* realtime_render.cu:311 */
             albedo = f3(h.mesh_albedo[0], h.mesh_albedo[1], h.mesh_albedo[2]);
             mirror = h.mesh_mirror;
             n_in = h.mesh_n_in;
@@ -652,7 +659,9 @@ __global__ void __launch_bounds__(WF_THREADS, 10) wf_generate(const __grid_const
     const int px = kr * a.W + j;
     if (j < a.W && kr < a.rows) {
         const int i = a.row_begin + kr * a.row_step;
-        const F3 uc = f3((float)j - (float)a.W / 2 + 0.5f, (float)a.H / 2 - (float)i - 0.5f, a.z); /* optimized.cu:751, exact in float */
+        F3 uc = f3((float)j - (float)a.W / 2 + 0.5f, (float)a.H / 2 - (float)i - 0.5f, a.z); /* optimized.cu:751, exact in float */
+        if (a.camera_mode == 1) /* the viewer's camera, realtime_render.cu:1113 (the camera position is part of the sum there) */
+            uc = ((f3(a.camx, a.camy, a.camz) + a.z * f3(a.bz[0], a.bz[1], a.bz[2])) + uc.x * f3(a.bx[0], a.bx[1], a.bx[2])) + uc.y * f3(a.by[0], a.by[1], a.by[2]);
         F3 u0;
         if (!STOCH) {
             u0 = normalized(uc); /* sigma == 0: the jitter terms of :758 are exactly 0 */
@@ -895,7 +904,10 @@ __global__ void __launch_bounds__(256) wf_fold(const __grid_constant__ WfArgs g)
     }
     const F3 sum = f3(tot.x, tot.y, tot.z) + ans; /* color_out = color_out + color, :762 */
     if (g.last_sample) {
-        if (a.rgb) {
+        if (a.linear) {
+            const F3 avg = sum / (float)a.num_rays;
+            a.linear[px] = make_float4(avg.x, avg.y, avg.z, 0.f);
+        } else if (a.rgb) {
             const F3 avg = sum / (float)a.num_rays; /* :764 */
             const float* T = a.gamma_tab + a.gamma_mode * 256;
             a.rgb[(size_t)px * 3 + 0] = (uint8_t)quantise(avg.x, T);
