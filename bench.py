@@ -7,9 +7,11 @@
 Workload (N = 1): BASELINE.json configs[1] — cadnav cat TriangleMesh with the array BVH + six wall spheres,
 1920x1080, 1 sample/pixel, primary + shadow rays (4,147,200 rays/frame), optimized.cu knobs. A "step" is one
 frame. For N > 1 the path shards by frame: every rank renders its own frames of the SAME workload (frame-parallel,
-no data-path collective, "scaling": "weak"), so that the per-N values are comparable; the frames of a light-orbit
-animation (BASELINE.json configs[3] style: the light's candidate bins are rebuilt every frame) and whole 4K depth-4
-frames rendered frame-parallel are reported beside the headline (`animation_light_orbit`, `frames_4k_depth4`).
+no data-path collective, "scaling": "weak"), so that the per-N values are comparable. The other BASELINE.json configs
+are reported beside the headline under "configs": [0] spheres scene 800x600, [2] one 4K depth-4 frame row-interleaved
+over the ranks (strong scaling, NCCL all-gather and NVLink push), [3] the 240-frame light-orbit animation of the spheres
+scene at 1080p frame-parallel over the ranks, [4] the 10 M-triangle scene at 4K built on rank 0, broadcast once and
+rendered row-interleaved; plus a light-orbit animation of the cat scene and whole 4K depth-4 frames.
 
 `value` times the render kernels with the scene resident in HBM (CUDA events on the launching stream, L2
 flushed between steps). `e2e` goes through the C ABI with HOST buffers: every step re-uploads the mesh in the
@@ -31,6 +33,11 @@ import numpy as np  # noqa: E402
 CAT_REL = os.path.join("cadnav.com_model", "Models_F0202A090", "cat.obj")
 W, H = 1920, 1080
 METRIC = "Mrays/s"
+
+
+def workload_string(mesh_name):
+    """The same string in both arms (the driver compares them)."""
+    return "BASELINE.json configs[1]: %s + 6 wall spheres, 1920x1080, 1 spp, primary+shadow rays, optimized.cu knobs" % mesh_name
 
 
 def find_cat():
@@ -90,18 +97,22 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic():
-    """DRAM bytes of ONE frame (all its render launches: wf_generate / wf_leaves / wf_shade per strip) from the newest
-    committed `ncu --set full` summary of this workload (profiles/*_ncu_summary.json, written by tools/ncu_summary.py, one
-    captured frame per file); None when no capture is committed. The render path has no single dominant kernel any more
-    (generate 45 %, leaves 40 %, shade 15 % of a frame), so the roofline is stated for the frame."""
+def ncu_frame_summary(pattern="*_ncu_summary.json", exclude=("config5", "config4")):
+    """Per-FRAME figures of the newest committed `ncu --set full` summary of the headline workload (profiles/*_ncu_summary.json,
+    written by tools/ncu_summary.py, one captured frame per file): DRAM bytes summed over the frame's render launches, the
+    serialised duration of those launches and the L2 throughput share. None when no capture is committed."""
     import glob
-    files = [f for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_ncu_summary.json"))) if "config5" not in f]
+    files = [f for f in sorted(glob.glob(os.path.join(ROOT, "profiles", pattern))) if not any(x in f for x in exclude)]
     if not files:
-        return None, None
+        return None
     d = json.load(open(files[-1]))
-    vals = [l["dram_traffic_B"] for l in d["launches"] if l["kernel"].startswith("wf_")]
-    return (int(sum(vals)) if vals else None), os.path.basename(files[-1])
+    L = [l for l in d["launches"] if l["kernel"].split("<")[0].replace("rtk::", "").startswith(("wf_", "bins_", "accumulate"))]
+    if not L:
+        return None
+    dur = sum(l["duration_us"] or 0 for l in L)
+    return {"file": os.path.basename(files[-1]), "dram_bytes": int(sum(l["dram_traffic_B"] or 0 for l in L)), "serialised_us": round(dur, 1), "launches": len(L),
+            "l2_throughput_pct_time_weighted": round(sum((l["l2_throughput_pct"] or 0) * (l["duration_us"] or 0) for l in L) / dur, 2) if dur else None,
+            "kernel_share": {k: round(sum(l["duration_us"] or 0 for l in L if l["kernel"].split("<")[0].endswith(k)) / dur, 3) for k in ("wf_generate", "wf_leaves", "wf_shade")} if dur else None}
 
 
 def build_scene_host(rt):
@@ -111,9 +122,8 @@ def build_scene_host(rt):
         mesh = rt.Mesh.read_obj(cat).rescale(0.6, (0.0, -4.0, 0.0)).build_bvh()
         name = "cadnav cat (3954 tris, 2019 BVH nodes)"
     else:  # the asset is not redistributable; without it a synthetic mesh of similar size keeps the bench runnable
-        sys.path.insert(0, ROOT)
-        from oracle import scenes
-        v, t = scenes.torus(64, 31)
+        from raytracinggpu_b200 import synthetic
+        v, t = synthetic.torus(64, 31)
         mesh = rt.Mesh.from_arrays(v, t).build_bvh()
         name = "synthetic torus (cat.obj unavailable)"
     walls, mesh_id = rt.default_walls("optimized")
@@ -278,6 +288,8 @@ def run_ours(args):
     # after sharded_single_frame every rank holds the mirror-cat scene: whole 4K depth-4 frames, one per rank at a time
     frames_4k = frame_parallel(rt.params_profile("optimized", 3840, 2160, 1, 4), 6, lambda i: (-10.0, 20.0, 40.0))
     frames_4k["workload"] = "BASELINE.json configs[2] frames (mirror cat 3840x2160, reflection depth 4), whole frames, frame-parallel over the ranks"
+    cfg0, cfg3 = spheres_configs(rt, torch, local, world, rank, flush)
+    cfg4 = config4_ten_million(rt, torch, local, world, rank, flush)
 
     if rank != 0:
         if world > 1:
@@ -289,18 +301,24 @@ def run_ours(args):
     alg_bytes = 32 * (n_mesh_queries + 2 * work["node_visits"]) + 48 * work["tri_tests"] + H * W * 3
     alg_flop = 150 * rays_per_frame + 19 * (n_mesh_queries + 2 * work["node_visits"]) + 50 * work["tri_tests"]
     kernel_ms = float(np.mean(ms_list))
-    peak, peak_src = measured_peaks()
-    traffic, traffic_src = ncu_traffic()
-    achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                "traffic": traffic, "traffic_source": "dram__bytes_read+write summed over the render launches of one frame, profiles/%s" % traffic_src if traffic_src else None, "peak_source": peak_src,
-                "note": "per FRAME (generate + leaves + shade launches; no single dominant kernel). Algorithmic bytes = SURVEY.md 8d: 32 B per box test and 48 B per triangle test of "
-                        "the reference's own traversal (node visits / triangle tests counted by the instrumented tree search). The anchored-ray bins find the same leaves with a "
-                        "quarter of the box tests, so the achieved figure is work the reference algorithm defines divided by the time this path needs (it can exceed the HBM peak: most of those bytes are never moved; measured DRAM traffic is `traffic`); the scene (0.4 MB) is "
-                        "L1/L2-resident and the binding limits are instruction issue (generate) and LSU wavefronts (leaves), see profiles/ and fp32",
-                "algorithmic_bytes_per_launch": int(alg_bytes), "node_visits": int(work["node_visits"]), "tri_tests": int(work["tri_tests"]),
-                "fp32": {"achieved_tflops": round(alg_flop / (kernel_ms * 1e-3) / 1e12, 3), "peak_tflops": round(148 * 128 * 2 * 1.965e9 / 1e12, 1),
-                         "frac": round(alg_flop / (kernel_ms * 1e-3) / (148 * 128 * 2 * 1.965e9), 4)}}
+    hbm_peak, hbm_src = measured_peaks()
+    fma_peak = rt.fma_peak_tflops(local)  # measured on this box, in this run: 8 FMA chains per thread (rt_selftest_fma_peak)
+    ncu = ncu_frame_summary()
+    traffic = ncu["dram_bytes"] if ncu else None
+    achieved_tf = alg_flop / (kernel_ms * 1e-3) / 1e12
+    frame_bytes = H * W * 3
+    roofline = {"bound": "fp32", "achieved": round(achieved_tf, 3), "peak": round(fma_peak, 2), "unit": "TFLOP/s", "frac": round(achieved_tf / fma_peak, 4),
+                "traffic": traffic,
+                "peak_source": "FMA micro-benchmark run by this bench (rt_selftest_fma_peak: 8 independent FFMA chains per thread, best of 5); nominal 148 SMs x 128 lanes x 2 x 1.965 GHz = 74.4",
+                "note": "per FRAME (generate + leaves + shade launches of both row bands; no single dominant kernel). The scene (0.4 MB) is L1/L2-resident: the compulsory HBM traffic is "
+                        "the 6.2 MB frame, so the binding roof is the FP32 pipe / instruction issue (SURVEY.md 8d). Algorithmic FLOP = SURVEY.md 8d's F_ray: 150 per ray (six sphere tests) "
+                        "+ 19 per box test + 50 per triangle test of the reference's own traversal (node visits / triangle tests counted by the instrumented tree search).",
+                "algorithmic_flop_per_frame": int(alg_flop), "algorithmic_bytes_per_frame": int(alg_bytes), "node_visits": int(work["node_visits"]), "tri_tests": int(work["tri_tests"]),
+                "hbm": {"compulsory_bytes": frame_bytes, "measured_dram_bytes": traffic, "traffic_over_compulsory": round(traffic / frame_bytes, 2) if traffic else None,
+                        "achieved_gbs": round(traffic / (kernel_ms * 1e-3) / 1e9, 1) if traffic else None, "peak_gbs": hbm_peak, "peak_source": hbm_src,
+                        "frac": round(traffic / (kernel_ms * 1e-3) / 1e9 / hbm_peak, 4) if traffic else None,
+                        "source": ("ncu --set full --cache-control none, dram__bytes_read+write summed over the render launches of one frame, profiles/%s" % ncu["file"]) if ncu else None},
+                "ncu": ncu}
 
     # ---- CPU baseline: the reference's own classes on this box's host cores (bounded sample) ---------------
     # N = 1 only; torchrun exports OMP_NUM_THREADS=1, so the thread count is passed explicitly
@@ -309,17 +327,200 @@ def run_ours(args):
     out = {"metric": METRIC, "value": round(value, 2), "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": round(ms_per_step, 5), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
            "data": "synthetic",
-           "config": {"workload": "BASELINE.json configs[1]: %s + 6 wall spheres, 1920x1080, 1 spp, primary+shadow rays, optimized.cu knobs" % mesh_name,
+           "config": {"workload": workload_string(mesh_name),
                       "rays_per_frame": rays_per_frame, "frames_per_step_per_gpu": 1, "sharding": "frame-parallel (every rank renders its own frames of this workload)" if world > 1 else "single GPU",
                       "l2": "256 MB memset between steps, outside the event pair", "timed_wall_s": round(wall_s, 4)},
            "e2e": {"value": round(e2e_value, 2), "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": round(e2e_s / e2e_steps * 1e3, 4),
                    "steps": e2e_steps},
            "gpu_launches": launches_per_step * args.steps, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
-           "ms_per_frame": round(kernel_ms, 5), "scene_broadcast_bytes": blob_bytes, "single_frame_sharded": sharded,
-           "animation_light_orbit": animation, "frames_4k_depth4": frames_4k, "bvh_build": bvh_build, "stochastic_vs_reference_gpu_kernel": like_for_like}
+           "ms_per_frame": round(kernel_ms, 5), "scene_broadcast_bytes": blob_bytes,
+           "configs": {"configs0_spheres_800x600": cfg0, "configs2_one_4k_depth4_frame_row_sharded": sharded, "configs3_spheres_animation_240_frames": cfg3,
+                       "configs4_10M_triangles_4k_row_sharded": cfg4},
+           "single_frame_sharded": sharded, "animation_light_orbit": animation, "frames_4k_depth4": frames_4k, "bvh_build": bvh_build,
+           "stochastic_vs_reference_gpu_kernel": like_for_like}
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+def _timed_frames(rt, torch, sc, stream, flush, params, frames, light_of=None, warm=3):
+    """`frames` frames of `params` on this rank, each between its own CUDA-event pair with an L2 flush before it (outside the pair).
+    Returns (sum of ms, rays of the last frame, launches of the last frame)."""
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(frames)]
+    rows = params.row_count if params.row_count > 0 else params.H
+    buf = torch.empty((rows, params.W, 3), dtype=torch.uint8, device="cuda")
+    for i in range(warm + frames):
+        if light_of is not None:
+            sc.set_light(light_of(i), 3e10)
+        with torch.cuda.stream(stream):
+            flush.zero_()
+            if i >= warm:
+                evs[i - warm][0].record(stream)
+            sc.render_into(params, rgb=buf, flags=rt.RT_RENDER_NO_SYNC)
+            if i >= warm:
+                evs[i - warm][1].record(stream)
+        if i == warm - 1:
+            sc.sync()  # end of the warm-up: lets the library enlarge buffers the first frames found too small
+    st = sc.sync()
+    torch.cuda.synchronize()
+    return float(sum(a.elapsed_time(b) for a, b in evs)), int(st.rays), int(st.launches)
+
+
+def _max_over_ranks(torch, world, x):
+    if world == 1:
+        return x
+    import torch.distributed as dist
+    t = torch.tensor([x], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def _sum_over_ranks(torch, world, x):
+    if world == 1:
+        return x
+    import torch.distributed as dist
+    t = torch.tensor([x], device="cuda", dtype=torch.int64)
+    dist.all_reduce(t)
+    return int(t.item())
+
+
+def spheres_configs(rt, torch, local, world, rank, flush):
+    """BASELINE.json configs[0] (spheres scene of cpu_launcher.cpp:668-678 with a point light, ONE 800x600 frame, 1 spp, cpu knobs)
+    and configs[3] (the same scene at 1920x1080, light on a one-revolution orbit, 240 frames, frame f on rank f mod N). The scene has
+    a mirror sphere and a refractive shell, so a path has up to 6 segments (num_bounce 5 in the recursive CPU program). Deterministic
+    mode (sigma 0, no indirect bounce: what the parity tests pin); the CPU reference beside it always bounces (its own getColor)."""
+    from raytracinggpu_b200 import synthetic
+    sc = rt.Scene(local)
+    stream = torch.cuda.Stream()
+    sc.set_stream(stream.cuda_stream)
+    sc.set_spheres(synthetic.spheres_scene_spheres(rt))
+    sc.set_light((-10.0, 20.0, 40.0), 3e10)
+    # configs[0]: every rank renders the same single frame (it does not shard: 0.48 Mpx); rank 0's numbers are reported
+    p0 = rt.params_profile("cpu", 800, 600, 1, 5)
+    ms0, rays0, l0 = _timed_frames(rt, torch, sc, stream, flush, p0, 20)
+    host = torch.empty((600, 800, 3), dtype=torch.uint8).pin_memory()
+    sc.render_into(p0, rgb=host.numpy())
+    t0 = time.perf_counter()
+    for _ in range(10):
+        sc.render_into(p0, rgb=host.numpy())
+    e2e0 = (time.perf_counter() - t0) / 10 * 1e3
+    cfg0 = {"workload": "BASELINE.json configs[0]: spheres scene (6 walls + white / mirror / refractive-shell spheres) with point light, 800x600, 1 spp, cpu_launcher.cpp knobs, up to 6 path segments",
+            "ms_per_frame": round(ms0 / 20, 5), "rays_per_frame": rays0, "mrays_per_s": round(rays0 * 20 / (ms0 * 1e-3) / 1e6, 1), "launches_per_frame": l0,
+            "e2e_ms_per_frame_host_buffers": round(e2e0, 4), "n_gpus_used": 1}
+    # configs[3]: 240 frames over the ranks
+    total_frames = 240
+    omega = 2 * np.pi / (total_frames * 0.02)
+    orbit = rt.sharding.light_positions((-10.0, 20.0, 40.0), total_frames, omega, 0.02, rt.move_light)
+    mine = rt.sharding.frames_for_rank(total_frames, rank, world)
+    p3 = rt.params_profile("cpu", W, H, 1, 5)
+    ms3, rays3, l3 = _timed_frames(rt, torch, sc, stream, flush, p3, len(mine), light_of=lambda i: orbit[mine[max(i - 3, 0)]])
+    ms3_max = _max_over_ranks(torch, world, ms3)
+    rays_total = _sum_over_ranks(torch, world, rays3 * len(mine))
+    cfg3 = {"workload": "BASELINE.json configs[3]: circulating-light spheres animation, 240 frames at 1920x1080, frame f on rank f mod N (no data-path collective)",
+            "frames": total_frames, "frames_per_gpu": len(mine), "ms_total_max_over_ranks": round(ms3_max, 3), "ms_per_frame_per_gpu": round(ms3 / max(len(mine), 1), 5),
+            "frames_per_s": round(total_frames / (ms3_max * 1e-3), 1), "rays_per_frame": rays3, "mrays_per_s": round(rays_total / (ms3_max * 1e-3) / 1e6, 1),
+            "launches_per_frame": l3, "scaling": "strong (240 frames whatever N)"}
+    if rank == 0 and world == 1:
+        try:  # the reference's own CPU classes on the same scene, bounded sample (oracle/_ref/libref_cpu.so, scene kind 2)
+            from oracle import pyoracle
+            if pyoracle.ref_cpu_available():
+                th = os.cpu_count() or 1
+                pyoracle.ref_cpu_set_light((-10.0, 20.0, 40.0))
+                pyoracle.ref_cpu_render("", 2, 200, 150, 1, 5, th, hits=False)
+                r0 = [pyoracle.ref_cpu_render("", 2, 800, 600, 1, 5, th, hits=False)["seconds"] for _ in range(5)]
+                r3 = [pyoracle.ref_cpu_render("", 2, W, H, 1, 5, th, hits=False)["seconds"] for _ in range(3)]
+                cfg0["cpu_reference"] = {"ms_per_frame": round(float(np.median(r0)) * 1e3, 2), "cores": th, "kind": "reference",
+                                         "sample": "5 frames by cpu_launcher.cpp's classes (its getColor also takes the random indirect bounce)"}
+                cfg3["cpu_reference"] = {"ms_per_frame": round(float(np.median(r3)) * 1e3, 2), "cores": th, "kind": "reference", "sample": "3 of the 240 frames"}
+        except Exception as e:  # noqa: BLE001
+            cfg0["cpu_reference"] = {"unavailable": repr(e)[:200]}
+    sc.close()
+    return cfg0, cfg3
+
+
+def config4_ten_million(rt, torch, local, world, rank, flush):
+    """BASELINE.json configs[4]: the cat instanced to 9,999,666 triangles (2,529 baked copies, raytracinggpu_b200.synthetic), 3840x2160,
+    primary + shadow rays. The scene is built on rank 0 only (device BVH builder + upload), packed, broadcast ONCE, and every rank
+    renders the rows r, r + N, ...; the bands go into rank 0's frame over NVLink (FramePush). The only scene that does not fit the
+    126 MB L2 (0.85 GB blob): its roofline is HBM, stated from MEASURED DRAM bytes (committed ncu capture of this frame)."""
+    import torch.distributed as dist
+    from raytracinggpu_b200 import distributed as rtd, synthetic
+    cat = find_cat()
+    if not cat:
+        return {"unavailable": "cat.obj not on this box"}
+    W4, H4 = 3840, 2160
+    sc = rt.Scene(local)
+    stream = torch.cuda.Stream()
+    sc.set_stream(stream.cuda_stream)
+    build = {}
+    if rank == 0:
+        t0 = time.perf_counter()
+        scales, offs = synthetic.instance_lattice()
+        mesh = rt.Mesh.read_obj(cat).instance(scales, offs)
+        t1 = time.perf_counter()
+        mesh.build_bvh_gpu(local)
+        t2 = time.perf_counter()
+        walls, mesh_id = rt.default_walls("optimized")
+        sc.set_spheres(walls)
+        sc.set_mesh(mesh.vertices, mesh.tri_records, mesh.arr_bvh, id=mesh_id)
+        sc.sync()
+        torch.cuda.synchronize()
+        t3 = time.perf_counter()
+        nv, nt, nn = mesh.counts()
+        build = {"triangles": nt, "bvh_nodes": nn, "instance_ms": round((t1 - t0) * 1e3, 1), "bvh_build_wall_ms": round((t2 - t1) * 1e3, 1),
+                 "bvh_build_device_ms": round(mesh.build_ms, 2), "upload_and_repack_ms": round((t3 - t2) * 1e3, 1)}
+        del mesh
+    bcast_ms, blob = 0.0, sc.blob_size() if rank == 0 else 0
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        blob = rtd.broadcast_scene(sc, src=0)
+        torch.cuda.synchronize()
+        dist.barrier()
+        bcast_ms = (time.perf_counter() - t0) * 1e3
+    p = rt.params_profile("optimized", W4, H4, 1, 1)
+    frames = 6
+    out = {"workload": "BASELINE.json configs[4]: cat instanced to 9,999,666 triangles, 3840x2160, primary + shadow rays, BVH built on rank 0 and broadcast once, rows interleaved over %d GPU(s)" % world,
+           "build_on_rank0": build, "scene_blob_bytes": int(blob), "scene_broadcast_ms": round(bcast_ms, 2),
+           "scene_broadcast_gbs": round(blob / (bcast_ms * 1e-3) / 1e9, 1) if bcast_ms > 0 else None, "scaling": "strong"}
+    if world == 1:
+        ms, rays, launches = _timed_frames(rt, torch, sc, stream, flush, p, frames, warm=2)
+        out.update({"ms_per_frame": round(ms / frames, 4), "rays_per_frame": rays, "mrays_per_s": round(rays * frames / (ms * 1e-3) / 1e6, 1), "launches_per_frame": launches})
+    else:
+        fp = rtd.FramePush(sc, H4, W4, world, rank, torch.device("cuda", local))
+        pp = fp.apply(p)
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(frames)]
+        rays = 0
+        for i in range(2 + frames):
+            dist.barrier()
+            with torch.cuda.stream(stream):
+                k = i - 2
+                flush.zero_()
+                if k >= 0:
+                    ev[k][0].record(stream)
+                sc.render_into(pp, rgb=fp.band, flags=rt.RT_RENDER_NO_SYNC)
+                if k >= 0:
+                    ev[k][1].record(stream)
+                fp.push()
+                if k >= 0:
+                    ev[k][2].record(stream)
+            rays = int(sc.sync().rays)
+        torch.cuda.synchronize()
+        tot = _max_over_ranks(torch, world, float(sum(a.elapsed_time(c) for a, _, c in ev)))
+        ren = _max_over_ranks(torch, world, float(sum(a.elapsed_time(b) for a, b, _ in ev)))
+        rays_all = _sum_over_ranks(torch, world, rays)
+        fp.close()
+        out.update({"ms_per_frame": round(tot / frames, 4), "render_ms": round(ren / frames, 4), "push_and_barrier_ms": round((tot - ren) / frames, 4),
+                    "rays_per_frame": rays_all, "mrays_per_s": round(rays_all * frames / (tot * 1e-3) / 1e6, 1)})
+    ncu = ncu_frame_summary("*config4*ncu*.json", exclude=()) or ncu_frame_summary("*config5*ncu*.json", exclude=())
+    if ncu and "ms_per_frame" in out and world == 1:
+        hbm_peak, hbm_src = measured_peaks()
+        gbs = ncu["dram_bytes"] / (out["ms_per_frame"] * 1e-3) / 1e9
+        out["roofline"] = {"bound": "hbm", "achieved": round(gbs, 1), "peak": hbm_peak, "unit": "GB/s", "frac": round(gbs / hbm_peak, 4), "traffic": ncu["dram_bytes"],
+                           "peak_source": hbm_src, "note": "MEASURED DRAM bytes of one frame (profiles/%s) over this run's frame time: the tree search of this scene is L2-latency / issue bound, not HBM bound" % ncu["file"]}
+    sc.close()
+    return out
 
 
 def stochastic_vs_reference_kernel(rt, torch, sc):
@@ -335,6 +536,7 @@ def stochastic_vs_reference_kernel(rt, torch, sc):
     for rays, bounce in ((1, 1), (4, 3)):
         p = rt.params_profile("optimized", W, H, rays, bounce)
         p.aa_sigma, p.indirect = 0.2, 1
+        p.z = rt.camera_z_device(W)  # optimized.cu evaluates z inside the kernel (rt_camera_z_device)
         rgb = torch.empty((H, W, 3), dtype=torch.uint8, device="cuda")
         ms = []
         for i in range(8):
@@ -491,8 +693,8 @@ def run_reference(args):
     out = {"impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": round(total / args.steps * 1e3, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
            "data": "synthetic",
-           "config": {"workload": "BASELINE.json configs[1]: cat + 6 wall spheres, 1920x1080, 1 spp, primary+shadow rays; each step = one full frame on the host CPU",
-                      "rays_per_frame": rays, "wall_s": round(wall, 3)},
+           "config": {"workload": workload_string("cadnav cat (3954 tris, 2019 BVH nodes)" if cat else "synthetic torus (cat.obj unavailable)"),
+                      "arm": "each step = one full frame on the host CPU (cpu_launcher.cpp's classes, OpenMP over rows)", "rays_per_frame": rays, "wall_s": round(wall, 3)},
            "cpu_baseline": {"value": round(value, 3), "unit": "Mrays/s", "cores": cores, "kind": kind,
                             "sample": "%d full 1920x1080 frames, render loop only (cpu_launcher.cpp:695-718), OpenMP over rows" % args.steps},
            "e2e": {"value": round(value, 3), "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

@@ -289,6 +289,9 @@ int rt_selftest_division(int device, uint64_t seed, int blocks, int per_thread, 
  * (n*4 floats) of the listed subsequences — the random stream of optimized.cu:745 that the stochastic mode reproduces. */
 int rt_selftest_xorwow(int device, uint64_t seed, const uint32_t* subsequences, int32_t n, uint32_t* states6, float* uniforms4);
 
+/* Device self-test / measurement: the FP32 FMA throughput of the device in TFLOP/s (8 independent FMA chains per thread, best of
+ * `reps` event-timed launches): the measured FP32 roof bench.py reports the render path against. */
+int rt_selftest_fma_peak(int device, int reps, double* tflops);
 /* Device self-test: CUDA's single-precision logf (which = 0) / sinf (1) / cosf (2) / tanf (3) on n host arguments — the functions
  * option "transcendentals" = 1 and rt_camera_z_device evaluate (optimized.cu:749, 756-758, 635-636 call them in the kernel). */
 int rt_selftest_libm(int device, int which, const float* x, int32_t n, float* y);

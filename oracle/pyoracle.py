@@ -305,6 +305,14 @@ def ref_cpu_render(obj_path, scene_kind, W, H, num_rays, num_bounce, threads=0, 
     return {"rgb": rgb, "hit_obj": obj, "P": P, "N": N, "seconds": sec.value}
 
 
+def ref_cpu_set_light(L):
+    """Scene::L of the scenes the following ref_cpu_render calls build."""
+    R = ref_lib()
+    R.ref_cpu_set_light.argtypes = [C.c_float, C.c_float, C.c_float]
+    R.ref_cpu_set_light.restype = None
+    R.ref_cpu_set_light(float(L[0]), float(L[1]), float(L[2]))
+
+
 def ref_cpu_mesh(obj_path, scene_kind):
     R = ref_lib()
     vals = [C.c_int() for _ in range(6)]

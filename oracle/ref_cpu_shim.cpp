@@ -21,7 +21,12 @@ struct Built {
 	TriangleMesh* mesh = nullptr;
 };
 
-/* scene_kind 0: cpu_launcher.cpp:673-685 (walls 0-5, cat 6, no rescale)
+float g_light[3] = {-10.f, 20.f, 40.f}; /* ref_cpu_set_light: Scene::L of the next scenes (cpu_launcher.cpp:650) */
+
+/* scene_kind 2: BASELINE.json configs[0] / configs[3] — the six walls + the demo spheres of the commented lines
+ *               cpu_launcher.cpp:668-672 (white diffuse, mirror, refractive shell = inner R 9 inside outer R 10), no mesh;
+ *               ids as oracle/scenes.py:spheres_scene gives them (walls 0-5, then the four spheres)
+ * scene_kind 0: cpu_launcher.cpp:673-685 (walls 0-5, cat 6, no rescale)
  * scene_kind 1: the object order and mesh transform of optimized.cu:684-726,804 (wall 0, cat 1, walls 2-6,
  *               rescale 0.6 / (0,-4,0)) built from cpu_launcher.cpp's classes. */
 void build_scene(Built& b, const char* obj_path, int scene_kind) {
@@ -45,7 +50,14 @@ void build_scene(Built& b, const char* obj_path, int scene_kind) {
 		mesh->buildBVH(&(mesh->bvh), 0, mesh->indices.size());
 	}
 	b.mesh = mesh;
-	if (scene_kind == 1) {
+	b.scene.L = Vector(g_light[0], g_light[1], g_light[2]);
+	if (scene_kind == 2) {
+		for (int k = 0; k < 6; k++) b.scene.addObject(walls[k]);
+		b.scene.addObject(new Sphere(Vector(0, 0, 0), 10, Vector(1., 1., 1.)));
+		b.scene.addObject(new Sphere(Vector(-20, 0, 0), 10, Vector(0., 0., 0.), 1));
+		b.scene.addObject(new Sphere(Vector(20, 0, 0), 9, Vector(0., 0., 0.), 0, 1, 1.5));
+		b.scene.addObject(new Sphere(Vector(20, 0, 0), 10, Vector(0., 0., 0.), 0, 1.5, 1));
+	} else if (scene_kind == 1) {
 		b.scene.addObject(walls[0]);
 		if (mesh) b.scene.addObject(mesh);
 		for (int k = 1; k < 6; k++) b.scene.addObject(walls[k]);
@@ -87,6 +99,13 @@ void dump_nodes(const BVH* n, float* arr, int& next, int idx) {
 } // namespace
 
 extern "C" {
+
+/* Scene::L of the scenes built from now on (the light orbit of BASELINE.json configs[3]). */
+void ref_cpu_set_light(float x, float y, float z) {
+	g_light[0] = x;
+	g_light[1] = y;
+	g_light[2] = z;
+}
 
 /* Render with the reference's classes. rgb: H*W*3; obj_id: H*W primary-ray object id; P_out/N_out: H*W*3
  * primary hit point / normal as intersect_all returns them. Any output may be NULL. seconds = render loop only. */

@@ -79,6 +79,7 @@ SIGNATURES = {
     "rt_comm_rank": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "rt_scene_broadcast": (C.c_int, [_vp, _vp, C.c_int, C.POINTER(C.c_size_t)]),
     "rt_gather_framebuffer": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, C.c_int]),
+    "rt_selftest_fma_peak": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "rt_selftest_libm": (C.c_int, [C.c_int, C.c_int, _vp, _i32, _vp]),
     "rt_selftest_division": (C.c_int, [C.c_int, _u64, C.c_int, C.c_int, C.POINTER(_u64)]),
     "rt_selftest_xorwow": (C.c_int, [C.c_int, _u64, _vp, C.c_int32, _vp, _vp]),
@@ -476,6 +477,13 @@ def comm_available():
     v = C.c_int()
     rc = lib().rt_comm_available(C.byref(v))
     return v.value if rc == RT_OK else 0
+
+
+def fma_peak_tflops(device=0, reps=5):
+    """Measured FP32 FMA throughput of the device (TFLOP/s)."""
+    v = C.c_double()
+    _check(lib().rt_selftest_fma_peak(int(device), int(reps), C.byref(v)))
+    return v.value
 
 
 def selftest_libm(which, x, device=0):

@@ -1621,6 +1621,7 @@ int enqueue_frame(rt_scene* s, const FramePlan& P, int& launches, bool& strip_co
         g.a.hit_tri = a.hit_tri ? a.hit_tri + px0 : nullptr;
         g.a.hit_t = a.hit_t ? a.hit_t + px0 : nullptr;
         g.a.shadow = a.shadow ? a.shadow + px0 : nullptr;
+        g.a.linear = a.linear ? a.linear + px0 : nullptr;
         g.qA[0] = s->wf_queue + px0;
         g.qA[1] = s->wf_queue + s->wf_capacity + px0;
         g.qS = s->wf_queue + 2 * s->wf_capacity + px0;
@@ -1988,6 +1989,56 @@ int rt_camera_z_device(int device, int32_t W, float alpha, float* z) {
     cudaError_t e = cudaMemcpy(z, d, sizeof(float), cudaMemcpyDeviceToHost);
     cudaFree(d);
     if (e != cudaSuccess) return rtb::fail(RT_ERR_CUDA, "rt_camera_z_device: %s", cudaGetErrorString(e));
+    return RT_OK;
+}
+
+/* FP32 roof of the device, measured (SURVEY.md 8d asks for an FMA micro-benchmark instead of the nominal SMs x 128 x 2 x clock):
+ * every thread runs 8 independent FMA chains; 2 flop per FMA. Best of `reps` launches, CUDA-event timed. */
+__global__ void __launch_bounds__(256) fma_peak_kernel(float* __restrict__ out, int iters, float b, float c) {
+    float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f, a4 = a0 + 4.f, a5 = a0 + 5.f, a6 = a0 + 6.f, a7 = a0 + 7.f;
+#pragma unroll 8
+    for (int i = 0; i < iters; i++) {
+        a0 = __fmaf_rn(a0, b, c);
+        a1 = __fmaf_rn(a1, b, c);
+        a2 = __fmaf_rn(a2, b, c);
+        a3 = __fmaf_rn(a3, b, c);
+        a4 = __fmaf_rn(a4, b, c);
+        a5 = __fmaf_rn(a5, b, c);
+        a6 = __fmaf_rn(a6, b, c);
+        a7 = __fmaf_rn(a7, b, c);
+    }
+    const float r = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    if (r == 12345.678f) out[blockIdx.x * blockDim.x + threadIdx.x] = r; /* keeps the chains alive; practically never true */
+}
+
+int rt_selftest_fma_peak(int device, int reps, double* tflops) {
+    if (!tflops || reps < 1) return rtb::fail(RT_ERR_INVALID, "rt_selftest_fma_peak: bad argument");
+    DeviceGuard g(device);
+    if (!g.ok) return rtb::fail(RT_ERR_CUDA, "rt_selftest_fma_peak: no device %d", device);
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 15;
+    float* d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, (size_t)blocks * threads * sizeof(float)));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    double best = 0.;
+    cudaError_t e = cudaSuccess;
+    for (int r = 0; r < reps + 1 && e == cudaSuccess; r++) {
+        cudaEventRecord(e0);
+        fma_peak_kernel<<<blocks, threads>>>(d, iters, 0.999f, 0.25f);
+        cudaEventRecord(e1);
+        e = cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (r > 0 && ms > 0.f) best = std::max(best, 2.0 * 8.0 * iters * (double)blocks * threads / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    if (e != cudaSuccess) return rtb::fail(RT_ERR_CUDA, "rt_selftest_fma_peak: %s", cudaGetErrorString(e));
+    *tflops = best;
     return RT_OK;
 }
 

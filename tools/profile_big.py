@@ -6,9 +6,11 @@ import raytracinggpu_b200 as rt
 from raytracinggpu_b200 import synthetic
 from oracle import profiles, scenes, pyoracle
 scales, offs = synthetic.instance_lattice()
-mesh = rt.Mesh.read_obj(pyoracle.cat_obj_path()).instance(scales, offs).build_bvh()
+mesh = rt.Mesh.read_obj(pyoracle.cat_obj_path()).instance(scales, offs).build_bvh_gpu(0)
 desc = dict(spheres=profiles.walls("optimized"), mesh=(mesh.vertices, mesh.tri_records, mesh.arr_bvh), mesh_mat=profiles.mesh_material("optimized", 0), light=profiles.LIGHT)
-sc = scenes.upload(rt.Scene(0), desc)
+sc = rt.Scene(0)
+sc.set_option("graph", 0)  # ncu: plain launches
+scenes.upload(sc, desc)
 p = profiles.params("optimized", 3840, 2160, 1, 1)
 rgb = torch.empty((2160, 3840, 3), dtype=torch.uint8, device="cuda")
 for i in range(int(sys.argv[1]) if len(sys.argv) > 1 else 3):

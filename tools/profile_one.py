@@ -11,6 +11,7 @@ Wd = int(sys.argv[2]) if len(sys.argv) > 2 else 1920
 Hd = int(sys.argv[3]) if len(sys.argv) > 3 else 1080
 mesh, walls, mesh_id, name = bench.build_scene_host(rt)
 sc = rt.Scene(0)
+sc.set_option("graph", 0)  # ncu: plain launches, one per kernel
 sc.set_spheres(walls)
 sc.set_mesh(mesh.vertices, mesh.tri_records, mesh.arr_bvh, id=mesh_id)
 p = rt.params_profile("optimized", Wd, Hd, 1, 1)
