@@ -55,6 +55,7 @@ struct RtOptions {
                               * restates the functions for the CPU (rt_oracle.cpp: cuda_logf ...); 0 evaluated in double and rounded once
                               * (the oracle's other canon: what a correctly rounded libm would give; 3-4x the instructions) */
     int graph = 1;           /* replay a recorded CUDA graph when a frame repeats the previous call's plan */
+    int pdl = 1;             /* programmatic dependent launch between consecutive kernels of a band (LaunchChain) */
     int debug_times = 0, debug_pool = 0, debug_bins = 0, debug_cost = 0;
     char debug_warps[256] = {0}; /* RT_DEBUG_WARPS=<file> at scene creation: per-warp timeline of wf_traverse (count_work renders) */
 };
@@ -81,6 +82,7 @@ static const RtOptionKey kOptionKeys[] = {
     {"leaves_blocks", &RtOptions::leaves_blocks, 0, 32},
     {"transcendentals", &RtOptions::transcendentals, 0, 1},
     {"graph", &RtOptions::graph, 0, 1},
+    {"pdl", &RtOptions::pdl, 0, 1},
     {"debug_times", &RtOptions::debug_times, 0, 1},
     {"debug_pool", &RtOptions::debug_pool, 0, 1},
     {"debug_bins", &RtOptions::debug_bins, 0, 1},
@@ -1574,6 +1576,43 @@ int plan_frame(rt_scene* s, const rt_params* p, uint32_t flags, void* const user
     return RT_OK;
 }
 
+/* Kernel launches of a frame with programmatic dependent launch (PDL) between consecutive kernels of one stream: the next kernel's
+ * blocks are placed while the previous kernel's last blocks still run and wait in griddepcontrol.wait (first statement of every wf_*
+ * kernel) until it has completed — the launch and ramp-up of the 8-30 small kernels of a frame overlap the tails of their predecessors.
+ * Only a kernel whose immediate predecessor on its stream is a kernel gets the attribute; any other operation (memset, event, copy)
+ * breaks the chain. Option "pdl" = 0: plain launches. */
+struct LaunchChain {
+    cudaStream_t st[2 * RT_MAX_STRIPS + 2];
+    bool after_kernel[2 * RT_MAX_STRIPS + 2];
+    int n = 0;
+    bool enabled = true;
+    bool& of(cudaStream_t x) {
+        for (int k = 0; k < n; k++)
+            if (st[k] == x) return after_kernel[k];
+        st[n] = x;
+        after_kernel[n] = false;
+        return after_kernel[n++];
+    }
+    void broke(cudaStream_t x) { of(x) = false; }
+    template <typename... KArgs, typename... Args>
+    cudaError_t launch(void (*kernel)(KArgs...), dim3 grid, unsigned block, size_t smem, cudaStream_t stream, Args&&... args) {
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof cfg);
+        cfg.gridDim = grid;
+        cfg.blockDim = dim3(block);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        bool& prev = of(stream);
+        cfg.attrs = at;
+        cfg.numAttrs = (enabled && prev) ? 1 : 0;
+        prev = true;
+        return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+    }
+};
+
 /* ---- rt_render, second half: the launches of one frame, nothing else (no allocation, no synchronisation, no host read-back):
  * the sequence is the same for every frame with the same plan, so it can be recorded once into a CUDA graph and replayed. */
 int enqueue_frame(rt_scene* s, const FramePlan& P, int& launches, bool& strip_copied) {
@@ -1589,6 +1628,8 @@ int enqueue_frame(rt_scene* s, const FramePlan& P, int& launches, bool& strip_co
     void* const* user = P.user;
     void* const* dev = P.dev;
     const bool* copy_back = P.copy_back;
+    LaunchChain chain;
+    chain.enabled = s->opt.pdl != 0 && !P.count && !P.dbg_times;
     if (variant == 2) {
         if (P.dbg_ints) CUDA_TRY(cudaMemsetAsync(s->dbg_warps, 0, P.dbg_ints * sizeof(int), s->stream));
         /* queue cursors and work statistics restart with every frame; the overflow flags live elsewhere (rt_scene::sticky) */
@@ -1612,6 +1653,7 @@ int enqueue_frame(rt_scene* s, const FramePlan& P, int& launches, bool& strip_co
         const size_t spx = (size_t)srows * p->W, px0 = (size_t)row0 * p->W;
         cudaStream_t stream = n_strips > 1 ? s->strip_stream[st] : s->stream;
         if (n_strips > 1) CUDA_TRY(cudaStreamWaitEvent(stream, s->fork_ev, 0));
+        chain.broke(stream);
         rtk::WfArgs g;
         g.a = a;
         g.a.rows = srows;
@@ -1681,15 +1723,16 @@ int enqueue_frame(rt_scene* s, const FramePlan& P, int& launches, bool& strip_co
             if (pass > 0) /* the queue counters restart with every pass; the work statistics keep adding up */
                 CUDA_TRY(cudaMemsetAsync(reinterpret_cast<unsigned char*>(s->wf_counters + st) + offsetof(rtk::WfCounters, nA), 0,
                                          sizeof(rtk::WfCounters) - offsetof(rtk::WfCounters, nA), stream));
+                chain.broke(stream);
             if (stochastic) {
-                if (count) rtk::wf_generate<true, true><<<gen_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
-                else if (diffuse_only) rtk::wf_generate<false, true, true><<<gen_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
-                else rtk::wf_generate<false, true><<<gen_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
+                if (count) CUDA_TRY(chain.launch(rtk::wf_generate<true, true>, dim3(gen_grid), WF_THREADS, 0, stream, s->header, s->blob, g));
+                else if (diffuse_only) CUDA_TRY(chain.launch(rtk::wf_generate<false, true, true>, dim3(gen_grid), WF_THREADS, 0, stream, s->header, s->blob, g));
+                else CUDA_TRY(chain.launch(rtk::wf_generate<false, true>, dim3(gen_grid), WF_THREADS, 0, stream, s->header, s->blob, g));
             } else {
-                if (count) rtk::wf_generate<true, false><<<gen_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
-                else if (diffuse_only && anchored) rtk::wf_generate<false, false, true, true><<<gen_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
-                else if (diffuse_only) rtk::wf_generate<false, false, true><<<gen_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
-                else rtk::wf_generate<false, false><<<gen_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
+                if (count) CUDA_TRY(chain.launch(rtk::wf_generate<true, false>, dim3(gen_grid), WF_THREADS, 0, stream, s->header, s->blob, g));
+                else if (diffuse_only && anchored) CUDA_TRY(chain.launch(rtk::wf_generate<false, false, true, true>, dim3(gen_grid), WF_THREADS, 0, stream, s->header, s->blob, g));
+                else if (diffuse_only) CUDA_TRY(chain.launch(rtk::wf_generate<false, false, true>, dim3(gen_grid), WF_THREADS, 0, stream, s->header, s->blob, g));
+                else CUDA_TRY(chain.launch(rtk::wf_generate<false, false>, dim3(gen_grid), WF_THREADS, 0, stream, s->header, s->blob, g));
             }
             launches++;
             mark();
@@ -1707,53 +1750,57 @@ int enqueue_frame(rt_scene* s, const FramePlan& P, int& launches, bool& strip_co
                     cudaStream_t tstream = side ? s->side_stream[st] : stream;
                     if (side) {
                         CUDA_TRY(cudaEventRecord(s->side_fork[st], stream));
+                        chain.broke(stream);
                         CUDA_TRY(cudaStreamWaitEvent(tstream, s->side_fork[st], 0));
+                        chain.broke(tstream);
                     }
                     if (trav_now) {
                         if (stochastic) {
-                            if (wide) rtk::wf_traverse<false, true, true><<<pers_grid, WF_THREADS, trav_smem, tstream>>>(s->header, s->blob, g, npool_cap);
-                            else rtk::wf_traverse<false, true, false><<<pers_grid, WF_THREADS, trav_smem, tstream>>>(s->header, s->blob, g, npool_cap);
+                            if (wide) CUDA_TRY(chain.launch(rtk::wf_traverse<false, true, true>, dim3(pers_grid), WF_THREADS, trav_smem, tstream, s->header, s->blob, g, npool_cap));
+                            else CUDA_TRY(chain.launch(rtk::wf_traverse<false, true, false>, dim3(pers_grid), WF_THREADS, trav_smem, tstream, s->header, s->blob, g, npool_cap));
                         } else {
-                            if (wide) rtk::wf_traverse<false, false, true><<<pers_grid, WF_THREADS, trav_smem, tstream>>>(s->header, s->blob, g, npool_cap);
-                            else rtk::wf_traverse<false, false, false><<<pers_grid, WF_THREADS, trav_smem, tstream>>>(s->header, s->blob, g, npool_cap);
+                            if (wide) CUDA_TRY(chain.launch(rtk::wf_traverse<false, false, true>, dim3(pers_grid), WF_THREADS, trav_smem, tstream, s->header, s->blob, g, npool_cap));
+                            else CUDA_TRY(chain.launch(rtk::wf_traverse<false, false, false>, dim3(pers_grid), WF_THREADS, trav_smem, tstream, s->header, s->blob, g, npool_cap));
                         }
                         launches++;
                         mark();
                     }
-                    if (stochastic) rtk::wf_leaves<true><<<leaves_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
-                    else rtk::wf_leaves<false><<<leaves_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
+                    if (stochastic) CUDA_TRY(chain.launch(rtk::wf_leaves<true>, dim3(leaves_grid), WF_THREADS, 0, stream, s->header, s->blob, g));
+                    else CUDA_TRY(chain.launch(rtk::wf_leaves<false>, dim3(leaves_grid), WF_THREADS, 0, stream, s->header, s->blob, g));
                     if (side) { /* join: wf_shade needs both */
                         CUDA_TRY(cudaEventRecord(s->side_join[st], tstream));
+                        chain.broke(tstream);
                         CUDA_TRY(cudaStreamWaitEvent(stream, s->side_join[st], 0));
+                        chain.broke(stream);
                     }
                 } else if (stochastic) {
-                    if (count) rtk::wf_traverse<true, true, false><<<pers_grid, WF_THREADS, trav_smem, stream>>>(s->header, s->blob, g, npool_cap);
-                    else if (wide) rtk::wf_traverse<false, true, true><<<pers_grid, WF_THREADS, trav_smem, stream>>>(s->header, s->blob, g, npool_cap);
-                    else rtk::wf_traverse<false, true, false><<<pers_grid, WF_THREADS, trav_smem, stream>>>(s->header, s->blob, g, npool_cap);
+                    if (count) CUDA_TRY(chain.launch(rtk::wf_traverse<true, true, false>, dim3(pers_grid), WF_THREADS, trav_smem, stream, s->header, s->blob, g, npool_cap));
+                    else if (wide) CUDA_TRY(chain.launch(rtk::wf_traverse<false, true, true>, dim3(pers_grid), WF_THREADS, trav_smem, stream, s->header, s->blob, g, npool_cap));
+                    else CUDA_TRY(chain.launch(rtk::wf_traverse<false, true, false>, dim3(pers_grid), WF_THREADS, trav_smem, stream, s->header, s->blob, g, npool_cap));
                 } else {
-                    if (count && wide) rtk::wf_traverse<true, false, true><<<pers_grid, WF_THREADS, trav_smem, stream>>>(s->header, s->blob, g, npool_cap);
-                    else if (count) rtk::wf_traverse<true, false, false><<<pers_grid, WF_THREADS, trav_smem, stream>>>(s->header, s->blob, g, npool_cap);
-                    else if (wide) rtk::wf_traverse<false, false, true><<<pers_grid, WF_THREADS, trav_smem, stream>>>(s->header, s->blob, g, npool_cap);
-                    else rtk::wf_traverse<false, false, false><<<pers_grid, WF_THREADS, trav_smem, stream>>>(s->header, s->blob, g, npool_cap);
+                    if (count && wide) CUDA_TRY(chain.launch(rtk::wf_traverse<true, false, true>, dim3(pers_grid), WF_THREADS, trav_smem, stream, s->header, s->blob, g, npool_cap));
+                    else if (count) CUDA_TRY(chain.launch(rtk::wf_traverse<true, false, false>, dim3(pers_grid), WF_THREADS, trav_smem, stream, s->header, s->blob, g, npool_cap));
+                    else if (wide) CUDA_TRY(chain.launch(rtk::wf_traverse<false, false, true>, dim3(pers_grid), WF_THREADS, trav_smem, stream, s->header, s->blob, g, npool_cap));
+                    else CUDA_TRY(chain.launch(rtk::wf_traverse<false, false, false>, dim3(pers_grid), WF_THREADS, trav_smem, stream, s->header, s->blob, g, npool_cap));
                 }
                 launches++;
                 mark();
                 if (r == segments) break;
                 if (stochastic) {
-                    if (count) rtk::wf_shade<true, true><<<shade_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
-                    else if (diffuse_only) rtk::wf_shade<false, true, true><<<shade_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
-                    else rtk::wf_shade<false, true><<<shade_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
+                    if (count) CUDA_TRY(chain.launch(rtk::wf_shade<true, true>, dim3(shade_grid), WF_THREADS, 0, stream, s->header, s->blob, g));
+                    else if (diffuse_only) CUDA_TRY(chain.launch(rtk::wf_shade<false, true, true>, dim3(shade_grid), WF_THREADS, 0, stream, s->header, s->blob, g));
+                    else CUDA_TRY(chain.launch(rtk::wf_shade<false, true>, dim3(shade_grid), WF_THREADS, 0, stream, s->header, s->blob, g));
                 } else {
-                    if (count) rtk::wf_shade<true, false><<<shade_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
-                    else if (diffuse_only && anchored) rtk::wf_shade<false, false, true, true><<<shade_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
-                    else if (diffuse_only) rtk::wf_shade<false, false, true><<<shade_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
-                    else rtk::wf_shade<false, false><<<shade_grid, WF_THREADS, 0, stream>>>(s->header, s->blob, g);
+                    if (count) CUDA_TRY(chain.launch(rtk::wf_shade<true, false>, dim3(shade_grid), WF_THREADS, 0, stream, s->header, s->blob, g));
+                    else if (diffuse_only && anchored) CUDA_TRY(chain.launch(rtk::wf_shade<false, false, true, true>, dim3(shade_grid), WF_THREADS, 0, stream, s->header, s->blob, g));
+                    else if (diffuse_only) CUDA_TRY(chain.launch(rtk::wf_shade<false, false, true>, dim3(shade_grid), WF_THREADS, 0, stream, s->header, s->blob, g));
+                    else CUDA_TRY(chain.launch(rtk::wf_shade<false, false>, dim3(shade_grid), WF_THREADS, 0, stream, s->header, s->blob, g));
                 }
                 launches++;
                 mark();
             }
             if (stochastic) {
-                rtk::wf_fold<<<(unsigned)((spx + 255) / 256), 256, 0, stream>>>(g);
+                CUDA_TRY(chain.launch(rtk::wf_fold, dim3((unsigned)((spx + 255) / 256)), 256, 0, stream, g));
                 launches++;
                 mark();
             }

@@ -31,6 +31,14 @@
 
 namespace rtk {
 
+/* Programmatic dependent launch (rt_device.cu: LaunchChain): first statement of every kernel of the pipeline. Waits until the kernel
+ * this one was launched behind has completed and its writes are visible (a no-op for a plain launch), then lets the NEXT kernel of the
+ * stream be placed as soon as all blocks of this one have started. Nothing upstream kernels produced may be read before the wait. */
+__device__ __forceinline__ void pdl_wait_then_release() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 #define WF_MODE_CLOSEST 1
 #define WF_MODE_ANY 2
 #define WF_MAX_ROUNDS 12
@@ -640,6 +648,7 @@ __device__ __forceinline__ void answer_deferred(const SceneHeader& h, const unsi
 template <bool COUNT, bool STOCH, bool DIFFUSE = false, bool LEAN = false>
 __global__ void __launch_bounds__(WF_THREADS, 10) wf_generate(const __grid_constant__ SceneHeader h, const unsigned char* __restrict__ blob,
                                                          const __grid_constant__ WfArgs g) {
+    pdl_wait_then_release();
     const RenderArgs& a = g.a;
     const float4* nodes = reinterpret_cast<const float4*>(blob + h.off_nodes);
     const float4* tris = reinterpret_cast<const float4*>(blob + h.off_tris);
@@ -707,6 +716,7 @@ __global__ void __launch_bounds__(WF_THREADS, 10) wf_generate(const __grid_const
 template <bool COUNT, bool STOCH, bool DIFFUSE = false, bool LEAN = false>
 __global__ void __launch_bounds__(WF_THREADS, 8) wf_shade(const __grid_constant__ SceneHeader h, const unsigned char* __restrict__ blob,
                                                       const __grid_constant__ WfArgs g) {
+    pdl_wait_then_release();
     const RenderArgs& a = g.a;
     const float4* nodes = reinterpret_cast<const float4*>(blob + h.off_nodes);
     const float4* tris = reinterpret_cast<const float4*>(blob + h.off_tris);
@@ -821,6 +831,7 @@ __global__ void __launch_bounds__(WF_THREADS) wf_leaves(const __grid_constant__ 
                                                        const __grid_constant__ WfArgs g) {
     /* Two phases per warp, both with full lanes: the box phase takes 32 tasks and keeps those whose box passes the slab
      * test (about half) in a small per-warp buffer; whenever the buffer holds 32 of them the triangle phase runs on 32. */
+    pdl_wait_then_release();
     __shared__ int2 hitbuf[WF_THREADS / 32][96]; /* < 32 left over + up to 64 new */
     const unsigned FULL = 0xffffffffu;
     const float4* tris = reinterpret_cast<const float4*>(blob + h.off_tris);
@@ -889,6 +900,7 @@ __global__ void __launch_bounds__(WF_THREADS) wf_leaves(const __grid_constant__ 
  * writes the averaged 8-bit pixel (optimized.cu:764-771). Runs after the pass's last traversal, when every shadow query
  * has had its say about the direct terms. */
 __global__ void __launch_bounds__(256) wf_fold(const __grid_constant__ WfArgs g) {
+    pdl_wait_then_release();
     const RenderArgs& a = g.a;
     const int px = blockIdx.x * blockDim.x + threadIdx.x;
     if (px >= g.npx) return;
@@ -961,6 +973,7 @@ struct WfWarpSmem { /* per warp; followed by the node pool (npool_cap ints) */
 template <bool COUNT, bool STOCH, bool WIDE>
 __global__ void __launch_bounds__(WF_THREADS, WIDE ? RT_WIDE_BLOCKS : 8) wf_traverse(const __grid_constant__ SceneHeader h, const unsigned char* __restrict__ blob,
                                                          const __grid_constant__ WfArgs g, const int npool_cap) {
+    pdl_wait_then_release();
     extern __shared__ __align__(16) unsigned char wf_smem[];
     const RenderArgs& a = g.a;
     const float4* nodes = reinterpret_cast<const float4*>(blob + h.off_nodes);
