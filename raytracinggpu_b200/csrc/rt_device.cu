@@ -55,7 +55,8 @@ struct RtOptions {
                               * restates the functions for the CPU (rt_oracle.cpp: cuda_logf ...); 0 evaluated in double and rounded once
                               * (the oracle's other canon: what a correctly rounded libm would give; 3-4x the instructions) */
     int graph = 1;           /* replay a recorded CUDA graph when a frame repeats the previous call's plan */
-    int pdl = 1;             /* programmatic dependent launch between consecutive kernels of a band (LaunchChain) */
+    int pdl = 0;             /* programmatic dependent launch between consecutive kernels of a band (LaunchChain). Measured (profiles/r02_notes.md):
+                              * no gain once a frame is a replayed graph (1/8 shard 0.299 vs 0.300 ms), +1 % on the full frame: off */
     int debug_times = 0, debug_pool = 0, debug_bins = 0, debug_cost = 0;
     char debug_warps[256] = {0}; /* RT_DEBUG_WARPS=<file> at scene creation: per-warp timeline of wf_traverse (count_work renders) */
 };
@@ -1404,7 +1405,10 @@ int plan_frame(rt_scene* s, const rt_params* p, uint32_t flags, void* const user
      * stochastic 4 3 4.91 -> 4.67 ms, but the mirror 4K frame 1.23 -> 1.28 ms and no gain for the tree search of
      * coherent rays, profiles/r01_notes.md) */
     const int env_wide_v = s->opt.wide;
-    const bool env_wide = env_wide_v > 0 || (env_wide_v < 0 && stochastic && p->indirect != 0);
+    /* small shards (one rank's rows of a frame split over 8 GPUs): a tree-search round is bound by the dependency depth of single rays,
+     * which the wide index halves (measured, 1/8 of the 4K depth-4 frame: 0.307 -> 0.285 ms; the whole frame 1.117 -> 1.170 ms) */
+    const bool small_shard = npx < 1500000;
+    const bool env_wide = env_wide_v > 0 || (env_wide_v < 0 && ((stochastic && p->indirect != 0) || small_shard));
     const bool env_wide_count = s->opt.wide_count != 0; /* timeline of the wide kernel: node_visits then counts wide nodes */
     const bool wide = env_wide && (!count || env_wide_count) && h.n_wide > 0;
     /* anchored rays (rt_bins.cuh): camera rays and shadow rays find their leaves through per-anchor bins and wf_leaves
@@ -1580,7 +1584,7 @@ int plan_frame(rt_scene* s, const rt_params* p, uint32_t flags, void* const user
  * blocks are placed while the previous kernel's last blocks still run and wait in griddepcontrol.wait (first statement of every wf_*
  * kernel) until it has completed — the launch and ramp-up of the 8-30 small kernels of a frame overlap the tails of their predecessors.
  * Only a kernel whose immediate predecessor on its stream is a kernel gets the attribute; any other operation (memset, event, copy)
- * breaks the chain. Option "pdl" = 0: plain launches. */
+ * breaks the chain. Option "pdl" = 1 turns it on (default off: the graph replay already removes the launch gaps, measured). */
 struct LaunchChain {
     cudaStream_t st[2 * RT_MAX_STRIPS + 2];
     bool after_kernel[2 * RT_MAX_STRIPS + 2];

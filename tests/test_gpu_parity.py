@@ -231,3 +231,73 @@ def test_config5_ten_million_triangles_4k_shadows(scene):
     q = profiles.params("optimized", W, H, 1, 1)
     q.row_begin, q.row_step, q.row_count = 100, 240, 0
     scenes.compare(scene.render(q), scenes.run_oracle(desc, q))
+
+
+def test_overflow_of_an_earlier_no_sync_frame_is_not_lost(gpu):
+    """the overflow flags are sticky on the device — a frame enqueued with RT_RENDER_NO_SYNC that overflowed the (ray,
+    leaf) task buffer is reported by rt_scene_sync (RT_ERR_AGAIN) even when later frames did not overflow."""
+    import torch
+    sc = rt.Scene(gpu)
+    try:
+        sc.set_option("anchored", 1)
+        sc.set_option("task_factor", 1)
+        desc = scenes.cat_scene("cpu") or scenes.torus_scene("cpu")
+        scenes.upload(sc, desc)
+        big = profiles.params("cpu", 640, 360, 1, 0)
+        big.cam[2] = 30.0                      # the mesh fills the view: more than one task per pixel
+        small = profiles.params("cpu", 640, 360, 1, 0)
+        small.cam[2] = 400.0                   # far away: a handful of tasks
+        buf = torch.zeros((360, 640, 3), dtype=torch.uint8, device="cuda")
+        sc.render_into(big, rgb=buf, flags=rt.RT_RENDER_NO_SYNC)     # overflows
+        for _ in range(3):
+            sc.render_into(small, rgb=buf, flags=rt.RT_RENDER_NO_SYNC)  # do not
+        with pytest.raises(rt.RtError) as e:
+            sc.sync()
+        assert e.value.code == -7  # RT_ERR_AGAIN
+        assert sc.get_option("task_factor") == 2
+        sc.sync()  # the flags were consumed
+        # rendered again (a few doublings later) the frame is complete and equals the tree search's
+        sc.set_option("task_factor", 16)
+        a = sc.render(big)
+        sc.set_option("anchored", 0)
+        b = sc.render(big)
+        for k in ("rgb", "hit_tri", "shadow"):
+            assert np.array_equal(a[k], b[k]), k
+    finally:
+        sc.close()
+
+
+def test_big_leaf_guard_travels_with_the_blob(gpu):
+    """max_leaf is part of the scene header, so a scene adopted with rt_scene_blob_import takes the same kernel variant as
+    its source. 70,000 triangles of which 40,000 share one centroid (a leaf the builder cannot split): with push order 0 the in-leaf
+    offset does not fit the tie-break rank and both scenes must fall back to the one-kernel variant."""
+    import torch
+    rng = np.random.RandomState(3)
+    n_fan, n_rest = 40000, 30000
+    verts, tris = [], []
+    q = rng.randint(-256, 257, size=(n_fan, 4)).astype(np.float32) / 64.0  # multiples of 1/64 in [-4, 4]: every sum below is exact
+    for a_, b_, c_, d_ in q:  # triangle (p, r, -(p + r)): its centroid is exactly (0, 0, 0), so the builder cannot split the group
+        k = len(verts)
+        verts += [np.float32([a_, b_, 1.0]), np.float32([c_, d_, -0.5]), np.float32([-a_ - c_, -b_ - d_, -0.5])]
+        tris.append((k, k + 1, k + 2))
+    base = rng.rand(n_rest, 3).astype(np.float32) * 20 - 10
+    for b_ in base:
+        k = len(verts)
+        verts += [b_, b_ + np.float32([0.3, 0, 0]), b_ + np.float32([0, 0.3, 0.1])]
+        tris.append((k, k + 1, k + 2))
+    m = rt.Mesh.from_arrays(np.asarray(verts, np.float32), np.asarray(tris, np.int32)).build_bvh()
+    assert m.bvh_info()["max_leaf"] > 32768
+    src, dst = rt.Scene(gpu), rt.Scene(gpu)
+    try:
+        src.set_spheres(profiles.walls("cpu"))
+        src.set_mesh(m.vertices, m.tri_records, m.arr_bvh, id=6)
+        ptr, n = src.blob_export()
+        dst.blob_import(ptr, n)
+        p = profiles.params("cpu", 160, 90, 1, 0)
+        a, b = src.render(p), dst.render(p)
+        assert a["stats"]["launches"] == 1 and b["stats"]["launches"] == 1  # the one-kernel variant on BOTH
+        for k in ("rgb", "hit_obj", "hit_tri", "shadow"):
+            assert np.array_equal(a[k], b[k]), k
+    finally:
+        src.close()
+        dst.close()
