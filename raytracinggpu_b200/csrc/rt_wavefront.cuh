@@ -411,16 +411,38 @@ __device__ __forceinline__ void path_advance(const SceneHeader& h, const WfArgs&
             const F3 Padj = P + eps * N;
             const F3 toL = Lp - Padj;
             const float D2 = norm2(toL);
-            const F3 su = toL / sqrtf(D2); /* NORMED_VEC :618 */
+            const float rootD = sqrtf(D2);
+            const F3 su = toL / rootD; /* NORMED_VEC :618 */
             /* shadow ray: the spheres here, the mesh through the queue (see mesh_query for the equivalence) */
             w.rays++;
             bool blocked = false;
+            /* Certified screen of the sphere tests. A sphere blocks the light iff the reference's t (Sphere::intersect) satisfies
+             * |fl(fl(P' + fl(t su)) - P')|^2 <= D2 (blocks_light). Every component of that reconstructed vector is within 2^-22 (A + t) of
+             * t su_c (A = largest |coordinate| of P'), |su| is within 2^-22 of 1, the squared norm within 2^-22 relative: a t above
+             * T_hi = (sqrt(D2) + 2^-18 A)(1 + 2^-17) cannot satisfy it. The discriminant is the reference's own; its square root is first taken
+             * with sqrt.approx (relative error 2^-23), which puts the reference's t1 within E = 2^-20 (|b| + sqrt(delta)) of t1a: when
+             * t1a - E > T_hi the near root is positive and beyond the light (not a blocker), when t2a + E < 0 the sphere is behind the ray
+             * (no hit); only the remaining spheres — in the closed room: the one the point lies on — evaluate the IEEE square root and the
+             * reference's predicate. Same decisions as the unscreened loop for every input (a NaN fails both screens). */
+            const float A = fmaxf(fmaxf(fabsf(Padj.x), fabsf(Padj.y)), fabsf(Padj.z));
+            const float T_hi = (rootD + A * 3.814697265625e-06f) * 1.00000762939453125f;
             /* no early exit: a sphere that blocks is rare, and without the exit the tests are independent of one another */
 #pragma unroll 2
             for (int s = 0; s < h.n_spheres; s++) {
-                float t;
-                const bool hit = sphere_t(h.spheres[s], Padj, su, t) && t < RTK_INF && blocks_light(Padj, su, t, D2);
-                blocked = blocked || hit;
+                const DevSphere& sp = h.spheres[s];
+                const F3 OC = f3(Padj.x - sp.cx, Padj.y - sp.cy, Padj.z - sp.cz);
+                const float b = dot(su, OC);
+                const float delta = b * b - (norm2(OC) - sp.RR); /* Sphere::intersect :124-126 */
+                if (delta < 0) continue;
+                const float bc = -b;
+                const float sqa = sqrt_approx(delta);
+                const float E = (fabsf(bc) + sqa) * 9.5367431640625e-07f;
+                if ((bc - sqa) - E > T_hi || (bc + sqa) + E < 0) continue; /* certainly not a blocker */
+                const float sq = sqrtf(delta);
+                const float t1 = bc - sq, t2 = bc + sq;
+                if (t2 < 0) continue;
+                const float t = t1 < 0 ? t2 : t1;
+                blocked = blocked || (t < RTK_INF && blocks_light(Padj, su, t, D2));
             }
             F3 dcol = f3(0.f, 0.f, 0.f);
             if (!blocked) {
