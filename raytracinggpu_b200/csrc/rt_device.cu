@@ -55,6 +55,7 @@ struct RtOptions {
                               * restates the functions for the CPU (rt_oracle.cpp: cuda_logf ...); 0 evaluated in double and rounded once
                               * (the oracle's other canon: what a correctly rounded libm would give; 3-4x the instructions) */
     int graph = 1;           /* replay a recorded CUDA graph when a frame repeats the previous call's plan */
+    int one_shot = 1;        /* stochastic frames of one sample and one segment through the deterministic pipeline with jittered camera rays */
     int pdl = 0;             /* programmatic dependent launch between consecutive kernels of a band (LaunchChain). Measured (profiles/r02_notes.md):
                               * no gain once a frame is a replayed graph (1/8 shard 0.299 vs 0.300 ms), +1 % on the full frame: off */
     int debug_times = 0, debug_pool = 0, debug_bins = 0, debug_cost = 0;
@@ -84,6 +85,7 @@ static const RtOptionKey kOptionKeys[] = {
     {"transcendentals", &RtOptions::transcendentals, 0, 1},
     {"graph", &RtOptions::graph, 0, 1},
     {"pdl", &RtOptions::pdl, 0, 1},
+    {"one_shot", &RtOptions::one_shot, 0, 1},
     {"debug_times", &RtOptions::debug_times, 0, 1},
     {"debug_pool", &RtOptions::debug_pool, 0, 1},
     {"debug_bins", &RtOptions::debug_bins, 0, 1},
@@ -1226,6 +1228,7 @@ struct FramePlan {
     int variant;       /* 0 / 1 render_mega, 2 wavefront, 3 render_stoch */
     unsigned grid;     /* render_mega / render_stoch */
     bool stochastic, count;
+    bool jitter;       /* one sample of one segment in stochastic mode: the deterministic pipeline with jittered camera rays */
     /* wavefront pipeline */
     bool wide, anchored, diffuse_only, trav_round0, dbg_times;
     int segments, npool_cap, n_strips, spill_cap;
@@ -1389,6 +1392,13 @@ int plan_frame(rt_scene* s, const rt_params* p, uint32_t flags, void* const user
             P.prelaunches++; /* the one-off table build is not part of the frame time */
         }
     }
+    /* `./optimized 1 1`-like calls — ONE sample of ONE segment: the only random numbers that reach the image are the two of the
+     * Box-Muller jitter (optimized.cu:756-758); the two drawn at the diffuse hit (:633-634) feed a bounce that is never traced, and
+     * the fold (:653-660) is c = direct. Such a frame is the deterministic pipeline with jittered camera rays: no per-pixel stream state,
+     * no diffuse records, no fold pass (224 B of state traffic per pixel otherwise). Same frames (tests/test_gpu_stochastic.py). */
+    const bool one_shot = stochastic && variant == 2 && p->num_rays == 1 && segments == 1 && !count && s->opt.one_shot != 0;
+    P.jitter = one_shot;
+    const bool stochastic_pipeline = stochastic && !one_shot;
     P.wide = P.anchored = P.diffuse_only = P.trav_round0 = P.dbg_times = false;
     P.npool_cap = P.spill_cap = 0;
     P.n_strips = 1;
@@ -1408,7 +1418,7 @@ int plan_frame(rt_scene* s, const rt_params* p, uint32_t flags, void* const user
     /* small shards (one rank's rows of a frame split over 8 GPUs): a tree-search round is bound by the dependency depth of single rays,
      * which the wide index halves (measured, 1/8 of the 4K depth-4 frame: 0.307 -> 0.285 ms; the whole frame 1.117 -> 1.170 ms) */
     const bool small_shard = npx < 1500000;
-    const bool env_wide = env_wide_v > 0 || (env_wide_v < 0 && ((stochastic && p->indirect != 0) || small_shard));
+    const bool env_wide = env_wide_v > 0 || (env_wide_v < 0 && ((stochastic_pipeline && p->indirect != 0) || small_shard));
     const bool env_wide_count = s->opt.wide_count != 0; /* timeline of the wide kernel: node_visits then counts wide nodes */
     const bool wide = env_wide && (!count || env_wide_count) && h.n_wide > 0;
     /* anchored rays (rt_bins.cuh): camera rays and shadow rays find their leaves through per-anchor bins and wf_leaves
@@ -1431,7 +1441,7 @@ int plan_frame(rt_scene* s, const rt_params* p, uint32_t flags, void* const user
     for (int k = 0; k < h.n_spheres; k++) diffuse_only = diffuse_only && !h.spheres[k].mirror && h.spheres[k].n_in == h.spheres[k].n_out;
     /* round 0 holds tree-searched queries only when a path can go on inside wf_generate: past a mirror or refractive
      * sphere, or along the indirect bounce of a pixel shaded on the spot */
-    bool trav_round0 = stochastic && p->indirect;
+    bool trav_round0 = stochastic_pipeline && p->indirect;
     for (int k = 0; k < h.n_spheres; k++) trav_round0 = trav_round0 || h.spheres[k].mirror || h.spheres[k].n_in != h.spheres[k].n_out;
     trav_round0 = trav_round0 && segments >= 2;
     /* node pool of wf_traverse: 32 lanes x (levels of the packed tree + roots of two batches + slack) */
@@ -1535,7 +1545,7 @@ int plan_frame(rt_scene* s, const rt_params* p, uint32_t flags, void* const user
     }
     /* stochastic mode: per compact pixel 32 B of stream state, 16 B of colour sum, 32 B per path segment of records */
     const size_t st_rng_off = 0, st_total_off = npx * 32, st_rec_off = st_total_off + npx * 16;
-    if (stochastic) {
+    if (stochastic_pipeline) {
         const size_t need = st_rec_off + npx * 32 * (size_t)std::max(segments, 1);
         if (s->st_buf_bytes < need) {
             CUDA_TRY(cudaStreamSynchronize(s->stream));
@@ -1574,7 +1584,7 @@ int plan_frame(rt_scene* s, const rt_params* p, uint32_t flags, void* const user
     P.a = a;
     P.variant = variant;
     P.grid = grid;
-    P.stochastic = stochastic;
+    P.stochastic = stochastic_pipeline;
     P.count = count;
     P.segments = segments;
     return RT_OK;
@@ -1732,6 +1742,10 @@ int enqueue_frame(rt_scene* s, const FramePlan& P, int& launches, bool& strip_co
                 if (count) CUDA_TRY(chain.launch(rtk::wf_generate<true, true>, dim3(gen_grid), WF_THREADS, 0, stream, s->header, s->blob, g));
                 else if (diffuse_only) CUDA_TRY(chain.launch(rtk::wf_generate<false, true, true>, dim3(gen_grid), WF_THREADS, 0, stream, s->header, s->blob, g));
                 else CUDA_TRY(chain.launch(rtk::wf_generate<false, true>, dim3(gen_grid), WF_THREADS, 0, stream, s->header, s->blob, g));
+            } else if (P.jitter) {
+                if (diffuse_only && anchored) CUDA_TRY(chain.launch(rtk::wf_generate<false, false, true, true, true>, dim3(gen_grid), WF_THREADS, 0, stream, s->header, s->blob, g));
+                else if (diffuse_only) CUDA_TRY(chain.launch(rtk::wf_generate<false, false, true, false, true>, dim3(gen_grid), WF_THREADS, 0, stream, s->header, s->blob, g));
+                else CUDA_TRY(chain.launch(rtk::wf_generate<false, false, false, false, true>, dim3(gen_grid), WF_THREADS, 0, stream, s->header, s->blob, g));
             } else {
                 if (count) CUDA_TRY(chain.launch(rtk::wf_generate<true, false>, dim3(gen_grid), WF_THREADS, 0, stream, s->header, s->blob, g));
                 else if (diffuse_only && anchored) CUDA_TRY(chain.launch(rtk::wf_generate<false, false, true, true>, dim3(gen_grid), WF_THREADS, 0, stream, s->header, s->blob, g));

@@ -667,7 +667,9 @@ __device__ __forceinline__ void answer_deferred(const SceneHeader& h, const unsi
 }
 
 /* ---- wf_generate: one thread per pixel (a warp covers an 8x4 tile) ------------------------------------------------ */
-template <bool COUNT, bool STOCH, bool DIFFUSE = false, bool LEAN = false>
+/* JITTER (deterministic instantiations only): the camera ray takes the Box-Muller jitter of optimized.cu:753-759 from the first two
+ * uniforms of the pixel's stream; nothing else of the stochastic mode is needed when a frame is one sample of one segment. */
+template <bool COUNT, bool STOCH, bool DIFFUSE = false, bool LEAN = false, bool JITTER = false>
 __global__ void __launch_bounds__(WF_THREADS, 10) wf_generate(const __grid_constant__ SceneHeader h, const unsigned char* __restrict__ blob,
                                                          const __grid_constant__ WfArgs g) {
     pdl_wait_then_release();
@@ -694,7 +696,19 @@ __global__ void __launch_bounds__(WF_THREADS, 10) wf_generate(const __grid_const
         if (a.camera_mode == 1) /* the viewer's camera, realtime_render.cu:1113 (the camera position is part of the sum there) */
             uc = ((f3(a.camx, a.camy, a.camz) + a.z * f3(a.bz[0], a.bz[1], a.bz[2])) + uc.x * f3(a.bx[0], a.bx[1], a.bx[2])) + uc.y * f3(a.by[0], a.by[1], a.by[2]);
         F3 u0;
-        if (!STOCH) {
+        if (!STOCH && JITTER) {
+            const uint4* t = g.rng_table + ((size_t)i * a.W + j) * 2; /* curand_init(seed, GLOBAL pixel index, 0), optimized.cu:745 */
+            const uint4 s0 = __ldg(t), s1 = __ldg(t + 1);
+            RngRef rng;
+            rng.p = nullptr;
+            rng.d = s0.x; rng.v0 = s0.y; rng.v1 = s0.z; rng.v2 = s0.w; rng.v3 = s1.x; rng.v4 = s1.y;
+            rng.loaded = true;
+            const float r1 = rng_uniform(rng), r2 = rng_uniform(rng); /* :756-757 */
+            const float rad = g.aa_sigma * sqrtf(-2 * (g.libm ? logf(r1) : canon_log(r1)));
+            const float ang = (float)(2 * 3.14159265358979323846 * (double)r2);
+            const float ca = g.libm ? cosf(ang) : canon_cos(ang), sa = g.libm ? sinf(ang) : canon_sin(ang);
+            u0 = normalized(uc + f3(rad * ca, rad * sa, 0.f)); /* :758-759 */
+        } else if (!STOCH) {
             u0 = normalized(uc); /* sigma == 0: the jitter terms of :758 are exactly 0 */
         } else {
             /* the pixel's stream: sample 0 starts from curand_init(seed, GLOBAL pixel index, 0) (optimized.cu:745), later

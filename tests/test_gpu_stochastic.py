@@ -117,6 +117,36 @@ def test_wavefront_and_thread_per_pixel_kernels_agree(scene):
     scenes.compare(scene.render(q), scenes.run_oracle(d, q))
 
 
+def test_one_sample_one_segment_fast_path(scene):
+    """`./optimized 1 1`-like frames run the deterministic pipeline with jittered camera rays (no stream state, records or fold pass):
+    the same frame as the general stochastic pipeline, the thread-per-pixel kernel and the oracle; sharding keeps it."""
+    for desc_fn, profile in ((lambda: scenes.cat_scene("optimized"), "optimized"), (scenes.spheres_scene, "cpu"), (lambda: scenes.torus_scene("optimized", mirror=1), "optimized")):
+        d = desc_fn()
+        if d is None:
+            continue
+        scenes.upload(scene, d)
+        p = stoch(profile, 400, 225, 1, 1 if profile != "cpu" else 0)
+        scene.render(p, want=("rgb",))  # builds the random-stream table (counted as a launch of that call)
+        fast = scene.render(p)
+        scene.set_option("one_shot", 0)
+        general = scene.render(p)
+        assert fast["stats"]["launches"] < general["stats"]["launches"]  # no wf_fold passes
+        scene.set_option("stoch_mega", 1)
+        mega = scene.render(p)
+        scene.set_option("stoch_mega", 0)
+        scene.set_option("one_shot", 1)
+        for k in ("rgb", "hit_obj", "hit_tri", "shadow"):
+            assert np.array_equal(fast[k], general[k]), k
+            assert np.array_equal(fast[k], mega[k]), k
+        assert np.array_equal(fast["hit_t"].view(np.uint32), general["hit_t"].view(np.uint32))
+        assert fast["stats"]["rays"] == general["stats"]["rays"]
+        res = scenes.compare(fast, scenes.run_oracle(d, p))
+        assert res["rgb_exact_mismatch"] == 0, res
+        q = stoch(profile, 400, 225, 1, 1 if profile != "cpu" else 0)
+        q.row_begin, q.row_step, q.row_count = rt.sharding.rows_for_rank(225, 1, 3)
+        assert np.array_equal(scene.render(q, want=("rgb",))["rgb"], fast["rgb"][1::3])
+
+
 @pytest.mark.parametrize("rays,bounce,min_exact", [(1, 1, 0.975), (4, 3, 0.80)])
 def test_against_the_unmodified_reference_gpu_kernel(scene, rays, bounce, min_exact):
     """optimized.cu's own KernelLaunch (oracle/_ref/ref_optimized, --use_fast_math) at 512x512 vs this library with the
