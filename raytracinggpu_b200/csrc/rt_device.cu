@@ -142,6 +142,11 @@ struct rt_scene {
     cudaEvent_t side_fork[RT_MAX_STRIPS] = {}, side_join[RT_MAX_STRIPS] = {};
     rtk::XorwowState* rng_states = nullptr; /* stochastic mode: curand_init(seed, pixel, 0) of every pixel of a rng_W x rng_H frame */
     size_t rng_capacity = 0;
+    float2* jitter_tab = nullptr;  /* first-sample jitter of every pixel (rt_wavefront.cuh: jitter_table), for one-sample one-segment frames */
+    size_t jitter_capacity = 0;
+    float jitter_sigma = 0.f;
+    int jitter_libm = -1;
+    bool jitter_valid = false;
     int rng_W = 0, rng_H = 0;
     unsigned long long rng_seed = 0;
     unsigned char* st_buf = nullptr; /* stochastic wavefront: per-pixel stream state, colour sum, diffuse records */
@@ -567,6 +572,7 @@ void rt_scene_destroy(rt_scene* s) {
     if (s->scan_tmp) cudaFree(s->scan_tmp);
     if (s->wf_tasks) cudaFree(s->wf_tasks);
     if (s->rng_states) cudaFree(s->rng_states);
+    if (s->jitter_tab) cudaFree(s->jitter_tab);
     if (s->st_buf) cudaFree(s->st_buf);
     if (s->h_wf_counters) cudaFreeHost(s->h_wf_counters);
     for (int k = 0; k < 5; k++)
@@ -1389,6 +1395,7 @@ int plan_frame(rt_scene* s, const rt_params* p, uint32_t flags, void* const user
             s->rng_W = p->W;
             s->rng_H = p->H;
             s->rng_seed = seed;
+            s->jitter_valid = false;
             P.prelaunches++; /* the one-off table build is not part of the frame time */
         }
     }
@@ -1398,6 +1405,24 @@ int plan_frame(rt_scene* s, const rt_params* p, uint32_t flags, void* const user
      * no diffuse records, no fold pass (224 B of state traffic per pixel otherwise). Same frames (tests/test_gpu_stochastic.py). */
     const bool one_shot = stochastic && variant == 2 && p->num_rays == 1 && segments == 1 && !count && s->opt.one_shot != 0;
     P.jitter = one_shot;
+    if (one_shot && (!s->jitter_valid || s->jitter_sigma != p->aa_sigma || s->jitter_libm != s->opt.transcendentals)) {
+        const size_t frame_px = (size_t)p->W * p->H;
+        if (s->jitter_capacity < frame_px) {
+            CUDA_TRY(cudaStreamSynchronize(s->stream));
+            if (s->jitter_tab) cudaFree(s->jitter_tab);
+            s->jitter_tab = nullptr;
+            s->jitter_capacity = 0;
+            CUDA_TRY(cudaMalloc(&s->jitter_tab, frame_px * sizeof(float2)));
+            s->jitter_capacity = frame_px;
+        }
+        rtk::jitter_table<<<(unsigned)((frame_px + 255) / 256), 256, 0, s->stream>>>(reinterpret_cast<const uint4*>(s->rng_states), (unsigned)frame_px, p->aa_sigma,
+                                                                                    s->opt.transcendentals, s->jitter_tab);
+        CUDA_TRY(cudaGetLastError());
+        s->jitter_sigma = p->aa_sigma;
+        s->jitter_libm = s->opt.transcendentals;
+        s->jitter_valid = true;
+        P.prelaunches++;
+    }
     const bool stochastic_pipeline = stochastic && !one_shot;
     P.wide = P.anchored = P.diffuse_only = P.trav_round0 = P.dbg_times = false;
     P.npool_cap = P.spill_cap = 0;
@@ -1724,6 +1749,7 @@ int enqueue_frame(rt_scene* s, const FramePlan& P, int& launches, bool& strip_co
         g.aa_sigma = p->aa_sigma;
         g.npx = (int)spx;
         g.rng_table = reinterpret_cast<const uint4*>(s->rng_states);
+        g.jitter_tab = s->jitter_tab;
         g.rng = stochastic ? reinterpret_cast<uint4*>(s->st_buf + st_rng_off) + px0 * 2 : nullptr;
         g.total = stochastic ? reinterpret_cast<float4*>(s->st_buf + st_total_off) + px0 : nullptr;
         g.rec = stochastic ? reinterpret_cast<float4*>(s->st_buf + st_rec_off) + px0 * 2 * (size_t)std::max(segments, 1) : nullptr;
@@ -1896,7 +1922,7 @@ void frame_key(rt_scene* s, const FramePlan& P, std::vector<unsigned char>& key)
         if (P.anchored) v = bins_view(s->bins[k]);
         put(&v, sizeof v);
     }
-    const void* ptrs[] = {s->blob, s->wf_queue, s->wf_tasks, s->wf_counters, s->wf_spill, s->st_buf, s->rng_states, s->gamma_tab, s->sticky, s->stream};
+    const void* ptrs[] = {s->blob, s->jitter_tab, s->wf_queue, s->wf_tasks, s->wf_counters, s->wf_spill, s->st_buf, s->rng_states, s->gamma_tab, s->sticky, s->stream};
     put(ptrs, sizeof ptrs);
     const size_t nums[] = {s->wf_capacity, s->wf_tasks_cap, (size_t)s->task_factor, (size_t)s->leaves_blocks_per_sm, (size_t)s->sm_count, (size_t)s->trav_blocks_per_sm};
     put(nums, sizeof nums);

@@ -84,6 +84,7 @@ struct WfArgs {
     float aa_sigma;
     int npx;               /* compact pixels of this strip: stride of rec */
     const uint4* rng_table; /* start state of every pixel of the W x H frame, 2 x uint4 per pixel (d, v0..v4, -, -) */
+    const float2* jitter_tab; /* JITTER instantiations: the Box-Muller jitter of every pixel's first sample (jitter_table) */
     uint4* rng;            /* running state per compact pixel of the strip, 2 x uint4 */
     float4* total;         /* per compact pixel: colour summed over the samples (xyz), bit mask of the diffuse segments of this sample (w) */
     float4* rec;           /* [segment][compact pixel][2]: direct term, albedo of the diffuse hit that ended that segment */
@@ -697,17 +698,10 @@ __global__ void __launch_bounds__(WF_THREADS, 10) wf_generate(const __grid_const
             uc = ((f3(a.camx, a.camy, a.camz) + a.z * f3(a.bz[0], a.bz[1], a.bz[2])) + uc.x * f3(a.bx[0], a.bx[1], a.bx[2])) + uc.y * f3(a.by[0], a.by[1], a.by[2]);
         F3 u0;
         if (!STOCH && JITTER) {
-            const uint4* t = g.rng_table + ((size_t)i * a.W + j) * 2; /* curand_init(seed, GLOBAL pixel index, 0), optimized.cu:745 */
-            const uint4 s0 = __ldg(t), s1 = __ldg(t + 1);
-            RngRef rng;
-            rng.p = nullptr;
-            rng.d = s0.x; rng.v0 = s0.y; rng.v1 = s0.z; rng.v2 = s0.w; rng.v3 = s1.x; rng.v4 = s1.y;
-            rng.loaded = true;
-            const float r1 = rng_uniform(rng), r2 = rng_uniform(rng); /* :756-757 */
-            const float rad = g.aa_sigma * sqrtf(-2 * (g.libm ? logf(r1) : canon_log(r1)));
-            const float ang = (float)(2 * 3.14159265358979323846 * (double)r2);
-            const float ca = g.libm ? cosf(ang) : canon_cos(ang), sa = g.libm ? sinf(ang) : canon_sin(ang);
-            u0 = normalized(uc + f3(rad * ca, rad * sa, 0.f)); /* :758-759 */
+            /* the jitter of the pixel's FIRST sample, optimized.cu:756-758: a function of (seed, global pixel index, sigma) only, kept in a
+             * table beside the stream start states (jitter_table below) */
+            const float2 jt = __ldg(g.jitter_tab + (size_t)i * a.W + j);
+            u0 = normalized(uc + f3(jt.x, jt.y, 0.f)); /* :758-759 */
         } else if (!STOCH) {
             u0 = normalized(uc); /* sigma == 0: the jitter terms of :758 are exactly 0 */
         } else {
@@ -929,6 +923,24 @@ __global__ void __launch_bounds__(WF_THREADS) wf_leaves(const __grid_constant__ 
         const int2 t = buf[lane];
         leaf_triangles<STOCH>(h, g, tris, ((t.x < 0) ? g.qS : qA) + (t.x & 0x7fffffff), t.x < 0, t.y);
     }
+}
+
+/* The Box-Muller jitter of the first sample of every pixel of the W x H frame (optimized.cu:756-758): the first two uniforms of the
+ * pixel's stream curand_init(seed, pixel, 0), (sigma sqrt(-2 log r1) cos(2 pi r2), sigma sqrt(-2 log r1) sin(2 pi r2)). Depends on the
+ * seed, the frame size, sigma and the transcendental canon only: built once beside the start-state table, 8 B per pixel. */
+__global__ void __launch_bounds__(256) jitter_table(const uint4* __restrict__ rng_table, unsigned n, float sigma, int libm, float2* __restrict__ out) {
+    const unsigned p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const uint4 s0 = __ldg(rng_table + 2 * (size_t)p), s1 = __ldg(rng_table + 2 * (size_t)p + 1);
+    RngRef rng;
+    rng.p = nullptr;
+    rng.d = s0.x; rng.v0 = s0.y; rng.v1 = s0.z; rng.v2 = s0.w; rng.v3 = s1.x; rng.v4 = s1.y;
+    rng.loaded = true;
+    const float r1 = rng_uniform(rng), r2 = rng_uniform(rng); /* :756-757 */
+    const float rad = sigma * sqrtf(-2 * (libm ? logf(r1) : canon_log(r1)));
+    const float ang = (float)(2 * 3.14159265358979323846 * (double)r2);
+    const float ca = libm ? cosf(ang) : canon_cos(ang), sa = libm ? sinf(ang) : canon_sin(ang);
+    out[p] = make_float2(rad * ca, rad * sa);
 }
 
 /* ---- wf_fold (stochastic mode): the end of one sample pass. Folds the pixel's diffuse records back to front,
