@@ -462,13 +462,15 @@ def config4_ten_million(rt, torch, local, world, rank, flush):
         t2 = time.perf_counter()
         walls, mesh_id = rt.default_walls("optimized")
         sc.set_spheres(walls)
-        sc.set_mesh(mesh.vertices, mesh.tri_records, mesh.arr_bvh, id=mesh_id)
+        sc.set_mesh_from(mesh, id=mesh_id)  # the builder's arrays never leave the device (rt_scene_set_mesh_device: relayout + repack as kernels)
         sc.sync()
         torch.cuda.synchronize()
         t3 = time.perf_counter()
         nv, nt, nn = mesh.counts()
-        build = {"triangles": nt, "bvh_nodes": nn, "instance_ms": round((t1 - t0) * 1e3, 1), "bvh_build_wall_ms": round((t2 - t1) * 1e3, 1),
-                 "bvh_build_device_ms": round(mesh.build_ms, 2), "upload_and_repack_ms": round((t3 - t2) * 1e3, 1)}
+        build = {"triangles": nt, "bvh_nodes": nn, "host_instancing_ms": round((t1 - t0) * 1e3, 1), "upload_and_bvh_build_wall_ms": round((t2 - t1) * 1e3, 1),
+                 "bvh_build_device_ms": round(mesh.build_ms, 2), "device_relayout_and_repack_ms": round((t3 - t2) * 1e3, 1),
+                 "scene_ready_ms_after_the_arrays_exist": round((t3 - t1) * 1e3, 1),
+                 "note": "round 1: host node relayout + 1.1 GB over PCIe, 1174 ms; builder results copied back and reordered on the host, 477 ms"}
         del mesh
     bcast_ms, blob = 0.0, sc.blob_size() if rank == 0 else 0
     if world > 1:

@@ -149,6 +149,8 @@ int rt_mesh_build_bvh(rt_mesh* m);
  * and triangle order (the reference builds on the host, optimized.cu:806-813, or in one device thread,
  * global_launcher.cu:298-331). build_ms (may be NULL): device time of the build without the transfers. */
 int rt_mesh_build_bvh_gpu(rt_mesh* m, int device, double* build_ms);
+/* After rt_mesh_build_bvh_gpu the post-build arrays STAY on that device; the host mirror (rt_mesh_tri_records, rt_mesh_arr_bvh) is
+ * fetched on the first access. rt_scene_set_mesh_from (below) hands them to a scene of the same device without a host round trip. */
 int rt_mesh_counts(const rt_mesh* m, int32_t* nv, int32_t* nt, int32_t* n_nodes);
 const float* rt_mesh_vertices(const rt_mesh* m);          /* nv*3 */
 const int32_t* rt_mesh_tri_records(const rt_mesh* m);     /* nt*RT_TRI_RECORD_WORDS, post-build order */
@@ -221,6 +223,15 @@ int rt_scene_set_mesh(rt_scene* s, const float* vertices, int32_t nv,
                       const int32_t* tri_records, int32_t nt,
                       const float* arr_bvh, int32_t n_nodes,
                       const float albedo[3], int32_t mirror, float n_in, float n_out, int32_t id);
+/* The same upload with the three interchange arrays ALREADY ON THE SCENE'S DEVICE (device pointers; e.g. produced by the caller's own
+ * kernels, or left there by rt_mesh_build_bvh_gpu): node relayout, leaf table and triangle repack run as kernels (csrc/rt_relayout.cuh),
+ * nothing crosses the bus. No 4-wide index is built on this path (tree searches use the two-child records), and vertex normals
+ * (rt_scene_set_mesh_normals) need the host upload. The arrays may be released when the call returns. */
+int rt_scene_set_mesh_device(rt_scene* s, const float* d_vertices, int32_t nv, const int32_t* d_tri_records, int32_t nt,
+                             const float* d_arr_bvh, int32_t n_nodes, const float albedo[3], int32_t mirror, float n_in, float n_out, int32_t id);
+/* The mesh of an rt_mesh handle: rt_scene_set_mesh_device when rt_mesh_build_bvh_gpu left its arrays on this scene's device,
+ * rt_scene_set_mesh with the host arrays otherwise. */
+int rt_scene_set_mesh_from(rt_scene* s, rt_mesh* m, const float albedo[3], int32_t mirror, float n_in, float n_out, int32_t id);
 /* Per-vertex normals for rt_params::smooth_normals (TriangleMesh::normals + TriangleIndices::ni,nj,nk, realtime_render.cu:239-241):
  * call after rt_scene_set_mesh with the mesh's normals array (rt_mesh_normals); the normal indices are words 6-8 of the triangle
  * records that call uploaded. Held beside the scene blob (not part of a broadcast: the viewer is single-GPU). n_normals == 0 removes them. */

@@ -64,6 +64,8 @@ SIGNATURES = {
     "rt_scene_get_option": (C.c_int, [_vp, C.c_char_p, C.POINTER(C.c_int64)]),
     "rt_scene_set_spheres": (C.c_int, [_vp, C.POINTER(rt_sphere), _i32]),
     "rt_scene_set_mesh": (C.c_int, [_vp, _vp, _i32, _vp, _i32, _vp, _i32, _pf, _i32, _f, _f, _i32]),
+    "rt_scene_set_mesh_device": (C.c_int, [_vp, _vp, _i32, _vp, _i32, _vp, _i32, _pf, _i32, _f, _f, _i32]),
+    "rt_scene_set_mesh_from": (C.c_int, [_vp, _vp, _pf, _i32, _f, _f, _i32]),
     "rt_scene_set_light": (C.c_int, [_vp, _pf, _f]),
     "rt_scene_blob_size": (C.c_int, [_vp, C.POINTER(C.c_size_t)]),
     "rt_scene_blob_export": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(C.c_size_t)]),
@@ -371,6 +373,15 @@ class Scene:
         _check(lib().rt_scene_set_mesh(self._h, v.ctypes.data, v.shape[0], t.ctypes.data, t.shape[0], b.ctypes.data, b.shape[0],
                                        _f3(albedo), int(mirror), float(n_in), float(n_out), int(id)))
         self.mesh_h2d_bytes = v.nbytes + t.nbytes + b.nbytes
+
+    def set_mesh_from(self, mesh, albedo=(0.25, 0.25, 0.25), mirror=0, n_in=1.0, n_out=1.0, id=1):
+        """The mesh of a Mesh handle: from the device when build_bvh_gpu left its arrays there (no host round trip), else from the host."""
+        _check(lib().rt_scene_set_mesh_from(self._h, mesh._h, _f3(albedo), int(mirror), float(n_in), float(n_out), int(id)))
+
+    def set_mesh_device(self, d_vertices, nv, d_tri_records, nt, d_arr_bvh, n_nodes, albedo=(0.25, 0.25, 0.25), mirror=0, n_in=1.0, n_out=1.0, id=1):
+        """rt_scene_set_mesh_device: the three interchange arrays as DEVICE pointers (ints)."""
+        _check(lib().rt_scene_set_mesh_device(self._h, C.c_void_p(int(d_vertices)), int(nv), C.c_void_p(int(d_tri_records)), int(nt), C.c_void_p(int(d_arr_bvh)), int(n_nodes),
+                                              _f3(albedo), int(mirror), float(n_in), float(n_out), int(id)))
 
     def set_mesh_normals(self, normals):
         """Per-vertex normals for rt_params.smooth_normals (after set_mesh; indices are words 6-8 of its triangle records)."""

@@ -40,9 +40,38 @@ struct rt_mesh {
     std::vector<TriRecord> tris;
     std::vector<float> arr_bvh; /* n_nodes * 10 */
     int32_t n_nodes = 0, n_leaves = 0, max_depth = 0, max_leaf = 0;
+    /* rt_mesh_build_bvh_gpu leaves the post-build arrays on the device (rt_scene_set_mesh_from takes them from there) and fetches the host
+     * mirror — the reordered records and arr_bvh — only when somebody asks for it */
+    void* device_keep = nullptr;
+    bool host_stale = false;
+    ~rt_mesh() {
+        if (device_keep) rtb::bvh_device_free(device_keep);
+    }
 };
 
+namespace rtb {
+void* mesh_device_handle(rt_mesh* m) { return m ? m->device_keep : nullptr; }
+} // namespace rtb
+
 namespace {
+
+/* the host mirror of a device-resident build, on demand */
+int materialize(rt_mesh* m) {
+    if (!m->host_stale) return RT_OK;
+    const int rc = rtb::bvh_device_download(m->device_keep, &m->tris[0].w[0], &m->arr_bvh);
+    if (rc != 0) return rtb::fail(RT_ERR_CUDA, "rt_mesh: fetching the device-built BVH failed (CUDA error %d)", rc);
+    m->host_stale = false;
+    return RT_OK;
+}
+/* before the mesh changes: the host copy becomes the truth again, the device copy goes */
+int take_back(rt_mesh* m) {
+    const int rc = materialize(m);
+    if (m->device_keep) {
+        rtb::bvh_device_free(m->device_keep);
+        m->device_keep = nullptr;
+    }
+    return rc;
+}
 
 /* ---- OBJ tokeniser ------------------------------------------------------------------------------------ */
 
@@ -91,6 +120,7 @@ bool parse_face_vertex(const char*& p, const char* end, long& vi, long& ni) {
 inline int32_t resolve(long i, size_t nv) { return i < 0 ? (int32_t)((long)nv + i) : (int32_t)(i - 1); }
 
 int read_obj(rt_mesh* m, const char* path) {
+    take_back(m);
     FILE* f = fopen(path, "rb");
     if (!f) return rtb::fail(RT_ERR_IO, "rt_mesh_read_obj: cannot open '%s'", path);
     std::vector<char> buf;
@@ -259,6 +289,7 @@ int rt_mesh_read_obj(rt_mesh* m, const char* path) {
 }
 
 int rt_mesh_set_triangles(rt_mesh* m, const float* vertices, int32_t nv, const int32_t* idx, int32_t nt) {
+    if (m) take_back(m);
     if (!m || nv < 0 || nt < 0 || (nv > 0 && !vertices) || (nt > 0 && !idx)) return rtb::fail(RT_ERR_INVALID, "rt_mesh_set_triangles: bad argument");
     for (int64_t i = 0; i < (int64_t)nt * 3; i++)
         if (idx[i] < 0 || idx[i] >= nv) return rtb::fail(RT_ERR_INVALID, "rt_mesh_set_triangles: vertex index %d out of range", idx[i]);
@@ -283,6 +314,7 @@ int rt_mesh_keep_normals(rt_mesh* m, int keep) {
 
 int rt_mesh_set_normals(rt_mesh* m, const float* normals, int32_t nn, const int32_t* normal_indices) {
     if (!m || nn < 0 || (nn > 0 && (!normals || !normal_indices))) return rtb::fail(RT_ERR_INVALID, "rt_mesh_set_normals: bad argument");
+    take_back(m);
     if (m->n_nodes > 0) return rtb::fail(RT_ERR_STATE, "rt_mesh_set_normals: attach the normals before the BVH is built (the build reorders the records)");
     const size_t nt = m->tris.size();
     for (size_t i = 0; i < 3 * nt && nn > 0; i++)
@@ -304,6 +336,7 @@ const float* rt_mesh_normals(const rt_mesh* m) { return (m && !m->normals.empty(
 
 int rt_mesh_rescale(rt_mesh* m, float scale, const float offset[3]) {
     if (!m || !offset) return rtb::fail(RT_ERR_INVALID, "rt_mesh_rescale: NULL argument");
+    take_back(m);
     for (rtb::Vec3& v : m->vertices) { /* vertices[i]*scale + offset, optimized.cu:299 */
         v.x = v.x * scale + offset[0];
         v.y = v.y * scale + offset[1];
@@ -316,6 +349,7 @@ int rt_mesh_rescale(rt_mesh* m, float scale, const float offset[3]) {
 
 int rt_mesh_instance(rt_mesh* m, int32_t copies, const float* scales, const float* offsets) {
     if (!m || copies < 1 || !scales || !offsets) return rtb::fail(RT_ERR_INVALID, "rt_mesh_instance: bad argument");
+    take_back(m);
     const size_t nv = m->vertices.size(), nt = m->tris.size();
     if ((uint64_t)nt * (uint64_t)copies >= (1u << 24)) return rtb::fail(RT_ERR_UNSUPPORTED, "rt_mesh_instance: %llu triangles exceed 2^24", (unsigned long long)nt * copies);
     std::vector<rtb::Vec3> v(nv * copies);
@@ -341,26 +375,29 @@ int rt_mesh_instance(rt_mesh* m, int32_t copies, const float* scales, const floa
 
 int rt_mesh_build_bvh(rt_mesh* m) {
     if (!m) return rtb::fail(RT_ERR_INVALID, "rt_mesh_build_bvh: NULL mesh");
+    take_back(m);
     return build_bvh(m);
 }
 
 int rt_mesh_build_bvh_gpu(rt_mesh* m, int device, double* build_ms) {
     if (!m) return rtb::fail(RT_ERR_INVALID, "rt_mesh_build_bvh_gpu: NULL mesh");
+    int rc0 = take_back(m);
+    if (rc0 != RT_OK) return rc0;
     const int32_t nt = (int32_t)m->tris.size(), nv = (int32_t)m->vertices.size();
     if (build_ms) *build_ms = 0.;
     if (nt < 2) return build_bvh(m); /* nothing to do in parallel */
     if (nt >= (1 << 24)) return rtb::fail(RT_ERR_UNSUPPORTED, "rt_mesh_build_bvh_gpu: %d triangles do not fit the float-encoded array BVH (2^24)", nt);
-    std::vector<int32_t> idx((size_t)nt * 3), perm;
-    for (int32_t i = 0; i < nt; i++)
-        for (int k = 0; k < 3; k++) idx[(size_t)3 * i + k] = m->tris[i].w[k];
+    std::vector<int32_t> perm;
     std::vector<float> arr;
     int32_t info[4] = {0, 0, 0, 0};
-    const int rc = rtb::bvh_build_device(device, &m->vertices[0].x, nv, idx.data(), nt, &perm, &arr, info, build_ms);
+    /* the post-build arrays stay on the device (rt_scene_set_mesh_from takes them from there); the host mirror — records in the
+     * builder's order, arr_bvh — is fetched by the accessors when somebody asks for it */
+    void* keep = nullptr;
+    const int rc = rtb::bvh_build_device(device, &m->vertices[0].x, nv, &m->tris[0].w[0], nt, &perm, &arr, info, build_ms, &keep);
     if (rc != 0) return rtb::fail(RT_ERR_CUDA, "rt_mesh_build_bvh_gpu: CUDA error %d (this library has no CPU fallback for the device builder; rt_mesh_build_bvh is the host builder)", rc);
-    std::vector<TriRecord> sorted((size_t)nt);
-    for (int32_t i = 0; i < nt; i++) sorted[i] = m->tris[perm[i]];
-    m->tris.swap(sorted);
-    m->arr_bvh.swap(arr);
+    m->device_keep = keep;
+    m->host_stale = true;
+    m->arr_bvh.clear();
     m->n_nodes = info[0];
     m->n_leaves = info[1];
     m->max_depth = info[2];
@@ -377,8 +414,14 @@ int rt_mesh_counts(const rt_mesh* m, int32_t* nv, int32_t* nt, int32_t* n_nodes)
 }
 
 const float* rt_mesh_vertices(const rt_mesh* m) { return (m && !m->vertices.empty()) ? &m->vertices[0].x : nullptr; }
-const int32_t* rt_mesh_tri_records(const rt_mesh* m) { return (m && !m->tris.empty()) ? &m->tris[0].w[0] : nullptr; }
-const float* rt_mesh_arr_bvh(const rt_mesh* m) { return (m && m->n_nodes > 0) ? m->arr_bvh.data() : nullptr; }
+const int32_t* rt_mesh_tri_records(const rt_mesh* m) {
+    if (m && m->host_stale && materialize(const_cast<rt_mesh*>(m)) != RT_OK) return nullptr;
+    return (m && !m->tris.empty()) ? &m->tris[0].w[0] : nullptr;
+}
+const float* rt_mesh_arr_bvh(const rt_mesh* m) {
+    if (m && m->host_stale && materialize(const_cast<rt_mesh*>(m)) != RT_OK) return nullptr;
+    return (m && m->n_nodes > 0) ? m->arr_bvh.data() : nullptr;
+}
 
 int rt_mesh_bvh_info(const rt_mesh* m, int32_t* n_leaves, int32_t* max_depth, int32_t* max_leaf) {
     if (!m) return rtb::fail(RT_ERR_INVALID, "rt_mesh_bvh_info: NULL mesh");

@@ -25,6 +25,7 @@
 #include <cub/cub.cuh>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include "rt_relayout.cuh"
 
 #include <vector>
 
@@ -243,8 +244,19 @@ __global__ void k_emit(Nodes n, int total, float* __restrict__ arr) {
     } while (0)
 
 /* info: [0] nodes, [1] leaves, [2] depth, [3] largest leaf. Returns a cudaError_t (0 = success). */
-inline int build(int device, const float* h_vertices, int nv, const int32_t* h_idx, int nt, std::vector<int32_t>& perm_out, std::vector<float>& arr_out,
-                 int32_t info[4], double* build_ms) {
+/* What a build leaves on the device for rt_scene_set_mesh_device: the interchange arrays in their final (post-build) order. */
+struct DeviceMesh {
+    int device = -1;
+    float* V = nullptr;    /* nv * 3 */
+    int* recs = nullptr;   /* nt * 10, permuted */
+    float* arr = nullptr;  /* nn * 10 */
+    int nv = 0, nt = 0, nn = 0;
+};
+
+/* h_recs: whole triangle records (nt x 10). keep != NULL: the results STAY on the device (keep->V / recs / arr, owned by the caller from
+ * then on) and nothing is copied back (perm_out / arr_out stay empty): the host mirror is fetched on demand (download). */
+inline int build(int device, const float* h_vertices, int nv, const int32_t* h_recs, int nt, std::vector<int32_t>& perm_out, std::vector<float>& arr_out,
+                 int32_t info[4], double* build_ms, DeviceMesh* keep = nullptr) {
     cudaError_t err = cudaSuccess;
     int prev = -1;
     cudaGetDevice(&prev);
@@ -252,6 +264,7 @@ inline int build(int device, const float* h_vertices, int nv, const int32_t* h_i
     const int max_nodes = 2 * nt;
     const int T = 256, B = (nt + T - 1) / T;
     float *V = nullptr, *arr = nullptr;
+    int *R_in = nullptr, *R_out = nullptr;
     int *I = nullptr, *perm = nullptr, *perm2 = nullptr, *seg = nullptr, *seg2 = nullptr, *flag = nullptr, *S = nullptr, *nx = nullptr, *nx2 = nullptr, *cnt = nullptr, *off = nullptr,
         *stats = nullptr;
     void* tmp = nullptr;
@@ -293,7 +306,9 @@ inline int build(int device, const float* h_vertices, int nv, const int32_t* h_i
     RTB_TRY(cudaMalloc(&n.size, (size_t)max_nodes * sizeof(int)));
     RTB_TRY(cudaMalloc(&n.pre, (size_t)max_nodes * sizeof(int)));
     RTB_TRY(cudaMemcpy(V, h_vertices, (size_t)nv * 3 * sizeof(float), cudaMemcpyHostToDevice));
-    RTB_TRY(cudaMemcpy(I, h_idx, (size_t)nt * 3 * sizeof(int), cudaMemcpyHostToDevice));
+    RTB_TRY(cudaMalloc(&R_in, (size_t)nt * 10 * sizeof(int)));
+    RTB_TRY(cudaMemcpy(R_in, h_recs, (size_t)nt * 10 * sizeof(int), cudaMemcpyHostToDevice));
+    rtrelayout::records_to_idx3<<<(unsigned)(((size_t)nt * 3 + T - 1) / T), T>>>(R_in, nt, I);
     RTB_TRY(cudaEventCreate(&e0));
     RTB_TRY(cudaEventCreate(&e1));
     RTB_TRY(cudaEventRecord(e0));
@@ -358,10 +373,27 @@ inline int build(int device, const float* h_vertices, int nv, const int32_t* h_i
         cudaEventElapsedTime(&ms, e0, e1);
         if (build_ms) *build_ms = ms;
     }
-    perm_out.resize(nt);
-    arr_out.resize((size_t)total * 10);
-    RTB_TRY(cudaMemcpy(perm_out.data(), perm, (size_t)nt * sizeof(int), cudaMemcpyDeviceToHost));
-    RTB_TRY(cudaMemcpy(arr_out.data(), arr, (size_t)total * 10 * sizeof(float), cudaMemcpyDeviceToHost));
+    if (keep) {
+        RTB_TRY(cudaMalloc(&R_out, (size_t)nt * 10 * sizeof(int)));
+        rtrelayout::gather_records<<<(unsigned)(((size_t)nt * 10 + T - 1) / T), T>>>(R_in, perm, nt, R_out);
+        RTB_TRY(cudaDeviceSynchronize());
+        RTB_TRY(cudaGetLastError());
+        keep->device = device;
+        keep->V = V;
+        keep->recs = R_out;
+        keep->arr = arr;
+        keep->nv = nv;
+        keep->nt = nt;
+        keep->nn = total;
+        V = nullptr; /* handed over */
+        R_out = nullptr;
+        arr = nullptr;
+    } else {
+        perm_out.resize(nt);
+        arr_out.resize((size_t)total * 10);
+        RTB_TRY(cudaMemcpy(perm_out.data(), perm, (size_t)nt * sizeof(int), cudaMemcpyDeviceToHost));
+        RTB_TRY(cudaMemcpy(arr_out.data(), arr, (size_t)total * 10 * sizeof(float), cudaMemcpyDeviceToHost));
+    }
     info[0] = total;
     info[1] = h_stats[0];
     info[2] = (int32_t)level_base.size();
@@ -369,7 +401,7 @@ inline int build(int device, const float* h_vertices, int nv, const int32_t* h_i
 done:
     if (e0) cudaEventDestroy(e0);
     if (e1) cudaEventDestroy(e1);
-    void* frees[] = {V, arr, I, perm, perm2, seg, seg2, flag, S, nx, nx2, cnt, off, stats, tmp, n.start, n.end, n.kmn, n.kmx, n.left, n.right, n.axis, n.split, n.nL, n.size, n.pre};
+    void* frees[] = {R_in, R_out, V, arr, I, perm, perm2, seg, seg2, flag, S, nx, nx2, cnt, off, stats, tmp, n.start, n.end, n.kmn, n.kmx, n.left, n.right, n.axis, n.split, n.nL, n.size, n.pre};
     for (void* p : frees)
         if (p) cudaFree(p);
     if (prev >= 0) cudaSetDevice(prev);

@@ -14,6 +14,7 @@
 #include "rt_wavefront.cuh"
 #include "rt_stochastic.cuh"
 #include "rt_bvh_build.cuh"
+#include "rt_relayout.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -475,9 +476,43 @@ int scene_blob_reserve(rt_scene* s, size_t bytes, void** device_ptr) {
     *device_ptr = s->blob;
     return RT_OK;
 }
-int bvh_build_device(int device, const float* vertices, int nv, const int32_t* idx3, int nt, std::vector<int32_t>* perm, std::vector<float>* arr, int32_t info[4],
-                     double* build_ms) {
-    return rtbuild::build(device, vertices, nv, idx3, nt, *perm, *arr, info, build_ms);
+int bvh_build_device(int device, const float* vertices, int nv, const int32_t* recs10, int nt, std::vector<int32_t>* perm, std::vector<float>* arr, int32_t info[4],
+                     double* build_ms, void** keep) {
+    rtbuild::DeviceMesh* dm = keep ? new rtbuild::DeviceMesh() : nullptr;
+    const int rc = rtbuild::build(device, vertices, nv, recs10, nt, *perm, *arr, info, build_ms, dm);
+    if (keep) {
+        if (rc != 0) {
+            delete dm;
+            dm = nullptr;
+        }
+        *keep = dm;
+    }
+    return rc;
+}
+int bvh_device_download(void* keep, int32_t* recs10_out, std::vector<float>* arr_out) {
+    rtbuild::DeviceMesh* dm = static_cast<rtbuild::DeviceMesh*>(keep);
+    DeviceGuard g(dm->device);
+    arr_out->resize((size_t)dm->nn * 10);
+    cudaError_t e = cudaMemcpy(recs10_out, dm->recs, (size_t)dm->nt * 10 * sizeof(int), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(arr_out->data(), dm->arr, (size_t)dm->nn * 10 * sizeof(float), cudaMemcpyDeviceToHost);
+    return (int)e;
+}
+void bvh_device_free(void* keep) {
+    rtbuild::DeviceMesh* dm = static_cast<rtbuild::DeviceMesh*>(keep);
+    if (!dm) return;
+    DeviceGuard g(dm->device);
+    if (dm->V) cudaFree(dm->V);
+    if (dm->recs) cudaFree(dm->recs);
+    if (dm->arr) cudaFree(dm->arr);
+    delete dm;
+}
+void bvh_device_arrays(void* keep, int* device, const float** vertices, const int32_t** recs10, const float** arr, int32_t* nn) {
+    rtbuild::DeviceMesh* dm = static_cast<rtbuild::DeviceMesh*>(keep);
+    *device = dm->device;
+    *vertices = dm->V;
+    *recs10 = dm->recs;
+    *arr = dm->arr;
+    *nn = dm->nn;
 }
 } // namespace rtb
 
@@ -1037,6 +1072,183 @@ int rt_scene_set_mesh(rt_scene* s, const float* vertices, int32_t nv, const int3
     h.total_bytes = total;
     s->header_dirty = true;
     return RT_OK;
+}
+
+/* rt_scene_set_mesh with the interchange arrays ALREADY ON THE DEVICE (rt_relayout.cuh): the node relayout, the leaf table and the
+ * triangle repack run as kernels; nothing crosses the bus but a 64-byte summary. */
+int rt_scene_set_mesh_device(rt_scene* s, const float* d_vertices, int32_t nv, const int32_t* d_tri_records, int32_t nt, const float* d_arr_bvh,
+                             int32_t n_nodes, const float albedo[3], int32_t mirror, float n_in, float n_out, int32_t id) {
+    if (!s) return rtb::fail(RT_ERR_INVALID, "rt_scene_set_mesh_device: NULL scene");
+    if (nt <= 0 || nv <= 0 || n_nodes <= 0 || !d_vertices || !d_tri_records || !d_arr_bvh || !albedo || id < 0)
+        return rtb::fail(RT_ERR_INVALID, "rt_scene_set_mesh_device: bad argument");
+    DeviceGuard g(s->device);
+    if (!g.ok) return rtb::fail(RT_ERR_CUDA, "rt_scene_set_mesh_device: cudaSetDevice failed");
+    if (!is_device_pointer(d_vertices, s->device) || !is_device_pointer(d_tri_records, s->device) || !is_device_pointer(d_arr_bvh, s->device))
+        return rtb::fail(RT_ERR_INVALID, "rt_scene_set_mesh_device: the three arrays must be device memory of device %d (host arrays: rt_scene_set_mesh)", s->device);
+    SceneHeader& h = s->header;
+    cudaStream_t st = s->stream;
+    CUDA_TRY(cudaStreamSynchronize(st));
+    const int T = 256, NB = (n_nodes + T - 1) / T;
+    /* scratch: 7 int arrays of n_nodes + 1, the totals, the scan's work space */
+    int* scratch = nullptr;
+    rtrelayout::Totals* d_tot = nullptr;
+    void* tmp = nullptr;
+    size_t tmp_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, (int*)nullptr, (int*)nullptr, n_nodes + 1);
+    const size_t N1 = (size_t)n_nodes + 1;
+    cudaError_t err = cudaMalloc(&scratch, 7 * N1 * sizeof(int));
+    if (err == cudaSuccess) err = cudaMalloc(&d_tot, sizeof(rtrelayout::Totals));
+    if (err == cudaSuccess) err = cudaMalloc(&tmp, tmp_bytes + 256);
+    auto cleanup = [&]() {
+        if (scratch) cudaFree(scratch);
+        if (d_tot) cudaFree(d_tot);
+        if (tmp) cudaFree(tmp);
+    };
+    if (err != cudaSuccess) {
+        cleanup();
+        return rtb::fail(RT_ERR_NOMEM, "rt_scene_set_mesh_device: %s", cudaGetErrorString(err));
+    }
+    int *is_inner = scratch, *n_chunks = scratch + N1, *n_virt = scratch + 2 * N1, *inner_rank = scratch + 3 * N1, *virt_base = scratch + 4 * N1,
+        *leaf_base = scratch + 5 * N1, *depth = scratch + 6 * N1;
+    cudaMemsetAsync(scratch, 0, 3 * N1 * sizeof(int), st);
+    cudaMemsetAsync(depth, 0xff, N1 * sizeof(int), st);
+    cudaMemsetAsync(depth, 0, sizeof(int), st);
+    cudaMemsetAsync(d_tot, 0, sizeof(rtrelayout::Totals), st);
+    rtrelayout::classify<<<NB, T, 0, st>>>(d_arr_bvh, n_nodes, nt, is_inner, n_chunks, n_virt, d_tot);
+    rtrelayout::check_indices<<<(nt + T - 1) / T, T, 0, st>>>(d_tri_records, nt, nv, d_tot);
+    cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, is_inner, inner_rank, n_nodes + 1, st);
+    cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, n_virt, virt_base, n_nodes + 1, st);
+    cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, n_chunks, leaf_base, n_nodes + 1, st);
+    for (int level = 0; level < RT_STACK_CAP; level++) rtrelayout::depth_step<<<NB, T, 0, st>>>(d_arr_bvh, n_nodes, level, depth, d_tot);
+    rtrelayout::Totals tot;
+    int sums[3] = {0, 0, 0};
+    float root[10];
+    err = cudaMemcpyAsync(&tot, d_tot, sizeof tot, cudaMemcpyDeviceToHost, st);
+    if (err == cudaSuccess) err = cudaMemcpyAsync(&sums[0], inner_rank + n_nodes, sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (err == cudaSuccess) err = cudaMemcpyAsync(&sums[1], virt_base + n_nodes, sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (err == cudaSuccess) err = cudaMemcpyAsync(&sums[2], leaf_base + n_nodes, sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (err == cudaSuccess) err = cudaMemcpyAsync(root, d_arr_bvh, sizeof root, cudaMemcpyDeviceToHost, st);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(st);
+    if (err != cudaSuccess) {
+        cleanup();
+        return rtb::fail(RT_ERR_CUDA, "rt_scene_set_mesh_device: %s", cudaGetErrorString(err));
+    }
+    if (tot.error) {
+        cleanup();
+        return rtb::fail(RT_ERR_INVALID, "rt_scene_set_mesh_device: malformed arrays (%s)", tot.error == 1 ? "a node with exactly one child" : tot.error == 2 ? "child index out of order / range" :
+                                                                                                 tot.error == 3 ? "leaf triangle range invalid" : "triangle references a vertex out of range");
+    }
+    const int n_real = sums[0], n_virtual = sums[1], n_leafrecs = sums[2];
+    int extra_levels = 0;
+    while ((1 << extra_levels) < tot.max_chunks) extra_levels++;
+    if (tot.max_chunks > 1) extra_levels++;
+    const int max_depth = tot.max_depth + 1 + extra_levels;
+    if (max_depth > RT_STACK_CAP - 2) {
+        cleanup();
+        return rtb::fail(RT_ERR_UNSUPPORTED, "rt_scene_set_mesh_device: packed BVH depth %d exceeds the traversal stack (%d)", max_depth, RT_STACK_CAP - 2);
+    }
+    const int n_inner = n_real + n_virtual;
+    const size_t off_nodes = RT_HEADER_BYTES;
+    const size_t off_tris = (off_nodes + (size_t)n_inner * RT_NODE_BYTES + 63) & ~(size_t)63;
+    const size_t off_wide = (off_tris + (size_t)nt * RT_TRI_BYTES + 127) & ~(size_t)127;
+    const size_t off_leaves = off_wide; /* no wide index on this path */
+    const size_t total = off_leaves + (size_t)n_leafrecs * RT_LEAFREC_BYTES;
+    if (s->blob_bytes < total || s->blob_bytes > 2 * total + (1u << 20)) {
+        if (s->blob) cudaFree(s->blob);
+        s->blob = nullptr;
+        s->blob_bytes = 0;
+        err = cudaMalloc(&s->blob, total);
+        if (err != cudaSuccess) {
+            cleanup();
+            return rtb::fail(RT_ERR_NOMEM, "rt_scene_set_mesh_device: %zu bytes for the scene blob: %s", total, cudaGetErrorString(err));
+        }
+        s->blob_bytes = total;
+    }
+    if (s->stage_bytes < (size_t)nt * sizeof(int32_t)) {
+        if (s->stage) cudaFree(s->stage);
+        s->stage = nullptr;
+        s->stage_bytes = 0;
+        err = cudaMalloc(&s->stage, (size_t)nt * sizeof(int32_t));
+        if (err != cudaSuccess) {
+            cleanup();
+            return rtb::fail(RT_ERR_NOMEM, "rt_scene_set_mesh_device: %s", cudaGetErrorString(err));
+        }
+        s->stage_bytes = (size_t)nt * sizeof(int32_t);
+    }
+    int32_t* d_leaf_start = reinterpret_cast<int32_t*>(s->stage);
+    float4* records = reinterpret_cast<float4*>(s->blob + off_nodes);
+    rtrelayout::write_inner<<<NB, T, 0, st>>>(d_arr_bvh, n_nodes, nt, is_inner, inner_rank, n_chunks, virt_base, n_real, records);
+    rtrelayout::write_leaves<<<NB, T, 0, st>>>(d_arr_bvh, n_nodes, nt, is_inner, n_chunks, virt_base, leaf_base, n_real, records,
+                                               reinterpret_cast<float4*>(s->blob + off_leaves), d_leaf_start);
+    rtk::repack_triangles<<<(nt + T - 1) / T, T, 0, st>>>(d_vertices, d_tri_records, nt, d_leaf_start, reinterpret_cast<float4*>(s->blob + off_tris));
+    err = cudaGetLastError();
+    if (err == cudaSuccess) err = cudaStreamSynchronize(st); /* the caller's arrays and the scratch may go away */
+    /* root reference, as child_ref() of node 0 */
+    int root_ref;
+    {
+        const int l = (int)root[0];
+        const int ts = (int)root[8], cnt = (int)root[9] - ts;
+        const int chunks = cnt > 0 ? (cnt + RT_LEAF_MAX - 1) / RT_LEAF_MAX : 0;
+        if (l != -1) root_ref = 0; /* the root is the first inner node in pre-order */
+        else if (cnt <= 0) root_ref = -1 - ((nt << 2) | 0);
+        else if (chunks == 1) root_ref = -1 - ((ts << 2) | (cnt - 1));
+        else root_ref = n_real + 0; /* virt_base of node 0 is 0 */
+    }
+    cleanup();
+    if (err != cudaSuccess) return rtb::fail(RT_ERR_CUDA, "rt_scene_set_mesh_device: %s", cudaGetErrorString(err));
+    h.has_mesh = 1;
+    h.n_inner = n_inner;
+    h.n_leaves = n_leafrecs;
+    h.n_tris = nt;
+    h.max_depth = max_depth;
+    h.mesh_id = id;
+    h.mesh_mirror = mirror ? 1 : 0;
+    h.mesh_n_in = n_in;
+    h.mesh_n_out = n_out;
+    memcpy(h.mesh_albedo, albedo, sizeof h.mesh_albedo);
+    for (int c = 0; c < 3; c++) {
+        h.root_mn[c] = root[2 + c];
+        h.root_mx[c] = root[5 + c];
+        memcpy(&h.box_abs[c], &tot.box_abs[c], sizeof(float));
+    }
+    h.root_ref = root_ref;
+    h.wroot_ref = 0;
+    h.max_leaf = tot.max_leaf;
+    s->max_leaf = tot.max_leaf;
+    h.off_nodes = off_nodes;
+    h.off_tris = off_tris;
+    h.off_wide = off_wide;
+    h.off_leaves = off_leaves;
+    h.n_wide = 0;
+    h.wide_depth = 0;
+    h.total_bytes = total;
+    s->mesh_generation++;
+    s->last_bvh.clear();
+    s->last_nv = s->last_nt = 0;
+    s->stage_nt = 0; /* the records are the caller's: vertex normals need the host upload */
+    s->has_normals = false;
+    s->header_dirty = true;
+    return RT_OK;
+}
+
+/* The mesh of an rt_mesh handle: straight from the device when rt_mesh_build_bvh_gpu left its arrays on this scene's device, through
+ * the host interchange arrays otherwise. */
+int rt_scene_set_mesh_from(rt_scene* s, rt_mesh* m, const float albedo[3], int32_t mirror, float n_in, float n_out, int32_t id) {
+    if (!s || !m) return rtb::fail(RT_ERR_INVALID, "rt_scene_set_mesh_from: NULL argument");
+    int32_t nv = 0, nt = 0, nn = 0;
+    int rc = rt_mesh_counts(m, &nv, &nt, &nn);
+    if (rc != RT_OK) return rc;
+    if (nn <= 0) return rtb::fail(RT_ERR_STATE, "rt_scene_set_mesh_from: build the BVH first");
+    void* keep = rtb::mesh_device_handle(m);
+    if (keep) {
+        int dev = -1;
+        const float *V = nullptr, *arr = nullptr;
+        const int32_t* recs = nullptr;
+        int32_t dn = 0;
+        rtb::bvh_device_arrays(keep, &dev, &V, &recs, &arr, &dn);
+        if (dev == s->device) return rt_scene_set_mesh_device(s, V, nv, recs, nt, arr, dn, albedo, mirror, n_in, n_out, id);
+    }
+    return rt_scene_set_mesh(s, rt_mesh_vertices(m), nv, rt_mesh_tri_records(m), nt, rt_mesh_arr_bvh(m), nn, albedo, mirror, n_in, n_out, id);
 }
 
 int rt_scene_set_mesh_normals(rt_scene* s, const float* normals, int32_t n_normals) {

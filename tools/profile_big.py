@@ -7,10 +7,11 @@ from raytracinggpu_b200 import synthetic
 from oracle import profiles, scenes, pyoracle
 scales, offs = synthetic.instance_lattice()
 mesh = rt.Mesh.read_obj(pyoracle.cat_obj_path()).instance(scales, offs).build_bvh_gpu(0)
-desc = dict(spheres=profiles.walls("optimized"), mesh=(mesh.vertices, mesh.tri_records, mesh.arr_bvh), mesh_mat=profiles.mesh_material("optimized", 0), light=profiles.LIGHT)
 sc = rt.Scene(0)
 sc.set_option("graph", 0)  # ncu: plain launches
-scenes.upload(sc, desc)
+sc.set_spheres(profiles.walls("optimized"))
+sc.set_light(*profiles.LIGHT)
+sc.set_mesh_from(mesh, id=1)
 p = profiles.params("optimized", 3840, 2160, 1, 1)
 rgb = torch.empty((2160, 3840, 3), dtype=torch.uint8, device="cuda")
 for i in range(int(sys.argv[1]) if len(sys.argv) > 1 else 3):
