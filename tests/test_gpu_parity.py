@@ -205,12 +205,14 @@ def test_config5_ten_million_triangles_4k_shadows(scene):
     if cat is None:
         pytest.skip("cat asset unavailable")
     scales, offs = synthetic.instance_lattice()
-    mesh = rt.Mesh.read_obj(cat).instance(scales, offs).build_bvh()
+    mesh = rt.Mesh.read_obj(cat).instance(scales, offs).build_bvh_gpu(0)   # the reference's tree, built on the device (tests/test_gpu_build.py)
     assert mesh.counts()[1] == 9999666
-    desc = dict(spheres=profiles.walls("optimized"), mesh=(mesh.vertices, mesh.tri_records, mesh.arr_bvh),
+    mesh_id = profiles.mesh_material("optimized", 0)["id"]
+    scene.set_spheres(profiles.walls("optimized"))
+    scene.set_light(*profiles.LIGHT)
+    scene.set_mesh_from(mesh, id=mesh_id)                                   # arrays never leave the device (rt_scene_set_mesh_device)
+    desc = dict(spheres=profiles.walls("optimized"), mesh=(mesh.vertices, mesh.tri_records, mesh.arr_bvh),  # host mirror, for the oracle
                 mesh_mat=profiles.mesh_material("optimized", 0), light=profiles.LIGHT)
-    mesh_id = desc["mesh_mat"]["id"]
-    scenes.upload(scene, desc)
     W, H = 3840, 2160
     p = profiles.params("optimized", W, H, 1, 1)
     a = scene.render(p)
