@@ -115,6 +115,29 @@ def ncu_frame_summary(pattern="*_ncu_summary.json", exclude=("config5", "config4
             "kernel_share": {k: round(sum(l["duration_us"] or 0 for l in L if l["kernel"].split("<")[0].endswith(k)) / dur, 3) for k in ("wf_generate", "wf_leaves", "wf_shade")} if dur else None}
 
 
+def pin_to_gpu_numa(local):
+    """N > 1: bind this rank's host threads (and with them the first-touch placement of its pinned buffers) to the CPUs of its GPU's NUMA
+    node: the e2e leg moves 6.5 MB per step between host and device on every rank at once. Best effort; returns what was done."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(local)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        dom, rest = bus.split(":", 1)
+        path = "/sys/bus/pci/devices/%s:%s/local_cpulist" % (dom[-4:].lower(), rest.lower())
+        cpus = set()
+        for part in open(path).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return "%d CPUs of the GPU's NUMA node" % len(cpus)
+    except Exception as e:  # noqa: BLE001
+        return "not pinned (%s)" % repr(e)[:80]
+    return "not pinned"
+
+
 def build_scene_host(rt):
     """Host side of the launcher (optimized.cu:801-813): load, rescale, build the BVH — with the product's host code."""
     cat = find_cat()
@@ -140,8 +163,10 @@ def run_ours(args):
     if rt.device_count() < 1:
         raise SystemExit("bench.py: no CUDA device; raytracinggpu_b200 has no CPU fallback")
     torch.cuda.set_device(local)
+    numa = None
     if world > 1:
         import torch.distributed as dist
+        numa = pin_to_gpu_numa(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     sc = rt.Scene(local)
     stream = torch.cuda.Stream()
@@ -235,6 +260,21 @@ def run_ours(args):
     e2e_value = rays_per_frame * e2e_steps * world / e2e_s / 1e6
     h2d = int(verts.nbytes + recs.nbytes + bvh.nbytes)
     d2h = int(H * W * 3)
+    # where the step goes, with every rank doing the same at the same time (max over ranks): the mesh upload alone, the frame's D2H alone
+    def timed(fn, n=10):
+        fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(n):
+            fn()
+        torch.cuda.synchronize()
+        return _max_over_ranks(torch, world, (time.perf_counter() - t0) / n * 1e3)
+    e2e_breakdown = {"set_mesh_ms": round(timed(lambda: (sc.set_mesh(verts, recs, bvh, id=mesh_id), sc.sync())), 4),
+                     "d2h_6MB_alone_ms": round(timed(lambda: host_rgb.copy_(rgb)), 4),
+                     "render_to_device_buffer_sync_ms": round(timed(lambda: sc.render_into(p, rgb=rgb)), 4),
+                     "note": "all ranks at once, max over ranks; on an 8-GPU board two GPUs share a PCIe switch uplink, which is what the D2H line shows at N = 8"}
 
     # ---- extra lines: frames of a one-revolution light orbit (the light's bins are rebuilt every frame) and
     # whole 4K depth-4 frames, both frame-parallel over the ranks, device-timed, max over ranks
@@ -329,9 +369,9 @@ def run_ours(args):
            "data": "synthetic",
            "config": {"workload": workload_string(mesh_name),
                       "rays_per_frame": rays_per_frame, "frames_per_step_per_gpu": 1, "sharding": "frame-parallel (every rank renders its own frames of this workload)" if world > 1 else "single GPU",
-                      "l2": "256 MB memset between steps, outside the event pair", "timed_wall_s": round(wall_s, 4)},
+                      "l2": "256 MB memset between steps, outside the event pair", "timed_wall_s": round(wall_s, 4), "host_affinity": numa},
            "e2e": {"value": round(e2e_value, 2), "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": round(e2e_s / e2e_steps * 1e3, 4),
-                   "steps": e2e_steps},
+                   "steps": e2e_steps, "breakdown": e2e_breakdown},
            "gpu_launches": launches_per_step * args.steps, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
            "ms_per_frame": round(kernel_ms, 5), "scene_broadcast_bytes": blob_bytes,
            "configs": {"configs0_spheres_800x600": cfg0, "configs2_one_4k_depth4_frame_row_sharded": sharded, "configs3_spheres_animation_240_frames": cfg3,
