@@ -303,3 +303,33 @@ def test_big_leaf_guard_travels_with_the_blob(gpu):
     finally:
         src.close()
         dst.close()
+
+
+def test_full_size_config0_spheres_800x600(scene):
+    """BASELINE.json configs[0] at its named size: the spheres scene of cpu_launcher.cpp:668-678 (mirror sphere, refractive shell), point
+    light, 800x600, 1 spp, cpu_launcher.cpp knobs with num_bounce 5 (6 path segments): every output against the oracle."""
+    desc = scenes.spheres_scene()
+    scenes.upload(scene, desc)
+    p = profiles.params("cpu", 800, 600, 1, 5)
+    got = scene.render(p)
+    ora = scenes.run_oracle(desc, p)
+    res = scenes.compare(got, ora)
+    assert res["rgb_exact_mismatch"] == 0, res
+    assert got["stats"]["rays"] == ora["work"]["rays"]
+
+
+def test_full_size_config3_animation_frames_1080p(scene):
+    """BASELINE.json configs[3] at its named size: frames of the 240-frame light orbit (realtime_render.cu:1072-1090, one revolution) of the
+    spheres scene at 1920x1080 — frames 0, 80 and 160 against the oracle, every rank deriving the same light positions in float."""
+    desc = scenes.spheres_scene()
+    scenes.upload(scene, desc)
+    omega = 2 * np.pi / (240 * 0.02)
+    orbit = rt.sharding.light_positions((-10.0, 20.0, 40.0), 240, omega, 0.02, rt.move_light)
+    p = profiles.params("cpu", 1920, 1080, 1, 5)
+    for f in (0, 80, 160):
+        scene.set_light(orbit[f], 3e10)
+        d = scenes.spheres_scene(light=(orbit[f], 3e10))
+        got = scene.render(p, want=("rgb", "hit_obj", "shadow"))
+        ora = scenes.run_oracle(d, p, want=("rgb", "hit_obj", "shadow"))
+        res = scenes.compare(got, ora)
+        assert res["rgb_exact_mismatch"] == 0, (f, res)
