@@ -97,10 +97,11 @@ struct rt_scene {
     int device = 0;
     RtOptions opt;
     bool plan_valid = false; /* unused marker kept for setters that invalidate recorded frames (the key comparison decides) */
-    cudaGraphExec_t graph_exec = nullptr;      /* the recorded frame (rt_render) */
-    std::vector<unsigned char> graph_key;      /* what it was recorded for */
-    std::vector<unsigned char> last_key;       /* the previous call's key: a frame is recorded when it repeats */
-    int graph_launches = 0;
+    /* the recorded frame (rt_render); two of them, because frames with asynchronous host outputs alternate between two scratch sets */
+    cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};
+    std::vector<unsigned char> graph_key[2];   /* what each was recorded for */
+    std::vector<unsigned char> last_key[2];    /* the previous call's key (per set): a frame is recorded when it repeats */
+    int graph_launches[2] = {0, 0};
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -115,8 +116,21 @@ struct rt_scene {
     unsigned long long* h_counters = nullptr; /* pinned */
 
     /* scratch outputs for host-pointer callers */
-    unsigned char* scratch[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-    size_t scratch_bytes[5] = {0, 0, 0, 0, 0};
+    unsigned char* scratch[2][5] = {};
+    size_t scratch_bytes[2][5] = {};
+    /* host outputs of frames enqueued with RT_RENDER_NO_SYNC leave on a copy stream of their own, from two alternating sets of scratch
+     * buffers: the copy-back of frame k overlaps the kernels of frame k + 1 (which write the other set) */
+    int scratch_set = 0;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t copy_done[2] = {nullptr, nullptr}, frame_done = nullptr;
+    bool copy_recorded[2] = {false, false};
+    bool copies_pending = false;
+    /* the pinned staging of rt_scene_set_mesh's fast path, two halves: the upload of step k + 1 does not wait for the frame of step k */
+    unsigned char* pin_alt = nullptr;
+    size_t pin_alt_bytes = 0;
+    cudaEvent_t pin_ev[2] = {nullptr, nullptr};
+    bool pin_ev_recorded[2] = {false, false};
+    int pin_set = 0;
 
     /* pending copy-back of a RT_RENDER_NO_SYNC call */
     bool pending = false;
@@ -259,13 +273,14 @@ bool is_device_pointer(const void* p, int device) {
     return (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged) && (at.type == cudaMemoryTypeManaged || at.device == device);
 }
 
-int ensure_scratch(rt_scene* s, int slot, size_t bytes) {
-    if (s->scratch_bytes[slot] >= bytes) return RT_OK;
-    if (s->scratch[slot]) cudaFree(s->scratch[slot]);
-    s->scratch[slot] = nullptr;
-    s->scratch_bytes[slot] = 0;
-    CUDA_TRY(cudaMalloc(&s->scratch[slot], bytes));
-    s->scratch_bytes[slot] = bytes;
+int ensure_scratch(rt_scene* s, int set, int slot, size_t bytes) {
+    if (s->scratch_bytes[set][slot] >= bytes) return RT_OK;
+    if (s->copy_stream) CUDA_TRY(cudaStreamSynchronize(s->copy_stream)); /* a copy may still read the buffer that goes away */
+    if (s->scratch[set][slot]) cudaFree(s->scratch[set][slot]);
+    s->scratch[set][slot] = nullptr;
+    s->scratch_bytes[set][slot] = 0;
+    CUDA_TRY(cudaMalloc(&s->scratch[set][slot], bytes));
+    s->scratch_bytes[set][slot] = bytes;
     return RT_OK;
 }
 
@@ -578,7 +593,18 @@ void rt_scene_destroy(rt_scene* s) {
     if (!s) return;
     DeviceGuard g(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
-    if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
+    if (s->copy_stream) {
+        cudaStreamSynchronize(s->copy_stream);
+        cudaStreamDestroy(s->copy_stream);
+    }
+    for (int k = 0; k < 2; k++) {
+        if (s->copy_done[k]) cudaEventDestroy(s->copy_done[k]);
+        if (s->pin_ev[k]) cudaEventDestroy(s->pin_ev[k]);
+    }
+    if (s->frame_done) cudaEventDestroy(s->frame_done);
+    if (s->pin_alt) cudaFreeHost(s->pin_alt);
+    for (int k = 0; k < 2; k++)
+        if (s->graph_exec[k]) cudaGraphExecDestroy(s->graph_exec[k]);
     if (s->tri_normals) cudaFree(s->tri_normals);
     if (s->d_normals) cudaFree(s->d_normals);
     if (s->accum) cudaFree(s->accum);
@@ -611,7 +637,8 @@ void rt_scene_destroy(rt_scene* s) {
     if (s->st_buf) cudaFree(s->st_buf);
     if (s->h_wf_counters) cudaFreeHost(s->h_wf_counters);
     for (int k = 0; k < 5; k++)
-        if (s->scratch[k]) cudaFree(s->scratch[k]);
+        for (int set = 0; set < 2; set++)
+            if (s->scratch[set][k]) cudaFree(s->scratch[set][k]);
     for (int k = 0; k < RT_MAX_STRIPS; k++) {
         if (s->strip_stream[k]) cudaStreamDestroy(s->strip_stream[k]);
         if (s->strip_done[k]) cudaEventDestroy(s->strip_done[k]);
@@ -633,7 +660,8 @@ int rt_scene_set_stream(rt_scene* s, void* cuda_stream) {
     if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
     s->stream = (cudaStream_t)cuda_stream;
     s->own_stream = false;
-    s->last_key.clear();
+    s->last_key[0].clear();
+    s->last_key[1].clear();
     return RT_OK;
 }
 
@@ -740,10 +768,27 @@ int rt_scene_set_mesh(rt_scene* s, const float* vertices, int32_t nv, const int3
         memcmp(s->last_bvh.data(), arr_bvh, s->last_bvh.size() * sizeof(float)) == 0) {
         const size_t vbytes = (size_t)nv * 3 * sizeof(float), rbytes = (size_t)nt * RT_TRI_RECORD_WORDS * sizeof(int32_t);
         const size_t r_off = (vbytes + 255) & ~(size_t)255, l_off = (r_off + rbytes + 255) & ~(size_t)255;
-        CUDA_TRY(cudaStreamSynchronize(s->stream)); /* the pinned buffer may still feed the previous upload */
-        memcpy(s->pin, vertices, vbytes);
-        memcpy(s->pin + r_off, tri_records, rbytes);
-        CUDA_TRY(cudaMemcpyAsync(s->stage, s->pin, r_off + rbytes, cudaMemcpyHostToDevice, s->stream));
+        /* two pinned halves, each guarded by an event behind its last upload: the host never waits for the frames in flight, only
+         * for the upload before last (long done) */
+        const size_t up_bytes = r_off + rbytes;
+        s->pin_set ^= 1;
+        const int half = s->pin_set;
+        if (half == 1 && s->pin_alt_bytes < up_bytes) {
+            if (s->pin_ev_recorded[1]) CUDA_TRY(cudaEventSynchronize(s->pin_ev[1]));
+            if (s->pin_alt) cudaFreeHost(s->pin_alt);
+            s->pin_alt = nullptr;
+            s->pin_alt_bytes = 0;
+            CUDA_TRY(cudaMallocHost(&s->pin_alt, up_bytes + up_bytes / 4));
+            s->pin_alt_bytes = up_bytes + up_bytes / 4;
+        }
+        if (!s->pin_ev[half]) CUDA_TRY(cudaEventCreateWithFlags(&s->pin_ev[half], cudaEventDisableTiming));
+        if (s->pin_ev_recorded[half]) CUDA_TRY(cudaEventSynchronize(s->pin_ev[half]));
+        unsigned char* const pin = half ? s->pin_alt : s->pin;
+        memcpy(pin, vertices, vbytes);
+        memcpy(pin + r_off, tri_records, rbytes);
+        CUDA_TRY(cudaMemcpyAsync(s->stage, pin, up_bytes, cudaMemcpyHostToDevice, s->stream));
+        CUDA_TRY(cudaEventRecord(s->pin_ev[half], s->stream));
+        s->pin_ev_recorded[half] = true;
         const int threads = 256, blocks = (nt + threads - 1) / threads;
         rtk::repack_triangles<<<blocks, threads, 0, s->stream>>>(reinterpret_cast<float*>(s->stage), reinterpret_cast<int32_t*>(s->stage + r_off), nt,
                                                                 reinterpret_cast<int32_t*>(s->stage + l_off), reinterpret_cast<float4*>(s->blob + h.off_tris));
@@ -1016,7 +1061,11 @@ int rt_scene_set_mesh(rt_scene* s, const float* vertices, int32_t nv, const int3
         err = cudaMemcpyAsync(s->stage, s->pin, stage_need, cudaMemcpyHostToDevice, s->stream);
         if (err == cudaSuccess && nodes_bytes) err = cudaMemcpyAsync(s->blob + off_nodes, s->pin + pin_nodes, nodes_bytes, cudaMemcpyHostToDevice, s->stream);
         if (err == cudaSuccess && tail_bytes) err = cudaMemcpyAsync(s->blob + off_wide, s->pin + pin_tail, tail_bytes, cudaMemcpyHostToDevice, s->stream);
-        need_sync = false; /* the next rt_scene_set_mesh waits for the stream before it touches the pinned buffer again */
+        need_sync = false; /* the next full upload waits for the stream before it touches the pinned buffer again; the fast path for this event */
+        if (err == cudaSuccess && !s->pin_ev[0]) err = cudaEventCreateWithFlags(&s->pin_ev[0], cudaEventDisableTiming);
+        if (err == cudaSuccess) err = cudaEventRecord(s->pin_ev[0], s->stream);
+        s->pin_ev_recorded[0] = err == cudaSuccess;
+        s->pin_set = 0;
     } else {
         if (err == cudaSuccess) err = cudaMemcpyAsync(d_vertices, vertices, vbytes, cudaMemcpyHostToDevice, s->stream);
         if (err == cudaSuccess) err = cudaMemcpyAsync(d_recs, tri_records, rbytes, cudaMemcpyHostToDevice, s->stream);
@@ -1366,6 +1415,10 @@ int rt_scene_sync(rt_scene* s, rt_stats* stats) {
             CUDA_TRY(cudaMemcpyAsync(s->h_counters, s->counters, RT_NCOUNTERS * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->stream));
     }
     CUDA_TRY(cudaStreamSynchronize(s->stream));
+    if (s->copies_pending) {
+        CUDA_TRY(cudaStreamSynchronize(s->copy_stream));
+        s->copies_pending = false;
+    }
     if (s->pending && s->last_was_wavefront) { /* fold the strips' counters */
         for (int k = 0; k < RT_NCOUNTERS; k++) s->h_counters[k] = 0;
         for (int st = 0; st < RT_MAX_STRIPS; st++)
@@ -1446,6 +1499,8 @@ struct FramePlan {
     int variant;       /* 0 / 1 render_mega, 2 wavefront, 3 render_stoch */
     unsigned grid;     /* render_mega / render_stoch */
     bool stochastic, count;
+    bool async_copy;   /* host outputs leave on the copy stream behind the frame (RT_RENDER_NO_SYNC), not inside it */
+    int scratch_set;
     bool jitter;       /* one sample of one segment in stochastic mode: the deterministic pipeline with jittered camera rays */
     /* wavefront pipeline */
     bool wide, anchored, diffuse_only, trav_round0, dbg_times;
@@ -1503,6 +1558,14 @@ int plan_frame(rt_scene* s, const rt_params* p, uint32_t flags, void* const user
     const size_t bytes[5] = {npx * 3, npx * 4, npx * 4, npx * 4, npx};
     void* dev[5];
     bool copy_back[5];
+    bool any_host = false;
+    for (int k = 0; k < 5; k++) any_host = any_host || (user[k] && !is_device_pointer(user[k], s->device));
+    /* host outputs of an enqueue-only call: the other scratch set, copied back on the copy stream behind the frame */
+    const bool async_copy = any_host && (flags & RT_RENDER_NO_SYNC) != 0;
+    if (async_copy) s->scratch_set ^= 1;
+    const int set = async_copy ? s->scratch_set : 0;
+    P.async_copy = async_copy;
+    P.scratch_set = set;
     for (int k = 0; k < 5; k++) {
         dev[k] = nullptr;
         copy_back[k] = false;
@@ -1510,9 +1573,9 @@ int plan_frame(rt_scene* s, const rt_params* p, uint32_t flags, void* const user
         if (is_device_pointer(user[k], s->device)) {
             dev[k] = user[k];
         } else {
-            int rc = ensure_scratch(s, k, bytes[k]);
+            int rc = ensure_scratch(s, set, k, bytes[k]);
             if (rc != RT_OK) return rc;
-            dev[k] = s->scratch[k];
+            dev[k] = s->scratch[set][k];
             copy_back[k] = true;
         }
     }
@@ -2066,7 +2129,7 @@ int enqueue_frame(rt_scene* s, const FramePlan& P, int& launches, bool& strip_co
              * (kernel_ms then spans the copies of all bands but the last as well) */
             const size_t elem[5] = {3, 4, 4, 4, 1};
             for (int k = 0; k < 5; k++)
-                if (copy_back[k] && !(a.linear && k == 0)) { /* accumulation: the 8-bit frame exists only after accumulate_frame */
+                if (copy_back[k] && !P.async_copy && !(a.linear && k == 0)) { /* accumulation: the 8-bit frame exists only after accumulate_frame */
                     CUDA_TRY(cudaMemcpyAsync((unsigned char*)user[k] + px0 * elem[k], (unsigned char*)dev[k] + px0 * elem[k], spx * elem[k], cudaMemcpyDeviceToHost, stream));
                     strip_copied = true;
                 }
@@ -2089,7 +2152,7 @@ int enqueue_frame(rt_scene* s, const FramePlan& P, int& launches, bool& strip_co
         if (a.linear) { /* progressive accumulation (realtime_render.cu:1136-1140) once every band has joined */
             rtk::accumulate_frame<<<(unsigned)((P.npx + 255) / 256), 256, 0, s->stream>>>(s->accum, s->linear, (int)P.npx, p->accumulate, a.rgb, a.gamma_tab, a.gamma_mode);
             launches++;
-            if (copy_back[0] && strip_copied) CUDA_TRY(cudaMemcpyAsync(user[0], dev[0], P.bytes[0], cudaMemcpyDeviceToHost, s->stream));
+            if (copy_back[0] && strip_copied && !P.async_copy) CUDA_TRY(cudaMemcpyAsync(user[0], dev[0], P.bytes[0], cudaMemcpyDeviceToHost, s->stream));
         }
         launches--; /* the common launches++ below counts one */
     } else if (variant == 3) {
@@ -2108,7 +2171,7 @@ int enqueue_frame(rt_scene* s, const FramePlan& P, int& launches, bool& strip_co
     launches++;
     CUDA_TRY(cudaGetLastError());
     for (int k = 0; k < 5; k++) /* host outputs of a frame rendered as one band (or by the one-kernel variants) */
-        if (copy_back[k] && !strip_copied) CUDA_TRY(cudaMemcpyAsync(user[k], dev[k], P.bytes[k], cudaMemcpyDeviceToHost, s->stream));
+        if (copy_back[k] && !strip_copied && !P.async_copy) CUDA_TRY(cudaMemcpyAsync(user[k], dev[k], P.bytes[k], cudaMemcpyDeviceToHost, s->stream));
     return RT_OK;
 }
 
@@ -2164,15 +2227,30 @@ int rt_render(rt_scene* s, const rt_params* p, uint32_t flags, uint8_t* rgb_out,
 
     bool graph_ok = s->opt.graph != 0 && P.variant == 2 && !P.count && !P.dbg_times;
     for (int k = 0; k < 5 && graph_ok; k++)
-        if (P.copy_back[k] && !is_pinned_host(P.user[k])) graph_ok = false; /* pageable host memory: the copy is not a pure stream operation */
+        if (P.copy_back[k] && !P.async_copy && !is_pinned_host(P.user[k])) graph_ok = false; /* pageable host memory: the copy is not a pure stream operation */
     std::vector<unsigned char> key;
     if (graph_ok) frame_key(s, P, key);
+    const int gs = P.async_copy ? P.scratch_set : 0;
 
+    if (P.async_copy) {
+        if (!s->copy_stream) {
+            CUDA_TRY(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+            CUDA_TRY(cudaEventCreateWithFlags(&s->copy_done[0], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&s->copy_done[1], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&s->frame_done, cudaEventDisableTiming));
+        }
+    }
+    /* this frame's kernels write scratch set P.scratch_set: the copy-back of the frame that used it last must have left it */
+    if (s->copy_recorded[P.scratch_set]) {
+        bool uses_scratch = false;
+        for (int k = 0; k < 5; k++) uses_scratch = uses_scratch || P.copy_back[k];
+        if (uses_scratch) CUDA_TRY(cudaStreamWaitEvent(s->stream, s->copy_done[P.scratch_set], 0));
+    }
     CUDA_TRY(cudaEventRecord(s->ev0, s->stream)); /* kernel_ms covers everything the frame enqueues, counter resets and copies to host outputs included */
-    if (graph_ok && s->graph_exec && key == s->graph_key) {
-        CUDA_TRY(cudaGraphLaunch(s->graph_exec, s->stream));
-        launches += s->graph_launches;
-    } else if (graph_ok && key == s->last_key) {
+    if (graph_ok && s->graph_exec[gs] && key == s->graph_key[gs]) {
+        CUDA_TRY(cudaGraphLaunch(s->graph_exec[gs], s->stream));
+        launches += s->graph_launches[gs];
+    } else if (graph_ok && key == s->last_key[gs]) {
         /* second identical frame in a row: record it */
         CUDA_TRY(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
         int n = 0;
@@ -2182,29 +2260,38 @@ int rt_render(rt_scene* s, const rt_params* p, uint32_t flags, uint8_t* rgb_out,
         if (rc != RT_OK || e != cudaSuccess) {
             if (graph) cudaGraphDestroy(graph);
             cudaGetLastError();
-            s->last_key.clear();
+            s->last_key[gs].clear();
             return rc != RT_OK ? rc : rtb::fail(RT_ERR_CUDA, "rt_render: cudaStreamEndCapture: %s", cudaGetErrorString(e));
         }
-        if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
-        s->graph_exec = nullptr;
-        const cudaError_t e2 = cudaGraphInstantiate(&s->graph_exec, graph, 0);
+        if (s->graph_exec[gs]) cudaGraphExecDestroy(s->graph_exec[gs]);
+        s->graph_exec[gs] = nullptr;
+        const cudaError_t e2 = cudaGraphInstantiate(&s->graph_exec[gs], graph, 0);
         cudaGraphDestroy(graph);
         if (e2 != cudaSuccess) {
-            s->graph_exec = nullptr;
-            s->last_key.clear();
+            s->graph_exec[gs] = nullptr;
+            s->last_key[gs].clear();
             return rtb::fail(RT_ERR_CUDA, "rt_render: cudaGraphInstantiate: %s", cudaGetErrorString(e2));
         }
-        s->graph_key = key;
-        s->graph_launches = n;
+        s->graph_key[gs] = key;
+        s->graph_launches[gs] = n;
         CUDA_TRY(cudaEventRecord(s->ev0, s->stream)); /* recording and instantiating are one-off costs, not frame time */
-        CUDA_TRY(cudaGraphLaunch(s->graph_exec, s->stream));
+        CUDA_TRY(cudaGraphLaunch(s->graph_exec[gs], s->stream));
         launches += n;
     } else {
         rc = enqueue_frame(s, P, launches, strip_copied);
         if (rc != RT_OK) return rc;
     }
-    s->last_key.swap(key);
+    s->last_key[gs].swap(key);
     CUDA_TRY(cudaEventRecord(s->ev1, s->stream));
+    if (P.async_copy) { /* the frame's host outputs: behind its kernels, beside the next frame's */
+        CUDA_TRY(cudaEventRecord(s->frame_done, s->stream));
+        CUDA_TRY(cudaStreamWaitEvent(s->copy_stream, s->frame_done, 0));
+        for (int k = 0; k < 5; k++)
+            if (P.copy_back[k]) CUDA_TRY(cudaMemcpyAsync(P.user[k], P.dev[k], P.bytes[k], cudaMemcpyDeviceToHost, s->copy_stream));
+        CUDA_TRY(cudaEventRecord(s->copy_done[P.scratch_set], s->copy_stream));
+        s->copy_recorded[P.scratch_set] = true;
+        s->copies_pending = true;
+    }
     s->pending = true; /* the counters are read back by rt_scene_sync, not per enqueued frame */
     s->pending_launches = launches;
     if (flags & RT_RENDER_NO_SYNC) {

@@ -67,3 +67,66 @@ def test_replayed_frames_equal_direct_launches(gpu, name, mirror, make):
     finally:
         ref_scene.close()
         sc.close()
+
+
+def test_pipelined_host_outputs(gpu):
+    """Frames enqueued with RT_RENDER_NO_SYNC into HOST buffers leave on the library's copy stream from two alternating scratch sets,
+    and rt_scene_set_mesh's fast path alternates between two pinned halves (rt_device.cu): whatever the interleaving — a changing
+    light, a mesh re-uploaded with moved vertices, pageable and pinned destinations, all five outputs, a synchronous frame in
+    between — every host buffer must hold exactly the frame a synchronous render of the same state returns."""
+    desc = scenes.cat_scene("optimized") or scenes.torus_scene("optimized")
+    ref_scene, sc = rt.Scene(gpu), rt.Scene(gpu)
+    try:
+        ref_scene.set_option("graph", 0)
+        scenes.upload(ref_scene, desc)
+        scenes.upload(sc, desc)
+        p = profiles.params("optimized", 640, 360, 1, 1)
+        v0, recs, bvh = desc["mesh"]
+        mm = desc["mesh_mat"]
+        kw = dict(albedo=mm["albedo"], mirror=mm["mirror"], n_in=mm["n_in"], n_out=mm["n_out"], id=mm["id"])
+        verts = [np.ascontiguousarray(v0, dtype=np.float32)]
+        moved = verts[0].copy()
+        moved[::7] += np.float32(0.01)  # same tree (arr_bvh unchanged: boxes are not re-fitted), different triangles
+        verts.append(moved)
+        n = 9
+        lights = [rt.move_light((-10.0, 20.0, 40.0), 1.309, 0.05 * (k // 3)) for k in range(n)]
+        names = ("rgb", "hit_obj", "hit_tri", "hit_t", "shadow")
+        want = []
+        for k in range(n):
+            ref_scene.set_light(lights[k], 3e10)
+            ref_scene.set_mesh(verts[k & 1], recs, bvh, **kw)
+            want.append(ref_scene.render(p, want=names))
+        # distinct destinations for every frame: nothing may be torn by a later frame
+        outs = []
+        for k in range(n):
+            o = {}
+            for nm in names:
+                w = want[k][nm]
+                t = torch.zeros(w.shape, dtype=torch.from_numpy(w).dtype)
+                o[nm] = (t.pin_memory() if k % 2 == 0 else t).numpy()
+            outs.append(o)
+        for k in range(n):
+            sc.set_light(lights[k], 3e10)
+            sc.set_mesh(verts[k & 1], recs, bvh, **kw)
+            if k == 5:  # a synchronous frame in the middle of the pipeline (uses scratch set 0 as well)
+                sc.render_into(p, **outs[k])
+            else:
+                sc.render_into(p, flags=rt.RT_RENDER_NO_SYNC, **outs[k])
+        sc.sync()
+        for k in range(n):
+            for nm in names:
+                assert np.array_equal(outs[k][nm], want[k][nm]), (k, nm)
+        # a static scene: the two scratch sets each record a graph and replay it
+        a = torch.zeros((p.H, p.W, 3), dtype=torch.uint8).pin_memory()
+        b = torch.zeros((p.H, p.W, 3), dtype=torch.uint8).pin_memory()
+        for k in range(8):
+            sc.set_mesh(verts[0], recs, bvh, **kw)
+            sc.render_into(p, rgb=(a if k % 2 == 0 else b).numpy(), flags=rt.RT_RENDER_NO_SYNC)
+        st = sc.sync()
+        ref_scene.set_mesh(verts[0], recs, bvh, **kw)
+        w = ref_scene.render(p, want=("rgb",))["rgb"]
+        assert np.array_equal(a.numpy(), w) and np.array_equal(b.numpy(), w)
+        assert st.rays > 0
+    finally:
+        ref_scene.close()
+        sc.close()
