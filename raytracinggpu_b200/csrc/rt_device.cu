@@ -131,6 +131,14 @@ struct rt_scene {
     cudaEvent_t pin_ev[2] = {nullptr, nullptr};
     bool pin_ev_recorded[2] = {false, false};
     int pin_set = 0;
+    /* ... and goes to the device on an upload stream of its own, into one of two small staging buffers: the copy runs while the frame before
+     * renders instead of queueing behind that frame's copy-back (H2D behind D2H cost 0.09 ms per step, profiles/r02_notes.md) */
+    cudaStream_t up_stream = nullptr;
+    unsigned char* stage_up[2] = {nullptr, nullptr};
+    size_t stage_up_bytes[2] = {0, 0};
+    cudaEvent_t stage_free[2] = {nullptr, nullptr};
+    bool stage_free_recorded[2] = {false, false};
+    const int32_t* cur_recs = nullptr; /* the triangle records of the last upload on the device (rt_scene_set_mesh_normals reads words 6-8) */
 
     /* pending copy-back of a RT_RENDER_NO_SYNC call */
     bool pending = false;
@@ -603,6 +611,14 @@ void rt_scene_destroy(rt_scene* s) {
     }
     if (s->frame_done) cudaEventDestroy(s->frame_done);
     if (s->pin_alt) cudaFreeHost(s->pin_alt);
+    if (s->up_stream) {
+        cudaStreamSynchronize(s->up_stream);
+        cudaStreamDestroy(s->up_stream);
+    }
+    for (int k = 0; k < 2; k++) {
+        if (s->stage_up[k]) cudaFree(s->stage_up[k]);
+        if (s->stage_free[k]) cudaEventDestroy(s->stage_free[k]);
+    }
     for (int k = 0; k < 2; k++)
         if (s->graph_exec[k]) cudaGraphExecDestroy(s->graph_exec[k]);
     if (s->tri_normals) cudaFree(s->tri_normals);
@@ -781,17 +797,33 @@ int rt_scene_set_mesh(rt_scene* s, const float* vertices, int32_t nv, const int3
             CUDA_TRY(cudaMallocHost(&s->pin_alt, up_bytes + up_bytes / 4));
             s->pin_alt_bytes = up_bytes + up_bytes / 4;
         }
+        if (!s->up_stream) CUDA_TRY(cudaStreamCreateWithFlags(&s->up_stream, cudaStreamNonBlocking));
         if (!s->pin_ev[half]) CUDA_TRY(cudaEventCreateWithFlags(&s->pin_ev[half], cudaEventDisableTiming));
-        if (s->pin_ev_recorded[half]) CUDA_TRY(cudaEventSynchronize(s->pin_ev[half]));
+        if (!s->stage_free[half]) CUDA_TRY(cudaEventCreateWithFlags(&s->stage_free[half], cudaEventDisableTiming));
+        if (s->stage_up_bytes[half] < up_bytes) {
+            CUDA_TRY(cudaStreamSynchronize(s->stream));
+            if (s->stage_up[half]) cudaFree(s->stage_up[half]);
+            s->stage_up[half] = nullptr;
+            s->stage_up_bytes[half] = 0;
+            CUDA_TRY(cudaMalloc(&s->stage_up[half], up_bytes + up_bytes / 4));
+            s->stage_up_bytes[half] = up_bytes + up_bytes / 4;
+        }
+        if (s->pin_ev_recorded[half]) CUDA_TRY(cudaEventSynchronize(s->pin_ev[half])); /* the upload before last has left this pinned half */
         unsigned char* const pin = half ? s->pin_alt : s->pin;
+        unsigned char* const stage = s->stage_up[half];
         memcpy(pin, vertices, vbytes);
         memcpy(pin + r_off, tri_records, rbytes);
-        CUDA_TRY(cudaMemcpyAsync(s->stage, pin, up_bytes, cudaMemcpyHostToDevice, s->stream));
-        CUDA_TRY(cudaEventRecord(s->pin_ev[half], s->stream));
+        if (s->stage_free_recorded[half]) CUDA_TRY(cudaStreamWaitEvent(s->up_stream, s->stage_free[half], 0)); /* its last repack has read it */
+        CUDA_TRY(cudaMemcpyAsync(stage, pin, up_bytes, cudaMemcpyHostToDevice, s->up_stream));
+        CUDA_TRY(cudaEventRecord(s->pin_ev[half], s->up_stream));
         s->pin_ev_recorded[half] = true;
+        CUDA_TRY(cudaStreamWaitEvent(s->stream, s->pin_ev[half], 0));
         const int threads = 256, blocks = (nt + threads - 1) / threads;
-        rtk::repack_triangles<<<blocks, threads, 0, s->stream>>>(reinterpret_cast<float*>(s->stage), reinterpret_cast<int32_t*>(s->stage + r_off), nt,
+        rtk::repack_triangles<<<blocks, threads, 0, s->stream>>>(reinterpret_cast<float*>(stage), reinterpret_cast<int32_t*>(stage + r_off), nt,
                                                                 reinterpret_cast<int32_t*>(s->stage + l_off), reinterpret_cast<float4*>(s->blob + h.off_tris));
+        CUDA_TRY(cudaEventRecord(s->stage_free[half], s->stream));
+        s->stage_free_recorded[half] = true;
+        s->cur_recs = reinterpret_cast<const int32_t*>(stage + r_off);
         CUDA_TRY(cudaGetLastError());
         s->has_normals = false; /* the records were uploaded again: rt_scene_set_mesh_normals must follow */
         const bool same_material = h.mesh_id == id && h.mesh_mirror == (mirror ? 1 : 0) && h.mesh_n_in == n_in && h.mesh_n_out == n_out &&
@@ -1113,6 +1145,7 @@ int rt_scene_set_mesh(rt_scene* s, const float* vertices, int32_t nv, const int3
     s->last_nv = pin_need <= ((size_t)64 << 20) ? nv : 0; /* the fast path needs the pinned staging layout */
     s->last_nt = nt;
     s->stage_r_off = r_off;
+    s->cur_recs = reinterpret_cast<const int32_t*>(s->stage + r_off);
     s->stage_nt = nt;
     s->has_normals = false;
     h.n_wide = n_wide;
@@ -1327,7 +1360,7 @@ int rt_scene_set_mesh_normals(rt_scene* s, const float* normals, int32_t n_norma
         s->tri_normals_cap = (size_t)nt * 3;
     }
     CUDA_TRY(cudaMemcpyAsync(s->d_normals, normals, (size_t)n_normals * 3 * sizeof(float), cudaMemcpyHostToDevice, s->stream));
-    rtk::repack_normals<<<(nt + 255) / 256, 256, 0, s->stream>>>(s->d_normals, n_normals, reinterpret_cast<const int32_t*>(s->stage + s->stage_r_off), nt, s->tri_normals);
+    rtk::repack_normals<<<(nt + 255) / 256, 256, 0, s->stream>>>(s->d_normals, n_normals, s->cur_recs, nt, s->tri_normals);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaStreamSynchronize(s->stream)); /* the caller's array may go away */
     s->has_normals = true;
