@@ -296,6 +296,9 @@ int rt_gather_framebuffer(rt_scene* s, rt_comm* c, const void* band, int32_t W, 
  * blocks*256*per_thread pseudo-random operand pairs. out[0] = mismatches with one correction step,
  * out[1] = with two, out[2] = pairs tested. */
 int rt_selftest_division(int device, uint64_t seed, int blocks, int per_thread, uint64_t out[3]);
+/* the three-quotients-one-reciprocal division of the shading code (rt_math.cuh: div3) against div.rn.f32: out[0] differing
+ * components, out[1] components tested */
+int rt_selftest_division3(int device, uint64_t seed, int blocks, int per_thread, uint64_t out[2]);
 /* Device self-test: the cuRAND library's XORWOW start states (d, v0..v4: n*6 words) and first four curand_uniform values
  * (n*4 floats) of the listed subsequences — the random stream of optimized.cu:745 that the stochastic mode reproduces. */
 int rt_selftest_xorwow(int device, uint64_t seed, const uint32_t* subsequences, int32_t n, uint32_t* states6, float* uniforms4);

@@ -84,6 +84,7 @@ SIGNATURES = {
     "rt_selftest_fma_peak": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "rt_selftest_libm": (C.c_int, [C.c_int, C.c_int, _vp, _i32, _vp]),
     "rt_selftest_division": (C.c_int, [C.c_int, _u64, C.c_int, C.c_int, C.POINTER(_u64)]),
+    "rt_selftest_division3": (C.c_int, [C.c_int, _u64, C.c_int, C.c_int, C.POINTER(_u64)]),
     "rt_selftest_xorwow": (C.c_int, [C.c_int, _u64, _vp, C.c_int32, _vp, _vp]),
 }
 # rt_default_walls(profile, walls, mesh_id): fix the argument order to the header's
@@ -509,6 +510,12 @@ def selftest_division(device=0, seed=1, blocks=148 * 8, per_thread=4096):
     out = (C.c_uint64 * 3)()
     _check(lib().rt_selftest_division(device, seed, blocks, per_thread, out))
     return {"mismatch_1step": out[0], "mismatch_2step": out[1], "pairs": out[2]}
+
+
+def selftest_division3(device=0, seed=1, blocks=148 * 8, per_thread=2048):
+    out = (C.c_uint64 * 2)()
+    _check(lib().rt_selftest_division3(device, seed, blocks, per_thread, out))
+    return {"mismatch": out[0], "components": out[1]}
 
 
 def selftest_xorwow(subsequences, seed=123456, device=0):

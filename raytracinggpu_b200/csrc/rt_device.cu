@@ -56,6 +56,7 @@ struct RtOptions {
                               * restates the functions for the CPU (rt_oracle.cpp: cuda_logf ...); 0 evaluated in double and rounded once
                               * (the oracle's other canon: what a correctly rounded libm would give; 3-4x the instructions) */
     int graph = 1;           /* replay a recorded CUDA graph when a frame repeats the previous call's plan */
+    int six = 1;             /* kernels with the sphere loops unrolled for the reference's room of exactly six spheres (constants as direct operands) */
     int one_shot = 1;        /* stochastic frames of one sample and one segment through the deterministic pipeline with jittered camera rays */
     int pdl = 0;             /* programmatic dependent launch between consecutive kernels of a band (LaunchChain). Measured (profiles/r02_notes.md):
                               * no gain once a frame is a replayed graph (1/8 shard 0.299 vs 0.300 ms), +1 % on the full frame: off */
@@ -87,6 +88,7 @@ static const RtOptionKey kOptionKeys[] = {
     {"graph", &RtOptions::graph, 0, 1},
     {"pdl", &RtOptions::pdl, 0, 1},
     {"one_shot", &RtOptions::one_shot, 0, 1},
+    {"six", &RtOptions::six, 0, 1},
     {"debug_times", &RtOptions::debug_times, 0, 1},
     {"debug_pool", &RtOptions::debug_pool, 0, 1},
     {"debug_bins", &RtOptions::debug_bins, 0, 1},
@@ -1968,6 +1970,7 @@ int enqueue_frame(rt_scene* s, const FramePlan& P, int& launches, bool& strip_co
     const rtk::RenderArgs& a = P.a;
     const bool stochastic = P.stochastic, count = P.count, wide = P.wide, anchored = P.anchored, diffuse_only = P.diffuse_only, trav_round0 = P.trav_round0,
                dbg_times = P.dbg_times;
+    const bool six = s->header.n_spheres == 6 && s->opt.six != 0;
     const int segments = P.segments, npool_cap = P.npool_cap, n_strips = P.n_strips, spill_cap = P.spill_cap, rows = P.rows, variant = P.variant;
     const size_t trav_smem = P.trav_smem, st_rng_off = P.st_rng_off, st_total_off = P.st_total_off, st_rec_off = P.st_rec_off, task_slack = P.task_slack;
     const unsigned pers_grid = P.pers_grid, grid = P.grid;
@@ -2077,11 +2080,13 @@ int enqueue_frame(rt_scene* s, const FramePlan& P, int& launches, bool& strip_co
                 else if (diffuse_only) CUDA_TRY(chain.launch(rtk::wf_generate<false, true, true>, dim3(gen_grid), WF_THREADS, 0, stream, s->header, s->blob, g));
                 else CUDA_TRY(chain.launch(rtk::wf_generate<false, true>, dim3(gen_grid), WF_THREADS, 0, stream, s->header, s->blob, g));
             } else if (P.jitter) {
-                if (diffuse_only && anchored) CUDA_TRY(chain.launch(rtk::wf_generate<false, false, true, true, true>, dim3(gen_grid), WF_THREADS, 0, stream, s->header, s->blob, g));
+                if (diffuse_only && anchored && six) CUDA_TRY(chain.launch(rtk::wf_generate<false, false, true, true, true, 6>, dim3(gen_grid), WF_THREADS, 0, stream, s->header, s->blob, g));
+                else if (diffuse_only && anchored) CUDA_TRY(chain.launch(rtk::wf_generate<false, false, true, true, true>, dim3(gen_grid), WF_THREADS, 0, stream, s->header, s->blob, g));
                 else if (diffuse_only) CUDA_TRY(chain.launch(rtk::wf_generate<false, false, true, false, true>, dim3(gen_grid), WF_THREADS, 0, stream, s->header, s->blob, g));
                 else CUDA_TRY(chain.launch(rtk::wf_generate<false, false, false, false, true>, dim3(gen_grid), WF_THREADS, 0, stream, s->header, s->blob, g));
             } else {
                 if (count) CUDA_TRY(chain.launch(rtk::wf_generate<true, false>, dim3(gen_grid), WF_THREADS, 0, stream, s->header, s->blob, g));
+                else if (diffuse_only && anchored && six) CUDA_TRY(chain.launch(rtk::wf_generate<false, false, true, true, false, 6>, dim3(gen_grid), WF_THREADS, 0, stream, s->header, s->blob, g));
                 else if (diffuse_only && anchored) CUDA_TRY(chain.launch(rtk::wf_generate<false, false, true, true>, dim3(gen_grid), WF_THREADS, 0, stream, s->header, s->blob, g));
                 else if (diffuse_only) CUDA_TRY(chain.launch(rtk::wf_generate<false, false, true>, dim3(gen_grid), WF_THREADS, 0, stream, s->header, s->blob, g));
                 else CUDA_TRY(chain.launch(rtk::wf_generate<false, false>, dim3(gen_grid), WF_THREADS, 0, stream, s->header, s->blob, g));
@@ -2144,6 +2149,7 @@ int enqueue_frame(rt_scene* s, const FramePlan& P, int& launches, bool& strip_co
                     else CUDA_TRY(chain.launch(rtk::wf_shade<false, true>, dim3(shade_grid), WF_THREADS, 0, stream, s->header, s->blob, g));
                 } else {
                     if (count) CUDA_TRY(chain.launch(rtk::wf_shade<true, false>, dim3(shade_grid), WF_THREADS, 0, stream, s->header, s->blob, g));
+                    else if (diffuse_only && anchored && six) CUDA_TRY(chain.launch(rtk::wf_shade<false, false, true, true, 6>, dim3(shade_grid), WF_THREADS, 0, stream, s->header, s->blob, g));
                     else if (diffuse_only && anchored) CUDA_TRY(chain.launch(rtk::wf_shade<false, false, true, true>, dim3(shade_grid), WF_THREADS, 0, stream, s->header, s->blob, g));
                     else if (diffuse_only) CUDA_TRY(chain.launch(rtk::wf_shade<false, false, true>, dim3(shade_grid), WF_THREADS, 0, stream, s->header, s->blob, g));
                     else CUDA_TRY(chain.launch(rtk::wf_shade<false, false>, dim3(shade_grid), WF_THREADS, 0, stream, s->header, s->blob, g));
@@ -2511,6 +2517,26 @@ int rt_selftest_division(int device, uint64_t seed, int blocks, int per_thread, 
     out[0] = hst[0];
     out[1] = hst[1];
     out[2] = hst[2];
+    return RT_OK;
+}
+
+/* Device self-test used by tests/: div3 / div3_or_zero (one refined reciprocal for three quotients) against three div.rn.f32.
+ * out[0] components that differ, out[1] components tested. */
+int rt_selftest_division3(int device, uint64_t seed, int blocks, int per_thread, uint64_t out[2]) {
+    if (!out || blocks <= 0 || per_thread <= 0) return rtb::fail(RT_ERR_INVALID, "rt_selftest_division3: bad argument");
+    DeviceGuard g(device);
+    if (!g.ok) return rtb::fail(RT_ERR_CUDA, "rt_selftest_division3: no device %d", device);
+    unsigned long long* d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, 2 * sizeof(unsigned long long)));
+    cudaMemset(d, 0, 2 * sizeof(unsigned long long));
+    rtk::selftest_division3<<<blocks, 256>>>(seed, per_thread, d);
+    cudaError_t e = cudaDeviceSynchronize();
+    unsigned long long hst[2] = {0, 0};
+    if (e == cudaSuccess) e = cudaMemcpy(hst, d, sizeof hst, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return rtb::fail(RT_ERR_CUDA, "rt_selftest_division3: %s", cudaGetErrorString(e));
+    out[0] = hst[0];
+    out[1] = hst[1];
     return RT_OK;
 }
 

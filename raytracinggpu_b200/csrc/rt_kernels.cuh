@@ -580,4 +580,39 @@ __global__ void selftest_division(unsigned long long seed, int per_thread, unsig
     atomicAdd(out + 2, (unsigned long long)n);
 }
 
+/* Device self-test of div3 / div3_or_zero (rt_math.cuh) against three div.rn.f32: pseudo-random triples and divisors across and beyond
+ * the guarded range (exponents 2^[-70, 70], zeros, hard mantissas), normalisation-shaped inputs (n = sqrtf(norm2)) and the constant pi.
+ * out[0] += components that differ in any bit, out[1] += components tested. */
+__global__ void selftest_division3(unsigned long long seed, int per_thread, unsigned long long* out) {
+    unsigned long long s = seed + 0x9E3779B97F4A7C15ull * (blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x + 1);
+    unsigned int bad = 0, n = 0;
+    for (int it = 0; it < per_thread; it++) {
+        float v[4];
+        for (int k = 0; k < 4; k++) {
+            s ^= s << 13; s ^= s >> 7; s ^= s << 17;
+            const unsigned int r = (unsigned int)(s >> 16);
+            const unsigned int e = 127 - 70 + (r >> 24) % 141;
+            unsigned int m = r & 0x7fffffu;
+            if (((it + k) & 7) == 0) m = (it & 8) ? (0x7fffffu - (m & 0xff)) : (m & 0xff);
+            v[k] = __uint_as_float(((r >> 23) & 1u) << 31 | e << 23 | m);
+            if ((r & 0x3f000000u) == 0x15000000u) v[k] = (r & 1) ? 0.f : -0.f; /* exact zeros of either sign */
+        }
+        F3 a = f3(v[0], v[1], v[2]);
+        float d = v[3];
+        const int shape = it & 3;
+        if (shape == 1) { /* a normalisation: moderate components, the divisor is their norm */
+            a = f3(v[0] * 1e-3f, (float)((int)(s & 0xffff) - 32768) * 0.5f, v[2] > 0 ? 0.57735026f : 940.f);
+            d = sqrtf(norm2(a));
+        } else if (shape == 2) {
+            d = 3.14159274f;
+        }
+        const F3 ref = f3(a.x / d, a.y / d, a.z / d);
+        const F3 q = shape == 2 ? div3_or_zero(a, d) : div3(a, d);
+        bad += (__float_as_uint(q.x) != __float_as_uint(ref.x)) + (__float_as_uint(q.y) != __float_as_uint(ref.y)) + (__float_as_uint(q.z) != __float_as_uint(ref.z));
+        n += 3;
+    }
+    atomicAdd(out + 0, (unsigned long long)bad);
+    atomicAdd(out + 1, (unsigned long long)n);
+}
+
 } // namespace rtk

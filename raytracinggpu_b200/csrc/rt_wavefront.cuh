@@ -189,11 +189,14 @@ __device__ __forceinline__ bool outside_contract(F3 u) {
 
 /* closest_sphere for a ray that starts at the camera: O - C and |O - C|^2 - R^2 of Sphere::intersect (optimized.cu:124-126)
  * do not depend on the pixel; cam_sph holds them (same operations, same order, evaluated once on the host). */
+/* NS > 0: the host knows the scene has exactly NS spheres (the reference's room: six walls); the loops over them are unrolled completely and
+ * every sphere constant becomes an operand from the constant bank instead of an indexed load */
+template <int NS = 0>
 __device__ __forceinline__ void closest_sphere_cam(const SceneHeader& h, const float4* __restrict__ cam_sph, F3 u, float& ts, int& sidx) {
     ts = RTK_INF;
     sidx = -1;
-#pragma unroll 2
-    for (int k = 0; k < h.n_spheres; k++) {
+#pragma unroll(NS > 0 ? NS : 2)
+    for (int k = 0; k < (NS > 0 ? NS : h.n_spheres); k++) {
         const float4 c = cam_sph[k];
         const float b = dot(u, f3(c.x, c.y, c.z));
         const float delta = b * b - c.w;
@@ -288,7 +291,7 @@ __device__ __forceinline__ void light_is_blocked(const RenderArgs& a, const WfAr
 /* LEAN (with DIFFUSE, deterministic mode, anchored-ray bins in use — the primary + shadow pipeline): every query is an
  * anchored one and every path ends at its first hit, so the tree-search branches (root-box tests with their exact
  * fallbacks, the general sphere search, the posting of tree-searched queries) are left out as well. */
-template <bool COUNT, bool STOCH, bool DIFFUSE = false, bool LEAN = false>
+template <bool COUNT, bool STOCH, bool DIFFUSE = false, bool LEAN = false, int NS = 0>
 __device__ __forceinline__ void path_advance(const SceneHeader& h, const WfArgs& g, const float4* __restrict__ nodes, const float4* __restrict__ tris, int px, F3 O, F3 u, float n_ray,
                                              int depth, bool have_hit, float t_hit, int sidx, int tri, Work& w, Post& post) {
     const RenderArgs& a = g.a;
@@ -302,7 +305,7 @@ __device__ __forceinline__ void path_advance(const SceneHeader& h, const WfArgs&
                 return;
             }
             w.rays++;
-            if (LEAN || depth == 0) closest_sphere_cam(h, g.cam_sph, u, t_hit, sidx); /* depth 0 without a hit: the camera ray (wf_generate) */
+            if (LEAN || depth == 0) closest_sphere_cam<NS>(h, g.cam_sph, u, t_hit, sidx); /* depth 0 without a hit: the camera ray (wf_generate) */
             else closest_sphere(h, O, u, t_hit, sidx);
             tri = -1;
             if (h.has_mesh && (LEAN || (g.anchored && depth == 0))) {
@@ -369,7 +372,7 @@ __device__ __forceinline__ void path_advance(const SceneHeader& h, const WfArgs&
         float n_in, n_out;
         if (tri < 0) {
             const DevSphere& s = h.spheres[sidx];
-            N = normalized(P - f3(s.cx, s.cy, s.cz)); /* :132-133 */
+            N = normalized3(P - f3(s.cx, s.cy, s.cz)); /* :132-133 */
             albedo = f3(s.ax, s.ay, s.az);
             mirror = s.mirror;
             n_in = s.n_in;
@@ -413,7 +416,7 @@ __device__ __forceinline__ void path_advance(const SceneHeader& h, const WfArgs&
             const F3 toL = Lp - Padj;
             const float D2 = norm2(toL);
             const float rootD = sqrtf(D2);
-            const F3 su = toL / rootD; /* NORMED_VEC :618 */
+            const F3 su = div3(toL, rootD); /* NORMED_VEC :618 */
             /* shadow ray: the spheres here, the mesh through the queue (see mesh_query for the equivalence) */
             w.rays++;
             bool blocked = false;
@@ -428,8 +431,8 @@ __device__ __forceinline__ void path_advance(const SceneHeader& h, const WfArgs&
             const float A = fmaxf(fmaxf(fabsf(Padj.x), fabsf(Padj.y)), fabsf(Padj.z));
             const float T_hi = (rootD + A * 3.814697265625e-06f) * 1.00000762939453125f;
             /* no early exit: a sphere that blocks is rare, and without the exit the tests are independent of one another */
-#pragma unroll 2
-            for (int s = 0; s < h.n_spheres; s++) {
+#pragma unroll(NS > 0 ? NS : 2)
+            for (int s = 0; s < (NS > 0 ? NS : h.n_spheres); s++) {
                 const DevSphere& sp = h.spheres[s];
                 const F3 OC = f3(Padj.x - sp.cx, Padj.y - sp.cy, Padj.z - sp.cz);
                 const float b = dot(su, OC);
@@ -448,11 +451,11 @@ __device__ __forceinline__ void path_advance(const SceneHeader& h, const WfArgs&
             F3 dcol = f3(0.f, 0.f, 0.f);
             if (!blocked) {
                 const F3 PL = Lp - P;
-                const F3 wl = normalized(PL);
+                const F3 wl = normalized3(PL);
                 const float ndl = dot(N, wl);
                 const float lambert = (ndl < 0.f) ? 0.f : ndl; /* std::max(dot, 0.f) */
                 const float l = (float)((double)h.intensity / (12.566370614359172 * (double)norm2(PL)) * (double)lambert); /* :628, in double */
-                dcol = (l * albedo) / 3.14159274f;                                                                        /* :629 */
+                dcol = div3_or_zero(l * albedo, 3.14159274f);                                                                       /* :629 */
             }
             const int seg = depth - 1;
             if (!STOCH) {
@@ -670,7 +673,7 @@ __device__ __forceinline__ void answer_deferred(const SceneHeader& h, const unsi
 /* ---- wf_generate: one thread per pixel (a warp covers an 8x4 tile) ------------------------------------------------ */
 /* JITTER (deterministic instantiations only): the camera ray takes the Box-Muller jitter of optimized.cu:753-759 from the first two
  * uniforms of the pixel's stream; nothing else of the stochastic mode is needed when a frame is one sample of one segment. */
-template <bool COUNT, bool STOCH, bool DIFFUSE = false, bool LEAN = false, bool JITTER = false>
+template <bool COUNT, bool STOCH, bool DIFFUSE = false, bool LEAN = false, bool JITTER = false, int NS = 0>
 __global__ void __launch_bounds__(WF_THREADS, 10) wf_generate(const __grid_constant__ SceneHeader h, const unsigned char* __restrict__ blob,
                                                          const __grid_constant__ WfArgs g) {
     pdl_wait_then_release();
@@ -701,9 +704,9 @@ __global__ void __launch_bounds__(WF_THREADS, 10) wf_generate(const __grid_const
             /* the jitter of the pixel's FIRST sample, optimized.cu:756-758: a function of (seed, global pixel index, sigma) only, kept in a
              * table beside the stream start states (jitter_table below) */
             const float2 jt = __ldg(g.jitter_tab + (size_t)i * a.W + j);
-            u0 = normalized(uc + f3(jt.x, jt.y, 0.f)); /* :758-759 */
+            u0 = normalized3(uc + f3(jt.x, jt.y, 0.f)); /* :758-759 */
         } else if (!STOCH) {
-            u0 = normalized(uc); /* sigma == 0: the jitter terms of :758 are exactly 0 */
+            u0 = normalized3(uc); /* sigma == 0: the jitter terms of :758 are exactly 0 */
         } else {
             /* the pixel's stream: sample 0 starts from curand_init(seed, GLOBAL pixel index, 0) (optimized.cu:745), later
              * samples from where the previous sample's path left it */
@@ -724,7 +727,7 @@ __global__ void __launch_bounds__(WF_THREADS, 10) wf_generate(const __grid_const
             const float rad = g.aa_sigma * sqrtf(-2 * (g.libm ? logf(r1) : canon_log(r1)));
             const float ang = (float)(2 * 3.14159265358979323846 * (double)r2);
             const float ca = g.libm ? cosf(ang) : canon_cos(ang), sa = g.libm ? sinf(ang) : canon_sin(ang);
-            u0 = normalized(uc + f3(rad * ca, rad * sa, 0.f)); /* :758-759 */
+            u0 = normalized3(uc + f3(rad * ca, rad * sa, 0.f)); /* :758-759 */
         }
         if (!STOCH || g.sample == 0) {
             if (a.hit_obj) a.hit_obj[px] = -1;
@@ -732,7 +735,7 @@ __global__ void __launch_bounds__(WF_THREADS, 10) wf_generate(const __grid_const
             if (a.hit_t) a.hit_t[px] = RTK_INF;
             if (a.shadow) a.shadow[px] = 2;
         }
-        path_advance<COUNT, STOCH, DIFFUSE, LEAN>(h, g, nodes, tris, px, f3(a.camx, a.camy, a.camz), u0, 1.f, 0, false, 0.f, -1, -1, w, post);
+        path_advance<COUNT, STOCH, DIFFUSE, LEAN, NS>(h, g, nodes, tris, px, f3(a.camx, a.camy, a.camz), u0, 1.f, 0, false, 0.f, -1, -1, w, post);
     }
     const int slot = post_queries<LEAN>(g, 0, post, px);
     if (LEAN || g.anchored) {
@@ -743,7 +746,7 @@ __global__ void __launch_bounds__(WF_THREADS, 10) wf_generate(const __grid_const
 }
 
 /* ---- wf_shade: one thread per answered closest-hit query of round g.round ------------------------------------------ */
-template <bool COUNT, bool STOCH, bool DIFFUSE = false, bool LEAN = false>
+template <bool COUNT, bool STOCH, bool DIFFUSE = false, bool LEAN = false, int NS = 0>
 __global__ void __launch_bounds__(WF_THREADS, 8) wf_shade(const __grid_constant__ SceneHeader h, const unsigned char* __restrict__ blob,
                                                       const __grid_constant__ WfArgs g) {
     pdl_wait_then_release();
@@ -786,7 +789,7 @@ __global__ void __launch_bounds__(WF_THREADS, 8) wf_shade(const __grid_constant_
 #ifdef RT_TRACE
             printf("  shade e %d px %d key %llx t_hit %f sidx %d tri %d depth %d\n", e, px, key, t_hit, sidx, tri, depth);
 #endif
-            path_advance<COUNT, STOCH, DIFFUSE, LEAN>(h, g, nodes, tris, px, O, u, p2.x, depth, true, t_hit, sidx, tri, w, post);
+            path_advance<COUNT, STOCH, DIFFUSE, LEAN, NS>(h, g, nodes, tris, px, O, u, p2.x, depth, true, t_hit, sidx, tri, w, post);
         }
         const int slot = post_queries<LEAN>(g, g.round + 1, post, px);
         if (LEAN || g.anchored) {

@@ -12,6 +12,9 @@ Hd = int(sys.argv[3]) if len(sys.argv) > 3 else 1080
 mesh, walls, mesh_id, name = bench.build_scene_host(rt)
 sc = rt.Scene(0)
 sc.set_option("graph", 0)  # ncu: plain launches, one per kernel
+for kv in os.environ.get("RT_OPTS", "").split(","):  # e.g. RT_OPTS=six=0,strips=1
+    if kv:
+        sc.set_option(kv.split("=")[0], int(kv.split("=")[1]))
 sc.set_spheres(walls)
 sc.set_mesh(mesh.vertices, mesh.tri_records, mesh.arr_bvh, id=mesh_id)
 p = rt.params_profile("optimized", Wd, Hd, 1, 1)
