@@ -112,7 +112,10 @@ typedef struct rt_stats {
 
 /* rt_render flags */
 #define RT_RENDER_COUNT_WORK 1u   /* fill node_visits / tri_tests / max_stack (slower instrumented kernel) */
-#define RT_RENDER_NO_SYNC    2u   /* enqueue only; kernel_ms and rays are not filled; call rt_scene_sync later */
+#define RT_RENDER_NO_SYNC    2u   /* enqueue only; kernel_ms and rays are not filled; call rt_scene_sync later. HOST output buffers of
+                                    * such a frame are filled on a copy stream behind the frame's kernels (two alternating device staging
+                                    * sets: the copy of frame k runs beside the kernels of frame k + 1) and are valid after rt_scene_sync;
+                                    * consecutive NO_SYNC frames must therefore be given different host buffers if both are to be read */
 
 typedef struct rt_mesh rt_mesh;     /* host-side TriangleMeshHost replacement */
 typedef struct rt_scene rt_scene;   /* device-resident Scene replacement */
@@ -209,7 +212,7 @@ int rt_scene_get_stream(rt_scene* s, void** cuda_stream);
  *   "wide" -1|0|1             4-wide index for the tree search: default on for stochastic indirect bounces only
  *   "strips" 0..8             row bands on separate streams, 0 = chosen per call
  *   "bins_r", "task_factor", "npool_cap", "run_shift", "gss", "leaves_blocks", "side_stream", "diffuse_kernels",
- *   "stoch_mega", "wide_count", "graph", "debug_times", "debug_pool", "debug_bins", "debug_cost"   (see rt_device.cu: RtOptions)
+ *   "stoch_mega", "wide_count", "graph", "six", "split", "debug_times", "debug_pool", "debug_bins", "debug_cost"   (see rt_device.cu: RtOptions)
  *   "transcendentals" 1|0     stochastic mode: log / cos / sin of optimized.cu:756-758, 635-636 by CUDA's single-precision
  *                             logf / cosf / sinf (1, default: what optimized.cu itself calls; frames equal those of the reference
  *                             kernel compiled without --use_fast_math bit for bit) or evaluated in double and rounded once (0)

@@ -56,6 +56,7 @@ struct RtOptions {
                               * restates the functions for the CPU (rt_oracle.cpp: cuda_logf ...); 0 evaluated in double and rounded once
                               * (the oracle's other canon: what a correctly rounded libm would give; 3-4x the instructions) */
     int graph = 1;           /* replay a recorded CUDA graph when a frame repeats the previous call's plan */
+    int split = 0;           /* two row bands: per cent of the rows in the first band; 0: equal halves */
     int six = 1;             /* kernels with the sphere loops unrolled for the reference's room of exactly six spheres (constants as direct operands) */
     int one_shot = 1;        /* stochastic frames of one sample and one segment through the deterministic pipeline with jittered camera rays */
     int pdl = 0;             /* programmatic dependent launch between consecutive kernels of a band (LaunchChain). Measured (profiles/r02_notes.md):
@@ -89,6 +90,7 @@ static const RtOptionKey kOptionKeys[] = {
     {"pdl", &RtOptions::pdl, 0, 1},
     {"one_shot", &RtOptions::one_shot, 0, 1},
     {"six", &RtOptions::six, 0, 1},
+    {"split", &RtOptions::split, 0, 95},
     {"debug_times", &RtOptions::debug_times, 0, 1},
     {"debug_pool", &RtOptions::debug_pool, 0, 1},
     {"debug_bins", &RtOptions::debug_bins, 0, 1},
@@ -1998,6 +2000,7 @@ int enqueue_frame(rt_scene* s, const FramePlan& P, int& launches, bool& strip_co
     for (int st = 0; st < n_strips; st++) {
         /* band boundaries on multiples of 8 rows (generate tiles are 8x4) */
         int row1 = (st == n_strips - 1) ? rows : (int)(((long long)rows * (st + 1) / n_strips) & ~7ll);
+        if (n_strips == 2 && st == 0 && s->opt.split > 0) row1 = (int)(((long long)rows * s->opt.split / 100) & ~7ll);
         if (row1 <= row0) continue;
         const int srows = row1 - row0;
         const size_t spx = (size_t)srows * p->W, px0 = (size_t)row0 * p->W;
