@@ -135,6 +135,12 @@ struct rt_scene {
     cudaEvent_t pin_ev[2] = {nullptr, nullptr};
     bool pin_ev_recorded[2] = {false, false};
     int pin_set = 0;
+#ifdef RT_TIMELINE
+    unsigned long long* tl_buf = nullptr; /* 2 x 64 words: min start / max end of the frame's launches (globaltimer, ns) */
+    int tl_n = 0;
+    const char* tl_name[64];
+    int tl_band[64];
+#endif
     /* ... and goes to the device on an upload stream of its own, into one of two small staging buffers: the copy runs while the frame before
      * renders instead of queueing behind that frame's copy-back (H2D behind D2H cost 0.09 ms per step, profiles/r02_notes.md) */
     cudaStream_t up_stream = nullptr;
@@ -1452,6 +1458,18 @@ int rt_scene_sync(rt_scene* s, rt_stats* stats) {
             CUDA_TRY(cudaMemcpyAsync(s->h_counters, s->counters, RT_NCOUNTERS * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->stream));
     }
     CUDA_TRY(cudaStreamSynchronize(s->stream));
+#ifdef RT_TIMELINE
+    if (s->tl_buf && s->tl_n > 0 && getenv("RT_TIMELINE_PRINT")) {
+        unsigned long long hst[128];
+        cudaMemcpy(hst, s->tl_buf, sizeof hst, cudaMemcpyDeviceToHost);
+        unsigned long long t0 = ~0ull;
+        for (int k = 0; k < s->tl_n; k++) t0 = std::min(t0, hst[k]);
+        fprintf(stderr, "[timeline us]");
+        for (int k = 0; k < s->tl_n; k++)
+            fprintf(stderr, " %s%d %.1f-%.1f", s->tl_name[k], s->tl_band[k], (double)(hst[k] - t0) * 1e-3, (double)(hst[64 + k] - t0) * 1e-3);
+        fprintf(stderr, "\n");
+    }
+#endif
     if (s->copies_pending) {
         CUDA_TRY(cudaStreamSynchronize(s->copy_stream));
         s->copies_pending = false;
@@ -1953,12 +1971,15 @@ struct LaunchChain {
         cfg.blockDim = dim3(block);
         cfg.dynamicSmemBytes = smem;
         cfg.stream = stream;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cudaLaunchAttribute at[2];
+        int na = 0;
         bool& prev = of(stream);
+        if (enabled && prev) {
+            at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            at[na++].val.programmaticStreamSerializationAllowed = 1;
+        }
         cfg.attrs = at;
-        cfg.numAttrs = (enabled && prev) ? 1 : 0;
+        cfg.numAttrs = na;
         prev = true;
         return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
     }
@@ -1973,6 +1994,24 @@ int enqueue_frame(rt_scene* s, const FramePlan& P, int& launches, bool& strip_co
     const bool stochastic = P.stochastic, count = P.count, wide = P.wide, anchored = P.anchored, diffuse_only = P.diffuse_only, trav_round0 = P.trav_round0,
                dbg_times = P.dbg_times;
     const bool six = s->header.n_spheres == 6 && s->opt.six != 0;
+#ifdef RT_TIMELINE
+    if (!s->tl_buf) CUDA_TRY(cudaMalloc(&s->tl_buf, 128 * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMemsetAsync(s->tl_buf, 0xff, 64 * sizeof(unsigned long long), s->stream));
+    CUDA_TRY(cudaMemsetAsync(s->tl_buf + 64, 0, 64 * sizeof(unsigned long long), s->stream));
+    s->tl_n = 0;
+#define TL_MARK(name)                                                       \
+    do {                                                                    \
+        g.tl_min = s->tl_buf;                                               \
+        g.tl_max = s->tl_buf + 64;                                          \
+        g.tl_slot = s->tl_n < 64 ? s->tl_n : 63;                            \
+        if (s->tl_n < 64) {                                                 \
+            s->tl_name[s->tl_n] = name;                                     \
+            s->tl_band[s->tl_n++] = st;                                     \
+        }                                                                   \
+    } while (0)
+#else
+#define TL_MARK(name)
+#endif
     const int segments = P.segments, npool_cap = P.npool_cap, n_strips = P.n_strips, spill_cap = P.spill_cap, rows = P.rows, variant = P.variant;
     const size_t trav_smem = P.trav_smem, st_rng_off = P.st_rng_off, st_total_off = P.st_total_off, st_rec_off = P.st_rec_off, task_slack = P.task_slack;
     const unsigned pers_grid = P.pers_grid, grid = P.grid;
@@ -2008,6 +2047,10 @@ int enqueue_frame(rt_scene* s, const FramePlan& P, int& launches, bool& strip_co
         if (n_strips > 1) CUDA_TRY(cudaStreamWaitEvent(stream, s->fork_ev, 0));
         chain.broke(stream);
         rtk::WfArgs g;
+#ifdef RT_TIMELINE
+        g.tl_min = g.tl_max = nullptr;
+        g.tl_slot = 0;
+#endif
         g.a = a;
         g.a.rows = srows;
         g.a.row_begin = a.row_begin + row0 * a.row_step;
@@ -2078,6 +2121,7 @@ int enqueue_frame(rt_scene* s, const FramePlan& P, int& launches, bool& strip_co
                 CUDA_TRY(cudaMemsetAsync(reinterpret_cast<unsigned char*>(s->wf_counters + st) + offsetof(rtk::WfCounters, nA), 0,
                                          sizeof(rtk::WfCounters) - offsetof(rtk::WfCounters, nA), stream));
                 chain.broke(stream);
+            TL_MARK("generate");
             if (stochastic) {
                 if (count) CUDA_TRY(chain.launch(rtk::wf_generate<true, true>, dim3(gen_grid), WF_THREADS, 0, stream, s->header, s->blob, g));
                 else if (diffuse_only) CUDA_TRY(chain.launch(rtk::wf_generate<false, true, true>, dim3(gen_grid), WF_THREADS, 0, stream, s->header, s->blob, g));
@@ -2125,6 +2169,7 @@ int enqueue_frame(rt_scene* s, const FramePlan& P, int& launches, bool& strip_co
                         launches++;
                         mark();
                     }
+                    TL_MARK("leaves");
                     if (stochastic) CUDA_TRY(chain.launch(rtk::wf_leaves<true>, dim3(leaves_grid), WF_THREADS, 0, stream, s->header, s->blob, g));
                     else CUDA_TRY(chain.launch(rtk::wf_leaves<false>, dim3(leaves_grid), WF_THREADS, 0, stream, s->header, s->blob, g));
                     if (side) { /* join: wf_shade needs both */
@@ -2146,6 +2191,7 @@ int enqueue_frame(rt_scene* s, const FramePlan& P, int& launches, bool& strip_co
                 launches++;
                 mark();
                 if (r == segments) break;
+                TL_MARK("shade");
                 if (stochastic) {
                     if (count) CUDA_TRY(chain.launch(rtk::wf_shade<true, true>, dim3(shade_grid), WF_THREADS, 0, stream, s->header, s->blob, g));
                     else if (diffuse_only) CUDA_TRY(chain.launch(rtk::wf_shade<false, true, true>, dim3(shade_grid), WF_THREADS, 0, stream, s->header, s->blob, g));

@@ -102,7 +102,24 @@ struct WfArgs {
     int task_cap;
     int qcap;     /* entries of each queue of this strip */
     float4 cam_sph[RT_MAX_SPHERES]; /* per sphere: O - C (xyz) and |O - C|^2 - R^2 (w) for O = the camera (closest_sphere_cam) */
+#ifdef RT_TIMELINE
+    unsigned long long *tl_min, *tl_max; /* investigation build (make EXTRA=-DRT_TIMELINE): first block start / last warp end of every launch */
+    int tl_slot;
+#endif
 };
+
+#ifdef RT_TIMELINE
+__device__ __forceinline__ unsigned long long tl_now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define TL_BEGIN(g) do { if (threadIdx.x == 0 && (g).tl_min) atomicMin((g).tl_min + (g).tl_slot, tl_now()); } while (0)
+#define TL_END(g) do { if ((threadIdx.x & 31) == 0 && (g).tl_max) atomicMax((g).tl_max + (g).tl_slot, tl_now()); } while (0)
+#else
+#define TL_BEGIN(g)
+#define TL_END(g)
+#endif
 
 __device__ __forceinline__ unsigned tie_rank(int i, int leaf_start, int n_tris, int push_order, int off_bits) {
     /* smaller wins at equal t. push_order 1 (L popped first, optimized.cu:265-266): ascending triangle index.
@@ -677,6 +694,7 @@ template <bool COUNT, bool STOCH, bool DIFFUSE = false, bool LEAN = false, bool 
 __global__ void __launch_bounds__(WF_THREADS, 10) wf_generate(const __grid_constant__ SceneHeader h, const unsigned char* __restrict__ blob,
                                                          const __grid_constant__ WfArgs g) {
     pdl_wait_then_release();
+    TL_BEGIN(g);
     const RenderArgs& a = g.a;
     const float4* nodes = reinterpret_cast<const float4*>(blob + h.off_nodes);
     const float4* tris = reinterpret_cast<const float4*>(blob + h.off_tris);
@@ -743,6 +761,7 @@ __global__ void __launch_bounds__(WF_THREADS, 10) wf_generate(const __grid_const
         answer_deferred<STOCH>(h, blob, g, 0, post, slot);
     }
     flush_work(w, g.c, COUNT);
+    TL_END(g);
 }
 
 /* ---- wf_shade: one thread per answered closest-hit query of round g.round ------------------------------------------ */
@@ -750,6 +769,7 @@ template <bool COUNT, bool STOCH, bool DIFFUSE = false, bool LEAN = false, int N
 __global__ void __launch_bounds__(WF_THREADS, 8) wf_shade(const __grid_constant__ SceneHeader h, const unsigned char* __restrict__ blob,
                                                       const __grid_constant__ WfArgs g) {
     pdl_wait_then_release();
+    TL_BEGIN(g);
     const RenderArgs& a = g.a;
     const float4* nodes = reinterpret_cast<const float4*>(blob + h.off_nodes);
     const float4* tris = reinterpret_cast<const float4*>(blob + h.off_tris);
@@ -798,6 +818,7 @@ __global__ void __launch_bounds__(WF_THREADS, 8) wf_shade(const __grid_constant_
         }
     }
     flush_work(w, g.c, COUNT);
+    TL_END(g);
 }
 
 /* ---- wf_leaves: one thread per (ray, candidate leaf) task of round g.round ----------------------------------------------
@@ -865,6 +886,7 @@ __global__ void __launch_bounds__(WF_THREADS) wf_leaves(const __grid_constant__ 
     /* Two phases per warp, both with full lanes: the box phase takes 32 tasks and keeps those whose box passes the slab
      * test (about half) in a small per-warp buffer; whenever the buffer holds 32 of them the triangle phase runs on 32. */
     pdl_wait_then_release();
+    TL_BEGIN(g);
     __shared__ int2 hitbuf[WF_THREADS / 32][96]; /* < 32 left over + up to 64 new */
     const unsigned FULL = 0xffffffffu;
     const float4* tris = reinterpret_cast<const float4*>(blob + h.off_tris);
@@ -926,6 +948,8 @@ __global__ void __launch_bounds__(WF_THREADS) wf_leaves(const __grid_constant__ 
         const int2 t = buf[lane];
         leaf_triangles<STOCH>(h, g, tris, ((t.x < 0) ? g.qS : qA) + (t.x & 0x7fffffff), t.x < 0, t.y);
     }
+    __syncwarp();
+    TL_END(g);
 }
 
 /* The Box-Muller jitter of the first sample of every pixel of the W x H frame (optimized.cu:756-758): the first two uniforms of the
