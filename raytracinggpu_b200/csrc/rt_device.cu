@@ -2159,6 +2159,7 @@ int enqueue_frame(rt_scene* s, const FramePlan& P, int& launches, bool& strip_co
                         chain.broke(tstream);
                     }
                     if (trav_now) {
+                        TL_MARK("traverse");
                         if (stochastic) {
                             if (wide) CUDA_TRY(chain.launch(rtk::wf_traverse<false, true, true>, dim3(pers_grid), WF_THREADS, trav_smem, tstream, s->header, s->blob, g, npool_cap));
                             else CUDA_TRY(chain.launch(rtk::wf_traverse<false, true, false>, dim3(pers_grid), WF_THREADS, trav_smem, tstream, s->header, s->blob, g, npool_cap));

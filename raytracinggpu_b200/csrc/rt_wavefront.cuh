@@ -1049,6 +1049,7 @@ template <bool COUNT, bool STOCH, bool WIDE>
 __global__ void __launch_bounds__(WF_THREADS, WIDE ? RT_WIDE_BLOCKS : 8) wf_traverse(const __grid_constant__ SceneHeader h, const unsigned char* __restrict__ blob,
                                                          const __grid_constant__ WfArgs g, const int npool_cap) {
     pdl_wait_then_release();
+    TL_BEGIN(g);
     extern __shared__ __align__(16) unsigned char wf_smem[];
     const RenderArgs& a = g.a;
     const float4* nodes = reinterpret_cast<const float4*>(blob + h.off_nodes);
@@ -1509,6 +1510,7 @@ __global__ void __launch_bounds__(WF_THREADS, WIDE ? RT_WIDE_BLOCKS : 8) wf_trav
         atomicAdd(&g.c->dbg[4], (unsigned long long)dbgAd);
     }
     flush_work(w, g.c, COUNT);
+    TL_END(g);
 }
 
 } // namespace rtk
