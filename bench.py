@@ -8,10 +8,10 @@ Workload (N = 1): BASELINE.json configs[1] — cadnav cat TriangleMesh with the 
 1920x1080, 1 sample/pixel, primary + shadow rays (4,147,200 rays/frame), optimized.cu knobs. A "step" is one
 frame. For N > 1 the path shards by frame: every rank renders its own frames of the SAME workload (frame-parallel,
 no data-path collective, "scaling": "weak"), so that the per-N values are comparable. The other BASELINE.json configs
-are reported beside the headline under "configs": [0] spheres scene 800x600, [2] one 4K depth-4 frame row-interleaved
+are reported beside the headline under "configs": [0] spheres scene 800x600, [2] one 4K depth-4 frame, groups of 16 rows interleaved
 over the ranks (strong scaling, NCCL all-gather and NVLink push), [3] the 240-frame light-orbit animation of the spheres
 scene at 1080p frame-parallel over the ranks, [4] the 10 M-triangle scene at 4K built on rank 0, broadcast once and
-rendered row-interleaved; plus a light-orbit animation of the cat scene and whole 4K depth-4 frames.
+rendered the same way; plus a light-orbit animation of the cat scene and whole 4K depth-4 frames.
 
 `value` times the render kernels with the scene resident in HBM (CUDA events on the launching stream, L2
 flushed between steps). `e2e` goes through the C ABI with HOST buffers: every step re-uploads the mesh in the
@@ -33,6 +33,7 @@ import numpy as np  # noqa: E402
 CAT_REL = os.path.join("cadnav.com_model", "Models_F0202A090", "cat.obj")
 W, H = 1920, 1080
 METRIC = "Mrays/s"
+ROW_GROUP = int(os.environ.get("RT_ROW_GROUP", "16"))  # single frames over N ranks: groups of 16 consecutive rows dealt out in turn (rt_params.row_group)
 
 
 def workload_string(mesh_name):
@@ -540,14 +541,14 @@ def config4_ten_million(rt, torch, local, world, rank, flush):
         bcast_ms = (time.perf_counter() - t0) * 1e3
     p = rt.params_profile("optimized", W4, H4, 1, 1)
     frames = 6
-    out = {"workload": "BASELINE.json configs[4]: cat instanced to 9,999,666 triangles, 3840x2160, primary + shadow rays, BVH built on rank 0 and broadcast once, rows interleaved over %d GPU(s)" % world,
+    out = {"workload": "BASELINE.json configs[4]: cat instanced to 9,999,666 triangles, 3840x2160, primary + shadow rays, BVH built on rank 0 and broadcast once, groups of %d rows interleaved over %d GPU(s)" % (ROW_GROUP, world),
            "build_on_rank0": build, "scene_blob_bytes": int(blob), "scene_broadcast_ms": round(bcast_ms, 2),
            "scene_broadcast_gbs": round(blob / (bcast_ms * 1e-3) / 1e9, 1) if bcast_ms > 0 else None, "scaling": "strong"}
     if world == 1:
         ms, rays, launches = _timed_frames(rt, torch, sc, stream, flush, p, frames, warm=2)
         out.update({"ms_per_frame": round(ms / frames, 4), "rays_per_frame": rays, "mrays_per_s": round(rays * frames / (ms * 1e-3) / 1e6, 1), "launches_per_frame": launches})
     else:
-        fp = rtd.FramePush(sc, H4, W4, world, rank, torch.device("cuda", local))
+        fp = rtd.FramePush(sc, H4, W4, world, rank, torch.device("cuda", local), group=ROW_GROUP)
         pp = fp.apply(p)
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(frames)]
         rays = 0
@@ -627,7 +628,7 @@ def sharded_single_frame(rt, torch, sc, stream, world, rank, verts, recs, bvh, m
     else:
         sc.set_mesh(verts, recs, bvh, mirror=1, id=mesh_id)
     sc.set_light((-10.0, 20.0, 40.0), 3e10)
-    fg = rtd.FrameGather(H4, W4, world, rank, torch.device("cuda", torch.cuda.current_device()))
+    fg = rtd.FrameGather(H4, W4, world, rank, torch.device("cuda", torch.cuda.current_device()), group=ROW_GROUP)
     p = fg.apply(rt.params_profile("optimized", W4, H4, 1, 4))
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(frames)]
     rays = 0
@@ -655,7 +656,7 @@ def sharded_single_frame(rt, torch, sc, stream, world, rank, verts, recs, bvh, m
     # the same frame with the bands pushed into rank 0's frame buffer over NVLink (CUDA IPC peer copies + one barrier)
     push = None
     if world > 1:
-        fp = rtd.FramePush(sc, H4, W4, world, rank, torch.device("cuda", torch.cuda.current_device()))
+        fp = rtd.FramePush(sc, H4, W4, world, rank, torch.device("cuda", torch.cuda.current_device()), group=ROW_GROUP)
         pp = fp.apply(rt.params_profile("optimized", W4, H4, 1, 4))
         ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(frames)]
         for i in range(3 + frames):
@@ -685,7 +686,7 @@ def sharded_single_frame(rt, torch, sc, stream, world, rank, verts, recs, bvh, m
         push = {"ms_per_frame": round(float(t2[0].item()) / frames, 4), "render_ms": round(float(t2[1].item()) / frames, 4),
                 "push_and_barrier_ms": round(float(t2[0].item() - t2[1].item()) / frames, 4), "frame_equals_all_gather": same,
                 "how": "rank 0 owns the frame (CUDA IPC handle broadcast once); every rank copies its band into it over NVLink, one barrier per frame"}
-    return {"workload": "BASELINE.json configs[2]: mirror cat 3840x2160, reflection depth 4, rows interleaved over %d GPU(s), all-gather to every rank" % world,
+    return {"workload": "BASELINE.json configs[2]: mirror cat 3840x2160, reflection depth 4, groups of %d rows interleaved over %d GPU(s), all-gather to every rank" % (ROW_GROUP, world),
             "p2p_push": push,
             "rays_per_frame": int(r.item()), "ms_per_frame": round(total_ms, 4), "render_ms": round(render_ms, 4), "gather_ms": round(total_ms - render_ms, 4),
             "mrays_per_s": round(int(r.item()) / (total_ms * 1e-3) / 1e6, 1), "gather_bytes_per_rank": int(fg.band.numel()), "frames": frames, "scaling": "strong"}

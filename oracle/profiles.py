@@ -67,7 +67,7 @@ def params(profile, W, H, num_rays=1, num_bounce=1):
     p.aa_sigma = 0.0
     p.indirect = 0
     p.gamma_mode = k["gamma_mode"]
-    p.row_begin, p.row_step, p.row_count = 0, 1, 0
+    p.row_begin, p.row_step, p.row_count, p.row_group = 0, 1, 0, 1
     if profile == "realtime":
         p.z = pyoracle.lib().orc_camera_z(W, float(np.float32(math.pi / 2)))
         p.camera_mode = 1

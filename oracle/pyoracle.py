@@ -207,7 +207,9 @@ def render(spheres, mesh_arrays, mesh_mat, light, params, threads=0, want=("rgb"
     L.orc_set_mesh_normals(nrm.ctypes.data if nrm is not None else None)
     p = params
     step = p.row_step if p.row_step > 0 else 1
-    rows = p.row_count if p.row_count > 0 else (p.H - p.row_begin + step - 1) // step
+    group = p.row_group if p.row_group > 1 else 1
+    n_groups = (p.H - p.row_begin + step - 1) // step
+    rows = p.row_count if p.row_count > 0 else (n_groups - 1) * group + min(group, p.H - (p.row_begin + (n_groups - 1) * step))
     n = len(spheres)
     arr = (rt_sphere * max(n, 1))(*spheres)
     if mesh_arrays is not None:

@@ -6,4 +6,4 @@ Python here is only the test/bench harness binding; the product is the shared li
 from ._abi import (RT_RENDER_COUNT_WORK, RT_RENDER_NO_SYNC, rt_params, rt_sphere, rt_stats)  # noqa: F401
 from . import sharding  # noqa: F401
 from .api import (LIB_PATH, Comm, comm_available, Mesh, RtError, Scene, camera_basis, camera_z, camera_z_device, default_walls, device_count, lib, move_light,  # noqa: F401
-                  params_profile, selftest_division, selftest_division3, fma_peak_tflops, selftest_libm, selftest_xorwow, write_png, PngWriter)
+                  params_profile, shard_rows, shard_row_count, selftest_division, selftest_division3, fma_peak_tflops, selftest_libm, selftest_xorwow, write_png, PngWriter)

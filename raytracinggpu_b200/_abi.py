@@ -54,6 +54,7 @@ class rt_params(C.Structure):
         ("cam_bz", C.c_float * 3),
         ("smooth_normals", C.c_int32),
         ("accumulate", C.c_int32),
+        ("row_group", C.c_int32),
     ]
 
 

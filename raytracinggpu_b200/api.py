@@ -51,6 +51,8 @@ SIGNATURES = {
     "rt_peer_close": (C.c_int, [C.c_int, _vp]),
     "rt_peer_free": (C.c_int, [C.c_int, _vp]),
     "rt_scene_push_rows": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32]),
+    "rt_scene_push_row_groups": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32]),
+    "rt_shard_rows": (C.c_int, [_i32, _i32, _i32, _i32, C.POINTER(rt_params)]),
     "rt_png_writer_create": (C.c_int, [C.POINTER(_vp), _i32, _i32]),
     "rt_png_writer_submit": (C.c_int, [_vp, C.c_char_p, _i32, _i32, _vp]),
     "rt_png_writer_wait": (C.c_int, [_vp]),
@@ -81,6 +83,7 @@ SIGNATURES = {
     "rt_comm_rank": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "rt_scene_broadcast": (C.c_int, [_vp, _vp, C.c_int, C.POINTER(C.c_size_t)]),
     "rt_gather_framebuffer": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, C.c_int]),
+    "rt_gather_framebuffer_groups": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, C.c_int]),
     "rt_selftest_fma_peak": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "rt_selftest_libm": (C.c_int, [C.c_int, C.c_int, _vp, _i32, _vp]),
     "rt_selftest_division": (C.c_int, [C.c_int, _u64, C.c_int, C.c_int, C.POINTER(_u64)]),
@@ -154,6 +157,24 @@ def camera_z_device(W, alpha=np.float32(np.pi / 3), device=0):
     z = C.c_float()
     _check(lib().rt_camera_z_device(int(device), int(W), float(alpha), C.byref(z)))
     return z.value
+
+
+def shard_rows(params, rank, nranks, row_group=1):
+    """rt_shard_rows: set row_begin / row_step / row_group / row_count of `params` for `rank` of `nranks`; returns the number of rows."""
+    n = lib().rt_shard_rows(int(params.H), int(rank), int(nranks), int(row_group), C.byref(params))
+    if n < 0:
+        _check(n)
+    return n
+
+
+def shard_row_count(p):
+    """Rows a call with these rt_params renders (row_count, or every row the shard holds when it is 0)."""
+    if p.row_count > 0:
+        return p.row_count
+    step = p.row_step if p.row_step > 0 else 1
+    group = p.row_group if p.row_group > 1 else 1
+    n_groups = (p.H - p.row_begin + step - 1) // step
+    return (n_groups - 1) * group + min(group, p.H - (p.row_begin + (n_groups - 1) * step))
 
 
 def params_profile(profile, W, H, num_rays=1, num_bounce=1):
@@ -408,10 +429,10 @@ class Scene:
     def blob_import(self, device_ptr, nbytes):
         _check(lib().rt_scene_blob_import(self._h, C.c_void_p(int(device_ptr)), int(nbytes)))
 
-    def push_rows(self, band_ptr, frame_ptr, W, bytes_per_pixel, row_begin, row_step, rows):
+    def push_rows(self, band_ptr, frame_ptr, W, bytes_per_pixel, row_begin, row_step, rows, row_group=1):
         """Strided device-to-device copy of this rank's row band into a (peer) frame buffer, on the scene's stream."""
-        _check(lib().rt_scene_push_rows(self._h, C.c_void_p(int(band_ptr)), C.c_void_p(int(frame_ptr)), int(W), int(bytes_per_pixel), int(row_begin),
-                                        int(row_step), int(rows)))
+        _check(lib().rt_scene_push_row_groups(self._h, C.c_void_p(int(band_ptr)), C.c_void_p(int(frame_ptr)), int(W), int(bytes_per_pixel), int(row_begin),
+                                              int(row_step), int(row_group), int(rows)))
 
     def render_into(self, params, rgb=None, hit_obj=None, hit_tri=None, hit_t=None, shadow=None, flags=0):
         """rt_render with caller-provided buffers (numpy = host, torch cuda tensor / int = device)."""
@@ -428,8 +449,7 @@ class Scene:
     def render(self, params, want=("rgb", "hit_obj", "hit_tri", "hit_t", "shadow"), count_work=False):
         """Render into fresh host arrays; returns dict of numpy arrays + 'stats'."""
         p = params
-        step = p.row_step if p.row_step > 0 else 1
-        rows = p.row_count if p.row_count > 0 else (p.H - p.row_begin + step - 1) // step
+        rows = shard_row_count(p)
         shapes = {"rgb": ((rows, p.W, 3), np.uint8), "hit_obj": ((rows, p.W), np.int32), "hit_tri": ((rows, p.W), np.int32),
                   "hit_t": ((rows, p.W), np.float32), "shadow": ((rows, p.W), np.uint8)}
         out = {k: np.zeros(*shapes[k]) for k in want}
@@ -480,9 +500,9 @@ class Comm:
         _check(lib().rt_scene_broadcast(scene._h, self._h, int(root), C.byref(n)))
         return n.value
 
-    def gather_framebuffer(self, scene, band_ptr, W, H, bytes_per_pixel, frame_ptr, root=0):
-        _check(lib().rt_gather_framebuffer(scene._h, self._h, C.c_void_p(int(band_ptr)), int(W), int(H), int(bytes_per_pixel),
-                                           C.c_void_p(int(frame_ptr)) if frame_ptr else None, int(root)))
+    def gather_framebuffer(self, scene, band_ptr, W, H, bytes_per_pixel, frame_ptr, root=0, row_group=1):
+        _check(lib().rt_gather_framebuffer_groups(scene._h, self._h, C.c_void_p(int(band_ptr)), int(W), int(H), int(bytes_per_pixel), int(row_group),
+                                                  C.c_void_p(int(frame_ptr)) if frame_ptr else None, int(root)))
 
 
 def comm_available():

@@ -108,6 +108,26 @@ void rt_camera_basis(float yaw, float pitch, float bx_[3], float by_[3], float b
     bz_[0] = bz.x; bz_[1] = bz.y; bz_[2] = bz.z;
 }
 
+int rt_shard_rows(int32_t H, int32_t rank, int32_t nranks, int32_t row_group, rt_params* p) {
+    if (H <= 0 || nranks < 1 || rank < 0 || rank >= nranks || row_group < 1 || row_group > 64 || (row_group & (row_group - 1)) != 0) {
+        rtb::fail(RT_ERR_INVALID, "rt_shard_rows: bad argument");
+        return RT_ERR_INVALID;
+    }
+    const int G = row_group, begin = rank * G, step = nranks * G;
+    int rows = 0;
+    if (begin < H) {
+        const int n_groups = (H - begin + step - 1) / step;
+        rows = (n_groups - 1) * G + std::min(G, H - (begin + (n_groups - 1) * step));
+    }
+    if (p) {
+        p->row_begin = begin < H ? begin : 0;
+        p->row_step = step;
+        p->row_group = G;
+        p->row_count = rows;
+    }
+    return rows;
+}
+
 int rt_params_profile(rt_params* p, const char* profile, int32_t W, int32_t H, int32_t num_rays, int32_t num_bounce) {
     if (!p) return rtb::fail(RT_ERR_INVALID, "rt_params_profile: NULL params");
     const Profile pr = parse_profile(profile);
@@ -127,6 +147,7 @@ int rt_params_profile(rt_params* p, const char* profile, int32_t W, int32_t H, i
     p->row_begin = 0;
     p->row_step = 1;
     p->row_count = 0;
+    p->row_group = 1;
     switch (pr) {
     case kCpu: /* cpu_launcher.cpp:575,301,291-292,567,714 */
         p->eps_surface = 1e-3f;

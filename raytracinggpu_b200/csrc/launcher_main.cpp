@@ -15,8 +15,8 @@
  *                                       indirect bounce on the cuRAND XORWOW stream of optimized.cu:745 (without the
  *                                       flag: the deterministic mode the parity contract is stated on; a notice says so)
  *   --gpus N                            one process, N devices: the scene is built on device 0 and broadcast (rt_scene_broadcast,
- *                                       NCCL), every device renders the rows r, r + N, ... of each frame on its own thread,
- *                                       the bands are gathered to device 0 (rt_gather_framebuffer)
+ *                                       NCCL), every device renders every N-th group of --row-group G (default 16) consecutive rows of
+ *                                       each frame on its own thread, the bands are gathered to device 0 (rt_gather_framebuffer_groups)
  *   --mirror                            the mesh is a mirror (Geometry::mirror, optimized.cu:111): BASELINE.json configs[2]
  */
 #include "scene.hpp"
@@ -50,7 +50,8 @@ struct MultiGpu {
     std::vector<void*> bands;      /* device buffers, one per device */
     void* frame = nullptr;         /* device 0 */
 
-    static int rows_of(int H, int r, int n) { return r < H ? (H - r + n - 1) / n : 0; }
+    int G = 16; /* rows per group of the interleave (--row-group): neighbouring rows keep a warp's pixel tile a tile */
+    int rows_of(int H_, int r, int n_) const { return rt_shard_rows(H_, r, n_, G, nullptr); }
 
     void init(int n_, rt_scene* root, int W_, int H_) {
         n = n_; W = W_; H = H_;
@@ -84,12 +85,10 @@ struct MultiGpu {
         std::vector<rt_stats> st(n);
         each([&](int d) {
             rt_params q = p;
-            q.row_begin = d;
-            q.row_step = n;
-            q.row_count = rows_of(H, d, n);
+            rt_shard_rows(H, d, n, G, &q);
             rtb200::check(rt_scene_set_light(scenes[d], L, intensity));
             if (q.row_count > 0) rtb200::check(rt_render(scenes[d], &q, 0, (uint8_t*)bands[d], nullptr, nullptr, nullptr, nullptr, &st[d]));
-            rtb200::check(rt_gather_framebuffer(scenes[d], comms[d], bands[d], W, H, 3, d == 0 ? frame : nullptr, 0));
+            rtb200::check(rt_gather_framebuffer_groups(scenes[d], comms[d], bands[d], W, H, 3, G, d == 0 ? frame : nullptr, 0));
             if (d == 0) rtb200::check(rt_scene_push_rows(scenes[0], frame, host_rgb, W, 3, 0, 1, H)); /* D2H on the scene's stream */
             rtb200::check(rt_scene_sync(scenes[d], nullptr));
         });
@@ -114,7 +113,7 @@ struct MultiGpu {
 int main(int argc, char** argv) {
     std::vector<std::string> pos;
     std::string profile = "optimized", obj = "cadnav.com_model/Models_F0202A090/cat.obj", out;
-    int W = 512, H = 512, device = 0, frames = 1, gpus = 1;
+    int W = 512, H = 512, device = 0, frames = 1, gpus = 1, row_group = 16;
     bool stochastic = false, gpu_build = false, mirror = false;
     std::string pattern;
     float orbit = 0.f;
@@ -131,6 +130,7 @@ int main(int argc, char** argv) {
         else if (a == "--stochastic") stochastic = true;
         else if (a == "--gpu-build") gpu_build = true;
         else if (a == "--gpus") gpus = atoi(next());
+        else if (a == "--row-group") row_group = atoi(next());
         else if (a == "--mirror") mirror = true;
         else if (a == "--out-pattern") pattern = next();
         else if (a == "--orbit") orbit = (float)atof(next());
@@ -142,6 +142,10 @@ int main(int argc, char** argv) {
     }
     if (!pattern.empty() && !pattern_ok(pattern)) {
         std::cerr << "rt_render: --out-pattern must contain exactly one %d (or %0Nd) and no other conversion\n";
+        return 2;
+    }
+    if (row_group < 1 || row_group > 64 || (row_group & (row_group - 1)) != 0) {
+        std::cerr << "rt_render: --row-group must be a power of two <= 64\n";
         return 2;
     }
     if (gpus < 1 || (gpus > 1 && device != 0)) {
@@ -194,6 +198,7 @@ int main(int argc, char** argv) {
         MultiGpu multi;
         if (gpus > 1) {
             scene.flush(); /* spheres + light onto device 0 before the blob is broadcast */
+            multi.G = row_group;
             multi.init(gpus, scene.handle(), W, H);
         }
         for (int f = 0; f < frames; f++) {

@@ -18,6 +18,7 @@
  * using that one copy, and librtb200.so has no link-time dependency for single-GPU callers. No CPU path.
  */
 #include "host_common.h"
+#include "rt_rows.h"
 
 #include <cuda_runtime.h>
 #include <dlfcn.h>
@@ -257,26 +258,31 @@ int rt_scene_broadcast(rt_scene* s, rt_comm* c, int root, size_t* bytes_out) {
     return RT_OK;
 }
 
-/* rows of a frame of H rows that rank r renders with row-interleave over n ranks */
-static int rows_of(int H, int r, int n) { return r < H ? (H - r + n - 1) / n : 0; }
-
 int rt_gather_framebuffer(rt_scene* s, rt_comm* c, const void* band, int32_t W, int32_t H, int32_t bytes_per_pixel, void* frame, int root) {
-    if (!s || !c || !band || W <= 0 || H <= 0 || bytes_per_pixel <= 0 || root < 0 || root >= c->nranks)
+    return rt_gather_framebuffer_groups(s, c, band, W, H, bytes_per_pixel, 1, frame, root);
+}
+
+/* row_group G: rank r rendered the groups r, r + nranks, ... of G consecutive rows each (rt_params: row_begin = r G, row_step = nranks G,
+ * row_group = G) */
+int rt_gather_framebuffer_groups(rt_scene* s, rt_comm* c, const void* band, int32_t W, int32_t H, int32_t bytes_per_pixel, int32_t row_group, void* frame,
+                                 int root) {
+    if (!s || !c || !band || W <= 0 || H <= 0 || bytes_per_pixel <= 0 || root < 0 || root >= c->nranks || row_group < 1 || row_group > 64 ||
+        (row_group & (row_group - 1)) != 0)
         return rtb::fail(RT_ERR_INVALID, "rt_gather_framebuffer: bad argument");
     if (c->rank == root && !frame) return rtb::fail(RT_ERR_INVALID, "rt_gather_framebuffer: the root rank needs a frame buffer");
     DevGuard g(c->device);
     cudaStream_t stream = rtb::scene_stream(s);
     const size_t line = (size_t)W * bytes_per_pixel;
-    const int n = c->nranks;
+    const int n = c->nranks, G = row_group;
     if (c->rank != root) {
-        const size_t mine = (size_t)rows_of(H, c->rank, n) * line;
+        const size_t mine = (size_t)rtb::shard_rows(H, c->rank, n, G) * line;
         if (mine) NCCL_TRY(nccl().Send(band, mine, ncclChar, root, c->comm, stream));
         return RT_OK;
     }
     /* root: its own band goes straight to its rows, the others arrive in the staging area */
     size_t need = 0;
     for (int r = 0; r < n; r++)
-        if (r != root) need += (size_t)rows_of(H, r, n) * line;
+        if (r != root) need += (size_t)rtb::shard_rows(H, r, n, G) * line;
     if (c->staging_bytes < need) {
         CUDA_TRY(cudaStreamSynchronize(stream));
         if (c->staging) cudaFree(c->staging);
@@ -289,17 +295,17 @@ int rt_gather_framebuffer(rt_scene* s, rt_comm* c, const void* band, int32_t W, 
     size_t off = 0;
     for (int r = 0; r < n; r++) {
         if (r == root) continue;
-        const size_t sz = (size_t)rows_of(H, r, n) * line;
+        const size_t sz = (size_t)rtb::shard_rows(H, r, n, G) * line;
         if (sz) NCCL_TRY(nccl().Recv(c->staging + off, sz, ncclChar, r, c->comm, stream));
         off += sz;
     }
     NCCL_TRY(nccl().GroupEnd());
     off = 0;
     for (int r = 0; r < n; r++) {
-        const int rows = rows_of(H, r, n);
+        const int rows = rtb::shard_rows(H, r, n, G);
         if (!rows) continue;
         const void* src = (r == root) ? band : (const void*)(c->staging + off);
-        CUDA_TRY(cudaMemcpy2DAsync((unsigned char*)frame + (size_t)r * line, (size_t)n * line, src, line, line, (size_t)rows, cudaMemcpyDeviceToDevice, stream));
+        CUDA_TRY(rtb::scatter_band(frame, src, line, r * G, n * G, G, rows, cudaMemcpyDeviceToDevice, stream));
         if (r != root) off += (size_t)rows * line;
     }
     return RT_OK;

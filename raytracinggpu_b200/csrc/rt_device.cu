@@ -10,6 +10,7 @@
 #include "host_common.h"
 #include "rt_kernels.cuh"
 #include "rt_layout.h"
+#include "rt_rows.h"
 #include <cub/cub.cuh>
 #include "rt_wavefront.cuh"
 #include "rt_stochastic.cuh"
@@ -1580,7 +1581,14 @@ int plan_frame(rt_scene* s, const rt_params* p, uint32_t flags, void* const user
     if (p->push_order != 0 && p->push_order != 1) return rtb::fail(RT_ERR_INVALID, "rt_render: push_order must be 0 or 1");
     const int step = p->row_step > 0 ? p->row_step : 1;
     if (p->row_begin < 0 || p->row_begin >= p->H) return rtb::fail(RT_ERR_INVALID, "rt_render: row_begin out of range");
-    const int max_rows = (p->H - p->row_begin + step - 1) / step;
+    const int group = p->row_group > 1 ? p->row_group : 1;
+    if ((group & (group - 1)) != 0 || group > 64) return rtb::fail(RT_ERR_INVALID, "rt_render: row_group must be a power of two <= 64");
+    if (group > 1 && step < group) return rtb::fail(RT_ERR_INVALID, "rt_render: row_step %d is smaller than row_group %d (groups would overlap)", step, group);
+    int group_shift = 0;
+    while ((1 << group_shift) < group) group_shift++;
+    /* groups start at row_begin, row_begin + step, ...; only the last one may be cut short by the frame's end */
+    const int n_groups = (p->H - p->row_begin + step - 1) / step;
+    const int max_rows = (n_groups - 1) * group + std::min(group, p->H - (p->row_begin + (n_groups - 1) * step));
     const int rows = p->row_count > 0 ? p->row_count : max_rows;
     if (rows > max_rows) return rtb::fail(RT_ERR_INVALID, "rt_render: row_count %d exceeds the %d rows available", rows, max_rows);
     const SceneHeader& h = s->header;
@@ -1642,6 +1650,8 @@ int plan_frame(rt_scene* s, const rt_params* p, uint32_t flags, void* const user
     a.rows = rows;
     a.row_begin = p->row_begin;
     a.row_step = step;
+    a.row0 = 0;
+    a.group_shift = group_shift;
     a.segments = p->num_bounce + (p->extra_segment ? 1 : 0);
     a.num_rays = p->num_rays;
     a.camx = p->cam[0];
@@ -2053,7 +2063,7 @@ int enqueue_frame(rt_scene* s, const FramePlan& P, int& launches, bool& strip_co
 #endif
         g.a = a;
         g.a.rows = srows;
-        g.a.row_begin = a.row_begin + row0 * a.row_step;
+        g.a.row0 = row0; /* the band's first compact row: image rows follow from row_begin / row_step / row_group (image_row) */
         g.a.rgb = a.rgb ? a.rgb + px0 * 3 : nullptr;
         g.a.hit_obj = a.hit_obj ? a.hit_obj + px0 : nullptr;
         g.a.hit_tri = a.hit_tri ? a.hit_tri + px0 : nullptr;
@@ -2442,12 +2452,16 @@ int rt_peer_free(int device, void* ptr) {
 }
 
 int rt_scene_push_rows(rt_scene* s, const void* band, void* frame, int32_t W, int32_t bytes_per_pixel, int32_t row_begin, int32_t row_step, int32_t rows) {
-    if (!s || !band || !frame || W <= 0 || bytes_per_pixel <= 0 || row_begin < 0 || row_step < 1 || rows < 0)
-        return rtb::fail(RT_ERR_INVALID, "rt_scene_push_rows: bad argument");
+    return rt_scene_push_row_groups(s, band, frame, W, bytes_per_pixel, row_begin, row_step, 1, rows);
+}
+
+int rt_scene_push_row_groups(rt_scene* s, const void* band, void* frame, int32_t W, int32_t bytes_per_pixel, int32_t row_begin, int32_t row_step, int32_t row_group,
+                             int32_t rows) {
+    if (!s || !band || !frame || W <= 0 || bytes_per_pixel <= 0 || row_begin < 0 || row_step < 1 || rows < 0 || row_group < 1 || row_step < row_group)
+        return rtb::fail(RT_ERR_INVALID, "rt_scene_push_row_groups: bad argument");
     if (rows == 0) return RT_OK;
     DeviceGuard g(s->device);
-    const size_t line = (size_t)W * bytes_per_pixel;
-    CUDA_TRY(cudaMemcpy2DAsync((unsigned char*)frame + (size_t)row_begin * line, (size_t)row_step * line, band, line, line, (size_t)rows, cudaMemcpyDefault, s->stream));
+    CUDA_TRY(rtb::scatter_band(frame, band, (size_t)W * bytes_per_pixel, row_begin, row_step, row_group, rows, cudaMemcpyDefault, s->stream));
     return RT_OK;
 }
 

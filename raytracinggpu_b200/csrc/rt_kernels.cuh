@@ -21,6 +21,7 @@ namespace rtk {
 
 struct RenderArgs {
     int32_t W, H, rows, row_begin, row_step;
+    int32_t row0, group_shift; /* compact row k of this launch is compact row row0 + k of the call; groups of 1 << group_shift image rows */
     int32_t segments, num_rays;
     float camx, camy, camz, z;
     float eps_surface, eps_tri;
@@ -40,6 +41,12 @@ struct RenderArgs {
     float4* linear;               /* progressive accumulation: the frame's linear colour per compact pixel instead of the 8-bit store */
     int32_t debug_cost;           /* investigation aid: with COUNT, hit_t <- thread clocks, hit_tri <- nodes+tris, hit_obj <- smid */
 };
+
+/* image row of the launch's compact row k (rt_params::row_begin / row_step / row_group) */
+__device__ __forceinline__ int image_row(const RenderArgs& a, int k) {
+    const int kk = a.row0 + k;
+    return a.row_begin + (kk >> a.group_shift) * a.row_step + (kk & ((1 << a.group_shift) - 1));
+}
 
 struct Work {
     unsigned int rays, nodes, tris, max_stack;
@@ -346,7 +353,7 @@ __global__ void __launch_bounds__(128) render_mega(const __grid_constant__ Scene
     Work w;
     w.rays = w.nodes = w.tris = w.max_stack = w.slab_fallbacks = w.tri_exact = 0;
     if (live) {
-        const int i = a.row_begin + k * a.row_step;
+        const int i = image_row(a, k);
         /* optimized.cu:751 — half-integers, exact in float */
         const F3 uc = f3((float)j - (float)a.W / 2 + 0.5f, (float)a.H / 2 - (float)i - 0.5f, a.z);
         const F3 cam = f3(a.camx, a.camy, a.camz);

@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(128) render_stoch(const __grid_constant__ Scen
     Work w;
     w.rays = w.nodes = w.tris = w.max_stack = w.slab_fallbacks = w.tri_exact = 0;
     if (j < a.W && k < a.rows) {
-        const int i = a.row_begin + k * a.row_step;
+        const int i = image_row(a, k);
         XorwowState rng = states[(size_t)i * a.W + j]; /* the GLOBAL pixel index keys the stream (optimized.cu:745) */
         const F3 uc = f3((float)j - (float)a.W / 2 + 0.5f, (float)a.H / 2 - (float)i - 0.5f, a.z);
         const F3 cam = f3(a.camx, a.camy, a.camz);

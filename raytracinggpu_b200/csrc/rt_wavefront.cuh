@@ -713,7 +713,7 @@ __global__ void __launch_bounds__(WF_THREADS, 10) wf_generate(const __grid_const
     post.cand_count = 0;
     const int px = kr * a.W + j;
     if (j < a.W && kr < a.rows) {
-        const int i = a.row_begin + kr * a.row_step;
+        const int i = image_row(a, kr);
         F3 uc = f3((float)j - (float)a.W / 2 + 0.5f, (float)a.H / 2 - (float)i - 0.5f, a.z); /* optimized.cu:751, exact in float */
         if (a.camera_mode == 1) /* the viewer's camera, realtime_render.cu:1113 (the camera position is part of the sum there) */
             uc = ((f3(a.camx, a.camy, a.camz) + a.z * f3(a.bz[0], a.bz[1], a.bz[2])) + uc.x * f3(a.bx[0], a.bx[1], a.bx[2])) + uc.y * f3(a.by[0], a.by[1], a.by[2]);

@@ -66,17 +66,18 @@ def broadcast_scene(scene, src=0, device=None):
 class FrameGather:
     """Buffers for row-interleaved rendering of H x W frames on `world` ranks, reused across frames."""
 
-    def __init__(self, H, W, world, rank, device, mode="interleave", channels=3):
+    def __init__(self, H, W, world, rank, device, mode="interleave", channels=3, group=1):
         self.H, self.W, self.world, self.rank, self.mode = H, W, world, rank, mode
-        self.pad = sharding.padded_rows(H, world, mode)
-        self.row_begin, self.row_step, self.row_count = sharding.rows_for_rank(H, rank, world, mode)
+        self.group = group if mode == "interleave" else 1
+        self.pad = sharding.padded_rows(H, world, mode, self.group)
+        self.row_begin, self.row_step, self.row_count = sharding.rows_for_rank(H, rank, world, mode, self.group)
         self.band = torch.zeros((self.pad, W, channels), dtype=torch.uint8, device=device)
         self.gathered = torch.empty((world, self.pad, W, channels), dtype=torch.uint8, device=device)
         self.frame = torch.empty((H, W, channels), dtype=torch.uint8, device=device)
 
     def apply(self, params):
         """Set the sharding fields of an rt_params for this rank."""
-        params.row_begin, params.row_step, params.row_count = self.row_begin, self.row_step, self.row_count
+        params.row_begin, params.row_step, params.row_count, params.row_group = self.row_begin, self.row_step, self.row_count, self.group
         return params
 
     def gather(self, scene=None):
@@ -92,10 +93,16 @@ class FrameGather:
                 dist.all_gather(parts, self.band)
         else:
             self.gathered[0].copy_(self.band)
+        G = self.group
         for r in range(self.world):
-            b, s, c = sharding.rows_for_rank(self.H, r, self.world, self.mode)
-            if c:
-                self.frame[b:b + s * c:s].copy_(self.gathered[r, :c])
+            b, s, c = sharding.rows_for_rank(self.H, r, self.world, self.mode, G)
+            full, rest = c // G, c % G
+            if full:  # whole groups: one strided copy (the frame seen as [groups, G rows])
+                dst = self.frame.as_strided((full, G) + tuple(self.frame.shape[1:]), (s * self.frame.stride(0), self.frame.stride(0)) + tuple(self.frame.stride()[1:]),
+                                            self.frame.storage_offset() + b * self.frame.stride(0))
+                dst.copy_(self.gathered[r, :full * G].view((full, G) + tuple(self.frame.shape[1:])))
+            if rest:
+                self.frame[b + full * s:b + full * s + rest].copy_(self.gathered[r, full * G:c])
         return self.frame
 
 
@@ -103,11 +110,12 @@ class FramePush:
     """Row-interleaved rendering of H x W frames on `world` ranks with the bands pushed into rank `dst`'s frame buffer over
     NVLink (CUDA IPC + peer copies; NCCL backend, one process per GPU of one node). `frame` is valid on rank `dst`."""
 
-    def __init__(self, scene, H, W, world, rank, device, dst=0, channels=3):
+    def __init__(self, scene, H, W, world, rank, device, dst=0, channels=3, group=1):
         from . import api
         self.scene, self.H, self.W, self.world, self.rank, self.dst, self.channels = scene, H, W, world, rank, dst, channels
+        self.group = group
         self.device_index = device.index if device.index is not None else torch.cuda.current_device()
-        self.row_begin, self.row_step, self.row_count = sharding.rows_for_rank(H, rank, world, "interleave")
+        self.row_begin, self.row_step, self.row_count = sharding.rows_for_rank(H, rank, world, "interleave", group)
         self.band = torch.zeros((max(self.row_count, 1), W, channels), dtype=torch.uint8, device=device)
         handle = torch.zeros(64, dtype=torch.uint8, device=device)
         self._own = self._peer = None
@@ -129,14 +137,14 @@ class FramePush:
         self._token = torch.zeros(1, dtype=torch.int32, device=device)
 
     def apply(self, params):
-        params.row_begin, params.row_step, params.row_count = self.row_begin, self.row_step, self.row_count
+        params.row_begin, params.row_step, params.row_count, params.row_group = self.row_begin, self.row_step, self.row_count, self.group
         return params
 
     def push(self):
         """Enqueue this rank's copy (on the scene's stream) and the barrier that tells `dst` every band has landed."""
         self.frame_ptr = self._base + (self.k & 1) * self.frame_bytes
         self.k += 1
-        self.scene.push_rows(self.band.data_ptr(), self.frame_ptr, self.W, self.channels, self.row_begin, self.row_step, self.row_count)
+        self.scene.push_rows(self.band.data_ptr(), self.frame_ptr, self.W, self.channels, self.row_begin, self.row_step, self.row_count, self.group)
         if self.world > 1:
             _order_after_scene(self.scene)   # the collective runs on torch's current stream: behind the copy on the scene's
             dist.all_reduce(self._token)     # complete when every rank's copy is

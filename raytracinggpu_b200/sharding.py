@@ -7,12 +7,17 @@ All functions here are pure host logic (tested on CPU with a 2-rank gloo group, 
 import numpy as np
 
 
-def rows_for_rank(H, rank, world, mode="interleave"):
-    """(row_begin, row_step, row_count) for rt_params. 'interleave': row % world == rank (best balance, the
-    mesh sits in the image centre); 'band': contiguous bands of ceil(H/world) rows."""
+def rows_for_rank(H, rank, world, mode="interleave", group=1):
+    """(row_begin, row_step, row_count) for rt_params. 'interleave': groups of `group` consecutive rows dealt out in turn, group g of the
+    frame to rank g % world (group 1: row % world == rank; rt_params.row_group = group, rt_shard_rows in the C ABI): balanced whatever the
+    image, and with group >= 4 a warp's 8x4 pixel tile stays a tile; 'band': contiguous bands of ceil(H/world) rows."""
     if mode == "interleave":
-        count = (H - rank + world - 1) // world if rank < H else 0
-        return rank, world, count
+        begin, step = rank * group, world * group
+        if begin >= H:
+            return 0, step, 0
+        n_groups = (H - begin + step - 1) // step
+        count = (n_groups - 1) * group + min(group, H - (begin + (n_groups - 1) * step))
+        return begin, step, count
     if mode == "band":
         per = (H + world - 1) // world
         begin = min(rank * per, H)
@@ -20,18 +25,24 @@ def rows_for_rank(H, rank, world, mode="interleave"):
     raise ValueError(mode)
 
 
-def padded_rows(H, world, mode="interleave"):
+def image_rows(begin, step, count, group=1):
+    """Image row of every compact row of a shard: begin + (k // group) * step + k % group."""
+    k = np.arange(count)
+    return begin + (k // group) * step + k % group
+
+
+def padded_rows(H, world, mode="interleave", group=1):
     """Rows every rank allocates so that an all-gather sees equal-size chunks."""
-    return (H + world - 1) // world
+    return max(rows_for_rank(H, r, world, mode, group)[2] for r in range(world))
 
 
-def assemble(gathered, H, world, mode="interleave"):
+def assemble(gathered, H, world, mode="interleave", group=1):
     """gathered: array [world, padded_rows, W, C] as all_gather delivers it -> full frame [H, W, C]."""
     g = np.asarray(gathered)
     out = np.empty((H,) + g.shape[2:], dtype=g.dtype)
     for r in range(world):
-        begin, step, count = rows_for_rank(H, r, world, mode)
-        out[begin:begin + step * count:step] = g[r, :count]
+        begin, step, count = rows_for_rank(H, r, world, mode, group)
+        out[image_rows(begin, step, count, group if mode == "interleave" else 1)] = g[r, :count]
     return out
 
 

@@ -42,7 +42,7 @@ def main():
     if rank == 0:
         assert np.array_equal(frame.cpu().numpy(), whole), "rt_gather_framebuffer"
     # ---- CUDA IPC peer frame, scene on its own (non-blocking) stream: three frames back to back, double-buffered
-    fp = rtd.FramePush(sc, H, W, world, rank, dev)
+    fp = rtd.FramePush(sc, H, W, world, rank, dev, group=8)
     pp = fp.apply(profiles.params("optimized", W, H, 1, 3))
     outs = []
     for k in range(3):

@@ -72,10 +72,10 @@ def test_one_process_n_devices(gpu):
             nbytes = comms[r].broadcast_scene(scs[r], 0)
             assert nbytes == scs[0].blob_size()
             p = profiles.params("optimized", W, H, 1, 3)
-            p.row_begin, p.row_step, p.row_count = sharding.rows_for_rank(H, r, n)
+            assert rt.shard_rows(p, r, n, 8) == sharding.rows_for_rank(H, r, n, group=8)[2]  # groups of 8 rows (rt_shard_rows)
             band = torch.zeros((max(p.row_count, 1), W, 3), dtype=torch.uint8, device="cuda:%d" % r)
             scs[r].render_into(p, rgb=band)
-            comms[r].gather_framebuffer(scs[r], band.data_ptr(), W, H, 3, frame.data_ptr() if r == 0 else 0, 0)
+            comms[r].gather_framebuffer(scs[r], band.data_ptr(), W, H, 3, frame.data_ptr() if r == 0 else 0, 0, row_group=8)
             scs[r].sync()
         except Exception as e:  # noqa: BLE001
             errors.append((r, repr(e)))

@@ -107,6 +107,22 @@ def test_4k_mirror_depth4_properties(scene):
     frame = rt.sharding.assemble(np.stack(parts), H, 8)
     assert np.array_equal(frame, a["rgb"])
     assert rays == a["stats"]["rays"]
+    # the same in groups of 8 consecutive rows (rt_params.row_group): all five outputs
+    parts, rays = {k: [] for k in ("rgb", "hit_obj", "hit_tri", "hit_t", "shadow")}, 0
+    pad = rt.sharding.padded_rows(H, 8, group=8)
+    for r in range(8):
+        q = profiles.params("optimized", W, H, 1, 4)
+        assert rt.shard_rows(q, r, 8, 8) == rt.sharding.rows_for_rank(H, r, 8, group=8)[2]
+        o = scene.render(q)
+        for k in parts:
+            band = np.zeros((pad,) + o[k].shape[1:], o[k].dtype)
+            band[:o[k].shape[0]] = o[k]
+            parts[k].append(band)
+        rays += o["stats"]["rays"]
+    for k in parts:
+        whole = rt.sharding.assemble(np.stack(parts[k]), H, 8, group=8)
+        assert np.array_equal(whole.view(np.uint32) if k == "hit_t" else whole, a[k].view(np.uint32) if k == "hit_t" else a[k]), k
+    assert rays == a["stats"]["rays"]
     # oracle on every 40th row
     q = profiles.params("optimized", W, H, 1, 4)
     q.row_begin, q.row_step, q.row_count = 7, 40, 0
@@ -333,3 +349,36 @@ def test_full_size_config3_animation_frames_1080p(scene):
         ora = scenes.run_oracle(d, p, want=("rgb", "hit_obj", "shadow"))
         res = scenes.compare(got, ora)
         assert res["rgb_exact_mismatch"] == 0, (f, res)
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("group,world,H", [(4, 3, 187), (8, 8, 200), (64, 2, 150)])
+def test_row_group_shards_match_the_oracle(scene, variant, group, world, H):
+    """rt_params.row_group: a rank's share of groups of consecutive rows (compact row k = image row begin + (k / G) step + k % G), rendered by
+    the wavefront pipeline and by the thread-per-pixel kernel, equals the oracle's rendering of the same rt_params in every output; ragged
+    frame heights (a last group cut short, a rank without rows) included."""
+    desc = scenes.cat_scene("optimized", mirror=1) or scenes.torus_scene("optimized", mirror=1)
+    scene.set_option("variant", variant)
+    scenes.upload(scene, desc)
+    W = 256
+    total = 0
+    for r in range(world):
+        p = profiles.params("optimized", W, H, 1, 3)
+        n = rt.shard_rows(p, r, world, group)
+        total += n
+        if n == 0:
+            continue
+        got = scene.render(p)
+        assert got["rgb"].shape[0] == n
+        ora = scenes.run_oracle(desc, p)
+        res = scenes.compare(got, ora)
+        assert res["rgb_exact_mismatch"] == 0, (r, res)
+    assert total == H
+    # a group that is not a power of two, or larger than the step, is refused
+    p = profiles.params("optimized", W, H, 1, 1)
+    p.row_group = 3
+    with pytest.raises(rt.RtError):
+        scene.render(p)
+    p.row_group, p.row_step = 8, 4
+    with pytest.raises(rt.RtError):
+        scene.render(p)

@@ -13,7 +13,8 @@ from oracle import profiles, scenes
 pytestmark = pytest.mark.gpu
 
 
-def test_pushed_bands_reassemble_the_frame(built):
+@pytest.mark.parametrize("group", [1, 4, 16])
+def test_pushed_bands_reassemble_the_frame(built, group):
     if rt.device_count() < 1:
         pytest.fail("no CUDA device: the gpu tests must run on the B200 box (there is no CPU fallback)")
     desc = scenes.cat_scene("optimized", mirror=1) or scenes.torus_scene("optimized", mirror=1)
@@ -24,10 +25,13 @@ def test_pushed_bands_reassemble_the_frame(built):
     assert len(handle) == 64
     for r in range(world):
         p = profiles.params("optimized", W, H, 1, 3)
-        p.row_begin, p.row_step, p.row_count = sharding.rows_for_rank(H, r, world)
+        p.row_begin, p.row_step, p.row_count = sharding.rows_for_rank(H, r, world, group=group)
+        p.row_group = group
+        if p.row_count == 0:
+            continue
         band = torch.zeros((max(p.row_count, 1), W, 3), dtype=torch.uint8, device="cuda")
         sc.render_into(p, rgb=band)
-        sc.push_rows(band.data_ptr(), frame_ptr, W, 3, p.row_begin, p.row_step, p.row_count)
+        sc.push_rows(band.data_ptr(), frame_ptr, W, 3, p.row_begin, p.row_step, p.row_count, group)
     out = torch.empty((H, W, 3), dtype=torch.uint8, device="cuda")
     sc.push_rows(frame_ptr, out.data_ptr(), W, 3, 0, 1, H)
     sc.sync()

@@ -89,6 +89,21 @@ def test_stochastic_sharding_keeps_the_image(scene):
     for r in range(3):
         stack[r, :parts[r].shape[0]] = parts[r]
     assert np.array_equal(rt.sharding.assemble(stack, H, 3), full["rgb"])
+    # row groups (rt_params.row_group = 4), through the wavefront passes and through the thread-per-pixel kernel, and a one-sample frame
+    for opt, rays, bounce in (("stoch_mega", 2, 3), (None, 2, 3), (None, 1, 1)):
+        want = full["rgb"] if (rays, bounce) == (2, 3) else scene.render(stoch("optimized", W, H, rays, bounce), want=("rgb",))["rgb"]
+        if opt:
+            scene.set_option(opt, 1)
+        pad = rt.sharding.padded_rows(H, 3, group=4)
+        stack = np.zeros((3, pad, W, 3), np.uint8)
+        for r in range(3):
+            q = stoch("optimized", W, H, rays, bounce)
+            rt.shard_rows(q, r, 3, 4)
+            o = scene.render(q, want=("rgb",))["rgb"]
+            stack[r, :o.shape[0]] = o
+        if opt:
+            scene.set_option(opt, 0)
+        assert np.array_equal(rt.sharding.assemble(stack, H, 3, group=4), want), (opt, rays, bounce)
     # a different seed gives a different image, the default seed is 123456
     q = stoch("optimized", W, H, 2, 3)
     q.reserved = 123456

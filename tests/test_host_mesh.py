@@ -24,7 +24,7 @@ def test_abi_exports_every_declared_symbol(built):
     for n in sorted(names):
         assert hasattr(L, n), "missing export %s" % n
     assert set(rt.api.SIGNATURES) == names
-    assert L.rt_abi_version() == 2
+    assert L.rt_abi_version() == 3
 
 
 def test_struct_layouts_match_header(built, tmp_path):
@@ -35,7 +35,7 @@ def test_struct_layouts_match_header(built, tmp_path):
     exe = str(tmp_path / "sz")
     subprocess.run(["/usr/bin/gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", exe], check=True)
     sizes = [int(x) for x in subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()]
-    assert sizes == [C.sizeof(rt.rt_sphere), C.sizeof(rt.rt_params), C.sizeof(rt.rt_stats)] == [44, 124, 56]
+    assert sizes == [C.sizeof(rt.rt_sphere), C.sizeof(rt.rt_params), C.sizeof(rt.rt_stats)] == [44, 128, 56]
 
 
 @pytest.mark.parametrize("profile", ["cpu", "optimized", "array_bvh"])

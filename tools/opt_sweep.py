@@ -21,7 +21,7 @@ for combo in itertools.product(*[args[k].split(",") for k in keys]):
     if mode == "stoch11":
         p.aa_sigma, p.indirect = 0.2, 1
     if mode == "shard8":
-        p.row_begin, p.row_step, p.row_count = rt.sharding.rows_for_rank(H, 0, 8)
+        rt.shard_rows(p, 0, 8, int(os.environ.get("RT_ROW_GROUP", "1")))
     rows = p.row_count if p.row_count > 0 else H
     rgb = torch.empty((rows, W, 3), dtype=torch.uint8, device="cuda")
     ms = []
