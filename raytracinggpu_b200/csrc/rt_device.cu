@@ -57,6 +57,7 @@ struct RtOptions {
                               * restates the functions for the CPU (rt_oracle.cpp: cuda_logf ...); 0 evaluated in double and rounded once
                               * (the oracle's other canon: what a correctly rounded libm would give; 3-4x the instructions) */
     int graph = 1;           /* replay a recorded CUDA graph when a frame repeats the previous call's plan */
+    int fair_share = 1;      /* wf_traverse: an admission takes at most the warp's even share of a short queue */
     int split = 0;           /* two row bands: per cent of the rows in the first band; 0: equal halves */
     int six = 1;             /* kernels with the sphere loops unrolled for the reference's room of exactly six spheres (constants as direct operands) */
     int one_shot = 1;        /* stochastic frames of one sample and one segment through the deterministic pipeline with jittered camera rays */
@@ -92,6 +93,7 @@ static const RtOptionKey kOptionKeys[] = {
     {"one_shot", &RtOptions::one_shot, 0, 1},
     {"six", &RtOptions::six, 0, 1},
     {"split", &RtOptions::split, 0, 95},
+    {"fair_share", &RtOptions::fair_share, 0, 1},
     {"debug_times", &RtOptions::debug_times, 0, 1},
     {"debug_pool", &RtOptions::debug_pool, 0, 1},
     {"debug_bins", &RtOptions::debug_bins, 0, 1},
@@ -2080,6 +2082,7 @@ int enqueue_frame(rt_scene* s, const FramePlan& P, int& launches, bool& strip_co
         {
             g.run_shift = s->opt.run_shift;
             g.gss_factor = s->opt.gss;
+            g.fair_share = s->opt.fair_share;
         }
         g.dbg_warps = dbg_ptr;
         g.anchored = anchored ? 1 : 0;

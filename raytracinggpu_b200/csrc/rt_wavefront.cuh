@@ -90,6 +90,7 @@ struct WfArgs {
     float4* rec;           /* [segment][compact pixel][2]: direct term, albedo of the diffuse hit that ended that segment */
     int run_shift;  /* log2 of the admission run length, -1 = chosen per launch from the queue length */
     int gss_factor; /* the last gss_factor * n_warps runs are admitted one at a time */
+    int fair_share; /* 1: an admission takes at most the warp's even share of the queue (short queues) */
     int* spill;     /* node-pool overflow area: spill_cap ints per traversal warp (global memory) */
     int spill_cap;
     int* dbg_warps; /* investigation aid (RT_DEBUG_WARPS, COUNT kernels only): 16 ints per traversal warp and round */
@@ -1087,6 +1088,7 @@ __global__ void __launch_bounds__(WF_THREADS, WIDE ? RT_WIDE_BLOCKS : 8) wf_trav
     }
     const int n_runs = (total + (1 << rs) - 1) >> rs; /* runs of 2^rs consecutive queue entries */
     const int n_quarter = (n_runs + 3) >> 2;           /* the queue is consumed as four interleaved quarters */
+    const int k_fair = g.fair_share ? max(1, (n_runs + n_warps - 1) / n_warps) : 32; /* runs per warp if the queue were dealt out evenly */
     int last_r0 = 0;                                   /* the queue cursor as this warp last saw it */
     bool exhausted = total == 0;
     bool failed = false;
@@ -1134,6 +1136,10 @@ __global__ void __launch_bounds__(WF_THREADS, WIDE ? RT_WIDE_BLOCKS : 8) wf_trav
              * takes on at most 8 more, so the expensive rays of a region end up spread over many warps. */
             const int fill = nN + nT;
             int k = max(1, (fill < 12 ? 32 : (fill < 28 ? 16 : 8)) >> rs);
+            /* a short queue (a bounce round, a small row shard): no warp takes more than its share at once — with 21 rays per warp the
+             * first two thirds of the warps used to leave with 32 each and the last third with none, and the round lasts as long as
+             * its fullest warp */
+            k = min(k, k_fair);
             /* guided self-scheduling: the last runs of the queue go out one at a time */
             if (4 * n_quarter - last_r0 < g.gss_factor * n_warps) k = 1;
             int r0 = 0;

@@ -13,13 +13,13 @@ sc = rt.Scene(0)
 for k, v in args.items():
     sc.set_option(k, int(v))
 sc.set_spheres(walls)
-sc.set_mesh(mesh.vertices, mesh.tri_records, mesh.arr_bvh, mirror=1 if mode == "shard8" else 0, id=mesh_id)
-W, H = (3840, 2160) if mode == "shard8" else (1920, 1080)
-p = rt.params_profile("optimized", W, H, 1, 4 if mode == "shard8" else 1)
+sc.set_mesh(mesh.vertices, mesh.tri_records, mesh.arr_bvh, mirror=1 if mode in ("shard8", "mirror4k") else 0, id=mesh_id)
+W, H = (3840, 2160) if mode in ("shard8", "mirror4k") else (1920, 1080)
+p = rt.params_profile("optimized", W, H, 1, 4 if mode in ("shard8", "mirror4k") else 1)
 if mode == "stoch11":
     p.aa_sigma, p.indirect = 0.2, 1
 if mode == "shard8":
-    p.row_begin, p.row_step, p.row_count = rt.sharding.rows_for_rank(H, 0, 8)
+    rt.shard_rows(p, 0, 8, int(os.environ.get("RT_ROW_GROUP", "16")))
 rows = p.row_count if p.row_count > 0 else H
 rgb = torch.empty((rows, W, 3), dtype=torch.uint8, device="cuda")
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
