@@ -659,6 +659,7 @@ def sharded_single_frame(rt, torch, sc, stream, world, rank, verts, recs, bvh, m
         fp = rtd.FramePush(sc, H4, W4, world, rank, torch.device("cuda", torch.cuda.current_device()), group=ROW_GROUP)
         pp = fp.apply(rt.params_profile("optimized", W4, H4, 1, 4))
         ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(frames)]
+        kernel_ms2 = []
         for i in range(3 + frames):
             dist.barrier()
             with torch.cuda.stream(stream):
@@ -671,9 +672,16 @@ def sharded_single_frame(rt, torch, sc, stream, world, rank, verts, recs, bvh, m
                 fp.push()
                 if k >= 0:
                     ev2[k][2].record(stream)
-            sc.sync()
+            st2 = sc.sync()
+            if i >= 3:
+                kernel_ms2.append(st2.kernel_ms)
         torch.cuda.synchronize()
         t2 = torch.tensor([sum(a.elapsed_time(c) for a, _, c in ev2), sum(a.elapsed_time(b) for a, b, _ in ev2)], device="cuda", dtype=torch.float64)
+        per_rank = [torch.zeros(2, device="cuda", dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(per_rank, t2)
+        lib_ms = torch.tensor([float(np.median(kernel_ms2))], device="cuda", dtype=torch.float64)  # rt_render's own event pair (graph launch to last kernel)
+        lib_ranks = [torch.zeros(1, device="cuda", dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(lib_ranks, lib_ms)
         dist.all_reduce(t2, op=dist.ReduceOp.MAX)
         same = None
         if rank == 0:
@@ -685,6 +693,8 @@ def sharded_single_frame(rt, torch, sc, stream, world, rank, verts, recs, bvh, m
         fp.close()
         push = {"ms_per_frame": round(float(t2[0].item()) / frames, 4), "render_ms": round(float(t2[1].item()) / frames, 4),
                 "push_and_barrier_ms": round(float(t2[0].item() - t2[1].item()) / frames, 4), "frame_equals_all_gather": same,
+                "render_ms_per_rank": [round(float(x[1].item()) / frames, 4) for x in per_rank],
+                "kernels_only_ms_per_rank": [round(float(x.item()), 4) for x in lib_ranks],
                 "how": "rank 0 owns the frame (CUDA IPC handle broadcast once); every rank copies its band into it over NVLink, one barrier per frame"}
     return {"workload": "BASELINE.json configs[2]: mirror cat 3840x2160, reflection depth 4, groups of %d rows interleaved over %d GPU(s), all-gather to every rank" % (ROW_GROUP, world),
             "p2p_push": push,
