@@ -539,7 +539,9 @@ __device__ __forceinline__ void path_advance(const SceneHeader& h, const WfArgs&
             const float an = (float)(2 * 3.14159265358979323846 * (double)q1);
             const float sq = sqrtf(1 - q2);
             const float x = (g.libm ? cosf(an) : canon_cos(an)) * sq, y = (g.libm ? sinf(an) : canon_sin(an)) * sq, z = sqrtf(q2);
-            const F3 T1 = normalized((fabsf(N.y) != 0 && fabsf(N.x) != 0) ? f3(-N.y, N.x, 0.f) : f3(-N.z, 0.f, N.x));
+            /* one component of T1 is an exact zero: div.rn.f32 would take its slow path for it at every diffuse hit (div3_or_zero) */
+            const F3 T1raw = (fabsf(N.y) != 0 && fabsf(N.x) != 0) ? f3(-N.y, N.x, 0.f) : f3(-N.z, 0.f, N.x);
+            const F3 T1 = div3_or_zero(T1raw, sqrtf(norm2(T1raw)));
             const F3 T2 = cross(N, T1);
             u = (x * T1 + y * T2) + z * N;
             O = Padj;

@@ -18,6 +18,9 @@ W, H = (3840, 2160) if mode in ("shard8", "mirror4k") else (1920, 1080)
 p = rt.params_profile("optimized", W, H, 1, 4 if mode in ("shard8", "mirror4k") else 1)
 if mode == "stoch11":
     p.aa_sigma, p.indirect = 0.2, 1
+if mode == "stoch13":
+    p = rt.params_profile("optimized", W, H, 1, 3)
+    p.aa_sigma, p.indirect = 0.2, 1
 if mode == "shard8":
     rt.shard_rows(p, 0, 8, int(os.environ.get("RT_ROW_GROUP", "16")))
 rows = p.row_count if p.row_count > 0 else H
