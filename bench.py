@@ -8,7 +8,7 @@ Workload (N = 1): BASELINE.json configs[1] — cadnav cat TriangleMesh with the 
 1920x1080, 1 sample/pixel, primary + shadow rays (4,147,200 rays/frame), optimized.cu knobs. A "step" is one
 frame. For N > 1 the path shards by frame: every rank renders its own frames of the SAME workload (frame-parallel,
 no data-path collective, "scaling": "weak"), so that the per-N values are comparable. The other BASELINE.json configs
-are reported beside the headline under "configs": [0] spheres scene 800x600, [2] one 4K depth-4 frame, groups of 16 rows interleaved
+are reported beside the headline under "configs": [0] spheres scene 800x600, [2] one 4K depth-4 frame, groups of 4 rows interleaved
 over the ranks (strong scaling, NCCL all-gather and NVLink push), [3] the 240-frame light-orbit animation of the spheres
 scene at 1080p frame-parallel over the ranks, [4] the 10 M-triangle scene at 4K built on rank 0, broadcast once and
 rendered the same way; plus a light-orbit animation of the cat scene and whole 4K depth-4 frames.
@@ -33,7 +33,7 @@ import numpy as np  # noqa: E402
 CAT_REL = os.path.join("cadnav.com_model", "Models_F0202A090", "cat.obj")
 W, H = 1920, 1080
 METRIC = "Mrays/s"
-ROW_GROUP = int(os.environ.get("RT_ROW_GROUP", "16"))  # single frames over N ranks: groups of 16 consecutive rows dealt out in turn (rt_params.row_group)
+ROW_GROUP = int(os.environ.get("RT_ROW_GROUP", "4"))  # single frames over N ranks: groups of 4 consecutive rows dealt out in turn (rt_params.row_group)
 
 
 def workload_string(mesh_name):

@@ -99,8 +99,8 @@ typedef struct rt_params {
     int32_t row_group;       /* sharding by GROUPS of consecutive rows (a power of two <= 64; 0 or 1: single rows): compact row k of this call
                                 is image row row_begin + (k / row_group) * row_step + k % row_group, row_step >= row_group being the distance
                                 between the starts of two groups (nranks * row_group for an interleave). Rows of one rank that are
-                                neighbours in the image keep a warp's 8x4 pixel tile a tile: on the 10 M-triangle scene a rank's share
-                                of single interleaved rows costs 64 % more than its eighth of the whole frame, groups of 8 rows 11 % */
+                                neighbours in the image keep a warp's 8x4 pixel tile a tile (the average rank of eight renders its
+                                share of a 4K frame 2-4 % faster; large groups unbalance the ranks) */
 } rt_params;
 
 typedef struct rt_stats {

@@ -15,7 +15,7 @@
  *                                       indirect bounce on the cuRAND XORWOW stream of optimized.cu:745 (without the
  *                                       flag: the deterministic mode the parity contract is stated on; a notice says so)
  *   --gpus N                            one process, N devices: the scene is built on device 0 and broadcast (rt_scene_broadcast,
- *                                       NCCL), every device renders every N-th group of --row-group G (default 16) consecutive rows of
+ *                                       NCCL), every device renders every N-th group of --row-group G (default 4) consecutive rows of
  *                                       each frame on its own thread, the bands are gathered to device 0 (rt_gather_framebuffer_groups)
  *   --mirror                            the mesh is a mirror (Geometry::mirror, optimized.cu:111): BASELINE.json configs[2]
  */
@@ -50,7 +50,7 @@ struct MultiGpu {
     std::vector<void*> bands;      /* device buffers, one per device */
     void* frame = nullptr;         /* device 0 */
 
-    int G = 16; /* rows per group of the interleave (--row-group): neighbouring rows keep a warp's pixel tile a tile */
+    int G = 4; /* rows per group of the interleave (--row-group): neighbouring rows keep a warp's pixel tile a tile */
     int rows_of(int H_, int r, int n_) const { return rt_shard_rows(H_, r, n_, G, nullptr); }
 
     void init(int n_, rt_scene* root, int W_, int H_) {
@@ -113,7 +113,7 @@ struct MultiGpu {
 int main(int argc, char** argv) {
     std::vector<std::string> pos;
     std::string profile = "optimized", obj = "cadnav.com_model/Models_F0202A090/cat.obj", out;
-    int W = 512, H = 512, device = 0, frames = 1, gpus = 1, row_group = 16;
+    int W = 512, H = 512, device = 0, frames = 1, gpus = 1, row_group = 4;
     bool stochastic = false, gpu_build = false, mirror = false;
     std::string pattern;
     float orbit = 0.f;
