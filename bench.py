@@ -657,6 +657,7 @@ def sharded_single_frame(rt, torch, sc, stream, world, rank, verts, recs, bvh, m
     push = None
     if world > 1:
         fp = rtd.FramePush(sc, H4, W4, world, rank, torch.device("cuda", torch.cuda.current_device()), group=ROW_GROUP)
+        push_signal = "flags in rank 0's memory (rt_peer_signal / rt_peer_wait)" if fp.signal == "flags" else "one all-reduce per frame"
         pp = fp.apply(rt.params_profile("optimized", W4, H4, 1, 4))
         ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(frames)]
         kernel_ms2 = []
@@ -692,10 +693,10 @@ def sharded_single_frame(rt, torch, sc, stream, world, rank, verts, recs, bvh, m
             same = bool(torch.equal(pushed, fg.frame))
         fp.close()
         push = {"ms_per_frame": round(float(t2[0].item()) / frames, 4), "render_ms": round(float(t2[1].item()) / frames, 4),
-                "push_and_barrier_ms": round(float(t2[0].item() - t2[1].item()) / frames, 4), "frame_equals_all_gather": same,
+                "push_and_barrier_ms": round(float(t2[0].item() - t2[1].item()) / frames, 4), "frame_equals_all_gather": same, "completion": push_signal,
                 "render_ms_per_rank": [round(float(x[1].item()) / frames, 4) for x in per_rank],
                 "kernels_only_ms_per_rank": [round(float(x.item()), 4) for x in lib_ranks],
-                "how": "rank 0 owns the frame (CUDA IPC handle broadcast once); every rank copies its band into it over NVLink, one barrier per frame"}
+                "how": "rank 0 owns the frame (CUDA IPC handle broadcast once); every rank copies its band into it over NVLink and writes a completion flag behind it"}
     return {"workload": "BASELINE.json configs[2]: mirror cat 3840x2160, reflection depth 4, groups of %d rows interleaved over %d GPU(s), all-gather to every rank" % (ROW_GROUP, world),
             "p2p_push": push,
             "rays_per_frame": int(r.item()), "ms_per_frame": round(total_ms, 4), "render_ms": round(render_ms, 4), "gather_ms": round(total_ms - render_ms, 4),

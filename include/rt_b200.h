@@ -277,6 +277,12 @@ int rt_peer_alloc(int device, size_t bytes, void** ptr, uint8_t handle[64]);
 int rt_peer_open(int device, const uint8_t handle[64], void** ptr);
 int rt_peer_close(int device, void* ptr);
 int rt_peer_free(int device, void* ptr);
+/* Completion flags for the pushes: rt_peer_signal writes `value` to the 32-bit word `flag` (device memory, typically inside the destination's
+ * rt_peer_alloc block) as an operation of the scene's stream, i.e. after the band pushed before it has landed; rt_peer_wait makes the scene's
+ * stream wait until the word is >= value (counters that only grow: the frame number). Neither involves a kernel, a collective or the host.
+ * RT_ERR_UNSUPPORTED when the driver has no stream memory operations (use a barrier then). */
+int rt_peer_signal(rt_scene* s, void* flag, uint32_t value);
+int rt_peer_wait(rt_scene* s, const void* flag, uint32_t value);
 int rt_scene_push_rows(rt_scene* s, const void* band, void* frame, int32_t W, int32_t bytes_per_pixel, int32_t row_begin, int32_t row_step, int32_t rows);
 /* the same for a band rendered with rt_params::row_group > 1: compact row k goes to row row_begin + (k / row_group) * row_step + k % row_group */
 int rt_scene_push_row_groups(rt_scene* s, const void* band, void* frame, int32_t W, int32_t bytes_per_pixel, int32_t row_begin, int32_t row_step, int32_t row_group,

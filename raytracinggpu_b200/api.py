@@ -51,6 +51,8 @@ SIGNATURES = {
     "rt_peer_close": (C.c_int, [C.c_int, _vp]),
     "rt_peer_free": (C.c_int, [C.c_int, _vp]),
     "rt_scene_push_rows": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32]),
+    "rt_peer_signal": (C.c_int, [_vp, _vp, C.c_uint32]),
+    "rt_peer_wait": (C.c_int, [_vp, _vp, C.c_uint32]),
     "rt_scene_push_row_groups": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32]),
     "rt_shard_rows": (C.c_int, [_i32, _i32, _i32, _i32, C.POINTER(rt_params)]),
     "rt_png_writer_create": (C.c_int, [C.POINTER(_vp), _i32, _i32]),
@@ -433,6 +435,14 @@ class Scene:
         """Strided device-to-device copy of this rank's row band into a (peer) frame buffer, on the scene's stream."""
         _check(lib().rt_scene_push_row_groups(self._h, C.c_void_p(int(band_ptr)), C.c_void_p(int(frame_ptr)), int(W), int(bytes_per_pixel), int(row_begin),
                                               int(row_step), int(row_group), int(rows)))
+
+    def peer_signal(self, flag_ptr, value):
+        """rt_peer_signal: stream-ordered write of `value` to the 32-bit word at flag_ptr (behind everything enqueued on the scene's stream)."""
+        _check(lib().rt_peer_signal(self._h, C.c_void_p(int(flag_ptr)), int(value) & 0xffffffff))
+
+    def peer_wait(self, flag_ptr, value):
+        """rt_peer_wait: the scene's stream waits until the 32-bit word at flag_ptr is >= value."""
+        _check(lib().rt_peer_wait(self._h, C.c_void_p(int(flag_ptr)), int(value) & 0xffffffff))
 
     def render_into(self, params, rgb=None, hit_obj=None, hit_tri=None, hit_t=None, shadow=None, flags=0):
         """rt_render with caller-provided buffers (numpy = host, torch cuda tensor / int = device)."""

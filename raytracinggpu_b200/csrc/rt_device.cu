@@ -12,6 +12,7 @@
 #include "rt_layout.h"
 #include "rt_rows.h"
 #include <cub/cub.cuh>
+#include <cuda.h> /* types of the stream memory operations only: the entry points come from cudaGetDriverEntryPoint */
 #include "rt_wavefront.cuh"
 #include "rt_stochastic.cuh"
 #include "rt_bvh_build.cuh"
@@ -2451,6 +2452,55 @@ int rt_peer_close(int device, void* ptr) {
 int rt_peer_free(int device, void* ptr) {
     DeviceGuard g(device);
     if (ptr) cudaFree(ptr);
+    return RT_OK;
+}
+
+/* ---- completion flags in peer memory: "my band of frame k has landed" as a stream-ordered 4-byte write into the destination's memory,
+ * awaited by a stream-ordered wait on the destination's stream (cuStreamWriteValue32 / cuStreamWaitValue32, bound through the runtime):
+ * no kernel, no collective, no host round trip. The write is ordered behind the copy enqueued before it on the same stream. */
+namespace {
+struct StreamMemOps {
+    CUresult (*write32)(CUstream, CUdeviceptr, cuuint32_t, unsigned int) = nullptr;
+    CUresult (*wait32)(CUstream, CUdeviceptr, cuuint32_t, unsigned int) = nullptr;
+    bool ok = false;
+};
+StreamMemOps& stream_memops() {
+    static StreamMemOps m;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        cudaDriverEntryPointQueryResult q1, q2;
+        void *f1 = nullptr, *f2 = nullptr;
+        if (cudaGetDriverEntryPoint("cuStreamWriteValue32", &f1, cudaEnableDefault, &q1) == cudaSuccess && q1 == cudaDriverEntryPointSuccess &&
+            cudaGetDriverEntryPoint("cuStreamWaitValue32", &f2, cudaEnableDefault, &q2) == cudaSuccess && q2 == cudaDriverEntryPointSuccess && f1 && f2) {
+            m.write32 = reinterpret_cast<decltype(m.write32)>(f1);
+            m.wait32 = reinterpret_cast<decltype(m.wait32)>(f2);
+            m.ok = true;
+        } else {
+            cudaGetLastError();
+        }
+    }
+    return m;
+}
+} // namespace
+
+int rt_peer_signal(rt_scene* s, void* flag, uint32_t value) {
+    if (!s || !flag) return rtb::fail(RT_ERR_INVALID, "rt_peer_signal: bad argument");
+    DeviceGuard g(s->device);
+    StreamMemOps& m = stream_memops();
+    if (!m.ok) return rtb::fail(RT_ERR_UNSUPPORTED, "rt_peer_signal: the driver exposes no stream memory operations");
+    const CUresult r = m.write32((CUstream)s->stream, (CUdeviceptr)(uintptr_t)flag, value, CU_STREAM_WRITE_VALUE_DEFAULT);
+    if (r != CUDA_SUCCESS) return rtb::fail(RT_ERR_CUDA, "rt_peer_signal: cuStreamWriteValue32 failed (%d)", (int)r);
+    return RT_OK;
+}
+
+int rt_peer_wait(rt_scene* s, const void* flag, uint32_t value) {
+    if (!s || !flag) return rtb::fail(RT_ERR_INVALID, "rt_peer_wait: bad argument");
+    DeviceGuard g(s->device);
+    StreamMemOps& m = stream_memops();
+    if (!m.ok) return rtb::fail(RT_ERR_UNSUPPORTED, "rt_peer_wait: the driver exposes no stream memory operations");
+    const CUresult r = m.wait32((CUstream)s->stream, (CUdeviceptr)(uintptr_t)flag, value, CU_STREAM_WAIT_VALUE_GEQ);
+    if (r != CUDA_SUCCESS) return rtb::fail(RT_ERR_CUDA, "rt_peer_wait: cuStreamWaitValue32 failed (%d)", (int)r);
     return RT_OK;
 }
 

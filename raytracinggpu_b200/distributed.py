@@ -108,9 +108,14 @@ class FrameGather:
 
 class FramePush:
     """Row-interleaved rendering of H x W frames on `world` ranks with the bands pushed into rank `dst`'s frame buffer over
-    NVLink (CUDA IPC + peer copies; NCCL backend, one process per GPU of one node). `frame` is valid on rank `dst`."""
+    NVLink (CUDA IPC + peer copies; NCCL backend, one process per GPU of one node). `frame` is valid on rank `dst`.
 
-    def __init__(self, scene, H, W, world, rank, device, dst=0, channels=3, group=1):
+    signal="flags" (default when the driver allows it): completion travels as stream-ordered 32-bit writes into the destination's memory
+    (rt_peer_signal / rt_peer_wait): rank r writes the frame number to flag r behind its copy, the destination's stream waits for every flag;
+    the destination acknowledges a frame it has consumed in an `ack` word that the peers' streams wait on before they overwrite the buffer
+    of two frames ago. No kernel, no collective, no host round trip per frame. signal="allreduce": one NCCL all-reduce per frame."""
+
+    def __init__(self, scene, H, W, world, rank, device, dst=0, channels=3, group=1, signal="flags"):
         from . import api
         self.scene, self.H, self.W, self.world, self.rank, self.dst, self.channels = scene, H, W, world, rank, dst, channels
         self.group = group
@@ -119,13 +124,16 @@ class FramePush:
         self.band = torch.zeros((max(self.row_count, 1), W, channels), dtype=torch.uint8, device=device)
         handle = torch.zeros(64, dtype=torch.uint8, device=device)
         self._own = self._peer = None
-        # two frames alternate: the destination may still be reading frame k while the peers push frame k + 1; the all-reduce
-        # after push k + 1 (enqueued on the destination behind its read of frame k) is what lets buffer k % 2 be written again
+        # two frames alternate: the destination may still be reading frame k while the peers push frame k + 1
         self.frame_bytes = H * W * channels
+        self.flags_off = (2 * self.frame_bytes + 255) & ~255  # world completion flags + one ack word behind the two frames
         self.k = 0
         if rank == dst:
-            self._own, hb = api.peer_alloc(self.device_index, 2 * self.frame_bytes)
+            self._own, hb = api.peer_alloc(self.device_index, self.flags_off + 4 * (world + 1))
             handle.copy_(torch.frombuffer(bytearray(hb), dtype=torch.uint8))
+            zeros = torch.zeros(world + 1, dtype=torch.int32, device=device)
+            scene.push_rows(zeros.data_ptr(), self._own + self.flags_off, world + 1, 4, 0, 1, 1)
+            scene.sync()
         if world > 1:
             dist.broadcast(handle, dst)
         if rank == dst:
@@ -135,20 +143,57 @@ class FramePush:
             self._base = self._peer
         self.frame_ptr = self._base
         self._token = torch.zeros(1, dtype=torch.int32, device=device)
+        # every rank must take the same path: try a harmless flag operation (value 0 to / against this rank's own flag), agree on the outcome
+        self.signal = "allreduce"
+        if signal == "flags" and world > 1:
+            ok = 1
+            try:
+                scene.peer_wait(self._base + self.flags_off + 4 * rank, 0)
+                if rank != dst:
+                    scene.peer_signal(self._base + self.flags_off + 4 * rank, 0)
+                scene.sync()
+            except api.RtError:
+                ok = 0
+            t = torch.tensor([ok], dtype=torch.int32, device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            if int(t.item()) == 1:
+                self.signal = "flags"
 
     def apply(self, params):
         params.row_begin, params.row_step, params.row_count, params.row_group = self.row_begin, self.row_step, self.row_count, self.group
         return params
 
-    def push(self):
-        """Enqueue this rank's copy (on the scene's stream) and the barrier that tells `dst` every band has landed."""
+    def push(self, release=True):
+        """Enqueue this rank's copy (on the scene's stream) and the completion signal that tells `dst` every band has landed.
+        release (destination, flags mode): acknowledge the frame at once — pass False and call release() after enqueueing the work that
+        reads the frame, so that the peers do not overwrite it two frames later while it is still being read."""
         self.frame_ptr = self._base + (self.k & 1) * self.frame_bytes
         self.k += 1
+        k = self.k  # frame number, from 1
+        flags = self._base + self.flags_off
+        if self.signal == "flags" and self.rank != self.dst and k > 2:
+            self.scene.peer_wait(flags + 4 * self.world, k - 2)  # the destination has consumed the frame that lived in this buffer
         self.scene.push_rows(self.band.data_ptr(), self.frame_ptr, self.W, self.channels, self.row_begin, self.row_step, self.row_count, self.group)
-        if self.world > 1:
+        if self.world == 1:
+            return
+        if self.signal == "flags":
+            if self.rank != self.dst:
+                self.scene.peer_signal(flags + 4 * self.rank, k)
+            else:
+                for r in range(self.world):
+                    if r != self.dst:
+                        self.scene.peer_wait(flags + 4 * r, k)
+                if release:
+                    self.release()
+        else:
             _order_after_scene(self.scene)   # the collective runs on torch's current stream: behind the copy on the scene's
             dist.all_reduce(self._token)     # complete when every rank's copy is
             _order_scene_after_current(self.scene)  # what the destination enqueues next on the scene's stream sees every band
+
+    def release(self):
+        """Destination, flags mode: everything enqueued so far on the scene's stream has read the current frame; its buffer may be reused."""
+        if self.signal == "flags" and self.rank == self.dst and self.world > 1:
+            self.scene.peer_signal(self._base + self.flags_off + 4 * self.world, self.k)
 
     def frame_tensor(self):
         """rank `dst` only: a copy of the assembled frame as a torch tensor (enqueued on the scene's stream)."""

@@ -41,21 +41,27 @@ def main():
     sc.sync()
     if rank == 0:
         assert np.array_equal(frame.cpu().numpy(), whole), "rt_gather_framebuffer"
-    # ---- CUDA IPC peer frame, scene on its own (non-blocking) stream: three frames back to back, double-buffered
-    fp = rtd.FramePush(sc, H, W, world, rank, dev, group=8)
-    pp = fp.apply(profiles.params("optimized", W, H, 1, 3))
-    outs = []
-    for k in range(3):
-        sc.render_into(pp, rgb=fp.band, flags=rt.RT_RENDER_NO_SYNC)
-        fp.push()
+    # ---- CUDA IPC peer frame, scene on its own (non-blocking) stream: frames back to back, double-buffered; completion by flags in the
+    # destination's memory (rt_peer_signal / rt_peer_wait) and by an all-reduce
+    for mode in ("flags", "allreduce"):
+        fp = rtd.FramePush(sc, H, W, world, rank, dev, group=8, signal=mode)
+        if mode == "allreduce":
+            assert fp.signal == "allreduce"
+        pp = fp.apply(profiles.params("optimized", W, H, 1, 3))
+        outs = []
+        for k in range(5):
+            sc.render_into(pp, rgb=fp.band, flags=rt.RT_RENDER_NO_SYNC)
+            fp.push(release=False)
+            if rank == 0:
+                outs.append(fp.frame_tensor())
+            fp.release()
+        sc.sync()
+        torch.cuda.synchronize()
         if rank == 0:
-            outs.append(fp.frame_tensor())
-    sc.sync()
-    torch.cuda.synchronize()
-    if rank == 0:
-        for o in outs:
-            assert np.array_equal(o.cpu().numpy(), whole), "FramePush"
-    fp.close()
+            print("FramePush", mode, "->", fp.signal)
+            for o in outs:
+                assert np.array_equal(o.cpu().numpy(), whole), "FramePush " + mode
+        fp.close()
     comm.close()
     sc.close()
     dist.barrier()
