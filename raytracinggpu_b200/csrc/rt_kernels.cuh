@@ -163,9 +163,10 @@ __device__ __forceinline__ TriScreen tri_screen(const float4 q0, const float4 q1
     return s;
 }
 __device__ __forceinline__ bool tri_finish(const TriScreen& s, float& t) {
-    const float beta = s.nb / s.d;
-    const float gamma = s.ng / s.d;
-    t = s.nt / s.d;
+    /* the reference's three divisions by d (moller_trumbore, optimized.cu:213-216), bit for bit, with the reciprocal refined once (div3) */
+    const F3 q = div3(f3(s.nb, s.ng, s.nt), s.d);
+    const float beta = q.x, gamma = q.y;
+    t = q.z;
     return (0 <= beta) & (beta <= 1) & (0 <= gamma) & (gamma <= 1) & (beta + gamma <= 1) & (t > 0);
 }
 
