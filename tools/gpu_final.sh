@@ -6,7 +6,7 @@ nvidia-smi --query-gpu=name,driver_version,clocks.max.sm,memory.total --format=c
 echo "== pytest -m gpu"; timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -5 | tee $OUT/pytest_gpu.log
 echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3 | tee $OUT/smoke.log
 echo "== reference arm"; timeout 600 python bench.py --impl reference --steps 5 --warmup 3 > $OUT/bench_reference.json 2>$OUT/bench_reference.err; echo "ref exit $?"
-echo "== bench (default flags)"; /usr/bin/time -v -o $OUT/bench_time.txt timeout 1200 python bench.py > $OUT/bench_n1.json 2> $OUT/bench_n1.err; echo "bench exit $?"; grep "Elapsed" $OUT/bench_time.txt
+echo "== bench (default flags)"; S=$SECONDS; timeout 1200 python bench.py > $OUT/bench_n1.json 2> $OUT/bench_n1.err; echo "bench exit $? in $((SECONDS-S)) s" | tee $OUT/bench_time.txt
 python - <<PY
 import json
 d=json.loads(open("$OUT/bench_n1.json").read().strip().splitlines()[-1])
