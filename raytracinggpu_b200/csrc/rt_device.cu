@@ -2292,7 +2292,14 @@ bool is_pinned_host(const void* p) {
 void frame_key(rt_scene* s, const FramePlan& P, std::vector<unsigned char>& key) {
     key.clear();
     auto put = [&](const void* p, size_t n) { key.insert(key.end(), (const unsigned char*)p, (const unsigned char*)p + n); };
-    put(&P, sizeof P);
+    if (P.async_copy) { /* host outputs that leave on the copy stream are not part of the recorded launches: any host buffer may follow a replay */
+        FramePlan Q = P;
+        for (int k = 0; k < 5; k++)
+            if (Q.copy_back[k]) Q.user[k] = nullptr;
+        put(&Q, sizeof Q);
+    } else {
+        put(&P, sizeof P);
+    }
     put(&s->header, sizeof s->header);
     for (int k = 0; k < 2; k++) {
         rtk::BinsView v;
