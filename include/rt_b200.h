@@ -217,7 +217,7 @@ int rt_scene_get_stream(rt_scene* s, void** cuda_stream);
  *   "wide" -1|0|1             4-wide index for the tree search: default on for stochastic indirect bounces only
  *   "strips" 0..8             row bands on separate streams, 0 = chosen per call
  *   "bins_r", "task_factor", "npool_cap", "run_shift", "gss", "leaves_blocks", "side_stream", "diffuse_kernels",
- *   "stoch_mega", "wide_count", "graph", "six", "split", "debug_times", "debug_pool", "debug_bins", "debug_cost"   (see rt_device.cu: RtOptions)
+ *   "stoch_mega", "wide_count", "graph", "six", "split", "fair_share", "top_smem", "debug_times", "debug_pool", "debug_bins", "debug_cost"   (see rt_device.cu: RtOptions)
  *   "transcendentals" 1|0     stochastic mode: log / cos / sin of optimized.cu:756-758, 635-636 by CUDA's single-precision
  *                             logf / cosf / sinf (1, default: what optimized.cu itself calls; frames equal those of the reference
  *                             kernel compiled without --use_fast_math bit for bit) or evaluated in double and rounded once (0)

@@ -59,6 +59,8 @@ struct RtOptions {
                               * (the oracle's other canon: what a correctly rounded libm would give; 3-4x the instructions) */
     int graph = 1;           /* replay a recorded CUDA graph when a frame repeats the previous call's plan */
     int fair_share = 1;      /* wf_traverse: an admission takes at most the warp's even share of a short queue */
+    int top_smem = 0;        /* wf_traverse takes the top four levels of the tree from shared memory (rt_wavefront.cuh: build_top_table). Measured
+                              * (profiles/r02_notes.md): see there; off by default */
     int split = 0;           /* two row bands: per cent of the rows in the first band; 0: equal halves */
     int six = 1;             /* kernels with the sphere loops unrolled for the reference's room of exactly six spheres (constants as direct operands) */
     int one_shot = 1;        /* stochastic frames of one sample and one segment through the deterministic pipeline with jittered camera rays */
@@ -94,6 +96,7 @@ static const RtOptionKey kOptionKeys[] = {
     {"one_shot", &RtOptions::one_shot, 0, 1},
     {"six", &RtOptions::six, 0, 1},
     {"split", &RtOptions::split, 0, 95},
+    {"top_smem", &RtOptions::top_smem, 0, 1},
     {"fair_share", &RtOptions::fair_share, 0, 1},
     {"debug_times", &RtOptions::debug_times, 0, 1},
     {"debug_pool", &RtOptions::debug_pool, 0, 1},
@@ -139,6 +142,11 @@ struct rt_scene {
     cudaEvent_t pin_ev[2] = {nullptr, nullptr};
     bool pin_ev_recorded[2] = {false, false};
     int pin_set = 0;
+    /* option top_smem: the top levels of the packed tree as a breadth-first table for the TOPS instantiations of wf_traverse */
+    float4* top_nodes = nullptr;
+    int* d_n_top = nullptr;
+    int n_top = 0;
+    uint64_t top_generation = ~0ull;
 #ifdef RT_TIMELINE
     unsigned long long* tl_buf = nullptr; /* 2 x 64 words: min start / max end of the frame's launches (globaltimer, ns) */
     int tl_n = 0;
@@ -625,6 +633,8 @@ void rt_scene_destroy(rt_scene* s) {
     }
     if (s->frame_done) cudaEventDestroy(s->frame_done);
     if (s->pin_alt) cudaFreeHost(s->pin_alt);
+    if (s->top_nodes) cudaFree(s->top_nodes);
+    if (s->d_n_top) cudaFree(s->d_n_top);
     if (s->up_stream) {
         cudaStreamSynchronize(s->up_stream);
         cudaStreamDestroy(s->up_stream);
@@ -1563,6 +1573,8 @@ struct FramePlan {
     bool jitter;       /* one sample of one segment in stochastic mode: the deterministic pipeline with jittered camera rays */
     /* wavefront pipeline */
     bool wide, anchored, diffuse_only, trav_round0, dbg_times;
+    bool tops;        /* wf_traverse reads the top levels from shared memory (option top_smem) */
+    int n_top;
     int segments, npool_cap, n_strips, spill_cap;
     size_t trav_smem;
     unsigned pers_grid;
@@ -1768,6 +1780,8 @@ int plan_frame(rt_scene* s, const rt_params* p, uint32_t flags, void* const user
     }
     const bool stochastic_pipeline = stochastic && !one_shot;
     P.wide = P.anchored = P.diffuse_only = P.trav_round0 = P.dbg_times = false;
+    P.tops = false;
+    P.n_top = 0;
     P.npool_cap = P.spill_cap = 0;
     P.n_strips = 1;
     P.trav_smem = P.st_rng_off = P.st_total_off = P.st_rec_off = 0;
@@ -1828,6 +1842,8 @@ int plan_frame(rt_scene* s, const rt_params* p, uint32_t flags, void* const user
         CUDA_TRY(cudaFuncSetAttribute(rtk::wf_traverse<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trav_smem));
         CUDA_TRY(cudaFuncSetAttribute(rtk::wf_traverse<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trav_smem));
         CUDA_TRY(cudaFuncSetAttribute(rtk::wf_traverse<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trav_smem));
+        CUDA_TRY(cudaFuncSetAttribute(rtk::wf_traverse<false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trav_smem));
+        CUDA_TRY(cudaFuncSetAttribute(rtk::wf_traverse<false, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trav_smem));
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wide ? rtk::wf_traverse<false, false, true> : rtk::wf_traverse<false, false, false>, WF_THREADS, trav_smem));
         cudaDeviceProp prop;
         CUDA_TRY(cudaGetDeviceProperties(&prop, s->device));
@@ -1924,6 +1940,22 @@ int plan_frame(rt_scene* s, const rt_params* p, uint32_t flags, void* const user
             s->st_buf_bytes = need;
         }
     }
+        /* the table of the top levels, rebuilt when the tree changes (one kernel of one thread + a 4-byte read-back) */
+        bool tops = s->opt.top_smem != 0 && h.has_mesh && h.root_ref >= 0 && !wide && !count && (long long)h.n_inner + WF_TOP_MAX < (1ll << 26);
+        if (tops && s->top_generation != s->mesh_generation) {
+            if (!s->top_nodes) {
+                CUDA_TRY(cudaMalloc(&s->top_nodes, WF_TOP_MAX * 4 * sizeof(float4)));
+                CUDA_TRY(cudaMalloc(&s->d_n_top, sizeof(int)));
+            }
+            rtk::build_top_table<<<1, 32, 0, s->stream>>>(reinterpret_cast<const float4*>(s->blob + h.off_nodes), h.n_inner, h.root_ref, WF_TOP_MAX, s->top_nodes, s->d_n_top);
+            CUDA_TRY(cudaGetLastError());
+            CUDA_TRY(cudaMemcpyAsync(&s->n_top, s->d_n_top, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+            CUDA_TRY(cudaStreamSynchronize(s->stream));
+            s->top_generation = s->mesh_generation;
+        }
+        tops = tops && s->n_top > 0;
+        P.tops = tops;
+        P.n_top = tops ? s->n_top : 0;
         P.wide = wide;
         P.anchored = anchored;
         P.diffuse_only = diffuse_only;
@@ -2084,6 +2116,8 @@ int enqueue_frame(rt_scene* s, const FramePlan& P, int& launches, bool& strip_co
             g.run_shift = s->opt.run_shift;
             g.gss_factor = s->opt.gss;
             g.fair_share = s->opt.fair_share;
+            g.top = P.tops ? s->top_nodes : nullptr;
+            g.n_top = P.n_top;
         }
         g.dbg_warps = dbg_ptr;
         g.anchored = anchored ? 1 : 0;
@@ -2176,9 +2210,11 @@ int enqueue_frame(rt_scene* s, const FramePlan& P, int& launches, bool& strip_co
                         TL_MARK("traverse");
                         if (stochastic) {
                             if (wide) CUDA_TRY(chain.launch(rtk::wf_traverse<false, true, true>, dim3(pers_grid), WF_THREADS, trav_smem, tstream, s->header, s->blob, g, npool_cap));
+                            else if (P.tops) CUDA_TRY(chain.launch(rtk::wf_traverse<false, true, false, true>, dim3(pers_grid), WF_THREADS, trav_smem, tstream, s->header, s->blob, g, npool_cap));
                             else CUDA_TRY(chain.launch(rtk::wf_traverse<false, true, false>, dim3(pers_grid), WF_THREADS, trav_smem, tstream, s->header, s->blob, g, npool_cap));
                         } else {
                             if (wide) CUDA_TRY(chain.launch(rtk::wf_traverse<false, false, true>, dim3(pers_grid), WF_THREADS, trav_smem, tstream, s->header, s->blob, g, npool_cap));
+                            else if (P.tops) CUDA_TRY(chain.launch(rtk::wf_traverse<false, false, false, true>, dim3(pers_grid), WF_THREADS, trav_smem, tstream, s->header, s->blob, g, npool_cap));
                             else CUDA_TRY(chain.launch(rtk::wf_traverse<false, false, false>, dim3(pers_grid), WF_THREADS, trav_smem, tstream, s->header, s->blob, g, npool_cap));
                         }
                         launches++;
@@ -2196,11 +2232,13 @@ int enqueue_frame(rt_scene* s, const FramePlan& P, int& launches, bool& strip_co
                 } else if (stochastic) {
                     if (count) CUDA_TRY(chain.launch(rtk::wf_traverse<true, true, false>, dim3(pers_grid), WF_THREADS, trav_smem, stream, s->header, s->blob, g, npool_cap));
                     else if (wide) CUDA_TRY(chain.launch(rtk::wf_traverse<false, true, true>, dim3(pers_grid), WF_THREADS, trav_smem, stream, s->header, s->blob, g, npool_cap));
+                    else if (P.tops) CUDA_TRY(chain.launch(rtk::wf_traverse<false, true, false, true>, dim3(pers_grid), WF_THREADS, trav_smem, stream, s->header, s->blob, g, npool_cap));
                     else CUDA_TRY(chain.launch(rtk::wf_traverse<false, true, false>, dim3(pers_grid), WF_THREADS, trav_smem, stream, s->header, s->blob, g, npool_cap));
                 } else {
                     if (count && wide) CUDA_TRY(chain.launch(rtk::wf_traverse<true, false, true>, dim3(pers_grid), WF_THREADS, trav_smem, stream, s->header, s->blob, g, npool_cap));
                     else if (count) CUDA_TRY(chain.launch(rtk::wf_traverse<true, false, false>, dim3(pers_grid), WF_THREADS, trav_smem, stream, s->header, s->blob, g, npool_cap));
                     else if (wide) CUDA_TRY(chain.launch(rtk::wf_traverse<false, false, true>, dim3(pers_grid), WF_THREADS, trav_smem, stream, s->header, s->blob, g, npool_cap));
+                    else if (P.tops) CUDA_TRY(chain.launch(rtk::wf_traverse<false, false, false, true>, dim3(pers_grid), WF_THREADS, trav_smem, stream, s->header, s->blob, g, npool_cap));
                     else CUDA_TRY(chain.launch(rtk::wf_traverse<false, false, false>, dim3(pers_grid), WF_THREADS, trav_smem, stream, s->header, s->blob, g, npool_cap));
                 }
                 launches++;
@@ -2307,7 +2345,7 @@ void frame_key(rt_scene* s, const FramePlan& P, std::vector<unsigned char>& key)
         if (P.anchored) v = bins_view(s->bins[k]);
         put(&v, sizeof v);
     }
-    const void* ptrs[] = {s->blob, s->jitter_tab, s->wf_queue, s->wf_tasks, s->wf_counters, s->wf_spill, s->st_buf, s->rng_states, s->gamma_tab, s->sticky, s->stream};
+    const void* ptrs[] = {s->top_nodes, s->blob, s->jitter_tab, s->wf_queue, s->wf_tasks, s->wf_counters, s->wf_spill, s->st_buf, s->rng_states, s->gamma_tab, s->sticky, s->stream};
     put(ptrs, sizeof ptrs);
     const size_t nums[] = {s->wf_capacity, s->wf_tasks_cap, (size_t)s->task_factor, (size_t)s->leaves_blocks_per_sm, (size_t)s->sm_count, (size_t)s->trav_blocks_per_sm};
     put(nums, sizeof nums);

@@ -91,6 +91,8 @@ struct WfArgs {
     int run_shift;  /* log2 of the admission run length, -1 = chosen per launch from the queue length */
     int gss_factor; /* the last gss_factor * n_warps runs are admitted one at a time */
     int fair_share; /* 1: an admission takes at most the warp's even share of the queue (short queues) */
+    const float4* top; /* TOPS instantiations of wf_traverse: the top levels of the tree as a table of n_top records in breadth-first order, */
+    int n_top;         /* child references into the table rewritten to n_inner + slot (build_top_table); staged in shared memory per block */
     int* spill;     /* node-pool overflow area: spill_cap ints per traversal warp (global memory) */
     int spill_cap;
     int* dbg_warps; /* investigation aid (RT_DEBUG_WARPS, COUNT kernels only): 16 ints per traversal warp and round */
@@ -1048,12 +1050,55 @@ struct WfWarpSmem { /* per warp; followed by the node pool (npool_cap ints) */
 #ifndef RT_WIDE_BLOCKS
 #define RT_WIDE_BLOCKS 6 /* resident blocks per SM the wide instantiations are compiled for: 80 registers, no spills (8: 64 registers, 86 B of spills, slower) */
 #endif
-template <bool COUNT, bool STOCH, bool WIDE>
+/* ---- the top levels of the tree in shared memory (north_star's "shared-memory-staged top levels"; option "top_smem") ------------------
+ * build_top_table copies the first WF_TOP_MAX inner records in breadth-first order (the root, its children, ...: four complete levels)
+ * into a table and rewrites the child references that stay inside the table to n_inner + slot, an index no real record has. A TOPS
+ * instantiation of wf_traverse stages the table in shared memory once per block and starts every ray at slot 0; an N step takes a record
+ * from shared memory when its index is >= n_inner and from global memory otherwise. Same boxes, same references, same visiting order.
+ * 15 records (960 B) is what fits: the pools take 26 KB per block and eight blocks share an SM's 228 KB. */
+#define WF_TOP_MAX 15
+__global__ void build_top_table(const float4* __restrict__ nodes, int n_inner, int root_ref, int limit, float4* __restrict__ top, int* __restrict__ n_top) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    int idx[WF_TOP_MAX];
+    int count = 0;
+    if (root_ref >= 0 && limit > 0) {
+        idx[0] = root_ref;
+        count = 1;
+    }
+    for (int s = 0; s < count; s++) {
+        const float4* n = nodes + 4 * (size_t)idx[s];
+        float4 q3 = n[3];
+        int rl = __float_as_int(q3.x), rr = __float_as_int(q3.y);
+        if (rl >= 0 && count < limit) {
+            idx[count] = rl;
+            rl = n_inner + count++;
+        }
+        if (rr >= 0 && count < limit) {
+            idx[count] = rr;
+            rr = n_inner + count++;
+        }
+        q3.x = __int_as_float(rl);
+        q3.y = __int_as_float(rr);
+        top[4 * s + 0] = n[0];
+        top[4 * s + 1] = n[1];
+        top[4 * s + 2] = n[2];
+        top[4 * s + 3] = q3;
+    }
+    *n_top = count;
+}
+
+template <bool COUNT, bool STOCH, bool WIDE, bool TOPS = false>
 __global__ void __launch_bounds__(WF_THREADS, WIDE ? RT_WIDE_BLOCKS : 8) wf_traverse(const __grid_constant__ SceneHeader h, const unsigned char* __restrict__ blob,
                                                          const __grid_constant__ WfArgs g, const int npool_cap) {
+    static_assert(!(TOPS && WIDE), "the top table holds two-child records");
     pdl_wait_then_release();
     TL_BEGIN(g);
     extern __shared__ __align__(16) unsigned char wf_smem[];
+    __shared__ float4 top_sm[TOPS ? WF_TOP_MAX * 4 : 1];
+    if (TOPS) {
+        for (int i = threadIdx.x; i < g.n_top * 4; i += WF_THREADS) top_sm[i] = __ldg(g.top + i);
+        __syncthreads();
+    }
     const RenderArgs& a = g.a;
     const float4* nodes = reinterpret_cast<const float4*>(blob + h.off_nodes);
     const float4* tris = reinterpret_cast<const float4*>(blob + h.off_tris);
@@ -1195,7 +1240,7 @@ __global__ void __launch_bounds__(WF_THREADS, WIDE ? RT_WIDE_BLOCKS : 8) wf_trav
                     sm.D[slot] = p1;
                     sm.best[slot] = WF_NOHIT;
                     sm.entry[slot] = e;
-                    const int task = (slot << 26) | (h.root_ref >= 0 ? (WIDE ? h.wroot_ref : h.root_ref) : (-1 - h.root_ref));
+                    const int task = (slot << 26) | (h.root_ref >= 0 ? (WIDE ? h.wroot_ref : (TOPS ? h.n_inner : h.root_ref)) : (-1 - h.root_ref));
                     const int pos = __popc(vmask & lt_mask);
                     if (h.root_ref >= 0) npool[nN + pos] = task;
                     else sm.tpool[nT + pos] = task;
@@ -1431,10 +1476,19 @@ __global__ void __launch_bounds__(WF_THREADS, WIDE ? RT_WIDE_BLOCKS : 8) wf_trav
                 slot = (unsigned)task >> 26;
                 const float4 a4 = sm.A[slot], b4 = sm.B[slot];
                 if (!(b4.w < 0.f)) {
-                    const float4* n = nodes + 4 * (size_t)(task & 0x3ffffff);
+                    const int node = task & 0x3ffffff;
                     float4 q0, q1, q2, q3f;
-                    ldg256(n, q0, q1);
-                    ldg256(n + 2, q2, q3f);
+                    if (TOPS && node >= h.n_inner) { /* a record of the staged top levels */
+                        const float4* n = top_sm + 4 * (node - h.n_inner);
+                        q0 = n[0];
+                        q1 = n[1];
+                        q2 = n[2];
+                        q3f = n[3];
+                    } else {
+                        const float4* n = nodes + 4 * (size_t)node;
+                        ldg256(n, q0, q1);
+                        ldg256(n + 2, q2, q3f);
+                    }
                     const int2 q3 = make_int2(__float_as_int(q3f.x), __float_as_int(q3f.y));
                     if (COUNT && __float_as_int(q3f.z) == 0) w.nodes++;
                     RayCtx c;

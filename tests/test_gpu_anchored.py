@@ -121,3 +121,36 @@ def test_wide_index_equals_two_child_records(scene):
     d2 = cat_or_torus("array_bvh")
     scenes.upload(scene, d2)
     scenes.compare(scene.render(q), scenes.run_oracle(d2, q))
+
+
+@pytest.mark.parametrize("profile,W,H,bounce,mirror,stoch,anchored", [
+    ("optimized", 960, 540, 1, 0, False, 0),   # every ray through the tree search
+    ("cpu", 640, 360, 0, 0, False, 0),         # push order 0, extra segment
+    ("optimized", 960, 540, 4, 1, False, -1),  # mirror mesh: bounce rays through wf_traverse beside the bins
+    ("optimized", 480, 270, 3, 0, True, -1),   # stochastic passes (the wide index is switched off below: TOPS is a two-child variant)
+])
+def test_top_levels_from_shared_memory(scene, profile, W, H, bounce, mirror, stoch, anchored):
+    """Option top_smem: wf_traverse takes the records of the top four levels from a breadth-first table staged in shared memory
+    (build_top_table: child references inside the table rewritten to n_inner + slot). Same boxes, same references, same order:
+    every output equals the global-memory traversal's, and the table follows a mesh change."""
+    desc = cat_or_torus(profile, mirror)
+    scenes.upload(scene, desc)
+    scene.set_option("anchored", anchored)
+    scene.set_option("wide", 0)
+    p = profiles.params(profile, W, H, 2 if stoch else 1, bounce)
+    if stoch:
+        p.aa_sigma, p.indirect = 0.2, 1
+    a = scene.render(p)
+    scene.set_option("top_smem", 1)
+    b = scene.render(p)
+    same(a, b)
+    assert a["stats"]["rays"] == b["stats"]["rays"]
+    # another tree: the table is rebuilt
+    other = scenes.torus_scene(profile, mirror=mirror, nu=40, nv=20)
+    scenes.upload(scene, other)
+    c = scene.render(p)
+    scene.set_option("top_smem", 0)
+    d = scene.render(p)
+    same(c, d)
+    if not stoch:
+        scenes.compare(c, scenes.run_oracle(other, p))

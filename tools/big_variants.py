@@ -15,7 +15,7 @@ sc.set_mesh_from(mesh, id=1)
 p = profiles.params("optimized", 3840, 2160, 1, 1)
 rgb = torch.empty((2160, 3840, 3), dtype=torch.uint8, device="cuda")
 ref = None
-for variant, extra in ((2, {}), (1, {}), (2, {"wide": 1})):
+for variant, extra in ((2, {}), (2, {"top_smem": 1}), (2, {"top_smem": 0}), (1, {})):
     sc.set_option("variant", variant)
     for k, v in extra.items():
         sc.set_option(k, v)
