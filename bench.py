@@ -246,7 +246,7 @@ def run_ours(args):
     # region waits for every kernel and every copy. Two host frames alternate, as a consumer that reads frame k during step k + 1 needs.
     host_frames = [torch.empty((H, W, 3), dtype=torch.uint8).pin_memory() for _ in range(2)]
     host_rgb = host_frames[0]
-    e2e_steps = max(3, min(args.steps, 20))
+    e2e_steps = max(3, min(args.steps, 50))
 
     def e2e_run(steps, pipelined):
         t0 = time.perf_counter()
