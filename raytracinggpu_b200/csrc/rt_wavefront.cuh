@@ -696,7 +696,12 @@ __device__ __forceinline__ void answer_deferred(const SceneHeader& h, const unsi
 /* JITTER (deterministic instantiations only): the camera ray takes the Box-Muller jitter of optimized.cu:753-759 from the first two
  * uniforms of the pixel's stream; nothing else of the stochastic mode is needed when a frame is one sample of one segment. */
 template <bool COUNT, bool STOCH, bool DIFFUSE = false, bool LEAN = false, bool JITTER = false, int NS = 0>
-__global__ void __launch_bounds__(WF_THREADS, 10) wf_generate(const __grid_constant__ SceneHeader h, const unsigned char* __restrict__ blob,
+#ifndef RT_GEN_BLOCKS
+#define RT_GEN_BLOCKS 12 /* resident blocks per SM the deterministic instantiations are compiled for: 40 registers, the same 44 B of spills as at 10 blocks /
+                          * 48 registers, and 1-1.7 % faster frames (same-box A/B; 8 / 9 blocks at 56 registers without spills: slower, 14 / 16 at 32
+                          * registers: no gain). The stochastic instantiations stay at 10 (at 12 they spill 250-280 B). */
+#endif
+__global__ void __launch_bounds__(WF_THREADS, STOCH ? 10 : RT_GEN_BLOCKS) wf_generate(const __grid_constant__ SceneHeader h, const unsigned char* __restrict__ blob,
                                                          const __grid_constant__ WfArgs g) {
     pdl_wait_then_release();
     TL_BEGIN(g);
@@ -771,7 +776,10 @@ __global__ void __launch_bounds__(WF_THREADS, 10) wf_generate(const __grid_const
 
 /* ---- wf_shade: one thread per answered closest-hit query of round g.round ------------------------------------------ */
 template <bool COUNT, bool STOCH, bool DIFFUSE = false, bool LEAN = false, int NS = 0>
-__global__ void __launch_bounds__(WF_THREADS, 8) wf_shade(const __grid_constant__ SceneHeader h, const unsigned char* __restrict__ blob,
+#ifndef RT_SHADE_BLOCKS
+#define RT_SHADE_BLOCKS 8
+#endif
+__global__ void __launch_bounds__(WF_THREADS, RT_SHADE_BLOCKS) wf_shade(const __grid_constant__ SceneHeader h, const unsigned char* __restrict__ blob,
                                                       const __grid_constant__ WfArgs g) {
     pdl_wait_then_release();
     TL_BEGIN(g);
