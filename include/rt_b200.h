@@ -280,7 +280,9 @@ int rt_peer_free(int device, void* ptr);
 /* Completion flags for the pushes: rt_peer_signal writes `value` to the 32-bit word `flag` (device memory, typically inside the destination's
  * rt_peer_alloc block) as an operation of the scene's stream, i.e. after the band pushed before it has landed; rt_peer_wait makes the scene's
  * stream wait until the word is >= value (counters that only grow: the frame number). Neither involves a kernel, a collective or the host.
- * RT_ERR_UNSUPPORTED when the driver has no stream memory operations (use a barrier then). */
+ * RT_ERR_UNSUPPORTED when the driver has no stream memory operations (use a barrier then). A wait is meant for a write that arrives from
+ * ANOTHER device: streams of one device may share a hardware queue, and a wait that only a later write of the same device can satisfy may hold
+ * that write back for ever. */
 int rt_peer_signal(rt_scene* s, void* flag, uint32_t value);
 int rt_peer_wait(rt_scene* s, const void* flag, uint32_t value);
 int rt_scene_push_rows(rt_scene* s, const void* band, void* frame, int32_t W, int32_t bytes_per_pixel, int32_t row_begin, int32_t row_step, int32_t rows);

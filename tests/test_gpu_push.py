@@ -39,3 +39,34 @@ def test_pushed_bands_reassemble_the_frame(built, group):
     assert np.array_equal(out.cpu().numpy(), whole)
     api.peer_free(0, frame_ptr)
     sc.close()
+
+
+def test_completion_flags_on_one_device(built):
+    """rt_peer_signal / rt_peer_wait (stream-ordered 32-bit write / wait-until->= on the scene's stream): a flag written behind a pushed
+    band is visible after the sync, and waits for values already reached do not block. (A wait that only a LATER write of the same device
+    can satisfy is not tested: streams of one device may share a hardware queue, where the waiting operation would hold the write back —
+    the flags are for writes that arrive from other devices, tests/mp_comm_worker.py.)"""
+    if rt.device_count() < 1:
+        pytest.fail("no CUDA device: the gpu tests must run on the B200 box (there is no CPU fallback)")
+    a = rt.Scene(0)
+    block, _ = api.peer_alloc(0, 4096)
+    try:
+        zero = torch.zeros(4, dtype=torch.int32, device="cuda")
+        a.push_rows(zero.data_ptr(), block, 4, 4, 0, 1, 1)
+        a.sync()
+        try:
+            a.peer_signal(block, 5)
+        except api.RtError as e:
+            pytest.skip("no stream memory operations on this driver: %s" % e)
+        a.peer_wait(block, 5)
+        a.peer_wait(block, 3)  # already reached
+        a.peer_signal(block + 4, 7)
+        a.peer_wait(block + 4, 7)
+        a.sync()
+        out = torch.empty(4, dtype=torch.int32, device="cuda")
+        a.push_rows(block, out.data_ptr(), 4, 4, 0, 1, 1)
+        a.sync()
+        assert out.cpu().tolist() == [5, 7, 0, 0]
+    finally:
+        api.peer_free(0, block)
+        a.close()
