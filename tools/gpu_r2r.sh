@@ -1,6 +1,6 @@
 #!/bin/bash
 # 8 GPUs: comm tests (N devices in one process, two processes), bench N=8, the C-ABI launcher over 8 devices
-OUT=gpurun_out/r02r
+OUT=gpurun_out/${1:-r02z}
 mkdir -p $OUT
 nvidia-smi -L | wc -l
 echo "== comm tests"; timeout 600 python -m pytest tests/test_gpu_comm.py tests/test_gpu_push.py -m gpu -q -x 2>&1 | tail -4 | tee $OUT/pytest_comm.log
