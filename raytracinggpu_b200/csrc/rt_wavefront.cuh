@@ -1140,6 +1140,9 @@ __global__ void __launch_bounds__(WF_THREADS, WIDE ? RT_WIDE_BLOCKS : 8) wf_trav
     if (rs < 0) {
         const int rpw = total / n_warps;
         rs = rpw >= 64 ? 3 : (rpw >= 16 ? 2 : (rpw >= 4 ? 1 : 0));
+        /* a mesh of millions of leaves under long queues: no region of the image concentrates the expensive rays, longer runs only add
+         * coherence (10 M triangles at 4K: 12.79 -> 12.47 ms; on the cat runs of 16 pile the head's rays up in few warps: 0.374 -> 0.476 ms) */
+        if (rpw >= 512 && h.n_leaves > (1 << 20)) rs = 4;
     }
     const int n_runs = (total + (1 << rs) - 1) >> rs; /* runs of 2^rs consecutive queue entries */
     const int n_quarter = (n_runs + 3) >> 2;           /* the queue is consumed as four interleaved quarters */
